@@ -1,0 +1,248 @@
+#!/usr/bin/env python
+"""Benchmark of the column radiative-transfer hot path (contract: see the task statement / DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one full evaluation of the workload's columns (all kernels of the path).  Default workload at
+N=1: BASELINE.json configs[1], "RRTMGLongwave clear-sky, 128x64 columns x 60 levels, fp64".
+`value` = columns/s with inputs resident in HBM (CUDA events, max over ranks); `e2e` = the same through the
+host-pointer C-ABI call (H2D of every input + D2H of every output inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+NCOL, NLAY = 128 * 64, 60
+WORKLOAD = "RRTMGLongwave clear-sky, 128x64 columns x 60 levels, fp64 (BASELINE.json configs[1])"
+# RRTMG-LW reference ABI, every array the wrapper reads/writes, L=60
+ALG_BYTES_PER_COL = (49 * NLAY + 2 * (NLAY + 1) + 17 + 4 * (NLAY + 1) + 2 * NLAY) * 8
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.stop, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def oracle_columns_per_s(st, threads, min_seconds=10.0, max_cols=None):
+    """Time the CPU restatement (the reference's algorithm, column-serial like the Fortran) on a bounded sample."""
+    import helpers as H
+    from concurrent.futures import ThreadPoolExecutor
+    orc = H.lw_oracle(cloud_overlap=1)
+    ncol = st["play"].shape[1]
+    n = min(ncol, max_cols or ncol)
+
+    def take(lo, hi):
+        return {k: np.ascontiguousarray(v[..., lo:hi] if k != "taucld" else v[:, lo:hi, :]) for k, v in st.items()}
+    blocks = [take(i * n // threads, (i + 1) * n // threads) for i in range(threads)]
+    H.run_lw_oracle(orc, blocks[0])     # warm
+    reps, t0 = 0, time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        while True:
+            list(ex.map(lambda b: H.run_lw_oracle(orc, b), blocks))
+            reps += 1
+            dt = time.perf_counter() - t0
+            if dt >= min_seconds:
+                break
+    return reps * n / dt, f"{n} of the workload's {ncol} columns x {reps} repetitions in {dt:.1f} s"
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The Fortran cannot be compiled in
+    this image (no Fortran compiler), so this is the C++ restatement (oracle/), on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from climt_b200 import synthetic as SY
+    st = SY.make_lw_state(NCOL, NLAY, seed=20260925)
+    threads = os.cpu_count() or 1
+    vals = []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        v, sample = oracle_columns_per_s(st, threads, min_seconds=0.0, max_cols=min(NCOL, 2048))
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    print(json.dumps({
+        "impl": "reference", "metric": "RRTMG-LW columns/s (60 lev)", "value": value, "unit": "columns/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * 2048 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "columns_per_step": 2048, "levels": NLAY},
+        "cpu_baseline": {"value": value, "unit": "columns/s", "cores": threads, "kind": "port",
+                         "sample": f"2048 of {NCOL} columns per step, {args.steps} steps, C++ restatement of the "
+                                   "reference Fortran (gfortran absent), columns block-partitioned over threads"},
+        "e2e": {"value": value, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from climt_b200 import synthetic as SY
+    from climt_b200.engine import LWEngine, LW_IN, LW_OUT, lw_shapes
+    import helpers as H
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    # weak scaling: every rank owns NCOL columns of the global (world*NCOL)-column grid; no data-path
+    # collective -- one all-gather reassembles the global flux / heating fields at the end of each step
+    st = SY.make_lw_state(NCOL, NLAY, seed=20260925 + rank)
+    abi = H.to_abi(st)
+    eng = LWEngine(device=local)
+    ins, outs = lw_shapes(NCOL, NLAY)
+    d_in = {k: torch.from_numpy(abi[k]).cuda() for k in LW_IN}
+    d_out = {k: torch.empty(outs[k], dtype=torch.float64, device="cuda") for k in LW_OUT}
+    gathered = None
+    if world > 1:
+        packed = torch.empty((4 * (NLAY + 1) + 2 * NLAY, NCOL), dtype=torch.float64, device="cuda")
+        gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.float64, device="cuda")
+
+    def step_device():
+        eng.run_device(NCOL, NLAY, d_in, d_out)
+        if world > 1:
+            torch.cat([d_out[k] for k in LW_OUT], dim=0, out=packed)
+            dist.all_gather_into_tensor(gathered, packed)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(W):
+        step_device()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    eng.check()
+    launches = eng.last_launches * K
+    # dominant kernel (g-point units) timed alone with CUDA events on its launch stream
+    eng.enable_timing(True)
+    unit_ms = []
+    for _ in range(max(3, min(K, 10))):
+        eng.run_device(NCOL, NLAY, d_in, d_out)
+        torch.cuda.synchronize()
+        unit_ms.append(eng.last_unit_kernel_ms)
+    eng.enable_timing(False)
+    unit_ms = float(np.mean(unit_ms))
+
+    # e2e: host buffers in pinned memory through the host-pointer C ABI (H2D + kernels + D2H per step)
+    pin_in = {k: torch.from_numpy(abi[k]).pin_memory() for k in LW_IN}
+    pin_out = {k: torch.empty(outs[k], dtype=torch.float64).pin_memory() for k in LW_OUT}
+    np_in = {k: v.numpy() for k, v in pin_in.items()}
+    np_out = {k: v.numpy() for k, v in pin_out.items()}
+    for _ in range(W):
+        eng.run_host(NCOL, NLAY, np_in, np_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        eng.run_host(NCOL, NLAY, np_in, np_out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(v.numel() * 8 for v in pin_in.values())
+    d2h = sum(v.numel() * 8 for v in pin_out.values())
+
+    t = torch.tensor([ms, e2e_s * 1e3, unit_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, unit_ms = [float(x) for x in t.tolist()]
+    if rank == 0:
+        sampler.stop.set()
+        sampler.join(timeout=2)
+        peaks, which = measured_peaks()
+        value = world * NCOL * K / (ms * 1e-3)
+        achieved = ALG_BYTES_PER_COL * NCOL / (unit_ms * 1e-3) / 1e9
+        line = {
+            "metric": "RRTMG-LW columns/s (60 lev)", "value": value, "unit": "columns/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "columns_per_gpu": NCOL, "levels": NLAY, "gpoints": 140,
+                       "cache": "working set per step (inputs 0.23 GB + per-g scratch 2.2 GB) exceeds the 126 MB L2",
+                       "parallelism": f"columns block-sharded over {world} GPU(s), one all-gather of outputs"},
+            "e2e": {"value": world * NCOL * K / (e2e_ms * 1e-3), "unit": "columns/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
+                         "kernel": "k_units", "kernel_ms": unit_ms, "alg_bytes_per_column": ALG_BYTES_PER_COL,
+                         "note": "fp64-issue / gather-latency bound, not HBM bound (SURVEY.md 8d)"},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, sample = oracle_columns_per_s(st, 1, min_seconds=10.0, max_cols=1024)
+            line["cpu_baseline"] = {"value": v, "unit": "columns/s", "cores": 1, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

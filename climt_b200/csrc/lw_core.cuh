@@ -1,0 +1,994 @@
+// climt_b200 -- RRTMG longwave engine, per-thread core (sm_100a device code; also host-compilable
+// so tests can single-step the very same code on the CPU without a GPU).
+//
+// Work decomposition (B200-first, not the reference's column-serial loop nest):
+//   prep_column   one thread per column     inatm + setcoef + cldprop   -> per-layer coefficients in HBM workspace
+//   lw_unit<B,U>  one thread per (column, unit); a unit = U (<=4) consecutive g-points of band B.
+//                 Lanes of a warp are 32 ADJACENT COLUMNS working on the SAME g-points, so all band-specific
+//                 code is warp-uniform, every state/workspace access is a coalesced 256-byte row, and table
+//                 gathers hit the same few L1 lines (neighbouring columns share jp/jt).  The vertical
+//                 recurrence runs in registers; the per-g transmittance/source pairs needed by the upward
+//                 sweep go through a (column-fastest) scratch row that is written once and read once.
+//   lw_reduce     one thread per (column, level): fixed-order sum of the per-unit partial fluxes (deterministic,
+//                 no atomics), band weights, W m-2; then heating rates.
+//
+// Reference being replaced (cited per function): climt/_lib/rrtmg_lw/rrtmg_lw_rad.nomcica.f90 (inatm, driver),
+// rrtmg_lw_setcoef.f90, rrtmg_lw_cldprop.f90, rrtmg_lw_taumol.f90, rrtmg_lw_rtrn.f90.
+// The 16 hand-specialised taugbNN routines are expressed here as ONE generic evaluator driven by a
+// compile-time band description (struct Region) -- see region<B,LOWER>().
+#pragma once
+#include <cmath>
+
+#include "cb_common.h"
+
+namespace cb {
+namespace lw {
+
+constexpr int NBND = 16, NGPT = 140, NTBL = 10000;
+constexpr int MAXU = 4;
+// workspace fields per (layer, column)
+enum WsField {
+  F_FAC00 = 0, F_FAC01, F_FAC10, F_FAC11,
+  F_COLH2O, F_COLCO2, F_COLO3, F_COLN2O, F_COLCO, F_COLCH4, F_COLO2,
+  F_COLBRD, F_COLDRY, F_WX1, F_WX2, F_WX3, F_WX4,
+  F_SELFFAC, F_SELFFRAC, F_FORFAC, F_FORFRAC, F_MINORFRAC, F_SCALEMINOR, F_SCALEMINORN2,
+  NF
+};
+
+struct BandOff {
+  int absa, absb, selfref, forref, fracrefa, fracrefb;
+  int m[5];  // minor-gas tables (slot meaning per band: see kMinorNames in lw_engine.cu)
+  int x[2];  // cross-section vectors
+  double refrat_planck_a, refrat_planck_b, refrat_m_a, refrat_m_b, refrat_m_a3;
+};
+
+struct Tables {
+  const double* base;  // one HBM buffer holding every table, offsets below are in doubles
+  BandOff b[NBND];
+  int chi_mls, preflog, tref, rat, totplnk, totplnkderiv, delwave;
+  int tau_tbl, exp_tbl, tfn_tbl;
+  int absice0, absice1, absice2, absice3, absliq1;
+  double abscld1, absliq0;
+  double bpade, heatfac, fluxfac, oneminus, avogad, grav;
+};
+
+struct In {  // reference ABI layout: (nlay[+1], ncol) column-fastest; emis (16,ncol); taucld (nlay,ncol,16); tauaer (16,nlay,ncol)
+  int ncol, nlay;
+  const double *play, *plev, *tlay, *tlev, *tsfc, *h2o, *o3, *co2, *ch4, *n2o, *o2, *cfc11, *cfc12, *cfc22, *ccl4,
+      *emis, *cldfr, *taucld, *cicewp, *cliqwp, *reice, *reliq, *tauaer;
+};
+struct Out {
+  double *uflx, *dflx, *hr, *uflxc, *dflxc, *hrc;
+};
+struct Flags {
+  int icld, idrv, inflag, iceflag, liqflag;
+};
+struct Work {  // all sized for a chunk of ncc columns
+  int ncc;
+  double* ws;    // [NF][nlay][ncc]
+  int* idx;      // [nlay][ncc]  packed jp|jt|jt1|indself|indfor|indminor
+  int* laytrop;  // [ncc]
+  int* ncbands;  // [ncc]   0 = column has no cloudy layer
+  double* pwvcm; // [ncc]
+  double* cld;   // [2][16][nlay][ncc]  odcld, efclfrac
+  double* scr;   // [140][4][nlay][ncc] atrans, bbugas, atot, bbutot
+  double* part;  // [nunits][4][nlay+1][ncc] up, dn, upclr, dnclr  (un-weighted sums over the unit's g-points)
+  int* err;      // [1]
+};
+
+CB_HD int pack_idx(int jp, int jt, int jt1, int inds, int indf, int indm) {
+  return jp | (jt << 6) | (jt1 << 9) | (inds << 12) | (indf << 16) | (indm << 18);
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep_column: inatm (rrtmg_lw_rad.nomcica.f90:572-900) + setcoef (rrtmg_lw_setcoef.f90:257-412) +
+// cldprop (rrtmg_lw_cldprop.f90:31-276) + the cloud prologue of rtrn (rrtmg_lw_rtrn.f90:260-318).
+CB_HD void secdiff_all(double pwvcm, double* secdiff /*[16]*/) {
+  const double a0[16] = {1.66, 1.55, 1.58, 1.66, 1.54, 1.454, 1.89, 1.33, 1.668, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66};
+  const double a1[16] = {0.00, 0.25, 0.22, 0.00, 0.13, 0.446, -0.10, 0.40, -0.006, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
+  const double a2[16] = {0.00, -12.0, -11.7, 0.00, -0.72, -0.243, 0.19, -0.062, 0.414, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
+  for (int ib = 0; ib < 16; ++ib) {
+    if (ib == 0 || ib == 3 || ib >= 9) {
+      secdiff[ib] = 1.66;
+    } else {
+      double s = a0[ib] + a1[ib] * exp(a2[ib] * pwvcm);
+      if (s > 1.80) s = 1.80;
+      if (s < 1.50) s = 1.50;
+      secdiff[ib] = s;
+    }
+  }
+}
+CB_HD double secdiff_band(double pwvcm, int ib /*0-based*/) {
+  const double a0[16] = {1.66, 1.55, 1.58, 1.66, 1.54, 1.454, 1.89, 1.33, 1.668, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66};
+  const double a1[16] = {0.00, 0.25, 0.22, 0.00, 0.13, 0.446, -0.10, 0.40, -0.006, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
+  const double a2[16] = {0.00, -12.0, -11.7, 0.00, -0.72, -0.243, 0.19, -0.062, 0.414, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
+  if (ib == 0 || ib == 3 || ib >= 9) return 1.66;
+  double s = a0[ib] + a1[ib] * exp(a2[ib] * pwvcm);
+  if (s > 1.80) s = 1.80;
+  if (s < 1.50) s = 1.50;
+  return s;
+}
+
+CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Work& W, int c0, int c) {
+  const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
+  const size_t gc = (size_t)(c0 + c);
+  const double* tb = T.base;
+  const double amd = 28.9660, amw = 18.0160;
+  const double stpfac = 296. / 1013.;
+  const bool clouds = fl.icld >= 1;
+  double amttl = 0.0, wvttl = 0.0;
+  int laytrop = 0;
+  int ncbands = 1;
+  bool anycld = false;
+  // cldprop state that persists across layers exactly as in the Fortran (abscoice/abscoliq/iceind/liqind are
+  // routine-local and keep their last value)
+  double abscoice[16], abscoliq[16];
+  for (int i = 0; i < 16; ++i) { abscoice[i] = 0.; abscoliq[i] = 0.; }
+  int iceind = 0, liqind = 0;
+  double pz_below = in.plev[gc];  // pz(0)
+#define WS(f, l) W.ws[((size_t)(f) * nlay + (l)) * ncc + c]
+  for (int l = 0; l < nlay; ++l) {
+    const size_t o = (size_t)l * ncol + gc;
+    const double pavel = in.play[o], tavel = in.tlay[o];
+    const double pz = in.plev[o + ncol];
+    double wkl[7];
+    wkl[0] = in.h2o[o]; wkl[1] = in.co2[o]; wkl[2] = in.o3[o]; wkl[3] = in.n2o[o];
+    wkl[4] = 0.0; wkl[5] = in.ch4[o]; wkl[6] = in.o2[o];
+    const double amm = (1. - wkl[0]) * amd + wkl[0] * amw;
+    const double coldry = (pz_below - pz) * 1.e3 * T.avogad / (1.e2 * T.grav * amm * (1. + wkl[0]));
+    pz_below = pz;
+    double summol = 0.0;
+    for (int i = 1; i < 7; ++i) summol = summol + wkl[i];
+    const double wbrodl = coldry * (1. - summol);
+    for (int i = 0; i < 7; ++i) wkl[i] = coldry * wkl[i];
+    amttl = amttl + coldry + wkl[0];
+    wvttl = wvttl + wkl[0];
+    WS(F_WX1, l) = coldry * in.ccl4[o] * 1.e-20;
+    WS(F_WX2, l) = coldry * in.cfc11[o] * 1.e-20;
+    WS(F_WX3, l) = coldry * in.cfc12[o] * 1.e-20;
+    WS(F_WX4, l) = coldry * in.cfc22[o] * 1.e-20;
+    // ---- setcoef, rrtmg_lw_setcoef.f90:257-412
+    const double plog = log(pavel);
+    int jp = (int)(36. - 5 * (plog + 0.04));
+    if (jp < 1) jp = 1; else if (jp > 58) jp = 58;
+    const double fp = 5. * (tb[T.preflog + jp - 1] - plog);
+    const double tr0 = tb[T.tref + jp - 1], tr1 = tb[T.tref + jp];
+    int jt = (int)(3. + (tavel - tr0) / 15.);
+    if (jt < 1) jt = 1; else if (jt > 4) jt = 4;
+    const double ft = ((tavel - tr0) / 15.) - (double)(jt - 3);
+    int jt1 = (int)(3. + (tavel - tr1) / 15.);
+    if (jt1 < 1) jt1 = 1; else if (jt1 > 4) jt1 = 4;
+    const double ft1 = ((tavel - tr1) / 15.) - (double)(jt1 - 3);
+    const double water = wkl[0] / coldry;
+    const double scalefac = pavel * stpfac / tavel;
+    double forfac = scalefac / (1. + water), forfrac, selffac = water * forfac, selffrac = 0.;
+    int indfor, indself = 1;
+    double factor;
+    if (!(plog <= 4.56)) {
+      laytrop = laytrop + 1;
+      factor = (332.0 - tavel) / 36.0;
+      indfor = imin(2, imax(1, (int)factor));
+      forfrac = factor - (double)indfor;
+      factor = (tavel - 188.0) / 7.2;
+      indself = imin(9, imax(1, (int)factor - 7));
+      selffrac = factor - (double)(indself + 7);
+    } else {
+      factor = (tavel - 188.0) / 36.0;
+      indfor = 3;
+      forfrac = factor - 1.0;
+    }
+    const double scaleminor = pavel / tavel;
+    const double scaleminorn2 = (pavel / tavel) * (wbrodl / (coldry + wkl[0]));
+    factor = (tavel - 180.8) / 7.2;
+    const int indminor = imin(18, imax(1, (int)factor));
+    const double minorfrac = factor - (double)indminor;
+    double colg[7];
+    for (int i = 0; i < 7; ++i) colg[i] = 1.e-20 * wkl[i];
+    if (colg[1] == 0.) colg[1] = 1.e-32 * coldry;
+    if (colg[2] == 0.) colg[2] = 1.e-32 * coldry;
+    if (colg[3] == 0.) colg[3] = 1.e-32 * coldry;
+    if (colg[4] == 0.) colg[4] = 1.e-32 * coldry;
+    if (colg[5] == 0.) colg[5] = 1.e-32 * coldry;
+    const double compfp = 1. - fp;
+    WS(F_FAC10, l) = compfp * ft;
+    WS(F_FAC00, l) = compfp * (1. - ft);
+    WS(F_FAC11, l) = fp * ft1;
+    WS(F_FAC01, l) = fp * (1. - ft1);
+    for (int i = 0; i < 7; ++i) WS(F_COLH2O + i, l) = colg[i];
+    WS(F_COLBRD, l) = 1.e-20 * wbrodl;
+    WS(F_COLDRY, l) = coldry;
+    WS(F_SELFFAC, l) = colg[0] * selffac;
+    WS(F_SELFFRAC, l) = selffrac;
+    WS(F_FORFAC, l) = colg[0] * forfac;
+    WS(F_FORFRAC, l) = forfrac;
+    WS(F_MINORFRAC, l) = minorfrac;
+    WS(F_SCALEMINOR, l) = scaleminor;
+    WS(F_SCALEMINORN2, l) = scaleminorn2;
+    W.idx[(size_t)l * ncc + c] = pack_idx(jp, jt, jt1, indself, indfor, indminor);
+    // ---- cldprop for this layer, rrtmg_lw_cldprop.f90:163-270 (taucloud parked in W.cld slot 0)
+    if (clouds) {
+      double taucloud[16];
+      for (int ib = 0; ib < 16; ++ib) taucloud[ib] = 0.0;
+      const double cldfrac = in.cldfr[o];
+      const double ciwp = in.cicewp[o], clwp = in.cliqwp[o];
+      double tauctot = 0.0;
+      const double* tc = in.taucld + 16 * ((size_t)l * ncol + gc);
+      for (int ib = 0; ib < 16; ++ib) tauctot = tauctot + tc[ib];
+      const double cwp = ciwp + clwp;
+      const double cldmin = 1.e-20;
+      if (cldfrac >= cldmin && (cwp >= cldmin || tauctot >= cldmin)) {
+        if (fl.inflag == 0) {
+          ncbands = 16;
+          for (int ib = 0; ib < 16; ++ib) taucloud[ib] = tc[ib];
+        } else if (fl.inflag == 1) {
+          ncbands = 16;
+          for (int ib = 0; ib < 16; ++ib) taucloud[ib] = T.abscld1 * cwp;
+        } else if (fl.inflag == 2) {
+          const double radice = in.reice[o];
+          if (ciwp == 0.0) {
+            abscoice[0] = 0.0;
+            iceind = 0;
+          } else if (fl.iceflag == 0) {
+            if (radice < 10.0) *W.err = 1;
+            abscoice[0] = tb[T.absice0] + tb[T.absice0 + 1] / radice;
+            iceind = 0;
+          } else if (fl.iceflag == 1) {
+            if (radice < 13.0 || radice > 130.) *W.err = 2;
+            ncbands = 5;
+            for (int ib = 0; ib < 5; ++ib) abscoice[ib] = tb[T.absice1 + 2 * ib] + tb[T.absice1 + 2 * ib + 1] / radice;
+            iceind = 1;
+          } else if (fl.iceflag == 2) {
+            if (radice < 5.0 || radice > 131.0) { *W.err = 2; }
+            else {
+              ncbands = 16;
+              factor = (radice - 2.) / 3.;
+              int index = (int)factor;
+              if (index == 43) index = 42;
+              const double fint = factor - (double)index;
+              for (int ib = 0; ib < 16; ++ib) {
+                const double k0 = tb[T.absice2 + (index - 1) * 16 + ib], k1 = tb[T.absice2 + index * 16 + ib];
+                abscoice[ib] = k0 + fint * (k1 - (k0));
+              }
+              iceind = 2;
+            }
+          } else if (fl.iceflag == 3) {
+            if (radice < 5.0 || radice > 140.0) { *W.err = 3; }
+            else {
+              ncbands = 16;
+              factor = (radice - 2.) / 3.;
+              int index = (int)factor;
+              if (index == 46) index = 45;
+              const double fint = factor - (double)index;
+              for (int ib = 0; ib < 16; ++ib) {
+                const double k0 = tb[T.absice3 + (index - 1) * 16 + ib], k1 = tb[T.absice3 + index * 16 + ib];
+                abscoice[ib] = k0 + fint * (k1 - (k0));
+              }
+              iceind = 2;
+            }
+          }
+          if (clwp == 0.0) {
+            abscoliq[0] = 0.0;
+            liqind = 0;
+            if (iceind == 1) iceind = 2;
+          } else if (fl.liqflag == 0) {
+            abscoliq[0] = T.absliq0;
+            liqind = 0;
+            if (iceind == 1) iceind = 2;
+          } else if (fl.liqflag == 1) {
+            const double radliq = in.reliq[o];
+            if (radliq < 2.5 || radliq > 60.) { *W.err = 4; }
+            else {
+              int index = (int)(radliq - 1.5);
+              if (index == 0) index = 1;
+              if (index == 58) index = 57;
+              const double fint = radliq - 1.5 - (double)index;
+              ncbands = 16;
+              for (int ib = 0; ib < 16; ++ib) {
+                const double k0 = tb[T.absliq1 + (index - 1) * 16 + ib], k1 = tb[T.absliq1 + index * 16 + ib];
+                abscoliq[ib] = k0 + fint * (k1 - (k0));
+              }
+              liqind = 2;
+            }
+          }
+          for (int ib = 0; ib < ncbands; ++ib) {
+            // icb(ib, ind): ind 0 -> 1 ; ind 1 -> {1,2,3,3,3,4,4,4,5,...}; ind 2 -> ib
+            const int pat5[16] = {0, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4};
+            const int ii = iceind == 0 ? 0 : (iceind == 1 ? pat5[ib] : ib);
+            const int il = liqind == 0 ? 0 : (liqind == 1 ? pat5[ib] : ib);
+            taucloud[ib] = ciwp * abscoice[ii] + clwp * abscoliq[il];
+          }
+        }
+      }
+      if (cldfrac >= 1.e-6) anycld = true;
+      for (int ib = 0; ib < 16; ++ib) W.cld[((size_t)ib * nlay + l) * ncc + c] = taucloud[ib];
+    }
+  }
+#undef WS
+  const double wvsh = (amw * wvttl) / (amd * amttl);
+  const double pwvcm = wvsh * (1.e3 * in.plev[gc]) / (1.e2 * T.grav);
+  W.pwvcm[c] = pwvcm;
+  W.laytrop[c] = laytrop;
+  W.ncbands[c] = (clouds && anycld) ? ncbands : 0;
+  if (clouds && anycld) {
+    // rtrn prologue, rrtmg_lw_rtrn.f90:300-316 (note: secdiff is indexed by the CLOUD band index there)
+    double secdiff[16];
+    secdiff_all(pwvcm, secdiff);
+    for (int l = 0; l < nlay; ++l) {
+      const double cldfrac = in.cldfr[(size_t)l * ncol + gc];
+      for (int ib = 0; ib < 16; ++ib) {
+        const size_t o0 = ((size_t)ib * nlay + l) * ncc + c;
+        const size_t o1 = ((size_t)(16 + ib) * nlay + l) * ncc + c;
+        if (ib < ncbands && cldfrac >= 1.e-6) {
+          const double od = secdiff[ib] * W.cld[o0];
+          const double transcld = exp(-od);
+          const double abscld = 1. - transcld;
+          W.cld[o0] = od;
+          W.cld[o1] = abscld * cldfrac;
+        } else {
+          W.cld[o0] = 0.0;
+          W.cld[o1] = 0.0;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Band descriptions.  Gas ids index WsField F_COLH2O + id.
+enum Gas { H2O = 0, CO2 = 1, O3 = 2, N2O = 3, CO = 4, CH4 = 5, O2 = 6 };
+enum RatId { R_H2OCO2 = 0, R_H2OO3 = 1, R_H2ON2O = 2, R_H2OCH4 = 3, R_N2OCO2 = 4, R_O3CO2 = 5 };
+enum AmtKind { A_COL, A_ADJ, A_BRD_N2, A_BRD, A_O2SC };
+enum RefR { RM_A, RM_B, RM_A3 };
+
+struct Minor {
+  int slot;     // BandOff::m[slot]
+  bool binary;  // table is (nsp, 19, ng) and interpolated in the key-species ratio too
+  int refr;     // which refrat_m_* drives the binary interpolation
+  int amt;      // AmtKind
+  int gas;      // for A_COL / A_ADJ
+  double thr, base, expo;  // A_ADJ: if ratio > thr: adj = base + (ratio-base)**expo
+  bool ref355;  // band 13: reference mixing ratio is the literal 3.55e-4 instead of chi_mls(gas, jp+1)
+  bool e20f;    // `1.e20` written as a default-real literal in the Fortran
+};
+struct Region {
+  int kind;  // 0: no key species, 1: one key species, 2: two key species
+  int a, b, rat;
+  bool self, forn;
+  int nminor;
+  Minor m[3];
+  int nx;
+  int xslot[2], xwx[2];
+  int corr;    // 0 none, 1: band-1 lower, 2: band-1 upper, 3: band-2 lower
+  int planck;  // 0: fixed fracref, 1: interpolated in the key-species ratio, 2: zero
+  int scale;   // 0 none, 1: band-4 upper, 2: band-7 upper
+};
+
+constexpr Minor kNoMinor = {0, false, RM_A, A_COL, H2O, 0., 0., 0., false, false};
+constexpr Minor minor_col(int slot, bool bin, int refr, int gas) { return {slot, bin, refr, A_COL, gas, 0., 0., 0., false, false}; }
+constexpr Minor minor_adj(int slot, bool bin, int refr, int gas, double thr, double base, double expo, bool e20f = false,
+                          bool ref355 = false) {
+  return {slot, bin, refr, A_ADJ, gas, thr, base, expo, ref355, e20f};
+}
+constexpr Minor minor_amt(int slot, bool bin, int refr, int amt) { return {slot, bin, refr, amt, H2O, 0., 0., 0., false, false}; }
+constexpr Region R0(int planck) { return {0, 0, 0, 0, false, false, 0, {kNoMinor, kNoMinor, kNoMinor}, 0, {0, 0}, {0, 0}, 0, planck, 0}; }
+
+// rrtmg_lw_taumol.f90: taugb1 :280-376, taugb2 :379-476, taugb3 :479-763, taugb4 :766-1018, taugb5 :1021-1300,
+// taugb6 :1303-1391, taugb7 :1394-1653, taugb8 :1656-1791, taugb9 :1794-2040, taugb10 :2043-2110,
+// taugb11 :2113-2195, taugb12 :2198-2395, taugb13 :2398-2650, taugb14 :2653-2718, taugb15 :2721-2936,
+// taugb16 :2939-3145.
+template <int B, bool LOWER>
+constexpr Region region() {
+  Region r = R0(0);
+  if (B == 1) {
+    r.kind = 1; r.a = H2O; r.self = LOWER; r.forn = true;
+    r.nminor = 1; r.m[0] = minor_amt(LOWER ? 0 : 1, false, RM_A, A_BRD_N2);
+    r.corr = LOWER ? 1 : 2;
+  } else if (B == 2) {
+    r.kind = 1; r.a = H2O; r.self = LOWER; r.forn = true; r.corr = LOWER ? 3 : 0;
+  } else if (B == 3) {
+    r.kind = 2; r.a = H2O; r.b = CO2; r.rat = R_H2OCO2; r.self = LOWER; r.forn = true;
+    r.nminor = 1; r.m[0] = minor_adj(LOWER ? 0 : 1, true, LOWER ? RM_A : RM_B, N2O, 1.5, 0.5, 0.65, !LOWER);
+    r.planck = 1;
+  } else if (B == 4) {
+    r.kind = 2; r.a = LOWER ? H2O : O3; r.b = CO2; r.rat = LOWER ? R_H2OCO2 : R_O3CO2; r.self = LOWER; r.forn = LOWER;
+    r.planck = 1; r.scale = LOWER ? 0 : 1;
+  } else if (B == 5) {
+    r.kind = 2; r.a = LOWER ? H2O : O3; r.b = CO2; r.rat = LOWER ? R_H2OCO2 : R_O3CO2; r.self = LOWER; r.forn = LOWER;
+    if (LOWER) { r.nminor = 1; r.m[0] = minor_col(0, true, RM_A, O3); }
+    r.nx = 1; r.xslot[0] = 0; r.xwx[0] = 0;
+    r.planck = 1;
+  } else if (B == 6) {
+    if (LOWER) {
+      r.kind = 1; r.a = H2O; r.self = true; r.forn = true;
+      r.nminor = 1; r.m[0] = minor_adj(0, false, RM_A, CO2, 3.0, 2.0, 0.77);
+    }
+    r.nx = 2; r.xslot[0] = 0; r.xwx[0] = 1; r.xslot[1] = 1; r.xwx[1] = 2;
+  } else if (B == 7) {
+    if (LOWER) {
+      r.kind = 2; r.a = H2O; r.b = O3; r.rat = R_H2OO3; r.self = true; r.forn = true;
+      r.nminor = 1; r.m[0] = minor_adj(0, true, RM_A, CO2, 3.0, 3.0, 0.79, true);
+      r.planck = 1;
+    } else {
+      r.kind = 1; r.a = O3;
+      r.nminor = 1; r.m[0] = minor_adj(1, false, RM_A, CO2, 3.0, 2.0, 0.79, true);
+      r.scale = 2;
+    }
+  } else if (B == 8) {
+    r.kind = 1; r.a = LOWER ? H2O : O3; r.self = LOWER; r.forn = LOWER;
+    if (LOWER) {
+      r.nminor = 3;
+      r.m[0] = minor_adj(0, false, RM_A, CO2, 3.0, 2.0, 0.65);
+      r.m[1] = minor_col(1, false, RM_A, O3);
+      r.m[2] = minor_col(2, false, RM_A, N2O);
+    } else {
+      r.nminor = 2;
+      r.m[0] = minor_adj(3, false, RM_A, CO2, 3.0, 2.0, 0.65);
+      r.m[1] = minor_col(4, false, RM_A, N2O);
+    }
+    r.nx = 2; r.xslot[0] = 0; r.xwx[0] = 2; r.xslot[1] = 1; r.xwx[1] = 3;
+  } else if (B == 9) {
+    if (LOWER) {
+      r.kind = 2; r.a = H2O; r.b = CH4; r.rat = R_H2OCH4; r.self = true; r.forn = true;
+      r.nminor = 1; r.m[0] = minor_adj(0, true, RM_A, N2O, 1.5, 0.5, 0.65);
+      r.planck = 1;
+    } else {
+      r.kind = 1; r.a = CH4;
+      r.nminor = 1; r.m[0] = minor_adj(1, false, RM_A, N2O, 1.5, 0.5, 0.65);
+    }
+  } else if (B == 10) {
+    r.kind = 1; r.a = H2O; r.self = LOWER; r.forn = true;
+  } else if (B == 11) {
+    r.kind = 1; r.a = H2O; r.self = LOWER; r.forn = true;
+    r.nminor = 1; r.m[0] = minor_amt(LOWER ? 0 : 1, false, RM_A, A_O2SC);
+  } else if (B == 12) {
+    if (LOWER) { r.kind = 2; r.a = H2O; r.b = CO2; r.rat = R_H2OCO2; r.self = true; r.forn = true; r.planck = 1; }
+    else r.planck = 2;
+  } else if (B == 13) {
+    if (LOWER) {
+      r.kind = 2; r.a = H2O; r.b = N2O; r.rat = R_H2ON2O; r.self = true; r.forn = true;
+      r.nminor = 2;
+      r.m[0] = minor_adj(0, true, RM_A, CO2, 3.0, 2.0, 0.68, false, true);
+      r.m[1] = minor_col(1, true, RM_A3, CO);
+      r.planck = 1;
+    } else {
+      r.nminor = 1; r.m[0] = minor_col(2, false, RM_A, O3);
+    }
+  } else if (B == 14) {
+    r.kind = 1; r.a = CO2; r.self = LOWER; r.forn = LOWER;
+  } else if (B == 15) {
+    if (LOWER) {
+      r.kind = 2; r.a = N2O; r.b = CO2; r.rat = R_N2OCO2; r.self = true; r.forn = true;
+      r.nminor = 1; r.m[0] = minor_amt(0, true, RM_A, A_BRD);
+      r.planck = 1;
+    } else r.planck = 2;
+  } else if (B == 16) {
+    if (LOWER) { r.kind = 2; r.a = H2O; r.b = CH4; r.rat = R_H2OCH4; r.self = true; r.forn = true; r.planck = 1; }
+    else { r.kind = 1; r.a = CH4; }
+  }
+  return r;
+}
+
+constexpr int kNG[16] = {10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2};
+constexpr int kGS[16] = {0, 10, 22, 38, 52, 68, 76, 88, 96, 108, 114, 122, 130, 134, 136, 138};
+constexpr int kNSPA[16] = {1, 1, 9, 9, 9, 1, 9, 1, 9, 1, 1, 9, 9, 1, 9, 9};
+constexpr int kNSPB[16] = {1, 1, 5, 5, 5, 0, 1, 1, 1, 1, 1, 0, 0, 1, 0, 0};
+
+struct BinSpec {
+  double speccomb, specparm, fs;
+  int js;  // 1-based like the Fortran
+};
+CB_HD BinSpec binspec(double cola, double rat, double colb, double n, double oneminus) {
+  BinSpec s;
+  s.speccomb = cola + rat * colb;
+  s.specparm = cola / s.speccomb;
+  if (s.specparm >= oneminus) s.specparm = oneminus;
+  const double specmult = n * s.specparm;
+  s.js = 1 + (int)specmult;
+  s.fs = fmod(specmult, 1.0);
+  return s;
+}
+// weights/row offsets of the 2x(2|3)-point stencil in (species ratio) x (temperature) for one pressure level
+struct Stencil {
+  double w[6];
+  int off[6];
+  int n;
+};
+template <bool LOWER>
+CB_HD Stencil make_stencil(double specparm, double fs, double fa, double fb) {
+  constexpr int nsp = LOWER ? 9 : 5;
+  Stencil s;
+  if (LOWER && specparm < 0.125) {
+    const double p = fs - 1, p2 = p * p, p4 = p2 * p2, fk0 = p4, fk1 = 1 - p - 2.0 * p4, fk2 = p + p4;
+    s.n = 6;
+    s.w[0] = fk0 * fa; s.off[0] = 0;
+    s.w[1] = fk1 * fa; s.off[1] = 1;
+    s.w[2] = fk2 * fa; s.off[2] = 2;
+    s.w[3] = fk0 * fb; s.off[3] = nsp;
+    s.w[4] = fk1 * fb; s.off[4] = nsp + 1;
+    s.w[5] = fk2 * fb; s.off[5] = nsp + 2;
+  } else if (LOWER && specparm > 0.875) {
+    const double p = -fs, p2 = p * p, p4 = p2 * p2, fk0 = p4, fk1 = 1 - p - 2.0 * p4, fk2 = p + p4;
+    s.n = 6;
+    s.w[0] = fk2 * fa; s.off[0] = -1;
+    s.w[1] = fk1 * fa; s.off[1] = 0;
+    s.w[2] = fk0 * fa; s.off[2] = 1;
+    s.w[3] = fk2 * fb; s.off[3] = nsp - 1;
+    s.w[4] = fk1 * fb; s.off[4] = nsp;
+    s.w[5] = fk0 * fb; s.off[5] = nsp + 1;
+  } else {
+    s.n = 4;
+    s.w[0] = (1. - fs) * fa; s.off[0] = 0;
+    s.w[1] = fs * fa;        s.off[1] = 1;
+    s.w[2] = (1. - fs) * fb; s.off[2] = nsp;
+    s.w[3] = fs * fb;        s.off[3] = nsp + 1;
+    s.w[4] = 0.; s.off[4] = 0; s.w[5] = 0.; s.off[5] = 0;
+  }
+  return s;
+}
+
+// Gas optical depth and Planck fraction for U consecutive g-points [g0, g0+U) of band B in ONE layer.
+template <int B, bool LOWER, int U>
+CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstride /* = nlay*ncc */, int idx, double pavel,
+                     int g0, double* __restrict__ tau, double* __restrict__ frac) {
+  constexpr Region R = region<B, LOWER>();
+  constexpr int ng = kNG[B - 1];
+  const BandOff& O = T.b[B - 1];
+  const double* __restrict__ tb = T.base;
+#define WSF(f) CB_LDG(ws + (size_t)(f) * wstride)
+  const int jp = idx & 63, jt = (idx >> 6) & 7, jt1 = (idx >> 9) & 7;
+  const int inds = (idx >> 12) & 15, indf = (idx >> 16) & 3, indm = (idx >> 18) & 31;
+  double acc[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) acc[u] = 0.0;
+  double cola = 0., colb = 0.;
+  if (R.kind >= 1) cola = WSF(F_COLH2O + R.a);
+  if (R.kind == 2) colb = WSF(F_COLH2O + R.b);
+
+  // ---- key species
+  if (R.kind == 1) {
+    const double fac00 = WSF(F_FAC00), fac01 = WSF(F_FAC01), fac10 = WSF(F_FAC10), fac11 = WSF(F_FAC11);
+    constexpr int nsp = LOWER ? kNSPA[B - 1] : kNSPB[B - 1];
+    const int row0 = LOWER ? ((jp - 1) * 5 + (jt - 1)) * nsp : ((jp - 13) * 5 + (jt - 1)) * nsp;
+    const int row1 = LOWER ? (jp * 5 + (jt1 - 1)) * nsp : ((jp - 12) * 5 + (jt1 - 1)) * nsp;
+    const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
+    const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      acc[u] = cola * (fac00 * CB_LDG(a0 + u) + fac10 * CB_LDG(a0 + ng + u) + fac01 * CB_LDG(a1 + u) +
+                       fac11 * CB_LDG(a1 + ng + u));
+  } else if (R.kind == 2) {
+    const double fac00 = WSF(F_FAC00), fac01 = WSF(F_FAC01), fac10 = WSF(F_FAC10), fac11 = WSF(F_FAC11);
+    constexpr double n = LOWER ? 8. : 4.;
+    constexpr int nsp = LOWER ? 9 : 5;
+    const double rat0 = CB_LDG(tb + T.rat + R.rat * 59 + jp - 1), rat1 = CB_LDG(tb + T.rat + R.rat * 59 + jp);
+    const BinSpec s0 = binspec(cola, rat0, colb, n, T.oneminus);
+    const BinSpec s1 = binspec(cola, rat1, colb, n, T.oneminus);
+    const int row0 = (LOWER ? ((jp - 1) * 5 + (jt - 1)) * nsp : ((jp - 13) * 5 + (jt - 1)) * nsp) + s0.js - 1;
+    const int row1 = (LOWER ? (jp * 5 + (jt1 - 1)) * nsp : ((jp - 12) * 5 + (jt1 - 1)) * nsp) + s1.js - 1;
+    const Stencil t0 = make_stencil<LOWER>(s0.specparm, s0.fs, fac00, fac10);
+    const Stencil t1 = make_stencil<LOWER>(s1.specparm, s1.fs, fac01, fac11);
+    const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
+    const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double d0 = t0.w[0] * CB_LDG(a0 + t0.off[0] * ng + u);
+      d0 = d0 + t0.w[1] * CB_LDG(a0 + t0.off[1] * ng + u);
+      d0 = d0 + t0.w[2] * CB_LDG(a0 + t0.off[2] * ng + u);
+      d0 = d0 + t0.w[3] * CB_LDG(a0 + t0.off[3] * ng + u);
+      if (LOWER && t0.n == 6) {
+        d0 = d0 + t0.w[4] * CB_LDG(a0 + t0.off[4] * ng + u);
+        d0 = d0 + t0.w[5] * CB_LDG(a0 + t0.off[5] * ng + u);
+      }
+      double d1 = t1.w[0] * CB_LDG(a1 + t1.off[0] * ng + u);
+      d1 = d1 + t1.w[1] * CB_LDG(a1 + t1.off[1] * ng + u);
+      d1 = d1 + t1.w[2] * CB_LDG(a1 + t1.off[2] * ng + u);
+      d1 = d1 + t1.w[3] * CB_LDG(a1 + t1.off[3] * ng + u);
+      if (LOWER && t1.n == 6) {
+        d1 = d1 + t1.w[4] * CB_LDG(a1 + t1.off[4] * ng + u);
+        d1 = d1 + t1.w[5] * CB_LDG(a1 + t1.off[5] * ng + u);
+      }
+      acc[u] = s0.speccomb * d0 + s1.speccomb * d1;
+    }
+  }
+  // ---- water-vapour self and foreign continua
+  if (R.self) {
+    const double selffac = WSF(F_SELFFAC), selffrac = WSF(F_SELFFRAC);
+    const double* __restrict__ s = tb + O.selfref + (size_t)(inds - 1) * ng + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double k0 = CB_LDG(s + u), k1 = CB_LDG(s + ng + u);
+      acc[u] = acc[u] + selffac * (k0 + selffrac * (k1 - k0));
+    }
+  }
+  if (R.forn) {
+    const double forfac = WSF(F_FORFAC), forfrac = WSF(F_FORFRAC);
+    const double* __restrict__ s = tb + O.forref + (size_t)(indf - 1) * ng + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double k0 = CB_LDG(s + u), k1 = CB_LDG(s + ng + u);
+      acc[u] = acc[u] + forfac * (k0 + forfrac * (k1 - k0));
+    }
+  }
+  // ---- minor gases
+  if (R.nminor > 0) {
+    const double minorfrac = WSF(F_MINORFRAC);
+#pragma unroll
+    for (int k = 0; k < R.nminor; ++k) {
+      const Minor M = R.m[k];
+      double amount;
+      if (M.amt == A_COL) {
+        amount = WSF(F_COLH2O + M.gas);
+      } else if (M.amt == A_BRD_N2) {
+        amount = WSF(F_COLBRD) * WSF(F_SCALEMINORN2);
+      } else if (M.amt == A_BRD) {
+        amount = WSF(F_COLBRD) * WSF(F_SCALEMINOR);
+      } else if (M.amt == A_O2SC) {
+        amount = WSF(F_COLO2) * WSF(F_SCALEMINOR);
+      } else {  // A_ADJ: in atmospheres where the gas is too abundant to be "minor" (e.g. taumol.f90:529-535)
+        const double colx = WSF(F_COLH2O + M.gas), coldry = WSF(F_COLDRY);
+        const double chi_x = colx / coldry;
+        const double e20 = M.e20f ? (double)1.e20f : 1.e20;
+        const double ref = M.ref355 ? 3.55e-4 : CB_LDG(tb + T.chi_mls + M.gas * 59 + jp);  // chi_mls(gas, jp+1)
+        const double ratio = e20 * chi_x / ref;
+        if (ratio > M.thr) {
+          const double adjfac = M.base + pow(ratio - M.base, M.expo);
+          const double ref2 = M.ref355 ? (double)3.55e-4f : ref;
+          amount = adjfac * ref2 * coldry * 1.e-20;
+        } else {
+          amount = colx;
+        }
+      }
+      if (M.binary) {
+        constexpr double n = LOWER ? 8. : 4.;
+        constexpr int nsp = LOWER ? 9 : 5;
+        const double refr = M.refr == RM_A ? O.refrat_m_a : (M.refr == RM_B ? O.refrat_m_b : O.refrat_m_a3);
+        const BinSpec sm = binspec(cola, refr, colb, n, T.oneminus);
+        const double* __restrict__ t = tb + O.m[M.slot] + ((size_t)(sm.js - 1) + nsp * (size_t)(indm - 1)) * ng + g0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const double k00 = CB_LDG(t + u), k10 = CB_LDG(t + ng + u);
+          const double k01 = CB_LDG(t + nsp * ng + u), k11 = CB_LDG(t + (nsp + 1) * ng + u);
+          const double m1 = k00 + sm.fs * (k10 - k00);
+          const double m2 = k01 + sm.fs * (k11 - k01);
+          acc[u] = acc[u] + amount * (m1 + minorfrac * (m2 - m1));
+        }
+      } else {
+        const double* __restrict__ t = tb + O.m[M.slot] + (size_t)(indm - 1) * ng + g0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const double k0 = CB_LDG(t + u), k1 = CB_LDG(t + ng + u);
+          acc[u] = acc[u] + amount * (k0 + minorfrac * (k1 - k0));
+        }
+      }
+    }
+  }
+  // ---- halocarbon cross sections
+#pragma unroll
+  for (int k = 0; k < R.nx; ++k) {
+    const double wx = WSF(F_WX1 + R.xwx[k]);
+    const double* __restrict__ t = tb + O.x[R.xslot[k]] + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = acc[u] + wx * CB_LDG(t + u);
+  }
+  // ---- empirical corrections
+  if (R.corr != 0) {
+    double corradj;
+    if (R.corr == 1) {
+      corradj = 1.;
+      if (pavel < 250.) corradj = 1. - 0.15 * (250. - pavel) / 154.4;
+    } else if (R.corr == 2) {
+      corradj = 1. - 0.15 * (pavel / 95.6);
+    } else {
+      corradj = 1. - .05 * (pavel - 100.) / 900.;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = corradj * acc[u];
+  }
+  if (R.scale == 1) {  // taumol.f90:1009-1015, default-real literals; g-points 8..14 of band 4
+    const double sc[7] = {(double)0.92f, (double)0.88f, (double)1.07f, (double)1.1f, (double)0.99f, (double)0.88f, (double)0.943f};
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int g = g0 + u;
+      if (g >= 7) acc[u] = acc[u] * sc[g - 7];
+    }
+  } else if (R.scale == 2) {  // :1642-1650; g-points 6..11 of band 7
+    const double sc[6] = {0.92, 0.88, 1.07, 1.1, 0.99, 0.855};
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int g = g0 + u;
+      if (g >= 5 && g <= 10) acc[u] = acc[u] * sc[g - 5];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) tau[u] = acc[u];
+  // ---- Planck fractions
+  if (R.planck == 2) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) frac[u] = 0.0;
+  } else if (R.planck == 1) {
+    constexpr double n = LOWER ? 8. : 4.;
+    const BinSpec sp = binspec(cola, LOWER ? O.refrat_planck_a : O.refrat_planck_b, colb, n, T.oneminus);
+    const double* __restrict__ f = tb + (LOWER ? O.fracrefa : O.fracrefb) + (size_t)(sp.js - 1) * ng + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double f0 = CB_LDG(f + u), f1 = CB_LDG(f + ng + u);
+      frac[u] = f0 + sp.fs * (f1 - f0);
+    }
+  } else {
+    // band 6 and 12/15 have no "b" table; band 6 upper uses fracrefa (taumol.f90:1388)
+    constexpr bool use_a = LOWER || B == 6;
+    const double* __restrict__ f = tb + (use_a ? O.fracrefa : O.fracrefb) + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) frac[u] = CB_LDG(f + u);
+  }
+#undef WSF
+}
+
+// Planck function integrated over band B at temperature t: 1-K table, linear interpolation
+// (rrtmg_lw_setcoef.f90:154-253).
+CB_HD double planck_band(const double* __restrict__ tp /* totplnk row of band */, double t) {
+  int ind = f2i(t - 159.);
+  if (ind < 1) ind = 1; else if (ind > 180) ind = 180;
+  const double fr = t - 159. - (double)ind;
+  const double p0 = CB_LDG(tp + ind - 1), p1 = CB_LDG(tp + ind);
+  return p0 + fr * (p1 - p0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// lw_unit: taumol + rtrn for U g-points of band B in one column (rrtmg_lw_rtrn.f90:320-526).
+template <int B, int U>
+CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int g0, int unit) {
+  const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
+  const size_t gc = (size_t)(c0 + c);
+  const double* __restrict__ tb = T.base;
+  const double rec_6 = 0.166667, tblint = 10000.0, bpade = T.bpade;
+  const double* __restrict__ tau_tbl = tb + T.tau_tbl;
+  const double* __restrict__ exp_tbl = tb + T.exp_tbl;
+  const double* __restrict__ tfn_tbl = tb + T.tfn_tbl;
+  const double* __restrict__ tp = tb + T.totplnk + (size_t)(B - 1) * 181;
+  const size_t wstride = (size_t)nlay * ncc;
+  const int laytrop = W.laytrop[c];
+  const int ncb = W.ncbands[c];
+  const double pwvcm = W.pwvcm[c];
+  const double secdiff = secdiff_band(pwvcm, B - 1);
+  // cloud band feeding this LW band: ipat(B, 0|1|2) for ncbands = 1|5|16 (rtrn.f90:233-235,324-330)
+  int ibc = 0;
+  if (ncb == 5) {
+    const int pat5[16] = {0, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4};
+    ibc = pat5[B - 1];
+  } else if (ncb == 16) {
+    ibc = B - 1;
+  }
+  const int gabs = kGS[B - 1] + g0;  // absolute g-point of u = 0
+  double radld[U], radclrd[U], frac1[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) { radld[u] = 0.; radclrd[u] = 0.; frac1[u] = 0.; }
+  int iclddn = 0;
+  double* __restrict__ part = W.part + (size_t)unit * 4 * (nlay + 1) * ncc + c;
+  const size_t pstride = (size_t)(nlay + 1) * ncc;
+  double plev_up = planck_band(tp, in.tlev[(size_t)nlay * ncol + gc]);  // planklev(nlay)
+  for (int lev = nlay; lev >= 1; --lev) {
+    const int l = lev - 1;
+    const size_t o = (size_t)l * ncol + gc;
+    const int idx = W.idx[(size_t)l * ncc + c];
+    const double pavel = in.play[o];
+    double tau[U], frac[U];
+    const double* ws = W.ws + (size_t)l * ncc + c;
+    if (lev <= laytrop) eval_band<B, true, U>(T, ws, wstride, idx, pavel, g0, tau, frac);
+    else eval_band<B, false, U>(T, ws, wstride, idx, pavel, g0, tau, frac);
+    const double taua = in.tauaer[((size_t)(B - 1) * nlay + l) * ncol + gc];
+    const double blay = planck_band(tp, in.tlay[o]);
+    const double plev_dn = planck_band(tp, in.tlev[o]);  // planklev(lev-1)
+    const double dplankup = plev_up - blay;
+    const double dplankdn = plev_dn - blay;
+    plev_up = plev_dn;
+    const bool cloudy = ncb > 0 && in.cldfr[o] >= 1.e-6;
+    double odcld = 0., efclfrac = 0., cldfrac = 0.;
+    if (cloudy) {
+      iclddn = 1;
+      cldfrac = in.cldfr[o];
+      odcld = W.cld[((size_t)ibc * nlay + l) * ncc + c];
+      efclfrac = W.cld[((size_t)(16 + ibc) * nlay + l) * ncc + c];
+    }
+    double sum_d = 0., sum_dc = 0.;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double plfrac = frac[u];
+      double odepth = secdiff * (tau[u] + taua);
+      if (odepth < 0.0) odepth = 0.0;
+      double atrans, bbd, bbugas;
+      double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * 4) * nlay + l) * ncc + c;
+      if (cloudy) {
+        double odtot = odepth + odcld;
+        double gassrc, bbdtot, atot, bbutot;
+        if (odtot < 0.06) {
+          atrans = odepth - 0.5 * odepth * odepth;
+          const double odepth_rec = rec_6 * odepth;
+          gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
+          atot = odtot - 0.5 * odtot * odtot;
+          const double odtot_rec = rec_6 * odtot;
+          bbdtot = plfrac * (blay + dplankdn * odtot_rec);
+          bbd = plfrac * (blay + dplankdn * odepth_rec);
+          bbugas = plfrac * (blay + dplankup * odepth_rec);
+          bbutot = plfrac * (blay + dplankup * odtot_rec);
+        } else if (odepth <= 0.06) {
+          atrans = odepth - 0.5 * odepth * odepth;
+          const double odepth_rec = rec_6 * odepth;
+          gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
+          odtot = odepth + odcld;
+          const double tblind = odtot / (bpade + odtot);
+          const int ittot = f2i(tblint * tblind + 0.5);
+          const double tfactot = CB_LDG(tfn_tbl + ittot);
+          bbdtot = plfrac * (blay + tfactot * dplankdn);
+          bbd = plfrac * (blay + dplankdn * odepth_rec);
+          atot = 1. - CB_LDG(exp_tbl + ittot);
+          bbugas = plfrac * (blay + dplankup * odepth_rec);
+          bbutot = plfrac * (blay + tfactot * dplankup);
+        } else {
+          double tblind = odepth / (bpade + odepth);
+          const int itgas = f2i(tblint * tblind + 0.5);
+          odepth = CB_LDG(tau_tbl + itgas);
+          atrans = 1. - CB_LDG(exp_tbl + itgas);
+          const double tfacgas = CB_LDG(tfn_tbl + itgas);
+          gassrc = atrans * plfrac * (blay + tfacgas * dplankdn);
+          odtot = odepth + odcld;
+          tblind = odtot / (bpade + odtot);
+          const int ittot = f2i(tblint * tblind + 0.5);
+          const double tfactot = CB_LDG(tfn_tbl + ittot);
+          bbdtot = plfrac * (blay + tfactot * dplankdn);
+          bbd = plfrac * (blay + tfacgas * dplankdn);
+          atot = 1. - CB_LDG(exp_tbl + ittot);
+          bbugas = plfrac * (blay + tfacgas * dplankup);
+          bbutot = plfrac * (blay + tfactot * dplankup);
+        }
+        radld[u] = radld[u] - radld[u] * (atrans + efclfrac * (1. - atrans)) + gassrc + cldfrac * (bbdtot * atot - gassrc);
+        scr[2 * wstride] = atot;
+        scr[3 * wstride] = bbutot;
+      } else {
+        if (odepth <= 0.06) {
+          atrans = odepth - 0.5 * odepth * odepth;
+          odepth = rec_6 * odepth;
+          bbd = plfrac * (blay + dplankdn * odepth);
+          bbugas = plfrac * (blay + dplankup * odepth);
+        } else {
+          const double tblind = odepth / (bpade + odepth);
+          const int itr = f2i(tblint * tblind + 0.5);
+          const double transc = CB_LDG(exp_tbl + itr);
+          atrans = 1. - transc;
+          const double tausfac = CB_LDG(tfn_tbl + itr);
+          bbd = plfrac * (blay + tausfac * dplankdn);
+          bbugas = plfrac * (blay + tausfac * dplankup);
+        }
+        radld[u] = radld[u] + (bbd - radld[u]) * atrans;
+      }
+      scr[0] = atrans;
+      scr[wstride] = bbugas;
+      sum_d = sum_d + radld[u];
+      if (iclddn == 1) {
+        radclrd[u] = radclrd[u] + (bbd - radclrd[u]) * atrans;
+      } else {
+        radclrd[u] = radld[u];
+      }
+      sum_dc = sum_dc + radclrd[u];
+      if (lev == 1) frac1[u] = plfrac;
+    }
+    part[1 * pstride + (size_t)(lev - 1) * ncc] = sum_d;
+    part[3 * pstride + (size_t)(lev - 1) * ncc] = sum_dc;
+  }
+  // top of atmosphere: no downward flux
+  part[1 * pstride + (size_t)nlay * ncc] = 0.0;
+  part[3 * pstride + (size_t)nlay * ncc] = 0.0;
+  // surface (rtrn.f90:455-470)
+  const double tbound = in.tsfc[gc];
+  const double semiss = in.emis[(size_t)(B - 1) * ncol + gc];
+  const double plankbnd = semiss * planck_band(tp, tbound);
+  const double reflect = 1. - semiss;
+  double radlu[U], radclru[U];
+  {
+    double s = 0., sc = 0.;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double rad0 = frac1[u] * plankbnd;
+      radlu[u] = rad0 + reflect * radld[u];
+      radclru[u] = rad0 + reflect * radclrd[u];
+      s = s + radlu[u];
+      sc = sc + radclru[u];
+    }
+    part[0] = s;
+    part[2 * pstride] = sc;
+  }
+  // upward sweep (rtrn.f90:478-521)
+  for (int lev = 1; lev <= nlay; ++lev) {
+    const int l = lev - 1;
+    const size_t o = (size_t)l * ncol + gc;
+    const bool cloudy = ncb > 0 && in.cldfr[o] >= 1.e-6;
+    double efclfrac = 0., cldfrac = 0.;
+    if (cloudy) {
+      cldfrac = in.cldfr[o];
+      efclfrac = W.cld[((size_t)(16 + ibc) * nlay + l) * ncc + c];
+    }
+    double s = 0., sc = 0.;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * 4) * nlay + l) * ncc + c;
+      const double atrans = scr[0], bbugas = scr[wstride];
+      if (cloudy) {
+        const double atot = scr[2 * wstride], bbutot = scr[3 * wstride];
+        const double gassrc = bbugas * atrans;
+        radlu[u] = radlu[u] - radlu[u] * (atrans + efclfrac * (1. - atrans)) + gassrc + cldfrac * (bbutot * atot - gassrc);
+      } else {
+        radlu[u] = radlu[u] + (bbugas - radlu[u]) * atrans;
+      }
+      s = s + radlu[u];
+      if (iclddn == 1) {
+        radclru[u] = radclru[u] + (bbugas - radclru[u]) * atrans;
+      } else {
+        radclru[u] = radlu[u];
+      }
+      sc = sc + radclru[u];
+    }
+    part[(size_t)lev * ncc] = s;
+    part[2 * pstride + (size_t)lev * ncc] = sc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Units: static list shared by host and device.  Bands are split in chunks of <= 4 g-points.
+struct Unit {
+  int band, g0, u;
+};
+constexpr int kMaxUnits = 40;
+inline int build_units(Unit* out) {  // host only
+  int n = 0;
+  // heavy (two-key-species, lower-atmosphere-rich) work first so the tail of the grid is made of light blocks
+  for (int pass = 0; pass < 2; ++pass)
+    for (int b = 1; b <= 16; ++b) {
+      const bool heavy = kNSPA[b - 1] == 9;
+      if ((pass == 0) != heavy) continue;
+      const int ng = kNG[b - 1];
+      for (int g0 = 0; g0 < ng; g0 += 4) {
+        out[n].band = b;
+        out[n].g0 = g0;
+        out[n].u = (ng - g0) >= 4 ? 4 : (ng - g0);
+        ++n;
+      }
+    }
+  return n;
+}
+
+// lw_reduce: band/g-point reduction in a fixed order (rtrn.f90:529-557) -> fluxes in W m-2.
+CB_HD void lw_reduce_level(const Tables& T, const Work& W, const Unit* units, int nunits, int nlay, int c0, int c,
+                           int lev, int ncol, const Out& out) {
+  const int ncc = W.ncc;
+  const size_t pstride = (size_t)(nlay + 1) * ncc;
+  const double wtdiff = 0.5;
+  double tot[4] = {0., 0., 0., 0.};
+  for (int b = 1; b <= 16; ++b) {
+    double bs[4] = {0., 0., 0., 0.};
+    for (int k = 0; k < nunits; ++k) {
+      if (units[k].band != b) continue;
+      const double* p = W.part + (size_t)k * 4 * pstride + (size_t)lev * ncc + c;
+      for (int q = 0; q < 4; ++q) bs[q] = bs[q] + p[q * pstride];
+    }
+    const double dw = CB_LDG(T.base + T.delwave + (b - 1));
+    for (int q = 0; q < 4; ++q) tot[q] = tot[q] + (bs[q] * wtdiff) * dw;
+  }
+  const size_t o = (size_t)lev * ncol + (c0 + c);
+  out.uflx[o] = tot[0] * T.fluxfac;
+  out.dflx[o] = tot[1] * T.fluxfac;
+  out.uflxc[o] = tot[2] * T.fluxfac;
+  out.dflxc[o] = tot[3] * T.fluxfac;
+}
+// heating rates (rtrn.f90:569-581)
+CB_HD void lw_heating(const Tables& T, const In& in, const Out& out, int gcol, int l) {
+  const int ncol = in.ncol;
+  const size_t o0 = (size_t)l * ncol + gcol, o1 = o0 + ncol;
+  const double dp = in.plev[o0] - in.plev[o1];
+  const double fnet0 = out.uflx[o0] - out.dflx[o0], fnet1 = out.uflx[o1] - out.dflx[o1];
+  const double fnetc0 = out.uflxc[o0] - out.dflxc[o0], fnetc1 = out.uflxc[o1] - out.dflxc[o1];
+  out.hr[o0] = T.heatfac * (fnet0 - fnet1) / dp;
+  out.hrc[o0] = T.heatfac * (fnetc0 - fnetc1) / dp;
+}
+
+}  // namespace lw
+}  // namespace cb

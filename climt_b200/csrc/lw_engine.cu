@@ -1,0 +1,346 @@
+// climt_b200 -- RRTMG longwave engine: CUDA kernels (sm_100a), launcher and C ABI (include/climt_b200.h).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/climt_b200.h"
+#include "lw_tables.h"
+
+using namespace cb::lw;
+
+namespace {
+
+constexpr int kBlock = 128;
+
+__global__ void __launch_bounds__(kBlock) k_prep(const __grid_constant__ Tables T, const __grid_constant__ In in,
+                                                 const Flags fl, const __grid_constant__ Work W, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) prep_column(T, in, fl, W, c0, c);
+}
+
+struct UnitList {
+  Unit u[kMaxUnits];
+  int n;
+};
+
+// One block = 128 adjacent columns x one unit (<=4 g-points of one band): every branch on the band is
+// block-uniform, all global accesses are column-contiguous.
+__global__ void __launch_bounds__(kBlock) k_units(const __grid_constant__ Tables T, const __grid_constant__ In in,
+                                                  const __grid_constant__ Work W, const __grid_constant__ UnitList UL,
+                                                  int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int k = blockIdx.y;
+  const Unit un = UL.u[k];
+#define CB_CASE(B)                                              \
+  case B:                                                       \
+    if (un.u == 4) lw_unit<B, 4>(T, in, W, c0, c, un.g0, k);    \
+    else lw_unit<B, 2>(T, in, W, c0, c, un.g0, k);              \
+    break;
+  switch (un.band) {
+    CB_CASE(1) CB_CASE(2) CB_CASE(3) CB_CASE(4) CB_CASE(5) CB_CASE(6) CB_CASE(7) CB_CASE(8)
+    CB_CASE(9) CB_CASE(10) CB_CASE(11) CB_CASE(12) CB_CASE(13) CB_CASE(14) CB_CASE(15) CB_CASE(16)
+  }
+#undef CB_CASE
+}
+
+__global__ void __launch_bounds__(kBlock) k_reduce(const __grid_constant__ Tables T, const __grid_constant__ Work W,
+                                                   const __grid_constant__ UnitList UL, const Out out, int nlay,
+                                                   int ncol, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lev = blockIdx.y;
+  if (c < n) lw_reduce_level(T, W, UL.u, UL.n, nlay, c0, c, lev, ncol, out);
+}
+
+__global__ void __launch_bounds__(kBlock) k_heat(const __grid_constant__ Tables T, const __grid_constant__ In in,
+                                                 const Out out, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = blockIdx.y;
+  if (c < n) lw_heating(T, in, out, c0 + c, l);
+}
+
+std::string g_error;
+std::mutex g_mu;
+
+#define CUDA_OK(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      e->error = std::string(#call) + ": " + cudaGetErrorString(_e);                          \
+      return -1;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+}  // namespace
+
+struct cb200_lw_engine {
+  int device = 0;
+  Tables T;
+  double* d_tables = nullptr;
+  Flags fl{1, 0, 2, 1, 1};
+  UnitList UL;
+  // workspace (grown on demand)
+  int cap_ncc = 0, cap_nlay = 0;
+  Work W{};
+  int max_chunk = 16384;
+  // host-pointer path staging
+  double* d_stage = nullptr;
+  size_t stage_cap = 0;
+  double* h_pinned = nullptr;
+  size_t pinned_cap = 0;
+  int* h_err = nullptr;
+  std::string error;
+  int launches = 0;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double unit_ms = 0.0;
+
+  void free_work() {
+    cudaFree(W.ws); cudaFree(W.idx); cudaFree(W.laytrop); cudaFree(W.ncbands); cudaFree(W.pwvcm);
+    cudaFree(W.cld); cudaFree(W.scr); cudaFree(W.part); cudaFree(W.err);
+    W = Work{};
+    cap_ncc = cap_nlay = 0;
+  }
+  int ensure_work(int ncc, int nlay) {
+    cb200_lw_engine* e = this;
+    if (ncc <= cap_ncc && nlay <= cap_nlay && W.ws) return 0;
+    free_work();
+    const size_t n = (size_t)ncc, L = (size_t)nlay;
+    CUDA_OK(cudaMalloc(&W.ws, sizeof(double) * NF * L * n));
+    CUDA_OK(cudaMalloc(&W.idx, sizeof(int) * L * n));
+    CUDA_OK(cudaMalloc(&W.laytrop, sizeof(int) * n));
+    CUDA_OK(cudaMalloc(&W.ncbands, sizeof(int) * n));
+    CUDA_OK(cudaMalloc(&W.pwvcm, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&W.cld, sizeof(double) * 32 * L * n));
+    CUDA_OK(cudaMalloc(&W.scr, sizeof(double) * 140 * 4 * L * n));
+    CUDA_OK(cudaMalloc(&W.part, sizeof(double) * UL.n * 4 * (L + 1) * n));
+    CUDA_OK(cudaMalloc(&W.err, sizeof(int)));
+    CUDA_OK(cudaMemset(W.err, 0, sizeof(int)));
+    cap_ncc = ncc;
+    cap_nlay = nlay;
+    return 0;
+  }
+};
+
+extern "C" const char* cb200_global_error(void) { return g_error.c_str(); }
+
+extern "C" int cb200_lw_create(cb200_lw_engine** out, const char* table_blob, const double constants[11], int device) {
+  *out = nullptr;
+  auto* e = new cb200_lw_engine();
+  try {
+    Constants k;
+    std::memcpy(&k, constants, sizeof(k));
+    std::vector<double> img;
+    build_tables(table_blob, k, img, e->T);
+    e->device = device;
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) throw std::runtime_error(std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+    ce = cudaMalloc(&e->d_tables, img.size() * sizeof(double));
+    if (ce != cudaSuccess) throw std::runtime_error(std::string("cudaMalloc(tables): ") + cudaGetErrorString(ce));
+    ce = cudaMemcpy(e->d_tables, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) throw std::runtime_error(std::string("cudaMemcpy(tables): ") + cudaGetErrorString(ce));
+    e->T.base = e->d_tables;
+    e->UL.n = build_units(e->UL.u);
+    if (const char* mc = std::getenv("CLIMT_B200_MAX_CHUNK")) e->max_chunk = std::max(128, std::atoi(mc));
+    cudaMallocHost(&e->h_err, sizeof(int));
+    cudaEventCreate(&e->ev0);
+    cudaEventCreate(&e->ev1);
+  } catch (std::exception& ex) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_error = ex.what();
+    delete e;
+    return -1;
+  }
+  *out = e;
+  return 0;
+}
+
+extern "C" void cb200_lw_destroy(cb200_lw_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  e->free_work();
+  cudaFree(e->d_tables);
+  cudaFree(e->d_stage);
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  if (e->h_err) cudaFreeHost(e->h_err);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  delete e;
+}
+
+extern "C" int cb200_lw_set_options(cb200_lw_engine* e, int icld, int idrv, int inflag, int iceflag, int liqflag) {
+  if (icld < 0 || icld > 3) icld = 2;  // rrtmg_lw_rad.nomcica.f90:437
+  if (idrv != 0) { e->error = "calculate_change_up_flux (idrv=1) is not implemented in the CUDA engine yet"; return -2; }
+  if (icld >= 2) { e->error = "maximum-random / maximum cloud overlap (icld=2,3) is not implemented in the CUDA engine yet"; return -2; }
+  e->fl = Flags{icld, idrv, inflag, iceflag, liqflag};
+  return 0;
+}
+
+extern "C" const char* cb200_lw_last_error(cb200_lw_engine* e) { return e ? e->error.c_str() : g_error.c_str(); }
+extern "C" int cb200_lw_last_launches(cb200_lw_engine* e) { return e->launches; }
+extern "C" int cb200_lw_enable_timing(cb200_lw_engine* e, int on) { e->timing = on != 0; return 0; }
+extern "C" double cb200_lw_last_unit_kernel_ms(cb200_lw_engine* e) { return e->unit_ms; }
+
+static In make_in(int ncol, int nlay, const cb200_lw_inputs* p) {
+  In in;
+  in.ncol = ncol; in.nlay = nlay;
+  in.play = p->play; in.plev = p->plev; in.tlay = p->tlay; in.tlev = p->tlev; in.tsfc = p->tsfc;
+  in.h2o = p->h2ovmr; in.o3 = p->o3vmr; in.co2 = p->co2vmr; in.ch4 = p->ch4vmr; in.n2o = p->n2ovmr; in.o2 = p->o2vmr;
+  in.cfc11 = p->cfc11vmr; in.cfc12 = p->cfc12vmr; in.cfc22 = p->cfc22vmr; in.ccl4 = p->ccl4vmr;
+  in.emis = p->emis; in.cldfr = p->cldfr; in.taucld = p->taucld; in.cicewp = p->cicewp; in.cliqwp = p->cliqwp;
+  in.reice = p->reice; in.reliq = p->reliq; in.tauaer = p->tauaer;
+  return in;
+}
+
+extern "C" int cb200_lw_run_device(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* pin,
+                                   const cb200_lw_outputs* pout, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (ncol <= 0 || nlay <= 0 || nlay > 203) { e->error = "bad ncol/nlay (1 <= nlay <= 203, parrrtm.f90:31)"; return -3; }
+  CUDA_OK(cudaSetDevice(e->device));
+  int chunk = ncol < e->max_chunk ? ncol : e->max_chunk;
+  chunk = (chunk + kBlock - 1) / kBlock * kBlock;
+  if (e->ensure_work(chunk, nlay)) return -1;
+  Work W = e->W;
+  W.ncc = chunk;
+  const In in = make_in(ncol, nlay, pin);
+  Out out{pout->uflx, pout->dflx, pout->hr, pout->uflxc, pout->dflxc, pout->hrc};
+  e->launches = 0;
+  e->unit_ms = 0.0;
+  for (int c0 = 0; c0 < ncol; c0 += chunk) {
+    const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
+    const int gx = (n + kBlock - 1) / kBlock;
+    k_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
+    if (e->timing) cudaEventRecord(e->ev0, st);
+    k_units<<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    if (e->timing) cudaEventRecord(e->ev1, st);
+    k_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(e->T, W, e->UL, out, nlay, ncol, c0, n);
+    k_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
+    e->launches += 4;
+    if (e->timing) {
+      CUDA_OK(cudaEventSynchronize(e->ev1));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+      e->unit_ms += ms;
+    }
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cb200_lw_check(cb200_lw_engine* e) {
+  if (!e->W.err) return 0;
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaMemcpy(e->h_err, e->W.err, sizeof(int), cudaMemcpyDeviceToHost));
+  const int code = *e->h_err;
+  if (code) {
+    static const char* msg[] = {"", "ICE RADIUS TOO SMALL", "ICE RADIUS OUT OF BOUNDS",
+                                "ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS", "LIQUID EFFECTIVE RADIUS OUT OF BOUNDS"};
+    e->error = msg[code < 5 ? code : 2];  // message text of the Fortran `stop` (rrtmg_lw_cldprop.f90:193-243)
+    cudaMemset(e->W.err, 0, sizeof(int));
+  }
+  return code;
+}
+
+extern "C" int cb200_lw_run_host(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* hin,
+                                 const cb200_lw_outputs* hout) {
+  CUDA_OK(cudaSetDevice(e->device));
+  const size_t n = (size_t)ncol, L = (size_t)nlay;
+  // sizes (doubles) of the 23 inputs in cb200_lw_inputs order, then the 6 outputs
+  const size_t isz[23] = {L * n, (L + 1) * n, L * n, (L + 1) * n, n, L * n, L * n, L * n, L * n, L * n, L * n, L * n,
+                          L * n, L * n, L * n, 16 * n, L * n, 16 * L * n, L * n, L * n, L * n, L * n, 16 * L * n};
+  const size_t osz[6] = {(L + 1) * n, (L + 1) * n, L * n, (L + 1) * n, (L + 1) * n, L * n};
+  size_t tot = 0;
+  for (size_t s : isz) tot += s;
+  size_t otot = 0;
+  for (size_t s : osz) otot += s;
+  if (tot + otot > e->stage_cap) {
+    cudaFree(e->d_stage);
+    e->d_stage = nullptr;
+    e->stage_cap = 0;
+    CUDA_OK(cudaMalloc(&e->d_stage, (tot + otot) * sizeof(double)));
+    e->stage_cap = tot + otot;
+  }
+  const double* const* hp = reinterpret_cast<const double* const*>(hin);
+  cb200_lw_inputs din;
+  const double** dp = reinterpret_cast<const double**>(&din);
+  size_t off = 0;
+  for (int i = 0; i < 23; ++i) {
+    CUDA_OK(cudaMemcpyAsync(e->d_stage + off, hp[i], isz[i] * sizeof(double), cudaMemcpyHostToDevice, 0));
+    dp[i] = e->d_stage + off;
+    off += isz[i];
+  }
+  cb200_lw_outputs dout;
+  double** dop = reinterpret_cast<double**>(&dout);
+  for (int i = 0; i < 6; ++i) {
+    dop[i] = e->d_stage + off;
+    off += osz[i];
+  }
+  int rc = cb200_lw_run_device(e, ncol, nlay, &din, &dout, 0);
+  if (rc) return rc;
+  double* const* hop = reinterpret_cast<double* const*>(hout);
+  for (int i = 0; i < 6; ++i)
+    CUDA_OK(cudaMemcpyAsync(hop[i], dop[i], osz[i] * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  CUDA_OK(cudaStreamSynchronize(0));
+  return cb200_lw_check(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference-named entry points bound to one process-global engine.
+namespace {
+double g_consts[11] = {0};
+cb200_lw_engine* g_engine = nullptr;
+
+std::string default_blob() {
+  if (const char* p = std::getenv("CLIMT_B200_LW_TABLES")) return p;
+  Dl_info info;
+  if (dladdr((void*)&cb200_lw_create, &info) && info.dli_fname) {
+    std::string so = info.dli_fname;
+    size_t k = so.find_last_of('/');
+    std::string dir = k == std::string::npos ? "." : so.substr(0, k);
+    return dir + "/data/_cache/rrtmg_lw_reduced.blob";
+  }
+  return "rrtmg_lw_reduced.blob";
+}
+}  // namespace
+
+extern "C" void rrtmg_set_constants(double* pi, double* grav, double* planck, double* boltz, double* clight,
+                                    double* avogad, double* alosmt, double* gascon, double* sbcnst, double* secdy) {
+  double v[10] = {*pi, *grav, *planck, *boltz, *clight, *avogad, *alosmt, *gascon, *sbcnst, *secdy};
+  std::memcpy(g_consts, v, sizeof v);
+}
+
+extern "C" void rrtmg_lw_ini_wrapper(double* cpdair) {
+  g_consts[10] = *cpdair;
+  if (g_engine) { cb200_lw_destroy(g_engine); g_engine = nullptr; }
+  int dev = 0;
+  if (const char* d = std::getenv("CLIMT_B200_DEVICE")) dev = std::atoi(d);
+  if (cb200_lw_create(&g_engine, default_blob().c_str(), g_consts, dev))
+    std::fprintf(stderr, "climt_b200: rrtmg_lw_ini_wrapper failed: %s\n", cb200_global_error());
+}
+
+extern "C" void rrtmg_lw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* idrv, double* play, double* plev,
+                                         double* tlay, double* tlev, double* tsfc, double* h2ovmr, double* o3vmr,
+                                         double* co2vmr, double* ch4vmr, double* n2ovmr, double* o2vmr,
+                                         double* cfc11vmr, double* cfc12vmr, double* cfc22vmr, double* ccl4vmr,
+                                         double* emis, int* inflglw, int* iceflglw, int* liqflglw, double* cldfr,
+                                         double* taucld, double* cicewp, double* cliqwp, double* reice, double* reliq,
+                                         double* tauaer, double* uflx, double* dflx, double* hr, double* uflxc,
+                                         double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt) {
+  (void)duflx_dt; (void)duflxc_dt;
+  if (!g_engine) { std::fprintf(stderr, "climt_b200: rrtmg_lw_ini_wrapper has not been called\n"); return; }
+  if (*icld < 0 || *icld > 3) *icld = 2;
+  if (cb200_lw_set_options(g_engine, *icld, *idrv, *inflglw, *iceflglw, *liqflglw)) {
+    std::fprintf(stderr, "climt_b200: %s\n", cb200_lw_last_error(g_engine));
+    return;
+  }
+  cb200_lw_inputs in{play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, cfc11vmr, cfc12vmr,
+                     cfc22vmr, ccl4vmr, emis, cldfr, taucld, cicewp, cliqwp, reice, reliq, tauaer};
+  cb200_lw_outputs out{uflx, dflx, hr, uflxc, dflxc, hrc};
+  if (cb200_lw_run_host(g_engine, *ncol, *nlay, &in, &out))
+    std::fprintf(stderr, "climt_b200: %s\n", cb200_lw_last_error(g_engine));
+}

@@ -1,0 +1,122 @@
+"""Python face of the native engines: thin, typed wrappers over the C ABI (include/climt_b200.h).
+
+`LWEngine.run_host` takes numpy arrays (what sympl hands to `array_call`), `LWEngine.run_device`
+takes torch CUDA tensors and is asynchronous on the current torch stream.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native
+from .constants import rrtmg_constants
+from .rrtmg_tables import lw_blob_path
+
+_dp = ctypes.POINTER(ctypes.c_double)
+LW_IN = [f[0] for f in _native.LwInputs._fields_]
+LW_OUT = [f[0] for f in _native.LwOutputs._fields_]
+_CONST_ORDER = ("pi", "grav", "planck", "boltz", "clight", "avogad", "alosmt", "gascon", "sbcnst", "secdy", "cpdair")
+
+
+def lw_shapes(ncol, nlay):
+    L, n = nlay, ncol
+    ins = {k: (L, n) for k in LW_IN}
+    ins.update(plev=(L + 1, n), tlev=(L + 1, n), tsfc=(n,), emis=(16, n), taucld=(L, n, 16), tauaer=(16, L, n))
+    outs = {"uflx": (L + 1, n), "dflx": (L + 1, n), "uflxc": (L + 1, n), "dflxc": (L + 1, n), "hr": (L, n), "hrc": (L, n)}
+    return ins, outs
+
+
+class LWEngine:
+    """One RRTMG-LW engine instance: tables resident in HBM, options and constants per instance
+    (the reference keeps them in Cython/Fortran module globals, _rrtmg_lw.pyx:8-14)."""
+
+    def __init__(self, constants=None, device=0, icld=1, idrv=0, inflag=2, iceflag=1, liqflag=1):
+        self._L = _native.lib()
+        k = constants or rrtmg_constants()
+        c = np.array([k[n] for n in _CONST_ORDER], dtype=np.float64)
+        h = ctypes.c_void_p()
+        rc = self._L.cb200_lw_create(ctypes.byref(h), lw_blob_path().encode(), c.ctypes.data_as(_dp), int(device))
+        if rc != 0 or not h:
+            raise RuntimeError("cb200_lw_create failed: " + self._L.cb200_global_error().decode())
+        self._h = h
+        self.device = device
+        self.set_options(icld, idrv, inflag, iceflag, liqflag)
+
+    def set_options(self, icld, idrv, inflag, iceflag, liqflag):
+        if self._L.cb200_lw_set_options(self._h, icld, idrv, inflag, iceflag, liqflag):
+            raise NotImplementedError(self._err())
+
+    def _err(self):
+        return self._L.cb200_lw_last_error(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cb200_lw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- host buffers (numpy) ------------------------------------------------------------------
+    def run_host(self, ncol, nlay, arrays, out=None):
+        ins, outs = lw_shapes(ncol, nlay)
+        keep = []
+        pin = _native.LwInputs()
+        for k in LW_IN:
+            a = np.ascontiguousarray(arrays[k], dtype=np.float64)
+            if a.shape != ins[k]:
+                raise ValueError(f"{k}: expected shape {ins[k]}, got {a.shape}")
+            keep.append(a)
+            setattr(pin, k, a.ctypes.data_as(_dp))
+        out = out if out is not None else {k: np.empty(outs[k]) for k in LW_OUT}
+        pout = _native.LwOutputs()
+        for k in LW_OUT:
+            a = out[k]
+            if a.shape != outs[k] or a.dtype != np.float64 or not a.flags.c_contiguous:
+                raise ValueError(f"output {k}: need C-contiguous float64 {outs[k]}")
+            setattr(pout, k, a.ctypes.data_as(_dp))
+        rc = self._L.cb200_lw_run_host(self._h, ncol, nlay, ctypes.byref(pin), ctypes.byref(pout))
+        if rc < 0:
+            raise RuntimeError(self._err())
+        if rc > 0:
+            raise ValueError(self._err())
+        return out
+
+    # -- device buffers (torch CUDA tensors), asynchronous ------------------------------------------
+    def run_device(self, ncol, nlay, tensors, out, stream=None):
+        import torch
+        ins, outs = lw_shapes(ncol, nlay)
+        pin = _native.LwInputs()
+        for k in LW_IN:
+            t = tensors[k]
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == ins[k]):
+                raise ValueError(f"{k}: need contiguous float64 CUDA tensor of shape {ins[k]}")
+            setattr(pin, k, ctypes.cast(t.data_ptr(), _dp))
+        pout = _native.LwOutputs()
+        for k in LW_OUT:
+            t = out[k]
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == outs[k]):
+                raise ValueError(f"output {k}: need contiguous float64 CUDA tensor of shape {outs[k]}")
+            setattr(pout, k, ctypes.cast(t.data_ptr(), _dp))
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        rc = self._L.cb200_lw_run_device(self._h, ncol, nlay, ctypes.byref(pin), ctypes.byref(pout), ctypes.c_void_p(s))
+        if rc:
+            raise RuntimeError(self._err())
+
+    def check(self):
+        rc = self._L.cb200_lw_check(self._h)
+        if rc:
+            raise ValueError(self._err())
+
+    def enable_timing(self, on=True):
+        self._L.cb200_lw_enable_timing(self._h, 1 if on else 0)
+
+    @property
+    def last_unit_kernel_ms(self):
+        return self._L.cb200_lw_last_unit_kernel_ms(self._h)
+
+    @property
+    def last_launches(self):
+        return self._L.cb200_lw_last_launches(self._h)

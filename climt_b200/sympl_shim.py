@@ -1,0 +1,118 @@
+"""Minimal stand-in for the slice of sympl the radiation components use.
+
+sympl is a third-party dependency of climt (`sympl>=0.5.0`, setup.py:49) and is not installable in
+this image.  When the real package is importable it is used unchanged; otherwise this shim provides
+just enough of `TendencyComponent.__call__` (dimension flattening to ["mid_levels", "*"], a small unit
+table, re-wrapping of outputs) for the drop-in components to be exercised through `component(state)`.
+"""
+import numpy as np
+
+try:  # pragma: no cover - not available in the build image
+    from sympl import TendencyComponent, DataArray, initialize_numpy_arrays_with_properties  # noqa: F401
+    HAVE_SYMPL = True
+except Exception:  # ImportError or a broken install
+    HAVE_SYMPL = False
+
+    class DataArray:
+        """Just enough of xarray.DataArray: values, dims, attrs['units']."""
+
+        def __init__(self, values, dims=(), attrs=None):
+            self.values = np.asarray(values)
+            self.dims = tuple(dims)
+            self.attrs = dict(attrs or {})
+
+        @property
+        def shape(self):
+            return self.values.shape
+
+        def to_units(self, units):
+            return DataArray(self.values * _unit_factor(self.attrs.get("units", ""), units), self.dims,
+                             {**self.attrs, "units": units})
+
+    _CANON = {"mbar": ("Pa", 100.0), "hPa": ("Pa", 100.0), "Pa": ("Pa", 1.0),
+              "g m^-2": ("kg m^-2", 1e-3), "kg m^-2": ("kg m^-2", 1.0),
+              "micrometer": ("m", 1e-6), "m": ("m", 1.0),
+              "degK": ("K", 1.0), "K": ("K", 1.0),
+              "g/g": ("1", 1.0), "kg/kg": ("1", 1.0), "dimensionless": ("1", 1.0), "mole/mole": ("1", 1.0),
+              "": ("1", 1.0), "1": ("1", 1.0),
+              "W m^-2": ("W m^-2", 1.0), "degK day^-1": ("K day^-1", 1.0), "K day^-1": ("K day^-1", 1.0),
+              "radians": ("rad", 1.0), "degrees": ("rad", np.pi / 180.0)}
+
+    def _unit_factor(src, dst):
+        if src == dst:
+            return 1.0
+        try:
+            (b0, f0), (b1, f1) = _CANON[src], _CANON[dst]
+        except KeyError as e:
+            raise ValueError(f"sympl shim: unknown unit {e}") from None
+        if b0 != b1:
+            raise ValueError(f"sympl shim: cannot convert {src!r} to {dst!r}")
+        return f0 / f1
+
+    def _to_raw(da, dims, units):
+        """DataArray -> numpy in the component's dims; '*' collects every other dim (C order)."""
+        vals = da.values * _unit_factor(da.attrs.get("units", ""), units)
+        named = [d for d in dims if d != "*"]
+        for d in named:
+            if d not in da.dims:
+                raise ValueError(f"dimension {d} missing from {da.dims}")
+        star = [d for d in da.dims if d not in named]
+        order = []
+        for d in dims:
+            order += [da.dims.index(x) for x in star] if d == "*" else [da.dims.index(d)]
+        v = np.transpose(vals, order)
+        shape, k = [], 0
+        for d in dims:
+            if d == "*":
+                n = int(np.prod([da.values.shape[da.dims.index(x)] for x in star])) if star else 1
+                shape.append(n)
+                k += len(star)
+            else:
+                shape.append(v.shape[k])
+                k += 1
+        star_shape = tuple(da.values.shape[da.dims.index(x)] for x in star)
+        return np.ascontiguousarray(v.reshape(shape), dtype=np.float64), tuple(star), star_shape
+
+    class TendencyComponent:
+        input_properties = {}
+        tendency_properties = {}
+        diagnostic_properties = {}
+
+        def __init__(self, **kwargs):
+            if kwargs:
+                raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
+
+        def __call__(self, state):
+            raw, star, star_shape = {}, (), ()
+            for name, prop in self.input_properties.items():
+                if name not in state:
+                    raise KeyError(f"state is missing input quantity {name!r}")
+                raw[name], s, ss = _to_raw(state[name], prop["dims"], prop.get("units", ""))
+                if "*" in prop["dims"] and len(s) >= len(star):
+                    star, star_shape = s, ss
+            tend, diag = self.array_call(raw)
+
+            def wrap(arr, prop):
+                dims, shape, k = [], [], 0
+                for d in prop["dims"]:
+                    if d == "*":
+                        dims += list(star)
+                        shape += list(star_shape)
+                    else:
+                        dims.append(d)
+                        shape.append(arr.shape[k])
+                    k += 1
+                return DataArray(np.asarray(arr).reshape(shape), dims, {"units": prop.get("units", "")})
+            return ({k: wrap(v, self.tendency_properties[k]) for k, v in tend.items()},
+                    {k: wrap(v, self.diagnostic_properties[k]) for k, v in diag.items()})
+
+    def initialize_numpy_arrays_with_properties(output_properties, raw_input_state, input_properties):
+        dim_len = {}
+        for name, prop in input_properties.items():
+            if name in raw_input_state:
+                for d, n in zip(prop["dims"], np.shape(raw_input_state[name])):
+                    dim_len[d] = n
+        out = {}
+        for name, prop in output_properties.items():
+            out[name] = np.zeros([dim_len[d] for d in prop["dims"]], dtype=np.float64)
+        return out

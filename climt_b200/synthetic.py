@@ -1,0 +1,52 @@
+"""Synthetic (lat x lon x level) column states for parity tests and the benchmark.
+
+Follows SURVEY.md section 8(d): hybrid sigma-pressure levels with a random surface pressure per column,
+a moist-adiabat-like temperature profile, humidity decaying with height and latitude, climt's
+default ozone profile, fixed well-mixed gases; optional random clouds.  Everything is fp64 and in the
+units the RRTMG C ABI takes (hPa, K, volume mixing ratios, g m-2, micron).
+"""
+import numpy as np
+
+from . import state as _s
+from .constants import get_constant
+
+LW_FIELDS = ("play", "plev", "tlay", "tlev", "tsfc", "h2o", "o3", "co2", "ch4", "n2o", "o2", "cfc11", "cfc12",
+             "cfc22", "ccl4", "emis", "cldfr", "taucld", "cicewp", "cliqwp", "reice", "reliq", "tauaer")
+
+
+def make_lw_state(ncol, nlay, seed=20260925, clouds=False, trace=True, aerosol=False, emis_range=None):
+    rng = np.random.default_rng(seed)
+    lat = np.deg2rad(rng.uniform(-90, 90, ncol))
+    ps = rng.uniform(9.5e4, 1.03e5, ncol)
+    ak, bk = _s.hybrid_sigma_pressure_levels(nlay + 1, get_constant("reference_air_pressure"),
+                                             get_constant("top_of_model_pressure"))
+    p, p_int = _s.pressure_from_hybrid(ak, bk, ps)          # Pa, (nlay, ncol), surface first
+    ts = 300.0 - 40.0 * np.sin(lat) ** 2 + rng.normal(0, 2, ncol)
+    t = np.maximum(ts[None, :] * (p / ps[None, :]) ** 0.19, 200.0) + rng.normal(0, 0.5, p.shape)
+    tsfc = ts + rng.uniform(0, 2, ncol)
+    q = 0.018 * (p / ps[None, :]) ** 3 * np.exp(-(np.rad2deg(lat)[None, :] / 30.0) ** 2) + 1e-6
+    h2o = _s.mass_to_volume_mixing_ratio(q, 18.02)
+    o3 = np.maximum(_s.init_ozone(p), 1e-9)
+    shp = (nlay, ncol)
+    st = {
+        "play": p / 100.0, "plev": p_int / 100.0, "tlay": t,
+        "tsfc": tsfc, "h2o": h2o, "o3": o3,
+        "co2": np.full(shp, 400e-6), "ch4": np.full(shp, 1.8e-6 if trace else 0.0),
+        "n2o": np.full(shp, 3.2e-7 if trace else 0.0), "o2": np.full(shp, 0.21),
+        "cfc11": np.full(shp, 2.3e-10 if trace else 0.0), "cfc12": np.full(shp, 5.2e-10 if trace else 0.0),
+        "cfc22": np.full(shp, 2.3e-10 if trace else 0.0), "ccl4": np.full(shp, 8.0e-11 if trace else 0.0),
+        "emis": np.ones((16, ncol)) if emis_range is None else rng.uniform(*emis_range, (16, ncol)),
+        "cldfr": np.zeros(shp), "taucld": np.zeros((nlay, ncol, 16)),
+        "cicewp": np.zeros(shp), "cliqwp": np.zeros(shp),
+        "reice": np.full(shp, 20.0), "reliq": np.full(shp, 10.0),
+        "tauaer": np.zeros((16, nlay, ncol)) if not aerosol else rng.uniform(0, 0.05, (16, nlay, ncol)),
+    }
+    st["tlev"] = _s.get_interface_values(st["tlay"], st["tsfc"], st["play"], st["plev"])
+    if clouds:
+        band = (p > 3.0e4) & (p < 9.0e4) & (rng.uniform(0, 1, shp) < 0.3)
+        st["cldfr"] = np.where(band, rng.uniform(0.05, 1, shp), 0.0)
+        st["cicewp"] = np.where(band, rng.uniform(0, 30, shp), 0.0)
+        st["cliqwp"] = np.where(band, rng.uniform(0, 30, shp), 0.0)
+        st["reice"] = rng.uniform(15, 120, shp)
+        st["reliq"] = rng.uniform(4, 30, shp)
+    return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in st.items()}

@@ -1,0 +1,87 @@
+/* climt_b200 -- C ABI of the B200-native column radiative-transfer engines.
+ *
+ * This is the drop-in boundary: it replaces the C symbols climt's Cython shims bind
+ * (all citations relative to the reference tree, climt/):
+ *
+ *   rrtmg_set_constants        _lib/rrtmg_lw/rrlw_con.f90:46-71      (decl _components/rrtmg/lw/_rrtmg_lw.pyx:19-24)
+ *   rrtmg_lw_ini_wrapper       _lib/rrtmg_lw/rrtmg_lw_c_binder.f90:39-48   (decl _rrtmg_lw.pyx:26)
+ *   rrtmg_lw_nomcica_wrapper   _lib/rrtmg_lw/rrtmg_lw_c_binder.f90:176-256 (decl _rrtmg_lw.pyx:62-80)
+ *
+ * Two flavours are exported:
+ *  (1) handle-based, re-entrant entry points (cb200_lw_*): explicit constants, explicit options, per-instance
+ *      tables in HBM, status codes instead of Fortran `stop`.  Device-pointer and host-pointer variants.
+ *  (2) the reference's own symbol names with the reference's own by-pointer signatures, bound to one
+ *      process-global engine, so `_rrtmg_lw.pyx` links against libclimt_b200.so unchanged.
+ *
+ * Array layout everywhere = the reference ABI: Fortran (ncol, nlay[+1]) == C (nlay[+1], ncol), column
+ * fastest; emis (16, ncol); taucld (nlay, ncol, 16) [Fortran (16,ncol,nlay)]; tauaer (16, nlay, ncol)
+ * [Fortran (ncol,nlay,16)].  fp64.  Pressures hPa, temperatures K, gases volume mixing ratio,
+ * cloud water paths g m-2, particle sizes micron.  Outputs: fluxes W m-2 on nlay+1 interfaces
+ * (surface first), heating rates K day-1 on nlay layers.
+ */
+#ifndef CLIMT_B200_H
+#define CLIMT_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cb200_lw_engine cb200_lw_engine;
+
+/* order = argument order of rrtmg_lw_nomcica_wrapper (rrtmg_lw_c_binder.f90:176-189) */
+typedef struct cb200_lw_inputs {
+  const double *play, *plev, *tlay, *tlev, *tsfc;
+  const double *h2ovmr, *o3vmr, *co2vmr, *ch4vmr, *n2ovmr, *o2vmr, *cfc11vmr, *cfc12vmr, *cfc22vmr, *ccl4vmr;
+  const double *emis;
+  const double *cldfr, *taucld, *cicewp, *cliqwp, *reice, *reliq;
+  const double *tauaer;
+} cb200_lw_inputs;
+
+typedef struct cb200_lw_outputs {
+  double *uflx, *dflx, *hr, *uflxc, *dflxc, *hrc; /* hr/hrc: (nlay, ncol); fluxes: (nlay+1, ncol) */
+} cb200_lw_outputs;
+
+/* constants[11] = pi, grav [m s-2], planck [erg s], boltz [erg K-1], clight [cm s-1], avogadro, loschmidt [cm-3],
+ * gas constant [erg mol-1 K-1], stefan-boltzmann [W cm-2 K-4], seconds per day  (rrtmg_set_constants)
+ * + cp of dry air [J kg-1 K-1] (rrtmg_lw_ini_wrapper).  table_blob: file written by climt_b200/rrtmg_tables.py.
+ * Returns 0 on success; on failure *out is NULL and cb200_global_error() explains. */
+int cb200_lw_create(cb200_lw_engine** out, const char* table_blob, const double constants[11], int device);
+void cb200_lw_destroy(cb200_lw_engine* e);
+/* icld: 0 clear, 1 random, 2 maximum-random, 3 maximum; idrv: 0/1; inflag/iceflag/liqflag as RRTMG
+ * (module globals in _rrtmg_lw.pyx:8-14 in the reference; per engine here). */
+int cb200_lw_set_options(cb200_lw_engine* e, int icld, int idrv, int inflag, int iceflag, int liqflag);
+/* Asynchronous on `stream` (a cudaStream_t, NULL = default stream); pointers are device pointers owned by
+ * the caller.  Returns 0 or a negative launch/configuration error.  Input-validation errors that the Fortran
+ * turns into `stop` are reported by cb200_lw_check() after the stream has been synchronised. */
+int cb200_lw_run_device(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* in,
+                        const cb200_lw_outputs* out, void* stream);
+/* Same with host pointers: stages H2D, runs, copies back, synchronises, checks. */
+int cb200_lw_run_host(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* in,
+                      const cb200_lw_outputs* out);
+/* 0 = ok; >0 = input out of the range the reference accepts (message via cb200_lw_last_error). */
+int cb200_lw_check(cb200_lw_engine* e);
+const char* cb200_lw_last_error(cb200_lw_engine* e);
+const char* cb200_global_error(void);
+/* number of kernel launches issued by the last run call (for bench.py's gpu_launches) */
+int cb200_lw_last_launches(cb200_lw_engine* e);
+/* device time [ms] of the dominant kernel (g-point units) in the last run_host/run_device call when
+ * timing was enabled with cb200_lw_enable_timing(e, 1); measured with CUDA events on the launch stream. */
+int cb200_lw_enable_timing(cb200_lw_engine* e, int on);
+double cb200_lw_last_unit_kernel_ms(cb200_lw_engine* e);
+
+/* ---- reference-named entry points (one process-global engine; tables from $CLIMT_B200_LW_TABLES or
+ *      <dir of this library>/../data/_cache/rrtmg_lw_reduced.blob) ---- */
+void rrtmg_set_constants(double* pi, double* grav, double* planck, double* boltz, double* clight, double* avogad,
+                         double* alosmt, double* gascon, double* sbcnst, double* secdy);
+void rrtmg_lw_ini_wrapper(double* cpdair);
+void rrtmg_lw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* idrv, double* play, double* plev, double* tlay,
+                              double* tlev, double* tsfc, double* h2ovmr, double* o3vmr, double* co2vmr,
+                              double* ch4vmr, double* n2ovmr, double* o2vmr, double* cfc11vmr, double* cfc12vmr,
+                              double* cfc22vmr, double* ccl4vmr, double* emis, int* inflglw, int* iceflglw,
+                              int* liqflglw, double* cldfr, double* taucld, double* cicewp, double* cliqwp,
+                              double* reice, double* reliq, double* tauaer, double* uflx, double* dflx, double* hr,
+                              double* uflxc, double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

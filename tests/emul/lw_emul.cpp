@@ -1,0 +1,63 @@
+// TEST-ONLY host emulation of the CUDA LW engine: runs the very same per-thread code
+// (climt_b200/csrc/lw_core.cuh) serially on the CPU so the kernel logic can be checked against the
+// oracle in a container without a GPU.  Not part of the product; the product never falls back to this.
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../climt_b200/csrc/lw_tables.h"
+
+using namespace cb::lw;
+
+template <int B, int U>
+static void run_unit(const Tables& T, const In& in, const Work& W, int n, int g0, int unit) {
+  for (int c = 0; c < n; ++c) lw_unit<B, U>(T, in, W, 0, c, g0, unit);
+}
+
+extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* flags5, int ncol, int nlay,
+                           const double* const* inp /*23 pointers in struct In order*/, double* const* outp /*6*/) {
+  try {
+    Constants k;
+    std::memcpy(&k, consts11, sizeof(k));
+    std::vector<double> img;
+    Tables T;
+    build_tables(blob, k, img, T);
+    T.base = img.data();
+    In in;
+    in.ncol = ncol; in.nlay = nlay;
+    const double** ip = &in.play;
+    for (int i = 0; i < 23; ++i) ip[i] = inp[i];
+    Out out;
+    double** op = &out.uflx;
+    for (int i = 0; i < 6; ++i) op[i] = outp[i];
+    Flags fl{flags5[0], flags5[1], flags5[2], flags5[3], flags5[4]};
+    Unit units[kMaxUnits];
+    const int nunits = build_units(units);
+    Work W;
+    W.ncc = ncol;
+    std::vector<double> ws((size_t)NF * nlay * ncol), pw(ncol), cld((size_t)32 * nlay * ncol),
+        scr((size_t)140 * 4 * nlay * ncol), part((size_t)nunits * 4 * (nlay + 1) * ncol);
+    std::vector<int> idx((size_t)nlay * ncol), lt(ncol), ncb(ncol);
+    int err = 0;
+    W.ws = ws.data(); W.idx = idx.data(); W.laytrop = lt.data(); W.ncbands = ncb.data(); W.pwvcm = pw.data();
+    W.cld = cld.data(); W.scr = scr.data(); W.part = part.data(); W.err = &err;
+    for (int c = 0; c < ncol; ++c) prep_column(T, in, fl, W, 0, c);
+    for (int k2 = 0; k2 < nunits; ++k2) {
+      const Unit un = units[k2];
+#define CASE(B) case B: if (un.u == 4) run_unit<B, 4>(T, in, W, ncol, un.g0, k2); else run_unit<B, 2>(T, in, W, ncol, un.g0, k2); break;
+      switch (un.band) {
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+        CASE(14) CASE(15) CASE(16)
+      }
+#undef CASE
+    }
+    for (int c = 0; c < ncol; ++c)
+      for (int lev = 0; lev <= nlay; ++lev) lw_reduce_level(T, W, units, nunits, nlay, 0, c, lev, ncol, out);
+    for (int c = 0; c < ncol; ++c)
+      for (int l = 0; l < nlay; ++l) lw_heating(T, in, out, c, l);
+    return err;
+  } catch (std::exception& e) {
+    std::fprintf(stderr, "emul_lw_run: %s\n", e.what());
+    return -1;
+  }
+}

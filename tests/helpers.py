@@ -1,0 +1,94 @@
+"""Shared test helpers: oracle drivers, default states in the C-ABI layout, the host emulation."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from climt_b200 import constants as C
+from climt_b200 import rrtmg_tables as RT
+from climt_b200 import state as S
+from climt_b200 import synthetic as SY
+from climt_b200 import tables as T
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden", "reference_caches.npz")
+_dp = ctypes.POINTER(ctypes.c_double)
+
+ORC_ARG_ORDER = ("play", "plev", "tlay", "tlev", "tsfc", "h2o", "o3", "co2", "ch4", "n2o", "o2", "cfc11", "cfc12",
+                 "cfc22", "ccl4", "emis", "cldfr", "tauaer", "taucld", "cicewp", "cliqwp", "reice", "reliq")
+# synthetic/oracle short names -> C ABI names
+ABI_NAME = {"h2o": "h2ovmr", "o3": "o3vmr", "co2": "co2vmr", "ch4": "ch4vmr", "n2o": "n2ovmr", "o2": "o2vmr",
+            "cfc11": "cfc11vmr", "cfc12": "cfc12vmr", "cfc22": "cfc22vmr", "ccl4": "ccl4vmr"}
+
+
+def to_abi(st):
+    return {ABI_NAME.get(k, k): v for k, v in st.items()}
+
+
+def lw_oracle(**flags):
+    from oracle.rrtmg import LWOracle
+    return LWOracle(C.rrtmg_constants(), T.raw_blob_path("lw"), **flags)
+
+
+def run_lw_oracle(orc, st):
+    return orc(*[st[k] for k in ORC_ARG_ORDER])
+
+
+def default_lw_abi_state(nz, ncol=1, external_tint=False):
+    """climt's default RRTMGLongwave state converted to the C-ABI arrays (what array_call hands down)."""
+    d = S.default_rrtmg_lw_state(nz, ncol)
+    p, pi = d["air_pressure"] / 100.0, d["air_pressure_on_interface_levels"] / 100.0
+    st = {
+        "play": p, "plev": pi, "tlay": d["air_temperature"], "tsfc": d["surface_temperature"],
+        "h2o": S.mass_to_volume_mixing_ratio(d["specific_humidity"], 18.02),
+        "o3": d["mole_fraction_of_ozone_in_air"], "co2": d["mole_fraction_of_carbon_dioxide_in_air"],
+        "ch4": d["mole_fraction_of_methane_in_air"], "n2o": d["mole_fraction_of_nitrous_oxide_in_air"],
+        "o2": d["mole_fraction_of_oxygen_in_air"], "cfc11": d["mole_fraction_of_cfc11_in_air"],
+        "cfc12": d["mole_fraction_of_cfc12_in_air"], "cfc22": d["mole_fraction_of_cfc22_in_air"],
+        "ccl4": d["mole_fraction_of_carbon_tetrachloride_in_air"], "emis": d["surface_longwave_emissivity"],
+        "cldfr": d["cloud_area_fraction_in_atmosphere_layer"],
+        "taucld": d["longwave_optical_thickness_due_to_cloud"],
+        "cicewp": d["mass_content_of_cloud_ice_in_atmosphere_layer"] * 1e3,
+        "cliqwp": d["mass_content_of_cloud_liquid_water_in_atmosphere_layer"] * 1e3,
+        "reice": d["cloud_ice_particle_size"], "reliq": d["cloud_water_droplet_radius"],
+        "tauaer": d["longwave_optical_thickness_due_to_aerosol"],
+    }
+    if external_tint:
+        st["tlev"] = np.full((nz + 1, ncol), 290.0)
+    else:
+        st["tlev"] = S.get_interface_values(st["tlay"], st["tsfc"], p, pi)
+    return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in st.items()}
+
+
+def golden():
+    return np.load(GOLDEN)
+
+
+def rel_err(got, ref, floor=1e-3):
+    return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), floor)))
+
+
+# ---- host emulation of the kernel code (tests/emul/lw_emul.cpp) ---------------------------------
+def emul_lib():
+    so = os.path.join(HERE, "emul", "libcb_emul.so")
+    src = os.path.join(HERE, "emul", "lw_emul.cpp")
+    deps = [src] + [os.path.join(HERE, "..", "climt_b200", "csrc", f) for f in ("lw_core.cuh", "lw_tables.h", "cb_common.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def run_lw_emul(st, flags=(1, 0, 2, 1, 1)):
+    lib = emul_lib()
+    k = C.rrtmg_constants()
+    consts = np.array([k[n] for n in ("pi", "grav", "planck", "boltz", "clight", "avogad", "alosmt", "gascon",
+                                      "sbcnst", "secdy", "cpdair")])
+    nlay, ncol = st["play"].shape
+    inp = (_dp * 23)(*[st[f].ctypes.data_as(_dp) for f in SY.LW_FIELDS])
+    out = {n: np.zeros((nlay + 1, ncol)) for n in ("uflx", "dflx", "uflxc", "dflxc")}
+    out.update({n: np.zeros((nlay, ncol)) for n in ("hr", "hrc")})
+    outp = (_dp * 6)(*[out[n].ctypes.data_as(_dp) for n in ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc")])
+    rc = lib.emul_lw_run(RT.lw_blob_path().encode(), consts.ctypes.data_as(_dp), (ctypes.c_int * 5)(*flags),
+                         ncol, nlay, inp, outp)
+    return rc, out

@@ -1,0 +1,81 @@
+"""Host logic: the product's numpy table reduction vs the oracle's loop-by-loop C++ reduction, blob
+round trip, and the C-ABI library exporting every symbol include/climt_b200.h declares (no GPU calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers as H
+from climt_b200 import _native, rrtmg_tables as RT, tables as T
+
+
+def test_reduced_tables_match_oracle_reduction():
+    orc = H.lw_oracle()
+    red = RT.reduce_lw()
+    checked = 0
+    for ib in range(1, 17):
+        ng = int(RT.LW_NGC[ib - 1])
+        for name, arr in red.items():
+            if not name.startswith(f"b{ib:02d}."):
+                continue
+            short = name.split(".", 1)[1]
+            oname = {"absa": "ka", "absb": "kb"}.get(short, short)
+            o = orc.reduced(ib, oname)                     # Fortran order (lead, ng) or (ng, np) for fracref 2-D
+            if short.startswith("fracref") and arr.shape[0] > 1:
+                o = o.reshape(arr.shape[0], ng)            # (np, ng): Fortran (ng, np) memory == C (np, ng)
+            else:
+                o = o.reshape(ng, -1).T                    # (lead, ng)
+            assert o.shape == arr.shape, (name, o.shape, arr.shape)
+            np.testing.assert_allclose(arr, o, rtol=1e-15, atol=0)
+            checked += 1
+    assert checked > 100
+    assert sum(RT.LW_NGC) == 140
+
+
+def test_planck_fractions_sum_to_one():
+    red = RT.reduce_lw()
+    for ib in range(1, 17):
+        fa = red[f"b{ib:02d}.fracrefa"]
+        np.testing.assert_allclose(fa.sum(axis=-1), 1.0, atol=2e-4)
+
+
+def test_blob_round_trip(tmp_path):
+    arrs = {"a": np.arange(6.0).reshape(2, 3), "b.c": np.array([1.5])}
+    p = T.write_blob(arrs, str(tmp_path / "x.blob"), order="C")
+    raw = open(p, "rb").read()
+    assert raw[:8] == b"CB2TBL01"
+    n = int(np.frombuffer(raw[8:16], dtype="<i8")[0])
+    assert n == 2
+    data = np.frombuffer(raw[16 + n * 128:], dtype="<f8")
+    np.testing.assert_array_equal(data[:6], np.arange(6.0))
+
+
+def test_exp_table_quirk():
+    """float32 abscissa of the LW transmittance tables (rrtmg_lw_init.f90:114)."""
+    tau, ex, tfn = H.lw_oracle().exp_tables()
+    x = np.float64(np.float32(1234) / np.float32(10000))
+    assert tau[1234] == (1.0 / 0.278) * x / (1.0 - x)
+    assert ex[0] == 1.0 and ex[-1] == 1e-20 and tau[-1] == 1e10 and tfn[-1] == 1.0
+
+
+def test_library_exports_every_declared_symbol():
+    so = _native.build()
+    lib = ctypes.CDLL(so)
+    hdr = open(os.path.join(os.path.dirname(H.HERE), "include", "climt_b200.h")).read()
+    names = set(re.findall(r"\b((?:cb200|rrtmg)_\w+)\s*\(", hdr))
+    assert {"cb200_lw_create", "cb200_lw_run_device", "rrtmg_lw_nomcica_wrapper"} <= names
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/climt_b200.h but not exported"
+
+
+def test_product_does_not_import_oracle():
+    root = os.path.join(os.path.dirname(H.HERE), "climt_b200")
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert not re.search(r'#include\s+"[^"]*oracle/', txt), f
+                assert "liborc" not in txt, f
