@@ -127,3 +127,43 @@ def default_rrtmg_lw_state(nz, ncol=1, p_surf=None):
         "longwave_optical_thickness_due_to_aerosol": np.zeros((16, nz, ncol)),
     })
     return st
+
+
+def default_rrtmg_sw_state(nz, ncol=1, p_surf=None):
+    """Raw default state of RRTMGShortwave (SI units; initialization.py:173-233, 740-1030).
+    `time` = 2000-01-01 (get_grid :520) -> day of year 1."""
+    g = default_grid(nz, ncol, p_surf)
+    shp = (nz, ncol)
+    st = dict(g)
+    st.update({
+        "air_temperature": np.full(shp, 290.0),
+        "surface_temperature": np.full(ncol, 300.0),
+        "specific_humidity": np.zeros(shp),
+        "mole_fraction_of_ozone_in_air": init_ozone(g["air_pressure"]),
+        "mole_fraction_of_carbon_dioxide_in_air": np.full(shp, 330e-6),
+        "mole_fraction_of_methane_in_air": np.zeros(shp),
+        "mole_fraction_of_nitrous_oxide_in_air": np.zeros(shp),
+        "mole_fraction_of_oxygen_in_air": np.full(shp, 0.21),
+        "mass_content_of_cloud_ice_in_atmosphere_layer": np.zeros(shp),
+        "mass_content_of_cloud_liquid_water_in_atmosphere_layer": np.zeros(shp),
+        "cloud_ice_particle_size": np.full(shp, 20.0),
+        "cloud_water_droplet_radius": np.full(shp, 10.0),
+        "cloud_area_fraction_in_atmosphere_layer": np.zeros(shp),
+        "zenith_angle": np.zeros(ncol),
+        "surface_albedo_for_direct_shortwave": np.full(ncol, 0.06),
+        "surface_albedo_for_direct_near_infrared": np.full(ncol, 0.06),
+        "surface_albedo_for_diffuse_near_infrared": np.full(ncol, 0.06),
+        "surface_albedo_for_diffuse_shortwave": np.full(ncol, 0.06),
+        "shortwave_optical_thickness_due_to_cloud": np.zeros((nz, ncol, 14)),
+        "cloud_asymmetry_parameter": 0.85 * np.ones((nz, ncol, 14)),
+        "cloud_forward_scattering_fraction": 0.8 * np.ones((nz, ncol, 14)),
+        "single_scattering_albedo_due_to_cloud": 0.9 * np.ones((nz, ncol, 14)),
+        "shortwave_optical_thickness_due_to_aerosol": np.zeros((14, nz, ncol)),
+        "aerosol_asymmetry_parameter": np.zeros((14, nz, ncol)),
+        "single_scattering_albedo_due_to_aerosol": 0.5 * np.ones((14, nz, ncol)),
+        "aerosol_optical_depth_at_55_micron": np.zeros((6, nz, ncol)),
+        "solar_cycle_fraction": 0.0,
+        "flux_adjustment_for_earth_sun_distance": 1.0,
+        "day_of_year": 1,
+    })
+    return st

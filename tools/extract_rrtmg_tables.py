@@ -222,6 +222,12 @@ def main():
         params, decls = parse_modules(mpaths)
         out = {}
         extract([os.path.join(d, s) for s in srcs], decls, out)
+        if tag == "sw":
+            # rrtmg_sw_k_g.f90:62442,62460-62461 -- the only non-literal data statement: band 29's irradnceo is
+            # scaled in place by `irradscl`, declared default `real` (float32), so the factor is rounded to
+            # float32 before the multiplication.
+            irradscl = np.float64(np.float32(13.221 / (13.221 - 0.455)))
+            out["rrsw_kg29.irradnceo"] = irradscl * out["rrsw_kg29.irradnceo"]
         bad = [k for k, v in out.items() if v.dtype == np.float64 and np.isnan(v).any()]
         # arrays that are declared but only partly data-initialised are dropped
         # (e.g. reduced-g arrays filled by cmbgb at run time never appear here)
