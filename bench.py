@@ -3,8 +3,9 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step = one full evaluation of the workload's columns (all kernels of the path).  Default workload at
-N=1: BASELINE.json configs[1], "RRTMGLongwave clear-sky, 128x64 columns x 60 levels, fp64".
+A step = one full LW + SW evaluation of the workload's columns (all kernels of both paths).  Default workload at
+N=1: the grid of BASELINE.json configs[1] (128x64 columns x 60 levels, clear sky, fp64) evaluated with the metric's
+"RRTMG LW+SW"; the LW-only number (configs[1] verbatim) is reported next to it in `config`.
 `value` = columns/s with inputs resident in HBM (CUDA events, max over ranks); `e2e` = the same through the
 host-pointer C-ABI call (H2D of every input + D2H of every output inside the timed region).
 """
@@ -23,9 +24,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 NCOL, NLAY = 128 * 64, 60
-WORKLOAD = "RRTMGLongwave clear-sky, 128x64 columns x 60 levels, fp64 (BASELINE.json configs[1])"
-# RRTMG-LW reference ABI, every array the wrapper reads/writes, L=60
-ALG_BYTES_PER_COL = (49 * NLAY + 2 * (NLAY + 1) + 17 + 4 * (NLAY + 1) + 2 * NLAY) * 8
+WORKLOAD = "RRTMG LW+SW clear-sky, 128x64 columns x 60 levels, fp64 (grid of BASELINE.json configs[1])"
+# reference ABI, every array the wrappers read/write, L=60
+ALG_BYTES_LW = (49 * NLAY + 2 * (NLAY + 1) + 17 + 4 * (NLAY + 1) + 2 * NLAY) * 8
+ALG_BYTES_SW = (117 * NLAY + 2 * (NLAY + 1) + 6 + 4 * (NLAY + 1) + 2 * NLAY) * 8
 
 
 def measured_peaks():
@@ -70,17 +72,25 @@ def oracle_columns_per_s(st, threads, min_seconds=10.0, max_cols=None):
     import helpers as H
     from concurrent.futures import ThreadPoolExecutor
     orc = H.lw_oracle(cloud_overlap=1)
-    ncol = st["play"].shape[1]
+    orcs = H.sw_oracle()
+    lw, sw = st
+    ncol = lw["play"].shape[1]
     n = min(ncol, max_cols or ncol)
 
-    def take(lo, hi):
-        return {k: np.ascontiguousarray(v[..., lo:hi] if k != "taucld" else v[:, lo:hi, :]) for k, v in st.items()}
-    blocks = [take(i * n // threads, (i + 1) * n // threads) for i in range(threads)]
-    H.run_lw_oracle(orc, blocks[0])     # warm
+    def take(d, lo, hi):
+        return {k: np.ascontiguousarray(v[:, lo:hi, :] if (v.ndim == 3 and v.shape[-1] in (14, 16)) else v[..., lo:hi])
+                for k, v in d.items()}
+    blocks = [(take(lw, i * n // threads, (i + 1) * n // threads), take(sw, i * n // threads, (i + 1) * n // threads))
+              for i in range(threads)]
+
+    def one(b):
+        H.run_lw_oracle(orc, b[0])
+        orcs(b[1], adjes=1.0, dyofyr=1, solcycfrac=0.0)
+    one(blocks[0])     # warm
     reps, t0 = 0, time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
         while True:
-            list(ex.map(lambda b: H.run_lw_oracle(orc, b), blocks))
+            list(ex.map(one, blocks))
             reps += 1
             dt = time.perf_counter() - t0
             if dt >= min_seconds:
@@ -95,7 +105,7 @@ def reference_arm(args):
     if rank != 0:
         return
     from climt_b200 import synthetic as SY
-    st = SY.make_lw_state(NCOL, NLAY, seed=20260925)
+    st = (SY.make_lw_state(NCOL, NLAY, seed=20260925), SY.make_sw_state(NCOL, NLAY, seed=20260925))
     threads = os.cpu_count() or 1
     vals = []
     t_all = time.perf_counter()
@@ -105,7 +115,7 @@ def reference_arm(args):
             vals.append(v)
     value = float(np.mean(vals))
     print(json.dumps({
-        "impl": "reference", "metric": "RRTMG-LW columns/s (60 lev)", "value": value, "unit": "columns/s",
+        "impl": "reference", "metric": "RRTMG LW+SW columns/s (60 lev)", "value": value, "unit": "columns/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * 2048 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -131,7 +141,7 @@ def main():
     import torch
     import torch.distributed as dist
     from climt_b200 import synthetic as SY
-    from climt_b200.engine import LWEngine, LW_IN, LW_OUT, lw_shapes
+    from climt_b200.engine import LWEngine, SWEngine, LW_IN, LW_OUT, SW_IN, lw_shapes, sw_shapes
     import helpers as H
 
     rank = int(os.environ.get("RANK", "0"))
@@ -148,20 +158,27 @@ def main():
     # weak scaling: every rank owns NCOL columns of the global (world*NCOL)-column grid; no data-path
     # collective -- one all-gather reassembles the global flux / heating fields at the end of each step
     st = SY.make_lw_state(NCOL, NLAY, seed=20260925 + rank)
-    abi = H.to_abi(st)
+    sts = SY.make_sw_state(NCOL, NLAY, seed=20260925 + rank)
+    abi, abis = H.to_abi(st), H.to_abi_sw(sts)
     eng = LWEngine(device=local)
+    engs = SWEngine(device=local)
     ins, outs = lw_shapes(NCOL, NLAY)
     d_in = {k: torch.from_numpy(abi[k]).cuda() for k in LW_IN}
     d_out = {k: torch.empty(outs[k], dtype=torch.float64, device="cuda") for k in LW_OUT}
+    ds_in = {k: torch.from_numpy(abis[k]).cuda() for k in SW_IN}
+    ds_out = {k: torch.empty(outs[k], dtype=torch.float64, device="cuda") for k in LW_OUT}
     gathered = None
     if world > 1:
-        packed = torch.empty((4 * (NLAY + 1) + 2 * NLAY, NCOL), dtype=torch.float64, device="cuda")
+        packed = torch.empty((2 * (4 * (NLAY + 1) + 2 * NLAY), NCOL), dtype=torch.float64, device="cuda")
         gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.float64, device="cuda")
 
-    def step_device():
-        eng.run_device(NCOL, NLAY, d_in, d_out)
+    def step_device(lw=True, sw=True):
+        if lw:
+            eng.run_device(NCOL, NLAY, d_in, d_out)
+        if sw:
+            engs.run_device(NCOL, NLAY, ds_in, ds_out, dyofyr=1)
         if world > 1:
-            torch.cat([d_out[k] for k in LW_OUT], dim=0, out=packed)
+            torch.cat([d_out[k] for k in LW_OUT] + [ds_out[k] for k in LW_OUT], dim=0, out=packed)
             dist.all_gather_into_tensor(gathered, packed)
 
     def barrier():
@@ -183,61 +200,89 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     eng.check()
-    launches = eng.last_launches * K
-    # dominant kernel (g-point units) timed alone with CUDA events on its launch stream
+    engs.check()
+    launches = (eng.last_launches + engs.last_launches) * K
+    # LW-only and SW-only steps (explain the headline)
+    part_ms = {}
+    for name, kw in (("lw", dict(lw=True, sw=False)), ("sw", dict(lw=False, sw=True))):
+        barrier()
+        e0.record()
+        for _ in range(K):
+            step_device(**kw)
+        e1.record()
+        barrier()
+        part_ms[name] = e0.elapsed_time(e1) / K
+    # dominant kernels (g-point units) timed alone with CUDA events on their launch stream
     eng.enable_timing(True)
-    unit_ms = []
+    engs.enable_timing(True)
+    unit_ms, unit_ms_sw = [], []
     for _ in range(max(3, min(K, 10))):
         eng.run_device(NCOL, NLAY, d_in, d_out)
+        engs.run_device(NCOL, NLAY, ds_in, ds_out, dyofyr=1)
         torch.cuda.synchronize()
         unit_ms.append(eng.last_unit_kernel_ms)
+        unit_ms_sw.append(engs.last_unit_kernel_ms)
     eng.enable_timing(False)
-    unit_ms = float(np.mean(unit_ms))
+    engs.enable_timing(False)
+    unit_ms, unit_ms_sw = float(np.mean(unit_ms)), float(np.mean(unit_ms_sw))
 
     # e2e: host buffers in pinned memory through the host-pointer C ABI (H2D + kernels + D2H per step)
     pin_in = {k: torch.from_numpy(abi[k]).pin_memory() for k in LW_IN}
     pin_out = {k: torch.empty(outs[k], dtype=torch.float64).pin_memory() for k in LW_OUT}
+    pins_in = {k: torch.from_numpy(abis[k]).pin_memory() for k in SW_IN}
+    pins_out = {k: torch.empty(outs[k], dtype=torch.float64).pin_memory() for k in LW_OUT}
     np_in = {k: v.numpy() for k, v in pin_in.items()}
     np_out = {k: v.numpy() for k, v in pin_out.items()}
-    for _ in range(W):
+    nps_in = {k: v.numpy() for k, v in pins_in.items()}
+    nps_out = {k: v.numpy() for k, v in pins_out.items()}
+
+    def step_host():
         eng.run_host(NCOL, NLAY, np_in, np_out)
+        engs.run_host(NCOL, NLAY, nps_in, nps_out, dyofyr=1)
+    for _ in range(W):
+        step_host()
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        eng.run_host(NCOL, NLAY, np_in, np_out)
+        step_host()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    h2d = sum(v.numel() * 8 for v in pin_in.values())
-    d2h = sum(v.numel() * 8 for v in pin_out.values())
+    h2d = sum(v.numel() * 8 for v in pin_in.values()) + sum(v.numel() * 8 for v in pins_in.values())
+    d2h = sum(v.numel() * 8 for v in pin_out.values()) + sum(v.numel() * 8 for v in pins_out.values())
 
-    t = torch.tensor([ms, e2e_s * 1e3, unit_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_s * 1e3, unit_ms, unit_ms_sw, part_ms["lw"], part_ms["sw"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, unit_ms = [float(x) for x in t.tolist()]
+    ms, e2e_ms, unit_ms, unit_ms_sw, lw_ms, sw_ms = [float(x) for x in t.tolist()]
     if rank == 0:
         sampler.stop.set()
         sampler.join(timeout=2)
         peaks, which = measured_peaks()
         value = world * NCOL * K / (ms * 1e-3)
-        achieved = ALG_BYTES_PER_COL * NCOL / (unit_ms * 1e-3) / 1e9
+        dom = "k_sw_units" if unit_ms_sw >= unit_ms else "k_units(lw)"
+        dom_ms = max(unit_ms_sw, unit_ms)
+        dom_bytes = ALG_BYTES_SW if unit_ms_sw >= unit_ms else ALG_BYTES_LW
+        achieved = dom_bytes * NCOL / (dom_ms * 1e-3) / 1e9
         line = {
-            "metric": "RRTMG-LW columns/s (60 lev)", "value": value, "unit": "columns/s", "n_gpus": world,
+            "metric": "RRTMG LW+SW columns/s (60 lev)", "value": value, "unit": "columns/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "columns_per_gpu": NCOL, "levels": NLAY, "gpoints": 140,
-                       "cache": "working set per step (inputs 0.23 GB + per-g scratch 2.2 GB) exceeds the 126 MB L2",
+            "config": {"workload": WORKLOAD, "columns_per_gpu": NCOL, "levels": NLAY, "gpoints": "140 LW + 112 SW",
+                       "lw_only_columns_per_s": world * NCOL / (lw_ms * 1e-3), "sw_only_columns_per_s": world * NCOL / (sw_ms * 1e-3),
+                       "cache": "working set per step (inputs 0.7 GB + per-g scratch > 5 GB) exceeds the 126 MB L2",
                        "parallelism": f"columns block-sharded over {world} GPU(s), one all-gather of outputs"},
             "e2e": {"value": world * NCOL * K / (e2e_ms * 1e-3), "unit": "columns/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                         "kernel": "k_units", "kernel_ms": unit_ms, "alg_bytes_per_column": ALG_BYTES_PER_COL,
+                         "kernel": dom, "kernel_ms": dom_ms, "alg_bytes_per_column": dom_bytes,
+                         "lw_units_ms": unit_ms, "sw_units_ms": unit_ms_sw,
                          "note": "fp64-issue / gather-latency bound, not HBM bound (SURVEY.md 8d)"},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline and world == 1:
-            v, sample = oracle_columns_per_s(st, 1, min_seconds=10.0, max_cols=1024)
+            v, sample = oracle_columns_per_s((st, sts), 1, min_seconds=10.0, max_cols=512)
             line["cpu_baseline"] = {"value": v, "unit": "columns/s", "cores": 1, "kind": "port", "sample": sample}
         print(json.dumps(line))
     if world > 1:

@@ -11,8 +11,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libclimt_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lw_engine.cu",)]
-HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("cb_common.h", "lw_core.cuh", "lw_tables.h")] + [
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lw_engine.cu", "sw_engine.cu")]
+HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("cb_common.h", "engine_common.h", "lw_core.cuh", "lw_tables.h", "sw_core.cuh", "sw_tables.h")] + [
     os.path.join(_HERE, "..", "include", "climt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "--fmad=false"]
@@ -65,7 +65,18 @@ class LwOutputs(ctypes.Structure):
     _fields_ = [(n, _dp) for n in ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc")]
 
 
-EXPORTS = ["cb200_lw_create", "cb200_lw_destroy", "cb200_lw_set_options", "cb200_lw_run_device",
+class SwInputs(ctypes.Structure):
+    _fields_ = [(n, _dp) for n in (
+        "play", "plev", "tlay", "tlev", "tsfc", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "n2ovmr", "o2vmr",
+        "asdir", "asdif", "aldir", "aldif", "coszen", "cldfr", "taucld", "ssacld", "asmcld", "fsfcld",
+        "cicewp", "cliqwp", "reice", "reliq", "tauaer", "ssaaer", "asmaer", "ecaer")]
+
+
+EXPORTS = ["cb200_sw_create", "cb200_sw_destroy", "cb200_sw_set_options", "cb200_sw_set_solar", "cb200_sw_run_device",
+           "cb200_sw_run_host", "cb200_sw_check", "cb200_sw_last_error", "cb200_sw_last_launches",
+           "cb200_sw_enable_timing", "cb200_sw_last_unit_kernel_ms", "rrtmg_sw_set_constants", "rrtmg_sw_ini_wrapper",
+           "rrtmg_sw_nomcica_wrapper",
+           "cb200_lw_create", "cb200_lw_destroy", "cb200_lw_set_options", "cb200_lw_run_device",
            "cb200_lw_run_host", "cb200_lw_check", "cb200_lw_last_error", "cb200_global_error",
            "cb200_lw_last_launches", "cb200_lw_enable_timing", "cb200_lw_last_unit_kernel_ms",
            "rrtmg_set_constants", "rrtmg_lw_ini_wrapper", "rrtmg_lw_nomcica_wrapper"]
@@ -99,5 +110,21 @@ def lib():
     L.cb200_lw_enable_timing.argtypes = [vp, ctypes.c_int]
     L.cb200_lw_last_unit_kernel_ms.argtypes = [vp]
     L.cb200_lw_last_unit_kernel_ms.restype = ctypes.c_double
+    L.cb200_sw_create.argtypes = [ctypes.POINTER(vp), ctypes.c_char_p, _dp, ctypes.c_int]
+    L.cb200_sw_destroy.argtypes = [vp]
+    L.cb200_sw_destroy.restype = None
+    L.cb200_sw_set_options.argtypes = [vp] + [ctypes.c_int] * 5
+    L.cb200_sw_set_solar.argtypes = [vp, ctypes.c_int, ctypes.c_double, _dp, _dp]
+    L.cb200_sw_run_device.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double,
+                                      ctypes.POINTER(SwInputs), ctypes.POINTER(LwOutputs), vp]
+    L.cb200_sw_run_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double,
+                                    ctypes.POINTER(SwInputs), ctypes.POINTER(LwOutputs)]
+    L.cb200_sw_check.argtypes = [vp]
+    L.cb200_sw_last_error.argtypes = [vp]
+    L.cb200_sw_last_error.restype = ctypes.c_char_p
+    L.cb200_sw_last_launches.argtypes = [vp]
+    L.cb200_sw_enable_timing.argtypes = [vp, ctypes.c_int]
+    L.cb200_sw_last_unit_kernel_ms.argtypes = [vp]
+    L.cb200_sw_last_unit_kernel_ms.restype = ctypes.c_double
     _lib = L
     return L

@@ -9,13 +9,14 @@
 #include <vector>
 
 #include "../../include/climt_b200.h"
+#include "engine_common.h"
 #include "lw_tables.h"
 
 using namespace cb::lw;
 
 namespace {
 
-constexpr int kBlock = 128;
+using cb::kBlock;
 
 __global__ void __launch_bounds__(kBlock) k_prep(const __grid_constant__ Tables T, const __grid_constant__ In in,
                                                  const Flags fl, const __grid_constant__ Work W, int c0, int n) {
@@ -63,9 +64,6 @@ __global__ void __launch_bounds__(kBlock) k_heat(const __grid_constant__ Tables 
   const int l = blockIdx.y;
   if (c < n) lw_heating(T, in, out, c0 + c, l);
 }
-
-std::string g_error;
-std::mutex g_mu;
 
 #define CUDA_OK(call)                                                                         \
   do {                                                                                        \
@@ -127,7 +125,7 @@ struct cb200_lw_engine {
   }
 };
 
-extern "C" const char* cb200_global_error(void) { return g_error.c_str(); }
+extern "C" const char* cb200_global_error(void) { return cb::g_error.c_str(); }
 
 extern "C" int cb200_lw_create(cb200_lw_engine** out, const char* table_blob, const double constants[11], int device) {
   *out = nullptr;
@@ -151,8 +149,7 @@ extern "C" int cb200_lw_create(cb200_lw_engine** out, const char* table_blob, co
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
   } catch (std::exception& ex) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_error = ex.what();
+    cb::set_global_error(ex.what());
     delete e;
     return -1;
   }
@@ -181,7 +178,7 @@ extern "C" int cb200_lw_set_options(cb200_lw_engine* e, int icld, int idrv, int 
   return 0;
 }
 
-extern "C" const char* cb200_lw_last_error(cb200_lw_engine* e) { return e ? e->error.c_str() : g_error.c_str(); }
+extern "C" const char* cb200_lw_last_error(cb200_lw_engine* e) { return e ? e->error.c_str() : cb::g_error.c_str(); }
 extern "C" int cb200_lw_last_launches(cb200_lw_engine* e) { return e->launches; }
 extern "C" int cb200_lw_enable_timing(cb200_lw_engine* e, int on) { e->timing = on != 0; return 0; }
 extern "C" double cb200_lw_last_unit_kernel_ms(cb200_lw_engine* e) { return e->unit_ms; }

@@ -1,0 +1,832 @@
+// climt_b200 -- RRTMG shortwave engine, per-thread core (sm_100a device code; host-compilable for the
+// test-only emulation).  Same decomposition as the longwave engine (lw_core.cuh):
+//   sw_prep_column  one thread per column: inatm_sw + setcoef_sw + cldprop_sw (+ ECMWF aerosol mix)
+//   sw_unit<B,U>    one thread per (column, unit of <=4 g-points of band B): taumol_sw + delta-scaling + reftra_sw
+//                   fused with the upward adding pass of vrtqdr_sw (surface -> top), then the downward pass
+//                   (top -> surface) that turns the stored layer properties into fluxes.  Lanes = adjacent columns.
+//   sw_reduce       fixed-order sum of the per-unit partial fluxes, then heating rates.
+//
+// Reference being replaced: climt/_lib/rrtmg_sw/rrtmg_sw_rad.nomcica.f90 (driver, inatm_sw), rrtmg_sw_setcoef.f90,
+// rrtmg_sw_cldprop.f90, rrtmg_sw_taumol.f90, rrtmg_sw_spcvrt.f90, rrtmg_sw_reftra.f90, rrtmg_sw_vrtqdr.f90.
+#pragma once
+#include <cmath>
+
+#include "cb_common.h"
+
+namespace cb {
+namespace sw {
+
+constexpr int NBND = 14, NGPT = 112, NTBL = 10000;
+enum WsField {
+  F_FAC00 = 0, F_FAC01, F_FAC10, F_FAC11,
+  F_COLH2O, F_COLCO2, F_COLO3, F_COLCH4, F_COLO2, F_COLMOL,
+  F_SELFFAC, F_SELFFRAC, F_FORFAC, F_FORFRAC,
+  NF
+};
+constexpr int NSCR = 14;  // per g-point scratch rows: 7 (ref, refd, tra, trad, dbt, rup, rupd) x {clear, total}
+
+struct BandOff {
+  int absa, absb, selfref, forref, sfluxref, irradnce, facbrght, snsptdrk;
+  int raylv;   // per-g Rayleigh vector (bands 23, 25, 26, 27), rayla (band 24, (9, ng)) else -1
+  int raylb;   // band 24 upper
+  int x0, x1;  // absch4 | abso3a, abso3b | absco2, absh2o
+  double rayl; // scalar Rayleigh coefficient
+};
+struct Tables {
+  const double* base;
+  BandOff b[NBND];
+  int preflog, tref, exp_tbl;
+  int extliq1, ssaliq1, asyliq1, extice2, ssaice2, asyice2, extice3, ssaice3, asyice3, fdlice3;  // (n, 14)
+  int abari, bbari, cbari, dbari, ebari, fbari;
+  int rsrtaua, rsrpiza, rsrasya;  // (14, 6)
+  double bpade, heatfac, oneminus, avogad, grav;
+};
+// Column-independent part of inatm_sw (solar constant / variability, earth-sun distance): computed on the host.
+struct Solar {
+  int isolvar;
+  double adjflux[NBND];
+  double svar_f, svar_s, svar_i;
+  double svar_f_bnd[NBND], svar_s_bnd[NBND], svar_i_bnd[NBND];
+};
+struct In {  // reference ABI layout (rrtmg_sw_c_binder.f90:203-270)
+  int ncol, nlay;
+  const double *play, *plev, *tlay, *tlev, *tsfc, *h2o, *o3, *co2, *ch4, *n2o, *o2, *asdir, *asdif, *aldir, *aldif,
+      *coszen, *cldfr, *taucld, *ssacld, *asmcld, *fsfcld, *cicewp, *cliqwp, *reice, *reliq, *tauaer, *ssaaer, *asmaer,
+      *ecaer;
+};
+struct Out {
+  double *uflx, *dflx, *hr, *uflxc, *dflxc, *hrc;
+};
+struct Flags {
+  int icld, iaer, inflag, iceflag, liqflag;
+};
+struct Work {
+  int ncc;
+  double* ws;     // [NF][nlay][ncc]
+  int* idx;       // [nlay][ncc] packed jp|jt|jt1|indself|indfor
+  int* laytrop;   // [ncc]
+  int* laysolfr;  // [14][ncc]   1-based layer that provides the solar source function of each band
+  int* anycld;    // [ncc]
+  double* cld;    // [3][14][nlay][ncc]  delta-scaled cloud tau, ssa, asym
+  double* aer;    // [3][14][nlay][ncc]  aerosol tau, ssa, asym (iaer = 6 only)
+  double* scr;    // [112][NSCR][nlay][ncc]
+  double* part;   // [nunits][4][nlay+1][ncc]   fu, fd, cu, cd  (already weighted by the incoming flux)
+  int* err;
+};
+
+CB_HD int pack_idx(int jp, int jt, int jt1, int inds, int indf) { return jp | (jt << 6) | (jt1 << 9) | (inds << 12) | (indf << 16); }
+
+constexpr int kNG[14] = {6, 12, 8, 8, 10, 10, 2, 10, 8, 6, 6, 8, 6, 12};
+constexpr int kGS[14] = {0, 6, 18, 26, 34, 44, 54, 56, 66, 74, 80, 86, 94, 100};
+constexpr int kNSPA[14] = {9, 9, 9, 9, 1, 9, 9, 1, 9, 1, 0, 1, 9, 1};
+constexpr int kNSPB[14] = {1, 5, 1, 1, 1, 5, 1, 0, 1, 0, 0, 1, 5, 1};
+
+// ---------------------------------------------------------------------------------------------
+// sw_prep_column: inatm_sw (rrtmg_sw_rad.nomcica.f90:1414-1537), setcoef_sw (rrtmg_sw_setcoef.f90:49-305),
+// cldprop_sw (rrtmg_sw_cldprop.f90:53-365), ECMWF aerosol mix (rad.nomcica.f90:693-727), and the layer that supplies
+// each band's solar source (the `laysolfr` logic of rrtmg_sw_taumol.f90, e.g. :334-337 and :586-590).
+CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const Work& W, int c0, int c) {
+  const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
+  const size_t gc = (size_t)(c0 + c);
+  const double* tb = T.base;
+  const double amd = 28.9660, amw = 18.0160;
+  const double stpfac = 296. / 1013.;
+  const bool clouds = fl.icld >= 1;
+  int laytrop = 0;
+  bool anycld = false;
+  double pz_below = in.plev[gc];
+  // cldprop_sw locals persist across layers like the Fortran routine-locals
+  double extcoice[14], gice[14], ssacoice[14], forwice[14], extcoliq[14], gliq[14], ssacoliq[14], forwliq[14];
+  for (int i = 0; i < 14; ++i) { extcoice[i] = gice[i] = ssacoice[i] = forwice[i] = extcoliq[i] = gliq[i] = ssacoliq[i] = forwliq[i] = 0.; }
+#define WS(f, l) W.ws[((size_t)(f) * nlay + (l)) * ncc + c]
+  for (int l = 0; l < nlay; ++l) {
+    const size_t o = (size_t)l * ncol + gc;
+    const double pavel = in.play[o], tavel = in.tlay[o];
+    const double pz = in.plev[o + ncol];
+    double wkl[7];
+    wkl[0] = in.h2o[o]; wkl[1] = in.co2[o]; wkl[2] = in.o3[o]; wkl[3] = in.n2o[o]; wkl[4] = 0.; wkl[5] = in.ch4[o]; wkl[6] = in.o2[o];
+    const double amm = (1. - wkl[0]) * amd + wkl[0] * amw;
+    const double coldry = (pz_below - pz) * 1.e3 * T.avogad / (1.e2 * T.grav * amm * (1. + wkl[0]));
+    pz_below = pz;
+    for (int i = 0; i < 7; ++i) wkl[i] = coldry * wkl[i];
+    const double plog = log(pavel);
+    int jp = (int)(36. - 5 * (plog + 0.04));
+    if (jp < 1) jp = 1; else if (jp > 58) jp = 58;
+    const double fp = 5. * (tb[T.preflog + jp - 1] - plog);
+    const double tr0 = tb[T.tref + jp - 1], tr1 = tb[T.tref + jp];
+    int jt = (int)(3. + (tavel - tr0) / 15.);
+    if (jt < 1) jt = 1; else if (jt > 4) jt = 4;
+    const double ft = ((tavel - tr0) / 15.) - (double)(jt - 3);
+    int jt1 = (int)(3. + (tavel - tr1) / 15.);
+    if (jt1 < 1) jt1 = 1; else if (jt1 > 4) jt1 = 4;
+    const double ft1 = ((tavel - tr1) / 15.) - (double)(jt1 - 3);
+    const double water = wkl[0] / coldry;
+    const double scalefac = pavel * stpfac / tavel;
+    const double forfac = scalefac / (1. + water);
+    double forfrac, selffac = 0., selffrac = 0., factor;
+    int indfor, indself = 0;
+    const bool lower = !(plog <= 4.56);
+    if (lower) {
+      laytrop = laytrop + 1;
+      factor = (332.0 - tavel) / 36.0;
+      indfor = imin(2, imax(1, (int)factor));
+      forfrac = factor - (double)indfor;
+      selffac = water * forfac;
+      factor = (tavel - 188.0) / 7.2;
+      indself = imin(9, imax(1, (int)factor - 7));
+      selffrac = factor - (double)(indself + 7);
+    } else {
+      factor = (tavel - 188.0) / 36.0;
+      indfor = 3;
+      forfrac = factor - 1.0;
+    }
+    const double colh2o = 1.e-20 * wkl[0];
+    double colco2 = 1.e-20 * wkl[1];
+    const double colo3 = 1.e-20 * wkl[2];
+    double colch4 = 1.e-20 * wkl[5], colo2 = 1.e-20 * wkl[6];
+    const double colmol = 1.e-20 * coldry + colh2o;
+    if (colco2 == 0.) colco2 = 1.e-32 * coldry;
+    if (colch4 == 0.) colch4 = 1.e-32 * coldry;
+    if (colo2 == 0.) colo2 = 1.e-32 * coldry;
+    const double compfp = 1. - fp;
+    WS(F_FAC10, l) = compfp * ft;
+    WS(F_FAC00, l) = compfp * (1. - ft);
+    WS(F_FAC11, l) = fp * ft1;
+    WS(F_FAC01, l) = fp * (1. - ft1);
+    WS(F_COLH2O, l) = colh2o; WS(F_COLCO2, l) = colco2; WS(F_COLO3, l) = colo3; WS(F_COLCH4, l) = colch4;
+    WS(F_COLO2, l) = colo2; WS(F_COLMOL, l) = colmol;
+    WS(F_SELFFAC, l) = selffac; WS(F_SELFFRAC, l) = selffrac; WS(F_FORFAC, l) = forfac; WS(F_FORFRAC, l) = forfrac;
+    W.idx[(size_t)l * ncc + c] = pack_idx(jp, jt, jt1, indself, indfor);
+    // ---- cloud optics
+    if (clouds) {
+      const double eps = 1.e-06, cldmin = 1.e-20;
+      const double cldfrac = in.cldfr[o];
+      if (cldfrac > 1.e-06 && cldfrac < T.oneminus) *W.err = 10;  // 'PARTIAL CLOUD NOT ALLOWED' (rad.nomcica.f90:616-620)
+      const double ciwp = in.cicewp[o], clwp = in.cliqwp[o];
+      const double* tc = in.taucld + 14 * ((size_t)l * ncol + gc);
+      const double* sc = in.ssacld + 14 * ((size_t)l * ncol + gc);
+      const double* ac = in.asmcld + 14 * ((size_t)l * ncol + gc);
+      const double* fc = in.fsfcld + 14 * ((size_t)l * ncol + gc);
+      double tauctot = 0.;
+      for (int ib = 0; ib < 14; ++ib) tauctot = tauctot + tc[ib];
+      double taucloud[14], ssacloud[14], asmcloud[14];
+      for (int ib = 0; ib < 14; ++ib) { taucloud[ib] = 0.; ssacloud[ib] = 1.; asmcloud[ib] = 0.; }
+      const double cwp = ciwp + clwp;
+      if (cldfrac >= cldmin && (cwp >= cldmin || tauctot >= cldmin)) {
+        if (fl.inflag == 0) {
+          for (int ib = 0; ib < 14; ++ib) {
+            const double ffp = fc[ib], ffp1 = 1.0 - ffp, ffpssa = 1.0 - ffp * sc[ib];
+            ssacloud[ib] = ffp1 * sc[ib] / ffpssa;
+            taucloud[ib] = ffpssa * tc[ib];
+            asmcloud[ib] = (ac[ib] - ffp) / (ffp1);
+          }
+        } else if (fl.inflag == 2) {
+          const double radice = in.reice[o];
+          if (ciwp == 0.0) {
+            for (int ib = 0; ib < 14; ++ib) { extcoice[ib] = 0.; ssacoice[ib] = 0.; gice[ib] = 0.; forwice[ib] = 0.; }
+          } else if (fl.iceflag == 1) {
+            if (radice < 13.0 || radice > 130.) { *W.err = 2; }
+            else {
+              const double wavenum2[14] = {3250., 4000., 4650., 5150., 6150., 7700., 8050., 12850., 16000., 22650., 29000., 38000., 50000., 2600.};
+              for (int ib = 0; ib < 14; ++ib) {
+                int icx = 5;
+                if (wavenum2[ib] > 1.43e04) icx = 1;
+                else if (wavenum2[ib] > 7.7e03) icx = 2;
+                else if (wavenum2[ib] > 5.3e03) icx = 3;
+                else if (wavenum2[ib] > 4.0e03) icx = 4;
+                extcoice[ib] = tb[T.abari + icx - 1] + tb[T.bbari + icx - 1] / radice;
+                ssacoice[ib] = 1. - tb[T.cbari + icx - 1] - tb[T.dbari + icx - 1] * radice;
+                gice[ib] = tb[T.ebari + icx - 1] + tb[T.fbari + icx - 1] * radice;
+                if (gice[ib] >= 1.0) gice[ib] = 1.0 - eps;
+                forwice[ib] = gice[ib] * gice[ib];
+                if (extcoice[ib] < 0.0 || ssacoice[ib] > 1.0 || ssacoice[ib] < 0.0 || gice[ib] > 1.0 || gice[ib] < 0.0) *W.err = 5;
+              }
+            }
+          } else if (fl.iceflag == 2 || fl.iceflag == 3) {
+            const double rmax = fl.iceflag == 2 ? 131.0 : 140.0;
+            if (radice < 5.0 || radice > rmax) { *W.err = fl.iceflag == 2 ? 2 : 3; }
+            else {
+              factor = (radice - 2.) / 3.;
+              int index = (int)factor;
+              const int top = fl.iceflag == 2 ? 43 : 46;
+              if (index == top) index = top - 1;
+              const double fint = factor - (double)index;
+              const int te = fl.iceflag == 2 ? T.extice2 : T.extice3, tsa = fl.iceflag == 2 ? T.ssaice2 : T.ssaice3,
+                        tg = fl.iceflag == 2 ? T.asyice2 : T.asyice3;
+              for (int ib = 0; ib < 14; ++ib) {
+                const size_t r0 = (size_t)(index - 1) * 14 + ib, r1 = (size_t)index * 14 + ib;
+                extcoice[ib] = tb[te + r0] + fint * (tb[te + r1] - tb[te + r0]);
+                ssacoice[ib] = tb[tsa + r0] + fint * (tb[tsa + r1] - tb[tsa + r0]);
+                gice[ib] = tb[tg + r0] + fint * (tb[tg + r1] - tb[tg + r0]);
+                if (fl.iceflag == 2) {
+                  forwice[ib] = gice[ib] * gice[ib];
+                } else {
+                  const double fdelta = tb[T.fdlice3 + r0] + fint * (tb[T.fdlice3 + r1] - tb[T.fdlice3 + r0]);
+                  if (fdelta < 0.0 || fdelta > 1.0) *W.err = 6;
+                  forwice[ib] = fdelta + 0.5 / ssacoice[ib];
+                  if (forwice[ib] > gice[ib]) forwice[ib] = gice[ib];
+                }
+                if (extcoice[ib] < 0.0 || ssacoice[ib] > 1.0 || ssacoice[ib] < 0.0 || gice[ib] > 1.0 || gice[ib] < 0.0) *W.err = 5;
+              }
+            }
+          }
+          if (clwp == 0.0) {
+            for (int ib = 0; ib < 14; ++ib) { extcoliq[ib] = 0.; ssacoliq[ib] = 0.; gliq[ib] = 0.; forwliq[ib] = 0.; }
+          } else if (fl.liqflag == 1) {
+            const double radliq = in.reliq[o];
+            if (radliq < 2.5 || radliq > 60.) { *W.err = 4; }
+            else {
+              int index = (int)(radliq - 1.5);
+              if (index == 0) index = 1;
+              if (index == 58) index = 57;
+              const double fint = radliq - 1.5 - (double)index;
+              for (int ib = 0; ib < 14; ++ib) {
+                const size_t r0 = (size_t)(index - 1) * 14 + ib, r1 = (size_t)index * 14 + ib;
+                extcoliq[ib] = tb[T.extliq1 + r0] + fint * (tb[T.extliq1 + r1] - tb[T.extliq1 + r0]);
+                ssacoliq[ib] = tb[T.ssaliq1 + r0] + fint * (tb[T.ssaliq1 + r1] - tb[T.ssaliq1 + r0]);
+                if (fint < 0. && ssacoliq[ib] > 1.) ssacoliq[ib] = tb[T.ssaliq1 + r0];
+                gliq[ib] = tb[T.asyliq1 + r0] + fint * (tb[T.asyliq1 + r1] - tb[T.asyliq1 + r0]);
+                forwliq[ib] = gliq[ib] * gliq[ib];
+                if (extcoliq[ib] < 0.0 || ssacoliq[ib] > 1.0 || ssacoliq[ib] < 0.0 || gliq[ib] > 1.0 || gliq[ib] < 0.0) *W.err = 7;
+              }
+            }
+          }
+          for (int ib = 0; ib < 14; ++ib) {
+            const double tauliqorig = clwp * extcoliq[ib], tauiceorig = ciwp * extcoice[ib];
+            const double ssaliq = ssacoliq[ib] * (1.0 - forwliq[ib]) / (1.0 - forwliq[ib] * ssacoliq[ib]);
+            const double tauliq = (1.0 - forwliq[ib] * ssacoliq[ib]) * tauliqorig;
+            const double ssaice = ssacoice[ib] * (1.0 - forwice[ib]) / (1.0 - forwice[ib] * ssacoice[ib]);
+            const double tauice = (1.0 - forwice[ib] * ssacoice[ib]) * tauiceorig;
+            const double scatliq = ssaliq * tauliq;
+            double scatice = ssaice * tauice;
+            taucloud[ib] = tauliq + tauice;
+            if (taucloud[ib] == 0.0) taucloud[ib] = cldmin;
+            if (scatice == 0.0) scatice = cldmin;
+            ssacloud[ib] = (scatliq + scatice) / taucloud[ib];
+            if (fl.iceflag == 3) {
+              asmcloud[ib] = (1.0 / (scatliq + scatice)) * (scatliq * (gliq[ib] - forwliq[ib]) / (1.0 - forwliq[ib]) +
+                                                           scatice * ((gice[ib] - forwice[ib]) / (1.0 - forwice[ib])));
+            } else {
+              asmcloud[ib] = (scatliq * (gliq[ib] - forwliq[ib]) / (1.0 - forwliq[ib]) +
+                              scatice * (gice[ib] - forwice[ib]) / (1.0 - forwice[ib])) / (scatliq + scatice);
+            }
+          }
+        }
+      }
+      if (cldfrac > 1.e-12) anycld = true;
+      for (int ib = 0; ib < 14; ++ib) {
+        W.cld[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c] = taucloud[ib];
+        W.cld[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c] = ssacloud[ib];
+        W.cld[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c] = asmcloud[ib];
+      }
+    }
+    // ---- ECMWF aerosols (iaer = 6), rad.nomcica.f90:693-727
+    if (fl.iaer == 6) {
+      for (int ib = 0; ib < 14; ++ib) {
+        double ta = 0., om = 0., as = 0.;
+        for (int ia = 0; ia < 6; ++ia) {
+          const double ec = in.ecaer[((size_t)ia * nlay + l) * ncol + gc];
+          const double rt = tb[T.rsrtaua + ib * 6 + ia], rp = tb[T.rsrpiza + ib * 6 + ia], ra = tb[T.rsrasya + ib * 6 + ia];
+          ta = ta + rt * ec;
+          om = om + rt * ec * rp;
+          as = as + rt * ec * rp * ra;
+        }
+        if (ta == 0.) { ta = 0.; as = 0.; om = 1.; }
+        else {
+          if (om != 0.) as = as / om;
+          if (ta != 0.) om = om / ta;
+        }
+        W.aer[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c] = ta;
+        W.aer[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c] = om;
+        W.aer[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c] = as;
+      }
+    }
+  }
+#undef WS
+  W.laytrop[c] = laytrop;
+  W.anycld[c] = (clouds && anycld) ? 1 : 0;
+  // Layer whose key-species ratio selects each band's solar source function.  The Fortran updates `laysolfr`
+  // while looping over layers and assigns the source when `lay == laysolfr`; the last assignment wins
+  // (lower-atmosphere form e.g. taumol18 :586-590, upper form e.g. taumol16 :334-337; band 26 :1455 has no trigger).
+  {
+    const int layreffr[14] = {18, 30, 6, 3, 3, 8, 2, 6, 1, 2, 0, 32, 58, 49};
+    const bool lower_src[14] = {false, false, true, true, true, true, true, true, true, true, true, false, false, false};
+    for (int b = 0; b < 14; ++b) {
+      int ls;
+      if (lower_src[b]) {
+        ls = laytrop;
+        for (int lay = 1; lay <= laytrop; ++lay) {
+          const int jp0 = W.idx[(size_t)(lay - 1) * ncc + c] & 63;
+          const int jp1 = lay < nlay ? (W.idx[(size_t)lay * ncc + c] & 63) : 0;
+          if (b != 10 && jp0 < layreffr[b] && jp1 >= layreffr[b]) ls = imin(lay + 1, laytrop);
+        }
+      } else {
+        ls = nlay;
+        for (int lay = laytrop + 1; lay <= nlay; ++lay) {
+          const int jpm = lay >= 2 ? (W.idx[(size_t)(lay - 2) * ncc + c] & 63) : 0;
+          const int jp0 = W.idx[(size_t)(lay - 1) * ncc + c] & 63;
+          if (jpm < layreffr[b] && jp0 >= layreffr[b]) ls = lay;
+        }
+      }
+      W.laysolfr[(size_t)b * ncc + c] = ls;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Band descriptions (rrtmg_sw_taumol.f90: taumol16 :275-389 ... taumol29 :1695-1787).
+enum Gas { H2O = 0, CO2 = 1, O3 = 2, CH4 = 3, O2 = 4 };  // F_COLH2O + id
+enum Extra { X_NONE, X_CH4, X_O2CONT, X_O3, X_CO2, X_H2O };
+enum RaylKind { RAY_SCALAR, RAY_VEC, RAY_A_INTERP, RAY_B };
+struct Region {
+  int kind;        // 0 none, 1 one key species, 2 two key species
+  int a, b;
+  double strrat;   // binary ratio (band 22: o2adj*strrat)
+  double keyscale; // band 23: givfac on the key term; band 22 upper: o2adj
+  bool self, forn;
+  bool inside;     // self/foreign continuum inside the colh2o*( ) bracket together with the key term
+  int extra;       // additional absorber
+  int xslot;       // BandOff x0/x1
+  int rayl;
+};
+constexpr Region mk(int kind, int a, int b, double strrat, double keyscale, bool self, bool forn, bool inside, int extra,
+                    int xslot, int rayl) {
+  return {kind, a, b, strrat, keyscale, self, forn, inside, extra, xslot, rayl};
+}
+template <int B, bool LOWER>
+constexpr Region region() {
+  // B = 16..29
+  return B == 16 ? (LOWER ? mk(2, H2O, CH4, 252.131, 1., true, true, false, X_NONE, 0, RAY_SCALAR)
+                          : mk(1, CH4, 0, 0., 1., false, false, false, X_NONE, 0, RAY_SCALAR))
+       : B == 17 ? (LOWER ? mk(2, H2O, CO2, 0.364641, 1., true, true, false, X_NONE, 0, RAY_SCALAR)
+                          : mk(2, H2O, CO2, 0.364641, 1., false, true, false, X_NONE, 0, RAY_SCALAR))
+       : B == 18 ? (LOWER ? mk(2, H2O, CH4, 38.9589, 1., true, true, false, X_NONE, 0, RAY_SCALAR)
+                          : mk(1, CH4, 0, 0., 1., false, false, false, X_NONE, 0, RAY_SCALAR))
+       : B == 19 ? (LOWER ? mk(2, H2O, CO2, 5.49281, 1., true, true, false, X_NONE, 0, RAY_SCALAR)
+                          : mk(1, CO2, 0, 0., 1., false, false, false, X_NONE, 0, RAY_SCALAR))
+       : B == 20 ? (LOWER ? mk(1, H2O, 0, 0., 1., true, true, true, X_CH4, 0, RAY_SCALAR)
+                          : mk(1, H2O, 0, 0., 1., false, true, true, X_CH4, 0, RAY_SCALAR))
+       : B == 21 ? (LOWER ? mk(2, H2O, CO2, 0.0045321, 1., true, true, false, X_NONE, 0, RAY_SCALAR)
+                          : mk(2, H2O, CO2, 0.0045321, 1., false, true, false, X_NONE, 0, RAY_SCALAR))
+       : B == 22 ? (LOWER ? mk(2, H2O, O2, 1.6 * 0.022708, 1., true, true, false, X_O2CONT, 0, RAY_SCALAR)
+                          : mk(1, O2, 0, 0., 1.6, false, false, false, X_O2CONT, 0, RAY_SCALAR))
+       : B == 23 ? (LOWER ? mk(1, H2O, 0, 0., 1.029, true, true, true, X_NONE, 0, RAY_VEC)
+                          : mk(0, 0, 0, 0., 1., false, false, false, X_NONE, 0, RAY_VEC))
+       : B == 24 ? (LOWER ? mk(2, H2O, O2, 0.124692, 1., true, true, false, X_O3, 0, RAY_A_INTERP)
+                          : mk(1, O2, 0, 0., 1., false, false, false, X_O3, 1, RAY_B))
+       : B == 25 ? (LOWER ? mk(1, H2O, 0, 0., 1., false, false, false, X_O3, 0, RAY_VEC)
+                          : mk(0, 0, 0, 0., 1., false, false, false, X_O3, 1, RAY_VEC))
+       : B == 26 ? mk(0, 0, 0, 0., 1., false, false, false, X_NONE, 0, RAY_VEC)
+       : B == 27 ? mk(1, O3, 0, 0., 1., false, false, false, X_NONE, 0, RAY_VEC)
+       : B == 28 ? mk(2, O3, O2, 6.67029e-07, 1., false, false, false, X_NONE, 0, RAY_SCALAR)
+       :           (LOWER ? mk(1, H2O, 0, 0., 1., true, true, true, X_CO2, 0, RAY_SCALAR)
+                          : mk(1, CO2, 0, 0., 1., false, false, false, X_H2O, 1, RAY_SCALAR));
+}
+// does the band's solar source depend on the key-species ratio at layer laysolfr?
+template <int B> constexpr bool src_interp() { return B == 17 || B == 18 || B == 19 || B == 21 || B == 22 || B == 24 || B == 28; }
+template <int B> constexpr bool src_lower() { return B >= 18 && B <= 26; }
+
+// Optical depths (gas, Rayleigh) for U consecutive g-points of band B in one layer; optionally the solar source.
+template <int B, bool LOWER, int U>
+CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstride, int idx, int g0,
+                     double* __restrict__ taug, double* __restrict__ taur, bool want_src, const Solar& sol,
+                     double* __restrict__ src) {
+  constexpr Region R = region<B, LOWER>();
+  constexpr int ib = B - 16;
+  constexpr int ng = kNG[ib];
+  const BandOff& O = T.b[ib];
+  const double* __restrict__ tb = T.base;
+#define WSF(f) CB_LDG(ws + (size_t)(f) * wstride)
+  const int jp = idx & 63, jt = (idx >> 6) & 7, jt1 = (idx >> 9) & 7, inds = (idx >> 12) & 15, indf = (idx >> 16) & 3;
+  double acc[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) acc[u] = 0.;
+  const double colh2o = WSF(F_COLH2O);
+  int js = 0;
+  double fs = 0.;
+  // water-vapour continua (SW: un-premultiplied selffac/forfac, rrtmg_sw_setcoef.f90:232,238)
+  double cont[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) cont[u] = 0.;
+  if (R.self || R.forn) {
+    const double forfac = WSF(F_FORFAC), forfrac = WSF(F_FORFRAC);
+    const double* __restrict__ f = tb + O.forref + (size_t)(indf - 1) * ng + g0;
+    if (R.self) {
+      const double selffac = WSF(F_SELFFAC), selffrac = WSF(F_SELFFRAC);
+      const double* __restrict__ s = tb + O.selfref + (size_t)(inds - 1) * ng + g0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double s0 = CB_LDG(s + u), s1 = CB_LDG(s + ng + u), f0 = CB_LDG(f + u), f1 = CB_LDG(f + ng + u);
+        cont[u] = selffac * (s0 + selffrac * (s1 - s0)) + forfac * (f0 + forfrac * (f1 - f0));
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double f0 = CB_LDG(f + u), f1 = CB_LDG(f + ng + u);
+        cont[u] = forfac * (f0 + forfrac * (f1 - f0));
+      }
+    }
+  }
+  if (R.kind == 2) {
+    const double fac00 = WSF(F_FAC00), fac01 = WSF(F_FAC01), fac10 = WSF(F_FAC10), fac11 = WSF(F_FAC11);
+    constexpr double n = LOWER ? 8. : 4.;
+    constexpr int nsp = LOWER ? 9 : 5;
+    const double cola = WSF(F_COLH2O + R.a), colb = WSF(F_COLH2O + R.b);
+    const double speccomb = cola + R.strrat * colb;
+    double specparm = cola / speccomb;
+    if (specparm >= T.oneminus) specparm = T.oneminus;
+    const double specmult = n * specparm;
+    js = 1 + (int)specmult;
+    fs = fmod(specmult, 1.);
+    const double f000 = (1. - fs) * fac00, f010 = (1. - fs) * fac10, f100 = fs * fac00, f110 = fs * fac10;
+    const double f001 = (1. - fs) * fac01, f011 = (1. - fs) * fac11, f101 = fs * fac01, f111 = fs * fac11;
+    const int row0 = (LOWER ? ((jp - 1) * 5 + (jt - 1)) * nsp : ((jp - 13) * 5 + (jt - 1)) * nsp) + js - 1;
+    const int row1 = (LOWER ? (jp * 5 + (jt1 - 1)) * nsp : ((jp - 12) * 5 + (jt1 - 1)) * nsp) + js - 1;
+    const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
+    const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double d = f000 * CB_LDG(a0 + u);
+      d = d + f100 * CB_LDG(a0 + ng + u);
+      d = d + f010 * CB_LDG(a0 + nsp * ng + u);
+      d = d + f110 * CB_LDG(a0 + (nsp + 1) * ng + u);
+      d = d + f001 * CB_LDG(a1 + u);
+      d = d + f101 * CB_LDG(a1 + ng + u);
+      d = d + f011 * CB_LDG(a1 + nsp * ng + u);
+      d = d + f111 * CB_LDG(a1 + (nsp + 1) * ng + u);
+      acc[u] = speccomb * d;
+      if (R.self || R.forn) acc[u] = acc[u] + colh2o * cont[u];
+    }
+  } else if (R.kind == 1) {
+    const double fac00 = WSF(F_FAC00), fac01 = WSF(F_FAC01), fac10 = WSF(F_FAC10), fac11 = WSF(F_FAC11);
+    constexpr int nsp = LOWER ? kNSPA[ib] : kNSPB[ib];
+    const int row0 = LOWER ? ((jp - 1) * 5 + (jt - 1)) * nsp : ((jp - 13) * 5 + (jt - 1)) * nsp;
+    const int row1 = LOWER ? (jp * 5 + (jt1 - 1)) * nsp : ((jp - 12) * 5 + (jt1 - 1)) * nsp;
+    const double cola = WSF(F_COLH2O + R.a);
+    const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
+    const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double k4 = fac00 * CB_LDG(a0 + u) + fac10 * CB_LDG(a0 + ng + u) + fac01 * CB_LDG(a1 + u) + fac11 * CB_LDG(a1 + ng + u);
+      if (R.inside) {
+        // e.g. taumol20 :830-842 / taumol23 :1179-1189 / taumol29 :1735-1746 ; upper 20: :857-866
+        if (R.keyscale != 1.) acc[u] = cola * (R.keyscale * k4 + cont[u]);
+        else acc[u] = cola * (k4 + cont[u]);
+      } else {
+        acc[u] = (R.keyscale != 1.) ? cola * R.keyscale * k4 : cola * k4;
+      }
+    }
+  }
+  // additional absorbers
+  if (R.extra == X_CH4 || R.extra == X_O3 || R.extra == X_CO2 || R.extra == X_H2O) {
+    const int gas = R.extra == X_CH4 ? CH4 : (R.extra == X_O3 ? O3 : (R.extra == X_CO2 ? CO2 : H2O));
+    const double colx = WSF(F_COLH2O + gas);
+    const double* __restrict__ x = tb + (R.xslot == 0 ? O.x0 : O.x1) + g0;
+    if (B == 24 && LOWER) {
+      // taumol24 :1262-1276: speccomb*(major) + colo3*abso3a + colh2o*(self+for): order differs only in association
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] = acc[u] + colx * CB_LDG(x + u);
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] = acc[u] + colx * CB_LDG(x + u);
+    }
+  } else if (R.extra == X_O2CONT) {
+    const double o2cont = 4.35e-4 * WSF(F_COLO2) / (350.0 * 2.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = acc[u] + o2cont;
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) taug[u] = acc[u];
+  // Rayleigh
+  const double colmol = WSF(F_COLMOL);
+  if (R.rayl == RAY_SCALAR) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) taur[u] = colmol * O.rayl;
+  } else if (R.rayl == RAY_VEC) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) taur[u] = colmol * CB_LDG(tb + O.raylv + g0 + u);
+  } else if (R.rayl == RAY_B) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) taur[u] = colmol * CB_LDG(tb + O.raylb + g0 + u);
+  } else {
+    const double* __restrict__ r = tb + O.raylv + (size_t)(js - 1) * ng + g0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double r0 = CB_LDG(r + u), r1 = CB_LDG(r + ng + u);
+      taur[u] = colmol * (r0 + fs * (r1 - r0));
+    }
+  }
+  // solar source function at this layer (only evaluated at layer laysolfr)
+  if (want_src) {
+    constexpr bool interp = src_interp<B>();
+    auto val = [&](int off, int u) {
+      if (interp) {
+        const double* __restrict__ t = tb + off + (size_t)(js - 1) * ng + g0 + u;
+        const double v0 = CB_LDG(t), v1 = CB_LDG(t + ng);
+        return v0 + fs * (v1 - v0);
+      }
+      return CB_LDG(tb + off + g0 + u);
+    };
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (sol.isolvar < 0) {
+        src[u] = (B == 27) ? (50.15 / 48.37) * val(O.sfluxref, u) : val(O.sfluxref, u);
+      } else if (sol.isolvar <= 2) {
+        src[u] = sol.svar_f * val(O.facbrght, u) + sol.svar_s * val(O.snsptdrk, u) + sol.svar_i * val(O.irradnce, u);
+      } else {
+        src[u] = sol.svar_f_bnd[ib] * val(O.facbrght, u) + sol.svar_s_bnd[ib] * val(O.snsptdrk, u) +
+                 sol.svar_i_bnd[ib] * val(O.irradnce, u);
+      }
+    }
+  }
+#undef WSF
+}
+
+// exp(-x) through the reference's 10 001-entry table or its small-argument series (spcvrt.f90:463-470 etc.)
+CB_HD double exp_neg(const double* __restrict__ exp_tbl, double bpade, double ze1) {
+  if (ze1 <= 0.06) return 1. - ze1 + 0.5 * ze1 * ze1;
+  const double tblind = ze1 / (bpade + ze1);
+  const int itind = f2i(10000.0 * tblind + 0.5);
+  return CB_LDG(exp_tbl + itind);
+}
+
+// reftra_sw for one layer (rrtmg_sw_reftra.f90:148-317, kmodts = 2)
+CB_HD void reftra(const double* __restrict__ exp_tbl, double bpade, double zg, double prmuz, double zto1, double zw,
+                  double& pref, double& prefd, double& ptra, double& ptrad) {
+  const double eps = 1.e-08, zwcrit = 0.9999995;
+  const double zg3 = 3. * zg;
+  const double zgamma1 = (8. - zw * (5. + zg3)) * 0.25;
+  const double zgamma2 = 3. * (zw * (1. - zg)) * 0.25;
+  const double zgamma3 = (2. - zg3 * prmuz) * 0.25;
+  const double zgamma4 = 1. - zgamma3;
+  const double r = zg / (1. - zg);
+  const double zwo = zw / (1. - (1. - zw) * (r * r));
+  if (zwo >= zwcrit) {
+    const double za = zgamma1 * prmuz;
+    const double za1 = za - zgamma3;
+    const double zgt = zgamma1 * zto1;
+    const double ze1 = fmin(zto1 / prmuz, 500.);
+    const double ze2 = exp_neg(exp_tbl, bpade, ze1);
+    pref = (zgt - za1 * (1. - ze2)) / (1. + zgt);
+    ptra = 1. - pref;
+    prefd = zgt / (1. + zgt);
+    ptrad = 1. - prefd;
+    if (ze2 == 1.0) { pref = 0.0; ptra = 1.0; prefd = 0.0; ptrad = 1.0; }
+  } else {
+    const double za1 = zgamma1 * zgamma4 + zgamma2 * zgamma3;
+    const double za2 = zgamma1 * zgamma3 + zgamma2 * zgamma4;
+    const double zrk = sqrt(zgamma1 * zgamma1 - zgamma2 * zgamma2);
+    const double zrp = zrk * prmuz;
+    const double zrp1 = 1. + zrp, zrm1 = 1. - zrp, zrk2 = 2. * zrk, zrpp = 1. - zrp * zrp, zrkg = zrk + zgamma1;
+    const double zr1 = zrm1 * (za2 + zrk * zgamma3);
+    const double zr2 = zrp1 * (za2 - zrk * zgamma3);
+    const double zr3 = zrk2 * (zgamma3 - za2 * prmuz);
+    const double zr4 = zrpp * zrkg;
+    const double zr5 = zrpp * (zrk - zgamma1);
+    const double zt1 = zrp1 * (za1 + zrk * zgamma4);
+    const double zt2 = zrm1 * (za1 - zrk * zgamma4);
+    const double zt3 = zrk2 * (zgamma4 + za1 * prmuz);
+    const double zbeta = (zgamma1 - zrk) / zrkg;
+    const double ze1 = fmin(zrk * zto1, 500.);
+    const double ze2 = fmin(zto1 / prmuz, 500.);
+    const double zem1 = exp_neg(exp_tbl, bpade, ze1), zep1 = 1. / zem1;
+    const double zem2 = exp_neg(exp_tbl, bpade, ze2), zep2 = 1. / zem2;
+    const double zdenr = zr4 * zep1 + zr5 * zem1;
+    const double zdent = zr4 * zep1 + zr5 * zem1;  // zt4 = zr4, zt5 = zr5
+    if (zdenr >= -eps && zdenr <= eps) {
+      pref = eps;
+      ptra = zem2;
+    } else {
+      pref = zw * (zr1 * zep1 - zr2 * zem1 - zr3 * zem2) / zdenr;
+      ptra = zem2 - zem2 * zw * (zt1 * zep1 - zt2 * zem1 - zt3 * zep2) / zdent;
+    }
+    const double zemm = zem1 * zem1;
+    const double zdend = 1. / ((1. - zbeta * zemm) * zrkg);
+    prefd = zgamma2 * (1. - zemm) * zdend;
+    ptrad = zrk2 * zem1 * zdend;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sw_unit: spcvrt_sw for U g-points of band B in one column (rrtmg_sw_spcvrt.f90:329-661).
+template <int B, int U>
+CB_HD void sw_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int c0, int c,
+                   int g0, int unit) {
+  constexpr int ib = B - 16;
+  const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
+  const size_t gc = (size_t)(c0 + c);
+  const double* __restrict__ tb = T.base;
+  const double* __restrict__ exp_tbl = tb + T.exp_tbl;
+  const double bpade = T.bpade;
+  const size_t wstride = (size_t)nlay * ncc;
+  const int laytrop = W.laytrop[c];
+  const int laysolfr = W.laysolfr[(size_t)ib * ncc + c];
+  const bool cloudy_col = W.anycld[c] != 0;
+  double prmu0 = in.coszen[gc];
+  if (prmu0 < 1.e-10) prmu0 = 1.e-10;
+  // albedo by band (rad.nomcica.f90:648-659): bands 16-24 and 29 near-IR, 25-28 UV/visible
+  const bool nir = (ib <= 8) || ib == 13;
+  const double albdir = nir ? in.aldir[gc] : in.asdir[gc];
+  const double albdif = nir ? in.aldif[gc] : in.asdif[gc];
+  const int gabs = kGS[ib] + g0;
+  // ---- pass A: surface -> top.  layer optical properties, two-stream R/T, upward adding
+  double rupc[U], rupdc[U], rup[U], rupd[U], src[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) { rupc[u] = albdir; rupdc[u] = albdif; rup[u] = albdir; rupd[u] = albdif; src[u] = 0.; }
+  for (int l = 0; l < nlay; ++l) {
+    const int lay = l + 1;
+    const int idx = W.idx[(size_t)l * ncc + c];
+    const double* ws = W.ws + (size_t)l * ncc + c;
+    double taug[U], taur[U];
+    const bool want = lay == laysolfr;
+    if (lay <= laytrop) eval_band<B, true, U>(T, ws, wstride, idx, g0, taug, taur, want, sol, src);
+    else eval_band<B, false, U>(T, ws, wstride, idx, g0, taug, taur, want, sol, src);
+    // aerosol optical properties of this band/layer
+    double ptaua = 0., pomga = 1., pasya = 0.;
+    if (fl.iaer == 10) {
+      const size_t oa = ((size_t)ib * nlay + l) * ncol + gc;
+      ptaua = in.tauaer[oa]; pomga = in.ssaaer[oa]; pasya = in.asmaer[oa];
+    } else if (fl.iaer == 6) {
+      ptaua = W.aer[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c];
+      pomga = W.aer[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c];
+      pasya = W.aer[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c];
+    }
+    double pclfr = 0., ptauc = 0., pomgc = 1., pasyc = 0.;
+    if (cloudy_col) {
+      pclfr = in.cldfr[(size_t)l * ncol + gc];
+      ptauc = W.cld[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c];
+      pomgc = W.cld[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c];
+      pasyc = W.cld[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double ztauc = taur[u] + taug[u] + ptaua;
+      double zomcc = taur[u] * 1.0 + ptaua * pomga;
+      double zgcc = pasya * pomga * ptaua / zomcc;
+      zomcc = zomcc / ztauc;
+      const double zf = zgcc * zgcc;
+      const double zwf = zomcc * zf;
+      ztauc = (1.0 - zwf) * ztauc;
+      zomcc = (zomcc - zwf) / (1.0 - zwf);
+      zgcc = (zgcc - zf) / (1.0 - zf);
+      double refc, refdc, trac, tradc;
+      reftra(exp_tbl, bpade, zgcc, prmu0, ztauc, zomcc, refc, refdc, trac, tradc);
+      const double dbtc = exp_neg(exp_tbl, bpade, ztauc / prmu0);
+      double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
+      {
+        const double zreflect = 1. / (1. - rupdc[u] * refdc);
+        const double rn = refc + (tradc * ((trac - dbtc) * rupdc[u] + dbtc * rupc[u])) * zreflect;
+        const double rdn = refdc + tradc * tradc * rupdc[u] * zreflect;
+        rupc[u] = rn; rupdc[u] = rdn;
+      }
+      scr[0 * wstride] = refc; scr[1 * wstride] = refdc; scr[2 * wstride] = trac; scr[3 * wstride] = tradc;
+      scr[4 * wstride] = dbtc; scr[5 * wstride] = rupc[u]; scr[6 * wstride] = rupdc[u];
+      if (cloudy_col) {
+        // cloudy (overcast) two-stream of this layer and the cloud-fraction mix (spcvrt.f90:516-588)
+        const double ztauo = ztauc + ptauc;
+        double zomco = ztauc * zomcc + ptauc * pomgc;
+        const double zgco = (ptauc * pomgc * pasyc + ztauc * zomcc * zgcc) / zomco;
+        zomco = zomco / ztauo;
+        double refo = 0., refdo = 0., trao = 1., trado = 1.;
+        if (pclfr > 1.e-12) reftra(exp_tbl, bpade, zgco, prmu0, ztauo, zomco, refo, refdo, trao, trado);
+        const double zclear = 1.0 - pclfr, zcloud = pclfr;
+        const double ref = zclear * refc + zcloud * refo;
+        const double refd = zclear * refdc + zcloud * refdo;
+        const double tra = zclear * trac + zcloud * trao;
+        const double trad = zclear * tradc + zcloud * trado;
+        const double dbtmo = exp_neg(exp_tbl, bpade, ztauo / prmu0);
+        const double dbt = zclear * dbtc + zcloud * dbtmo;
+        const double zreflect = 1. / (1. - rupd[u] * refd);
+        const double rn = ref + (trad * ((tra - dbt) * rupd[u] + dbt * rup[u])) * zreflect;
+        const double rdn = refd + trad * trad * rupd[u] * zreflect;
+        rup[u] = rn; rupd[u] = rdn;
+        scr[7 * wstride] = ref; scr[8 * wstride] = refd; scr[9 * wstride] = tra; scr[10 * wstride] = trad;
+        scr[11 * wstride] = dbt; scr[12 * wstride] = rup[u]; scr[13 * wstride] = rupd[u];
+      }
+    }
+  }
+  // ---- pass B: top -> surface.  downward adding and fluxes (vrtqdr.f90:146-169), weighted by the incoming flux
+  double zinc[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) zinc[u] = sol.adjflux[ib] * src[u] * prmu0;
+  double tdnc[U], rdndc[U], tdbtc[U], tdn[U], rdnd[U], tdbt[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) { tdnc[u] = 1.; rdndc[u] = 0.; tdbtc[u] = 1.; tdn[u] = 1.; rdnd[u] = 0.; tdbt[u] = 1.; }
+  double* __restrict__ part = W.part + (size_t)unit * 4 * (nlay + 1) * ncc + c;
+  const size_t pstride = (size_t)(nlay + 1) * ncc;
+  for (int l = nlay - 1; l >= -1; --l) {
+    // interface above layer l (level index l+1); l = -1 is the surface interface
+    double sfu = 0., sfd = 0., scu = 0., scd = 0.;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double refc = 0., refdc = 0., trac = 0., tradc = 0., dbtc = 0., prupc = albdir, prupdc = albdif;
+      double ref = 0., refd = 0., tra = 0., trad = 0., dbt = 0., prup = albdir, prupd = albdif;
+      if (l >= 0) {
+        const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
+        refc = scr[0 * wstride]; refdc = scr[1 * wstride]; trac = scr[2 * wstride]; tradc = scr[3 * wstride];
+        dbtc = scr[4 * wstride]; prupc = scr[5 * wstride]; prupdc = scr[6 * wstride];
+        if (cloudy_col) {
+          ref = scr[7 * wstride]; refd = scr[8 * wstride]; tra = scr[9 * wstride]; trad = scr[10 * wstride];
+          dbt = scr[11 * wstride]; prup = scr[12 * wstride]; prupd = scr[13 * wstride];
+        }
+      }
+      {
+        const double zreflect = 1. / (1. - rdndc[u] * prupdc);
+        const double fu = (tdbtc[u] * prupc + (tdnc[u] - tdbtc[u]) * prupdc) * zreflect;
+        const double fd = tdbtc[u] + (tdnc[u] - tdbtc[u] + tdbtc[u] * prupc * rdndc[u]) * zreflect;
+        scu = scu + zinc[u] * fu;
+        scd = scd + zinc[u] * fd;
+        if (!cloudy_col) { sfu = sfu + zinc[u] * fu; sfd = sfd + zinc[u] * fd; }
+        if (l >= 0) {
+          if (l == nlay - 1) {  // jk = 1: ztdn(2) = ptra(1), prdnd(2) = prefd(1)
+            tdnc[u] = trac;
+            rdndc[u] = refdc;
+          } else {
+            const double zr = 1. / (1. - refdc * rdndc[u]);
+            const double t = tdbtc[u] * trac + (tradc * ((tdnc[u] - tdbtc[u]) + tdbtc[u] * refc * rdndc[u])) * zr;
+            const double rd = refdc + tradc * tradc * rdndc[u] * zr;
+            tdnc[u] = t; rdndc[u] = rd;
+          }
+          tdbtc[u] = dbtc * tdbtc[u];
+        }
+      }
+      if (cloudy_col) {
+        const double zreflect = 1. / (1. - rdnd[u] * prupd);
+        const double fu = (tdbt[u] * prup + (tdn[u] - tdbt[u]) * prupd) * zreflect;
+        const double fd = tdbt[u] + (tdn[u] - tdbt[u] + tdbt[u] * prup * rdnd[u]) * zreflect;
+        sfu = sfu + zinc[u] * fu;
+        sfd = sfd + zinc[u] * fd;
+        if (l >= 0) {
+          if (l == nlay - 1) {
+            tdn[u] = tra;
+            rdnd[u] = refd;
+          } else {
+            const double zr = 1. / (1. - refd * rdnd[u]);
+            const double t = tdbt[u] * tra + (trad * ((tdn[u] - tdbt[u]) + tdbt[u] * ref * rdnd[u])) * zr;
+            const double rd = refd + trad * trad * rdnd[u] * zr;
+            tdn[u] = t; rdnd[u] = rd;
+          }
+          tdbt[u] = dbt * tdbt[u];
+        }
+      }
+    }
+    const size_t lev = (size_t)(l + 1);
+    part[0 * pstride + lev * ncc] = sfu;
+    part[1 * pstride + lev * ncc] = sfd;
+    part[2 * pstride + lev * ncc] = scu;
+    part[3 * pstride + lev * ncc] = scd;
+  }
+}
+
+struct Unit {
+  int band, g0, u;  // band = 16..29
+};
+constexpr int kMaxUnits = 40;
+inline int build_units(Unit* out) {  // host only
+  int n = 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int b = 16; b <= 29; ++b) {
+      const bool heavy = kNSPA[b - 16] == 9;
+      if ((pass == 0) != heavy) continue;
+      const int ng = kNG[b - 16];
+      for (int g0 = 0; g0 < ng; g0 += 4) {
+        out[n].band = b;
+        out[n].g0 = g0;
+        out[n].u = (ng - g0) >= 4 ? 4 : (ng - g0);
+        ++n;
+      }
+    }
+  return n;
+}
+
+// fixed-order reduction over units (the Fortran accumulates g-point by g-point in band order, spcvrt.f90:614-618)
+CB_HD void sw_reduce_level(const Work& W, const Unit* units, int nunits, int nlay, int c0, int c, int lev, int ncol,
+                           const Out& out) {
+  const int ncc = W.ncc;
+  const size_t pstride = (size_t)(nlay + 1) * ncc;
+  double tot[4] = {0., 0., 0., 0.};
+  for (int b = 16; b <= 29; ++b)
+    for (int k = 0; k < nunits; ++k) {
+      if (units[k].band != b) continue;
+      const double* p = W.part + (size_t)k * 4 * pstride + (size_t)lev * ncc + c;
+      for (int q = 0; q < 4; ++q) tot[q] = tot[q] + p[q * pstride];
+    }
+  const size_t o = (size_t)lev * ncol + (c0 + c);
+  out.uflx[o] = tot[0];
+  out.dflx[o] = tot[1];
+  out.uflxc[o] = tot[2];
+  out.dflxc[o] = tot[3];
+}
+// heating rates (rad.nomcica.f90:797-807)
+CB_HD void sw_heating(const Tables& T, const In& in, const Out& out, int gcol, int l) {
+  const int ncol = in.ncol;
+  const size_t o0 = (size_t)l * ncol + gcol, o1 = o0 + ncol;
+  const double zdpgcp = T.heatfac / (in.plev[o0] - in.plev[o1]);
+  const double n1 = out.dflx[o1] - out.uflx[o1], n0 = out.dflx[o0] - out.uflx[o0];
+  const double c1 = out.dflxc[o1] - out.uflxc[o1], cc0 = out.dflxc[o0] - out.uflxc[o0];
+  out.hr[o0] = (n1 - n0) * zdpgcp;
+  out.hrc[o0] = (c1 - cc0) * zdpgcp;
+}
+
+}  // namespace sw
+}  // namespace cb

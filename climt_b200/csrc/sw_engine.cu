@@ -1,0 +1,342 @@
+// climt_b200 -- RRTMG shortwave engine: CUDA kernels (sm_100a), launcher and C ABI (include/climt_b200.h).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../include/climt_b200.h"
+#include "engine_common.h"
+#include "sw_tables.h"
+
+using namespace cb::sw;
+
+namespace {
+using cb::kBlock;
+
+struct UnitList {
+  Unit u[kMaxUnits];
+  int n;
+};
+
+__global__ void __launch_bounds__(kBlock) k_sw_prep(const __grid_constant__ Tables T, const __grid_constant__ In in,
+                                                    const Flags fl, const __grid_constant__ Work W, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) sw_prep_column(T, in, fl, W, c0, c);
+}
+
+__global__ void __launch_bounds__(kBlock) k_sw_units(const __grid_constant__ Tables T, const __grid_constant__ Solar sol,
+                                                     const __grid_constant__ In in, const Flags fl,
+                                                     const __grid_constant__ Work W, const __grid_constant__ UnitList UL,
+                                                     int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int k = blockIdx.y;
+  const Unit un = UL.u[k];
+#define CB_CASE(B)                                                      \
+  case B:                                                               \
+    if (un.u == 4) sw_unit<B, 4>(T, sol, in, fl, W, c0, c, un.g0, k);   \
+    else sw_unit<B, 2>(T, sol, in, fl, W, c0, c, un.g0, k);             \
+    break;
+  switch (un.band) {
+    CB_CASE(16) CB_CASE(17) CB_CASE(18) CB_CASE(19) CB_CASE(20) CB_CASE(21) CB_CASE(22)
+    CB_CASE(23) CB_CASE(24) CB_CASE(25) CB_CASE(26) CB_CASE(27) CB_CASE(28) CB_CASE(29)
+  }
+#undef CB_CASE
+}
+
+__global__ void __launch_bounds__(kBlock) k_sw_reduce(const __grid_constant__ Work W, const __grid_constant__ UnitList UL,
+                                                      const Out out, int nlay, int ncol, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lev = blockIdx.y;
+  if (c < n) sw_reduce_level(W, UL.u, UL.n, nlay, c0, c, lev, ncol, out);
+}
+
+__global__ void __launch_bounds__(kBlock) k_sw_heat(const __grid_constant__ Tables T, const __grid_constant__ In in,
+                                                    const Out out, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = blockIdx.y;
+  if (c < n) sw_heating(T, in, out, c0 + c, l);
+}
+
+#define CUDA_OK(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      e->error = std::string(#call) + ": " + cudaGetErrorString(_e);                          \
+      return -1;                                                                              \
+    }                                                                                         \
+  } while (0)
+}  // namespace
+
+struct cb200_sw_engine {
+  int device = 0;
+  Tables T;
+  double* d_tables = nullptr;
+  Flags fl{1, 0, 2, 1, 1};
+  SolarOptions solar;
+  UnitList UL;
+  int cap_ncc = 0, cap_nlay = 0;
+  Work W{};
+  int max_chunk = 8192;
+  double* d_stage = nullptr;
+  size_t stage_cap = 0;
+  int* h_err = nullptr;
+  std::string error;
+  int launches = 0;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double unit_ms = 0.0;
+
+  void free_work() {
+    cudaFree(W.ws); cudaFree(W.idx); cudaFree(W.laytrop); cudaFree(W.laysolfr); cudaFree(W.anycld);
+    cudaFree(W.cld); cudaFree(W.aer); cudaFree(W.scr); cudaFree(W.part); cudaFree(W.err);
+    W = Work{};
+    cap_ncc = cap_nlay = 0;
+  }
+  int ensure_work(int ncc, int nlay) {
+    cb200_sw_engine* e = this;
+    if (ncc <= cap_ncc && nlay <= cap_nlay && W.ws) return 0;
+    free_work();
+    const size_t n = (size_t)ncc, L = (size_t)nlay;
+    CUDA_OK(cudaMalloc(&W.ws, sizeof(double) * NF * L * n));
+    CUDA_OK(cudaMalloc(&W.idx, sizeof(int) * L * n));
+    CUDA_OK(cudaMalloc(&W.laytrop, sizeof(int) * n));
+    CUDA_OK(cudaMalloc(&W.laysolfr, sizeof(int) * 14 * n));
+    CUDA_OK(cudaMalloc(&W.anycld, sizeof(int) * n));
+    CUDA_OK(cudaMalloc(&W.cld, sizeof(double) * 42 * L * n));
+    CUDA_OK(cudaMalloc(&W.aer, sizeof(double) * 42 * L * n));
+    CUDA_OK(cudaMalloc(&W.scr, sizeof(double) * 112 * NSCR * L * n));
+    CUDA_OK(cudaMalloc(&W.part, sizeof(double) * UL.n * 4 * (L + 1) * n));
+    CUDA_OK(cudaMalloc(&W.err, sizeof(int)));
+    CUDA_OK(cudaMemset(W.err, 0, sizeof(int)));
+    cap_ncc = ncc;
+    cap_nlay = nlay;
+    return 0;
+  }
+};
+
+extern "C" int cb200_sw_create(cb200_sw_engine** out, const char* table_blob, const double constants[11], int device) {
+  *out = nullptr;
+  auto* e = new cb200_sw_engine();
+  try {
+    Constants k;
+    std::memcpy(&k, constants, sizeof(k));
+    std::vector<double> img;
+    build_tables(table_blob, k, img, e->T);
+    e->device = device;
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) throw std::runtime_error(std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+    ce = cudaMalloc(&e->d_tables, img.size() * sizeof(double));
+    if (ce != cudaSuccess) throw std::runtime_error(std::string("cudaMalloc(tables): ") + cudaGetErrorString(ce));
+    ce = cudaMemcpy(e->d_tables, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) throw std::runtime_error(std::string("cudaMemcpy(tables): ") + cudaGetErrorString(ce));
+    e->T.base = e->d_tables;
+    e->UL.n = build_units(e->UL.u);
+    if (const char* mc = std::getenv("CLIMT_B200_MAX_CHUNK")) e->max_chunk = std::max(128, std::atoi(mc));
+    cudaMallocHost(&e->h_err, sizeof(int));
+    cudaEventCreate(&e->ev0);
+    cudaEventCreate(&e->ev1);
+  } catch (std::exception& ex) {
+    cb::set_global_error(ex.what());
+    delete e;
+    return -1;
+  }
+  *out = e;
+  return 0;
+}
+
+extern "C" void cb200_sw_destroy(cb200_sw_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  e->free_work();
+  cudaFree(e->d_tables);
+  cudaFree(e->d_stage);
+  if (e->h_err) cudaFreeHost(e->h_err);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  delete e;
+}
+
+extern "C" int cb200_sw_set_options(cb200_sw_engine* e, int icld, int iaer, int inflag, int iceflag, int liqflag) {
+  if (icld < 0 || icld > 3) icld = 2;                       // rrtmg_sw_rad.nomcica.f90:558
+  if (iaer != 0 && iaer != 6 && iaer != 10) iaer = 0;       // :566
+  e->fl = Flags{icld, iaer, inflag, iceflag, liqflag};
+  return 0;
+}
+extern "C" int cb200_sw_set_solar(cb200_sw_engine* e, int isolvar, double scon, const double indsolvar[2],
+                                  const double bndsolvar[14]) {
+  e->solar.isolvar = isolvar;
+  e->solar.scon = scon;
+  if (indsolvar) { e->solar.indsolvar[0] = indsolvar[0]; e->solar.indsolvar[1] = indsolvar[1]; }
+  if (bndsolvar) for (int i = 0; i < 14; ++i) e->solar.bndsolvar[i] = bndsolvar[i];
+  return 0;
+}
+extern "C" const char* cb200_sw_last_error(cb200_sw_engine* e) { return e ? e->error.c_str() : cb::g_error.c_str(); }
+extern "C" int cb200_sw_last_launches(cb200_sw_engine* e) { return e->launches; }
+extern "C" int cb200_sw_enable_timing(cb200_sw_engine* e, int on) { e->timing = on != 0; return 0; }
+extern "C" double cb200_sw_last_unit_kernel_ms(cb200_sw_engine* e) { return e->unit_ms; }
+
+static In make_in(int ncol, int nlay, const cb200_sw_inputs* p) {
+  In in;
+  in.ncol = ncol; in.nlay = nlay;
+  const double** d = &in.play;
+  const double* const* s = reinterpret_cast<const double* const*>(p);
+  for (int i = 0; i < 29; ++i) d[i] = s[i];  // identical field order (checked by the static_assert below)
+  return in;
+}
+static_assert(sizeof(cb200_sw_inputs) == 29 * sizeof(double*), "cb200_sw_inputs layout");
+
+extern "C" int cb200_sw_run_device(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
+                                   const cb200_sw_inputs* pin, const cb200_sw_outputs* pout, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (ncol <= 0 || nlay <= 0 || nlay > 203) { e->error = "bad ncol/nlay (1 <= nlay <= 203, parrrsw.f90:27)"; return -3; }
+  CUDA_OK(cudaSetDevice(e->device));
+  int chunk = ncol < e->max_chunk ? ncol : e->max_chunk;
+  chunk = (chunk + kBlock - 1) / kBlock * kBlock;
+  if (e->ensure_work(chunk, nlay)) return -1;
+  Work W = e->W;
+  W.ncc = chunk;
+  const In in = make_in(ncol, nlay, pin);
+  Out out{pout->uflx, pout->dflx, pout->hr, pout->uflxc, pout->dflxc, pout->hrc};
+  const Solar sol = compute_solar(e->solar, adjes, dyofyr, solcycfrac);
+  e->launches = 0;
+  e->unit_ms = 0.0;
+  for (int c0 = 0; c0 < ncol; c0 += chunk) {
+    const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
+    const int gx = (n + kBlock - 1) / kBlock;
+    k_sw_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
+    if (e->timing) cudaEventRecord(e->ev0, st);
+    k_sw_units<<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+    if (e->timing) cudaEventRecord(e->ev1, st);
+    k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, e->UL, out, nlay, ncol, c0, n);
+    k_sw_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
+    e->launches += 4;
+    if (e->timing) {
+      CUDA_OK(cudaEventSynchronize(e->ev1));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+      e->unit_ms += ms;
+    }
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cb200_sw_check(cb200_sw_engine* e) {
+  if (!e->W.err) return 0;
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaMemcpy(e->h_err, e->W.err, sizeof(int), cudaMemcpyDeviceToHost));
+  const int code = *e->h_err;
+  if (code) {
+    // message text of the Fortran `stop` statements (rrtmg_sw_cldprop.f90:166-294, rrtmg_sw_rad.nomcica.f90:618)
+    switch (code) {
+      case 2: e->error = "ICE RADIUS OUT OF BOUNDS"; break;
+      case 3: e->error = "ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS"; break;
+      case 4: e->error = "LIQUID EFFECTIVE RADIUS OUT OF BOUNDS"; break;
+      case 5: e->error = "ICE OPTICAL PROPERTY OUT OF RANGE"; break;
+      case 6: e->error = "FDELTA OUT OF RANGE"; break;
+      case 7: e->error = "LIQUID OPTICAL PROPERTY OUT OF RANGE"; break;
+      case 10: e->error = "PARTIAL CLOUD NOT ALLOWED"; break;
+      default: e->error = "invalid input"; break;
+    }
+    cudaMemset(e->W.err, 0, sizeof(int));
+  }
+  return code;
+}
+
+extern "C" int cb200_sw_run_host(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
+                                 const cb200_sw_inputs* hin, const cb200_sw_outputs* hout) {
+  CUDA_OK(cudaSetDevice(e->device));
+  const size_t n = (size_t)ncol, L = (size_t)nlay;
+  const size_t isz[29] = {L * n, (L + 1) * n, L * n, (L + 1) * n, n, L * n, L * n, L * n, L * n, L * n, L * n,
+                          n, n, n, n, n, L * n, 14 * L * n, 14 * L * n, 14 * L * n, 14 * L * n, L * n, L * n, L * n, L * n,
+                          14 * L * n, 14 * L * n, 14 * L * n, 6 * L * n};
+  const size_t osz[6] = {(L + 1) * n, (L + 1) * n, L * n, (L + 1) * n, (L + 1) * n, L * n};
+  size_t tot = 0, otot = 0;
+  for (size_t s : isz) tot += s;
+  for (size_t s : osz) otot += s;
+  if (tot + otot > e->stage_cap) {
+    cudaFree(e->d_stage);
+    e->d_stage = nullptr;
+    e->stage_cap = 0;
+    CUDA_OK(cudaMalloc(&e->d_stage, (tot + otot) * sizeof(double)));
+    e->stage_cap = tot + otot;
+  }
+  const double* const* hp = reinterpret_cast<const double* const*>(hin);
+  cb200_sw_inputs din;
+  const double** dp = reinterpret_cast<const double**>(&din);
+  size_t off = 0;
+  for (int i = 0; i < 29; ++i) {
+    CUDA_OK(cudaMemcpyAsync(e->d_stage + off, hp[i], isz[i] * sizeof(double), cudaMemcpyHostToDevice, 0));
+    dp[i] = e->d_stage + off;
+    off += isz[i];
+  }
+  cb200_sw_outputs dout;
+  double** dop = reinterpret_cast<double**>(&dout);
+  for (int i = 0; i < 6; ++i) {
+    dop[i] = e->d_stage + off;
+    off += osz[i];
+  }
+  int rc = cb200_sw_run_device(e, ncol, nlay, adjes, dyofyr, solcycfrac, &din, &dout, 0);
+  if (rc) return rc;
+  double* const* hop = reinterpret_cast<double* const*>(hout);
+  for (int i = 0; i < 6; ++i)
+    CUDA_OK(cudaMemcpyAsync(hop[i], dop[i], osz[i] * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  CUDA_OK(cudaStreamSynchronize(0));
+  return cb200_sw_check(e);
+}
+
+// ---- reference-named entry points, one process-global engine
+namespace {
+double g_consts[11] = {0};
+cb200_sw_engine* g_engine = nullptr;
+std::string default_blob() {
+  if (const char* p = std::getenv("CLIMT_B200_SW_TABLES")) return p;
+  Dl_info info;
+  if (dladdr((void*)&cb200_sw_create, &info) && info.dli_fname) {
+    std::string so = info.dli_fname;
+    size_t k = so.find_last_of('/');
+    std::string dir = k == std::string::npos ? "." : so.substr(0, k);
+    return dir + "/data/_cache/rrtmg_sw_reduced.blob";
+  }
+  return "rrtmg_sw_reduced.blob";
+}
+}  // namespace
+
+extern "C" void rrtmg_sw_set_constants(double* pi, double* grav, double* planck, double* boltz, double* clight,
+                                       double* avogad, double* alosmt, double* gascon, double* sbcnst, double* secdy) {
+  double v[10] = {*pi, *grav, *planck, *boltz, *clight, *avogad, *alosmt, *gascon, *sbcnst, *secdy};
+  std::memcpy(g_consts, v, sizeof v);
+}
+extern "C" void rrtmg_sw_ini_wrapper(double* cpdair) {
+  g_consts[10] = *cpdair;
+  if (g_engine) { cb200_sw_destroy(g_engine); g_engine = nullptr; }
+  int dev = 0;
+  if (const char* d = std::getenv("CLIMT_B200_DEVICE")) dev = std::atoi(d);
+  if (cb200_sw_create(&g_engine, default_blob().c_str(), g_consts, dev))
+    std::fprintf(stderr, "climt_b200: rrtmg_sw_ini_wrapper failed: %s\n", cb200_global_error());
+}
+extern "C" void rrtmg_sw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* iaer, double* play, double* plev,
+                                         double* tlay, double* tlev, double* tsfc, double* h2ovmr, double* o3vmr,
+                                         double* co2vmr, double* ch4vmr, double* n2ovmr, double* o2vmr, double* asdir,
+                                         double* asdif, double* aldir, double* aldif, double* coszen, double* adjes,
+                                         int* dyofyr, double* scon, int* isolvar, int* inflgsw, int* iceflgsw,
+                                         int* liqflgsw, double* cldfr, double* taucld, double* ssacld, double* asmcld,
+                                         double* fsfcld, double* cicewp, double* cliqwp, double* reice, double* reliq,
+                                         double* tauaer, double* ssaaer, double* asmaer, double* ecaer, double* swuflx,
+                                         double* swdflx, double* swhr, double* swuflxc, double* swdflxc, double* swhrc,
+                                         double* bndsolvar, double* indsolvar, double* solcycfrac) {
+  if (!g_engine) { std::fprintf(stderr, "climt_b200: rrtmg_sw_ini_wrapper has not been called\n"); return; }
+  if (*icld < 0 || *icld > 3) *icld = 2;
+  if (*iaer != 0 && *iaer != 6 && *iaer != 10) *iaer = 0;
+  cb200_sw_set_options(g_engine, *icld, *iaer, *inflgsw, *iceflgsw, *liqflgsw);
+  cb200_sw_set_solar(g_engine, *isolvar, *scon, indsolvar, bndsolvar);
+  cb200_sw_inputs in{play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, asdir, asdif, aldir, aldif,
+                     coszen, cldfr, taucld, ssacld, asmcld, fsfcld, cicewp, cliqwp, reice, reliq, tauaer, ssaaer, asmaer, ecaer};
+  cb200_sw_outputs out{swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc};
+  if (cb200_sw_run_host(g_engine, *ncol, *nlay, *adjes, *dyofyr, solcycfrac ? *solcycfrac : 0.0, &in, &out))
+    std::fprintf(stderr, "climt_b200: %s\n", cb200_sw_last_error(g_engine));
+}

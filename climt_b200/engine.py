@@ -9,7 +9,7 @@ import numpy as np
 
 from . import _native
 from .constants import rrtmg_constants
-from .rrtmg_tables import lw_blob_path
+from .rrtmg_tables import lw_blob_path, sw_blob_path
 
 _dp = ctypes.POINTER(ctypes.c_double)
 LW_IN = [f[0] for f in _native.LwInputs._fields_]
@@ -120,3 +120,112 @@ class LWEngine:
     @property
     def last_launches(self):
         return self._L.cb200_lw_last_launches(self._h)
+
+
+SW_IN = [f[0] for f in _native.SwInputs._fields_]
+
+
+def sw_shapes(ncol, nlay):
+    L, n = nlay, ncol
+    ins = {k: (L, n) for k in SW_IN}
+    ins.update(plev=(L + 1, n), tlev=(L + 1, n), tsfc=(n,), asdir=(n,), asdif=(n,), aldir=(n,), aldif=(n,), coszen=(n,),
+               taucld=(L, n, 14), ssacld=(L, n, 14), asmcld=(L, n, 14), fsfcld=(L, n, 14),
+               tauaer=(14, L, n), ssaaer=(14, L, n), asmaer=(14, L, n), ecaer=(6, L, n))
+    outs = {"uflx": (L + 1, n), "dflx": (L + 1, n), "uflxc": (L + 1, n), "dflxc": (L + 1, n), "hr": (L, n), "hrc": (L, n)}
+    return ins, outs
+
+
+class SWEngine:
+    """One RRTMG-SW engine instance (non-McICA driver)."""
+
+    def __init__(self, constants=None, device=0, icld=1, iaer=0, inflag=2, iceflag=1, liqflag=1, isolvar=0,
+                 scon=1367.0, indsolvar=(1.0, 1.0), bndsolvar=None):
+        self._L = _native.lib()
+        k = constants or rrtmg_constants()
+        c = np.array([k[n] for n in _CONST_ORDER], dtype=np.float64)
+        h = ctypes.c_void_p()
+        rc = self._L.cb200_sw_create(ctypes.byref(h), sw_blob_path().encode(), c.ctypes.data_as(_dp), int(device))
+        if rc != 0 or not h:
+            raise RuntimeError("cb200_sw_create failed: " + self._L.cb200_global_error().decode())
+        self._h = h
+        self.device = device
+        self._L.cb200_sw_set_options(self._h, icld, iaer, inflag, iceflag, liqflag)
+        ind = np.array(indsolvar, dtype=np.float64)
+        bnd = np.ones(14) if bndsolvar is None else np.ascontiguousarray(np.asarray(bndsolvar, dtype=np.float64)[:14])
+        self._L.cb200_sw_set_solar(self._h, int(isolvar), float(scon), ind.ctypes.data_as(_dp), bnd.ctypes.data_as(_dp))
+
+    def _err(self):
+        return self._L.cb200_sw_last_error(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cb200_sw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_host(self, ncol, nlay, arrays, out=None, adjes=1.0, dyofyr=0, solcycfrac=0.0):
+        ins, outs = sw_shapes(ncol, nlay)
+        keep = []
+        pin = _native.SwInputs()
+        for k in SW_IN:
+            a = np.ascontiguousarray(arrays[k], dtype=np.float64)
+            if a.shape != ins[k]:
+                raise ValueError(f"{k}: expected shape {ins[k]}, got {a.shape}")
+            keep.append(a)
+            setattr(pin, k, a.ctypes.data_as(_dp))
+        out = out if out is not None else {k: np.empty(outs[k]) for k in LW_OUT}
+        pout = _native.LwOutputs()
+        for k in LW_OUT:
+            a = out[k]
+            if a.shape != outs[k] or a.dtype != np.float64 or not a.flags.c_contiguous:
+                raise ValueError(f"output {k}: need C-contiguous float64 {outs[k]}")
+            setattr(pout, k, a.ctypes.data_as(_dp))
+        rc = self._L.cb200_sw_run_host(self._h, ncol, nlay, float(adjes), int(dyofyr), float(solcycfrac),
+                                       ctypes.byref(pin), ctypes.byref(pout))
+        if rc < 0:
+            raise RuntimeError(self._err())
+        if rc > 0:
+            raise ValueError(self._err())
+        return out
+
+    def run_device(self, ncol, nlay, tensors, out, adjes=1.0, dyofyr=0, solcycfrac=0.0, stream=None):
+        import torch
+        ins, outs = sw_shapes(ncol, nlay)
+        pin = _native.SwInputs()
+        for k in SW_IN:
+            t = tensors[k]
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == ins[k]):
+                raise ValueError(f"{k}: need contiguous float64 CUDA tensor of shape {ins[k]}")
+            setattr(pin, k, ctypes.cast(t.data_ptr(), _dp))
+        pout = _native.LwOutputs()
+        for k in LW_OUT:
+            t = out[k]
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == outs[k]):
+                raise ValueError(f"output {k}: need contiguous float64 CUDA tensor of shape {outs[k]}")
+            setattr(pout, k, ctypes.cast(t.data_ptr(), _dp))
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        rc = self._L.cb200_sw_run_device(self._h, ncol, nlay, float(adjes), int(dyofyr), float(solcycfrac),
+                                         ctypes.byref(pin), ctypes.byref(pout), ctypes.c_void_p(s))
+        if rc:
+            raise RuntimeError(self._err())
+
+    def check(self):
+        rc = self._L.cb200_sw_check(self._h)
+        if rc:
+            raise ValueError(self._err())
+
+    def enable_timing(self, on=True):
+        self._L.cb200_sw_enable_timing(self._h, 1 if on else 0)
+
+    @property
+    def last_unit_kernel_ms(self):
+        return self._L.cb200_sw_last_unit_kernel_ms(self._h)
+
+    @property
+    def last_launches(self):
+        return self._L.cb200_sw_last_launches(self._h)

@@ -138,6 +138,69 @@ def reduce_lw(raw=None):
     return out
 
 
+# swcmbdat (rrtmg_sw_init.f90:286-340), swdatinit (:195-203)
+SW_NGC = np.array([6, 12, 8, 8, 10, 10, 2, 10, 8, 6, 6, 8, 6, 12])
+SW_NGN = np.array([2, 2, 2, 2, 4, 4] + [1, 1, 1, 1, 1, 2, 1, 2, 1, 2, 1, 2] + [1, 1, 1, 1, 2, 2, 4, 4] * 2
+                  + [1, 1, 1, 1, 1, 1, 1, 1, 2, 6] * 2 + [8, 8] + [2, 2, 1, 1, 1, 1, 1, 1, 2, 4] + [2] * 8
+                  + [1, 1, 2, 2, 4, 6] * 2 + [1, 1, 1, 1, 1, 1, 4, 6] + [1, 1, 2, 2, 4, 6]
+                  + [1, 1, 1, 1, 2, 2, 2, 2, 1, 1, 1, 1])
+SW_NSPA = [9, 9, 9, 9, 1, 9, 9, 1, 9, 1, 0, 1, 9, 1]
+SW_NSPB = [1, 5, 1, 1, 1, 5, 1, 0, 1, 0, 0, 1, 5, 1]
+SW_WAVENUM2 = np.array([3250., 4000., 4650., 5150., 6150., 7700., 8050., 12850., 16000., 22650., 29000., 38000.,
+                        50000., 2600.])
+_SW_PLAIN = ("sfluxrefo", "irradnceo", "facbrghto", "snsptdrko")   # plain sums (cmbgb16s :579-591)
+
+
+def reduce_sw(raw=None):
+    """-> dict of float64 arrays, g fastest; names `b<NN>.<table>` with NN = 16..29."""
+    raw = raw or _t.load_raw("sw")
+    out = {}
+    off = 0
+    for ib in range(1, 15):
+        ngc = int(SW_NGC[ib - 1])
+        groups = _groups(SW_NGN[off:off + ngc])
+        off += ngc
+        w = _band_weights(groups)
+        pre = f"rrsw_kg{ib + 15:02d}."
+        for key in sorted(k for k in raw if k.startswith(pre) and not k.endswith("__lb")):
+            name = key[len(pre):]
+            a = raw[key]
+            if name == "rayl":
+                out[f"b{ib + 15:02d}.rayl"] = np.array([float(a)])
+                continue
+            red = {"kao": "absa", "kbo": "absb"}.get(name, name[:-1])
+            plain = name in _SW_PLAIN
+            if a.ndim == 1:
+                r = _reduce(a[None, :], groups, None if plain else w)          # (1, ng)
+            elif plain or name == "raylao":                                    # (16, np): g first -> (np, ng)
+                r = _reduce(np.ascontiguousarray(a.T), groups, None if plain else w)
+            else:
+                r = _rows_g(_reduce(a, groups, w))
+            out[f"b{ib + 15:02d}.{red}"] = np.ascontiguousarray(r)
+    out["preflog"] = raw["rrsw_ref.preflog"]
+    out["tref"] = raw["rrsw_ref.tref"]
+    # cloud optics (swcldpr, rrtmg_sw_init.f90:1692-3514): (index, band) tables
+    for nm in ("extliq1", "ssaliq1", "asyliq1", "extice2", "ssaice2", "asyice2", "extice3", "ssaice3", "asyice3",
+               "fdlice3"):
+        out["cld." + nm] = np.ascontiguousarray(raw["rrsw_cld." + nm])       # (n, 14)
+    for nm in ("abari", "bbari", "cbari", "dbari", "ebari", "fbari"):
+        out["cld." + nm] = raw["rrsw_cld." + nm]
+    # ECMWF aerosol optics (swaerpr :389-489): (band, type)
+    for nm in ("rsrtaua", "rsrpiza", "rsrasya"):
+        out["aer." + nm] = np.ascontiguousarray(raw["rrsw_aer." + nm])       # (14, 6)
+    return out
+
+
+def sw_blob_path(rebuild=False):
+    path = os.path.join(_t.DATA_DIR, "_cache", "rrtmg_sw_reduced.blob")
+    src = os.path.join(_t.DATA_DIR, "rrtmg_sw_raw.npz")
+    if rebuild or not os.path.exists(path) or os.path.getmtime(path) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.abspath(__file__))):
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        _t.write_blob(reduce_sw(), path, order="C")
+    return path
+
+
 def lw_blob_path(rebuild=False):
     path = os.path.join(_t.DATA_DIR, "_cache", "rrtmg_lw_reduced.blob")
     src = os.path.join(_t.DATA_DIR, "rrtmg_lw_raw.npz")
@@ -150,3 +213,4 @@ def lw_blob_path(rebuild=False):
 
 if __name__ == "__main__":
     print(lw_blob_path(rebuild=True))
+    print(sw_blob_path(rebuild=True))

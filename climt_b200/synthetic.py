@@ -50,3 +50,36 @@ def make_lw_state(ncol, nlay, seed=20260925, clouds=False, trace=True, aerosol=F
         st["reice"] = rng.uniform(15, 120, shp)
         st["reliq"] = rng.uniform(4, 30, shp)
     return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in st.items()}
+
+SW_FIELDS = ("play", "plev", "tlay", "tlev", "tsfc", "h2o", "o3", "co2", "ch4", "n2o", "o2", "asdir", "asdif", "aldir",
+             "aldif", "coszen", "cldfr", "taucld", "ssacld", "asmcld", "fsfcld", "cicewp", "cliqwp", "reice", "reliq",
+             "tauaer", "ssaaer", "asmaer", "ecaer")
+
+
+def make_sw_state(ncol, nlay, seed=20260925, clouds=False, trace=True, aerosol=False, ecmwf=False, overcast_only=True):
+    """Shortwave twin of make_lw_state (same atmosphere for the same seed).  Non-McICA RRTMG-SW only accepts cloud
+    fractions 0 or 1 (rrtmg_sw_rad.nomcica.f90:616-620) -> overcast_only."""
+    lw = make_lw_state(ncol, nlay, seed=seed, clouds=clouds, trace=trace)
+    rng = np.random.default_rng(seed + 1)
+    shp = (nlay, ncol)
+    st = {k: lw[k] for k in ("play", "plev", "tlay", "tlev", "tsfc", "h2o", "o3", "co2", "ch4", "n2o", "o2", "cldfr",
+                             "cicewp", "cliqwp", "reice", "reliq")}
+    if clouds and overcast_only:
+        st["cldfr"] = np.where(st["cldfr"] > 0, 1.0, 0.0)
+    zen = np.deg2rad(np.clip(rng.uniform(0, 85, ncol), 0, 85))
+    st.update({
+        "asdir": rng.uniform(0.06, 0.3, ncol), "asdif": rng.uniform(0.06, 0.3, ncol),
+        "aldir": rng.uniform(0.06, 0.3, ncol), "aldif": rng.uniform(0.06, 0.3, ncol),
+        "coszen": np.cos(zen),
+        "taucld": np.zeros((nlay, ncol, 14)), "ssacld": 0.9 * np.ones((nlay, ncol, 14)),
+        "asmcld": 0.85 * np.ones((nlay, ncol, 14)), "fsfcld": 0.8 * np.ones((nlay, ncol, 14)),
+        "tauaer": np.zeros((14, nlay, ncol)), "ssaaer": 0.5 * np.ones((14, nlay, ncol)),
+        "asmaer": np.zeros((14, nlay, ncol)), "ecaer": np.zeros((6, nlay, ncol)),
+    })
+    if aerosol:
+        st["tauaer"] = rng.uniform(0, 0.05, (14, nlay, ncol))
+        st["ssaaer"] = rng.uniform(0.7, 0.99, (14, nlay, ncol))
+        st["asmaer"] = rng.uniform(0.5, 0.8, (14, nlay, ncol))
+    if ecmwf:
+        st["ecaer"] = rng.uniform(0, 0.02, (6, nlay, ncol))
+    return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in st.items()}

@@ -81,6 +81,51 @@ void rrtmg_lw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* idrv, double
                               double* reice, double* reliq, double* tauaer, double* uflx, double* dflx, double* hr,
                               double* uflxc, double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt);
 
+
+/* ============================== shortwave ==============================
+ * Replaces (climt/_lib/rrtmg_sw/rrtmg_sw_c_binder.f90): rrtmg_sw_set_constants :19-46, rrtmg_sw_ini_wrapper :48-57,
+ * rrtmg_sw_nomcica_wrapper :203-296 (decls in _components/rrtmg/sw/_rrtmg_sw.pyx:22-105).
+ * Cloud arrays taucld/ssacld/asmcld/fsfcld are (nlay, ncol, 14) [Fortran (14,ncol,nlay)]; aerosol arrays
+ * tauaer/ssaaer/asmaer (14, nlay, ncol); ecaer (6, nlay, ncol); albedos and coszen (ncol). */
+typedef struct cb200_sw_engine cb200_sw_engine;
+typedef struct cb200_sw_inputs {
+  const double *play, *plev, *tlay, *tlev, *tsfc;
+  const double *h2ovmr, *o3vmr, *co2vmr, *ch4vmr, *n2ovmr, *o2vmr;
+  const double *asdir, *asdif, *aldir, *aldif, *coszen;
+  const double *cldfr, *taucld, *ssacld, *asmcld, *fsfcld, *cicewp, *cliqwp, *reice, *reliq;
+  const double *tauaer, *ssaaer, *asmaer, *ecaer;
+} cb200_sw_inputs;
+typedef cb200_lw_outputs cb200_sw_outputs; /* swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc */
+
+int cb200_sw_create(cb200_sw_engine** out, const char* table_blob, const double constants[11], int device);
+void cb200_sw_destroy(cb200_sw_engine* e);
+/* icld 0..3 (non-McICA accepts cloud fractions 0 or 1 only), iaer 0|6|10, inflag 0|2, iceflag 1|2|3, liqflag 1 */
+int cb200_sw_set_options(cb200_sw_engine* e, int icld, int iaer, int inflag, int iceflag, int liqflag);
+/* isolvar -1..3, scon [W m-2] (0 = internal), indsolvar[2], bndsolvar[14] (module globals in _rrtmg_sw.pyx:8-19) */
+int cb200_sw_set_solar(cb200_sw_engine* e, int isolvar, double scon, const double indsolvar[2], const double bndsolvar[14]);
+int cb200_sw_run_device(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
+                        const cb200_sw_inputs* in, const cb200_sw_outputs* out, void* stream);
+int cb200_sw_run_host(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
+                      const cb200_sw_inputs* in, const cb200_sw_outputs* out);
+int cb200_sw_check(cb200_sw_engine* e);
+const char* cb200_sw_last_error(cb200_sw_engine* e);
+int cb200_sw_last_launches(cb200_sw_engine* e);
+int cb200_sw_enable_timing(cb200_sw_engine* e, int on);
+double cb200_sw_last_unit_kernel_ms(cb200_sw_engine* e);
+
+void rrtmg_sw_set_constants(double* pi, double* grav, double* planck, double* boltz, double* clight, double* avogad,
+                            double* alosmt, double* gascon, double* sbcnst, double* secdy);
+void rrtmg_sw_ini_wrapper(double* cpdair);
+void rrtmg_sw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* iaer, double* play, double* plev, double* tlay,
+                              double* tlev, double* tsfc, double* h2ovmr, double* o3vmr, double* co2vmr,
+                              double* ch4vmr, double* n2ovmr, double* o2vmr, double* asdir, double* asdif,
+                              double* aldir, double* aldif, double* coszen, double* adjes, int* dyofyr, double* scon,
+                              int* isolvar, int* inflgsw, int* iceflgsw, int* liqflgsw, double* cldfr, double* taucld,
+                              double* ssacld, double* asmcld, double* fsfcld, double* cicewp, double* cliqwp,
+                              double* reice, double* reliq, double* tauaer, double* ssaaer, double* asmaer,
+                              double* ecaer, double* swuflx, double* swdflx, double* swhr, double* swuflxc,
+                              double* swdflxc, double* swhrc, double* bndsolvar, double* indsolvar, double* solcycfrac);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,66 @@
+// TEST-ONLY host emulation of the CUDA SW engine (same per-thread code as the kernels, stepped serially).
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../climt_b200/csrc/sw_tables.h"
+
+using namespace cb::sw;
+
+template <int B, int U>
+static void run_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int n, int g0, int unit) {
+  for (int c = 0; c < n; ++c) sw_unit<B, U>(T, sol, in, fl, W, 0, c, g0, unit);
+}
+
+// scal = {adjes, scon, solcycfrac, indsolvar0, indsolvar1, bndsolvar[14]}; iopt = {icld, iaer, inflag, iceflag, liqflag, isolvar, dyofyr}
+extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* iopt, const double* scal, int ncol, int nlay,
+                           const double* const* inp /*29 pointers in struct In order*/, double* const* outp /*6*/) {
+  try {
+    Constants k;
+    std::memcpy(&k, consts11, sizeof(k));
+    std::vector<double> img;
+    Tables T;
+    build_tables(blob, k, img, T);
+    T.base = img.data();
+    In in;
+    in.ncol = ncol; in.nlay = nlay;
+    const double** ip = &in.play;
+    for (int i = 0; i < 29; ++i) ip[i] = inp[i];
+    Out out;
+    double** op = &out.uflx;
+    for (int i = 0; i < 6; ++i) op[i] = outp[i];
+    Flags fl{iopt[0], iopt[1], iopt[2], iopt[3], iopt[4]};
+    SolarOptions so;
+    so.isolvar = iopt[5]; so.scon = scal[1]; so.indsolvar[0] = scal[3]; so.indsolvar[1] = scal[4];
+    for (int i = 0; i < 14; ++i) so.bndsolvar[i] = scal[5 + i];
+    Solar sol = compute_solar(so, scal[0], iopt[6], scal[2]);
+    Unit units[kMaxUnits];
+    const int nunits = build_units(units);
+    Work W;
+    W.ncc = ncol;
+    std::vector<double> ws((size_t)NF * nlay * ncol), cld((size_t)42 * nlay * ncol), aer((size_t)42 * nlay * ncol),
+        scr((size_t)112 * NSCR * nlay * ncol), part((size_t)nunits * 4 * (nlay + 1) * ncol);
+    std::vector<int> idx((size_t)nlay * ncol), lt(ncol), ls((size_t)14 * ncol), ac(ncol);
+    int err = 0;
+    W.ws = ws.data(); W.idx = idx.data(); W.laytrop = lt.data(); W.laysolfr = ls.data(); W.anycld = ac.data();
+    W.cld = cld.data(); W.aer = aer.data(); W.scr = scr.data(); W.part = part.data(); W.err = &err;
+    for (int c = 0; c < ncol; ++c) sw_prep_column(T, in, fl, W, 0, c);
+    for (int k2 = 0; k2 < nunits; ++k2) {
+      const Unit un = units[k2];
+#define CASE(B) case B: if (un.u == 4) run_unit<B, 4>(T, sol, in, fl, W, ncol, un.g0, k2); else run_unit<B, 2>(T, sol, in, fl, W, ncol, un.g0, k2); break;
+      switch (un.band) {
+        CASE(16) CASE(17) CASE(18) CASE(19) CASE(20) CASE(21) CASE(22) CASE(23) CASE(24) CASE(25) CASE(26) CASE(27)
+        CASE(28) CASE(29)
+      }
+#undef CASE
+    }
+    for (int c = 0; c < ncol; ++c)
+      for (int lev = 0; lev <= nlay; ++lev) sw_reduce_level(W, units, nunits, nlay, 0, c, lev, ncol, out);
+    for (int c = 0; c < ncol; ++c)
+      for (int l = 0; l < nlay; ++l) sw_heating(T, in, out, c, l);
+    return err;
+  } catch (std::exception& e) {
+    std::fprintf(stderr, "emul_sw_run: %s\n", e.what());
+    return -1;
+  }
+}

@@ -61,6 +61,40 @@ def default_lw_abi_state(nz, ncol=1, external_tint=False):
     return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in st.items()}
 
 
+SW_ABI_NAME = dict(ABI_NAME)
+
+
+def to_abi_sw(st):
+    return {ABI_NAME.get(k, k): v for k, v in st.items()}
+
+
+def sw_oracle(**flags):
+    from oracle.rrtmg import SWOracle
+    return SWOracle(C.rrtmg_constants(), T.raw_blob_path("sw"), **flags)
+
+
+def default_sw_abi_state(nz, ncol=1):
+    d = S.default_rrtmg_sw_state(nz, ncol)
+    p, pi = d["air_pressure"] / 100.0, d["air_pressure_on_interface_levels"] / 100.0
+    st = dict(
+        play=p, plev=pi, tlay=d["air_temperature"], tsfc=d["surface_temperature"],
+        h2o=S.mass_to_volume_mixing_ratio(d["specific_humidity"], 18.02), o3=d["mole_fraction_of_ozone_in_air"],
+        co2=d["mole_fraction_of_carbon_dioxide_in_air"], ch4=d["mole_fraction_of_methane_in_air"],
+        n2o=d["mole_fraction_of_nitrous_oxide_in_air"], o2=d["mole_fraction_of_oxygen_in_air"],
+        asdir=d["surface_albedo_for_direct_shortwave"], asdif=d["surface_albedo_for_diffuse_shortwave"],
+        aldir=d["surface_albedo_for_direct_near_infrared"], aldif=d["surface_albedo_for_diffuse_near_infrared"],
+        coszen=np.cos(d["zenith_angle"]), cldfr=d["cloud_area_fraction_in_atmosphere_layer"],
+        taucld=d["shortwave_optical_thickness_due_to_cloud"], ssacld=d["single_scattering_albedo_due_to_cloud"],
+        asmcld=d["cloud_asymmetry_parameter"], fsfcld=d["cloud_forward_scattering_fraction"],
+        cicewp=d["mass_content_of_cloud_ice_in_atmosphere_layer"] * 1e3,
+        cliqwp=d["mass_content_of_cloud_liquid_water_in_atmosphere_layer"] * 1e3,
+        reice=d["cloud_ice_particle_size"], reliq=d["cloud_water_droplet_radius"],
+        tauaer=d["shortwave_optical_thickness_due_to_aerosol"], ssaaer=d["single_scattering_albedo_due_to_aerosol"],
+        asmaer=d["aerosol_asymmetry_parameter"], ecaer=d["aerosol_optical_depth_at_55_micron"])
+    st["tlev"] = S.get_interface_values(st["tlay"], st["tsfc"], p, pi)
+    return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in st.items()}
+
+
 def golden():
     return np.load(GOLDEN)
 
@@ -70,10 +104,11 @@ def rel_err(got, ref, floor=1e-3):
 
 
 # ---- host emulation of the kernel code (tests/emul/lw_emul.cpp) ---------------------------------
-def emul_lib():
-    so = os.path.join(HERE, "emul", "libcb_emul.so")
-    src = os.path.join(HERE, "emul", "lw_emul.cpp")
-    deps = [src] + [os.path.join(HERE, "..", "climt_b200", "csrc", f) for f in ("lw_core.cuh", "lw_tables.h", "cb_common.h")]
+def emul_lib(which="lw"):
+    so = os.path.join(HERE, "emul", "libcb_emul.so" if which == "lw" else "libcb_emul_sw.so")
+    src = os.path.join(HERE, "emul", f"{which}_emul.cpp")
+    deps = [src] + [os.path.join(HERE, "..", "climt_b200", "csrc", f)
+                    for f in ("lw_core.cuh", "lw_tables.h", "cb_common.h", "sw_core.cuh", "sw_tables.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
     return ctypes.CDLL(so)
@@ -92,3 +127,23 @@ def run_lw_emul(st, flags=(1, 0, 2, 1, 1)):
     rc = lib.emul_lw_run(RT.lw_blob_path().encode(), consts.ctypes.data_as(_dp), (ctypes.c_int * 5)(*flags),
                          ncol, nlay, inp, outp)
     return rc, out
+
+
+def run_sw_emul(st, iopt=(1, 0, 2, 1, 1, 0, 1), scal=None):
+    """iopt = (icld, iaer, inflag, iceflag, liqflag, isolvar, dyofyr); scal = [adjes, scon, solcycfrac, ind0, ind1, bnd[14]]"""
+    lib = emul_lib("sw")
+    k = C.rrtmg_constants()
+    consts = np.array([k[n] for n in ("pi", "grav", "planck", "boltz", "clight", "avogad", "alosmt", "gascon",
+                                      "sbcnst", "secdy", "cpdair")])
+    scal = np.array(scal if scal is not None else [1.0, 1367.0, 0.0, 1.0, 1.0] + [1.0] * 14, dtype=np.float64)
+    nlay, ncol = st["play"].shape
+    inp = (_dp * 29)(*[st[f].ctypes.data_as(_dp) for f in SY.SW_FIELDS])
+    out = {n: np.zeros((nlay + 1, ncol)) for n in ("uflx", "dflx", "uflxc", "dflxc")}
+    out.update({n: np.zeros((nlay, ncol)) for n in ("hr", "hrc")})
+    outp = (_dp * 6)(*[out[n].ctypes.data_as(_dp) for n in ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc")])
+    rc = lib.emul_sw_run(RT.sw_blob_path().encode(), consts.ctypes.data_as(_dp), (ctypes.c_int * 7)(*iopt),
+                         scal.ctypes.data_as(_dp), ncol, nlay, inp, outp)
+    return rc, out
+
+
+SW_KEYS = {"uflx": "swuflx", "dflx": "swdflx", "uflxc": "swuflxc", "dflxc": "swdflxc", "hr": "swhr", "hrc": "swhrc"}
