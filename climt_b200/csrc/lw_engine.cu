@@ -17,6 +17,9 @@ using namespace cb::lw;
 namespace {
 
 using cb::kBlock;
+#ifndef CB_UNITS_MIN_BLOCKS
+#define CB_UNITS_MIN_BLOCKS 1
+#endif
 
 __global__ void __launch_bounds__(kBlock) k_prep(const __grid_constant__ Tables T, const __grid_constant__ In in,
                                                  const Flags fl, const __grid_constant__ Work W, int c0, int n) {
@@ -31,7 +34,7 @@ struct UnitList {
 
 // One block = 128 adjacent columns x one unit (<=4 g-points of one band): every branch on the band is
 // block-uniform, all global accesses are column-contiguous.
-__global__ void __launch_bounds__(kBlock) k_units(const __grid_constant__ Tables T, const __grid_constant__ In in,
+__global__ void __launch_bounds__(kBlock, CB_UNITS_MIN_BLOCKS) k_units(const __grid_constant__ Tables T, const __grid_constant__ In in,
                                                   const __grid_constant__ Work W, const __grid_constant__ UnitList UL,
                                                   int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;

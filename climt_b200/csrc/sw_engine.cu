@@ -15,6 +15,9 @@ using namespace cb::sw;
 
 namespace {
 using cb::kBlock;
+#ifndef CB_UNITS_MIN_BLOCKS
+#define CB_UNITS_MIN_BLOCKS 1
+#endif
 
 struct UnitList {
   Unit u[kMaxUnits];
@@ -27,7 +30,7 @@ __global__ void __launch_bounds__(kBlock) k_sw_prep(const __grid_constant__ Tabl
   if (c < n) sw_prep_column(T, in, fl, W, c0, c);
 }
 
-__global__ void __launch_bounds__(kBlock) k_sw_units(const __grid_constant__ Tables T, const __grid_constant__ Solar sol,
+__global__ void __launch_bounds__(kBlock, CB_UNITS_MIN_BLOCKS) k_sw_units(const __grid_constant__ Tables T, const __grid_constant__ Solar sol,
                                                      const __grid_constant__ In in, const Flags fl,
                                                      const __grid_constant__ Work W, const __grid_constant__ UnitList UL,
                                                      int c0, int n) {

@@ -167,3 +167,12 @@ def default_rrtmg_sw_state(nz, ncol=1, p_surf=None):
         "day_of_year": 1,
     })
     return st
+
+
+def default_gray_state(nz, ncol=1, p_surf=None):
+    """Default state of GrayLongwaveRadiation: tau = 1 - p/ps on interfaces (initialization.py:1144-1150)."""
+    g = default_grid(nz, ncol, p_surf)
+    ps = g["surface_air_pressure"]
+    return {"air_temperature": np.full((nz, ncol), 290.0), "surface_temperature": np.full(ncol, 300.0),
+            "air_pressure": g["air_pressure"], "air_pressure_on_interface_levels": g["air_pressure_on_interface_levels"],
+            "longwave_optical_depth_on_interface_levels": 1.0 * (1.0 - g["air_pressure_on_interface_levels"] / ps[None, :])}

@@ -126,6 +126,19 @@ void rrtmg_sw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* iaer, double
                               double* ecaer, double* swuflx, double* swdflx, double* swhr, double* swuflxc,
                               double* swdflxc, double* swhrc, double* bndsolvar, double* indsolvar, double* solcycfrac);
 
+
+/* ============================== gray longwave ==============================
+ * Replaces the numba kernel `_gray_lw_kernel_np` and the flux-divergence arithmetic of
+ * GrayLongwaveRadiation.array_call (climt/_components/radiation.py:65-109,162-190).  Stateless.
+ * t (nlay, ncol) [K], tau, p_int (nlay+1, ncol) [-, Pa], t_surf (ncol) -> lw_down, lw_up (nlay+1, ncol) [W m-2],
+ * tendency (nlay, ncol) [K s-1].  sigma [W m-2 K-4], g [m s-2], cpd [J kg-1 K-1]. */
+int cb200_gray_lw_run_device(int device, int ncol, int nlay, const double* t, const double* p_int, const double* t_surf,
+                             const double* tau, double sigma, double g, double cpd, double* lw_down, double* lw_up,
+                             double* tendency, void* stream);
+int cb200_gray_lw_run_host(int device, int ncol, int nlay, const double* t, const double* p_int, const double* t_surf,
+                           const double* tau, double sigma, double g, double cpd, double* lw_down, double* lw_up,
+                           double* tendency);
+
 #ifdef __cplusplus
 }
 #endif

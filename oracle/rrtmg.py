@@ -163,3 +163,29 @@ class SWOracle:
         if rc:
             raise RuntimeError(L.orc_sw_last_error().decode())
         return out
+
+
+def lw_mcica(oracle, st, permuteseed, irng=1, return_mask=False):
+    """McICA longwave through the oracle (mcica_subcol_lw + rrtmg_lw mcica).  `oracle` is an initialised LWOracle
+    (its flags give icld / inflag / iceflag / liqflag); st uses the oracle's short names."""
+    nlay, ncol = st["play"].shape
+    f = oracle.flags
+    order = ("play", "plev", "tlay", "tlev", "tsfc", "h2o", "o3", "co2", "ch4", "n2o", "o2", "cfc11", "cfc12", "cfc22",
+             "ccl4", "emis")
+    a = [_c(st[k]) for k in order]
+    cl = [_c(st[k]) for k in ("cldfr", "taucld", "cicewp", "cliqwp", "reice", "reliq", "tauaer")]
+    out = {k: np.zeros((nlay + 1, ncol)) for k in ("uflx", "dflx", "uflxc", "dflxc")}
+    out.update({k: np.zeros((nlay, ncol)) for k in ("hr", "hrc")})
+    mask = np.zeros((nlay, ncol, 140)) if return_mask else None
+    icld = ctypes.c_int(f["icld"])
+    L = lib()
+    rc = L.orc_lw_mcica(ctypes.c_int(ncol), ctypes.c_int(nlay), ctypes.byref(icld), ctypes.c_int(int(permuteseed)),
+                        ctypes.c_int(irng), *[_p(x) for x in a], ctypes.c_int(f["inflag"]), ctypes.c_int(f["iceflag"]),
+                        ctypes.c_int(f["liqflag"]), *[_p(x) for x in cl],
+                        _p(out["uflx"]), _p(out["dflx"]), _p(out["hr"]), _p(out["uflxc"]), _p(out["dflxc"]), _p(out["hrc"]),
+                        _p(mask) if return_mask else None)
+    if rc:
+        raise RuntimeError(L.orc_last_error().decode())
+    if return_mask:
+        out["mask"] = mask
+    return out

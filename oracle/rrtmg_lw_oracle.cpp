@@ -1723,3 +1723,455 @@ extern "C" int orc_lw_nomcica(int ncol, int nlay, int* icld, int idrv, const dou
   }
   return 0;
 }
+
+// =============================================================================================
+// McICA longwave: mcica_subcol_lw + cldprmc + rtrnmc (rrtmg_lw_rad.f90:80-576)
+namespace orc {
+
+// MersenneTwister (mcica_random_numbers.f90:60-300), signed 32-bit arithmetic as in the Fortran
+struct MT19937 {
+  int32_t state[624];
+  int cur;
+  static int32_t shr(int32_t x, int n) { return (int32_t)((uint32_t)x >> n); }
+  static int32_t shl(int32_t x, int n) { return (int32_t)((uint32_t)x << n); }
+  explicit MT19937(int32_t seed) {  // initialize_scalar :169-185
+    state[0] = seed;
+    for (int i = 1; i < 624; ++i) {
+      uint32_t prev = (uint32_t)state[i - 1];
+      state[i] = (int32_t)(1812433253u * (prev ^ (prev >> 30)) + (uint32_t)i);
+    }
+    cur = 624;
+  }
+  static int32_t mixbits(int32_t u, int32_t v) { return (int32_t)(((uint32_t)u & 0x80000000u) | ((uint32_t)v & 0x7fffffffu)); }
+  static int32_t twist(int32_t u, int32_t v) {
+    const int32_t t_matrix[2] = {0, (int32_t)0x9908b0dfu};
+    return shr(mixbits(u, v), 1) ^ t_matrix[v & 1];
+  }
+  void nextState() {  // :116-133
+    const int M = 397, N = 624;
+    for (int k = 0; k <= N - M - 1; ++k) state[k] = state[k + M] ^ twist(state[k], state[k + 1]);
+    for (int k = N - M; k <= N - 2; ++k) state[k] = state[k + M - N] ^ twist(state[k], state[k + 1]);
+    state[N - 1] = state[M - 1] ^ twist(state[N - 1], state[0]);
+    cur = 0;
+  }
+  static int32_t temper(int32_t y) {  // :154-165
+    int32_t x = y ^ shr(y, 11);
+    x = x ^ (shl(x, 7) & (int32_t)0x9d2c5680u);
+    x = x ^ (shl(x, 15) & (int32_t)0xefc60000u);
+    return x ^ shr(x, 18);
+  }
+  int32_t getRandomInt() {
+    if (cur >= 624) nextState();
+    return temper(state[cur++]);
+  }
+  double getRandomReal() {  // :276-295 -- note the default-real (float32) numerator for negative integers
+    int32_t localInt = getRandomInt();
+    if (localInt < 0) {
+      float num = (float)localInt + 4294967296.0f;
+      return (double)num / (4294967296.0 - 1.0);
+    }
+    return (double)localInt / (4294967296.0 - 1.0);
+  }
+};
+
+// kissvec (mcica_subcol_gen_lw.f90:530-562) for one column, wrap-around int32 arithmetic
+struct Kiss {
+  int32_t s1, s2, s3, s4;
+  static int32_t m(int32_t k, int n) {
+    uint32_t u = (uint32_t)k;
+    uint32_t sh = n >= 0 ? (u << n) : (u >> (-n));
+    return (int32_t)(u ^ sh);
+  }
+  double next() {
+    s1 = (int32_t)(69069u * (uint32_t)s1 + 1327217885u);
+    s2 = m(m(m(s2, 13), -17), 5);
+    s3 = (int32_t)(18000u * ((uint32_t)s3 & 65535u) + ((uint32_t)s3 >> 16));
+    s4 = (int32_t)(30903u * ((uint32_t)s4 & 65535u) + ((uint32_t)s4 >> 16));
+    int32_t kiss = (int32_t)((uint32_t)s1 + (uint32_t)s2 + ((uint32_t)s3 << 16) + (uint32_t)s4);
+    return kiss * 2.328306e-10 + 0.5;
+  }
+};
+
+// generate_stochastic_clouds (mcica_subcol_gen_lw.f90:156-522).  Arrays: cld/clwp/ciwp (ncol,nlay) column-fastest,
+// tauc (nb, ncol, nlay); outputs (nsub, ncol, nlay) with nsub fastest.  ngb maps sub-column -> band (1-based).
+static int generate_stochastic_clouds(int ncol, int nlay, int nsub, int icld, int irng, const double* pmid,
+                                      const double* cld, const double* clwp, const double* ciwp, const double* tauc,
+                                      int nb, const int* ngb, int bandoff, double* cld_stoch, double* clwp_stoch,
+                                      double* ciwp_stoch, double* tauc_stoch, int changeSeed, std::string& err) {
+  const double cldmin = 1.0e-20;
+  if (irng != 0) irng = 1;
+  auto C2 = [&](const double* a, int i, int l) { return a[(size_t)i + (size_t)ncol * l]; };  // 0-based
+  std::vector<double> cldf((size_t)ncol * nlay);
+  for (int l = 0; l < nlay; ++l)
+    for (int i = 0; i < ncol; ++i) {
+      double v = C2(cld, i, l);
+      cldf[(size_t)i + (size_t)ncol * l] = v < cldmin ? 0. : v;
+    }
+  std::vector<double> CDF((size_t)nsub * ncol * nlay);
+  auto X = [&](int s, int i, int l) -> double& { return CDF[(size_t)s + (size_t)nsub * ((size_t)i + (size_t)ncol * l)]; };
+  std::vector<Kiss> ks;
+  MT19937 mt(changeSeed);
+  if (irng == 0) {
+    ks.resize(ncol);
+    for (int i = 0; i < ncol; ++i) {
+      if (nlay < 4 || C2(pmid, i, 0) < C2(pmid, i, 1)) { err = "MCICA_SUBCOL: KISSVEC SEED GENERATOR REQUIRES PMID FROM BOTTOM FOUR LAYERS."; return 1; }
+      auto sd = [&](int l) { double p = C2(pmid, i, l); return (int32_t)((p - (double)(int)p) * 1000000000.0); };
+      ks[i].s1 = sd(0); ks[i].s2 = sd(1); ks[i].s3 = sd(2); ks[i].s4 = sd(3);
+    }
+    for (int k = 1; k <= changeSeed; ++k)
+      for (int i = 0; i < ncol; ++i) ks[i].next();
+  }
+  if (icld == 1 || icld == 2) {
+    if (irng == 0) {
+      for (int s = 0; s < nsub; ++s)
+        for (int l = 0; l < nlay; ++l)
+          for (int i = 0; i < ncol; ++i) X(s, i, l) = ks[i].next();
+    } else {
+      for (int s = 0; s < nsub; ++s)
+        for (int i = 0; i < ncol; ++i)
+          for (int l = 0; l < nlay; ++l) X(s, i, l) = mt.getRandomReal();
+    }
+    if (icld == 2)
+      for (int l = 1; l < nlay; ++l)
+        for (int i = 0; i < ncol; ++i)
+          for (int s = 0; s < nsub; ++s) {
+            double cf = cldf[(size_t)i + (size_t)ncol * (l - 1)];
+            if (X(s, i, l - 1) > 1. - cf) X(s, i, l) = X(s, i, l - 1);
+            else X(s, i, l) = X(s, i, l) * (1. - cf);
+          }
+  } else if (icld == 3) {
+    if (irng == 0) {
+      for (int s = 0; s < nsub; ++s)
+        for (int i = 0; i < ncol; ++i) {
+          double r = ks[i].next();
+          for (int l = 0; l < nlay; ++l) X(s, i, l) = r;
+        }
+    } else {
+      for (int s = 0; s < nsub; ++s)
+        for (int i = 0; i < ncol; ++i) {
+          double r = mt.getRandomReal();
+          for (int l = 0; l < nlay; ++l) X(s, i, l) = r;
+        }
+    }
+  }
+  for (int l = 0; l < nlay; ++l)
+    for (int i = 0; i < ncol; ++i)
+      for (int s = 0; s < nsub; ++s) {
+        size_t o = (size_t)s + (size_t)nsub * ((size_t)i + (size_t)ncol * l);
+        bool cloudy = X(s, i, l) >= 1. - cldf[(size_t)i + (size_t)ncol * l];
+        if (cloudy) {
+          cld_stoch[o] = 1.;
+          clwp_stoch[o] = C2(clwp, i, l);
+          ciwp_stoch[o] = C2(ciwp, i, l);
+          int n = ngb[s] - bandoff;  // 1-based band within the tauc array
+          tauc_stoch[o] = tauc[(size_t)(n - 1) + (size_t)nb * ((size_t)i + (size_t)ncol * l)];
+        } else {
+          cld_stoch[o] = 0.; clwp_stoch[o] = 0.; ciwp_stoch[o] = 0.; tauc_stoch[o] = 0.;
+        }
+      }
+  return 0;
+}
+
+static int ngb_lw_[140];
+static void init_ngb_lw() {
+  int ib = 1;
+  for (int ig = 1; ig <= 140; ++ig) {
+    while (ig > ngs_[ib - 1]) ++ib;
+    ngb_lw_[ig - 1] = ib;
+  }
+}
+
+// cldprmc — rrtmg_lw_cldprmc.f90:32-254 (per column; cldfmc/ciwpmc/clwpmc/taucmc are (140, nlay), 1-based views)
+static int cldprmc(int nlayers, int inflag, int iceflag, int liqflag, const A2& cldfmc, const A2& ciwpmc, const A2& clwpmc,
+                   const A1& reicmc, const A1& relqmc, A2& taucmc, std::string& err) {
+  const double cldmin = 1.e-20;
+  static const int icb[16] = {1, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5};
+  double abscoice[141] = {0}, abscoliq[141] = {0};
+  for (int lay = 1; lay <= nlayers; ++lay)
+    for (int ig = 1; ig <= ngptlw; ++ig) {
+      double cwp = ciwpmc(ig, lay) + clwpmc(ig, lay);
+      if (cldfmc(ig, lay) >= cldmin && (cwp >= cldmin || taucmc(ig, lay) >= cldmin)) {
+        if (inflag == 0) return 0;
+        else if (inflag == 1) { err = "INFLAG = 1 OPTION NOT AVAILABLE WITH MCICA"; return 1; }
+        else if (inflag == 2) {
+          double radice = reicmc(lay);
+          if (ciwpmc(ig, lay) == 0.0) abscoice[ig] = 0.0;
+          else if (iceflag == 0) {
+            if (radice < 10.0) { err = "ICE RADIUS TOO SMALL"; return 1; }
+            abscoice[ig] = S.absice0(1) + S.absice0(2) / radice;
+          } else if (iceflag == 1) {
+            if (radice < 13.0 || radice > 130.) { err = "ICE RADIUS OUT OF BOUNDS"; return 1; }
+            int ib = icb[ngb_lw_[ig - 1] - 1];
+            abscoice[ig] = S.absice1(1, ib) + S.absice1(2, ib) / radice;
+          } else if (iceflag == 2) {
+            if (radice < 5.0 || radice > 131.0) { err = "ICE RADIUS OUT OF BOUNDS"; return 1; }
+            double factor = (radice - 2.) / 3.;
+            int index = (int)factor;
+            if (index == 43) index = 42;
+            double fint = factor - (double)(float)index;
+            int ib = ngb_lw_[ig - 1];
+            abscoice[ig] = S.absice2(index, ib) + fint * (S.absice2(index + 1, ib) - (S.absice2(index, ib)));
+          } else if (iceflag == 3) {
+            if (radice < 5.0 || radice > 140.0) { err = "ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS"; return 1; }
+            double factor = (radice - 2.) / 3.;
+            int index = (int)factor;
+            if (index == 46) index = 45;
+            double fint = factor - (double)(float)index;
+            int ib = ngb_lw_[ig - 1];
+            abscoice[ig] = S.absice3(index, ib) + fint * (S.absice3(index + 1, ib) - (S.absice3(index, ib)));
+          }
+          if (clwpmc(ig, lay) == 0.0) abscoliq[ig] = 0.0;
+          else if (liqflag == 0) abscoliq[ig] = S.absliq0;
+          else if (liqflag == 1) {
+            double radliq = relqmc(lay);
+            if (radliq < 2.5 || radliq > 60.) { err = "LIQUID EFFECTIVE RADIUS OUT OF BOUNDS"; return 1; }
+            int index = (int)(radliq - 1.5);
+            if (index == 0) index = 1;
+            if (index == 58) index = 57;
+            double fint = radliq - 1.5 - (double)(float)index;
+            int ib = ngb_lw_[ig - 1];
+            abscoliq[ig] = S.absliq1(index, ib) + fint * (S.absliq1(index + 1, ib) - (S.absliq1(index, ib)));
+          }
+          taucmc(ig, lay) = ciwpmc(ig, lay) * abscoice[ig] + clwpmc(ig, lay) * abscoliq[ig];
+        }
+      }
+    }
+  return 0;
+}
+
+// rtrnmc — rrtmg_lw_rtrnmc.f90:32-576 (idrv = 0 path)
+static void rtrnmc(Col& c, int istart, int iend, const A2& cldfmc, const A2& taucmc, Flux& F) {
+  const int nlayers = c.nlayers;
+  const double wtdiff = 0.5, rec_6 = 0.166667, tblint = 10000.0, bpade = S.bpade;
+  const std::vector<double>&tau_tbl = S.tau_tbl, &exp_tbl = S.exp_tbl, &tfn_tbl = S.tfn_tbl;
+  int n = nlayers + 2;
+  A1 urad(n, 0), drad(n, 0), clrurad(n, 0), clrdrad(n, 0), atrans(n), atot(n), bbugas(n), bbutot(n);
+  A2 odcld(n, 140), abscld(n, 140), efclfrac(n, 140);
+  std::vector<int> icldlyr(n, 0);
+  double secdiff[17];
+  for (int ibnd = 1; ibnd <= nbndlw; ++ibnd) {
+    if (ibnd == 1 || ibnd == 4 || ibnd >= 10) secdiff[ibnd] = 1.66;
+    else {
+      secdiff[ibnd] = a0_[ibnd - 1] + a1_[ibnd - 1] * std::exp(a2_[ibnd - 1] * c.pwvcm);
+      if (secdiff[ibnd] > 1.80) secdiff[ibnd] = 1.80;
+      if (secdiff[ibnd] < 1.50) secdiff[ibnd] = 1.50;
+    }
+  }
+  for (int lay = 0; lay <= nlayers; ++lay) {
+    urad(lay) = 0.; drad(lay) = 0.; F.totuflux(lay) = 0.; F.totdflux(lay) = 0.;
+    clrurad(lay) = 0.; clrdrad(lay) = 0.; F.totuclfl(lay) = 0.; F.totdclfl(lay) = 0.;
+    if (lay == 0) continue;
+    icldlyr[lay] = 0;
+    for (int ig = 1; ig <= ngptlw; ++ig) {
+      if (cldfmc(ig, lay) == 1.) {
+        int ib = ngb_lw_[ig - 1];
+        odcld(lay, ig) = secdiff[ib] * taucmc(ig, lay);
+        double transcld = std::exp(-odcld(lay, ig));
+        abscld(lay, ig) = 1. - transcld;
+        efclfrac(lay, ig) = abscld(lay, ig) * cldfmc(ig, lay);
+        icldlyr[lay] = 1;
+      } else {
+        odcld(lay, ig) = 0.; abscld(lay, ig) = 0.; efclfrac(lay, ig) = 0.;
+      }
+    }
+  }
+  int igc = 1;
+  for (int iband = istart; iband <= iend; ++iband) {
+    do {
+      double radld = 0., radclrd = 0.;
+      int iclddn = 0;
+      for (int lev = nlayers; lev >= 1; --lev) {
+        double plfrac = c.fracs(lev, igc), blay = c.planklay(lev, iband);
+        double dplankup = c.planklev(lev, iband) - blay, dplankdn = c.planklev(lev - 1, iband) - blay;
+        double odepth = secdiff[iband] * c.taut(lev, igc);
+        if (odepth < 0.0) odepth = 0.0;
+        double bbd;
+        if (icldlyr[lev] == 1) {
+          iclddn = 1;
+          double odtot = odepth + odcld(lev, igc), gassrc, bbdtot;
+          if (odtot < 0.06) {
+            atrans(lev) = odepth - 0.5 * odepth * odepth;
+            double odepth_rec = rec_6 * odepth;
+            gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans(lev);
+            atot(lev) = odtot - 0.5 * odtot * odtot;
+            double odtot_rec = rec_6 * odtot;
+            bbdtot = plfrac * (blay + dplankdn * odtot_rec);
+            bbd = plfrac * (blay + dplankdn * odepth_rec);
+            bbugas(lev) = plfrac * (blay + dplankup * odepth_rec);
+            bbutot(lev) = plfrac * (blay + dplankup * odtot_rec);
+          } else if (odepth <= 0.06) {
+            atrans(lev) = odepth - 0.5 * odepth * odepth;
+            double odepth_rec = rec_6 * odepth;
+            gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans(lev);
+            odtot = odepth + odcld(lev, igc);
+            double tblind = odtot / (bpade + odtot);
+            int ittot = f2i(tblint * tblind + 0.5);
+            double tfactot = tfn_tbl[ittot];
+            bbdtot = plfrac * (blay + tfactot * dplankdn);
+            bbd = plfrac * (blay + dplankdn * odepth_rec);
+            atot(lev) = 1. - exp_tbl[ittot];
+            bbugas(lev) = plfrac * (blay + dplankup * odepth_rec);
+            bbutot(lev) = plfrac * (blay + tfactot * dplankup);
+          } else {
+            double tblind = odepth / (bpade + odepth);
+            int itgas = f2i(tblint * tblind + 0.5);
+            odepth = tau_tbl[itgas];
+            atrans(lev) = 1. - exp_tbl[itgas];
+            double tfacgas = tfn_tbl[itgas];
+            gassrc = atrans(lev) * plfrac * (blay + tfacgas * dplankdn);
+            odtot = odepth + odcld(lev, igc);
+            tblind = odtot / (bpade + odtot);
+            int ittot = f2i(tblint * tblind + 0.5);
+            double tfactot = tfn_tbl[ittot];
+            bbdtot = plfrac * (blay + tfactot * dplankdn);
+            bbd = plfrac * (blay + tfacgas * dplankdn);
+            atot(lev) = 1. - exp_tbl[ittot];
+            bbugas(lev) = plfrac * (blay + tfacgas * dplankup);
+            bbutot(lev) = plfrac * (blay + tfactot * dplankup);
+          }
+          radld = radld - radld * (atrans(lev) + efclfrac(lev, igc) * (1. - atrans(lev))) + gassrc +
+                  cldfmc(igc, lev) * (bbdtot * atot(lev) - gassrc);
+          drad(lev - 1) = drad(lev - 1) + radld;
+        } else {
+          if (odepth <= 0.06) {
+            atrans(lev) = odepth - 0.5 * odepth * odepth;
+            odepth = rec_6 * odepth;
+            bbd = plfrac * (blay + dplankdn * odepth);
+            bbugas(lev) = plfrac * (blay + dplankup * odepth);
+          } else {
+            double tblind = odepth / (bpade + odepth);
+            int itr = f2i(tblint * tblind + 0.5);
+            double transc = exp_tbl[itr];
+            atrans(lev) = 1. - transc;
+            double tausfac = tfn_tbl[itr];
+            bbd = plfrac * (blay + tausfac * dplankdn);
+            bbugas(lev) = plfrac * (blay + tausfac * dplankup);
+          }
+          radld = radld + (bbd - radld) * atrans(lev);
+          drad(lev - 1) = drad(lev - 1) + radld;
+        }
+        if (iclddn == 1) {
+          radclrd = radclrd + (bbd - radclrd) * atrans(lev);
+          clrdrad(lev - 1) = clrdrad(lev - 1) + radclrd;
+        } else {
+          radclrd = radld;
+          clrdrad(lev - 1) = drad(lev - 1);
+        }
+      }
+      double rad0 = c.fracs(1, igc) * c.plankbnd[iband];
+      double reflect = 1. - c.semiss[iband];
+      double radlu = rad0 + reflect * radld, radclru = rad0 + reflect * radclrd;
+      urad(0) = urad(0) + radlu;
+      clrurad(0) = clrurad(0) + radclru;
+      for (int lev = 1; lev <= nlayers; ++lev) {
+        if (icldlyr[lev] == 1) {
+          double gassrc = bbugas(lev) * atrans(lev);
+          radlu = radlu - radlu * (atrans(lev) + efclfrac(lev, igc) * (1. - atrans(lev))) + gassrc +
+                  cldfmc(igc, lev) * (bbutot(lev) * atot(lev) - gassrc);
+          urad(lev) = urad(lev) + radlu;
+        } else {
+          radlu = radlu + (bbugas(lev) - radlu) * atrans(lev);
+          urad(lev) = urad(lev) + radlu;
+        }
+        if (iclddn == 1) {
+          radclru = radclru + (bbugas(lev) - radclru) * atrans(lev);
+          clrurad(lev) = clrurad(lev) + radclru;
+        } else {
+          radclru = radlu;
+          clrurad(lev) = urad(lev);
+        }
+      }
+      igc = igc + 1;
+    } while (igc <= ngs_[iband - 1]);
+    for (int lev = nlayers; lev >= 0; --lev) {
+      double uflux = urad(lev) * wtdiff, dflux = drad(lev) * wtdiff;
+      urad(lev) = 0.; drad(lev) = 0.;
+      F.totuflux(lev) = F.totuflux(lev) + uflux * delwave_[iband - 1];
+      F.totdflux(lev) = F.totdflux(lev) + dflux * delwave_[iband - 1];
+      double uclfl = clrurad(lev) * wtdiff, dclfl = clrdrad(lev) * wtdiff;
+      clrurad(lev) = 0.; clrdrad(lev) = 0.;
+      F.totuclfl(lev) = F.totuclfl(lev) + uclfl * delwave_[iband - 1];
+      F.totdclfl(lev) = F.totdclfl(lev) + dclfl * delwave_[iband - 1];
+    }
+  }
+  F.totuflux(0) = F.totuflux(0) * S.fluxfac; F.totdflux(0) = F.totdflux(0) * S.fluxfac;
+  F.fnet(0) = F.totuflux(0) - F.totdflux(0);
+  F.totuclfl(0) = F.totuclfl(0) * S.fluxfac; F.totdclfl(0) = F.totdclfl(0) * S.fluxfac;
+  F.fnetc(0) = F.totuclfl(0) - F.totdclfl(0);
+  for (int lev = 1; lev <= nlayers; ++lev) {
+    F.totuflux(lev) = F.totuflux(lev) * S.fluxfac; F.totdflux(lev) = F.totdflux(lev) * S.fluxfac;
+    F.fnet(lev) = F.totuflux(lev) - F.totdflux(lev);
+    F.totuclfl(lev) = F.totuclfl(lev) * S.fluxfac; F.totdclfl(lev) = F.totdclfl(lev) * S.fluxfac;
+    F.fnetc(lev) = F.totuclfl(lev) - F.totdclfl(lev);
+    int l = lev - 1;
+    F.htr(l) = S.heatfac * (F.fnet(l) - F.fnet(lev)) / (c.pz(l) - c.pz(lev));
+    F.htrc(l) = S.heatfac * (F.fnetc(l) - F.fnetc(lev)) / (c.pz(l) - c.pz(lev));
+  }
+  F.htr(nlayers) = 0.; F.htrc(nlayers) = 0.;
+}
+}  // namespace orc
+
+// mcica_subcol_lw_wrapper + rrtmg_lw_mcica_wrapper (rrtmg_lw_c_binder.f90:50-174), as chained by
+// _rrtmg_lw.pyx:214-320.  cldfmcl_out (140, ncol, nlay) may be null (debug: the generated cloud mask).
+extern "C" int orc_lw_mcica(int ncol, int nlay, int* icld, int permuteseed, int irng, const double* play,
+                            const double* plev, const double* tlay, const double* tlev, const double* tsfc,
+                            const double* h2ovmr, const double* o3vmr, const double* co2vmr, const double* ch4vmr,
+                            const double* n2ovmr, const double* o2vmr, const double* cfc11vmr, const double* cfc12vmr,
+                            const double* cfc22vmr, const double* ccl4vmr, const double* emis, int inflglw, int iceflglw,
+                            int liqflglw, const double* cldfr, const double* taucld, const double* cicewp,
+                            const double* cliqwp, const double* reice, const double* reliq, const double* tauaer,
+                            double* uflx, double* dflx, double* hr, double* uflxc, double* dflxc, double* hrc,
+                            double* cldfmcl_out) {
+  if (!S.ready) { g_err = "orc_lw_ini not called"; return 1; }
+  init_ngb_lw();
+  S.oneminus = 1. - 1.e-6;
+  S.pi = 2. * std::asin(1.);
+  S.fluxfac = S.pi * 2.e4;
+  if (*icld < 0 || *icld > 3) { g_err = "MCICA_SUBCOL: INVALID ICLD"; return 2; }
+  const size_t nsub = 140, tot = nsub * (size_t)ncol * nlay;
+  std::vector<double> cldfmcl(tot, 0.), ciwpmcl(tot, 0.), clwpmcl(tot, 0.), taucmcl(tot, 0.);
+  if (*icld != 0) {
+    std::vector<double> pmid((size_t)ncol * nlay);
+    for (size_t i = 0; i < pmid.size(); ++i) pmid[i] = play[i] * 1.e2;
+    if (generate_stochastic_clouds(ncol, nlay, 140, *icld, irng, pmid.data(), cldfr, cliqwp, cicewp, taucld, 16, ngb_lw_,
+                                   0, cldfmcl.data(), clwpmcl.data(), ciwpmcl.data(), taucmcl.data(), permuteseed, g_err))
+      return 2;
+  }
+  if (cldfmcl_out) std::memcpy(cldfmcl_out, cldfmcl.data(), tot * sizeof(double));
+  const int istart = 1, iend = 16, iaer = 10, idrv = 0;
+  LwIn in{ncol, nlay, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, cfc11vmr, cfc12vmr,
+          cfc22vmr, ccl4vmr, emis, cldfr, taucld, cicewp, cliqwp, reice, reliq, tauaer};
+  Col c(nlay);
+  Flux F(nlay);
+  A2 cldfmc(140, nlay + 1), taucmc(140, nlay + 1), ciwpmc(140, nlay + 1), clwpmc(140, nlay + 1);
+  A1 reicmc(nlay + 1), relqmc(nlay + 1);
+  for (int iplon = 1; iplon <= ncol; ++iplon) {
+    inatm(in, iplon, 0, iaer, inflglw, iceflglw, liqflglw, c);  // gas/aerosol part (cloud copy is per g-point below)
+    std::fill(cldfmc.d.begin(), cldfmc.d.end(), 0.); std::fill(taucmc.d.begin(), taucmc.d.end(), 0.);
+    std::fill(ciwpmc.d.begin(), ciwpmc.d.end(), 0.); std::fill(clwpmc.d.begin(), clwpmc.d.end(), 0.);
+    if (*icld >= 1)
+      for (int l = 1; l <= nlay; ++l) {
+        for (int ig = 1; ig <= 140; ++ig) {
+          size_t o = (size_t)(ig - 1) + nsub * ((size_t)(iplon - 1) + (size_t)ncol * (l - 1));
+          cldfmc(ig, l) = cldfmcl[o]; taucmc(ig, l) = taucmcl[o]; ciwpmc(ig, l) = ciwpmcl[o]; clwpmc(ig, l) = clwpmcl[o];
+        }
+        reicmc(l) = reice[(size_t)(iplon - 1) + (size_t)ncol * (l - 1)];
+        relqmc(l) = reliq[(size_t)(iplon - 1) + (size_t)ncol * (l - 1)];
+      }
+    if (cldprmc(nlay, inflglw, iceflglw, liqflglw, cldfmc, ciwpmc, clwpmc, reicmc, relqmc, taucmc, g_err)) return 2;
+    setcoef(c, istart, idrv);
+    taumol(c);
+    for (int k = 1; k <= nlay; ++k)
+      for (int ig = 1; ig <= ngptlw; ++ig) c.taut(k, ig) = c.taug(k, ig) + c.taua(k, ngb_lw_[ig - 1]);
+    rtrnmc(c, istart, iend, cldfmc, taucmc, F);
+    for (int k = 0; k <= nlay; ++k) {
+      size_t o = (size_t)(iplon - 1) + (size_t)ncol * k;
+      uflx[o] = F.totuflux(k); dflx[o] = F.totdflux(k); uflxc[o] = F.totuclfl(k); dflxc[o] = F.totdclfl(k);
+    }
+    for (int k = 0; k <= nlay - 1; ++k) {
+      size_t o = (size_t)(iplon - 1) + (size_t)ncol * k;
+      hr[o] = F.htr(k); hrc[o] = F.htrc(k);
+    }
+  }
+  return 0;
+}

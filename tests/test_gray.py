@@ -1,0 +1,45 @@
+"""Gray longwave (BASELINE config 1): oracle vs the reference golden (CPU); CUDA kernel vs oracle (GPU)."""
+import numpy as np
+import pytest
+
+import helpers as H
+from climt_b200 import constants as C, state as S
+from oracle.gray import gray_lw
+
+K = dict(sigma=C.get_constant("stefan_boltzmann_constant"), g=C.get_constant("gravitational_acceleration"),
+         cpd=C.get_constant("heat_capacity_of_dry_air_at_constant_pressure"))
+
+
+@pytest.mark.parametrize("kind,nz", [("column", 30), ("3d", 28)])
+def test_gray_oracle_matches_reference_golden(kind, nz):
+    g = H.golden()
+    st = S.default_gray_state(nz, 1)
+    o = gray_lw(st["air_temperature"], st["air_pressure_on_interface_levels"], st["surface_temperature"],
+                st["longwave_optical_depth_on_interface_levels"], **K)
+    cls = "TestGrayLongwaveRadiation"
+    np.testing.assert_allclose(o["lw_up"][:, 0], g[f"{cls}-{kind}/diag/upwelling_longwave_flux_in_air"][:, 0, 0], rtol=1e-14)
+    np.testing.assert_allclose(o["lw_down"][:, 0], g[f"{cls}-{kind}/diag/downwelling_longwave_flux_in_air"][:, 0, 0], rtol=1e-14, atol=1e-13)
+    np.testing.assert_allclose(o["tendency_per_day"][:, 0], g[f"{cls}-{kind}/diag/air_temperature_tendency_from_longwave"][:, 0, 0], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(o["tendency"][:, 0], g[f"{cls}-{kind}/tend/air_temperature"][:, 0, 0], rtol=1e-10, atol=1e-16)
+
+
+@pytest.mark.gpu
+def test_gray_cuda_matches_oracle_and_golden():
+    from climt_b200.gray import GrayLongwaveRadiation, gray_lw_host
+    rng = np.random.default_rng(0)
+    nz, ncol = 30, 3000
+    st = S.default_gray_state(nz, ncol, p_surf=rng.uniform(9.5e4, 1.03e5, ncol))
+    st["air_temperature"] = rng.uniform(200, 310, (nz, ncol))
+    st["surface_temperature"] = rng.uniform(250, 320, ncol)
+    ref = gray_lw(st["air_temperature"], st["air_pressure_on_interface_levels"], st["surface_temperature"],
+                  st["longwave_optical_depth_on_interface_levels"], **K)
+    down, up, tend = gray_lw_host(st["air_temperature"], st["air_pressure_on_interface_levels"], st["surface_temperature"],
+                                  st["longwave_optical_depth_on_interface_levels"], K["sigma"], K["g"], K["cpd"])
+    np.testing.assert_allclose(up, ref["lw_up"], rtol=1e-13)          # fp64; tolerance 1e-13 relative
+    np.testing.assert_allclose(down, ref["lw_down"], rtol=1e-13, atol=1e-12)
+    np.testing.assert_allclose(tend, ref["tendency"], rtol=1e-9, atol=1e-15)
+    g = H.golden()
+    d = S.default_gray_state(30, 1)
+    tend, diag = GrayLongwaveRadiation().array_call(d)
+    np.testing.assert_allclose(diag["lw_up"][:, 0], g["TestGrayLongwaveRadiation-column/diag/upwelling_longwave_flux_in_air"][:, 0, 0], rtol=1e-13)
+    np.testing.assert_allclose(tend["sl"][:, 0], g["TestGrayLongwaveRadiation-column/tend/air_temperature"][:, 0, 0], rtol=1e-9, atol=1e-15)
