@@ -12,7 +12,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("CLIMT_B200_SO") or os.path.join(_HERE, "libclimt_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lw_engine.cu", "sw_engine.cu", "gray_engine.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("cb_common.h", "engine_common.h", "lw_core.cuh", "lw_tables.h", "sw_core.cuh", "sw_tables.h")] + [
+HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("cb_common.h", "engine_common.h", "lw_core.cuh", "lw_tables.h", "sw_core.cuh", "sw_tables.h",
+                                                          "mcica_core.cuh", "mcica_host.h")] + [
     os.path.join(_HERE, "..", "include", "climt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "--fmad=false"]
@@ -76,7 +77,7 @@ EXPORTS = ["cb200_gray_lw_run_device", "cb200_gray_lw_run_host", "cb200_sw_creat
            "cb200_sw_run_host", "cb200_sw_check", "cb200_sw_last_error", "cb200_sw_last_launches",
            "cb200_sw_enable_timing", "cb200_sw_last_unit_kernel_ms", "rrtmg_sw_set_constants", "rrtmg_sw_ini_wrapper",
            "rrtmg_sw_nomcica_wrapper",
-           "cb200_lw_create", "cb200_lw_destroy", "cb200_lw_set_options", "cb200_lw_run_device",
+           "cb200_lw_create", "cb200_lw_destroy", "cb200_lw_set_options", "cb200_lw_set_mcica", "cb200_lw_run_device",
            "cb200_lw_run_host", "cb200_lw_check", "cb200_lw_last_error", "cb200_global_error",
            "cb200_lw_last_launches", "cb200_lw_enable_timing", "cb200_lw_last_unit_kernel_ms",
            "rrtmg_set_constants", "rrtmg_lw_ini_wrapper", "rrtmg_lw_nomcica_wrapper"]
@@ -98,6 +99,7 @@ def lib():
     L.cb200_lw_destroy.argtypes = [vp]
     L.cb200_lw_destroy.restype = None
     L.cb200_lw_set_options.argtypes = [vp] + [ctypes.c_int] * 5
+    L.cb200_lw_set_mcica.argtypes = [vp] + [ctypes.c_int] * 3
     L.cb200_lw_run_device.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(LwInputs),
                                       ctypes.POINTER(LwOutputs), vp]
     L.cb200_lw_run_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(LwInputs),

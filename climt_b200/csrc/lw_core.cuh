@@ -62,6 +62,7 @@ struct Out {
 };
 struct Flags {
   int icld, idrv, inflag, iceflag, liqflag;
+  int mcica;  // 0: rtrn (band cloud optics, fractional cloud); 1: McICA (rtrnmc: per-g-point 0/1 cloud mask)
 };
 struct Work {  // all sized for a chunk of ncc columns
   int ncc;
@@ -73,6 +74,8 @@ struct Work {  // all sized for a chunk of ncc columns
   double* cld;   // [2][16][nlay][ncc]  odcld, efclfrac
   double* scr;   // [140][4][nlay][ncc] atrans, bbugas, atot, bbutot
   double* part;  // [nunits][4][nlay+1][ncc] up, dn, upclr, dnclr  (un-weighted sums over the unit's g-points)
+  unsigned* mask; // [nlay][5][mstride] McICA cloud mask (+ moff), bit (g & 31) of word (g >> 5) set = sub-column g cloudy
+  int mstride, moff;
   int* err;      // [1]
 };
 
@@ -205,8 +208,66 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
     WS(F_SCALEMINOR, l) = scaleminor;
     WS(F_SCALEMINORN2, l) = scaleminorn2;
     W.idx[(size_t)l * ncc + c] = pack_idx(jp, jt, jt1, indself, indfor, indminor);
+    // ---- McICA: cldprmc (rrtmg_lw_cldprmc.f90:160-247).  Every cloudy sub-column of a layer carries the layer's
+    // water paths, so the per-g-point optical depth only depends on the g-point's band: one value per (layer, band).
+    if (clouds && fl.mcica) {
+      const double cldmin = 1.e-20;
+      const double ciwp = in.cicewp[o], clwp = in.cliqwp[o];
+      const double* tc = in.taucld + 16 * ((size_t)l * ncol + gc);
+      const double cwp = ciwp + clwp;
+      const int pat5[16] = {0, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4};
+      for (int ib = 0; ib < 16; ++ib) {
+        double tau = tc[ib];
+        if (cwp >= cldmin || tau >= cldmin) {
+          if (fl.inflag == 1) *W.err = 8;  // 'INFLAG = 1 OPTION NOT AVAILABLE WITH MCICA'
+          if (fl.inflag == 2) {
+            double aice = 0.0, aliq = 0.0;
+            const double radice = in.reice[o];
+            if (ciwp == 0.0) aice = 0.0;
+            else if (fl.iceflag == 0) {
+              if (radice < 10.0) *W.err = 1;
+              aice = tb[T.absice0] + tb[T.absice0 + 1] / radice;
+            } else if (fl.iceflag == 1) {
+              if (radice < 13.0 || radice > 130.) *W.err = 2;
+              aice = tb[T.absice1 + 2 * pat5[ib]] + tb[T.absice1 + 2 * pat5[ib] + 1] / radice;
+            } else if (fl.iceflag == 2 || fl.iceflag == 3) {
+              const double rmax = fl.iceflag == 2 ? 131.0 : 140.0;
+              if (radice < 5.0 || radice > rmax) { *W.err = fl.iceflag == 2 ? 2 : 3; }
+              else {
+                factor = (radice - 2.) / 3.;
+                int index = (int)factor;
+                const int top = fl.iceflag == 2 ? 43 : 46;
+                if (index == top) index = top - 1;
+                const double fint = factor - (double)index;
+                const int t0 = fl.iceflag == 2 ? T.absice2 : T.absice3;
+                const double k0 = tb[t0 + (index - 1) * 16 + ib], k1 = tb[t0 + index * 16 + ib];
+                aice = k0 + fint * (k1 - (k0));
+              }
+            }
+            if (clwp == 0.0) aliq = 0.0;
+            else if (fl.liqflag == 0) aliq = T.absliq0;
+            else if (fl.liqflag == 1) {
+              const double radliq = in.reliq[o];
+              if (radliq < 2.5 || radliq > 60.) { *W.err = 4; }
+              else {
+                int index = (int)(radliq - 1.5);
+                if (index == 0) index = 1;
+                if (index == 58) index = 57;
+                const double fint = radliq - 1.5 - (double)index;
+                const double k0 = tb[T.absliq1 + (index - 1) * 16 + ib], k1 = tb[T.absliq1 + index * 16 + ib];
+                aliq = k0 + fint * (k1 - (k0));
+              }
+            }
+            tau = ciwp * aice + clwp * aliq;
+          }
+        }
+        W.cld[((size_t)ib * nlay + l) * ncc + c] = tau;
+      }
+      if (in.cldfr[o] >= cldmin) anycld = true;
+      ncbands = 16;
+    }
     // ---- cldprop for this layer, rrtmg_lw_cldprop.f90:163-270 (taucloud parked in W.cld slot 0)
-    if (clouds) {
+    if (clouds && !fl.mcica) {
       double taucloud[16];
       for (int ib = 0; ib < 16; ++ib) taucloud[ib] = 0.0;
       const double cldfrac = in.cldfr[o];
@@ -318,12 +379,12 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
       for (int ib = 0; ib < 16; ++ib) {
         const size_t o0 = ((size_t)ib * nlay + l) * ncc + c;
         const size_t o1 = ((size_t)(16 + ib) * nlay + l) * ncc + c;
-        if (ib < ncbands && cldfrac >= 1.e-6) {
+        if (ib < ncbands && (fl.mcica || cldfrac >= 1.e-6)) {
           const double od = secdiff[ib] * W.cld[o0];
           const double transcld = exp(-od);
           const double abscld = 1. - transcld;
           W.cld[o0] = od;
-          W.cld[o1] = abscld * cldfrac;
+          W.cld[o1] = fl.mcica ? abscld : abscld * cldfrac;  // McICA: efclfrac = abscld * 1 (rtrnmc.f90:307)
         } else {
           W.cld[o0] = 0.0;
           W.cld[o1] = 0.0;
@@ -736,7 +797,7 @@ CB_HD double planck_band(const double* __restrict__ tp /* totplnk row of band */
 
 // ---------------------------------------------------------------------------------------------
 // lw_unit: taumol + rtrn for U g-points of band B in one column (rrtmg_lw_rtrn.f90:320-526).
-template <int B, int U>
+template <int B, int U, bool MC>
 CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int g0, int unit) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
@@ -782,17 +843,39 @@ CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, 
     const double dplankup = plev_up - blay;
     const double dplankdn = plev_dn - blay;
     plev_up = plev_dn;
-    const bool cloudy = ncb > 0 && in.cldfr[o] >= 1.e-6;
-    double odcld = 0., efclfrac = 0., cldfrac = 0.;
+    // non-McICA: a layer is cloudy when its cloud fraction is >= 1e-6 (rtrn.f90:302); McICA: when ANY sub-column
+    // of the layer is cloudy (rtrnmc.f90:298-309), each g-point then sees cloud fraction 0 or 1.
+    bool cloudy;
+    unsigned mbits = 0u;
+    double odcld_l = 0., efclfrac_l = 0., cldfrac_l = 0.;
+    if (MC) {
+      cloudy = false;
+      if (ncb > 0) {
+        const size_t ms = (size_t)W.mstride;
+        const unsigned* mw = W.mask + ((size_t)l * 5) * ms + W.moff + c;
+        const unsigned w0 = mw[0], w1 = mw[ms], w2 = mw[2 * ms], w3 = mw[3 * ms], w4 = mw[4 * ms];
+        cloudy = (w0 | w1 | w2 | w3 | w4) != 0u;
+        // the unit's <= 4 g-points never straddle a 32-bit word boundary twice; fetch their bits
+        for (int u = 0; u < U; ++u) {
+          const int g = gabs + u;
+          const unsigned w = (g >> 5) == 0 ? w0 : ((g >> 5) == 1 ? w1 : ((g >> 5) == 2 ? w2 : ((g >> 5) == 3 ? w3 : w4)));
+          mbits |= ((w >> (g & 31)) & 1u) << u;
+        }
+      }
+    } else {
+      cloudy = ncb > 0 && in.cldfr[o] >= 1.e-6;
+    }
     if (cloudy) {
       iclddn = 1;
-      cldfrac = in.cldfr[o];
-      odcld = W.cld[((size_t)ibc * nlay + l) * ncc + c];
-      efclfrac = W.cld[((size_t)(16 + ibc) * nlay + l) * ncc + c];
+      cldfrac_l = MC ? 1.0 : in.cldfr[o];
+      odcld_l = W.cld[((size_t)ibc * nlay + l) * ncc + c];
+      efclfrac_l = W.cld[((size_t)(16 + ibc) * nlay + l) * ncc + c];
     }
     double sum_d = 0., sum_dc = 0.;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      const bool on = !MC || ((mbits >> u) & 1u);
+      const double odcld = on ? odcld_l : 0., efclfrac = on ? efclfrac_l : 0., cldfrac = on ? cldfrac_l : 0.;
       const double plfrac = frac[u];
       double odepth = secdiff * (tau[u] + taua);
       if (odepth < 0.0) odepth = 0.0;
@@ -901,15 +984,34 @@ CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, 
   for (int lev = 1; lev <= nlay; ++lev) {
     const int l = lev - 1;
     const size_t o = (size_t)l * ncol + gc;
-    const bool cloudy = ncb > 0 && in.cldfr[o] >= 1.e-6;
-    double efclfrac = 0., cldfrac = 0.;
+    bool cloudy;
+    unsigned mbits = 0u;
+    if (MC) {
+      cloudy = false;
+      if (ncb > 0) {
+        const size_t ms = (size_t)W.mstride;
+        const unsigned* mw = W.mask + ((size_t)l * 5) * ms + W.moff + c;
+        const unsigned w0 = mw[0], w1 = mw[ms], w2 = mw[2 * ms], w3 = mw[3 * ms], w4 = mw[4 * ms];
+        cloudy = (w0 | w1 | w2 | w3 | w4) != 0u;
+        for (int u = 0; u < U; ++u) {
+          const int g = gabs + u;
+          const unsigned w = (g >> 5) == 0 ? w0 : ((g >> 5) == 1 ? w1 : ((g >> 5) == 2 ? w2 : ((g >> 5) == 3 ? w3 : w4)));
+          mbits |= ((w >> (g & 31)) & 1u) << u;
+        }
+      }
+    } else {
+      cloudy = ncb > 0 && in.cldfr[o] >= 1.e-6;
+    }
+    double efclfrac_l = 0., cldfrac_l = 0.;
     if (cloudy) {
-      cldfrac = in.cldfr[o];
-      efclfrac = W.cld[((size_t)(16 + ibc) * nlay + l) * ncc + c];
+      cldfrac_l = MC ? 1.0 : in.cldfr[o];
+      efclfrac_l = W.cld[((size_t)(16 + ibc) * nlay + l) * ncc + c];
     }
     double s = 0., sc = 0.;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      const bool on = !MC || ((mbits >> u) & 1u);
+      const double efclfrac = on ? efclfrac_l : 0., cldfrac = on ? cldfrac_l : 0.;
       const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * 4) * nlay + l) * ncc + c;
       const double atrans = scr[0], bbugas = scr[wstride];
       if (cloudy) {

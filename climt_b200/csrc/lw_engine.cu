@@ -11,6 +11,7 @@
 #include "../../include/climt_b200.h"
 #include "engine_common.h"
 #include "lw_tables.h"
+#include "mcica_host.h"
 
 using namespace cb::lw;
 
@@ -34,6 +35,7 @@ struct UnitList {
 
 // One block = 128 adjacent columns x one unit (<=4 g-points of one band): every branch on the band is
 // block-uniform, all global accesses are column-contiguous.
+template <bool MC>
 __global__ void __launch_bounds__(kBlock, CB_UNITS_MIN_BLOCKS) k_units(const __grid_constant__ Tables T, const __grid_constant__ In in,
                                                   const __grid_constant__ Work W, const __grid_constant__ UnitList UL,
                                                   int c0, int n) {
@@ -41,16 +43,24 @@ __global__ void __launch_bounds__(kBlock, CB_UNITS_MIN_BLOCKS) k_units(const __g
   if (c >= n) return;
   const int k = blockIdx.y;
   const Unit un = UL.u[k];
-#define CB_CASE(B)                                              \
-  case B:                                                       \
-    if (un.u == 4) lw_unit<B, 4>(T, in, W, c0, c, un.g0, k);    \
-    else lw_unit<B, 2>(T, in, W, c0, c, un.g0, k);              \
+#define CB_CASE(B)                                                  \
+  case B:                                                           \
+    if (un.u == 4) lw_unit<B, 4, MC>(T, in, W, c0, c, un.g0, k);    \
+    else lw_unit<B, 2, MC>(T, in, W, c0, c, un.g0, k);              \
     break;
   switch (un.band) {
     CB_CASE(1) CB_CASE(2) CB_CASE(3) CB_CASE(4) CB_CASE(5) CB_CASE(6) CB_CASE(7) CB_CASE(8)
     CB_CASE(9) CB_CASE(10) CB_CASE(11) CB_CASE(12) CB_CASE(13) CB_CASE(14) CB_CASE(15) CB_CASE(16)
   }
 #undef CB_CASE
+}
+
+// McICA cloud mask with the per-column kissvec generator: one thread per column
+__global__ void __launch_bounds__(kBlock) k_mask_kiss(const __grid_constant__ In in, const __grid_constant__ Work W,
+                                                      int icld, int seed, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  if (cb::mcica::mask_column_kiss(in.play, in.cldfr, in.ncol, in.nlay, 140, 5, icld, seed, W.mask, W.ncc, c0, c)) *W.err = 9;
 }
 
 __global__ void __launch_bounds__(kBlock) k_reduce(const __grid_constant__ Tables T, const __grid_constant__ Work W,
@@ -83,7 +93,10 @@ struct cb200_lw_engine {
   int device = 0;
   Tables T;
   double* d_tables = nullptr;
-  Flags fl{1, 0, 2, 1, 1};
+  Flags fl{1, 0, 2, 1, 1, 0};
+  int irng = 1, permuteseed = 0;
+  unsigned* d_mask_full = nullptr;
+  size_t mask_full_cap = 0;
   UnitList UL;
   // workspace (grown on demand)
   int cap_ncc = 0, cap_nlay = 0;
@@ -103,7 +116,7 @@ struct cb200_lw_engine {
 
   void free_work() {
     cudaFree(W.ws); cudaFree(W.idx); cudaFree(W.laytrop); cudaFree(W.ncbands); cudaFree(W.pwvcm);
-    cudaFree(W.cld); cudaFree(W.scr); cudaFree(W.part); cudaFree(W.err);
+    cudaFree(W.cld); cudaFree(W.scr); cudaFree(W.part); cudaFree(W.err); cudaFree(W.mask);
     W = Work{};
     cap_ncc = cap_nlay = 0;
   }
@@ -120,6 +133,7 @@ struct cb200_lw_engine {
     CUDA_OK(cudaMalloc(&W.cld, sizeof(double) * 32 * L * n));
     CUDA_OK(cudaMalloc(&W.scr, sizeof(double) * 140 * 4 * L * n));
     CUDA_OK(cudaMalloc(&W.part, sizeof(double) * UL.n * 4 * (L + 1) * n));
+    CUDA_OK(cudaMalloc(&W.mask, sizeof(unsigned) * 5 * L * n));
     CUDA_OK(cudaMalloc(&W.err, sizeof(int)));
     CUDA_OK(cudaMemset(W.err, 0, sizeof(int)));
     cap_ncc = ncc;
@@ -166,6 +180,7 @@ extern "C" void cb200_lw_destroy(cb200_lw_engine* e) {
   e->free_work();
   cudaFree(e->d_tables);
   cudaFree(e->d_stage);
+  cudaFree(e->d_mask_full);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   if (e->h_err) cudaFreeHost(e->h_err);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -176,8 +191,15 @@ extern "C" void cb200_lw_destroy(cb200_lw_engine* e) {
 extern "C" int cb200_lw_set_options(cb200_lw_engine* e, int icld, int idrv, int inflag, int iceflag, int liqflag) {
   if (icld < 0 || icld > 3) icld = 2;  // rrtmg_lw_rad.nomcica.f90:437
   if (idrv != 0) { e->error = "calculate_change_up_flux (idrv=1) is not implemented in the CUDA engine yet"; return -2; }
-  if (icld >= 2) { e->error = "maximum-random / maximum cloud overlap (icld=2,3) is not implemented in the CUDA engine yet"; return -2; }
-  e->fl = Flags{icld, idrv, inflag, iceflag, liqflag};
+  if (icld >= 2 && !e->fl.mcica) { e->error = "maximum-random / maximum cloud overlap (icld=2,3) without McICA (rtrnmr) is not implemented in the CUDA engine yet"; return -2; }
+  e->fl = Flags{icld, idrv, inflag, iceflag, liqflag, e->fl.mcica};
+  return 0;
+}
+
+extern "C" int cb200_lw_set_mcica(cb200_lw_engine* e, int enabled, int irng, int permuteseed) {
+  e->fl.mcica = enabled ? 1 : 0;
+  e->irng = irng != 0 ? 1 : 0;  // mcica_subcol_gen_lw.f90:303
+  e->permuteseed = permuteseed;
   return 0;
 }
 
@@ -211,12 +233,37 @@ extern "C" int cb200_lw_run_device(cb200_lw_engine* e, int ncol, int nlay, const
   Out out{pout->uflx, pout->dflx, pout->hr, pout->uflxc, pout->dflxc, pout->hrc};
   e->launches = 0;
   e->unit_ms = 0.0;
+  const bool mc = e->fl.mcica && e->fl.icld >= 1;
+  W.mstride = chunk;
+  W.moff = 0;
+  if (mc && e->irng == 1) {
+    // Mersenne twister: one serial stream for the whole call (bit parity with climt's default RNG) -> host
+    std::vector<double> h_cld((size_t)nlay * ncol);
+    CUDA_OK(cudaMemcpyAsync(h_cld.data(), in.cldfr, h_cld.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<unsigned> h_mask;
+    cb::mcica::mask_mt_host(h_cld.data(), ncol, nlay, 140, 5, e->fl.icld, e->permuteseed, h_mask);
+    if (h_mask.size() > e->mask_full_cap) {
+      cudaFree(e->d_mask_full);
+      e->d_mask_full = nullptr;
+      e->mask_full_cap = 0;
+      CUDA_OK(cudaMalloc(&e->d_mask_full, h_mask.size() * sizeof(unsigned)));
+      e->mask_full_cap = h_mask.size();
+    }
+    CUDA_OK(cudaMemcpyAsync(e->d_mask_full, h_mask.data(), h_mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    W.mask = e->d_mask_full;
+    W.mstride = ncol;
+  }
   for (int c0 = 0; c0 < ncol; c0 += chunk) {
     const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
     const int gx = (n + kBlock - 1) / kBlock;
+    if (mc && e->irng == 0) { k_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
+    if (mc && e->irng == 1) W.moff = c0;
     k_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
     if (e->timing) cudaEventRecord(e->ev0, st);
-    k_units<<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    if (mc) k_units<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    else k_units<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
     if (e->timing) cudaEventRecord(e->ev1, st);
     k_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(e->T, W, e->UL, out, nlay, ncol, c0, n);
     k_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
@@ -239,8 +286,10 @@ extern "C" int cb200_lw_check(cb200_lw_engine* e) {
   const int code = *e->h_err;
   if (code) {
     static const char* msg[] = {"", "ICE RADIUS TOO SMALL", "ICE RADIUS OUT OF BOUNDS",
-                                "ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS", "LIQUID EFFECTIVE RADIUS OUT OF BOUNDS"};
-    e->error = msg[code < 5 ? code : 2];  // message text of the Fortran `stop` (rrtmg_lw_cldprop.f90:193-243)
+                                "ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS", "LIQUID EFFECTIVE RADIUS OUT OF BOUNDS",
+                                "", "", "", "INFLAG = 1 OPTION NOT AVAILABLE WITH MCICA",
+                                "MCICA_SUBCOL: KISSVEC SEED GENERATOR REQUIRES PMID FROM BOTTOM FOUR LAYERS."};
+    e->error = msg[code < 10 ? code : 2];  // message text of the Fortran `stop` (rrtmg_lw_cldprop.f90:193-243)
     cudaMemset(e->W.err, 0, sizeof(int));
   }
   return code;

@@ -29,7 +29,8 @@ class LWEngine:
     """One RRTMG-LW engine instance: tables resident in HBM, options and constants per instance
     (the reference keeps them in Cython/Fortran module globals, _rrtmg_lw.pyx:8-14)."""
 
-    def __init__(self, constants=None, device=0, icld=1, idrv=0, inflag=2, iceflag=1, liqflag=1):
+    def __init__(self, constants=None, device=0, icld=1, idrv=0, inflag=2, iceflag=1, liqflag=1, mcica=False, irng=1,
+                 permuteseed=0):
         self._L = _native.lib()
         k = constants or rrtmg_constants()
         c = np.array([k[n] for n in _CONST_ORDER], dtype=np.float64)
@@ -39,7 +40,12 @@ class LWEngine:
             raise RuntimeError("cb200_lw_create failed: " + self._L.cb200_global_error().decode())
         self._h = h
         self.device = device
+        self.set_mcica(mcica, irng, permuteseed)
         self.set_options(icld, idrv, inflag, iceflag, liqflag)
+
+    def set_mcica(self, enabled, irng=1, permuteseed=0):
+        """McICA on/off, RNG (0 kissvec on the device, 1 Mersenne twister on the host for bit parity), seed."""
+        self._L.cb200_lw_set_mcica(self._h, 1 if enabled else 0, int(irng), int(permuteseed))
 
     def set_options(self, icld, idrv, inflag, iceflag, liqflag):
         if self._L.cb200_lw_set_options(self._h, icld, idrv, inflag, iceflag, liqflag):

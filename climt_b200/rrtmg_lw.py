@@ -88,11 +88,10 @@ class RRTMGLongwave(TendencyComponent):
         self._calc_Tint = calculate_interface_temperature
         if not self._calc_Tint:
             self.input_properties["air_temperature_on_interface_levels"] = _p(["interface_levels", "*"], "degK")
-        if mcica:
-            raise NotImplementedError("McICA is not available in the CUDA longwave engine yet")
         # constants are captured per instance at construction (climt reads sympl's registry here, :298-309)
         self._engine = LWEngine(rrtmg_constants(), device=device, icld=self._cloud_overlap, idrv=self._calc_dflxdt,
-                                inflag=self._cloud_optics, iceflag=self._ice_props, liqflag=self._liq_props)
+                                inflag=self._cloud_optics, iceflag=self._ice_props, liqflag=self._liq_props,
+                                mcica=bool(mcica), irng=getattr(self, "_random_number_generator", 1))
         super().__init__(**kwargs)
 
     def array_call(self, state):
@@ -133,6 +132,15 @@ class RRTMGLongwave(TendencyComponent):
             "dflxc": diagnostics["downwelling_longwave_flux_in_air_assuming_clear_sky"],
             "hrc": diagnostics["air_temperature_tendency_from_longwave_assuming_clear_sky"],
         }
+        if self._mcica:
+            # same draw as the reference (lw/component.py:415-423): every call gets a new seed from numpy's global
+            # legacy generator, so `np.random.seed(k)` before the call makes it reproducible.  Unlike the
+            # reference, the k-tables are NOT re-initialised on every call (:425-434).
+            if self._random_number_generator == 0:
+                self._permute_seed = np.random.randint(0, 1024)
+            else:
+                self._permute_seed = np.random.randint(0, 2 ** 31 - 1)
+            self._engine.set_mcica(True, self._random_number_generator, self._permute_seed)
         self._engine.run_host(n_columns, n_layers, arrays, out)
         diagnostics["air_temperature_tendency_from_longwave"] = tendencies["air_temperature"]
         return tendencies, diagnostics

@@ -49,6 +49,10 @@ void cb200_lw_destroy(cb200_lw_engine* e);
 /* icld: 0 clear, 1 random, 2 maximum-random, 3 maximum; idrv: 0/1; inflag/iceflag/liqflag as RRTMG
  * (module globals in _rrtmg_lw.pyx:8-14 in the reference; per engine here). */
 int cb200_lw_set_options(cb200_lw_engine* e, int icld, int idrv, int inflag, int iceflag, int liqflag);
+/* McICA (rrtmg_lw_rad.f90 + mcica_subcol_gen_lw.f90): enabled 0/1; irng 0 = kissvec (per-column seeds, generated on the
+ * device), 1 = Mersenne twister (one serial stream per call, generated on the host for bit parity);
+ * permuteseed as in mcica_subcol_lw_wrapper (rrtmg_lw_c_binder.f90:50-92).  Call before cb200_lw_set_options. */
+int cb200_lw_set_mcica(cb200_lw_engine* e, int enabled, int irng, int permuteseed);
 /* Asynchronous on `stream` (a cudaStream_t, NULL = default stream); pointers are device pointers owned by
  * the caller.  Returns 0 or a negative launch/configuration error.  Input-validation errors that the Fortran
  * turns into `stop` are reported by cb200_lw_check() after the stream has been synchronised. */

@@ -6,14 +6,19 @@
 #include <vector>
 
 #include "../../climt_b200/csrc/lw_tables.h"
+#include "../../climt_b200/csrc/mcica_host.h"
 
 using namespace cb::lw;
 
 template <int B, int U>
-static void run_unit(const Tables& T, const In& in, const Work& W, int n, int g0, int unit) {
-  for (int c = 0; c < n; ++c) lw_unit<B, U>(T, in, W, 0, c, g0, unit);
+static void run_unit(const Tables& T, const In& in, const Work& W, int n, int g0, int unit, bool mc) {
+  for (int c = 0; c < n; ++c) {
+    if (mc) lw_unit<B, U, true>(T, in, W, 0, c, g0, unit);
+    else lw_unit<B, U, false>(T, in, W, 0, c, g0, unit);
+  }
 }
 
+// flags8 = {icld, idrv, inflag, iceflag, liqflag, mcica, irng, permuteseed}
 extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* flags5, int ncol, int nlay,
                            const double* const* inp /*23 pointers in struct In order*/, double* const* outp /*6*/) {
   try {
@@ -30,7 +35,9 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
     Out out;
     double** op = &out.uflx;
     for (int i = 0; i < 6; ++i) op[i] = outp[i];
-    Flags fl{flags5[0], flags5[1], flags5[2], flags5[3], flags5[4]};
+    Flags fl{flags5[0], flags5[1], flags5[2], flags5[3], flags5[4], flags5[5]};
+    const int irng = flags5[6], seed = flags5[7];
+    const bool mc = fl.mcica && fl.icld >= 1;
     Unit units[kMaxUnits];
     const int nunits = build_units(units);
     Work W;
@@ -38,13 +45,19 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
     std::vector<double> ws((size_t)NF * nlay * ncol), pw(ncol), cld((size_t)32 * nlay * ncol),
         scr((size_t)140 * 4 * nlay * ncol), part((size_t)nunits * 4 * (nlay + 1) * ncol);
     std::vector<int> idx((size_t)nlay * ncol), lt(ncol), ncb(ncol);
+    std::vector<unsigned> mask((size_t)5 * nlay * ncol, 0u);
     int err = 0;
+    W.mask = mask.data(); W.mstride = ncol; W.moff = 0;
     W.ws = ws.data(); W.idx = idx.data(); W.laytrop = lt.data(); W.ncbands = ncb.data(); W.pwvcm = pw.data();
     W.cld = cld.data(); W.scr = scr.data(); W.part = part.data(); W.err = &err;
+    if (mc && irng == 1) { cb::mcica::mask_mt_host(in.cldfr, ncol, nlay, 140, 5, fl.icld, seed, mask); W.mask = mask.data(); }
+    if (mc && irng == 0)
+      for (int c = 0; c < ncol; ++c)
+        if (cb::mcica::mask_column_kiss(in.play, in.cldfr, ncol, nlay, 140, 5, fl.icld, seed, W.mask, ncol, 0, c)) err = 9;
     for (int c = 0; c < ncol; ++c) prep_column(T, in, fl, W, 0, c);
     for (int k2 = 0; k2 < nunits; ++k2) {
       const Unit un = units[k2];
-#define CASE(B) case B: if (un.u == 4) run_unit<B, 4>(T, in, W, ncol, un.g0, k2); else run_unit<B, 2>(T, in, W, ncol, un.g0, k2); break;
+#define CASE(B) case B: if (un.u == 4) run_unit<B, 4>(T, in, W, ncol, un.g0, k2, mc); else run_unit<B, 2>(T, in, W, ncol, un.g0, k2, mc); break;
       switch (un.band) {
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
         CASE(14) CASE(15) CASE(16)

@@ -108,13 +108,16 @@ def emul_lib(which="lw"):
     so = os.path.join(HERE, "emul", "libcb_emul.so" if which == "lw" else "libcb_emul_sw.so")
     src = os.path.join(HERE, "emul", f"{which}_emul.cpp")
     deps = [src] + [os.path.join(HERE, "..", "climt_b200", "csrc", f)
-                    for f in ("lw_core.cuh", "lw_tables.h", "cb_common.h", "sw_core.cuh", "sw_tables.h")]
+                    for f in ("lw_core.cuh", "lw_tables.h", "cb_common.h", "sw_core.cuh", "sw_tables.h", "mcica_core.cuh",
+                              "mcica_host.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
     return ctypes.CDLL(so)
 
 
-def run_lw_emul(st, flags=(1, 0, 2, 1, 1)):
+def run_lw_emul(st, flags=(1, 0, 2, 1, 1), mcica=(0, 1, 0)):
+    """flags = (icld, idrv, inflag, iceflag, liqflag); mcica = (enabled, irng, permuteseed)"""
+    flags = tuple(flags) + tuple(mcica)
     lib = emul_lib()
     k = C.rrtmg_constants()
     consts = np.array([k[n] for n in ("pi", "grav", "planck", "boltz", "clight", "avogad", "alosmt", "gascon",
@@ -124,7 +127,7 @@ def run_lw_emul(st, flags=(1, 0, 2, 1, 1)):
     out = {n: np.zeros((nlay + 1, ncol)) for n in ("uflx", "dflx", "uflxc", "dflxc")}
     out.update({n: np.zeros((nlay, ncol)) for n in ("hr", "hrc")})
     outp = (_dp * 6)(*[out[n].ctypes.data_as(_dp) for n in ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc")])
-    rc = lib.emul_lw_run(RT.lw_blob_path().encode(), consts.ctypes.data_as(_dp), (ctypes.c_int * 5)(*flags),
+    rc = lib.emul_lw_run(RT.lw_blob_path().encode(), consts.ctypes.data_as(_dp), (ctypes.c_int * 8)(*flags),
                          ncol, nlay, inp, outp)
     return rc, out
 

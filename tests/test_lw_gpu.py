@@ -105,3 +105,39 @@ def test_bad_cloud_radius_raises_value_error(engine):
     st["reice"][10, :] = 500.0
     with pytest.raises(ValueError, match="ICE RADIUS OUT OF BOUNDS"):
         _run(engine, st)
+
+
+@pytest.mark.parametrize("icld,irng", [(1, 1), (2, 0), (3, 0)])
+def test_cuda_lw_mcica_matches_oracle(icld, irng):
+    from climt_b200.engine import LWEngine
+    from oracle.rrtmg import lw_mcica
+    st = SY.make_lw_state(200, 60, seed=9 + icld, clouds=True, aerosol=True)
+    ref = lw_mcica(H.lw_oracle(cloud_overlap=icld), st, 112, irng=irng)
+    eng = LWEngine(icld=icld, mcica=True, irng=irng, permuteseed=112)
+    got = eng.run_host(200, 60, H.to_abi(st))
+    eng.close()
+    for k in ("uflx", "dflx", "uflxc", "dflxc"):
+        assert H.rel_err(got[k], ref[k]) < RTOL, (k, H.rel_err(got[k], ref[k]))
+
+
+def test_mcica_component_matches_reference_golden():
+    """TestRRTMGLongwaveMCICA-3d through the drop-in component with the reference harness's seeding."""
+    from climt_b200.rrtmg_lw import RRTMGLongwave
+    from climt_b200 import state as S
+    g = H.golden()
+    st = S.default_rrtmg_lw_state(28, 50)
+    raw = dict(st)
+    raw["air_pressure"] = st["air_pressure"] / 100.0
+    raw["air_pressure_on_interface_levels"] = st["air_pressure_on_interface_levels"] / 100.0
+    raw["cloud_area_fraction_in_atmosphere_layer"] = st["cloud_area_fraction_in_atmosphere_layer"].copy()
+    raw["cloud_area_fraction_in_atmosphere_layer"][16:19] = 0.5
+    ice = st["mass_content_of_cloud_ice_in_atmosphere_layer"].copy()
+    ice[16:19] = 0.3
+    raw["mass_content_of_cloud_ice_in_atmosphere_layer"] = ice * 1e3
+    raw["mass_content_of_cloud_liquid_water_in_atmosphere_layer"] = st["mass_content_of_cloud_liquid_water_in_atmosphere_layer"] * 1e3
+    comp = RRTMGLongwave(mcica=True)
+    np.random.seed(0)
+    tend, diag = comp.array_call(raw)
+    for name in ("upwelling_longwave_flux_in_air", "downwelling_longwave_flux_in_air", "air_temperature_tendency_from_longwave"):
+        np.testing.assert_allclose(diag[name], g[f"TestRRTMGLongwaveMCICA-3d/diag/{name}"].reshape(diag[name].shape[0], -1),
+                                   rtol=0, atol=1e-8)
