@@ -73,7 +73,7 @@ class SwInputs(ctypes.Structure):
         "cicewp", "cliqwp", "reice", "reliq", "tauaer", "ssaaer", "asmaer", "ecaer")]
 
 
-EXPORTS = ["cb200_gray_lw_run_device", "cb200_gray_lw_run_host", "cb200_sw_create", "cb200_sw_destroy", "cb200_sw_set_options", "cb200_sw_set_solar", "cb200_sw_run_device",
+EXPORTS = ["cb200_gray_lw_run_device", "cb200_gray_lw_run_host", "cb200_sw_create", "cb200_sw_destroy", "cb200_sw_set_options", "cb200_sw_set_mcica", "cb200_sw_set_solar", "cb200_sw_run_device",
            "cb200_sw_run_host", "cb200_sw_check", "cb200_sw_last_error", "cb200_sw_last_launches",
            "cb200_sw_enable_timing", "cb200_sw_last_unit_kernel_ms", "rrtmg_sw_set_constants", "rrtmg_sw_ini_wrapper",
            "rrtmg_sw_nomcica_wrapper",
@@ -116,6 +116,7 @@ def lib():
     L.cb200_sw_destroy.argtypes = [vp]
     L.cb200_sw_destroy.restype = None
     L.cb200_sw_set_options.argtypes = [vp] + [ctypes.c_int] * 5
+    L.cb200_sw_set_mcica.argtypes = [vp] + [ctypes.c_int] * 3
     L.cb200_sw_set_solar.argtypes = [vp, ctypes.c_int, ctypes.c_double, _dp, _dp]
     L.cb200_sw_run_device.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double,
                                       ctypes.POINTER(SwInputs), ctypes.POINTER(LwOutputs), vp]

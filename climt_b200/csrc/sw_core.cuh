@@ -59,6 +59,7 @@ struct Out {
 };
 struct Flags {
   int icld, iaer, inflag, iceflag, liqflag;
+  int mcica;  // 0: spcvrt (cloud fraction 0/1 per layer); 1: McICA (spcvmc: per-g-point 0/1 cloud mask)
 };
 struct Work {
   int ncc;
@@ -71,6 +72,8 @@ struct Work {
   double* aer;    // [3][14][nlay][ncc]  aerosol tau, ssa, asym (iaer = 6 only)
   double* scr;    // [112][NSCR][nlay][ncc]
   double* part;   // [nunits][4][nlay+1][ncc]   fu, fd, cu, cd  (already weighted by the incoming flux)
+  unsigned* mask; // [nlay][4][mstride] (+ moff) McICA cloud mask, bit (g & 31) of word (g >> 5)
+  int mstride, moff;
   int* err;
 };
 
@@ -161,7 +164,7 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
     if (clouds) {
       const double eps = 1.e-06, cldmin = 1.e-20;
       const double cldfrac = in.cldfr[o];
-      if (cldfrac > 1.e-06 && cldfrac < T.oneminus) *W.err = 10;  // 'PARTIAL CLOUD NOT ALLOWED' (rad.nomcica.f90:616-620)
+      if (!fl.mcica && cldfrac > 1.e-06 && cldfrac < T.oneminus) *W.err = 10;  // 'PARTIAL CLOUD NOT ALLOWED' (rad.nomcica.f90:616-620)
       const double ciwp = in.cicewp[o], clwp = in.cliqwp[o];
       const double* tc = in.taucld + 14 * ((size_t)l * ncol + gc);
       const double* sc = in.ssacld + 14 * ((size_t)l * ncol + gc);
@@ -172,9 +175,24 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
       double taucloud[14], ssacloud[14], asmcloud[14];
       for (int ib = 0; ib < 14; ++ib) { taucloud[ib] = 0.; ssacloud[ib] = 1.; asmcloud[ib] = 0.; }
       const double cwp = ciwp + clwp;
-      if (cldfrac >= cldmin && (cwp >= cldmin || tauctot >= cldmin)) {
+      // McICA (cldprmc_sw, rrtmg_sw_cldprmc.f90:155-161): a cloudy sub-column carries the layer's water paths and its
+      // band's direct-input optics, so the result only depends on the band; the entry test is per band there.
+      bool enter = cldfrac >= cldmin && (cwp >= cldmin || tauctot >= cldmin);
+      bool band_ok[14];
+      for (int ib = 0; ib < 14; ++ib) band_ok[ib] = true;
+      if (fl.mcica) {
+        enter = false;
+        for (int ib = 0; ib < 14; ++ib) {
+          band_ok[ib] = cwp >= cldmin || tc[ib] >= cldmin;
+          enter = enter || band_ok[ib];
+          taucloud[ib] = tc[ib]; ssacloud[ib] = sc[ib]; asmcloud[ib] = ac[ib];
+        }
+        if (fl.inflag == 1 && enter) *W.err = 8;
+      }
+      if (enter) {
         if (fl.inflag == 0) {
           for (int ib = 0; ib < 14; ++ib) {
+            if (!band_ok[ib]) continue;
             const double ffp = fc[ib], ffp1 = 1.0 - ffp, ffpssa = 1.0 - ffp * sc[ib];
             ssacloud[ib] = ffp1 * sc[ib] / ffpssa;
             taucloud[ib] = ffpssa * tc[ib];
@@ -252,6 +270,7 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
             }
           }
           for (int ib = 0; ib < 14; ++ib) {
+            if (!band_ok[ib]) continue;
             const double tauliqorig = clwp * extcoliq[ib], tauiceorig = ciwp * extcoice[ib];
             const double ssaliq = ssacoliq[ib] * (1.0 - forwliq[ib]) / (1.0 - forwliq[ib] * ssacoliq[ib]);
             const double tauliq = (1.0 - forwliq[ib] * ssacoliq[ib]) * tauliqorig;
@@ -609,7 +628,7 @@ CB_HD void reftra(const double* __restrict__ exp_tbl, double bpade, double zg, d
 
 // ---------------------------------------------------------------------------------------------
 // sw_unit: spcvrt_sw for U g-points of band B in one column (rrtmg_sw_spcvrt.f90:329-661).
-template <int B, int U>
+template <int B, int U, bool MC>
 CB_HD void sw_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int c0, int c,
                    int g0, int unit) {
   constexpr int ib = B - 16;
@@ -651,15 +670,27 @@ CB_HD void sw_unit(const Tables& T, const Solar& sol, const In& in, const Flags&
       pomga = W.aer[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c];
       pasya = W.aer[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c];
     }
-    double pclfr = 0., ptauc = 0., pomgc = 1., pasyc = 0.;
+    double pclfr_l = 0., ptauc_l = 0., pomgc_l = 1., pasyc_l = 0.;
+    unsigned mbits = 0u;
     if (cloudy_col) {
-      pclfr = in.cldfr[(size_t)l * ncol + gc];
-      ptauc = W.cld[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c];
-      pomgc = W.cld[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c];
-      pasyc = W.cld[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c];
+      pclfr_l = MC ? 1.0 : in.cldfr[(size_t)l * ncol + gc];
+      ptauc_l = W.cld[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c];
+      pomgc_l = W.cld[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c];
+      pasyc_l = W.cld[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c];
+      if (MC) {
+        const size_t ms = (size_t)W.mstride;
+        const unsigned* mw = W.mask + ((size_t)l * 4) * ms + W.moff + c;
+        for (int u = 0; u < U; ++u) {
+          const int g = gabs + u;
+          mbits |= ((mw[(size_t)(g >> 5) * ms] >> (g & 31)) & 1u) << u;
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      // spcvmc: the sub-column is either overcast with its band's optics or clear (mcica_subcol_gen_sw.f90:523-548)
+      const bool on = !MC || ((mbits >> u) & 1u);
+      const double pclfr = on ? pclfr_l : 0., ptauc = on ? ptauc_l : 0., pomgc = on ? pomgc_l : 1., pasyc = on ? pasyc_l : 0.;
       double ztauc = taur[u] + taug[u] + ptaua;
       double zomcc = taur[u] * 1.0 + ptaua * pomga;
       double zgcc = pasya * pomga * ptaua / zomcc;

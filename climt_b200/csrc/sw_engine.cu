@@ -10,6 +10,7 @@
 #include "../../include/climt_b200.h"
 #include "engine_common.h"
 #include "sw_tables.h"
+#include "mcica_host.h"
 
 using namespace cb::sw;
 
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(kBlock) k_sw_prep(const __grid_constant__ Tabl
   if (c < n) sw_prep_column(T, in, fl, W, c0, c);
 }
 
+template <bool MC>
 __global__ void __launch_bounds__(kBlock, CB_UNITS_MIN_BLOCKS) k_sw_units(const __grid_constant__ Tables T, const __grid_constant__ Solar sol,
                                                      const __grid_constant__ In in, const Flags fl,
                                                      const __grid_constant__ Work W, const __grid_constant__ UnitList UL,
@@ -40,14 +42,21 @@ __global__ void __launch_bounds__(kBlock, CB_UNITS_MIN_BLOCKS) k_sw_units(const 
   const Unit un = UL.u[k];
 #define CB_CASE(B)                                                      \
   case B:                                                               \
-    if (un.u == 4) sw_unit<B, 4>(T, sol, in, fl, W, c0, c, un.g0, k);   \
-    else sw_unit<B, 2>(T, sol, in, fl, W, c0, c, un.g0, k);             \
+    if (un.u == 4) sw_unit<B, 4, MC>(T, sol, in, fl, W, c0, c, un.g0, k);   \
+    else sw_unit<B, 2, MC>(T, sol, in, fl, W, c0, c, un.g0, k);             \
     break;
   switch (un.band) {
     CB_CASE(16) CB_CASE(17) CB_CASE(18) CB_CASE(19) CB_CASE(20) CB_CASE(21) CB_CASE(22)
     CB_CASE(23) CB_CASE(24) CB_CASE(25) CB_CASE(26) CB_CASE(27) CB_CASE(28) CB_CASE(29)
   }
 #undef CB_CASE
+}
+
+__global__ void __launch_bounds__(kBlock) k_sw_mask_kiss(const __grid_constant__ In in, const __grid_constant__ Work W,
+                                                         int icld, int seed, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  if (cb::mcica::mask_column_kiss(in.play, in.cldfr, in.ncol, in.nlay, 112, 4, icld, seed, W.mask, W.ncc, c0, c)) *W.err = 9;
 }
 
 __global__ void __launch_bounds__(kBlock) k_sw_reduce(const __grid_constant__ Work W, const __grid_constant__ UnitList UL,
@@ -78,7 +87,10 @@ struct cb200_sw_engine {
   int device = 0;
   Tables T;
   double* d_tables = nullptr;
-  Flags fl{1, 0, 2, 1, 1};
+  Flags fl{1, 0, 2, 1, 1, 0};
+  int irng = 1, permuteseed = 0;
+  unsigned* d_mask_full = nullptr;
+  size_t mask_full_cap = 0;
   SolarOptions solar;
   UnitList UL;
   int cap_ncc = 0, cap_nlay = 0;
@@ -95,7 +107,7 @@ struct cb200_sw_engine {
 
   void free_work() {
     cudaFree(W.ws); cudaFree(W.idx); cudaFree(W.laytrop); cudaFree(W.laysolfr); cudaFree(W.anycld);
-    cudaFree(W.cld); cudaFree(W.aer); cudaFree(W.scr); cudaFree(W.part); cudaFree(W.err);
+    cudaFree(W.cld); cudaFree(W.aer); cudaFree(W.scr); cudaFree(W.part); cudaFree(W.err); cudaFree(W.mask);
     W = Work{};
     cap_ncc = cap_nlay = 0;
   }
@@ -113,6 +125,7 @@ struct cb200_sw_engine {
     CUDA_OK(cudaMalloc(&W.aer, sizeof(double) * 42 * L * n));
     CUDA_OK(cudaMalloc(&W.scr, sizeof(double) * 112 * NSCR * L * n));
     CUDA_OK(cudaMalloc(&W.part, sizeof(double) * UL.n * 4 * (L + 1) * n));
+    CUDA_OK(cudaMalloc(&W.mask, sizeof(unsigned) * 4 * L * n));
     CUDA_OK(cudaMalloc(&W.err, sizeof(int)));
     CUDA_OK(cudaMemset(W.err, 0, sizeof(int)));
     cap_ncc = ncc;
@@ -157,6 +170,7 @@ extern "C" void cb200_sw_destroy(cb200_sw_engine* e) {
   e->free_work();
   cudaFree(e->d_tables);
   cudaFree(e->d_stage);
+  cudaFree(e->d_mask_full);
   if (e->h_err) cudaFreeHost(e->h_err);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -166,7 +180,13 @@ extern "C" void cb200_sw_destroy(cb200_sw_engine* e) {
 extern "C" int cb200_sw_set_options(cb200_sw_engine* e, int icld, int iaer, int inflag, int iceflag, int liqflag) {
   if (icld < 0 || icld > 3) icld = 2;                       // rrtmg_sw_rad.nomcica.f90:558
   if (iaer != 0 && iaer != 6 && iaer != 10) iaer = 0;       // :566
-  e->fl = Flags{icld, iaer, inflag, iceflag, liqflag};
+  e->fl = Flags{icld, iaer, inflag, iceflag, liqflag, e->fl.mcica};
+  return 0;
+}
+extern "C" int cb200_sw_set_mcica(cb200_sw_engine* e, int enabled, int irng, int permuteseed) {
+  e->fl.mcica = enabled ? 1 : 0;
+  e->irng = irng != 0 ? 1 : 0;
+  e->permuteseed = permuteseed;
   return 0;
 }
 extern "C" int cb200_sw_set_solar(cb200_sw_engine* e, int isolvar, double scon, const double indsolvar[2],
@@ -207,12 +227,36 @@ extern "C" int cb200_sw_run_device(cb200_sw_engine* e, int ncol, int nlay, doubl
   const Solar sol = compute_solar(e->solar, adjes, dyofyr, solcycfrac);
   e->launches = 0;
   e->unit_ms = 0.0;
+  const bool mc = e->fl.mcica && e->fl.icld >= 1;
+  W.mstride = chunk;
+  W.moff = 0;
+  if (mc && e->irng == 1) {  // Mersenne twister: serial stream, generated on the host for bit parity
+    std::vector<double> h_cld((size_t)nlay * ncol);
+    CUDA_OK(cudaMemcpyAsync(h_cld.data(), in.cldfr, h_cld.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<unsigned> h_mask;
+    cb::mcica::mask_mt_host(h_cld.data(), ncol, nlay, 112, 4, e->fl.icld, e->permuteseed, h_mask);
+    if (h_mask.size() > e->mask_full_cap) {
+      cudaFree(e->d_mask_full);
+      e->d_mask_full = nullptr;
+      e->mask_full_cap = 0;
+      CUDA_OK(cudaMalloc(&e->d_mask_full, h_mask.size() * sizeof(unsigned)));
+      e->mask_full_cap = h_mask.size();
+    }
+    CUDA_OK(cudaMemcpyAsync(e->d_mask_full, h_mask.data(), h_mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    W.mask = e->d_mask_full;
+    W.mstride = ncol;
+  }
   for (int c0 = 0; c0 < ncol; c0 += chunk) {
     const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
     const int gx = (n + kBlock - 1) / kBlock;
+    if (mc && e->irng == 0) { k_sw_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
+    if (mc && e->irng == 1) W.moff = c0;
     k_sw_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
     if (e->timing) cudaEventRecord(e->ev0, st);
-    k_sw_units<<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+    if (mc) k_sw_units<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+    else k_sw_units<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
     if (e->timing) cudaEventRecord(e->ev1, st);
     k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, e->UL, out, nlay, ncol, c0, n);
     k_sw_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
@@ -242,6 +286,8 @@ extern "C" int cb200_sw_check(cb200_sw_engine* e) {
       case 5: e->error = "ICE OPTICAL PROPERTY OUT OF RANGE"; break;
       case 6: e->error = "FDELTA OUT OF RANGE"; break;
       case 7: e->error = "LIQUID OPTICAL PROPERTY OUT OF RANGE"; break;
+      case 8: e->error = "INFLAG = 1 OPTION NOT AVAILABLE WITH MCICA"; break;
+      case 9: e->error = "MCICA_SUBCOL: KISSVEC SEED GENERATOR REQUIRES PMID FROM BOTTOM FOUR LAYERS."; break;
       case 10: e->error = "PARTIAL CLOUD NOT ALLOWED"; break;
       default: e->error = "invalid input"; break;
     }

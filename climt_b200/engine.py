@@ -145,7 +145,7 @@ class SWEngine:
     """One RRTMG-SW engine instance (non-McICA driver)."""
 
     def __init__(self, constants=None, device=0, icld=1, iaer=0, inflag=2, iceflag=1, liqflag=1, isolvar=0,
-                 scon=1367.0, indsolvar=(1.0, 1.0), bndsolvar=None):
+                 scon=1367.0, indsolvar=(1.0, 1.0), bndsolvar=None, mcica=False, irng=1, permuteseed=0):
         self._L = _native.lib()
         k = constants or rrtmg_constants()
         c = np.array([k[n] for n in _CONST_ORDER], dtype=np.float64)
@@ -155,10 +155,14 @@ class SWEngine:
             raise RuntimeError("cb200_sw_create failed: " + self._L.cb200_global_error().decode())
         self._h = h
         self.device = device
+        self.set_mcica(mcica, irng, permuteseed)
         self._L.cb200_sw_set_options(self._h, icld, iaer, inflag, iceflag, liqflag)
         ind = np.array(indsolvar, dtype=np.float64)
         bnd = np.ones(14) if bndsolvar is None else np.ascontiguousarray(np.asarray(bndsolvar, dtype=np.float64)[:14])
         self._L.cb200_sw_set_solar(self._h, int(isolvar), float(scon), ind.ctypes.data_as(_dp), bnd.ctypes.data_as(_dp))
+
+    def set_mcica(self, enabled, irng=1, permuteseed=0):
+        self._L.cb200_sw_set_mcica(self._h, 1 if enabled else 0, int(irng), int(permuteseed))
 
     def _err(self):
         return self._L.cb200_sw_last_error(self._h).decode()

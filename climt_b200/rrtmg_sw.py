@@ -104,12 +104,11 @@ class RRTMGShortwave(TendencyComponent):
         self._solar_var_by_band = np.ones(16) if solar_variability_by_band is None else np.asarray(solar_variability_by_band, dtype=float)
         self._aerosol_type = rrtmg_aerosol_input_dict[aerosol_type.lower()]
         self._solar_const = 0.0 if use_solar_constant_from_fortran else get_constant("stellar_irradiance")
-        if mcica:
-            raise NotImplementedError("McICA is not available in the CUDA shortwave engine yet")
         self._engine = SWEngine(rrtmg_constants(), device=device, icld=self._cloud_overlap, iaer=self._aerosol_type,
                                 inflag=self._cloud_optics, iceflag=self._ice_props, liqflag=self._liq_props,
                                 isolvar=self._solar_var_flag, scon=self._solar_const,
-                                indsolvar=self._fac_sunspot_coeff, bndsolvar=self._solar_var_by_band)
+                                indsolvar=self._fac_sunspot_coeff, bndsolvar=self._solar_var_by_band,
+                                mcica=bool(mcica), irng=getattr(self, "_random_number_generator", 1))
         super().__init__(**kwargs)
 
     def array_call(self, state):
@@ -155,6 +154,13 @@ class RRTMGShortwave(TendencyComponent):
             "dflxc": diagnostics["downwelling_shortwave_flux_in_air_assuming_clear_sky"],
             "hrc": diagnostics["air_temperature_tendency_from_shortwave_assuming_clear_sky"],
         }
+        if self._mcica:
+            # same seed draw as the reference (sw/component.py:535-545); tables are NOT re-initialised per call
+            if self._random_number_generator == 0:
+                self._permute_seed = np.random.randint(0, 1024)
+            else:
+                self._permute_seed = np.random.randint(0, 2 ** 31 - 1)
+            self._engine.set_mcica(True, self._random_number_generator, self._permute_seed)
         self._engine.run_host(n_columns, n_layers, arrays, out,
                               adjes=float(np.asarray(st["flux_adjustment_for_earth_sun_distance"]).item()),
                               dyofyr=day_of_year, solcycfrac=float(np.asarray(st["solar_cycle_fraction"]).item()))

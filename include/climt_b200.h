@@ -105,6 +105,8 @@ int cb200_sw_create(cb200_sw_engine** out, const char* table_blob, const double 
 void cb200_sw_destroy(cb200_sw_engine* e);
 /* icld 0..3 (non-McICA accepts cloud fractions 0 or 1 only), iaer 0|6|10, inflag 0|2, iceflag 1|2|3, liqflag 1 */
 int cb200_sw_set_options(cb200_sw_engine* e, int icld, int iaer, int inflag, int iceflag, int liqflag);
+/* McICA (rrtmg_sw_rad.f90 + mcica_subcol_gen_sw.f90), same meaning as cb200_lw_set_mcica; call before set_options. */
+int cb200_sw_set_mcica(cb200_sw_engine* e, int enabled, int irng, int permuteseed);
 /* isolvar -1..3, scon [W m-2] (0 = internal), indsolvar[2], bndsolvar[14] (module globals in _rrtmg_sw.pyx:8-19) */
 int cb200_sw_set_solar(cb200_sw_engine* e, int isolvar, double scon, const double indsolvar[2], const double bndsolvar[14]);
 int cb200_sw_run_device(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,

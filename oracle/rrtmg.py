@@ -12,7 +12,7 @@ _dp = ctypes.POINTER(ctypes.c_double)
 
 def build(force=False):
     so = os.path.join(_HERE, "liborc_rrtmg.so")
-    srcs = [os.path.join(_HERE, f) for f in ("rrtmg_lw_oracle.cpp", "rrtmg_sw_oracle.cpp", "ftn.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("rrtmg_lw_oracle.cpp", "rrtmg_sw_oracle.cpp", "ftn.hpp", "mcica_gen.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -188,4 +188,30 @@ def lw_mcica(oracle, st, permuteseed, irng=1, return_mask=False):
         raise RuntimeError(L.orc_last_error().decode())
     if return_mask:
         out["mask"] = mask
+    return out
+
+
+def sw_mcica(oracle, st, permuteseed, irng=1, adjes=1.0, dyofyr=1, solcycfrac=0.0):
+    """McICA shortwave through the oracle (mcica_subcol_sw + rrtmg_sw mcica); `oracle` is an initialised SWOracle."""
+    nlay, ncol = st["play"].shape
+    f = oracle.flags
+    a = {k: _c(st[k]) for k in SW_ARRAYS}
+    out = {k: np.zeros((nlay + 1, ncol)) for k in ("swuflx", "swdflx", "swuflxc", "swdflxc")}
+    out.update({k: np.zeros((nlay, ncol)) for k in ("swhr", "swhrc")})
+    icld, iaer = ctypes.c_int(f["icld"]), ctypes.c_int(f["iaer"])
+    ind = oracle.indsolvar.copy()
+    L = lib()
+    pre = [a[k] for k in ("play", "plev", "tlay", "tlev", "tsfc", "h2o", "o3", "co2", "ch4", "n2o", "o2", "asdir",
+                          "asdif", "aldir", "aldif", "coszen")]
+    cl = [a[k] for k in ("cldfr", "taucld", "ssacld", "asmcld", "fsfcld", "cicewp", "cliqwp", "reice", "reliq",
+                         "tauaer", "ssaaer", "asmaer", "ecaer")]
+    rc = L.orc_sw_mcica(
+        ctypes.c_int(ncol), ctypes.c_int(nlay), ctypes.byref(icld), ctypes.byref(iaer), ctypes.c_int(int(permuteseed)),
+        ctypes.c_int(irng), *[_p(x) for x in pre], ctypes.c_double(adjes), ctypes.c_int(dyofyr),
+        ctypes.c_double(f["scon"]), ctypes.c_int(f["isolvar"]), ctypes.c_int(f["inflag"]), ctypes.c_int(f["iceflag"]),
+        ctypes.c_int(f["liqflag"]), *[_p(x) for x in cl], _p(out["swuflx"]), _p(out["swdflx"]), _p(out["swhr"]),
+        _p(out["swuflxc"]), _p(out["swdflxc"]), _p(out["swhrc"]), _p(oracle.bndsolvar), _p(ind),
+        ctypes.c_double(solcycfrac))
+    if rc:
+        raise RuntimeError(L.orc_sw_last_error().decode())
     return out

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "ftn.hpp"
+#include "mcica_gen.hpp"
 
 namespace orcsw {
 using orc::A1;
@@ -1206,9 +1207,14 @@ struct SwFlux {
   A1 bbfd, bbfu, bbcd, bbcu;
   explicit SwFlux(int nlay) : bbfd(nlay + 2), bbfu(nlay + 2), bbcd(nlay + 2), bbcu(nlay + 2) {}
 };
+// With mc != nullptr this is spcvmc_sw (rrtmg_sw_spcvmc.f90:53-663): cloud fraction / optics per g-point
+// (pcldfmc, ptaucmc, pasycmc, pomgcmc dimensioned (nlay, 112)) instead of per band.
+struct McCloud {
+  const A2 *cldfmc, *taucmc, *asycmc, *omgcmc;
+};
 static void spcvrt_sw(Col& c, int icpr, const double* palbd, const double* palbp, const A2& ptauc, const A2& pasyc,
                       const A2& pomgc, const A2& ptaua, const A2& pasya, const A2& pomga, double prmu0, int isolvar,
-                      SwFlux& F) {
+                      SwFlux& F, const McCloud* mc = nullptr) {
   const int klev = c.nlayers;
   const double repclc = 1.e-12, od_lo = 0.06, tblint = 10000.0, bpade = S.bpade;
   const std::vector<double>& exp_tbl = S.exp_tbl;
@@ -1239,7 +1245,11 @@ static void spcvrt_sw(Col& c, int icpr, const double* palbd, const double* palbp
       for (int jk = 1; jk <= klev; ++jk) {
         int ikl = klev + 1 - jk;
         lrtchkclr[jk] = 1;
-        lrtchkcld[jk] = (c.cldfrac(ikl) > repclc);
+        const double clf = mc ? (*mc->cldfmc)(ikl, iw) : c.cldfrac(ikl);
+        const double tcl = mc ? (*mc->taucmc)(ikl, iw) : ptauc(ikl, ibm);
+        const double ocl = mc ? (*mc->omgcmc)(ikl, iw) : pomgc(ikl, ibm);
+        const double gcl = mc ? (*mc->asycmc)(ikl, iw) : pasyc(ikl, ibm);
+        lrtchkcld[jk] = (clf > repclc);
         ztauc(jk) = sp.taur(ikl, iw) + sp.taug(ikl, iw) + ptaua(ikl, ibm);
         zomcc(jk) = sp.taur(ikl, iw) * 1.0 + ptaua(ikl, ibm) * pomga(ikl, ibm);
         zgcc(jk) = pasya(ikl, ibm) * pomga(ikl, ibm) * ptaua(ikl, ibm) / zomcc(jk);
@@ -1250,14 +1260,14 @@ static void spcvrt_sw(Col& c, int icpr, const double* palbd, const double* palbp
         zomcc(jk) = (zomcc(jk) - zwf) / (1.0 - zwf);
         zgcc(jk) = (zgcc(jk) - zf) / (1.0 - zf);
         if (icpr >= 1) {
-          ztauo(jk) = ztauc(jk) + ptauc(ikl, ibm);
-          zomco(jk) = ztauc(jk) * zomcc(jk) + ptauc(ikl, ibm) * pomgc(ikl, ibm);
-          zgco(jk) = (ptauc(ikl, ibm) * pomgc(ikl, ibm) * pasyc(ikl, ibm) + ztauc(jk) * zomcc(jk) * zgcc(jk)) / zomco(jk);
+          ztauo(jk) = ztauc(jk) + tcl;
+          zomco(jk) = ztauc(jk) * zomcc(jk) + tcl * ocl;
+          zgco(jk) = (tcl * ocl * gcl + ztauc(jk) * zomcc(jk) * zgcc(jk)) / zomco(jk);
           zomco(jk) = zomco(jk) / ztauo(jk);
         } else {
-          ztauo(jk) = sp.taur(ikl, iw) + sp.taug(ikl, iw) + ptaua(ikl, ibm) + ptauc(ikl, ibm);
-          zomco(jk) = ptaua(ikl, ibm) * pomga(ikl, ibm) + ptauc(ikl, ibm) * pomgc(ikl, ibm) + sp.taur(ikl, iw) * 1.0;
-          zgco(jk) = (ptauc(ikl, ibm) * pomgc(ikl, ibm) * pasyc(ikl, ibm) + ptaua(ikl, ibm) * pomga(ikl, ibm) * pasya(ikl, ibm)) / zomco(jk);
+          ztauo(jk) = sp.taur(ikl, iw) + sp.taug(ikl, iw) + ptaua(ikl, ibm) + tcl;
+          zomco(jk) = ptaua(ikl, ibm) * pomga(ikl, ibm) + tcl * ocl + sp.taur(ikl, iw) * 1.0;
+          zgco(jk) = (tcl * ocl * gcl + ptaua(ikl, ibm) * pomga(ikl, ibm) * pasya(ikl, ibm)) / zomco(jk);
           zomco(jk) = zomco(jk) / ztauo(jk);
           zf = zgco(jk) * zgco(jk);
           zwf = zomco(jk) * zf;
@@ -1270,7 +1280,8 @@ static void spcvrt_sw(Col& c, int icpr, const double* palbd, const double* palbp
       reftra_sw(klev, lrtchkcld, zgco, prmu0, ztauo, zomco, zrefo, zrefdo, ztrao, ztrado);
       for (int jk = 1; jk <= klev; ++jk) {
         int ikl = klev + 1 - jk;
-        double zclear = 1.0 - c.cldfrac(ikl), zcloud = c.cldfrac(ikl);
+        const double clf2 = mc ? (*mc->cldfmc)(ikl, iw) : c.cldfrac(ikl);
+        double zclear = 1.0 - clf2, zcloud = clf2;
         zref(jk) = zclear * zrefc(jk) + zcloud * zrefo(jk);
         zrefd(jk) = zclear * zrefdc(jk) + zcloud * zrefdo(jk);
         ztra(jk) = zclear * ztrac(jk) + zcloud * ztrao(jk);
@@ -1411,6 +1422,235 @@ extern "C" int orc_sw_nomcica(int ncol, int nlay, int* icld, int* iaer, const do
         for (int ib = 1; ib <= nbndsw; ++ib) { ztaua(i, ib) = c.taua(i, ib); zasya(i, ib) = c.asma(i, ib); zomga(i, ib) = c.ssaa(i, ib); }
     }
     spcvrt_sw(c, 1, albdif, albdir, ztauc, zasyc, zomgc, ztaua, zasya, zomga, cossza, isolvar, F);
+    for (int i = 1; i <= nlay + 1; ++i) {
+      size_t o = (size_t)(iplon - 1) + (size_t)ncol * (i - 1);
+      swuflxc[o] = F.bbcu(i); swdflxc[o] = F.bbcd(i); swuflx[o] = F.bbfu(i); swdflx[o] = F.bbfd(i);
+    }
+    for (int i = 1; i <= nlay; ++i) {
+      size_t o = (size_t)(iplon - 1) + (size_t)ncol * (i - 1);
+      double zdpgcp = S.heatfac / c.pdp(i);
+      double n1 = F.bbcd(i + 1) - F.bbcu(i + 1), n0 = F.bbcd(i) - F.bbcu(i);
+      swhrc[o] = (n1 - n0) * zdpgcp;
+      n1 = F.bbfd(i + 1) - F.bbfu(i + 1); n0 = F.bbfd(i) - F.bbfu(i);
+      swhr[o] = (n1 - n0) * zdpgcp;
+    }
+  }
+  return 0;
+}
+
+
+// =============================================================================================
+// McICA shortwave: mcica_subcol_sw + cldprmc_sw + spcvmc_sw (rrtmg_sw_rad.f90:100-850)
+namespace orcsw {
+static int ngb_sw_[112];
+static void init_ngb_sw() {
+  int ib = 1;
+  for (int ig = 1; ig <= 112; ++ig) {
+    while (ig > ngs_[ib - 1]) ++ib;
+    ngb_sw_[ig - 1] = ib + 15;
+  }
+}
+
+// cldprmc_sw — rrtmg_sw_cldprmc.f90:53-349; arrays (112, nlay)
+static int cldprmc_sw(int nlayers, int inflag, int iceflag, int liqflag, const A2& cldfmc, const A2& ciwpmc, const A2& clwpmc,
+                      const A1& reicmc, const A1& relqmc, A2& taormc, A2& taucmc, A2& ssacmc, A2& asmcmc, A2& fsfcmc,
+                      std::string& err) {
+  const double eps = 1.e-06, cldmin = 1.e-20;
+  double extcoice[113] = {0}, gice[113] = {0}, ssacoice[113] = {0}, forwice[113] = {0}, extcoliq[113] = {0},
+         gliq[113] = {0}, ssacoliq[113] = {0}, forwliq[113] = {0}, fdelta[113] = {0};
+  for (int lay = 1; lay <= nlayers; ++lay)
+    for (int ig = 1; ig <= ngptsw; ++ig) taormc(ig, lay) = taucmc(ig, lay);
+  for (int lay = 1; lay <= nlayers; ++lay)
+    for (int ig = 1; ig <= ngptsw; ++ig) {
+      double cwp = ciwpmc(ig, lay) + clwpmc(ig, lay);
+      if (cldfmc(ig, lay) >= cldmin && (cwp >= cldmin || taucmc(ig, lay) >= cldmin)) {
+        if (inflag == 0) {
+          double taucldorig_a = taucmc(ig, lay);
+          double ffp = fsfcmc(ig, lay), ffp1 = 1.0 - ffp, ffpssa = 1.0 - ffp * ssacmc(ig, lay);
+          double ssacloud_a = ffp1 * ssacmc(ig, lay) / ffpssa;
+          double taucloud_a = ffpssa * taucldorig_a;
+          taormc(ig, lay) = taucldorig_a;
+          ssacmc(ig, lay) = ssacloud_a;
+          taucmc(ig, lay) = taucloud_a;
+          asmcmc(ig, lay) = (asmcmc(ig, lay) - ffp) / (ffp1);
+        } else if (inflag == 1) {
+          err = "INFLAG = 1 OPTION NOT AVAILABLE WITH MCICA"; return 1;
+        } else if (inflag == 2) {
+          double radice = reicmc(lay);
+          int ib = ngb_sw_[ig - 1];
+          int k = ib - 15;
+          if (ciwpmc(ig, lay) == 0.0) { extcoice[ig] = 0.; ssacoice[ig] = 0.; gice[ig] = 0.; forwice[ig] = 0.; }
+          else if (iceflag == 1) {
+            if (radice < 13.0 || radice > 130.) { err = "ICE RADIUS OUT OF BOUNDS"; return 1; }
+            int icx = 5;
+            double w2 = wavenum2_[ib - 16];
+            if (w2 > 1.43e04) icx = 1; else if (w2 > 7.7e03) icx = 2; else if (w2 > 5.3e03) icx = 3; else if (w2 > 4.0e03) icx = 4;
+            extcoice[ig] = (S.abari(icx) + S.bbari(icx) / radice);
+            ssacoice[ig] = 1. - S.cbari(icx) - S.dbari(icx) * radice;
+            gice[ig] = S.ebari(icx) + S.fbari(icx) * radice;
+            if (gice[ig] >= 1.) gice[ig] = 1. - eps;
+            forwice[ig] = gice[ig] * gice[ig];
+          } else if (iceflag == 2) {
+            if (radice < 5.0 || radice > 131.0) { err = "ICE RADIUS OUT OF BOUNDS"; return 1; }
+            double factor = (radice - 2.) / 3.;
+            int index = (int)factor;
+            if (index == 43) index = 42;
+            double fint = factor - (double)index;
+            extcoice[ig] = S.extice2(index, k) + fint * (S.extice2(index + 1, k) - S.extice2(index, k));
+            ssacoice[ig] = S.ssaice2(index, k) + fint * (S.ssaice2(index + 1, k) - S.ssaice2(index, k));
+            gice[ig] = S.asyice2(index, k) + fint * (S.asyice2(index + 1, k) - S.asyice2(index, k));
+            forwice[ig] = gice[ig] * gice[ig];
+          } else if (iceflag == 3) {
+            if (radice < 5.0 || radice > 140.0) { err = "ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS"; return 1; }
+            double factor = (radice - 2.) / 3.;
+            int index = (int)factor;
+            if (index == 46) index = 45;
+            double fint = factor - (double)index;
+            extcoice[ig] = S.extice3(index, k) + fint * (S.extice3(index + 1, k) - S.extice3(index, k));
+            ssacoice[ig] = S.ssaice3(index, k) + fint * (S.ssaice3(index + 1, k) - S.ssaice3(index, k));
+            gice[ig] = S.asyice3(index, k) + fint * (S.asyice3(index + 1, k) - S.asyice3(index, k));
+            fdelta[ig] = S.fdlice3(index, k) + fint * (S.fdlice3(index + 1, k) - S.fdlice3(index, k));
+            forwice[ig] = fdelta[ig] + 0.5 / ssacoice[ig];
+            if (forwice[ig] > gice[ig]) forwice[ig] = gice[ig];
+          }
+          if (clwpmc(ig, lay) == 0.0) { extcoliq[ig] = 0.; ssacoliq[ig] = 0.; gliq[ig] = 0.; forwliq[ig] = 0.; }
+          else if (liqflag == 1) {
+            double radliq = relqmc(lay);
+            if (radliq < 2.5 || radliq > 60.) { err = "LIQUID EFFECTIVE RADIUS OUT OF BOUNDS"; return 1; }
+            int index = (int)(radliq - 1.5);
+            if (index == 0) index = 1;
+            if (index == 58) index = 57;
+            double fint = radliq - 1.5 - (double)index;
+            extcoliq[ig] = S.extliq1(index, k) + fint * (S.extliq1(index + 1, k) - S.extliq1(index, k));
+            ssacoliq[ig] = S.ssaliq1(index, k) + fint * (S.ssaliq1(index + 1, k) - S.ssaliq1(index, k));
+            if (fint < 0. && ssacoliq[ig] > 1.) ssacoliq[ig] = S.ssaliq1(index, k);
+            gliq[ig] = S.asyliq1(index, k) + fint * (S.asyliq1(index + 1, k) - S.asyliq1(index, k));
+            forwliq[ig] = gliq[ig] * gliq[ig];
+          }
+          double tauliqorig = clwpmc(ig, lay) * extcoliq[ig], tauiceorig = ciwpmc(ig, lay) * extcoice[ig];
+          taormc(ig, lay) = tauliqorig + tauiceorig;
+          double ssaliq = ssacoliq[ig] * (1. - forwliq[ig]) / (1. - forwliq[ig] * ssacoliq[ig]);
+          double tauliq = (1. - forwliq[ig] * ssacoliq[ig]) * tauliqorig;
+          double ssaice = ssacoice[ig] * (1. - forwice[ig]) / (1. - forwice[ig] * ssacoice[ig]);
+          double tauice = (1. - forwice[ig] * ssacoice[ig]) * tauiceorig;
+          double scatliq = ssaliq * tauliq, scatice = ssaice * tauice;
+          taucmc(ig, lay) = tauliq + tauice;
+          if (taucmc(ig, lay) == 0.) taucmc(ig, lay) = cldmin;
+          if (scatice == 0.) scatice = cldmin;
+          ssacmc(ig, lay) = (scatliq + scatice) / taucmc(ig, lay);
+          if (iceflag == 3)
+            asmcmc(ig, lay) = (1.0 / (scatliq + scatice)) * (scatliq * (gliq[ig] - forwliq[ig]) / (1.0 - forwliq[ig]) +
+                                                             scatice * ((gice[ig] - forwice[ig]) / (1.0 - forwice[ig])));
+          else
+            asmcmc(ig, lay) = (scatliq * (gliq[ig] - forwliq[ig]) / (1.0 - forwliq[ig]) +
+                               scatice * (gice[ig] - forwice[ig]) / (1.0 - forwice[ig])) / (scatliq + scatice);
+        }
+      }
+    }
+  return 0;
+}
+}  // namespace orcsw
+
+// mcica_subcol_sw_wrapper + rrtmg_sw_mcica_wrapper (rrtmg_sw_c_binder.f90:59-201) as chained by _rrtmg_sw.pyx:284-417
+extern "C" int orc_sw_mcica(int ncol, int nlay, int* icld, int* iaer, int permuteseed, int irng, const double* play,
+                            const double* plev, const double* tlay, const double* tlev, const double* tsfc,
+                            const double* h2ovmr, const double* o3vmr, const double* co2vmr, const double* ch4vmr,
+                            const double* n2ovmr, const double* o2vmr, const double* asdir, const double* asdif,
+                            const double* aldir, const double* aldif, const double* coszen, double adjes, int dyofyr,
+                            double scon, int isolvar, int inflgsw, int iceflgsw, int liqflgsw, const double* cldfr,
+                            const double* taucld, const double* ssacld, const double* asmcld, const double* fsfcld,
+                            const double* cicewp, const double* cliqwp, const double* reice, const double* reliq,
+                            const double* tauaer, const double* ssaaer, const double* asmaer, const double* ecaer,
+                            double* swuflx, double* swdflx, double* swhr, double* swuflxc, double* swdflxc, double* swhrc,
+                            const double* bndsolvar, double* indsolvar, double solcycfrac) {
+  if (!S.ready) { g_err_sw = "orc_sw_ini not called"; return 1; }
+  init_ngb_sw();
+  const double zepzen = 1.e-10;
+  S.oneminus = 1.0 - 1.e-06;
+  S.pi = 2. * std::asin(1.);
+  if (*icld < 0 || *icld > 3) { g_err_sw = "MCICA_SUBCOL: INVALID ICLD"; return 2; }
+  if (*iaer != 0 && *iaer != 6 && *iaer != 10) *iaer = 0;
+  const size_t nsub = 112, tot = nsub * (size_t)ncol * nlay;
+  std::vector<double> cldfmcl(tot, 0.), ciwpmcl(tot, 0.), clwpmcl(tot, 0.), taucmcl(tot, 0.), ssacmcl(tot, 1.),
+      asmcmcl(tot, 0.), fsfcmcl(tot, 0.);
+  if (*icld != 0) {
+    std::vector<double> pmid((size_t)ncol * nlay);
+    for (size_t i = 0; i < pmid.size(); ++i) pmid[i] = play[i] * 1.e2;
+    if (orc::generate_stochastic_clouds(ncol, nlay, 112, *icld, irng, pmid.data(), cldfr, cliqwp, cicewp, taucld, 14,
+                                        ngb_sw_, 15, cldfmcl.data(), clwpmcl.data(), ciwpmcl.data(), taucmcl.data(),
+                                        permuteseed, g_err_sw, ssacld, asmcld, fsfcld, ssacmcl.data(), asmcmcl.data(),
+                                        fsfcmcl.data()))
+      return 2;
+  }
+  SwIn in{ncol, nlay, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, asdir, asdif, aldir, aldif,
+          coszen, cldfr, taucld, ssacld, asmcld, fsfcld, cicewp, cliqwp, reice, reliq, tauaer, ssaaer, asmaer, ecaer};
+  Col c(nlay);
+  SwFlux F(nlay);
+  A2 dummy(nlay + 1, 14), ztaua(nlay + 1, 14), zasya(nlay + 1, 14), zomga(nlay + 1, 14);
+  A2 cldfmc(112, nlay + 1), taucmc(112, nlay + 1), ciwpmc(112, nlay + 1), clwpmc(112, nlay + 1), ssacmc(112, nlay + 1),
+      asmcmc(112, nlay + 1), fsfcmc(112, nlay + 1), taormc(112, nlay + 1);
+  A2 zcldfmc(nlay + 1, 112), ztaucmc(nlay + 1, 112), zasycmc(nlay + 1, 112), zomgcmc(nlay + 1, 112);
+  A1 reicmc(nlay + 1), relqmc(nlay + 1);
+  for (int iplon = 1; iplon <= ncol; ++iplon) {
+    inatm_sw(in, iplon, 0, *iaer, adjes, dyofyr, scon, isolvar, inflgsw, iceflgsw, liqflgsw, bndsolvar, indsolvar,
+             solcycfrac, c);
+    std::fill(cldfmc.d.begin(), cldfmc.d.end(), 0.); std::fill(taucmc.d.begin(), taucmc.d.end(), 0.);
+    std::fill(ssacmc.d.begin(), ssacmc.d.end(), 1.); std::fill(asmcmc.d.begin(), asmcmc.d.end(), 0.);
+    std::fill(fsfcmc.d.begin(), fsfcmc.d.end(), 0.); std::fill(ciwpmc.d.begin(), ciwpmc.d.end(), 0.);
+    std::fill(clwpmc.d.begin(), clwpmc.d.end(), 0.);
+    if (*icld >= 1)
+      for (int l = 1; l <= nlay; ++l) {
+        for (int ig = 1; ig <= 112; ++ig) {
+          size_t o = (size_t)(ig - 1) + nsub * ((size_t)(iplon - 1) + (size_t)ncol * (l - 1));
+          cldfmc(ig, l) = cldfmcl[o]; taucmc(ig, l) = taucmcl[o]; ssacmc(ig, l) = ssacmcl[o]; asmcmc(ig, l) = asmcmcl[o];
+          fsfcmc(ig, l) = fsfcmcl[o]; ciwpmc(ig, l) = ciwpmcl[o]; clwpmc(ig, l) = clwpmcl[o];
+        }
+        reicmc(l) = reice[(size_t)(iplon - 1) + (size_t)ncol * (l - 1)];
+        relqmc(l) = reliq[(size_t)(iplon - 1) + (size_t)ncol * (l - 1)];
+      }
+    if (cldprmc_sw(nlay, inflgsw, iceflgsw, liqflgsw, cldfmc, ciwpmc, clwpmc, reicmc, relqmc, taormc, taucmc, ssacmc, asmcmc,
+                   fsfcmc, g_err_sw))
+      return 2;
+    setcoef_sw(c);
+    double cossza = coszen[iplon - 1];
+    if (cossza < zepzen) cossza = zepzen;
+    double albdir[15], albdif[15];
+    for (int ib = 1; ib <= 9; ++ib) { albdir[ib] = aldir[iplon - 1]; albdif[ib] = aldif[iplon - 1]; }
+    albdir[nbndsw] = aldir[iplon - 1]; albdif[nbndsw] = aldif[iplon - 1];
+    for (int ib = 10; ib <= 13; ++ib) { albdir[ib] = asdir[iplon - 1]; albdif[ib] = asdif[iplon - 1]; }
+    if (*icld == 0) {
+      std::fill(zcldfmc.d.begin(), zcldfmc.d.end(), 0.); std::fill(ztaucmc.d.begin(), ztaucmc.d.end(), 0.);
+      std::fill(zasycmc.d.begin(), zasycmc.d.end(), 0.); std::fill(zomgcmc.d.begin(), zomgcmc.d.end(), 1.);
+    } else {
+      for (int i = 1; i <= nlay; ++i)
+        for (int ig = 1; ig <= 112; ++ig) {
+          zcldfmc(i, ig) = cldfmc(ig, i); ztaucmc(i, ig) = taucmc(ig, i); zasycmc(i, ig) = asmcmc(ig, i); zomgcmc(i, ig) = ssacmc(ig, i);
+        }
+    }
+    if (*iaer == 0) {
+      std::fill(ztaua.d.begin(), ztaua.d.end(), 0.); std::fill(zasya.d.begin(), zasya.d.end(), 0.); std::fill(zomga.d.begin(), zomga.d.end(), 1.);
+    } else if (*iaer == 6) {
+      for (int i = 1; i <= nlay; ++i)
+        for (int ib = 1; ib <= nbndsw; ++ib) {
+          ztaua(i, ib) = 0.; zasya(i, ib) = 0.; zomga(i, ib) = 0.;
+          for (int ia = 1; ia <= naerec; ++ia) {
+            double ec = ecaer[(size_t)(iplon - 1) + (size_t)ncol * ((i - 1) + (size_t)nlay * (ia - 1))];
+            ztaua(i, ib) = ztaua(i, ib) + S.rsrtaua(ib, ia) * ec;
+            zomga(i, ib) = zomga(i, ib) + S.rsrtaua(ib, ia) * ec * S.rsrpiza(ib, ia);
+            zasya(i, ib) = zasya(i, ib) + S.rsrtaua(ib, ia) * ec * S.rsrpiza(ib, ia) * S.rsrasya(ib, ia);
+          }
+          if (ztaua(i, ib) == 0.) { ztaua(i, ib) = 0.; zasya(i, ib) = 0.; zomga(i, ib) = 1.; }
+          else {
+            if (zomga(i, ib) != 0.) zasya(i, ib) = zasya(i, ib) / zomga(i, ib);
+            if (ztaua(i, ib) != 0.) zomga(i, ib) = zomga(i, ib) / ztaua(i, ib);
+          }
+        }
+    } else {
+      for (int i = 1; i <= nlay; ++i)
+        for (int ib = 1; ib <= nbndsw; ++ib) { ztaua(i, ib) = c.taua(i, ib); zasya(i, ib) = c.asma(i, ib); zomga(i, ib) = c.ssaa(i, ib); }
+    }
+    McCloud mc{&zcldfmc, &ztaucmc, &zasycmc, &zomgcmc};
+    spcvrt_sw(c, 1, albdif, albdir, dummy, dummy, dummy, ztaua, zasya, zomga, cossza, isolvar, F, &mc);
     for (int i = 1; i <= nlay + 1; ++i) {
       size_t o = (size_t)(iplon - 1) + (size_t)ncol * (i - 1);
       swuflxc[o] = F.bbcu(i); swdflxc[o] = F.bbcd(i); swuflx[o] = F.bbfu(i); swdflx[o] = F.bbfd(i);

@@ -4,15 +4,19 @@
 #include <vector>
 
 #include "../../climt_b200/csrc/sw_tables.h"
+#include "../../climt_b200/csrc/mcica_host.h"
 
 using namespace cb::sw;
 
 template <int B, int U>
-static void run_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int n, int g0, int unit) {
-  for (int c = 0; c < n; ++c) sw_unit<B, U>(T, sol, in, fl, W, 0, c, g0, unit);
+static void run_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int n, int g0, int unit, bool mc) {
+  for (int c = 0; c < n; ++c) {
+    if (mc) sw_unit<B, U, true>(T, sol, in, fl, W, 0, c, g0, unit);
+    else sw_unit<B, U, false>(T, sol, in, fl, W, 0, c, g0, unit);
+  }
 }
 
-// scal = {adjes, scon, solcycfrac, indsolvar0, indsolvar1, bndsolvar[14]}; iopt = {icld, iaer, inflag, iceflag, liqflag, isolvar, dyofyr}
+// scal = {adjes, scon, solcycfrac, indsolvar0, indsolvar1, bndsolvar[14]}; iopt = {icld, iaer, inflag, iceflag, liqflag, isolvar, dyofyr, mcica, irng, permuteseed}
 extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* iopt, const double* scal, int ncol, int nlay,
                            const double* const* inp /*29 pointers in struct In order*/, double* const* outp /*6*/) {
   try {
@@ -29,7 +33,9 @@ extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* 
     Out out;
     double** op = &out.uflx;
     for (int i = 0; i < 6; ++i) op[i] = outp[i];
-    Flags fl{iopt[0], iopt[1], iopt[2], iopt[3], iopt[4]};
+    Flags fl{iopt[0], iopt[1], iopt[2], iopt[3], iopt[4], iopt[7]};
+    const int irng = iopt[8], seed = iopt[9];
+    const bool mc = fl.mcica && fl.icld >= 1;
     SolarOptions so;
     so.isolvar = iopt[5]; so.scon = scal[1]; so.indsolvar[0] = scal[3]; so.indsolvar[1] = scal[4];
     for (int i = 0; i < 14; ++i) so.bndsolvar[i] = scal[5 + i];
@@ -41,13 +47,19 @@ extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* 
     std::vector<double> ws((size_t)NF * nlay * ncol), cld((size_t)42 * nlay * ncol), aer((size_t)42 * nlay * ncol),
         scr((size_t)112 * NSCR * nlay * ncol), part((size_t)nunits * 4 * (nlay + 1) * ncol);
     std::vector<int> idx((size_t)nlay * ncol), lt(ncol), ls((size_t)14 * ncol), ac(ncol);
+    std::vector<unsigned> mask((size_t)4 * nlay * ncol, 0u);
     int err = 0;
+    W.mask = mask.data(); W.mstride = ncol; W.moff = 0;
     W.ws = ws.data(); W.idx = idx.data(); W.laytrop = lt.data(); W.laysolfr = ls.data(); W.anycld = ac.data();
     W.cld = cld.data(); W.aer = aer.data(); W.scr = scr.data(); W.part = part.data(); W.err = &err;
+    if (mc && irng == 1) { cb::mcica::mask_mt_host(in.cldfr, ncol, nlay, 112, 4, fl.icld, seed, mask); W.mask = mask.data(); }
+    if (mc && irng == 0)
+      for (int c = 0; c < ncol; ++c)
+        if (cb::mcica::mask_column_kiss(in.play, in.cldfr, ncol, nlay, 112, 4, fl.icld, seed, W.mask, ncol, 0, c)) err = 9;
     for (int c = 0; c < ncol; ++c) sw_prep_column(T, in, fl, W, 0, c);
     for (int k2 = 0; k2 < nunits; ++k2) {
       const Unit un = units[k2];
-#define CASE(B) case B: if (un.u == 4) run_unit<B, 4>(T, sol, in, fl, W, ncol, un.g0, k2); else run_unit<B, 2>(T, sol, in, fl, W, ncol, un.g0, k2); break;
+#define CASE(B) case B: if (un.u == 4) run_unit<B, 4>(T, sol, in, fl, W, ncol, un.g0, k2, mc); else run_unit<B, 2>(T, sol, in, fl, W, ncol, un.g0, k2, mc); break;
       switch (un.band) {
         CASE(16) CASE(17) CASE(18) CASE(19) CASE(20) CASE(21) CASE(22) CASE(23) CASE(24) CASE(25) CASE(26) CASE(27)
         CASE(28) CASE(29)

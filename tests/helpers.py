@@ -132,7 +132,7 @@ def run_lw_emul(st, flags=(1, 0, 2, 1, 1), mcica=(0, 1, 0)):
     return rc, out
 
 
-def run_sw_emul(st, iopt=(1, 0, 2, 1, 1, 0, 1), scal=None):
+def run_sw_emul(st, iopt=(1, 0, 2, 1, 1, 0, 1), scal=None, mcica=(0, 1, 0)):
     """iopt = (icld, iaer, inflag, iceflag, liqflag, isolvar, dyofyr); scal = [adjes, scon, solcycfrac, ind0, ind1, bnd[14]]"""
     lib = emul_lib("sw")
     k = C.rrtmg_constants()
@@ -144,7 +144,8 @@ def run_sw_emul(st, iopt=(1, 0, 2, 1, 1, 0, 1), scal=None):
     out = {n: np.zeros((nlay + 1, ncol)) for n in ("uflx", "dflx", "uflxc", "dflxc")}
     out.update({n: np.zeros((nlay, ncol)) for n in ("hr", "hrc")})
     outp = (_dp * 6)(*[out[n].ctypes.data_as(_dp) for n in ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc")])
-    rc = lib.emul_sw_run(RT.sw_blob_path().encode(), consts.ctypes.data_as(_dp), (ctypes.c_int * 7)(*iopt),
+    iopt = tuple(iopt) + tuple(mcica)
+    rc = lib.emul_sw_run(RT.sw_blob_path().encode(), consts.ctypes.data_as(_dp), (ctypes.c_int * 10)(*iopt),
                          scal.ctypes.data_as(_dp), ncol, nlay, inp, outp)
     return rc, out
 

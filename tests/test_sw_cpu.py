@@ -75,3 +75,39 @@ def test_sw_partial_cloud_is_reported():
     st["cicewp"][10, :] = 10.0
     rc, _ = H.run_sw_emul(st)
     assert rc == 10    # 'PARTIAL CLOUD NOT ALLOWED' (rrtmg_sw_rad.nomcica.f90:618)
+
+
+def _mcica_golden_state():
+    """TestRRTMGShortwaveMCICA-3d: 3x2 columns x 15 levels, cloud 0.5 / ice 0.3 kg m-2 in layers 10:12 (tests/test_components.py:487-499)."""
+    st = H.default_sw_abi_state(15, 6)
+    st["cldfr"][10:12] = 0.5
+    st["cicewp"][10:12] = 0.3e3
+    np.random.seed(0)
+    return st, int(np.random.randint(0, 2 ** 31 - 1))
+
+
+def test_sw_mcica_oracle_and_emulated_kernels_match_reference_golden():
+    from oracle.rrtmg import sw_mcica
+    g = H.golden()
+    st, seed = _mcica_golden_state()
+    o = sw_mcica(H.sw_oracle(), st, seed, irng=1, dyofyr=1)
+    rc, e = H.run_sw_emul(st, (1, 0, 2, 1, 1, 0, 1), mcica=(1, 1, seed))
+    assert rc == 0
+    for name, k in (("upwelling_shortwave_flux_in_air", "uflx"), ("downwelling_shortwave_flux_in_air", "dflx"),
+                    ("air_temperature_tendency_from_shortwave", "hr")):
+        ref = g[f"TestRRTMGShortwaveMCICA-3d/diag/{name}"].reshape(-1, 6)
+        np.testing.assert_allclose(o[H.SW_KEYS[k]], ref, rtol=0, atol=1e-8)
+        np.testing.assert_allclose(e[k], ref, rtol=0, atol=1e-8)
+    assert np.ptp(e["uflx"][0]) > 5.0   # SURVEY appendix B: columns differ only through the random masks
+
+
+@pytest.mark.parametrize("icld,irng", [(1, 0), (2, 0), (3, 0), (1, 1), (2, 1), (3, 1)])
+def test_sw_mcica_emulated_kernels_match_oracle(icld, irng):
+    from oracle.rrtmg import sw_mcica
+    st = SY.make_sw_state(8, 33, seed=3 + icld, clouds=True, overcast_only=False, aerosol=True)
+    ref = sw_mcica(H.sw_oracle(cloud_overlap=icld, iaer=10), st, 55, irng=irng, dyofyr=150)
+    rc, got = H.run_sw_emul(st, (icld, 10, 2, 1, 1, 0, 150), mcica=(1, irng, 55))
+    assert rc == 0
+    for k, kk in H.SW_KEYS.items():
+        if not k.startswith("hr"):
+            assert H.rel_err(got[k], ref[kk]) < 1e-10, k
