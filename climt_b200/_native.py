@@ -16,7 +16,7 @@ HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("cb_common.h", "engine_commo
                                                           "mcica_core.cuh", "mcica_host.h")] + [
     os.path.join(_HERE, "..", "include", "climt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "--fmad=false"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "--fmad=true"]
 
 _lib = None
 _dp = ctypes.POINTER(ctypes.c_double)

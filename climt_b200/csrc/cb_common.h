@@ -18,7 +18,42 @@
 #define CB_LDG(p) (*(p))
 #endif
 
+#if defined(__CUDA_ARCH__)
+// a*b + c with two roundings (never contracted to an FMA): used wherever the result is truncated to a table index,
+// so that the device picks the same table slot as the reference's separately-rounded multiply and add.
+#define CB_MULADD_2R(a, b, c) __dadd_rn(__dmul_rn((a), (b)), (c))
+#else
+#define CB_MULADD_2R(a, b, c) (((a) * (b)) + (c))
+#endif
+
 namespace cb {
+
+// U consecutive doubles of a table row (16-byte aligned by construction: even table offsets, even g-point counts,
+// unit starts that are multiples of 4) fetched with 128-bit read-only loads.
+template <int U>
+struct Row {
+  double v[U];
+  CB_HD double operator[](int i) const { return v[i]; }
+};
+template <int U>
+CB_HD Row<U> ldrow(const double* __restrict__ p) {
+  Row<U> r;
+#if defined(__CUDA_ARCH__)
+  if (U == 4) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+  } else if (U == 2) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    r.v[0] = a.x; r.v[1] = a.y;
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u) r.v[u] = __ldg(p + u);
+  }
+#else
+  for (int u = 0; u < U; ++u) r.v[u] = p[u];
+#endif
+  return r;
+}
 
 // Fortran real->integer assignment / int(): truncation toward zero.
 CB_HD int f2i(double x) { return (int)x; }

@@ -47,6 +47,7 @@ struct Tables {
   BandOff b[NBND];
   int chi_mls, preflog, tref, rat, totplnk, totplnkderiv, delwave;
   int tau_tbl, exp_tbl, tfn_tbl;
+  int et_tbl;  // interleaved {exp_tbl[i], tfn_tbl[i]} pairs: one 128-bit gather instead of two 64-bit ones
   int absice0, absice1, absice2, absice3, absliq1;
   double abscld1, absliq0;
   double bpade, heatfac, fluxfac, oneminus, avogad, grav;
@@ -152,7 +153,7 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
     WS(F_WX4, l) = coldry * in.cfc22[o] * 1.e-20;
     // ---- setcoef, rrtmg_lw_setcoef.f90:257-412
     const double plog = log(pavel);
-    int jp = (int)(36. - 5 * (plog + 0.04));
+    int jp = (int)(CB_MULADD_2R(-5., (plog + 0.04), 36.));
     if (jp < 1) jp = 1; else if (jp > 58) jp = 58;
     const double fp = 5. * (tb[T.preflog + jp - 1] - plog);
     const double tr0 = tb[T.tref + jp - 1], tr1 = tb[T.tref + jp];
@@ -213,11 +214,11 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
     if (clouds && fl.mcica) {
       const double cldmin = 1.e-20;
       const double ciwp = in.cicewp[o], clwp = in.cliqwp[o];
-      const double* tc = in.taucld + 16 * ((size_t)l * ncol + gc);
+      const double* tc = in.taucld ? in.taucld + 16 * ((size_t)l * ncol + gc) : nullptr;  // null = all zero
       const double cwp = ciwp + clwp;
       const int pat5[16] = {0, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4};
       for (int ib = 0; ib < 16; ++ib) {
-        double tau = tc[ib];
+        double tau = tc ? tc[ib] : 0.0;
         if (cwp >= cldmin || tau >= cldmin) {
           if (fl.inflag == 1) *W.err = 8;  // 'INFLAG = 1 OPTION NOT AVAILABLE WITH MCICA'
           if (fl.inflag == 2) {
@@ -273,14 +274,14 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
       const double cldfrac = in.cldfr[o];
       const double ciwp = in.cicewp[o], clwp = in.cliqwp[o];
       double tauctot = 0.0;
-      const double* tc = in.taucld + 16 * ((size_t)l * ncol + gc);
-      for (int ib = 0; ib < 16; ++ib) tauctot = tauctot + tc[ib];
+      const double* tc = in.taucld ? in.taucld + 16 * ((size_t)l * ncol + gc) : nullptr;  // null = all zero
+      if (tc) for (int ib = 0; ib < 16; ++ib) tauctot = tauctot + tc[ib];
       const double cwp = ciwp + clwp;
       const double cldmin = 1.e-20;
       if (cldfrac >= cldmin && (cwp >= cldmin || tauctot >= cldmin)) {
         if (fl.inflag == 0) {
           ncbands = 16;
-          for (int ib = 0; ib < 16; ++ib) taucloud[ib] = tc[ib];
+          for (int ib = 0; ib < 16; ++ib) taucloud[ib] = tc ? tc[ib] : 0.0;
         } else if (fl.inflag == 1) {
           ncbands = 16;
           for (int ib = 0; ib < 16; ++ib) taucloud[ib] = T.abscld1 * cwp;
@@ -613,10 +614,9 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     const int row1 = LOWER ? (jp * 5 + (jt1 - 1)) * nsp : ((jp - 12) * 5 + (jt1 - 1)) * nsp;
     const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
     const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
+    const Row<U> k00 = ldrow<U>(a0), k10 = ldrow<U>(a0 + ng), k01 = ldrow<U>(a1), k11 = ldrow<U>(a1 + ng);
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      acc[u] = cola * (fac00 * CB_LDG(a0 + u) + fac10 * CB_LDG(a0 + ng + u) + fac01 * CB_LDG(a1 + u) +
-                       fac11 * CB_LDG(a1 + ng + u));
+    for (int u = 0; u < U; ++u) acc[u] = cola * (fac00 * k00[u] + fac10 * k10[u] + fac01 * k01[u] + fac11 * k11[u]);
   } else if (R.kind == 2) {
     const double fac00 = WSF(F_FAC00), fac01 = WSF(F_FAC01), fac10 = WSF(F_FAC10), fac11 = WSF(F_FAC11);
     constexpr double n = LOWER ? 8. : 4.;
@@ -630,45 +630,46 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     const Stencil t1 = make_stencil<LOWER>(s1.specparm, s1.fs, fac01, fac11);
     const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
     const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
+    double d0[U], d1[U];
+    {
+      const Row<U> r0 = ldrow<U>(a0 + t0.off[0] * ng), r1 = ldrow<U>(a0 + t0.off[1] * ng), r2 = ldrow<U>(a0 + t0.off[2] * ng),
+                   r3 = ldrow<U>(a0 + t0.off[3] * ng);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      double d0 = t0.w[0] * CB_LDG(a0 + t0.off[0] * ng + u);
-      d0 = d0 + t0.w[1] * CB_LDG(a0 + t0.off[1] * ng + u);
-      d0 = d0 + t0.w[2] * CB_LDG(a0 + t0.off[2] * ng + u);
-      d0 = d0 + t0.w[3] * CB_LDG(a0 + t0.off[3] * ng + u);
+      for (int u = 0; u < U; ++u) d0[u] = ((t0.w[0] * r0[u] + t0.w[1] * r1[u]) + t0.w[2] * r2[u]) + t0.w[3] * r3[u];
       if (LOWER && t0.n == 6) {
-        d0 = d0 + t0.w[4] * CB_LDG(a0 + t0.off[4] * ng + u);
-        d0 = d0 + t0.w[5] * CB_LDG(a0 + t0.off[5] * ng + u);
+        const Row<U> r4 = ldrow<U>(a0 + t0.off[4] * ng), r5 = ldrow<U>(a0 + t0.off[5] * ng);
+#pragma unroll
+        for (int u = 0; u < U; ++u) d0[u] = (d0[u] + t0.w[4] * r4[u]) + t0.w[5] * r5[u];
       }
-      double d1 = t1.w[0] * CB_LDG(a1 + t1.off[0] * ng + u);
-      d1 = d1 + t1.w[1] * CB_LDG(a1 + t1.off[1] * ng + u);
-      d1 = d1 + t1.w[2] * CB_LDG(a1 + t1.off[2] * ng + u);
-      d1 = d1 + t1.w[3] * CB_LDG(a1 + t1.off[3] * ng + u);
-      if (LOWER && t1.n == 6) {
-        d1 = d1 + t1.w[4] * CB_LDG(a1 + t1.off[4] * ng + u);
-        d1 = d1 + t1.w[5] * CB_LDG(a1 + t1.off[5] * ng + u);
-      }
-      acc[u] = s0.speccomb * d0 + s1.speccomb * d1;
     }
+    {
+      const Row<U> r0 = ldrow<U>(a1 + t1.off[0] * ng), r1 = ldrow<U>(a1 + t1.off[1] * ng), r2 = ldrow<U>(a1 + t1.off[2] * ng),
+                   r3 = ldrow<U>(a1 + t1.off[3] * ng);
+#pragma unroll
+      for (int u = 0; u < U; ++u) d1[u] = ((t1.w[0] * r0[u] + t1.w[1] * r1[u]) + t1.w[2] * r2[u]) + t1.w[3] * r3[u];
+      if (LOWER && t1.n == 6) {
+        const Row<U> r4 = ldrow<U>(a1 + t1.off[4] * ng), r5 = ldrow<U>(a1 + t1.off[5] * ng);
+#pragma unroll
+        for (int u = 0; u < U; ++u) d1[u] = (d1[u] + t1.w[4] * r4[u]) + t1.w[5] * r5[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = s0.speccomb * d0[u] + s1.speccomb * d1[u];
   }
   // ---- water-vapour self and foreign continua
   if (R.self) {
     const double selffac = WSF(F_SELFFAC), selffrac = WSF(F_SELFFRAC);
     const double* __restrict__ s = tb + O.selfref + (size_t)(inds - 1) * ng + g0;
+    const Row<U> k0 = ldrow<U>(s), k1 = ldrow<U>(s + ng);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const double k0 = CB_LDG(s + u), k1 = CB_LDG(s + ng + u);
-      acc[u] = acc[u] + selffac * (k0 + selffrac * (k1 - k0));
-    }
+    for (int u = 0; u < U; ++u) acc[u] = acc[u] + selffac * (k0[u] + selffrac * (k1[u] - k0[u]));
   }
   if (R.forn) {
     const double forfac = WSF(F_FORFAC), forfrac = WSF(F_FORFRAC);
     const double* __restrict__ s = tb + O.forref + (size_t)(indf - 1) * ng + g0;
+    const Row<U> k0 = ldrow<U>(s), k1 = ldrow<U>(s + ng);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const double k0 = CB_LDG(s + u), k1 = CB_LDG(s + ng + u);
-      acc[u] = acc[u] + forfac * (k0 + forfrac * (k1 - k0));
-    }
+    for (int u = 0; u < U; ++u) acc[u] = acc[u] + forfac * (k0[u] + forfrac * (k1[u] - k0[u]));
   }
   // ---- minor gases
   if (R.nminor > 0) {
@@ -705,21 +706,18 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
         const double refr = M.refr == RM_A ? O.refrat_m_a : (M.refr == RM_B ? O.refrat_m_b : O.refrat_m_a3);
         const BinSpec sm = binspec(cola, refr, colb, n, T.oneminus);
         const double* __restrict__ t = tb + O.m[M.slot] + ((size_t)(sm.js - 1) + nsp * (size_t)(indm - 1)) * ng + g0;
+        const Row<U> k00 = ldrow<U>(t), k10 = ldrow<U>(t + ng), k01 = ldrow<U>(t + nsp * ng), k11 = ldrow<U>(t + (nsp + 1) * ng);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const double k00 = CB_LDG(t + u), k10 = CB_LDG(t + ng + u);
-          const double k01 = CB_LDG(t + nsp * ng + u), k11 = CB_LDG(t + (nsp + 1) * ng + u);
-          const double m1 = k00 + sm.fs * (k10 - k00);
-          const double m2 = k01 + sm.fs * (k11 - k01);
+          const double m1 = k00[u] + sm.fs * (k10[u] - k00[u]);
+          const double m2 = k01[u] + sm.fs * (k11[u] - k01[u]);
           acc[u] = acc[u] + amount * (m1 + minorfrac * (m2 - m1));
         }
       } else {
         const double* __restrict__ t = tb + O.m[M.slot] + (size_t)(indm - 1) * ng + g0;
+        const Row<U> k0 = ldrow<U>(t), k1 = ldrow<U>(t + ng);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const double k0 = CB_LDG(t + u), k1 = CB_LDG(t + ng + u);
-          acc[u] = acc[u] + amount * (k0 + minorfrac * (k1 - k0));
-        }
+        for (int u = 0; u < U; ++u) acc[u] = acc[u] + amount * (k0[u] + minorfrac * (k1[u] - k0[u]));
       }
     }
   }
@@ -728,8 +726,9 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
   for (int k = 0; k < R.nx; ++k) {
     const double wx = WSF(F_WX1 + R.xwx[k]);
     const double* __restrict__ t = tb + O.x[R.xslot[k]] + g0;
+    const Row<U> xr = ldrow<U>(t);
 #pragma unroll
-    for (int u = 0; u < U; ++u) acc[u] = acc[u] + wx * CB_LDG(t + u);
+    for (int u = 0; u < U; ++u) acc[u] = acc[u] + wx * xr[u];
   }
   // ---- empirical corrections
   if (R.corr != 0) {
@@ -770,17 +769,16 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     constexpr double n = LOWER ? 8. : 4.;
     const BinSpec sp = binspec(cola, LOWER ? O.refrat_planck_a : O.refrat_planck_b, colb, n, T.oneminus);
     const double* __restrict__ f = tb + (LOWER ? O.fracrefa : O.fracrefb) + (size_t)(sp.js - 1) * ng + g0;
+    const Row<U> f0 = ldrow<U>(f), f1 = ldrow<U>(f + ng);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const double f0 = CB_LDG(f + u), f1 = CB_LDG(f + ng + u);
-      frac[u] = f0 + sp.fs * (f1 - f0);
-    }
+    for (int u = 0; u < U; ++u) frac[u] = f0[u] + sp.fs * (f1[u] - f0[u]);
   } else {
     // band 6 and 12/15 have no "b" table; band 6 upper uses fracrefa (taumol.f90:1388)
     constexpr bool use_a = LOWER || B == 6;
     const double* __restrict__ f = tb + (use_a ? O.fracrefa : O.fracrefb) + g0;
+    const Row<U> f0 = ldrow<U>(f);
 #pragma unroll
-    for (int u = 0; u < U; ++u) frac[u] = CB_LDG(f + u);
+    for (int u = 0; u < U; ++u) frac[u] = f0[u];
   }
 #undef WSF
 }
@@ -806,6 +804,8 @@ CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, 
   const double* __restrict__ tau_tbl = tb + T.tau_tbl;
   const double* __restrict__ exp_tbl = tb + T.exp_tbl;
   const double* __restrict__ tfn_tbl = tb + T.tfn_tbl;
+  const double* __restrict__ et_tbl = tb + T.et_tbl;
+  (void)exp_tbl; (void)tfn_tbl;
   const double* __restrict__ tp = tb + T.totplnk + (size_t)(B - 1) * 181;
   const size_t wstride = (size_t)nlay * ncc;
   const int laytrop = W.laytrop[c];
@@ -900,27 +900,30 @@ CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, 
           gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
           odtot = odepth + odcld;
           const double tblind = odtot / (bpade + odtot);
-          const int ittot = f2i(tblint * tblind + 0.5);
-          const double tfactot = CB_LDG(tfn_tbl + ittot);
+          const int ittot = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
+          const Row<2> ett = ldrow<2>(et_tbl + 2 * ittot);
+          const double tfactot = ett[1];
           bbdtot = plfrac * (blay + tfactot * dplankdn);
           bbd = plfrac * (blay + dplankdn * odepth_rec);
-          atot = 1. - CB_LDG(exp_tbl + ittot);
+          atot = 1. - ett[0];
           bbugas = plfrac * (blay + dplankup * odepth_rec);
           bbutot = plfrac * (blay + tfactot * dplankup);
         } else {
           double tblind = odepth / (bpade + odepth);
-          const int itgas = f2i(tblint * tblind + 0.5);
+          const int itgas = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
           odepth = CB_LDG(tau_tbl + itgas);
-          atrans = 1. - CB_LDG(exp_tbl + itgas);
-          const double tfacgas = CB_LDG(tfn_tbl + itgas);
+          const Row<2> etg = ldrow<2>(et_tbl + 2 * itgas);
+          atrans = 1. - etg[0];
+          const double tfacgas = etg[1];
           gassrc = atrans * plfrac * (blay + tfacgas * dplankdn);
           odtot = odepth + odcld;
           tblind = odtot / (bpade + odtot);
-          const int ittot = f2i(tblint * tblind + 0.5);
-          const double tfactot = CB_LDG(tfn_tbl + ittot);
+          const int ittot = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
+          const Row<2> ett = ldrow<2>(et_tbl + 2 * ittot);
+          const double tfactot = ett[1];
           bbdtot = plfrac * (blay + tfactot * dplankdn);
           bbd = plfrac * (blay + tfacgas * dplankdn);
-          atot = 1. - CB_LDG(exp_tbl + ittot);
+          atot = 1. - ett[0];
           bbugas = plfrac * (blay + tfacgas * dplankup);
           bbutot = plfrac * (blay + tfactot * dplankup);
         }
@@ -935,10 +938,11 @@ CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, 
           bbugas = plfrac * (blay + dplankup * odepth);
         } else {
           const double tblind = odepth / (bpade + odepth);
-          const int itr = f2i(tblint * tblind + 0.5);
-          const double transc = CB_LDG(exp_tbl + itr);
+          const int itr = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
+          const Row<2> et = ldrow<2>(et_tbl + 2 * itr);
+          const double transc = et[0];
           atrans = 1. - transc;
-          const double tausfac = CB_LDG(tfn_tbl + itr);
+          const double tausfac = et[1];
           bbd = plfrac * (blay + tausfac * dplankdn);
           bbugas = plfrac * (blay + tausfac * dplankup);
         }
@@ -1039,7 +1043,10 @@ CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, 
 struct Unit {
   int band, g0, u;
 };
-constexpr int kMaxUnits = 40;
+#ifndef CB_LW_UMAX
+#define CB_LW_UMAX 4  // g-points per thread (2 or 4)
+#endif
+constexpr int kMaxUnits = 72;
 inline int build_units(Unit* out) {  // host only
   int n = 0;
   // heavy (two-key-species, lower-atmosphere-rich) work first so the tail of the grid is made of light blocks
@@ -1048,10 +1055,10 @@ inline int build_units(Unit* out) {  // host only
       const bool heavy = kNSPA[b - 1] == 9;
       if ((pass == 0) != heavy) continue;
       const int ng = kNG[b - 1];
-      for (int g0 = 0; g0 < ng; g0 += 4) {
+      for (int g0 = 0; g0 < ng; g0 += CB_LW_UMAX) {
         out[n].band = b;
         out[n].g0 = g0;
-        out[n].u = (ng - g0) >= 4 ? 4 : (ng - g0);
+        out[n].u = (ng - g0) >= CB_LW_UMAX ? CB_LW_UMAX : (ng - g0);
         ++n;
       }
     }

@@ -19,7 +19,7 @@ namespace {
 
 using cb::kBlock;
 #ifndef CB_UNITS_MIN_BLOCKS
-#define CB_UNITS_MIN_BLOCKS 1
+#define CB_UNITS_MIN_BLOCKS 4
 #endif
 
 __global__ void __launch_bounds__(kBlock) k_prep(const __grid_constant__ Tables T, const __grid_constant__ In in,
@@ -102,11 +102,8 @@ struct cb200_lw_engine {
   int cap_ncc = 0, cap_nlay = 0;
   Work W{};
   int max_chunk = 16384;
-  // host-pointer path staging
-  double* d_stage = nullptr;
-  size_t stage_cap = 0;
-  double* h_pinned = nullptr;
-  size_t pinned_cap = 0;
+  // host-pointer path
+  cb::HostPipe pipe;
   int* h_err = nullptr;
   std::string error;
   int launches = 0;
@@ -179,9 +176,8 @@ extern "C" void cb200_lw_destroy(cb200_lw_engine* e) {
   cudaSetDevice(e->device);
   e->free_work();
   cudaFree(e->d_tables);
-  cudaFree(e->d_stage);
   cudaFree(e->d_mask_full);
-  if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  e->pipe.destroy();
   if (e->h_err) cudaFreeHost(e->h_err);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -219,6 +215,46 @@ static In make_in(int ncol, int nlay, const cb200_lw_inputs* p) {
   return in;
 }
 
+// One chunk of columns [c0, c0+n) of `in` through the kernels on stream `st` (the engine's single workspace).
+static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& W, int c0, int n, int out_ncol, bool mc,
+                        cudaStream_t st) {
+  const int nlay = in.nlay;
+  const int gx = (n + kBlock - 1) / kBlock;
+  if (mc && e->irng == 0) { k_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
+  k_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
+  if (e->timing) cudaEventRecord(e->ev0, st);
+  if (mc) k_units<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+  else k_units<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+  if (e->timing) cudaEventRecord(e->ev1, st);
+  k_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(e->T, W, e->UL, out, nlay, out_ncol, c0, n);
+  k_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
+  e->launches += 4;
+  if (e->timing) {
+    CUDA_OK(cudaEventSynchronize(e->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->unit_ms += ms;
+  }
+  return 0;
+}
+
+// Mersenne-twister McICA mask: one serial stream for the whole call (bit parity with climt's default RNG), so it is
+// drawn on the host from the host copy of the cloud fraction and uploaded once, [lay][word][ncol].
+static int upload_mt_mask(cb200_lw_engine* e, const double* h_cldfr, int ncol, int nlay, cudaStream_t st) {
+  std::vector<unsigned> h_mask;
+  cb::mcica::mask_mt_host(h_cldfr, ncol, nlay, 140, 5, e->fl.icld, e->permuteseed, h_mask);
+  if (h_mask.size() > e->mask_full_cap) {
+    cudaFree(e->d_mask_full);
+    e->d_mask_full = nullptr;
+    e->mask_full_cap = 0;
+    CUDA_OK(cudaMalloc(&e->d_mask_full, h_mask.size() * sizeof(unsigned)));
+    e->mask_full_cap = h_mask.size();
+  }
+  CUDA_OK(cudaMemcpyAsync(e->d_mask_full, h_mask.data(), h_mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 extern "C" int cb200_lw_run_device(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* pin,
                                    const cb200_lw_outputs* pout, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
@@ -237,43 +273,17 @@ extern "C" int cb200_lw_run_device(cb200_lw_engine* e, int ncol, int nlay, const
   W.mstride = chunk;
   W.moff = 0;
   if (mc && e->irng == 1) {
-    // Mersenne twister: one serial stream for the whole call (bit parity with climt's default RNG) -> host
     std::vector<double> h_cld((size_t)nlay * ncol);
     CUDA_OK(cudaMemcpyAsync(h_cld.data(), in.cldfr, h_cld.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    std::vector<unsigned> h_mask;
-    cb::mcica::mask_mt_host(h_cld.data(), ncol, nlay, 140, 5, e->fl.icld, e->permuteseed, h_mask);
-    if (h_mask.size() > e->mask_full_cap) {
-      cudaFree(e->d_mask_full);
-      e->d_mask_full = nullptr;
-      e->mask_full_cap = 0;
-      CUDA_OK(cudaMalloc(&e->d_mask_full, h_mask.size() * sizeof(unsigned)));
-      e->mask_full_cap = h_mask.size();
-    }
-    CUDA_OK(cudaMemcpyAsync(e->d_mask_full, h_mask.data(), h_mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    if (upload_mt_mask(e, h_cld.data(), ncol, nlay, st)) return -1;
     W.mask = e->d_mask_full;
     W.mstride = ncol;
   }
   for (int c0 = 0; c0 < ncol; c0 += chunk) {
     const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
-    const int gx = (n + kBlock - 1) / kBlock;
-    if (mc && e->irng == 0) { k_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
     if (mc && e->irng == 1) W.moff = c0;
-    k_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
-    if (e->timing) cudaEventRecord(e->ev0, st);
-    if (mc) k_units<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
-    else k_units<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
-    if (e->timing) cudaEventRecord(e->ev1, st);
-    k_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(e->T, W, e->UL, out, nlay, ncol, c0, n);
-    k_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
-    e->launches += 4;
-    if (e->timing) {
-      CUDA_OK(cudaEventSynchronize(e->ev1));
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, e->ev0, e->ev1);
-      e->unit_ms += ms;
-    }
+    if (launch_chunk(e, in, out, W, c0, n, ncol, mc, st)) return -1;
   }
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -295,46 +305,84 @@ extern "C" int cb200_lw_check(cb200_lw_engine* e) {
   return code;
 }
 
+// Host-pointer call (what the reference-named wrapper and the Python component use).  Column chunks flow through
+// the three-stream pipeline of cb::HostPipe; arrays the option flags make dead are not transferred at all
+// (cloud inputs when icld = 0, taucld unless inflag = 0 -- see DESIGN.md "host path").
 extern "C" int cb200_lw_run_host(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* hin,
                                  const cb200_lw_outputs* hout) {
+  if (ncol <= 0 || nlay <= 0 || nlay > 203) { e->error = "bad ncol/nlay (1 <= nlay <= 203, parrrtm.f90:31)"; return -3; }
   CUDA_OK(cudaSetDevice(e->device));
-  const size_t n = (size_t)ncol, L = (size_t)nlay;
-  // sizes (doubles) of the 23 inputs in cb200_lw_inputs order, then the 6 outputs
-  const size_t isz[23] = {L * n, (L + 1) * n, L * n, (L + 1) * n, n, L * n, L * n, L * n, L * n, L * n, L * n, L * n,
-                          L * n, L * n, L * n, 16 * n, L * n, 16 * L * n, L * n, L * n, L * n, L * n, 16 * L * n};
-  const size_t osz[6] = {(L + 1) * n, (L + 1) * n, L * n, (L + 1) * n, (L + 1) * n, L * n};
-  size_t tot = 0;
-  for (size_t s : isz) tot += s;
-  size_t otot = 0;
-  for (size_t s : osz) otot += s;
-  if (tot + otot > e->stage_cap) {
-    cudaFree(e->d_stage);
-    e->d_stage = nullptr;
-    e->stage_cap = 0;
-    CUDA_OK(cudaMalloc(&e->d_stage, (tot + otot) * sizeof(double)));
-    e->stage_cap = tot + otot;
-  }
+  cb::HostPipe& P = e->pipe;
+  CUDA_OK(P.init());
+  const int L = nlay;
+  // rows (of ncol doubles) of the 23 inputs in cb200_lw_inputs order, then of the 6 outputs
+  const int irows[23] = {L, L + 1, L, L + 1, 1, L, L, L, L, L, L, L, L, L, L, 16, L, L, L, L, L, L, 16 * L};
+  int inner[23];
+  for (int i = 0; i < 23; ++i) inner[i] = 1;
+  inner[17] = 16;  // taucld(nbndlw, ncol, nlay): band-fastest
+  const int orows[6] = {L + 1, L + 1, L, L + 1, L + 1, L};
+  bool used[23];
+  for (int i = 0; i < 23; ++i) used[i] = true;
+  const bool clouds = e->fl.icld >= 1;
+  const bool mc = e->fl.mcica && clouds;
+  // 16 cldfr, 17 taucld, 18 cicewp, 19 cliqwp, 20 reice, 21 reliq
+  if (!clouds) for (int i = 16; i <= 21; ++i) used[i] = false;
+  if (e->fl.inflag != 0) used[17] = false;
+  size_t irow_tot = 0, orow_tot = 0;
+  for (int i = 0; i < 23; ++i) if (used[i]) irow_tot += (size_t)irows[i] * inner[i];
+  for (int i = 0; i < 6; ++i) orow_tot += (size_t)orows[i];
+  int chunk = ncol < P.chunk ? ncol : P.chunk;
+  const int wchunk = (chunk + kBlock - 1) / kBlock * kBlock;
+  if (e->ensure_work(wchunk, nlay)) return -1;
+  CUDA_OK(P.ensure(irow_tot * (size_t)chunk, orow_tot * (size_t)chunk));
   const double* const* hp = reinterpret_cast<const double* const*>(hin);
-  cb200_lw_inputs din;
-  const double** dp = reinterpret_cast<const double**>(&din);
-  size_t off = 0;
-  for (int i = 0; i < 23; ++i) {
-    CUDA_OK(cudaMemcpyAsync(e->d_stage + off, hp[i], isz[i] * sizeof(double), cudaMemcpyHostToDevice, 0));
-    dp[i] = e->d_stage + off;
-    off += isz[i];
-  }
-  cb200_lw_outputs dout;
-  double** dop = reinterpret_cast<double**>(&dout);
-  for (int i = 0; i < 6; ++i) {
-    dop[i] = e->d_stage + off;
-    off += osz[i];
-  }
-  int rc = cb200_lw_run_device(e, ncol, nlay, &din, &dout, 0);
-  if (rc) return rc;
   double* const* hop = reinterpret_cast<double* const*>(hout);
-  for (int i = 0; i < 6; ++i)
-    CUDA_OK(cudaMemcpyAsync(hop[i], dop[i], osz[i] * sizeof(double), cudaMemcpyDeviceToHost, 0));
-  CUDA_OK(cudaStreamSynchronize(0));
+  Work W = e->W;
+  W.ncc = wchunk;
+  W.mstride = wchunk;
+  W.moff = 0;
+  e->launches = 0;
+  e->unit_ms = 0.0;
+  if (mc && e->irng == 1) {
+    if (upload_mt_mask(e, hin->cldfr, ncol, nlay, P.s_cmp)) return -1;
+    W.mask = e->d_mask_full;
+    W.mstride = ncol;
+  }
+  int k = 0;
+  for (int c0 = 0; c0 < ncol; c0 += chunk, ++k) {
+    const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
+    const int s = k & 1;
+    // H2D: the slot is free once the chunk that last used it has been computed
+    CUDA_OK(cudaStreamWaitEvent(P.s_in, P.cmp_done[s], 0));
+    cb200_lw_inputs din;
+    const double** dp = reinterpret_cast<const double**>(&din);
+    size_t off = 0;
+    for (int i = 0; i < 23; ++i) {
+      if (!used[i]) { dp[i] = nullptr; continue; }
+      CUDA_OK(P.gather(P.d_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
+      dp[i] = P.d_in[s] + off;
+      off += (size_t)irows[i] * inner[i] * n;
+    }
+    CUDA_OK(cudaEventRecord(P.in_done[s], P.s_in));
+    cb200_lw_outputs dout;
+    double** dop = reinterpret_cast<double**>(&dout);
+    off = 0;
+    for (int i = 0; i < 6; ++i) { dop[i] = P.d_out[s] + off; off += (size_t)orows[i] * n; }
+    // compute: inputs landed, and the output slot has been drained
+    CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.in_done[s], 0));
+    CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.out_done[s], 0));
+    const In in = make_in(n, nlay, &din);
+    Out out{dout.uflx, dout.dflx, dout.hr, dout.uflxc, dout.dflxc, dout.hrc};
+    if (mc && e->irng == 1) W.moff = c0;
+    if (launch_chunk(e, in, out, W, 0, n, n, mc, P.s_cmp)) return -1;
+    CUDA_OK(cudaEventRecord(P.cmp_done[s], P.s_cmp));
+    // D2H
+    CUDA_OK(cudaStreamWaitEvent(P.s_out, P.cmp_done[s], 0));
+    for (int i = 0; i < 6; ++i) CUDA_OK(P.scatter(hop[i], dop[i], orows[i], ncol, c0, n));
+    CUDA_OK(cudaEventRecord(P.out_done[s], P.s_out));
+  }
+  CUDA_OK(cudaStreamSynchronize(P.s_out));
+  CUDA_OK(cudaGetLastError());
   return cb200_lw_check(e);
 }
 

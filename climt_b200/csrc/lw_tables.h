@@ -156,6 +156,9 @@ inline void build_tables(const std::string& blob_path, const Constants& k, std::
     T.tau_tbl = put(tau.data(), tau.size());
     T.exp_tbl = put(ex.data(), ex.size());
     T.tfn_tbl = put(tfn.data(), tfn.size());
+    std::vector<double> et(2 * (NTBL + 1));
+    for (int i = 0; i <= NTBL; ++i) { et[2 * i] = ex[i]; et[2 * i + 1] = tfn[i]; }
+    T.et_tbl = put(et.data(), et.size());
   }
   // rrtmg_lw_rad.nomcica.f90:419-421, rrtmg_lw_init.f90:279
   T.oneminus = 1. - 1.e-6;

@@ -113,7 +113,7 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
     pz_below = pz;
     for (int i = 0; i < 7; ++i) wkl[i] = coldry * wkl[i];
     const double plog = log(pavel);
-    int jp = (int)(36. - 5 * (plog + 0.04));
+    int jp = (int)(CB_MULADD_2R(-5., (plog + 0.04), 36.));
     if (jp < 1) jp = 1; else if (jp > 58) jp = 58;
     const double fp = 5. * (tb[T.preflog + jp - 1] - plog);
     const double tr0 = tb[T.tref + jp - 1], tr1 = tb[T.tref + jp];
@@ -166,10 +166,13 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
       const double cldfrac = in.cldfr[o];
       if (!fl.mcica && cldfrac > 1.e-06 && cldfrac < T.oneminus) *W.err = 10;  // 'PARTIAL CLOUD NOT ALLOWED' (rad.nomcica.f90:616-620)
       const double ciwp = in.cicewp[o], clwp = in.cliqwp[o];
-      const double* tc = in.taucld + 14 * ((size_t)l * ncol + gc);
-      const double* sc = in.ssacld + 14 * ((size_t)l * ncol + gc);
-      const double* ac = in.asmcld + 14 * ((size_t)l * ncol + gc);
-      const double* fc = in.fsfcld + 14 * ((size_t)l * ncol + gc);
+      // direct-input cloud optics; a null taucld means "all four arrays are zero" (host path with inflag != 0)
+      const double zero14[14] = {0., 0., 0., 0., 0., 0., 0., 0., 0., 0., 0., 0., 0., 0.};
+      const bool direct = in.taucld != nullptr;
+      const double* tc = direct ? in.taucld + 14 * ((size_t)l * ncol + gc) : zero14;
+      const double* sc = direct ? in.ssacld + 14 * ((size_t)l * ncol + gc) : zero14;
+      const double* ac = direct ? in.asmcld + 14 * ((size_t)l * ncol + gc) : zero14;
+      const double* fc = direct ? in.fsfcld + 14 * ((size_t)l * ncol + gc) : zero14;
       double tauctot = 0.;
       for (int ib = 0; ib < 14; ++ib) tauctot = tauctot + tc[ib];
       double taucloud[14], ssacloud[14], asmcloud[14];
@@ -433,17 +436,14 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     if (R.self) {
       const double selffac = WSF(F_SELFFAC), selffrac = WSF(F_SELFFRAC);
       const double* __restrict__ s = tb + O.selfref + (size_t)(inds - 1) * ng + g0;
+      const Row<U> s0 = ldrow<U>(s), s1 = ldrow<U>(s + ng), f0 = ldrow<U>(f), f1 = ldrow<U>(f + ng);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const double s0 = CB_LDG(s + u), s1 = CB_LDG(s + ng + u), f0 = CB_LDG(f + u), f1 = CB_LDG(f + ng + u);
-        cont[u] = selffac * (s0 + selffrac * (s1 - s0)) + forfac * (f0 + forfrac * (f1 - f0));
-      }
+      for (int u = 0; u < U; ++u)
+        cont[u] = selffac * (s0[u] + selffrac * (s1[u] - s0[u])) + forfac * (f0[u] + forfrac * (f1[u] - f0[u]));
     } else {
+      const Row<U> f0 = ldrow<U>(f), f1 = ldrow<U>(f + ng);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const double f0 = CB_LDG(f + u), f1 = CB_LDG(f + ng + u);
-        cont[u] = forfac * (f0 + forfrac * (f1 - f0));
-      }
+      for (int u = 0; u < U; ++u) cont[u] = forfac * (f0[u] + forfrac * (f1[u] - f0[u]));
     }
   }
   if (R.kind == 2) {
@@ -463,16 +463,18 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     const int row1 = (LOWER ? (jp * 5 + (jt1 - 1)) * nsp : ((jp - 12) * 5 + (jt1 - 1)) * nsp) + js - 1;
     const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
     const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
+    const Row<U> k000 = ldrow<U>(a0), k100 = ldrow<U>(a0 + ng), k010 = ldrow<U>(a0 + nsp * ng), k110 = ldrow<U>(a0 + (nsp + 1) * ng);
+    const Row<U> k001 = ldrow<U>(a1), k101 = ldrow<U>(a1 + ng), k011 = ldrow<U>(a1 + nsp * ng), k111 = ldrow<U>(a1 + (nsp + 1) * ng);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      double d = f000 * CB_LDG(a0 + u);
-      d = d + f100 * CB_LDG(a0 + ng + u);
-      d = d + f010 * CB_LDG(a0 + nsp * ng + u);
-      d = d + f110 * CB_LDG(a0 + (nsp + 1) * ng + u);
-      d = d + f001 * CB_LDG(a1 + u);
-      d = d + f101 * CB_LDG(a1 + ng + u);
-      d = d + f011 * CB_LDG(a1 + nsp * ng + u);
-      d = d + f111 * CB_LDG(a1 + (nsp + 1) * ng + u);
+      double d = f000 * k000[u];
+      d = d + f100 * k100[u];
+      d = d + f010 * k010[u];
+      d = d + f110 * k110[u];
+      d = d + f001 * k001[u];
+      d = d + f101 * k101[u];
+      d = d + f011 * k011[u];
+      d = d + f111 * k111[u];
       acc[u] = speccomb * d;
       if (R.self || R.forn) acc[u] = acc[u] + colh2o * cont[u];
     }
@@ -484,9 +486,10 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     const double cola = WSF(F_COLH2O + R.a);
     const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
     const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
+    const Row<U> k00 = ldrow<U>(a0), k10 = ldrow<U>(a0 + ng), k01 = ldrow<U>(a1), k11 = ldrow<U>(a1 + ng);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const double k4 = fac00 * CB_LDG(a0 + u) + fac10 * CB_LDG(a0 + ng + u) + fac01 * CB_LDG(a1 + u) + fac11 * CB_LDG(a1 + ng + u);
+      const double k4 = fac00 * k00[u] + fac10 * k10[u] + fac01 * k01[u] + fac11 * k11[u];
       if (R.inside) {
         // e.g. taumol20 :830-842 / taumol23 :1179-1189 / taumol29 :1735-1746 ; upper 20: :857-866
         if (R.keyscale != 1.) acc[u] = cola * (R.keyscale * k4 + cont[u]);
@@ -501,14 +504,9 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     const int gas = R.extra == X_CH4 ? CH4 : (R.extra == X_O3 ? O3 : (R.extra == X_CO2 ? CO2 : H2O));
     const double colx = WSF(F_COLH2O + gas);
     const double* __restrict__ x = tb + (R.xslot == 0 ? O.x0 : O.x1) + g0;
-    if (B == 24 && LOWER) {
-      // taumol24 :1262-1276: speccomb*(major) + colo3*abso3a + colh2o*(self+for): order differs only in association
+    const Row<U> xr = ldrow<U>(x);
 #pragma unroll
-      for (int u = 0; u < U; ++u) acc[u] = acc[u] + colx * CB_LDG(x + u);
-    } else {
-#pragma unroll
-      for (int u = 0; u < U; ++u) acc[u] = acc[u] + colx * CB_LDG(x + u);
-    }
+    for (int u = 0; u < U; ++u) acc[u] = acc[u] + colx * xr[u];
   } else if (R.extra == X_O2CONT) {
     const double o2cont = 4.35e-4 * WSF(F_COLO2) / (350.0 * 2.0);
 #pragma unroll
@@ -529,11 +527,9 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     for (int u = 0; u < U; ++u) taur[u] = colmol * CB_LDG(tb + O.raylb + g0 + u);
   } else {
     const double* __restrict__ r = tb + O.raylv + (size_t)(js - 1) * ng + g0;
+    const Row<U> r0 = ldrow<U>(r), r1 = ldrow<U>(r + ng);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const double r0 = CB_LDG(r + u), r1 = CB_LDG(r + ng + u);
-      taur[u] = colmol * (r0 + fs * (r1 - r0));
-    }
+    for (int u = 0; u < U; ++u) taur[u] = colmol * (r0[u] + fs * (r1[u] - r0[u]));
   }
   // solar source function at this layer (only evaluated at layer laysolfr)
   if (want_src) {
@@ -565,7 +561,7 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
 CB_HD double exp_neg(const double* __restrict__ exp_tbl, double bpade, double ze1) {
   if (ze1 <= 0.06) return 1. - ze1 + 0.5 * ze1 * ze1;
   const double tblind = ze1 / (bpade + ze1);
-  const int itind = f2i(10000.0 * tblind + 0.5);
+  const int itind = f2i(CB_MULADD_2R(10000.0, tblind, 0.5));
   return CB_LDG(exp_tbl + itind);
 }
 
@@ -812,7 +808,10 @@ CB_HD void sw_unit(const Tables& T, const Solar& sol, const In& in, const Flags&
 struct Unit {
   int band, g0, u;  // band = 16..29
 };
-constexpr int kMaxUnits = 40;
+#ifndef CB_SW_UMAX
+#define CB_SW_UMAX 4  // g-points per thread (2 or 4)
+#endif
+constexpr int kMaxUnits = 64;
 inline int build_units(Unit* out) {  // host only
   int n = 0;
   for (int pass = 0; pass < 2; ++pass)
@@ -820,10 +819,10 @@ inline int build_units(Unit* out) {  // host only
       const bool heavy = kNSPA[b - 16] == 9;
       if ((pass == 0) != heavy) continue;
       const int ng = kNG[b - 16];
-      for (int g0 = 0; g0 < ng; g0 += 4) {
+      for (int g0 = 0; g0 < ng; g0 += CB_SW_UMAX) {
         out[n].band = b;
         out[n].g0 = g0;
-        out[n].u = (ng - g0) >= 4 ? 4 : (ng - g0);
+        out[n].u = (ng - g0) >= CB_SW_UMAX ? CB_SW_UMAX : (ng - g0);
         ++n;
       }
     }

@@ -17,7 +17,7 @@ using namespace cb::sw;
 namespace {
 using cb::kBlock;
 #ifndef CB_UNITS_MIN_BLOCKS
-#define CB_UNITS_MIN_BLOCKS 1
+#define CB_UNITS_MIN_BLOCKS 3
 #endif
 
 struct UnitList {
@@ -96,8 +96,7 @@ struct cb200_sw_engine {
   int cap_ncc = 0, cap_nlay = 0;
   Work W{};
   int max_chunk = 8192;
-  double* d_stage = nullptr;
-  size_t stage_cap = 0;
+  cb::HostPipe pipe;
   int* h_err = nullptr;
   std::string error;
   int launches = 0;
@@ -169,7 +168,7 @@ extern "C" void cb200_sw_destroy(cb200_sw_engine* e) {
   cudaSetDevice(e->device);
   e->free_work();
   cudaFree(e->d_tables);
-  cudaFree(e->d_stage);
+  e->pipe.destroy();
   cudaFree(e->d_mask_full);
   if (e->h_err) cudaFreeHost(e->h_err);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -212,6 +211,45 @@ static In make_in(int ncol, int nlay, const cb200_sw_inputs* p) {
 }
 static_assert(sizeof(cb200_sw_inputs) == 29 * sizeof(double*), "cb200_sw_inputs layout");
 
+// One chunk of columns [c0, c0+n) of `in` through the kernels on stream `st` (the engine's single workspace).
+static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, const Out& out, Work& W, int c0, int n,
+                        int out_ncol, bool mc, cudaStream_t st) {
+  const int nlay = in.nlay;
+  const int gx = (n + kBlock - 1) / kBlock;
+  if (mc && e->irng == 0) { k_sw_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
+  k_sw_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
+  if (e->timing) cudaEventRecord(e->ev0, st);
+  if (mc) k_sw_units<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+  else k_sw_units<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+  if (e->timing) cudaEventRecord(e->ev1, st);
+  k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, e->UL, out, nlay, out_ncol, c0, n);
+  k_sw_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
+  e->launches += 4;
+  if (e->timing) {
+    CUDA_OK(cudaEventSynchronize(e->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->unit_ms += ms;
+  }
+  return 0;
+}
+
+// Mersenne-twister McICA mask: serial stream, generated on the host for bit parity, uploaded once [lay][word][ncol]
+static int upload_mt_mask(cb200_sw_engine* e, const double* h_cldfr, int ncol, int nlay, cudaStream_t st) {
+  std::vector<unsigned> h_mask;
+  cb::mcica::mask_mt_host(h_cldfr, ncol, nlay, 112, 4, e->fl.icld, e->permuteseed, h_mask);
+  if (h_mask.size() > e->mask_full_cap) {
+    cudaFree(e->d_mask_full);
+    e->d_mask_full = nullptr;
+    e->mask_full_cap = 0;
+    CUDA_OK(cudaMalloc(&e->d_mask_full, h_mask.size() * sizeof(unsigned)));
+    e->mask_full_cap = h_mask.size();
+  }
+  CUDA_OK(cudaMemcpyAsync(e->d_mask_full, h_mask.data(), h_mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 extern "C" int cb200_sw_run_device(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
                                    const cb200_sw_inputs* pin, const cb200_sw_outputs* pout, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
@@ -230,43 +268,18 @@ extern "C" int cb200_sw_run_device(cb200_sw_engine* e, int ncol, int nlay, doubl
   const bool mc = e->fl.mcica && e->fl.icld >= 1;
   W.mstride = chunk;
   W.moff = 0;
-  if (mc && e->irng == 1) {  // Mersenne twister: serial stream, generated on the host for bit parity
+  if (mc && e->irng == 1) {
     std::vector<double> h_cld((size_t)nlay * ncol);
     CUDA_OK(cudaMemcpyAsync(h_cld.data(), in.cldfr, h_cld.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    std::vector<unsigned> h_mask;
-    cb::mcica::mask_mt_host(h_cld.data(), ncol, nlay, 112, 4, e->fl.icld, e->permuteseed, h_mask);
-    if (h_mask.size() > e->mask_full_cap) {
-      cudaFree(e->d_mask_full);
-      e->d_mask_full = nullptr;
-      e->mask_full_cap = 0;
-      CUDA_OK(cudaMalloc(&e->d_mask_full, h_mask.size() * sizeof(unsigned)));
-      e->mask_full_cap = h_mask.size();
-    }
-    CUDA_OK(cudaMemcpyAsync(e->d_mask_full, h_mask.data(), h_mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    if (upload_mt_mask(e, h_cld.data(), ncol, nlay, st)) return -1;
     W.mask = e->d_mask_full;
     W.mstride = ncol;
   }
   for (int c0 = 0; c0 < ncol; c0 += chunk) {
     const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
-    const int gx = (n + kBlock - 1) / kBlock;
-    if (mc && e->irng == 0) { k_sw_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
     if (mc && e->irng == 1) W.moff = c0;
-    k_sw_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
-    if (e->timing) cudaEventRecord(e->ev0, st);
-    if (mc) k_sw_units<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
-    else k_sw_units<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
-    if (e->timing) cudaEventRecord(e->ev1, st);
-    k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, e->UL, out, nlay, ncol, c0, n);
-    k_sw_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
-    e->launches += 4;
-    if (e->timing) {
-      CUDA_OK(cudaEventSynchronize(e->ev1));
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, e->ev0, e->ev1);
-      e->unit_ms += ms;
-    }
+    if (launch_chunk(e, sol, in, out, W, c0, n, ncol, mc, st)) return -1;
   }
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -296,45 +309,83 @@ extern "C" int cb200_sw_check(cb200_sw_engine* e) {
   return code;
 }
 
+// Host-pointer call: column chunks through the three-stream pipeline of cb::HostPipe.  Arrays the option flags make
+// dead are not transferred (cloud inputs when icld = 0; direct cloud optics unless inflag = 0; aerosol arrays by iaer).
 extern "C" int cb200_sw_run_host(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
                                  const cb200_sw_inputs* hin, const cb200_sw_outputs* hout) {
+  if (ncol <= 0 || nlay <= 0 || nlay > 203) { e->error = "bad ncol/nlay (1 <= nlay <= 203, parrrsw.f90:27)"; return -3; }
   CUDA_OK(cudaSetDevice(e->device));
-  const size_t n = (size_t)ncol, L = (size_t)nlay;
-  const size_t isz[29] = {L * n, (L + 1) * n, L * n, (L + 1) * n, n, L * n, L * n, L * n, L * n, L * n, L * n,
-                          n, n, n, n, n, L * n, 14 * L * n, 14 * L * n, 14 * L * n, 14 * L * n, L * n, L * n, L * n, L * n,
-                          14 * L * n, 14 * L * n, 14 * L * n, 6 * L * n};
-  const size_t osz[6] = {(L + 1) * n, (L + 1) * n, L * n, (L + 1) * n, (L + 1) * n, L * n};
-  size_t tot = 0, otot = 0;
-  for (size_t s : isz) tot += s;
-  for (size_t s : osz) otot += s;
-  if (tot + otot > e->stage_cap) {
-    cudaFree(e->d_stage);
-    e->d_stage = nullptr;
-    e->stage_cap = 0;
-    CUDA_OK(cudaMalloc(&e->d_stage, (tot + otot) * sizeof(double)));
-    e->stage_cap = tot + otot;
-  }
+  cb::HostPipe& P = e->pipe;
+  CUDA_OK(P.init());
+  const int L = nlay;
+  const int irows[29] = {L, L + 1, L, L + 1, 1, L, L, L, L, L, L, 1, 1, 1, 1, 1, L, L, L, L, L,
+                         L, L, L, L, 14 * L, 14 * L, 14 * L, 6 * L};
+  int inner[29];
+  for (int i = 0; i < 29; ++i) inner[i] = 1;
+  for (int i = 17; i <= 20; ++i) inner[i] = 14;  // taucld/ssacld/asmcld/fsfcld(nbndsw, ncol, nlay): band-fastest
+  const int orows[6] = {L + 1, L + 1, L, L + 1, L + 1, L};
+  bool used[29];
+  for (int i = 0; i < 29; ++i) used[i] = true;
+  const bool clouds = e->fl.icld >= 1;
+  const bool mc = e->fl.mcica && clouds;
+  // 16 cldfr | 17-20 taucld ssacld asmcld fsfcld | 21-24 cicewp cliqwp reice reliq | 25-27 tau/ssa/asm aer | 28 ecaer
+  if (!clouds) for (int i = 16; i <= 24; ++i) used[i] = false;
+  if (e->fl.inflag != 0) for (int i = 17; i <= 20; ++i) used[i] = false;
+  if (e->fl.iaer != 10) for (int i = 25; i <= 27; ++i) used[i] = false;
+  if (e->fl.iaer != 6) used[28] = false;
+  size_t irow_tot = 0, orow_tot = 0;
+  for (int i = 0; i < 29; ++i) if (used[i]) irow_tot += (size_t)irows[i] * inner[i];
+  for (int i = 0; i < 6; ++i) orow_tot += (size_t)orows[i];
+  int chunk = ncol < P.chunk ? ncol : P.chunk;
+  const int wchunk = (chunk + kBlock - 1) / kBlock * kBlock;
+  if (e->ensure_work(wchunk, nlay)) return -1;
+  CUDA_OK(P.ensure(irow_tot * (size_t)chunk, orow_tot * (size_t)chunk));
   const double* const* hp = reinterpret_cast<const double* const*>(hin);
-  cb200_sw_inputs din;
-  const double** dp = reinterpret_cast<const double**>(&din);
-  size_t off = 0;
-  for (int i = 0; i < 29; ++i) {
-    CUDA_OK(cudaMemcpyAsync(e->d_stage + off, hp[i], isz[i] * sizeof(double), cudaMemcpyHostToDevice, 0));
-    dp[i] = e->d_stage + off;
-    off += isz[i];
-  }
-  cb200_sw_outputs dout;
-  double** dop = reinterpret_cast<double**>(&dout);
-  for (int i = 0; i < 6; ++i) {
-    dop[i] = e->d_stage + off;
-    off += osz[i];
-  }
-  int rc = cb200_sw_run_device(e, ncol, nlay, adjes, dyofyr, solcycfrac, &din, &dout, 0);
-  if (rc) return rc;
   double* const* hop = reinterpret_cast<double* const*>(hout);
-  for (int i = 0; i < 6; ++i)
-    CUDA_OK(cudaMemcpyAsync(hop[i], dop[i], osz[i] * sizeof(double), cudaMemcpyDeviceToHost, 0));
-  CUDA_OK(cudaStreamSynchronize(0));
+  const Solar sol = compute_solar(e->solar, adjes, dyofyr, solcycfrac);
+  Work W = e->W;
+  W.ncc = wchunk;
+  W.mstride = wchunk;
+  W.moff = 0;
+  e->launches = 0;
+  e->unit_ms = 0.0;
+  if (mc && e->irng == 1) {
+    if (upload_mt_mask(e, hin->cldfr, ncol, nlay, P.s_cmp)) return -1;
+    W.mask = e->d_mask_full;
+    W.mstride = ncol;
+  }
+  int k = 0;
+  for (int c0 = 0; c0 < ncol; c0 += chunk, ++k) {
+    const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
+    const int s = k & 1;
+    CUDA_OK(cudaStreamWaitEvent(P.s_in, P.cmp_done[s], 0));
+    cb200_sw_inputs din;
+    const double** dp = reinterpret_cast<const double**>(&din);
+    size_t off = 0;
+    for (int i = 0; i < 29; ++i) {
+      if (!used[i]) { dp[i] = nullptr; continue; }
+      CUDA_OK(P.gather(P.d_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
+      dp[i] = P.d_in[s] + off;
+      off += (size_t)irows[i] * inner[i] * n;
+    }
+    CUDA_OK(cudaEventRecord(P.in_done[s], P.s_in));
+    cb200_sw_outputs dout;
+    double** dop = reinterpret_cast<double**>(&dout);
+    off = 0;
+    for (int i = 0; i < 6; ++i) { dop[i] = P.d_out[s] + off; off += (size_t)orows[i] * n; }
+    CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.in_done[s], 0));
+    CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.out_done[s], 0));
+    const In in = make_in(n, nlay, &din);
+    Out out{dout.uflx, dout.dflx, dout.hr, dout.uflxc, dout.dflxc, dout.hrc};
+    if (mc && e->irng == 1) W.moff = c0;
+    if (launch_chunk(e, sol, in, out, W, 0, n, n, mc, P.s_cmp)) return -1;
+    CUDA_OK(cudaEventRecord(P.cmp_done[s], P.s_cmp));
+    CUDA_OK(cudaStreamWaitEvent(P.s_out, P.cmp_done[s], 0));
+    for (int i = 0; i < 6; ++i) CUDA_OK(P.scatter(hop[i], dop[i], orows[i], ncol, c0, n));
+    CUDA_OK(cudaEventRecord(P.out_done[s], P.s_out));
+  }
+  CUDA_OK(cudaStreamSynchronize(P.s_out));
+  CUDA_OK(cudaGetLastError());
   return cb200_sw_check(e);
 }
 
