@@ -11,9 +11,9 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("CLIMT_B200_SO") or os.path.join(_HERE, "libclimt_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lw_engine.cu", "sw_engine.cu", "gray_engine.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lw_engine.cu", "sw_engine.cu", "gray_engine.cu", "cork_engine.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("cb_common.h", "engine_common.h", "lw_core.cuh", "lw_tables.h", "sw_core.cuh", "sw_tables.h",
-                                                          "mcica_core.cuh", "mcica_host.h")] + [
+                                                          "mcica_core.cuh", "mcica_host.h", "cork_core.cuh", "cork_tables.h")] + [
     os.path.join(_HERE, "..", "include", "climt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "--fmad=true"]
@@ -73,7 +73,10 @@ class SwInputs(ctypes.Structure):
         "cicewp", "cliqwp", "reice", "reliq", "tauaer", "ssaaer", "asmaer", "ecaer")]
 
 
-EXPORTS = ["cb200_gray_lw_run_device", "cb200_gray_lw_run_host", "cb200_sw_create", "cb200_sw_destroy", "cb200_sw_set_options", "cb200_sw_set_mcica", "cb200_sw_set_solar", "cb200_sw_run_device",
+EXPORTS = ["cb200_cork_create", "cb200_cork_destroy", "cb200_cork_last_error", "cb200_cork_last_launches", "cb200_cork_enable_timing",
+           "cb200_cork_last_unit_kernel_ms", "cb200_cork_lw_run_device", "cb200_cork_sw_run_device", "cb200_cork_lw_run_host",
+           "cb200_cork_sw_run_host",
+           "cb200_gray_lw_run_device", "cb200_gray_lw_run_host", "cb200_sw_create", "cb200_sw_destroy", "cb200_sw_set_options", "cb200_sw_set_mcica", "cb200_sw_set_solar", "cb200_sw_run_device",
            "cb200_sw_run_host", "cb200_sw_check", "cb200_sw_last_error", "cb200_sw_last_launches",
            "cb200_sw_enable_timing", "cb200_sw_last_unit_kernel_ms", "rrtmg_sw_set_constants", "rrtmg_sw_ini_wrapper",
            "rrtmg_sw_nomcica_wrapper",

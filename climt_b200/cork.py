@@ -1,0 +1,534 @@
+"""CORK correlated-k radiation -- drop-ins for climt.CorkLongwaveRadiation / climt.CorkShortwaveRadiation.
+
+Mirrors climt/_components/cork/lw/component.py:20-373 and cork/sw/component.py:20-496 for ``optics="correlated_k"``
+(additive overlap): same constructor arguments, property dictionaries, aliases, units and ``array_call`` return
+values.  The optical-depth interpolation, Planck sources, transport sweeps, flux sums and heating rates run in the
+CUDA engine (csrc/cork_engine.cu) behind the C ABI of include/climt_b200.h; there is no CPU implementation here.
+
+Not provided (raise NotImplementedError at construction): ``optics="parmentier"`` (picket-fence analytic optics,
+cork/optics/parmentier.py -- scalar Python in the reference, outside BASELINE.json's configs), ESFT-overlap tables,
+and ``diagnostics_level >= 1`` (per-g-point diagnostic dumps).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _native
+from .constants import get_constant
+from .sympl_shim import TendencyComponent
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_fp = ctypes.POINTER(ctypes.c_float)
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "cork")
+DIFFUSIVITY_FACTOR = 1.66  # cork/lw/kernels.py:6
+CO2_INTERP_LOGK = True     # cork/optics/correlated_k.py:27
+
+_NETCDF_VARS = ("k_coefficients", "gpoint_weights", "temperature_grid", "pressure_grid_log", "h2o_vmr_grid", "co2_vmr_grid",
+                "band_wavenumber_limits", "planck_fraction", "solar_source_per_gpoint", "rayleigh_coefficient", "continuum_kappa")
+
+
+def _decode(x):
+    if isinstance(x, bytes):
+        return x.decode("utf-8")
+    if isinstance(x, np.ndarray) and x.dtype.kind == "S":
+        return x.tobytes().decode("utf-8").rstrip("\x00")
+    return str(x)
+
+
+def _load_netcdf_table(path):
+    from scipy.io import netcdf_file
+    out = {}
+    with netcdf_file(path, "r", mmap=False) as nc:
+        for name in _NETCDF_VARS:
+            if name in nc.variables:
+                arr = np.asarray(nc.variables[name][:]).copy()
+                if arr.dtype.byteorder not in ("=", "|"):
+                    arr = arr.astype(arr.dtype.newbyteorder("="))
+                out[name] = arr
+        if "gas_names" in nc.variables:
+            out["gas_names"] = np.asarray([_decode(x) for x in np.atleast_1d(nc.variables["gas_names"][:])])
+        elif getattr(nc, "gas_names", None) is not None:
+            out["gas_names"] = np.asarray([s.strip() for s in _decode(nc.gas_names).split(",") if s.strip()])
+        for attr in ("overlap_method", "resolution", "background_is_premixed"):
+            val = getattr(nc, attr, None)
+            if val is not None:
+                out[attr] = np.asarray(_decode(val))
+    return out
+
+
+def load_k_table(name_or_path):
+    """Same contract as the reference's load_k_table (cork/optics/correlated_k.py:186-218): a path to a ``.npz`` /
+    ``.nc`` file, or the name of a table shipped under ``climt_b200/data/cork/``; returns a dict of arrays."""
+    path = name_or_path
+    if not os.path.isfile(path):
+        for ext in (".npz", ".nc"):
+            cand = os.path.join(_DATA, f"{name_or_path}{ext}")
+            if os.path.isfile(cand):
+                path = cand
+                break
+        else:
+            raise FileNotFoundError(f"No k-table named {name_or_path!r} (.npz or .nc)")
+    if path.endswith(".nc"):
+        return _load_netcdf_table(path)
+    with np.load(path, allow_pickle=True) as z:
+        return {k: z[k] for k in z.files}
+
+
+class CorkTable(ctypes.Structure):
+    """cb200_cork_table (include/climt_b200.h)."""
+    _fields_ = [(n, ctypes.c_int) for n in ("ngas", "nband", "ngpt", "nT", "nP", "nX", "nC")] + [
+        ("k_coefficients_f32", _fp), ("k_coefficients_f64", _dp), ("temperature_grid", _dp), ("pressure_grid_log", _dp),
+        ("h2o_vmr_grid", _dp), ("co2_vmr_grid", _dp), ("gpoint_weights", _dp), ("planck_fraction", _dp),
+        ("nband_pf", ctypes.c_int), ("ngpt_pf", ctypes.c_int), ("continuum_kappa", _dp), ("solar_source_per_gpoint", _dp),
+        ("rayleigh_coefficient", _dp), ("co2_logk", ctypes.c_int), ("premixed", ctypes.c_int)]
+
+
+CORK_IN = ("T", "p", "p_int", "T_surf", "q_h2o", "co2_vmr", "gas_q", "emissivity", "tau_cloud", "zenith", "albedo", "ssa_cloud", "g_cloud")
+CORK_OUT = ("up_broad", "down_broad", "heating_rate", "up_band", "down_band", "tau_band", "trans_band", "hr_band")
+
+
+class CorkInputs(ctypes.Structure):
+    _fields_ = [(n, _dp) for n in CORK_IN]
+
+
+class CorkOutputs(ctypes.Structure):
+    _fields_ = [(n, _dp) for n in CORK_OUT]
+
+
+def table_flags(table):
+    """The table-classification logic of the reference constructors (cork/lw/component.py:46-59)."""
+    gas_names = [str(g) for g in table["gas_names"]] if "gas_names" in table else ["effective"]
+    has_h2o = "h2o_vmr_grid" in table
+    has_co2 = "co2_vmr_grid" in table
+    fully_premixed = gas_names == ["effective"] and not has_h2o
+    premixed_bg = (gas_names == ["effective"] and has_h2o) or str(table.get("background_is_premixed", np.array(""))).lower() == "true"
+    return gas_names, has_h2o, has_co2, fully_premixed, premixed_bg
+
+
+def _bind(L):
+    vp = ctypes.c_void_p
+    L.cb200_cork_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(CorkTable), ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                    ctypes.c_int]
+    L.cb200_cork_destroy.argtypes = [vp]
+    L.cb200_cork_destroy.restype = None
+    L.cb200_cork_last_error.argtypes = [vp]
+    L.cb200_cork_last_error.restype = ctypes.c_char_p
+    L.cb200_cork_last_launches.argtypes = [vp]
+    L.cb200_cork_enable_timing.argtypes = [vp, ctypes.c_int]
+    L.cb200_cork_last_unit_kernel_ms.argtypes = [vp]
+    L.cb200_cork_last_unit_kernel_ms.restype = ctypes.c_double
+    pi, po = ctypes.POINTER(CorkInputs), ctypes.POINTER(CorkOutputs)
+    L.cb200_cork_lw_run_device.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, pi, po, vp]
+    L.cb200_cork_sw_run_device.argtypes = [vp, ctypes.c_int, ctypes.c_int, _dp, pi, po, vp]
+    L.cb200_cork_lw_run_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, pi, po]
+    L.cb200_cork_sw_run_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, _dp, pi, po]
+
+
+def make_ctable(table, co2_logk=CO2_INTERP_LOGK):
+    """dict of arrays -> (cb200_cork_table, keep-alive list).  float32 k stays float32; grids are promoted to float64 exactly."""
+    overlap = str(table.get("overlap_method", np.array("additive")))
+    if overlap == "esft":
+        raise NotImplementedError("ESFT-overlap k-tables are not supported by the CUDA engine (additive overlap only)")
+    k = np.asarray(table["k_coefficients"])
+    if k.ndim not in (5, 6, 7):
+        raise ValueError(f"k_coefficients must have 5, 6 or 7 dimensions, got {k.ndim}")
+    gas_names, has_h2o, has_co2, fully_premixed, premixed_bg = table_flags(table)
+    keep = []
+
+    def d64(name):
+        if name not in table or table[name] is None:
+            return None
+        a = np.ascontiguousarray(table[name], dtype=np.float64)
+        keep.append(a)
+        return a.ctypes.data_as(_dp)
+
+    t = CorkTable()
+    t.ngas, t.nband, t.ngpt, t.nT, t.nP = k.shape[:5]
+    t.nX = k.shape[5] if k.ndim >= 6 else 0
+    t.nC = k.shape[6] if k.ndim == 7 else 0
+    if k.dtype == np.float32:
+        kk = np.ascontiguousarray(k)
+        t.k_coefficients_f32 = kk.ctypes.data_as(_fp)
+    else:
+        kk = np.ascontiguousarray(k, dtype=np.float64)
+        t.k_coefficients_f64 = kk.ctypes.data_as(_dp)
+    keep.append(kk)
+    t.temperature_grid = d64("temperature_grid")
+    t.pressure_grid_log = d64("pressure_grid_log")
+    t.h2o_vmr_grid = d64("h2o_vmr_grid") if t.nX else None
+    t.co2_vmr_grid = d64("co2_vmr_grid") if t.nC else None
+    t.gpoint_weights = d64("gpoint_weights")
+    if "planck_fraction" in table:
+        pf = np.asarray(table["planck_fraction"])
+        t.planck_fraction = d64("planck_fraction")
+        t.nband_pf, t.ngpt_pf = pf.shape[0], pf.shape[1]
+    cont = table.get("continuum_kappa")
+    if cont is not None and np.asarray(cont).ndim == 4 and t.nX:
+        t.continuum_kappa = d64("continuum_kappa")
+    if "solar_source_per_gpoint" in table:
+        t.solar_source_per_gpoint = d64("solar_source_per_gpoint")
+    if table.get("rayleigh_coefficient") is not None:
+        t.rayleigh_coefficient = d64("rayleigh_coefficient")
+    t.co2_logk = 1 if co2_logk else 0
+    t.premixed = 1 if (fully_premixed or premixed_bg) else 0
+    return t, keep
+
+
+class CorkEngine:
+    """Handle of one cb200_cork_engine (one k-table resident in HBM)."""
+
+    def __init__(self, table, g=None, cpd=None, sigma=None, device=0):
+        self._L = _native.lib()
+        _bind(self._L)
+        self.table = load_k_table(table) if isinstance(table, (str, os.PathLike)) else table
+        self.ctable, self._keep = make_ctable(self.table)
+        g = get_constant("gravitational_acceleration", "m/s^2") if g is None else g
+        cpd = get_constant("heat_capacity_of_dry_air_at_constant_pressure", "J/kg/K") if cpd is None else cpd
+        sigma = get_constant("stefan_boltzmann_constant", "W/m^2/K^4") if sigma is None else sigma
+        self._h = ctypes.c_void_p()
+        if self._L.cb200_cork_create(ctypes.byref(self._h), ctypes.byref(self.ctable), g, cpd, sigma, device):
+            raise RuntimeError(self._L.cb200_global_error().decode())
+        self.nband, self.ngpt, self.ngas = self.ctable.nband, self.ctable.ngpt, self.ctable.ngas
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cb200_cork_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self):
+        return self._L.cb200_cork_last_error(self._h).decode()
+
+    def shapes(self, ncol, nlev):
+        L, n, nb = nlev, ncol, self.nband
+        ins = {"T": (L, n), "p": (L, n), "p_int": (L + 1, n), "T_surf": (n,), "q_h2o": (L, n), "co2_vmr": (L, n),
+               "gas_q": (self.ngas, L, n), "emissivity": (nb, n), "tau_cloud": (L, n, nb), "zenith": (n,), "albedo": (n,),
+               "ssa_cloud": (L, n, nb), "g_cloud": (L, n, nb)}
+        outs = {"up_broad": (L + 1, n), "down_broad": (L + 1, n), "heating_rate": (L, n), "up_band": (nb, L + 1, n),
+                "down_band": (nb, L + 1, n), "tau_band": (nb, L, n), "trans_band": (nb, L, n), "hr_band": (nb, L, n)}
+        return ins, outs
+
+    def _pack_host(self, ncol, nlev, arrays, out, which, bands):
+        ins, outs = self.shapes(ncol, nlev)
+        keep, pin = [], CorkInputs()
+        for k in CORK_IN:
+            a = arrays.get(k)
+            if a is None:
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != ins[k]:
+                raise ValueError(f"{k}: expected shape {ins[k]}, got {a.shape}")
+            keep.append(a)
+            setattr(pin, k, a.ctypes.data_as(_dp))
+        names = ["up_broad", "down_broad", "heating_rate"]
+        if bands:
+            names += ["up_band", "down_band", "tau_band", "hr_band"] + (["trans_band"] if which == "lw" else [])
+        out = out if out is not None else {k: np.empty(outs[k]) for k in names}
+        pout = CorkOutputs()
+        for k, a in out.items():
+            if a.shape != outs[k] or a.dtype != np.float64 or not a.flags.c_contiguous:
+                raise ValueError(f"output {k}: need C-contiguous float64 {outs[k]}")
+            setattr(pout, k, a.ctypes.data_as(_dp))
+        return pin, pout, out, keep
+
+    def lw_host(self, ncol, nlev, arrays, out=None, diffusivity_factor=DIFFUSIVITY_FACTOR, bands=True):
+        pin, pout, out, keep = self._pack_host(ncol, nlev, arrays, out, "lw", bands)
+        rc = self._L.cb200_cork_lw_run_host(self._h, ncol, nlev, float(diffusivity_factor), ctypes.byref(pin), ctypes.byref(pout))
+        if rc:
+            raise (ValueError if rc == -3 else RuntimeError)(self._err())
+        return out
+
+    def solar_flux(self, earth_sun_factor):
+        """solar_source_per_gpoint * earth_sun_factor with numpy's dtype rules, as the reference evaluates it
+        (cork/sw/component.py:371-372: a float32 table gives a float32 product), handed to the engine as float64."""
+        return np.ascontiguousarray(np.asarray(self.table["solar_source_per_gpoint"]) * float(earth_sun_factor), dtype=np.float64)
+
+    def sw_host(self, ncol, nlev, arrays, out=None, earth_sun_factor=1.0, bands=True):
+        pin, pout, out, keep = self._pack_host(ncol, nlev, arrays, out, "sw", bands)
+        sf = self.solar_flux(earth_sun_factor)
+        rc = self._L.cb200_cork_sw_run_host(self._h, ncol, nlev, sf.ctypes.data_as(_dp), ctypes.byref(pin), ctypes.byref(pout))
+        if rc:
+            raise (ValueError if rc == -3 else RuntimeError)(self._err())
+        return out
+
+    def _run_device(self, fn, ncol, nlev, scalar, tensors, out, stream):
+        """scalar: float (lw diffusivity) or a float64 numpy (nband, ngpt) solar flux (sw)"""
+        import torch
+        ins, outs = self.shapes(ncol, nlev)
+        pin, pout = CorkInputs(), CorkOutputs()
+        for k, t in tensors.items():
+            if t is None:
+                continue
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == ins[k]):
+                raise ValueError(f"{k}: need contiguous float64 CUDA tensor of shape {ins[k]}")
+            setattr(pin, k, ctypes.cast(t.data_ptr(), _dp))
+        for k, t in out.items():
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == outs[k]):
+                raise ValueError(f"output {k}: need contiguous float64 CUDA tensor of shape {outs[k]}")
+            setattr(pout, k, ctypes.cast(t.data_ptr(), _dp))
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        arg = scalar.ctypes.data_as(_dp) if isinstance(scalar, np.ndarray) else float(scalar)
+        rc = fn(self._h, ncol, nlev, arg, ctypes.byref(pin), ctypes.byref(pout), ctypes.c_void_p(s))
+        if rc:
+            raise (ValueError if rc == -3 else RuntimeError)(self._err())
+
+    def lw_device(self, ncol, nlev, tensors, out, diffusivity_factor=DIFFUSIVITY_FACTOR, stream=None):
+        self._run_device(self._L.cb200_cork_lw_run_device, ncol, nlev, diffusivity_factor, tensors, out, stream)
+
+    def sw_device(self, ncol, nlev, tensors, out, earth_sun_factor=1.0, stream=None):
+        self._run_device(self._L.cb200_cork_sw_run_device, ncol, nlev, self.solar_flux(earth_sun_factor), tensors, out, stream)
+
+    def enable_timing(self, on=True):
+        self._L.cb200_cork_enable_timing(self._h, 1 if on else 0)
+
+    @property
+    def last_unit_kernel_ms(self):
+        return self._L.cb200_cork_last_unit_kernel_ms(self._h)
+
+    @property
+    def last_launches(self):
+        return self._L.cb200_cork_last_launches(self._h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+MOLAR_MASS_DRY_AIR = 28.970  # cork/common.py:9-17
+MOLAR_MASS = {"h2o": 18.015, "co2": 44.010, "o3": 47.998, "ch4": 16.043, "n2o": 44.013, "o2": 31.998}
+_GAS_CF_NAME = {"h2o": "specific_humidity", "co2": "mole_fraction_of_carbon_dioxide_in_air"}
+_num_bands = {"lw": None, "sw": None}  # set_num_{long,short}wave_bands (climt/_core/initialization.py:108-122)
+
+
+def _p(dims, units, alias=None):
+    d = {"dims": dims, "units": units}
+    if alias:
+        d["alias"] = alias
+    return d
+
+
+class _CorkBase(TendencyComponent):
+    _which = "lw"
+
+    def _setup(self, optics, table, kwargs, device):
+        if optics == "parmentier":
+            raise NotImplementedError("optics='parmentier' (analytic picket-fence optics) is not part of the CUDA engine; "
+                                      "use optics='correlated_k' with a k-table")
+        if optics != "correlated_k":
+            raise ValueError(f"Unknown optics mode: {optics}")
+        self._optics_mode = optics
+        self._table = load_k_table(table) if isinstance(table, (str, os.PathLike)) else table
+        k = self._table["k_coefficients"]
+        self._num_bands, self._num_gpts = k.shape[1], k.shape[2]
+        (self._gas_names, _has_h2o, self._has_co2_axis, self._fully_premixed, self._premixed_bg) = table_flags(self._table)
+        self._diagnostics_level = kwargs.pop("diagnostics_level", 0)
+        if self._diagnostics_level:
+            raise NotImplementedError("diagnostics_level >= 1 (per-g-point dumps) is not provided by the CUDA engine")
+        self._engine = CorkEngine(self._table, device=device)
+        _num_bands[self._which] = self._num_bands
+
+    def _gas_props(self, props, with_co2):
+        if self._premixed_bg:
+            props["specific_humidity"] = _p(["mid_levels", "*"], "kg/kg", "h2o")
+            if with_co2 and self._has_co2_axis:
+                props["mole_fraction_of_carbon_dioxide_in_air"] = _p(["mid_levels", "*"], "mole/mole", "co2")
+        elif not self._fully_premixed:
+            for gas in self._gas_names:
+                props[_GAS_CF_NAME.get(gas, f"mole_fraction_of_{gas}_in_air")] = _p(
+                    ["mid_levels", "*"], "kg/kg" if gas == "h2o" else "mole/mole", gas)
+
+    def _gas_arrays(self, state, nlev, arrays):
+        """the gas part of array_call (cork/lw/component.py:243-287): what goes to the engine, in its units"""
+        if self._fully_premixed:
+            return
+        if self._premixed_bg:
+            arrays["q_h2o"] = state["h2o"].reshape(nlev, -1)
+            if self._has_co2_axis and self._which == "lw":
+                arrays["co2_vmr"] = state["co2"].reshape(nlev, -1)
+            return
+        gq = []
+        for gas in self._gas_names:
+            q = state[gas].reshape(nlev, -1)
+            if gas != "h2o":
+                q = q * (MOLAR_MASS.get(gas, MOLAR_MASS_DRY_AIR) / MOLAR_MASS_DRY_AIR)
+            gq.append(q)
+        arrays["gas_q"] = np.stack(gq)
+
+    @staticmethod
+    def _band_last(a, shape):
+        # (nband, nlev, ncol) -> (nlev, *horizontal, nband); the reference returns the same values through moveaxis+reshape
+        return np.moveaxis(a, 0, -1).reshape(shape + (a.shape[0],))
+
+
+class CorkLongwaveRadiation(_CorkBase):
+    """Drop-in for climt.CorkLongwaveRadiation (cork/lw/component.py:20-373), optics="correlated_k"."""
+    _which = "lw"
+
+    def __init__(self, optics="parmentier", table=None, coefficients="solar_composition", rosseland_mean_fit="freedman2014",
+                 diffusivity_factor=DIFFUSIVITY_FACTOR, device=0, **kwargs):
+        self._diffusivity_factor = diffusivity_factor
+        self._setup(optics, table, kwargs, device)
+        super().__init__(**kwargs)
+
+    @property
+    def input_properties(self):
+        props = {
+            "air_temperature": _p(["mid_levels", "*"], "degK", "T"),
+            "air_pressure": _p(["mid_levels", "*"], "Pa", "p"),
+            "air_pressure_on_interface_levels": _p(["interface_levels", "*"], "Pa", "p_int"),
+            "surface_temperature": _p(["*"], "degK", "T_surf"),
+            "surface_longwave_emissivity": _p(["num_longwave_bands", "*"], "dimensionless", "emissivity"),
+        }
+        self._gas_props(props, with_co2=True)
+        props["longwave_optical_thickness_due_to_cloud"] = _p(["mid_levels", "*", "num_longwave_bands"], "dimensionless", "tau_cloud_lw")
+        return props
+
+    @property
+    def tendency_properties(self):
+        return {"air_temperature": {"units": "degK s^-1"}}
+
+    @property
+    def diagnostic_properties(self):
+        band_i = ["interface_levels", "*", "num_longwave_bands"]
+        band_m = ["mid_levels", "*", "num_longwave_bands"]
+        return {
+            "upwelling_longwave_flux_in_air": _p(["interface_levels", "*"], "W m^-2"),
+            "downwelling_longwave_flux_in_air": _p(["interface_levels", "*"], "W m^-2"),
+            "upwelling_longwave_flux_in_air_per_band": _p(band_i, "W m^-2"),
+            "downwelling_longwave_flux_in_air_per_band": _p(band_i, "W m^-2"),
+            "air_temperature_tendency_from_longwave": _p(["mid_levels", "*"], "degK day^-1"),
+            "longwave_optical_depth_per_band": _p(band_m, "dimensionless"),
+            "longwave_transmittance_per_band": _p(band_m, "dimensionless"),
+            "air_temperature_tendency_from_longwave_per_band": _p(band_m, "degK day^-1"),
+        }
+
+    @property
+    def num_longwave_bands(self):
+        return self._num_bands
+
+    def array_call(self, state):
+        T, p_int = _alias(state, "T", "air_temperature"), _alias(state, "p_int", "air_pressure_on_interface_levels")
+        st = _AliasView(state, self.input_properties)
+        shape_T, shape_pint = T.shape, p_int.shape
+        nlev = T.shape[0]
+        arrays = {"T": T.reshape(nlev, -1), "p": st["p"].reshape(nlev, -1), "p_int": p_int.reshape(nlev + 1, -1),
+                  "T_surf": st["T_surf"].reshape(-1)}
+        ncol = arrays["T"].shape[1]
+        self._gas_arrays(st, nlev, arrays)
+        arrays["emissivity"] = st["emissivity"].reshape(self._num_bands, ncol)
+        arrays["tau_cloud"] = st["tau_cloud_lw"].reshape(nlev, ncol, self._num_bands)
+        o = self._engine.lw_host(ncol, nlev, arrays, diffusivity_factor=self._diffusivity_factor)
+        hr = o["heating_rate"].reshape(shape_T)
+        diagnostics = {
+            "upwelling_longwave_flux_in_air": o["up_broad"].reshape(shape_pint),
+            "downwelling_longwave_flux_in_air": o["down_broad"].reshape(shape_pint),
+            "upwelling_longwave_flux_in_air_per_band": self._band_last(o["up_band"], shape_pint),
+            "downwelling_longwave_flux_in_air_per_band": self._band_last(o["down_band"], shape_pint),
+            "air_temperature_tendency_from_longwave": hr * 86400.0,
+            "longwave_optical_depth_per_band": self._band_last(o["tau_band"], shape_T),
+            "longwave_transmittance_per_band": self._band_last(o["trans_band"], shape_T),
+            "air_temperature_tendency_from_longwave_per_band": self._band_last(o["hr_band"], shape_T),
+        }
+        return {_tend_key(state): hr}, diagnostics
+
+
+class CorkShortwaveRadiation(_CorkBase):
+    """Drop-in for climt.CorkShortwaveRadiation (cork/sw/component.py:20-496), optics="correlated_k"."""
+    _which = "sw"
+
+    def __init__(self, optics="parmentier", table=None, coefficients="solar_composition", stellar_spectrum="sun",
+                 rosseland_mean_fit="freedman2014", device=0, **kwargs):
+        self._bond_albedo_feedback = kwargs.pop("bond_albedo_feedback", False)
+        self._setup(optics, table, kwargs, device)
+        self._solar_source = self._table["solar_source_per_gpoint"]
+        self._rayleigh = self._table.get("rayleigh_coefficient", None)
+        super().__init__(**kwargs)
+
+    @property
+    def input_properties(self):
+        props = {
+            "air_temperature": _p(["mid_levels", "*"], "degK", "T"),
+            "air_pressure": _p(["mid_levels", "*"], "Pa", "p"),
+            "air_pressure_on_interface_levels": _p(["interface_levels", "*"], "Pa", "p_int"),
+            "surface_temperature": _p(["*"], "degK", "T_surf"),
+            "zenith_angle": _p(["*"], "radians", "zenith"),
+            "surface_albedo_for_direct_shortwave": _p(["*"], "dimensionless", "albedo"),
+            "flux_adjustment_for_earth_sun_distance": _p(["*"], "dimensionless", "earth_sun_factor"),
+        }
+        self._gas_props(props, with_co2=False)
+        band_m = ["mid_levels", "*", "num_shortwave_bands"]
+        props["shortwave_optical_thickness_due_to_cloud"] = _p(band_m, "dimensionless", "tau_cloud_sw")
+        props["single_scattering_albedo_due_to_cloud"] = _p(band_m, "dimensionless", "ssa_cloud")
+        props["cloud_asymmetry_parameter"] = _p(band_m, "dimensionless", "g_cloud")
+        return props
+
+    @property
+    def tendency_properties(self):
+        return {"air_temperature": {"units": "degK s^-1"}}
+
+    @property
+    def diagnostic_properties(self):
+        band_i = ["interface_levels", "*", "num_shortwave_bands"]
+        band_m = ["mid_levels", "*", "num_shortwave_bands"]
+        return {
+            "upwelling_shortwave_flux_in_air": _p(["interface_levels", "*"], "W m^-2"),
+            "downwelling_shortwave_flux_in_air": _p(["interface_levels", "*"], "W m^-2"),
+            "upwelling_shortwave_flux_in_air_per_band": _p(band_i, "W m^-2"),
+            "downwelling_shortwave_flux_in_air_per_band": _p(band_i, "W m^-2"),
+            "air_temperature_tendency_from_shortwave": _p(["mid_levels", "*"], "degK day^-1"),
+            "shortwave_optical_depth_per_band": _p(band_m, "dimensionless"),
+            "air_temperature_tendency_from_shortwave_per_band": _p(band_m, "degK day^-1"),
+        }
+
+    @property
+    def num_shortwave_bands(self):
+        return self._num_bands
+
+    def array_call(self, state):
+        T, p_int = _alias(state, "T", "air_temperature"), _alias(state, "p_int", "air_pressure_on_interface_levels")
+        st = _AliasView(state, self.input_properties)
+        shape_T, shape_pint = T.shape, p_int.shape
+        nlev = T.shape[0]
+        arrays = {"T": T.reshape(nlev, -1), "p": st["p"].reshape(nlev, -1), "p_int": p_int.reshape(nlev + 1, -1),
+                  "zenith": st["zenith"].reshape(-1), "albedo": st["albedo"].reshape(-1)}
+        ncol = arrays["T"].shape[1]
+        self._gas_arrays(st, nlev, arrays)
+        nb = self._num_bands
+        arrays["tau_cloud"] = st["tau_cloud_sw"].reshape(nlev, ncol, nb)
+        arrays["ssa_cloud"] = st["ssa_cloud"].reshape(nlev, ncol, nb)
+        arrays["g_cloud"] = st["g_cloud"].reshape(nlev, ncol, nb)
+        esf = float(np.asarray(st["earth_sun_factor"]).reshape(-1)[0])  # cork/sw/component.py:370
+        o = self._engine.sw_host(ncol, nlev, arrays, earth_sun_factor=esf)
+        hr = o["heating_rate"].reshape(shape_T)
+        diagnostics = {
+            "upwelling_shortwave_flux_in_air": o["up_broad"].reshape(shape_pint),
+            "downwelling_shortwave_flux_in_air": o["down_broad"].reshape(shape_pint),
+            "upwelling_shortwave_flux_in_air_per_band": self._band_last(o["up_band"], shape_pint),
+            "downwelling_shortwave_flux_in_air_per_band": self._band_last(o["down_band"], shape_pint),
+            "air_temperature_tendency_from_shortwave": hr * 86400.0,
+            "shortwave_optical_depth_per_band": self._band_last(o["tau_band"], shape_T),
+            "air_temperature_tendency_from_shortwave_per_band": self._band_last(o["hr_band"], shape_T),
+        }
+        return {_tend_key(state): hr}, diagnostics
+
+
+# sympl hands array_call a dict keyed by alias when aliases are declared (the reference indexes state["T"]); the local shim
+# keys by quantity name.  Accept both.
+def _alias(state, alias, name):
+    return state[alias] if alias in state else state[name]
+
+
+def _tend_key(state):
+    return "T" if "T" in state else "air_temperature"
+
+
+class _AliasView:
+    def __init__(self, state, props):
+        self._s = state
+        self._by_alias = {v["alias"]: k for k, v in props.items() if "alias" in v}
+
+    def __getitem__(self, alias):
+        return self._s[alias] if alias in self._s else self._s[self._by_alias[alias]]

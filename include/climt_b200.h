@@ -145,6 +145,77 @@ int cb200_gray_lw_run_host(int device, int ncol, int nlay, const double* t, cons
                            const double* tau, double sigma, double g, double cpd, double* lw_down, double* lw_up,
                            double* tendency);
 
+/* ============================== CORK correlated-k longwave / shortwave ==============================
+ * Replaces, fused into one engine call, the reference's numba kernels and the numpy glue between them:
+ *   _ck_tau_additive_co2_kernel / compute_ck_optical_depth   climt/_components/cork/optics/correlated_k.py:81-117, 378-561
+ *   planck_sources_kernel, _lw_transport_kernel / lw_transport climt/_components/cork/lw/kernels.py:9-184
+ *   _sw_two_stream_core / sw_two_stream                       climt/_components/cork/sw/kernels.py:18-263
+ *   compute_column_amount, compute_heating_rate               climt/_components/cork/common.py:38-80
+ *   CorkLongwaveRadiation.array_call  (optics="correlated_k") climt/_components/cork/lw/component.py:208-373
+ *   CorkShortwaveRadiation.array_call (optics="correlated_k") climt/_components/cork/sw/component.py:223-496
+ * Additive overlap only (ESFT tables are rejected at create).  Arrays are fp64, (nlev[+1], ncol) column-fastest, level 0 at
+ * the surface; per-band state arrays keep the reference's state layout (nlev, ncol, nband).
+ */
+typedef struct cb200_cork_engine cb200_cork_engine;
+
+/* A k-table exactly as the reference's .npz/.nc files hold it (correlated_k.py:9-21); host pointers, read at create. */
+typedef struct cb200_cork_table {
+  int ngas, nband, ngpt, nT, nP, nX, nC;  /* nX = 0: no H2O axis; nC = 0: no CO2 axis */
+  const float* k_coefficients_f32;        /* (ngas, nband, ngpt, nT, nP[, nX[, nC]]) C order, in the table's own dtype: */
+  const double* k_coefficients_f64;       /* exactly one of the two is non-NULL (float32 tables stay float32 in HBM) */
+  const double* temperature_grid;         /* (nT) */
+  const double* pressure_grid_log;        /* (nP) */
+  const double* h2o_vmr_grid;             /* (nX) or NULL */
+  const double* co2_vmr_grid;             /* (nC) or NULL */
+  const double* gpoint_weights;           /* (nband, ngpt) */
+  const double* planck_fraction;          /* (nband_pf, ngpt_pf, nT), longwave tables; NULL otherwise */
+  int nband_pf, ngpt_pf;
+  const double* continuum_kappa;          /* (nband, nT, nP, nX) or NULL */
+  const double* solar_source_per_gpoint;  /* (nband, ngpt), shortwave tables; NULL otherwise */
+  const double* rayleigh_coefficient;     /* (nband) or NULL */
+  int co2_logk;                           /* _CO2_INTERP_LOGK (correlated_k.py:27): 1 = geometric interpolation in CO2 */
+  int premixed;                           /* 1: k per kg of air -> the gas amount is the column mass of air (lw/component.py:254-267) */
+} cb200_cork_table;
+
+typedef struct cb200_cork_inputs {
+  const double *T, *p, *p_int, *T_surf;   /* K, Pa, Pa (nlev+1), K (ncol) */
+  const double* q_h2o;                    /* specific humidity (nlev, ncol); NULL when the table has no H2O axis */
+  const double* co2_vmr;                  /* (nlev, ncol); NULL when the table has no CO2 axis */
+  const double* gas_q;                    /* (ngas, nlev, ncol) mass mixing ratios, non-premixed tables only; else NULL */
+  const double* emissivity;               /* LW: (nband, ncol) */
+  const double* tau_cloud;                /* (nlev, ncol, nband) or NULL (= 0) */
+  const double *zenith, *albedo;          /* SW: (ncol) radians / - */
+  const double *ssa_cloud, *g_cloud;      /* SW: (nlev, ncol, nband), required when tau_cloud is given */
+} cb200_cork_inputs;
+
+typedef struct cb200_cork_outputs {
+  double *up_broad, *down_broad;          /* (nlev+1, ncol) W m-2 */
+  double* heating_rate;                   /* (nlev, ncol) K s-1 */
+  double *up_band, *down_band;            /* (nband, nlev+1, ncol) or NULL */
+  double *tau_band, *trans_band, *hr_band; /* (nband, nlev, ncol) or NULL; trans_band longwave only; hr_band K day-1 */
+} cb200_cork_outputs;
+
+/* g [m s-2], cpd [J kg-1 K-1], sigma [W m-2 K-4] as sympl's get_constant gives them (lw/component.py:224-226) */
+int cb200_cork_create(cb200_cork_engine** out, const cb200_cork_table* table, double g, double cpd, double sigma, int device);
+void cb200_cork_destroy(cb200_cork_engine* e);
+const char* cb200_cork_last_error(cb200_cork_engine* e);
+int cb200_cork_last_launches(cb200_cork_engine* e);
+int cb200_cork_enable_timing(cb200_cork_engine* e, int on);
+double cb200_cork_last_unit_kernel_ms(cb200_cork_engine* e);
+/* Device-pointer calls, asynchronous on `stream`.  diffusivity_factor: D in trans = exp(-D tau) (lw/kernels.py:6). */
+int cb200_cork_lw_run_device(cb200_cork_engine* e, int ncol, int nlev, double diffusivity_factor, const cb200_cork_inputs* in,
+                             const cb200_cork_outputs* out, void* stream);
+/* solar_flux: HOST pointer to (nband, ngpt) doubles = solar_source_per_gpoint * earth_sun_factor, evaluated by the caller in the
+ * table's own dtype exactly as sw/component.py:371-372 does (a float32 table gives a float32 product); NULL = the table's
+ * solar_source_per_gpoint unscaled. */
+int cb200_cork_sw_run_device(cb200_cork_engine* e, int ncol, int nlev, const double* solar_flux, const cb200_cork_inputs* in,
+                             const cb200_cork_outputs* out, void* stream);
+/* Host-pointer calls: chunked 3-stream pipeline (H2D | kernels | D2H); NULL outputs are neither computed nor copied. */
+int cb200_cork_lw_run_host(cb200_cork_engine* e, int ncol, int nlev, double diffusivity_factor, const cb200_cork_inputs* in,
+                           const cb200_cork_outputs* out);
+int cb200_cork_sw_run_host(cb200_cork_engine* e, int ncol, int nlev, const double* solar_flux, const cb200_cork_inputs* in,
+                           const cb200_cork_outputs* out);
+
 #ifdef __cplusplus
 }
 #endif

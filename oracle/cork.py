@@ -64,7 +64,9 @@ def heating_rate(net, p_int, g, cpd):
 
 def optical_depth(table, T, p, gas_amounts, h2o_vmr=None, co2_vmr=None, co2_logk=True):
     """compute_ck_optical_depth for additive overlap (correlated_k.py:378-470, 526-561)."""
-    k = np.ascontiguousarray(table["k_coefficients"], dtype=np.float32)
+    k = np.ascontiguousarray(table["k_coefficients"])
+    if k.dtype not in (np.float32, np.float64):
+        k = k.astype(np.float64)
     ngas, nband, ngpt, nT, nP = k.shape[:5]
     nX = k.shape[5] if k.ndim >= 6 else 0
     nC = k.shape[6] if k.ndim == 7 else 0
@@ -87,18 +89,18 @@ def optical_depth(table, T, p, gas_amounts, h2o_vmr=None, co2_vmr=None, co2_logk
     log_cont = np.log(np.maximum(np.asarray(table["continuum_kappa"], dtype=np.float64), 1e-40)) if has_cont else zero
     tau = np.zeros((nband, ngpt, nlev, ncol))
     ga = _c(gas_amounts)
-    lib().orc_cork_tau(k.ctypes.data_as(_fp), ngas, nband, ngpt, nT, nP, nX, nC, _p(T_grid), _p(p_grid_log), _p(_c(log_x_grid)),
+    lib().orc_cork_tau(k.ctypes.data_as(ctypes.c_void_p), int(k.dtype == np.float64), ngas, nband, ngpt, nT, nP, nX, nC, _p(T_grid), _p(p_grid_log), _p(_c(log_x_grid)),
                        _p(_c(log_c_grid)), _p(_c(T)), _p(_c(log_p)), _p(_c(log_x)), _p(_c(log_c)), _p(ga), int(has_cont),
                        _p(_c(log_cont)), int(co2_logk), nlev, ncol, _p(tau))
     return tau
 
 
 def planck_sources(table, T, T_surf, sigma, nband, ngpt):
-    pf = np.ascontiguousarray(table["planck_fraction"], dtype=np.float32)
+    pf = np.ascontiguousarray(table["planck_fraction"], dtype=np.float64)
     nlev, ncol = T.shape
     planck_src = np.zeros((nband, ngpt, nlev, ncol))
     surf_src = np.zeros((nband, ngpt, ncol))
-    lib().orc_cork_planck(pf.ctypes.data_as(_fp), pf.shape[0], pf.shape[1], pf.shape[2], _p(_c(table["temperature_grid"])),
+    lib().orc_cork_planck(pf.ctypes.data_as(_dp), pf.shape[0], pf.shape[1], pf.shape[2], _p(_c(table["temperature_grid"])),
                           _p(_c(T)), _p(_c(T_surf)), ctypes.c_double(sigma), nband, ngpt, 0, nlev, ncol, _p(planck_src), _p(surf_src))
     return planck_src, surf_src
 

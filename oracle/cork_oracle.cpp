@@ -40,8 +40,9 @@ inline Br bracket(const double* grid, int n, double v) {
 
 extern "C" {
 
-// tau[b][g][lev][col].  nX == 0: 5-D table (T, P); nC == 0: no CO2 axis.
-void orc_cork_tau(const float* k, int ngas, int nband, int ngpt, int nT, int nP, int nX, int nC, const double* T_grid,
+// tau[b][g][lev][col].  nX == 0: 5-D table (T, P); nC == 0: no CO2 axis.  k in the table's own dtype (float32 entries are
+// promoted on use, exactly as numba/numpy promote them); planck_fraction is handed over promoted to double.
+void orc_cork_tau(const void* kptr, int k_is_f64, int ngas, int nband, int ngpt, int nT, int nP, int nX, int nC, const double* T_grid,
                   const double* p_grid_log, const double* log_x_grid, const double* log_c_grid, const double* T,
                   const double* log_p, const double* log_x, const double* log_c, const double* gas_amounts, int has_cont,
                   const double* log_cont, int co2_logk, int nlev, int ncol, double* tau) {
@@ -49,7 +50,7 @@ void orc_cork_tau(const float* k, int ngas, int nband, int ngpt, int nT, int nP,
   const int nXe = nX > 0 ? nX : 1, nCe = nC > 0 ? nC : 1;
   auto K = [&](int ig, int ib, int igp, int iT, int iP, int iX, int iC) -> double {
     const size_t o = ((((((size_t)ig * nband + ib) * ngpt + igp) * nT + iT) * nP + iP) * nXe + iX) * nCe + iC;
-    return (double)k[o];
+    return k_is_f64 ? static_cast<const double*>(kptr)[o] : (double)static_cast<const float*>(kptr)[o];
   };
   auto LC = [&](int ib, int iT, int iP, int iX) -> double { return log_cont[(((size_t)ib * nT + iT) * nP + iP) * nXe + iX]; };
   for (int i = 0; i < ncol; ++i)
@@ -107,7 +108,7 @@ void orc_cork_tau(const float* k, int ngas, int nband, int ngpt, int nT, int nP,
     }
 }
 
-void orc_cork_planck(const float* planck_frac, int nband_orig, int ngpt_orig, int nT, const double* T_grid, const double* T,
+void orc_cork_planck(const double* planck_frac, int nband_orig, int ngpt_orig, int nT, const double* T_grid, const double* T,
                      const double* T_surf, double sigma, int nband, int ngpt, int is_esft, int nlev, int ncol,
                      double* planck_src, double* surf_src) {
   auto PF = [&](int b, int g, int t) -> double { return (double)planck_frac[((size_t)b * ngpt_orig + g) * nT + t]; };

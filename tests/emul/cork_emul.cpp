@@ -1,0 +1,58 @@
+// TEST-ONLY host emulation of the CUDA CORK engine (same per-thread code as the kernels, stepped serially).
+#include <cstring>
+#include <vector>
+
+#include "../../climt_b200/csrc/cork_tables.h"
+
+using namespace cb::cork;
+
+template <int U, typename KT>
+static void run_units(bool lw, const Table& T, const Consts& K, const In& in, const Work& W, int n) {
+  for (int unit = 0; unit < T.nband * T.nchunk; ++unit) {
+    const int band = unit / T.nchunk, chunk = unit - band * T.nchunk;
+    for (int c = 0; c < n; ++c) {
+      if (lw) lw_unit<U, KT>(T, K, in, W, 0, c, band, chunk, unit);
+      else sw_unit<U, KT>(T, K, in, W, 0, c, band, chunk, unit);
+    }
+  }
+}
+
+// scal = {g, cpd, sigma, D}; solar_flux (nband, ngpt) for sw; inp: 13 pointers in cb200_cork_inputs order; outp: 8 pointers
+extern "C" int emul_cork_run(const cb200_cork_table* t, int lw, int umax, const double* scal, const double* solar_flux, int ncol, int nlev,
+                             const double* const* inp, double* const* outp) {
+  if (!check_table(t).empty()) return -1;
+  Table T;
+  TableImage im;
+  build_images(t, umax, T, im);
+  bind(T, im, im.k_f64 ? static_cast<const void*>(im.k64.data()) : static_cast<const void*>(im.k32.data()), im.planck.data(), im.d.data());
+  Consts K{scal[0], scal[1], scal[2], scal[3]};
+  In in{};
+  in.ncol = ncol; in.nlev = nlev;
+  in.T = inp[0]; in.p = inp[1]; in.p_int = inp[2]; in.T_surf = inp[3]; in.q_h2o = inp[4]; in.co2_vmr = inp[5];
+  in.gas_q = t->premixed ? nullptr : inp[6];
+  in.emissivity = inp[7]; in.tau_cloud = inp[8]; in.zenith = inp[9]; in.albedo = inp[10]; in.ssa_cloud = inp[11]; in.g_cloud = inp[12];
+  in.solar_flux = solar_flux;
+  Out out{outp[0], outp[1], outp[2], outp[3], outp[4], outp[5], outp[6], outp[7]};
+  const int nunits = T.nband * T.nchunk;
+  Work W;
+  W.ncc = ncol;
+  W.nscr = lw ? 2 * T.U : 7 * T.U;
+  std::vector<double> ws((size_t)(F_AMT0 + T.ngas) * nlev * ncol), scr((size_t)nunits * W.nscr * nlev * ncol),
+      part((size_t)nunits * 3 * (nlev + 1) * ncol);
+  std::vector<int> idx((size_t)nlev * ncol);
+  W.ws = ws.data(); W.idx = idx.data(); W.scr = scr.data(); W.part = part.data();
+  for (int l = 0; l < nlev; ++l)
+    for (int c = 0; c < ncol; ++c) prep_cell(T, K, in, W, 0, c, l);
+#define CB_RUN(U)                                                                 \
+  case U:                                                                         \
+    if (im.k_f64) run_units<U, double>(lw != 0, T, K, in, W, ncol);               \
+    else run_units<U, float>(lw != 0, T, K, in, W, ncol);                         \
+    break;
+  switch (T.U) { CB_RUN(1) CB_RUN(2) CB_RUN(4) CB_RUN(8) }
+#undef CB_RUN
+  for (int lev = 0; lev <= nlev; ++lev)
+    for (int c = 0; c < ncol; ++c) reduce_level(T, W, nlev, ncol, 0, c, lev, out);
+  for (int l = 0; l < nlev; ++l)
+    for (int c = 0; c < ncol; ++c) heat_layer(T, K, in, out, 0, c, l, lw != 0);
+  return 0;
+}

@@ -151,3 +151,66 @@ def run_sw_emul(st, iopt=(1, 0, 2, 1, 1, 0, 1), scal=None, mcica=(0, 1, 0)):
 
 
 SW_KEYS = {"uflx": "swuflx", "dflx": "swdflx", "uflxc": "swuflxc", "dflxc": "swdflxc", "hr": "swhr", "hrc": "swhrc"}
+
+
+# ---- CORK -----------------------------------------------------------------------------------------------------------
+CORK_G, CORK_CPD, CORK_SIGMA = 9.80665, 1004.64, 5.670367e-08   # sympl defaults
+
+
+def cork_table(name):
+    from climt_b200 import cork
+    return cork.load_k_table(name)
+
+
+def cork_emul_lib():
+    so = os.path.join(HERE, "emul", "libcb_emul_cork.so")
+    src = os.path.join(HERE, "emul", "cork_emul.cpp")
+    deps = [src] + [os.path.join(HERE, "..", "climt_b200", "csrc", f) for f in ("cork_core.cuh", "cork_tables.h", "cb_common.h")]
+    deps.append(os.path.join(HERE, "..", "include", "climt_b200.h"))
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def cork_arrays(s, which):
+    """golden/oracle state dict -> engine input arrays (cb200_cork_inputs names)"""
+    a = {"T": s["T"], "p": s["p"], "p_int": s["p_int"], "q_h2o": s["q"]}
+    if which == "lw":
+        a.update(T_surf=s["T_surf"], co2_vmr=s["co2"], emissivity=s["emissivity"], tau_cloud=s["tau_cloud_lw"])
+    else:
+        a.update(zenith=s["zenith"], albedo=s["albedo"], tau_cloud=s["tau_cloud_sw"], ssa_cloud=s["ssa_cloud"], g_cloud=s["g_cloud"])
+    return a
+
+
+def cork_solar_flux(table, earth_sun_factor):
+    """solar_source * earth_sun_factor with the reference's dtype semantics (sw/component.py:371-372), as float64"""
+    return np.ascontiguousarray(np.asarray(table["solar_source_per_gpoint"]) * float(earth_sun_factor), dtype=np.float64)
+
+
+def run_cork_emul(table, which, arrays, scalar, umax=4):
+    """The CUDA engine's per-thread code, compiled for the host.  scalar = D (lw) or earth_sun_factor (sw)."""
+    from climt_b200 import cork
+    lib = cork_emul_lib()
+    ct, keep = cork.make_ctable(table)
+    nlev, ncol = arrays["T"].shape
+    nb = ct.nband
+    shapes = {"up_broad": (nlev + 1, ncol), "down_broad": (nlev + 1, ncol), "heating_rate": (nlev, ncol), "up_band": (nb, nlev + 1, ncol),
+              "down_band": (nb, nlev + 1, ncol), "tau_band": (nb, nlev, ncol), "trans_band": (nb, nlev, ncol), "hr_band": (nb, nlev, ncol)}
+    out = {k: np.zeros(v) for k, v in shapes.items()}
+    ins = []
+    for k in cork.CORK_IN:
+        a = arrays.get(k)
+        if a is not None:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+        ins.append(a)
+    inp = (_dp * 13)(*[a.ctypes.data_as(_dp) if a is not None else None for a in ins])
+    outp = (_dp * 8)(*[out[k].ctypes.data_as(_dp) for k in cork.CORK_OUT])
+    scal = np.array([CORK_G, CORK_CPD, CORK_SIGMA, scalar if which == "lw" else 1.66])
+    solar = cork_solar_flux(table, scalar) if which == "sw" else np.zeros(1)
+    lib.emul_cork_run.argtypes = [ctypes.POINTER(cork.CorkTable), ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_int, ctypes.c_int,
+                                  ctypes.POINTER(_dp), ctypes.POINTER(_dp)]
+    rc = lib.emul_cork_run(ctypes.byref(ct), 1 if which == "lw" else 0, umax, scal.ctypes.data_as(_dp), solar.ctypes.data_as(_dp), ncol, nlev,
+                           ctypes.cast(inp, ctypes.POINTER(_dp)), ctypes.cast(outp, ctypes.POINTER(_dp)))
+    assert rc == 0
+    return out
