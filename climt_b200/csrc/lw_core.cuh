@@ -103,11 +103,21 @@ CB_HD void secdiff_all(double pwvcm, double* secdiff /*[16]*/) {
   }
 }
 CB_HD double secdiff_band(double pwvcm, int ib /*0-based*/) {
-  const double a0[16] = {1.66, 1.55, 1.58, 1.66, 1.54, 1.454, 1.89, 1.33, 1.668, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66};
-  const double a1[16] = {0.00, 0.25, 0.22, 0.00, 0.13, 0.446, -0.10, 0.40, -0.006, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
-  const double a2[16] = {0.00, -12.0, -11.7, 0.00, -0.72, -0.243, 0.19, -0.062, 0.414, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
-  if (ib == 0 || ib == 3 || ib >= 9) return 1.66;
-  double s = a0[ib] + a1[ib] * exp(a2[ib] * pwvcm);
+  // a0 + a1*exp(a2*pwvcm) clamped to [1.5, 1.8] for bands 2-3 and 5-9, 1.66 otherwise (rrtmg_lw_rtrn.f90:246-270).
+  // A switch, not indexed arrays: ib is a run-time value in the band-generic transfer kernel and indexed local arrays
+  // would live in (and be initialised into) local memory by every thread.
+  double a0, a1, a2;
+  switch (ib) {
+    case 1: a0 = 1.55; a1 = 0.25; a2 = -12.0; break;
+    case 2: a0 = 1.58; a1 = 0.22; a2 = -11.7; break;
+    case 4: a0 = 1.54; a1 = 0.13; a2 = -0.72; break;
+    case 5: a0 = 1.454; a1 = 0.446; a2 = -0.243; break;
+    case 6: a0 = 1.89; a1 = -0.10; a2 = 0.19; break;
+    case 7: a0 = 1.33; a1 = 0.40; a2 = -0.062; break;
+    case 8: a0 = 1.668; a1 = -0.006; a2 = 0.414; break;
+    default: return 1.66;
+  }
+  double s = a0 + a1 * exp(a2 * pwvcm);
   if (s > 1.80) s = 1.80;
   if (s < 1.50) s = 1.50;
   return s;
@@ -795,8 +805,49 @@ CB_HD double planck_band(const double* __restrict__ tp /* totplnk row of band */
 
 // ---------------------------------------------------------------------------------------------
 // lw_unit: taumol + rtrn for U g-points of band B in one column (rrtmg_lw_rtrn.f90:320-526).
-template <int B, int U, bool MC>
-CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int g0, int unit) {
+// The per-g-point work is split in two kernels (r01 ncu: 49 % of the fused kernel's stalls were memory latency with 16 warps
+// per SM, 14 % instruction fetch across 32 band variants):
+//   lw_taumol_unit<B,U>    band-specialised, layers independent: taug and Planck fractions of U g-points (taumol) for a
+//                          chunk of layers -> two scratch rows per g-point
+//   lw_transfer_unit<U,MC> ONE code body for every band: rtrn / rtrnmc (down sweep, surface, up sweep)
+constexpr int NSCR = 6;               // scratch rows per g-point
+constexpr int R_TAU = 4, R_FRAC = 5;  // written by lw_taumol_unit (rows 0-3: atrans, bbugas, atot, bbutot of the down sweep)
+
+CB_HD int band_gstart(int ib) {  // first g-point of band ib (0-based), for code that is generic in the band
+  switch (ib) {
+    case 0: return 0; case 1: return 10; case 2: return 22; case 3: return 38; case 4: return 52; case 5: return 68;
+    case 6: return 76; case 7: return 88; case 8: return 96; case 9: return 108; case 10: return 114; case 11: return 122;
+    case 12: return 130; case 13: return 134; case 14: return 136; default: return 138;
+  }
+}
+
+template <int B, int U>
+CB_HD void lw_taumol_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int g0, int l0, int l1) {
+  const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
+  const size_t gc = (size_t)(c0 + c);
+  const size_t wstride = (size_t)nlay * ncc;
+  const int laytrop = W.laytrop[c];
+  const int gabs = kGS[B - 1] + g0;
+  for (int l = l0; l < l1; ++l) {
+    const int lev = l + 1;
+    const int idx = W.idx[(size_t)l * ncc + c];
+    const double pavel = in.play[(size_t)l * ncol + gc];
+    double tau[U], frac[U];
+    const double* ws = W.ws + (size_t)l * ncc + c;
+    if (lev <= laytrop) eval_band<B, true, U>(T, ws, wstride, idx, pavel, g0, tau, frac);
+    else eval_band<B, false, U>(T, ws, wstride, idx, pavel, g0, tau, frac);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
+      scr[R_TAU * wstride] = tau[u];
+      scr[R_FRAC * wstride] = frac[u];
+    }
+  }
+}
+
+// rtrn / rtrnmc for U consecutive g-points of band ib (0-based) -- generic in the band (rrtmg_lw_rtrn.f90:300-557)
+template <int U, bool MC>
+CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int ib, int g0, int unit) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
   const double* __restrict__ tb = T.base;
@@ -806,21 +857,19 @@ CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, 
   const double* __restrict__ tfn_tbl = tb + T.tfn_tbl;
   const double* __restrict__ et_tbl = tb + T.et_tbl;
   (void)exp_tbl; (void)tfn_tbl;
-  const double* __restrict__ tp = tb + T.totplnk + (size_t)(B - 1) * 181;
+  const double* __restrict__ tp = tb + T.totplnk + (size_t)ib * 181;
   const size_t wstride = (size_t)nlay * ncc;
-  const int laytrop = W.laytrop[c];
   const int ncb = W.ncbands[c];
   const double pwvcm = W.pwvcm[c];
-  const double secdiff = secdiff_band(pwvcm, B - 1);
+  const double secdiff = secdiff_band(pwvcm, ib);
   // cloud band feeding this LW band: ipat(B, 0|1|2) for ncbands = 1|5|16 (rtrn.f90:233-235,324-330)
   int ibc = 0;
   if (ncb == 5) {
-    const int pat5[16] = {0, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4};
-    ibc = pat5[B - 1];
+    ibc = ib <= 1 ? ib : (ib <= 4 ? 2 : (ib <= 7 ? 3 : 4));  // ipat(:,1) = 1,2,3,3,3,4,4,4,5,...,5
   } else if (ncb == 16) {
-    ibc = B - 1;
+    ibc = ib;
   }
-  const int gabs = kGS[B - 1] + g0;  // absolute g-point of u = 0
+  const int gabs = band_gstart(ib) + g0;  // absolute g-point of u = 0
   double radld[U], radclrd[U], frac1[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) { radld[u] = 0.; radclrd[u] = 0.; frac1[u] = 0.; }
@@ -831,13 +880,7 @@ CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, 
   for (int lev = nlay; lev >= 1; --lev) {
     const int l = lev - 1;
     const size_t o = (size_t)l * ncol + gc;
-    const int idx = W.idx[(size_t)l * ncc + c];
-    const double pavel = in.play[o];
-    double tau[U], frac[U];
-    const double* ws = W.ws + (size_t)l * ncc + c;
-    if (lev <= laytrop) eval_band<B, true, U>(T, ws, wstride, idx, pavel, g0, tau, frac);
-    else eval_band<B, false, U>(T, ws, wstride, idx, pavel, g0, tau, frac);
-    const double taua = in.tauaer[((size_t)(B - 1) * nlay + l) * ncol + gc];
+    const double taua = in.tauaer[((size_t)ib * nlay + l) * ncol + gc];
     const double blay = planck_band(tp, in.tlay[o]);
     const double plev_dn = planck_band(tp, in.tlev[o]);  // planklev(lev-1)
     const double dplankup = plev_up - blay;
@@ -876,11 +919,11 @@ CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, 
     for (int u = 0; u < U; ++u) {
       const bool on = !MC || ((mbits >> u) & 1u);
       const double odcld = on ? odcld_l : 0., efclfrac = on ? efclfrac_l : 0., cldfrac = on ? cldfrac_l : 0.;
-      const double plfrac = frac[u];
-      double odepth = secdiff * (tau[u] + taua);
+      double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
+      const double plfrac = scr[R_FRAC * wstride];
+      double odepth = secdiff * (scr[R_TAU * wstride] + taua);
       if (odepth < 0.0) odepth = 0.0;
       double atrans, bbd, bbugas;
-      double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * 4) * nlay + l) * ncc + c;
       if (cloudy) {
         double odtot = odepth + odcld;
         double gassrc, bbdtot, atot, bbutot;
@@ -967,7 +1010,7 @@ CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, 
   part[3 * pstride + (size_t)nlay * ncc] = 0.0;
   // surface (rtrn.f90:455-470)
   const double tbound = in.tsfc[gc];
-  const double semiss = in.emis[(size_t)(B - 1) * ncol + gc];
+  const double semiss = in.emis[(size_t)ib * ncol + gc];
   const double plankbnd = semiss * planck_band(tp, tbound);
   const double reflect = 1. - semiss;
   double radlu[U], radclru[U];
@@ -1016,7 +1059,7 @@ CB_HD void lw_unit(const Tables& T, const In& in, const Work& W, int c0, int c, 
     for (int u = 0; u < U; ++u) {
       const bool on = !MC || ((mbits >> u) & 1u);
       const double efclfrac = on ? efclfrac_l : 0., cldfrac = on ? cldfrac_l : 0.;
-      const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * 4) * nlay + l) * ncc + c;
+      const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
       const double atrans = scr[0], bbugas = scr[wstride];
       if (cloudy) {
         const double atot = scr[2 * wstride], bbutot = scr[3 * wstride];
@@ -1044,10 +1087,13 @@ struct Unit {
   int band, g0, u;
 };
 #ifndef CB_LW_UMAX
-#define CB_LW_UMAX 4  // g-points per thread (2 or 4)
+#define CB_LW_UMAX 2      // g-points per thread of the transfer kernel (2 or 4)
+#endif
+#ifndef CB_LW_TAU_UMAX
+#define CB_LW_TAU_UMAX 4  // g-points per thread of the taumol kernel (2 or 4)
 #endif
 constexpr int kMaxUnits = 72;
-inline int build_units(Unit* out) {  // host only
+inline int build_units(Unit* out, int umax) {  // host only
   int n = 0;
   // heavy (two-key-species, lower-atmosphere-rich) work first so the tail of the grid is made of light blocks
   for (int pass = 0; pass < 2; ++pass)
@@ -1055,10 +1101,10 @@ inline int build_units(Unit* out) {  // host only
       const bool heavy = kNSPA[b - 1] == 9;
       if ((pass == 0) != heavy) continue;
       const int ng = kNG[b - 1];
-      for (int g0 = 0; g0 < ng; g0 += CB_LW_UMAX) {
+      for (int g0 = 0; g0 < ng; g0 += umax) {
         out[n].band = b;
         out[n].g0 = g0;
-        out[n].u = (ng - g0) >= CB_LW_UMAX ? CB_LW_UMAX : (ng - g0);
+        out[n].u = (ng - g0) >= umax ? umax : (ng - g0);
         ++n;
       }
     }

@@ -18,8 +18,8 @@ using namespace cb::lw;
 namespace {
 
 using cb::kBlock;
-#ifndef CB_UNITS_MIN_BLOCKS
-#define CB_UNITS_MIN_BLOCKS 4
+#ifndef CB_LW_RT_MIN_BLOCKS
+#define CB_LW_RT_MIN_BLOCKS 6  // transfer kernel: 80 registers, no spills (ptxas), 24 warps per SM
 #endif
 
 __global__ void __launch_bounds__(kBlock) k_prep(const __grid_constant__ Tables T, const __grid_constant__ In in,
@@ -33,26 +33,46 @@ struct UnitList {
   int n;
 };
 
-// One block = 128 adjacent columns x one unit (<=4 g-points of one band): every branch on the band is
-// block-uniform, all global accesses are column-contiguous.
-template <bool MC>
-__global__ void __launch_bounds__(kBlock, CB_UNITS_MIN_BLOCKS) k_units(const __grid_constant__ Tables T, const __grid_constant__ In in,
-                                                  const __grid_constant__ Work W, const __grid_constant__ UnitList UL,
-                                                  int c0, int n) {
+#ifndef CB_LW_TAU_MIN_BLOCKS
+#define CB_LW_TAU_MIN_BLOCKS 4
+#endif
+#ifndef CB_LW_LAYER_CHUNKS
+#define CB_LW_LAYER_CHUNKS 4  // taumol: layers are independent -> blockIdx.z cuts them into chunks for more threads in flight
+#endif
+
+// taumol: one block = 128 adjacent columns x one unit (<= 4 g-points of one band) x one chunk of layers; every branch on
+// the band is block-uniform, all global accesses are column-contiguous.
+__global__ void __launch_bounds__(kBlock, CB_LW_TAU_MIN_BLOCKS)
+    k_lw_taumol(const __grid_constant__ Tables T, const __grid_constant__ In in, const __grid_constant__ Work W,
+                const __grid_constant__ UnitList UL, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
-  const int k = blockIdx.y;
-  const Unit un = UL.u[k];
-#define CB_CASE(B)                                                  \
-  case B:                                                           \
-    if (un.u == 4) lw_unit<B, 4, MC>(T, in, W, c0, c, un.g0, k);    \
-    else lw_unit<B, 2, MC>(T, in, W, c0, c, un.g0, k);              \
+  const Unit un = UL.u[blockIdx.y];
+  const int per = (in.nlay + gridDim.z - 1) / gridDim.z;
+  const int l0 = blockIdx.z * per, l1 = min(in.nlay, l0 + per);
+#define CB_CASE(B)                                                       \
+  case B:                                                                \
+    if (un.u == 4) lw_taumol_unit<B, 4>(T, in, W, c0, c, un.g0, l0, l1);  \
+    else lw_taumol_unit<B, 2>(T, in, W, c0, c, un.g0, l0, l1);            \
     break;
   switch (un.band) {
     CB_CASE(1) CB_CASE(2) CB_CASE(3) CB_CASE(4) CB_CASE(5) CB_CASE(6) CB_CASE(7) CB_CASE(8)
     CB_CASE(9) CB_CASE(10) CB_CASE(11) CB_CASE(12) CB_CASE(13) CB_CASE(14) CB_CASE(15) CB_CASE(16)
   }
 #undef CB_CASE
+}
+
+// rtrn / rtrnmc: one block = 128 adjacent columns x one unit (<= CB_LW_UMAX g-points of one band); one code body for all bands
+template <bool MC>
+__global__ void __launch_bounds__(kBlock, CB_LW_RT_MIN_BLOCKS)
+    k_units(const __grid_constant__ Tables T, const __grid_constant__ In in, const __grid_constant__ Work W,
+            const __grid_constant__ UnitList UL, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int k = blockIdx.y;
+  const Unit un = UL.u[k];
+  if (CB_LW_UMAX >= 4 && un.u == 4) lw_transfer_unit<4, MC>(T, in, W, c0, c, un.band - 1, un.g0, k);
+  else lw_transfer_unit<2, MC>(T, in, W, c0, c, un.band - 1, un.g0, k);
 }
 
 // McICA cloud mask with the per-column kissvec generator: one thread per column
@@ -97,13 +117,16 @@ struct cb200_lw_engine {
   int irng = 1, permuteseed = 0;
   unsigned* d_mask_full = nullptr;
   size_t mask_full_cap = 0;
-  UnitList UL;
+  UnitList UL;      // transfer kernel units (<= CB_LW_UMAX g-points); `part` holds one flux set per unit
+  UnitList UL_tau;  // taumol kernel units (<= CB_LW_TAU_UMAX g-points)
   // workspace (grown on demand)
   int cap_ncc = 0, cap_nlay = 0;
   Work W{};
   int max_chunk = 16384;
   // host-pointer path
   cb::HostPipe pipe;
+  size_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the last host-pointer call
+  bool host_pending = false;
   int* h_err = nullptr;
   std::string error;
   int launches = 0;
@@ -128,7 +151,7 @@ struct cb200_lw_engine {
     CUDA_OK(cudaMalloc(&W.ncbands, sizeof(int) * n));
     CUDA_OK(cudaMalloc(&W.pwvcm, sizeof(double) * n));
     CUDA_OK(cudaMalloc(&W.cld, sizeof(double) * 32 * L * n));
-    CUDA_OK(cudaMalloc(&W.scr, sizeof(double) * 140 * 4 * L * n));
+    CUDA_OK(cudaMalloc(&W.scr, sizeof(double) * 140 * NSCR * L * n));
     CUDA_OK(cudaMalloc(&W.part, sizeof(double) * UL.n * 4 * (L + 1) * n));
     CUDA_OK(cudaMalloc(&W.mask, sizeof(unsigned) * 5 * L * n));
     CUDA_OK(cudaMalloc(&W.err, sizeof(int)));
@@ -157,7 +180,8 @@ extern "C" int cb200_lw_create(cb200_lw_engine** out, const char* table_blob, co
     ce = cudaMemcpy(e->d_tables, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) throw std::runtime_error(std::string("cudaMemcpy(tables): ") + cudaGetErrorString(ce));
     e->T.base = e->d_tables;
-    e->UL.n = build_units(e->UL.u);
+    e->UL.n = build_units(e->UL.u, CB_LW_UMAX);
+    e->UL_tau.n = build_units(e->UL_tau.u, CB_LW_TAU_UMAX);
     if (const char* mc = std::getenv("CLIMT_B200_MAX_CHUNK")) e->max_chunk = std::max(128, std::atoi(mc));
     cudaMallocHost(&e->h_err, sizeof(int));
     cudaEventCreate(&e->ev0);
@@ -223,12 +247,13 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
   if (mc && e->irng == 0) { k_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
   k_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
   if (e->timing) cudaEventRecord(e->ev0, st);
+  k_lw_taumol<<<dim3(gx, e->UL_tau.n, CB_LW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, in, W, e->UL_tau, c0, n);
   if (mc) k_units<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
   else k_units<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
   if (e->timing) cudaEventRecord(e->ev1, st);
   k_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(e->T, W, e->UL, out, nlay, out_ncol, c0, n);
   k_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
-  e->launches += 4;
+  e->launches += 5;
   if (e->timing) {
     CUDA_OK(cudaEventSynchronize(e->ev1));
     float ms = 0.f;
@@ -308,12 +333,13 @@ extern "C" int cb200_lw_check(cb200_lw_engine* e) {
 // Host-pointer call (what the reference-named wrapper and the Python component use).  Column chunks flow through
 // the three-stream pipeline of cb::HostPipe; arrays the option flags make dead are not transferred at all
 // (cloud inputs when icld = 0, taucld unless inflag = 0 -- see DESIGN.md "host path").
-extern "C" int cb200_lw_run_host(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* hin,
-                                 const cb200_lw_outputs* hout) {
+extern "C" int cb200_lw_run_host_async(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* hin,
+                                       const cb200_lw_outputs* hout) {
   if (ncol <= 0 || nlay <= 0 || nlay > 203) { e->error = "bad ncol/nlay (1 <= nlay <= 203, parrrtm.f90:31)"; return -3; }
   CUDA_OK(cudaSetDevice(e->device));
   cb::HostPipe& P = e->pipe;
   CUDA_OK(P.init());
+  if (e->host_pending) { e->error = "a previous run_host_async call has not been waited for"; return -3; }
   const int L = nlay;
   // rows (of ncol doubles) of the 23 inputs in cb200_lw_inputs order, then of the 6 outputs
   const int irows[23] = {L, L + 1, L, L + 1, 1, L, L, L, L, L, L, L, L, L, L, 16, L, L, L, L, L, L, 16 * L};
@@ -331,6 +357,8 @@ extern "C" int cb200_lw_run_host(cb200_lw_engine* e, int ncol, int nlay, const c
   size_t irow_tot = 0, orow_tot = 0;
   for (int i = 0; i < 23; ++i) if (used[i]) irow_tot += (size_t)irows[i] * inner[i];
   for (int i = 0; i < 6; ++i) orow_tot += (size_t)orows[i];
+  e->h2d_bytes = irow_tot * (size_t)ncol * sizeof(double);
+  e->d2h_bytes = orow_tot * (size_t)ncol * sizeof(double);
   int chunk = ncol < P.chunk ? ncol : P.chunk;
   const int wchunk = (chunk + kBlock - 1) / kBlock * kBlock;
   if (e->ensure_work(wchunk, nlay)) return -1;
@@ -381,9 +409,29 @@ extern "C" int cb200_lw_run_host(cb200_lw_engine* e, int ncol, int nlay, const c
     for (int i = 0; i < 6; ++i) CUDA_OK(P.scatter(hop[i], dop[i], orows[i], ncol, c0, n));
     CUDA_OK(cudaEventRecord(P.out_done[s], P.s_out));
   }
-  CUDA_OK(cudaStreamSynchronize(P.s_out));
   CUDA_OK(cudaGetLastError());
+  e->host_pending = true;
+  return 0;
+}
+
+// Completes the call started by cb200_lw_run_host_async: outputs are in the caller's buffers on return.
+extern "C" int cb200_lw_wait(cb200_lw_engine* e) {
+  if (!e->host_pending) return 0;
+  e->host_pending = false;
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->pipe.s_out));
   return cb200_lw_check(e);
+}
+
+extern "C" int cb200_lw_run_host(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* hin,
+                                 const cb200_lw_outputs* hout) {
+  if (int rc = cb200_lw_run_host_async(e, ncol, nlay, hin, hout)) return rc;
+  return cb200_lw_wait(e);
+}
+
+extern "C" void cb200_lw_last_transfer_bytes(cb200_lw_engine* e, double* h2d, double* d2h) {
+  *h2d = (double)e->h2d_bytes;
+  *d2h = (double)e->d2h_bytes;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ enum WsField {
   F_SELFFAC, F_SELFFRAC, F_FORFAC, F_FORFRAC,
   NF
 };
-constexpr int NSCR = 14;  // per g-point scratch rows: 7 (ref, refd, tra, trad, dbt, rup, rupd) x {clear, total}
+constexpr int NSCR = 16;  // per g-point scratch rows: 7 (ref, refd, tra, trad, dbt, rup, rupd) x {clear, total} + taug, taur
 
 struct BandOff {
   int absa, absb, selfref, forref, sfluxref, irradnce, facbrght, snsptdrk;
@@ -71,6 +71,7 @@ struct Work {
   double* cld;    // [3][14][nlay][ncc]  delta-scaled cloud tau, ssa, asym
   double* aer;    // [3][14][nlay][ncc]  aerosol tau, ssa, asym (iaer = 6 only)
   double* scr;    // [112][NSCR][nlay][ncc]
+  double* src;    // [112][ncc]  solar source function of each g-point (taken at layer laysolfr of its band)
   double* part;   // [nunits][4][nlay+1][ncc]   fu, fd, cu, cd  (already weighted by the incoming flux)
   unsigned* mask; // [nlay][4][mstride] (+ moff) McICA cloud mask, bit (g & 31) of word (g >> 5)
   int mstride, moff;
@@ -81,6 +82,14 @@ CB_HD int pack_idx(int jp, int jt, int jt1, int inds, int indf) { return jp | (j
 
 constexpr int kNG[14] = {6, 12, 8, 8, 10, 10, 2, 10, 8, 6, 6, 8, 6, 12};
 constexpr int kGS[14] = {0, 6, 18, 26, 34, 44, 54, 56, 66, 74, 80, 86, 94, 100};
+// first g-point of band ib, for code that is generic in the band (a constexpr array cannot be indexed at run time on the device)
+CB_HD int band_gstart(int ib) {
+  switch (ib) {
+    case 0: return 0; case 1: return 6; case 2: return 18; case 3: return 26; case 4: return 34; case 5: return 44;
+    case 6: return 54; case 7: return 56; case 8: return 66; case 9: return 74; case 10: return 80; case 11: return 86;
+    case 12: return 94; default: return 100;
+  }
+}
 constexpr int kNSPA[14] = {9, 9, 9, 9, 1, 9, 9, 1, 9, 1, 0, 1, 9, 1};
 constexpr int kNSPB[14] = {1, 5, 1, 1, 1, 5, 1, 0, 1, 0, 0, 1, 5, 1};
 
@@ -623,19 +632,49 @@ CB_HD void reftra(const double* __restrict__ exp_tbl, double bpade, double zg, d
 }
 
 // ---------------------------------------------------------------------------------------------
-// sw_unit: spcvrt_sw for U g-points of band B in one column (rrtmg_sw_spcvrt.f90:329-661).
-template <int B, int U, bool MC>
-CB_HD void sw_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int c0, int c,
-                   int g0, int unit) {
+// The per-g-point work is split in two kernels (r01 ncu: the fused version stalled 26 % of its issue slots on
+// instruction fetch -- 28 band variants of ~55 KB each -- and ran 12 warps per SM at 168 registers):
+//   sw_taumol_unit<B,U>   band-specialised, layers independent: gas optical depth + Rayleigh depth of U g-points
+//                         (taumol_sw) for a chunk of layers -> two scratch rows per g-point; solar source at laysolfr
+//   sw_transfer_unit<U,MC> ONE code body for every band: delta-scaling, reftra_sw, adding (spcvrt_sw / spcvmc_sw)
+constexpr int R_TAUG = 14, R_TAUR = 15;  // scratch rows written by sw_taumol_unit (rows 0-13: sw_transfer_unit)
+
+template <int B, int U>
+CB_HD void sw_taumol_unit(const Tables& T, const Solar& sol, const In& in, const Work& W, int c0, int c, int g0, int l0, int l1) {
   constexpr int ib = B - 16;
+  const int nlay = in.nlay, ncc = W.ncc;
+  const size_t wstride = (size_t)nlay * ncc;
+  const int laytrop = W.laytrop[c];
+  const int laysolfr = W.laysolfr[(size_t)ib * ncc + c];
+  const int gabs = kGS[ib] + g0;
+  for (int l = l0; l < l1; ++l) {
+    const int lay = l + 1;
+    const int idx = W.idx[(size_t)l * ncc + c];
+    const double* ws = W.ws + (size_t)l * ncc + c;
+    double taug[U], taur[U], src[U];
+    const bool want = lay == laysolfr;
+    if (lay <= laytrop) eval_band<B, true, U>(T, ws, wstride, idx, g0, taug, taur, want, sol, src);
+    else eval_band<B, false, U>(T, ws, wstride, idx, g0, taug, taur, want, sol, src);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
+      scr[R_TAUG * wstride] = taug[u];
+      scr[R_TAUR * wstride] = taur[u];
+      if (want) W.src[(size_t)(gabs + u) * ncc + c] = src[u];
+    }
+  }
+}
+
+// spcvrt_sw / spcvmc_sw for U consecutive g-points of band ib (rrtmg_sw_spcvrt.f90:329-661) -- generic in the band.
+template <int U, bool MC>
+CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int c0, int c,
+                            int ib, int g0, int unit) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
   const double* __restrict__ tb = T.base;
   const double* __restrict__ exp_tbl = tb + T.exp_tbl;
   const double bpade = T.bpade;
   const size_t wstride = (size_t)nlay * ncc;
-  const int laytrop = W.laytrop[c];
-  const int laysolfr = W.laysolfr[(size_t)ib * ncc + c];
   const bool cloudy_col = W.anycld[c] != 0;
   double prmu0 = in.coszen[gc];
   if (prmu0 < 1.e-10) prmu0 = 1.e-10;
@@ -643,19 +682,14 @@ CB_HD void sw_unit(const Tables& T, const Solar& sol, const In& in, const Flags&
   const bool nir = (ib <= 8) || ib == 13;
   const double albdir = nir ? in.aldir[gc] : in.asdir[gc];
   const double albdif = nir ? in.aldif[gc] : in.asdif[gc];
-  const int gabs = kGS[ib] + g0;
+  const int gabs = band_gstart(ib) + g0;
+  const size_t growstride = (size_t)NSCR * wstride;  // scratch stride between consecutive g-points
+  double* __restrict__ scr0 = W.scr + ((size_t)gabs * NSCR) * wstride + c;
   // ---- pass A: surface -> top.  layer optical properties, two-stream R/T, upward adding
-  double rupc[U], rupdc[U], rup[U], rupd[U], src[U];
+  double rupc[U], rupdc[U], rup[U], rupd[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) { rupc[u] = albdir; rupdc[u] = albdif; rup[u] = albdir; rupd[u] = albdif; src[u] = 0.; }
+  for (int u = 0; u < U; ++u) { rupc[u] = albdir; rupdc[u] = albdif; rup[u] = albdir; rupd[u] = albdif; }
   for (int l = 0; l < nlay; ++l) {
-    const int lay = l + 1;
-    const int idx = W.idx[(size_t)l * ncc + c];
-    const double* ws = W.ws + (size_t)l * ncc + c;
-    double taug[U], taur[U];
-    const bool want = lay == laysolfr;
-    if (lay <= laytrop) eval_band<B, true, U>(T, ws, wstride, idx, g0, taug, taur, want, sol, src);
-    else eval_band<B, false, U>(T, ws, wstride, idx, g0, taug, taur, want, sol, src);
     // aerosol optical properties of this band/layer
     double ptaua = 0., pomga = 1., pasya = 0.;
     if (fl.iaer == 10) {
@@ -676,6 +710,7 @@ CB_HD void sw_unit(const Tables& T, const Solar& sol, const In& in, const Flags&
       if (MC) {
         const size_t ms = (size_t)W.mstride;
         const unsigned* mw = W.mask + ((size_t)l * 4) * ms + W.moff + c;
+#pragma unroll
         for (int u = 0; u < U; ++u) {
           const int g = gabs + u;
           mbits |= ((mw[(size_t)(g >> 5) * ms] >> (g & 31)) & 1u) << u;
@@ -684,11 +719,13 @@ CB_HD void sw_unit(const Tables& T, const Solar& sol, const In& in, const Flags&
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      double* __restrict__ scr = scr0 + (size_t)u * growstride + (size_t)l * ncc;
+      const double taug = scr[R_TAUG * wstride], taur = scr[R_TAUR * wstride];
       // spcvmc: the sub-column is either overcast with its band's optics or clear (mcica_subcol_gen_sw.f90:523-548)
       const bool on = !MC || ((mbits >> u) & 1u);
       const double pclfr = on ? pclfr_l : 0., ptauc = on ? ptauc_l : 0., pomgc = on ? pomgc_l : 1., pasyc = on ? pasyc_l : 0.;
-      double ztauc = taur[u] + taug[u] + ptaua;
-      double zomcc = taur[u] * 1.0 + ptaua * pomga;
+      double ztauc = taur + taug + ptaua;
+      double zomcc = taur * 1.0 + ptaua * pomga;
       double zgcc = pasya * pomga * ptaua / zomcc;
       zomcc = zomcc / ztauc;
       const double zf = zgcc * zgcc;
@@ -699,7 +736,6 @@ CB_HD void sw_unit(const Tables& T, const Solar& sol, const In& in, const Flags&
       double refc, refdc, trac, tradc;
       reftra(exp_tbl, bpade, zgcc, prmu0, ztauc, zomcc, refc, refdc, trac, tradc);
       const double dbtc = exp_neg(exp_tbl, bpade, ztauc / prmu0);
-      double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
       {
         const double zreflect = 1. / (1. - rupdc[u] * refdc);
         const double rn = refc + (tradc * ((trac - dbtc) * rupdc[u] + dbtc * rupc[u])) * zreflect;
@@ -735,7 +771,7 @@ CB_HD void sw_unit(const Tables& T, const Solar& sol, const In& in, const Flags&
   // ---- pass B: top -> surface.  downward adding and fluxes (vrtqdr.f90:146-169), weighted by the incoming flux
   double zinc[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) zinc[u] = sol.adjflux[ib] * src[u] * prmu0;
+  for (int u = 0; u < U; ++u) zinc[u] = sol.adjflux[ib] * W.src[(size_t)(gabs + u) * ncc + c] * prmu0;
   double tdnc[U], rdndc[U], tdbtc[U], tdn[U], rdnd[U], tdbt[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) { tdnc[u] = 1.; rdndc[u] = 0.; tdbtc[u] = 1.; tdn[u] = 1.; rdnd[u] = 0.; tdbt[u] = 1.; }
@@ -749,7 +785,7 @@ CB_HD void sw_unit(const Tables& T, const Solar& sol, const In& in, const Flags&
       double refc = 0., refdc = 0., trac = 0., tradc = 0., dbtc = 0., prupc = albdir, prupdc = albdif;
       double ref = 0., refd = 0., tra = 0., trad = 0., dbt = 0., prup = albdir, prupd = albdif;
       if (l >= 0) {
-        const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
+        const double* __restrict__ scr = scr0 + (size_t)u * growstride + (size_t)l * ncc;
         refc = scr[0 * wstride]; refdc = scr[1 * wstride]; trac = scr[2 * wstride]; tradc = scr[3 * wstride];
         dbtc = scr[4 * wstride]; prupc = scr[5 * wstride]; prupdc = scr[6 * wstride];
         if (cloudy_col) {
@@ -809,20 +845,23 @@ struct Unit {
   int band, g0, u;  // band = 16..29
 };
 #ifndef CB_SW_UMAX
-#define CB_SW_UMAX 4  // g-points per thread (2 or 4)
+#define CB_SW_UMAX 2      // g-points per thread of the transfer kernel (2 or 4)
+#endif
+#ifndef CB_SW_TAU_UMAX
+#define CB_SW_TAU_UMAX 4  // g-points per thread of the taumol kernel (2 or 4)
 #endif
 constexpr int kMaxUnits = 64;
-inline int build_units(Unit* out) {  // host only
+inline int build_units(Unit* out, int umax) {  // host only
   int n = 0;
   for (int pass = 0; pass < 2; ++pass)
     for (int b = 16; b <= 29; ++b) {
       const bool heavy = kNSPA[b - 16] == 9;
       if ((pass == 0) != heavy) continue;
       const int ng = kNG[b - 16];
-      for (int g0 = 0; g0 < ng; g0 += CB_SW_UMAX) {
+      for (int g0 = 0; g0 < ng; g0 += umax) {
         out[n].band = b;
         out[n].g0 = g0;
-        out[n].u = (ng - g0) >= CB_SW_UMAX ? CB_SW_UMAX : (ng - g0);
+        out[n].u = (ng - g0) >= umax ? umax : (ng - g0);
         ++n;
       }
     }

@@ -16,8 +16,8 @@ using namespace cb::sw;
 
 namespace {
 using cb::kBlock;
-#ifndef CB_UNITS_MIN_BLOCKS
-#define CB_UNITS_MIN_BLOCKS 3
+#ifndef CB_SW_RT_MIN_BLOCKS
+#define CB_SW_RT_MIN_BLOCKS 4  // transfer kernel: 128 registers, no spills (ptxas), 16 warps per SM
 #endif
 
 struct UnitList {
@@ -31,25 +31,47 @@ __global__ void __launch_bounds__(kBlock) k_sw_prep(const __grid_constant__ Tabl
   if (c < n) sw_prep_column(T, in, fl, W, c0, c);
 }
 
-template <bool MC>
-__global__ void __launch_bounds__(kBlock, CB_UNITS_MIN_BLOCKS) k_sw_units(const __grid_constant__ Tables T, const __grid_constant__ Solar sol,
-                                                     const __grid_constant__ In in, const Flags fl,
-                                                     const __grid_constant__ Work W, const __grid_constant__ UnitList UL,
-                                                     int c0, int n) {
+#ifndef CB_SW_TAU_MIN_BLOCKS
+#define CB_SW_TAU_MIN_BLOCKS 4
+#endif
+#ifndef CB_SW_LAYER_CHUNKS
+#define CB_SW_LAYER_CHUNKS 4  // taumol: layers are independent -> blockIdx.z cuts them into chunks for more threads in flight
+#endif
+
+// taumol_sw: one block = 128 adjacent columns x one unit (<= 4 g-points of one band) x one chunk of layers;
+// every branch on the band is block-uniform.
+__global__ void __launch_bounds__(kBlock, CB_SW_TAU_MIN_BLOCKS)
+    k_sw_taumol(const __grid_constant__ Tables T, const __grid_constant__ Solar sol, const __grid_constant__ In in,
+                const __grid_constant__ Work W, const __grid_constant__ UnitList UL, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
-  const int k = blockIdx.y;
-  const Unit un = UL.u[k];
-#define CB_CASE(B)                                                      \
-  case B:                                                               \
-    if (un.u == 4) sw_unit<B, 4, MC>(T, sol, in, fl, W, c0, c, un.g0, k);   \
-    else sw_unit<B, 2, MC>(T, sol, in, fl, W, c0, c, un.g0, k);             \
+  const Unit un = UL.u[blockIdx.y];
+  const int per = (in.nlay + gridDim.z - 1) / gridDim.z;
+  const int l0 = blockIdx.z * per, l1 = min(in.nlay, l0 + per);
+#define CB_CASE(B)                                                           \
+  case B:                                                                    \
+    if (un.u == 4) sw_taumol_unit<B, 4>(T, sol, in, W, c0, c, un.g0, l0, l1); \
+    else sw_taumol_unit<B, 2>(T, sol, in, W, c0, c, un.g0, l0, l1);           \
     break;
   switch (un.band) {
     CB_CASE(16) CB_CASE(17) CB_CASE(18) CB_CASE(19) CB_CASE(20) CB_CASE(21) CB_CASE(22)
     CB_CASE(23) CB_CASE(24) CB_CASE(25) CB_CASE(26) CB_CASE(27) CB_CASE(28) CB_CASE(29)
   }
 #undef CB_CASE
+}
+
+// spcvrt_sw / spcvmc_sw: one block = 128 adjacent columns x one unit (<= CB_SW_UMAX g-points of one band); the same code
+// for every band, so the instruction working set of an SM is one function body.
+template <bool MC>
+__global__ void __launch_bounds__(kBlock, CB_SW_RT_MIN_BLOCKS)
+    k_sw_transfer(const __grid_constant__ Tables T, const __grid_constant__ Solar sol, const __grid_constant__ In in, const Flags fl,
+                  const __grid_constant__ Work W, const __grid_constant__ UnitList UL, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int k = blockIdx.y;
+  const Unit un = UL.u[k];
+  if (CB_SW_UMAX >= 4 && un.u == 4) sw_transfer_unit<4, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, k);
+  else sw_transfer_unit<2, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, k);
 }
 
 __global__ void __launch_bounds__(kBlock) k_sw_mask_kiss(const __grid_constant__ In in, const __grid_constant__ Work W,
@@ -92,11 +114,14 @@ struct cb200_sw_engine {
   unsigned* d_mask_full = nullptr;
   size_t mask_full_cap = 0;
   SolarOptions solar;
-  UnitList UL;
+  UnitList UL;      // transfer kernel units (<= CB_SW_UMAX g-points); `part` holds one flux set per unit
+  UnitList UL_tau;  // taumol kernel units (<= CB_SW_TAU_UMAX g-points)
   int cap_ncc = 0, cap_nlay = 0;
   Work W{};
   int max_chunk = 8192;
   cb::HostPipe pipe;
+  size_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the last host-pointer call
+  bool host_pending = false;
   int* h_err = nullptr;
   std::string error;
   int launches = 0;
@@ -106,7 +131,7 @@ struct cb200_sw_engine {
 
   void free_work() {
     cudaFree(W.ws); cudaFree(W.idx); cudaFree(W.laytrop); cudaFree(W.laysolfr); cudaFree(W.anycld);
-    cudaFree(W.cld); cudaFree(W.aer); cudaFree(W.scr); cudaFree(W.part); cudaFree(W.err); cudaFree(W.mask);
+    cudaFree(W.cld); cudaFree(W.aer); cudaFree(W.scr); cudaFree(W.src); cudaFree(W.part); cudaFree(W.err); cudaFree(W.mask);
     W = Work{};
     cap_ncc = cap_nlay = 0;
   }
@@ -123,6 +148,7 @@ struct cb200_sw_engine {
     CUDA_OK(cudaMalloc(&W.cld, sizeof(double) * 42 * L * n));
     CUDA_OK(cudaMalloc(&W.aer, sizeof(double) * 42 * L * n));
     CUDA_OK(cudaMalloc(&W.scr, sizeof(double) * 112 * NSCR * L * n));
+    CUDA_OK(cudaMalloc(&W.src, sizeof(double) * 112 * n));
     CUDA_OK(cudaMalloc(&W.part, sizeof(double) * UL.n * 4 * (L + 1) * n));
     CUDA_OK(cudaMalloc(&W.mask, sizeof(unsigned) * 4 * L * n));
     CUDA_OK(cudaMalloc(&W.err, sizeof(int)));
@@ -149,7 +175,8 @@ extern "C" int cb200_sw_create(cb200_sw_engine** out, const char* table_blob, co
     ce = cudaMemcpy(e->d_tables, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) throw std::runtime_error(std::string("cudaMemcpy(tables): ") + cudaGetErrorString(ce));
     e->T.base = e->d_tables;
-    e->UL.n = build_units(e->UL.u);
+    e->UL.n = build_units(e->UL.u, CB_SW_UMAX);
+    e->UL_tau.n = build_units(e->UL_tau.u, CB_SW_TAU_UMAX);
     if (const char* mc = std::getenv("CLIMT_B200_MAX_CHUNK")) e->max_chunk = std::max(128, std::atoi(mc));
     cudaMallocHost(&e->h_err, sizeof(int));
     cudaEventCreate(&e->ev0);
@@ -219,12 +246,13 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
   if (mc && e->irng == 0) { k_sw_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
   k_sw_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
   if (e->timing) cudaEventRecord(e->ev0, st);
-  if (mc) k_sw_units<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
-  else k_sw_units<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+  k_sw_taumol<<<dim3(gx, e->UL_tau.n, CB_SW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, sol, in, W, e->UL_tau, c0, n);
+  if (mc) k_sw_transfer<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+  else k_sw_transfer<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
   if (e->timing) cudaEventRecord(e->ev1, st);
   k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, e->UL, out, nlay, out_ncol, c0, n);
   k_sw_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
-  e->launches += 4;
+  e->launches += 5;
   if (e->timing) {
     CUDA_OK(cudaEventSynchronize(e->ev1));
     float ms = 0.f;
@@ -311,12 +339,13 @@ extern "C" int cb200_sw_check(cb200_sw_engine* e) {
 
 // Host-pointer call: column chunks through the three-stream pipeline of cb::HostPipe.  Arrays the option flags make
 // dead are not transferred (cloud inputs when icld = 0; direct cloud optics unless inflag = 0; aerosol arrays by iaer).
-extern "C" int cb200_sw_run_host(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
-                                 const cb200_sw_inputs* hin, const cb200_sw_outputs* hout) {
+extern "C" int cb200_sw_run_host_async(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
+                                       const cb200_sw_inputs* hin, const cb200_sw_outputs* hout) {
   if (ncol <= 0 || nlay <= 0 || nlay > 203) { e->error = "bad ncol/nlay (1 <= nlay <= 203, parrrsw.f90:27)"; return -3; }
   CUDA_OK(cudaSetDevice(e->device));
   cb::HostPipe& P = e->pipe;
   CUDA_OK(P.init());
+  if (e->host_pending) { e->error = "a previous run_host_async call has not been waited for"; return -3; }
   const int L = nlay;
   const int irows[29] = {L, L + 1, L, L + 1, 1, L, L, L, L, L, L, 1, 1, 1, 1, 1, L, L, L, L, L,
                          L, L, L, L, 14 * L, 14 * L, 14 * L, 6 * L};
@@ -336,6 +365,8 @@ extern "C" int cb200_sw_run_host(cb200_sw_engine* e, int ncol, int nlay, double 
   size_t irow_tot = 0, orow_tot = 0;
   for (int i = 0; i < 29; ++i) if (used[i]) irow_tot += (size_t)irows[i] * inner[i];
   for (int i = 0; i < 6; ++i) orow_tot += (size_t)orows[i];
+  e->h2d_bytes = irow_tot * (size_t)ncol * sizeof(double);
+  e->d2h_bytes = orow_tot * (size_t)ncol * sizeof(double);
   int chunk = ncol < P.chunk ? ncol : P.chunk;
   const int wchunk = (chunk + kBlock - 1) / kBlock * kBlock;
   if (e->ensure_work(wchunk, nlay)) return -1;
@@ -384,9 +415,29 @@ extern "C" int cb200_sw_run_host(cb200_sw_engine* e, int ncol, int nlay, double 
     for (int i = 0; i < 6; ++i) CUDA_OK(P.scatter(hop[i], dop[i], orows[i], ncol, c0, n));
     CUDA_OK(cudaEventRecord(P.out_done[s], P.s_out));
   }
-  CUDA_OK(cudaStreamSynchronize(P.s_out));
   CUDA_OK(cudaGetLastError());
+  e->host_pending = true;
+  return 0;
+}
+
+// Completes the call started by cb200_sw_run_host_async: outputs are in the caller's buffers on return.
+extern "C" int cb200_sw_wait(cb200_sw_engine* e) {
+  if (!e->host_pending) return 0;
+  e->host_pending = false;
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->pipe.s_out));
   return cb200_sw_check(e);
+}
+
+extern "C" int cb200_sw_run_host(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
+                                 const cb200_sw_inputs* hin, const cb200_sw_outputs* hout) {
+  if (int rc = cb200_sw_run_host_async(e, ncol, nlay, adjes, dyofyr, solcycfrac, hin, hout)) return rc;
+  return cb200_sw_wait(e);
+}
+
+extern "C" void cb200_sw_last_transfer_bytes(cb200_sw_engine* e, double* h2d, double* d2h) {
+  *h2d = (double)e->h2d_bytes;
+  *d2h = (double)e->d2h_bytes;
 }
 
 // ---- reference-named entry points, one process-global engine

@@ -66,7 +66,8 @@ class LWEngine:
             pass
 
     # -- host buffers (numpy) ------------------------------------------------------------------
-    def run_host(self, ncol, nlay, arrays, out=None):
+    def run_host(self, ncol, nlay, arrays, out=None, wait=True):
+        """wait=False: return as soon as the call is enqueued (overlap with other engines); finish with .wait()."""
         ins, outs = lw_shapes(ncol, nlay)
         keep = []
         pin = _native.LwInputs()
@@ -83,12 +84,33 @@ class LWEngine:
             if a.shape != outs[k] or a.dtype != np.float64 or not a.flags.c_contiguous:
                 raise ValueError(f"output {k}: need C-contiguous float64 {outs[k]}")
             setattr(pout, k, a.ctypes.data_as(_dp))
-        rc = self._L.cb200_lw_run_host(self._h, ncol, nlay, ctypes.byref(pin), ctypes.byref(pout))
+        fn = self._L.cb200_lw_run_host_async if wait is False else self._L.cb200_lw_run_host
+        rc = fn(self._h, ncol, nlay, ctypes.byref(pin), ctypes.byref(pout))
+        if wait is False and rc == 0:
+            self._pending = (keep, out)  # keep the (possibly converted) host buffers alive until wait()
+        if rc == -3:
+            raise ValueError(self._err())
         if rc < 0:
             raise RuntimeError(self._err())
         if rc > 0:
             raise ValueError(self._err())
         return out
+
+    def wait(self):
+        """Complete a run_host(..., wait=False) call: the outputs are filled on return."""
+        rc = self._L.cb200_lw_wait(self._h)
+        pend, self._pending = getattr(self, "_pending", None), None
+        if rc < 0:
+            raise RuntimeError(self._err())
+        if rc > 0:
+            raise ValueError(self._err())
+        return pend[1] if pend else None
+
+    @property
+    def last_transfer_bytes(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self._L.cb200_lw_last_transfer_bytes(self._h, ctypes.byref(a), ctypes.byref(b))
+        return int(a.value), int(b.value)
 
     # -- device buffers (torch CUDA tensors), asynchronous ------------------------------------------
     def run_device(self, ncol, nlay, tensors, out, stream=None):
@@ -178,7 +200,7 @@ class SWEngine:
         except Exception:
             pass
 
-    def run_host(self, ncol, nlay, arrays, out=None, adjes=1.0, dyofyr=0, solcycfrac=0.0):
+    def run_host(self, ncol, nlay, arrays, out=None, adjes=1.0, dyofyr=0, solcycfrac=0.0, wait=True):
         ins, outs = sw_shapes(ncol, nlay)
         keep = []
         pin = _native.SwInputs()
@@ -195,13 +217,33 @@ class SWEngine:
             if a.shape != outs[k] or a.dtype != np.float64 or not a.flags.c_contiguous:
                 raise ValueError(f"output {k}: need C-contiguous float64 {outs[k]}")
             setattr(pout, k, a.ctypes.data_as(_dp))
-        rc = self._L.cb200_sw_run_host(self._h, ncol, nlay, float(adjes), int(dyofyr), float(solcycfrac),
-                                       ctypes.byref(pin), ctypes.byref(pout))
+        fn = self._L.cb200_sw_run_host_async if wait is False else self._L.cb200_sw_run_host
+        rc = fn(self._h, ncol, nlay, float(adjes), int(dyofyr), float(solcycfrac), ctypes.byref(pin), ctypes.byref(pout))
+        if wait is False and rc == 0:
+            self._pending = (keep, out)
+        if rc == -3:
+            raise ValueError(self._err())
         if rc < 0:
             raise RuntimeError(self._err())
         if rc > 0:
             raise ValueError(self._err())
         return out
+
+    def wait(self):
+        """Complete a run_host(..., wait=False) call: the outputs are filled on return."""
+        rc = self._L.cb200_sw_wait(self._h)
+        pend, self._pending = getattr(self, "_pending", None), None
+        if rc < 0:
+            raise RuntimeError(self._err())
+        if rc > 0:
+            raise ValueError(self._err())
+        return pend[1] if pend else None
+
+    @property
+    def last_transfer_bytes(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self._L.cb200_sw_last_transfer_bytes(self._h, ctypes.byref(a), ctypes.byref(b))
+        return int(a.value), int(b.value)
 
     def run_device(self, ncol, nlay, tensors, out, adjes=1.0, dyofyr=0, solcycfrac=0.0, stream=None):
         import torch

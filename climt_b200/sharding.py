@@ -1,0 +1,70 @@
+"""Column sharding across GPUs: every function on the radiation path is column-independent, so the flattened
+(lat x lon) axis is cut into contiguous blocks, one per rank, tables are replicated, and the only communication is one
+all-gather that reassembles the global flux / heating-rate fields.
+
+Host-side logic only (slicing, packing, the collective); it is backend-agnostic so the N > 1 path is exercised with gloo on
+CPU in tests/test_sharding_cpu.py and runs over NCCL in bench.py.
+"""
+import numpy as np
+
+
+def shard_bounds(ncol, world):
+    """Contiguous blocks of ceil(ncol / world) columns; trailing ranks may be short or empty."""
+    per = -(-ncol // world)
+    return [(min(r * per, ncol), min((r + 1) * per, ncol)) for r in range(world)]
+
+
+def column_axis(shape, ncol):
+    """Axis that holds the columns in the engine's layouts: (..., ncol) for level-major fields, (nlev, ncol, nband) for the
+    band-fastest cloud arrays."""
+    if shape and shape[-1] == ncol:
+        return len(shape) - 1
+    if len(shape) == 3 and shape[1] == ncol:
+        return 1
+    raise ValueError(f"no column axis of length {ncol} in shape {shape}")
+
+
+def shard_arrays(arrays, ncol, rank, world):
+    """This rank's block of every array (contiguous copies, so each rank's tensors are dense as the engines require)."""
+    lo, hi = shard_bounds(ncol, world)[rank]
+    out = {}
+    for k, a in arrays.items():
+        a = np.asarray(a)
+        if a.ndim == 0:
+            out[k] = a
+            continue
+        ax = column_axis(a.shape, ncol)
+        out[k] = np.ascontiguousarray(np.take(a, np.arange(lo, hi), axis=ax))
+    return out
+
+
+def pack_rows(tensors, names):
+    """Stack the (rows, ncol_local) output fields into one (total_rows, ncol_local) tensor for a single collective."""
+    import torch
+    return torch.cat([tensors[k].reshape(-1, tensors[k].shape[-1]) for k in names], dim=0)
+
+
+def all_gather_columns(local, names, ncol, group=None):
+    """One all-gather of the packed local outputs; returns {name: (rows..., ncol)} global tensors on every rank.
+    Ranks with short blocks pad to the common width (all_gather needs equal shapes); the padding is trimmed off."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    bounds = shard_bounds(ncol, world)
+    per = bounds[0][1] - bounds[0][0]
+    packed = pack_rows(local, names)
+    rows, nloc = packed.shape
+    if nloc < per:
+        packed = torch.cat([packed, packed.new_zeros((rows, per - nloc))], dim=1)
+    packed = packed.contiguous()
+    flat = packed.new_empty((world * rows, per))  # concatenation along dim 0: the form both NCCL and gloo accept
+    dist.all_gather_into_tensor(flat, packed, group=group)
+    gathered = flat.view(world, rows, per)
+    full = torch.cat([gathered[r, :, : hi - lo] for r, (lo, hi) in enumerate(bounds)], dim=1)
+    out, r0 = {}, 0
+    for k in names:
+        shp = tuple(local[k].shape[:-1])
+        n = int(np.prod(shp)) if shp else 1
+        out[k] = full[r0:r0 + n].reshape(shp + (ncol,))
+        r0 += n
+    return out

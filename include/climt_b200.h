@@ -61,6 +61,13 @@ int cb200_lw_run_device(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_i
 /* Same with host pointers: stages H2D, runs, copies back, synchronises, checks. */
 int cb200_lw_run_host(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* in,
                       const cb200_lw_outputs* out);
+/* The same call split in two: _async returns once every copy and kernel of the call is enqueued (host buffers must stay
+ * valid and, to overlap, be page-locked); cb200_lw_wait blocks until the outputs are in the caller's buffers and reports
+ * input-validation errors like cb200_lw_check.  Lets a caller overlap the LW and SW engines' pipelines. */
+int cb200_lw_run_host_async(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* in, const cb200_lw_outputs* out);
+int cb200_lw_wait(cb200_lw_engine* e);
+/* bytes the last host-pointer call moved over PCIe (arrays the option flags make dead are not transferred) */
+void cb200_lw_last_transfer_bytes(cb200_lw_engine* e, double* h2d, double* d2h);
 /* 0 = ok; >0 = input out of the range the reference accepts (message via cb200_lw_last_error). */
 int cb200_lw_check(cb200_lw_engine* e);
 const char* cb200_lw_last_error(cb200_lw_engine* e);
@@ -113,6 +120,10 @@ int cb200_sw_run_device(cb200_sw_engine* e, int ncol, int nlay, double adjes, in
                         const cb200_sw_inputs* in, const cb200_sw_outputs* out, void* stream);
 int cb200_sw_run_host(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
                       const cb200_sw_inputs* in, const cb200_sw_outputs* out);
+int cb200_sw_run_host_async(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
+                            const cb200_sw_inputs* in, const cb200_sw_outputs* out);
+int cb200_sw_wait(cb200_sw_engine* e);
+void cb200_sw_last_transfer_bytes(cb200_sw_engine* e, double* h2d, double* d2h);
 int cb200_sw_check(cb200_sw_engine* e);
 const char* cb200_sw_last_error(cb200_sw_engine* e);
 int cb200_sw_last_launches(cb200_sw_engine* e);

@@ -11,10 +11,19 @@
 using namespace cb::lw;
 
 template <int B, int U>
-static void run_unit(const Tables& T, const In& in, const Work& W, int n, int g0, int unit, bool mc) {
+static void run_taumol(const Tables& T, const In& in, const Work& W, int n, int g0) {
+  const int cut = in.nlay / 3;  // two layer chunks, like two blockIdx.z slices of the kernel
   for (int c = 0; c < n; ++c) {
-    if (mc) lw_unit<B, U, true>(T, in, W, 0, c, g0, unit);
-    else lw_unit<B, U, false>(T, in, W, 0, c, g0, unit);
+    lw_taumol_unit<B, U>(T, in, W, 0, c, g0, cut, in.nlay);
+    lw_taumol_unit<B, U>(T, in, W, 0, c, g0, 0, cut);
+  }
+}
+
+template <int U>
+static void run_transfer(const Tables& T, const In& in, const Work& W, int n, int ib, int g0, int unit, bool mc) {
+  for (int c = 0; c < n; ++c) {
+    if (mc) lw_transfer_unit<U, true>(T, in, W, 0, c, ib, g0, unit);
+    else lw_transfer_unit<U, false>(T, in, W, 0, c, ib, g0, unit);
   }
 }
 
@@ -39,11 +48,11 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
     const int irng = flags5[6], seed = flags5[7];
     const bool mc = fl.mcica && fl.icld >= 1;
     Unit units[kMaxUnits];
-    const int nunits = build_units(units);
+    const int nunits = build_units(units, CB_LW_UMAX);
     Work W;
     W.ncc = ncol;
     std::vector<double> ws((size_t)NF * nlay * ncol), pw(ncol), cld((size_t)32 * nlay * ncol),
-        scr((size_t)140 * 4 * nlay * ncol), part((size_t)nunits * 4 * (nlay + 1) * ncol);
+        scr((size_t)140 * NSCR * nlay * ncol), part((size_t)nunits * 4 * (nlay + 1) * ncol);
     std::vector<int> idx((size_t)nlay * ncol), lt(ncol), ncb(ncol);
     std::vector<unsigned> mask((size_t)5 * nlay * ncol, 0u);
     int err = 0;
@@ -55,14 +64,21 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
       for (int c = 0; c < ncol; ++c)
         if (cb::mcica::mask_column_kiss(in.play, in.cldfr, ncol, nlay, 140, 5, fl.icld, seed, W.mask, ncol, 0, c)) err = 9;
     for (int c = 0; c < ncol; ++c) prep_column(T, in, fl, W, 0, c);
-    for (int k2 = 0; k2 < nunits; ++k2) {
-      const Unit un = units[k2];
-#define CASE(B) case B: if (un.u == 4) run_unit<B, 4>(T, in, W, ncol, un.g0, k2, mc); else run_unit<B, 2>(T, in, W, ncol, un.g0, k2, mc); break;
+    Unit tunits[kMaxUnits];
+    const int ntau = build_units(tunits, CB_LW_TAU_UMAX);
+    for (int k2 = 0; k2 < ntau; ++k2) {
+      const Unit un = tunits[k2];
+#define CASE(B) case B: if (un.u == 4) run_taumol<B, 4>(T, in, W, ncol, un.g0); else run_taumol<B, 2>(T, in, W, ncol, un.g0); break;
       switch (un.band) {
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
         CASE(14) CASE(15) CASE(16)
       }
 #undef CASE
+    }
+    for (int k2 = 0; k2 < nunits; ++k2) {
+      const Unit un = units[k2];
+      if (un.u == 4) run_transfer<4>(T, in, W, ncol, un.band - 1, un.g0, k2, mc);
+      else run_transfer<2>(T, in, W, ncol, un.band - 1, un.g0, k2, mc);
     }
     for (int c = 0; c < ncol; ++c)
       for (int lev = 0; lev <= nlay; ++lev) lw_reduce_level(T, W, units, nunits, nlay, 0, c, lev, ncol, out);

@@ -9,10 +9,20 @@
 using namespace cb::sw;
 
 template <int B, int U>
-static void run_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int n, int g0, int unit, bool mc) {
+static void run_taumol(const Tables& T, const Solar& sol, const In& in, const Work& W, int n, int g0) {
+  // two layer chunks, like two blockIdx.z slices of the kernel
+  const int half = in.nlay / 2;
   for (int c = 0; c < n; ++c) {
-    if (mc) sw_unit<B, U, true>(T, sol, in, fl, W, 0, c, g0, unit);
-    else sw_unit<B, U, false>(T, sol, in, fl, W, 0, c, g0, unit);
+    sw_taumol_unit<B, U>(T, sol, in, W, 0, c, g0, half, in.nlay);
+    sw_taumol_unit<B, U>(T, sol, in, W, 0, c, g0, 0, half);
+  }
+}
+
+template <int U>
+static void run_transfer(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int n, int ib, int g0, int unit, bool mc) {
+  for (int c = 0; c < n; ++c) {
+    if (mc) sw_transfer_unit<U, true>(T, sol, in, fl, W, 0, c, ib, g0, unit);
+    else sw_transfer_unit<U, false>(T, sol, in, fl, W, 0, c, ib, g0, unit);
   }
 }
 
@@ -41,30 +51,37 @@ extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* 
     for (int i = 0; i < 14; ++i) so.bndsolvar[i] = scal[5 + i];
     Solar sol = compute_solar(so, scal[0], iopt[6], scal[2]);
     Unit units[kMaxUnits];
-    const int nunits = build_units(units);
+    const int nunits = build_units(units, CB_SW_UMAX);
     Work W;
     W.ncc = ncol;
     std::vector<double> ws((size_t)NF * nlay * ncol), cld((size_t)42 * nlay * ncol), aer((size_t)42 * nlay * ncol),
-        scr((size_t)112 * NSCR * nlay * ncol), part((size_t)nunits * 4 * (nlay + 1) * ncol);
+        scr((size_t)112 * NSCR * nlay * ncol), srcv((size_t)112 * ncol), part((size_t)nunits * 4 * (nlay + 1) * ncol);
     std::vector<int> idx((size_t)nlay * ncol), lt(ncol), ls((size_t)14 * ncol), ac(ncol);
     std::vector<unsigned> mask((size_t)4 * nlay * ncol, 0u);
     int err = 0;
     W.mask = mask.data(); W.mstride = ncol; W.moff = 0;
     W.ws = ws.data(); W.idx = idx.data(); W.laytrop = lt.data(); W.laysolfr = ls.data(); W.anycld = ac.data();
-    W.cld = cld.data(); W.aer = aer.data(); W.scr = scr.data(); W.part = part.data(); W.err = &err;
+    W.cld = cld.data(); W.aer = aer.data(); W.scr = scr.data(); W.src = srcv.data(); W.part = part.data(); W.err = &err;
     if (mc && irng == 1) { cb::mcica::mask_mt_host(in.cldfr, ncol, nlay, 112, 4, fl.icld, seed, mask); W.mask = mask.data(); }
     if (mc && irng == 0)
       for (int c = 0; c < ncol; ++c)
         if (cb::mcica::mask_column_kiss(in.play, in.cldfr, ncol, nlay, 112, 4, fl.icld, seed, W.mask, ncol, 0, c)) err = 9;
     for (int c = 0; c < ncol; ++c) sw_prep_column(T, in, fl, W, 0, c);
-    for (int k2 = 0; k2 < nunits; ++k2) {
-      const Unit un = units[k2];
-#define CASE(B) case B: if (un.u == 4) run_unit<B, 4>(T, sol, in, fl, W, ncol, un.g0, k2, mc); else run_unit<B, 2>(T, sol, in, fl, W, ncol, un.g0, k2, mc); break;
+    Unit tunits[kMaxUnits];
+    const int ntau = build_units(tunits, CB_SW_TAU_UMAX);
+    for (int k2 = 0; k2 < ntau; ++k2) {
+      const Unit un = tunits[k2];
+#define CASE(B) case B: if (un.u == 4) run_taumol<B, 4>(T, sol, in, W, ncol, un.g0); else run_taumol<B, 2>(T, sol, in, W, ncol, un.g0); break;
       switch (un.band) {
         CASE(16) CASE(17) CASE(18) CASE(19) CASE(20) CASE(21) CASE(22) CASE(23) CASE(24) CASE(25) CASE(26) CASE(27)
         CASE(28) CASE(29)
       }
 #undef CASE
+    }
+    for (int k2 = 0; k2 < nunits; ++k2) {
+      const Unit un = units[k2];
+      if (un.u == 4) run_transfer<4>(T, sol, in, fl, W, ncol, un.band - 16, un.g0, k2, mc);
+      else run_transfer<2>(T, sol, in, fl, W, ncol, un.band - 16, un.g0, k2, mc);
     }
     for (int c = 0; c < ncol; ++c)
       for (int lev = 0; lev <= nlay; ++lev) sw_reduce_level(W, units, nunits, nlay, 0, c, lev, ncol, out);

@@ -70,3 +70,33 @@ def test_sw_chunked_host_call_equals_device_call(monkeypatch, kw, mode):
     for k in dev:
         np.testing.assert_array_equal(host[k], dev[k], err_msg=k)
     assert np.isfinite(host["dflx"]).all()
+
+
+def test_async_host_calls_overlap_and_match_sync(monkeypatch):
+    """run_host(wait=False) on the LW and SW engines, then wait(): same bits as the synchronous calls; transfer-byte
+    accounting reflects the skipped arrays."""
+    from climt_b200.engine import LWEngine, SWEngine
+    monkeypatch.setenv("CLIMT_B200_HOST_CHUNK", "512")
+    ncol, nlay = 1500, 30
+    abi = H.to_abi(SY.make_lw_state(ncol, nlay, seed=3, clouds=True))
+    abis = H.to_abi_sw(SY.make_sw_state(ncol, nlay, seed=3, clouds=True))
+    lw, sw = LWEngine(), SWEngine()
+    ref_lw = lw.run_host(ncol, nlay, abi)
+    ref_sw = sw.run_host(ncol, nlay, abis, dyofyr=40)
+    out_lw = lw.run_host(ncol, nlay, abi, wait=False)
+    out_sw = sw.run_host(ncol, nlay, abis, dyofyr=40, wait=False)
+    with pytest.raises(ValueError, match="has not been waited for"):
+        lw.run_host(ncol, nlay, abi, wait=False)
+    lw.wait()
+    sw.wait()
+    for k in ref_lw:
+        np.testing.assert_array_equal(out_lw[k], ref_lw[k], err_msg=k)
+        np.testing.assert_array_equal(out_sw[k], ref_sw[k], err_msg=k)
+    h2d, d2h = lw.last_transfer_bytes
+    L, n = nlay, ncol
+    assert h2d == 8 * n * (16 * L + 2 * (L + 1) + 1 + 16 + 16 * L)   # 12 gases/p/T + 4 cloud physics fields; no taucld (inflag=2)
+    assert d2h == 8 * n * (4 * (L + 1) + 2 * L)
+    h2d_sw, _ = sw.last_transfer_bytes
+    assert h2d_sw == 8 * n * (13 * L + 2 * (L + 1) + 6)             # no direct cloud optics, no aerosol arrays (iaer=0)
+    lw.close()
+    sw.close()
