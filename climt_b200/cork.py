@@ -247,6 +247,8 @@ class CorkEngine:
     def solar_flux(self, earth_sun_factor):
         """solar_source_per_gpoint * earth_sun_factor with numpy's dtype rules, as the reference evaluates it
         (cork/sw/component.py:371-372: a float32 table gives a float32 product), handed to the engine as float64."""
+        if "solar_source_per_gpoint" not in self.table:
+            raise ValueError("cork: this table has no solar_source_per_gpoint (not a shortwave table)")
         return np.ascontiguousarray(np.asarray(self.table["solar_source_per_gpoint"]) * float(earth_sun_factor), dtype=np.float64)
 
     def sw_host(self, ncol, nlev, arrays, out=None, earth_sun_factor=1.0, bands=True):

@@ -123,13 +123,18 @@ CB_HD double secdiff_band(double pwvcm, int ib /*0-based*/) {
   return s;
 }
 
-CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Work& W, int c0, int c) {
+// Two launch modes (r01 ncu: the one-thread-per-column version cost as much as a transfer kernel -- 64 blocks on 148 SMs,
+// 60 serial layers): LAYER_PART = inatm + setcoef of layers [l0, l1), independent per layer (one thread per (column, layer));
+// COLUMN_PART = what couples the layers of a column: pwvcm, laytrop, cldprop / cldprmc (whose routine-locals persist from
+// layer to layer in the Fortran) and the rtrn cloud prologue.  <true, true> over [0, nlay) is the original single pass.
+template <bool LAYER_PART, bool COLUMN_PART>
+CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Work& W, int c0, int c, int l0, int l1) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
   const double* tb = T.base;
   const double amd = 28.9660, amw = 18.0160;
   const double stpfac = 296. / 1013.;
-  const bool clouds = fl.icld >= 1;
+  bool clouds = fl.icld >= 1;
   double amttl = 0.0, wvttl = 0.0;
   int laytrop = 0;
   int ncbands = 1;
@@ -139,89 +144,98 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
   double abscoice[16], abscoliq[16];
   for (int i = 0; i < 16; ++i) { abscoice[i] = 0.; abscoliq[i] = 0.; }
   int iceind = 0, liqind = 0;
-  double pz_below = in.plev[gc];  // pz(0)
+  if (COLUMN_PART && clouds) {
+    // no layer reaches the cloud threshold -> nothing downstream reads the cloud optics: skip cldprop altogether
+    bool any = false;
+    for (int l = 0; l < nlay; ++l) any = any || in.cldfr[(size_t)l * ncol + gc] >= (fl.mcica ? 1.e-20 : 1.e-6);
+    clouds = any;
+  }
 #define WS(f, l) W.ws[((size_t)(f) * nlay + (l)) * ncc + c]
-  for (int l = 0; l < nlay; ++l) {
+  for (int l = l0; l < l1; ++l) {
     const size_t o = (size_t)l * ncol + gc;
     const double pavel = in.play[o], tavel = in.tlay[o];
+    const double pz_below = in.plev[o];  // pz(l-1)
     const double pz = in.plev[o + ncol];
     double wkl[7];
     wkl[0] = in.h2o[o]; wkl[1] = in.co2[o]; wkl[2] = in.o3[o]; wkl[3] = in.n2o[o];
     wkl[4] = 0.0; wkl[5] = in.ch4[o]; wkl[6] = in.o2[o];
     const double amm = (1. - wkl[0]) * amd + wkl[0] * amw;
     const double coldry = (pz_below - pz) * 1.e3 * T.avogad / (1.e2 * T.grav * amm * (1. + wkl[0]));
-    pz_below = pz;
     double summol = 0.0;
     for (int i = 1; i < 7; ++i) summol = summol + wkl[i];
     const double wbrodl = coldry * (1. - summol);
     for (int i = 0; i < 7; ++i) wkl[i] = coldry * wkl[i];
-    amttl = amttl + coldry + wkl[0];
-    wvttl = wvttl + wkl[0];
-    WS(F_WX1, l) = coldry * in.ccl4[o] * 1.e-20;
-    WS(F_WX2, l) = coldry * in.cfc11[o] * 1.e-20;
-    WS(F_WX3, l) = coldry * in.cfc12[o] * 1.e-20;
-    WS(F_WX4, l) = coldry * in.cfc22[o] * 1.e-20;
-    // ---- setcoef, rrtmg_lw_setcoef.f90:257-412
-    const double plog = log(pavel);
-    int jp = (int)(CB_MULADD_2R(-5., (plog + 0.04), 36.));
-    if (jp < 1) jp = 1; else if (jp > 58) jp = 58;
-    const double fp = 5. * (tb[T.preflog + jp - 1] - plog);
-    const double tr0 = tb[T.tref + jp - 1], tr1 = tb[T.tref + jp];
-    int jt = (int)(3. + (tavel - tr0) / 15.);
-    if (jt < 1) jt = 1; else if (jt > 4) jt = 4;
-    const double ft = ((tavel - tr0) / 15.) - (double)(jt - 3);
-    int jt1 = (int)(3. + (tavel - tr1) / 15.);
-    if (jt1 < 1) jt1 = 1; else if (jt1 > 4) jt1 = 4;
-    const double ft1 = ((tavel - tr1) / 15.) - (double)(jt1 - 3);
-    const double water = wkl[0] / coldry;
-    const double scalefac = pavel * stpfac / tavel;
-    double forfac = scalefac / (1. + water), forfrac, selffac = water * forfac, selffrac = 0.;
-    int indfor, indself = 1;
-    double factor;
-    if (!(plog <= 4.56)) {
-      laytrop = laytrop + 1;
-      factor = (332.0 - tavel) / 36.0;
-      indfor = imin(2, imax(1, (int)factor));
-      forfrac = factor - (double)indfor;
-      factor = (tavel - 188.0) / 7.2;
-      indself = imin(9, imax(1, (int)factor - 7));
-      selffrac = factor - (double)(indself + 7);
-    } else {
-      factor = (tavel - 188.0) / 36.0;
-      indfor = 3;
-      forfrac = factor - 1.0;
+    if (COLUMN_PART) {
+      amttl = amttl + coldry + wkl[0];
+      wvttl = wvttl + wkl[0];
     }
-    const double scaleminor = pavel / tavel;
-    const double scaleminorn2 = (pavel / tavel) * (wbrodl / (coldry + wkl[0]));
-    factor = (tavel - 180.8) / 7.2;
-    const int indminor = imin(18, imax(1, (int)factor));
-    const double minorfrac = factor - (double)indminor;
-    double colg[7];
-    for (int i = 0; i < 7; ++i) colg[i] = 1.e-20 * wkl[i];
-    if (colg[1] == 0.) colg[1] = 1.e-32 * coldry;
-    if (colg[2] == 0.) colg[2] = 1.e-32 * coldry;
-    if (colg[3] == 0.) colg[3] = 1.e-32 * coldry;
-    if (colg[4] == 0.) colg[4] = 1.e-32 * coldry;
-    if (colg[5] == 0.) colg[5] = 1.e-32 * coldry;
-    const double compfp = 1. - fp;
-    WS(F_FAC10, l) = compfp * ft;
-    WS(F_FAC00, l) = compfp * (1. - ft);
-    WS(F_FAC11, l) = fp * ft1;
-    WS(F_FAC01, l) = fp * (1. - ft1);
-    for (int i = 0; i < 7; ++i) WS(F_COLH2O + i, l) = colg[i];
-    WS(F_COLBRD, l) = 1.e-20 * wbrodl;
-    WS(F_COLDRY, l) = coldry;
-    WS(F_SELFFAC, l) = colg[0] * selffac;
-    WS(F_SELFFRAC, l) = selffrac;
-    WS(F_FORFAC, l) = colg[0] * forfac;
-    WS(F_FORFRAC, l) = forfrac;
-    WS(F_MINORFRAC, l) = minorfrac;
-    WS(F_SCALEMINOR, l) = scaleminor;
-    WS(F_SCALEMINORN2, l) = scaleminorn2;
-    W.idx[(size_t)l * ncc + c] = pack_idx(jp, jt, jt1, indself, indfor, indminor);
+    const double plog = log(pavel);
+    if (COLUMN_PART && !(plog <= 4.56)) laytrop = laytrop + 1;  // rrtmg_lw_setcoef.f90:293
+    double factor = 0.;
+    if (LAYER_PART) {
+      WS(F_WX1, l) = coldry * in.ccl4[o] * 1.e-20;
+      WS(F_WX2, l) = coldry * in.cfc11[o] * 1.e-20;
+      WS(F_WX3, l) = coldry * in.cfc12[o] * 1.e-20;
+      WS(F_WX4, l) = coldry * in.cfc22[o] * 1.e-20;
+      // ---- setcoef, rrtmg_lw_setcoef.f90:257-412
+      int jp = (int)(CB_MULADD_2R(-5., (plog + 0.04), 36.));
+      if (jp < 1) jp = 1; else if (jp > 58) jp = 58;
+      const double fp = 5. * (tb[T.preflog + jp - 1] - plog);
+      const double tr0 = tb[T.tref + jp - 1], tr1 = tb[T.tref + jp];
+      int jt = (int)(3. + (tavel - tr0) / 15.);
+      if (jt < 1) jt = 1; else if (jt > 4) jt = 4;
+      const double ft = ((tavel - tr0) / 15.) - (double)(jt - 3);
+      int jt1 = (int)(3. + (tavel - tr1) / 15.);
+      if (jt1 < 1) jt1 = 1; else if (jt1 > 4) jt1 = 4;
+      const double ft1 = ((tavel - tr1) / 15.) - (double)(jt1 - 3);
+      const double water = wkl[0] / coldry;
+      const double scalefac = pavel * stpfac / tavel;
+      double forfac = scalefac / (1. + water), forfrac, selffac = water * forfac, selffrac = 0.;
+      int indfor, indself = 1;
+      if (!(plog <= 4.56)) {
+        factor = (332.0 - tavel) / 36.0;
+        indfor = imin(2, imax(1, (int)factor));
+        forfrac = factor - (double)indfor;
+        factor = (tavel - 188.0) / 7.2;
+        indself = imin(9, imax(1, (int)factor - 7));
+        selffrac = factor - (double)(indself + 7);
+      } else {
+        factor = (tavel - 188.0) / 36.0;
+        indfor = 3;
+        forfrac = factor - 1.0;
+      }
+      const double scaleminor = pavel / tavel;
+      const double scaleminorn2 = (pavel / tavel) * (wbrodl / (coldry + wkl[0]));
+      factor = (tavel - 180.8) / 7.2;
+      const int indminor = imin(18, imax(1, (int)factor));
+      const double minorfrac = factor - (double)indminor;
+      double colg[7];
+      for (int i = 0; i < 7; ++i) colg[i] = 1.e-20 * wkl[i];
+      if (colg[1] == 0.) colg[1] = 1.e-32 * coldry;
+      if (colg[2] == 0.) colg[2] = 1.e-32 * coldry;
+      if (colg[3] == 0.) colg[3] = 1.e-32 * coldry;
+      if (colg[4] == 0.) colg[4] = 1.e-32 * coldry;
+      if (colg[5] == 0.) colg[5] = 1.e-32 * coldry;
+      const double compfp = 1. - fp;
+      WS(F_FAC10, l) = compfp * ft;
+      WS(F_FAC00, l) = compfp * (1. - ft);
+      WS(F_FAC11, l) = fp * ft1;
+      WS(F_FAC01, l) = fp * (1. - ft1);
+      for (int i = 0; i < 7; ++i) WS(F_COLH2O + i, l) = colg[i];
+      WS(F_COLBRD, l) = 1.e-20 * wbrodl;
+      WS(F_COLDRY, l) = coldry;
+      WS(F_SELFFAC, l) = colg[0] * selffac;
+      WS(F_SELFFRAC, l) = selffrac;
+      WS(F_FORFAC, l) = colg[0] * forfac;
+      WS(F_FORFRAC, l) = forfrac;
+      WS(F_MINORFRAC, l) = minorfrac;
+      WS(F_SCALEMINOR, l) = scaleminor;
+      WS(F_SCALEMINORN2, l) = scaleminorn2;
+      W.idx[(size_t)l * ncc + c] = pack_idx(jp, jt, jt1, indself, indfor, indminor);
+    }
     // ---- McICA: cldprmc (rrtmg_lw_cldprmc.f90:160-247).  Every cloudy sub-column of a layer carries the layer's
     // water paths, so the per-g-point optical depth only depends on the g-point's band: one value per (layer, band).
-    if (clouds && fl.mcica) {
+    if (COLUMN_PART && clouds && fl.mcica) {
       const double cldmin = 1.e-20;
       const double ciwp = in.cicewp[o], clwp = in.cliqwp[o];
       const double* tc = in.taucld ? in.taucld + 16 * ((size_t)l * ncol + gc) : nullptr;  // null = all zero
@@ -278,7 +292,7 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
       ncbands = 16;
     }
     // ---- cldprop for this layer, rrtmg_lw_cldprop.f90:163-270 (taucloud parked in W.cld slot 0)
-    if (clouds && !fl.mcica) {
+    if (COLUMN_PART && clouds && !fl.mcica) {
       double taucloud[16];
       for (int ib = 0; ib < 16; ++ib) taucloud[ib] = 0.0;
       const double cldfrac = in.cldfr[o];
@@ -376,6 +390,7 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
     }
   }
 #undef WS
+  if (!COLUMN_PART) return;
   const double wvsh = (amw * wvttl) / (amd * amttl);
   const double pwvcm = wvsh * (1.e3 * in.plev[gc]) / (1.e2 * T.grav);
   W.pwvcm[c] = pwvcm;
@@ -1003,11 +1018,11 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       if (lev == 1) frac1[u] = plfrac;
     }
     part[1 * pstride + (size_t)(lev - 1) * ncc] = sum_d;
-    part[3 * pstride + (size_t)(lev - 1) * ncc] = sum_dc;
+    if (ncb > 0) part[3 * pstride + (size_t)(lev - 1) * ncc] = sum_dc;  // cloud-free column: clear == total, not stored
   }
   // top of atmosphere: no downward flux
   part[1 * pstride + (size_t)nlay * ncc] = 0.0;
-  part[3 * pstride + (size_t)nlay * ncc] = 0.0;
+  if (ncb > 0) part[3 * pstride + (size_t)nlay * ncc] = 0.0;
   // surface (rtrn.f90:455-470)
   const double tbound = in.tsfc[gc];
   const double semiss = in.emis[(size_t)ib * ncol + gc];
@@ -1025,7 +1040,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       sc = sc + radclru[u];
     }
     part[0] = s;
-    part[2 * pstride] = sc;
+    if (ncb > 0) part[2 * pstride] = sc;
   }
   // upward sweep (rtrn.f90:478-521)
   for (int lev = 1; lev <= nlay; ++lev) {
@@ -1077,7 +1092,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       sc = sc + radclru[u];
     }
     part[(size_t)lev * ncc] = s;
-    part[2 * pstride + (size_t)lev * ncc] = sc;
+    if (ncb > 0) part[2 * pstride + (size_t)lev * ncc] = sc;
   }
 }
 
@@ -1117,17 +1132,20 @@ CB_HD void lw_reduce_level(const Tables& T, const Work& W, const Unit* units, in
   const int ncc = W.ncc;
   const size_t pstride = (size_t)(nlay + 1) * ncc;
   const double wtdiff = 0.5;
+  // cloud-free column: the clear-sky streams equal the total ones bit for bit and were not stored (lw_transfer_unit)
+  const int nq = W.ncbands[c] > 0 ? 4 : 2;
   double tot[4] = {0., 0., 0., 0.};
   for (int b = 1; b <= 16; ++b) {
     double bs[4] = {0., 0., 0., 0.};
     for (int k = 0; k < nunits; ++k) {
       if (units[k].band != b) continue;
       const double* p = W.part + (size_t)k * 4 * pstride + (size_t)lev * ncc + c;
-      for (int q = 0; q < 4; ++q) bs[q] = bs[q] + p[q * pstride];
+      for (int q = 0; q < nq; ++q) bs[q] = bs[q] + p[q * pstride];
     }
     const double dw = CB_LDG(T.base + T.delwave + (b - 1));
-    for (int q = 0; q < 4; ++q) tot[q] = tot[q] + (bs[q] * wtdiff) * dw;
+    for (int q = 0; q < nq; ++q) tot[q] = tot[q] + (bs[q] * wtdiff) * dw;
   }
+  if (nq == 2) { tot[2] = tot[0]; tot[3] = tot[1]; }
   const size_t o = (size_t)lev * ncol + (c0 + c);
   out.uflx[o] = tot[0] * T.fluxfac;
   out.dflx[o] = tot[1] * T.fluxfac;

@@ -22,10 +22,18 @@ using cb::kBlock;
 #define CB_LW_RT_MIN_BLOCKS 6  // transfer kernel: 80 registers, no spills (ptxas), 24 warps per SM
 #endif
 
-__global__ void __launch_bounds__(kBlock) k_prep(const __grid_constant__ Tables T, const __grid_constant__ In in,
-                                                 const Flags fl, const __grid_constant__ Work W, int c0, int n) {
+// inatm + setcoef: one thread per (column, layer)
+__global__ void __launch_bounds__(kBlock) k_prep_layer(const __grid_constant__ Tables T, const __grid_constant__ In in, const Flags fl,
+                                                       const __grid_constant__ Work W, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < n) prep_column(T, in, fl, W, c0, c);
+  const int l = blockIdx.y;
+  if (c < n) prep_column<true, false>(T, in, fl, W, c0, c, l, l + 1);
+}
+// what couples the layers of a column (pwvcm, laytrop, cloud optics): one thread per column
+__global__ void __launch_bounds__(kBlock) k_prep(const __grid_constant__ Tables T, const __grid_constant__ In in, const Flags fl,
+                                                 const __grid_constant__ Work W, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) prep_column<false, true>(T, in, fl, W, c0, c, 0, in.nlay);
 }
 
 struct UnitList {
@@ -245,6 +253,7 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
   const int nlay = in.nlay;
   const int gx = (n + kBlock - 1) / kBlock;
   if (mc && e->irng == 0) { k_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
+  k_prep_layer<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
   k_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
   if (e->timing) cudaEventRecord(e->ev0, st);
   k_lw_taumol<<<dim3(gx, e->UL_tau.n, CB_LW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, in, W, e->UL_tau, c0, n);
@@ -253,7 +262,7 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
   if (e->timing) cudaEventRecord(e->ev1, st);
   k_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(e->T, W, e->UL, out, nlay, out_ncol, c0, n);
   k_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
-  e->launches += 5;
+  e->launches += 6;
   if (e->timing) {
     CUDA_OK(cudaEventSynchronize(e->ev1));
     float ms = 0.f;

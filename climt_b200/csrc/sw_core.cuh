@@ -97,80 +97,92 @@ constexpr int kNSPB[14] = {1, 5, 1, 1, 1, 5, 1, 0, 1, 0, 0, 1, 5, 1};
 // sw_prep_column: inatm_sw (rrtmg_sw_rad.nomcica.f90:1414-1537), setcoef_sw (rrtmg_sw_setcoef.f90:49-305),
 // cldprop_sw (rrtmg_sw_cldprop.f90:53-365), ECMWF aerosol mix (rad.nomcica.f90:693-727), and the layer that supplies
 // each band's solar source (the `laysolfr` logic of rrtmg_sw_taumol.f90, e.g. :334-337 and :586-590).
-CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const Work& W, int c0, int c) {
+// Two launch modes (see lw_core.cuh prep_column): LAYER_PART = inatm_sw + setcoef_sw + the ECMWF aerosol mix of layers
+// [l0, l1), independent per layer; COLUMN_PART = laytrop, cldprop_sw (routine-locals persist from layer to layer in the
+// Fortran), the solar-source layers.  <true, true> over [0, nlay) is the original single pass.
+template <bool LAYER_PART, bool COLUMN_PART>
+CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const Work& W, int c0, int c, int l0, int l1) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
   const double* tb = T.base;
   const double amd = 28.9660, amw = 18.0160;
   const double stpfac = 296. / 1013.;
-  const bool clouds = fl.icld >= 1;
+  bool clouds = fl.icld >= 1;
   int laytrop = 0;
   bool anycld = false;
-  double pz_below = in.plev[gc];
+  if (COLUMN_PART && clouds) {
+    // no cloudy layer -> nothing downstream reads the cloud optics (anycld = 0): skip cldprop_sw altogether
+    bool any = false;
+    for (int l = 0; l < nlay; ++l) any = any || in.cldfr[(size_t)l * ncol + gc] > 1.e-12;
+    clouds = any;
+  }
   // cldprop_sw locals persist across layers like the Fortran routine-locals
   double extcoice[14], gice[14], ssacoice[14], forwice[14], extcoliq[14], gliq[14], ssacoliq[14], forwliq[14];
   for (int i = 0; i < 14; ++i) { extcoice[i] = gice[i] = ssacoice[i] = forwice[i] = extcoliq[i] = gliq[i] = ssacoliq[i] = forwliq[i] = 0.; }
 #define WS(f, l) W.ws[((size_t)(f) * nlay + (l)) * ncc + c]
-  for (int l = 0; l < nlay; ++l) {
+  for (int l = l0; l < l1; ++l) {
     const size_t o = (size_t)l * ncol + gc;
     const double pavel = in.play[o], tavel = in.tlay[o];
+    const double pz_below = in.plev[o];
     const double pz = in.plev[o + ncol];
     double wkl[7];
     wkl[0] = in.h2o[o]; wkl[1] = in.co2[o]; wkl[2] = in.o3[o]; wkl[3] = in.n2o[o]; wkl[4] = 0.; wkl[5] = in.ch4[o]; wkl[6] = in.o2[o];
     const double amm = (1. - wkl[0]) * amd + wkl[0] * amw;
     const double coldry = (pz_below - pz) * 1.e3 * T.avogad / (1.e2 * T.grav * amm * (1. + wkl[0]));
-    pz_below = pz;
     for (int i = 0; i < 7; ++i) wkl[i] = coldry * wkl[i];
     const double plog = log(pavel);
-    int jp = (int)(CB_MULADD_2R(-5., (plog + 0.04), 36.));
-    if (jp < 1) jp = 1; else if (jp > 58) jp = 58;
-    const double fp = 5. * (tb[T.preflog + jp - 1] - plog);
-    const double tr0 = tb[T.tref + jp - 1], tr1 = tb[T.tref + jp];
-    int jt = (int)(3. + (tavel - tr0) / 15.);
-    if (jt < 1) jt = 1; else if (jt > 4) jt = 4;
-    const double ft = ((tavel - tr0) / 15.) - (double)(jt - 3);
-    int jt1 = (int)(3. + (tavel - tr1) / 15.);
-    if (jt1 < 1) jt1 = 1; else if (jt1 > 4) jt1 = 4;
-    const double ft1 = ((tavel - tr1) / 15.) - (double)(jt1 - 3);
-    const double water = wkl[0] / coldry;
-    const double scalefac = pavel * stpfac / tavel;
-    const double forfac = scalefac / (1. + water);
-    double forfrac, selffac = 0., selffrac = 0., factor;
-    int indfor, indself = 0;
-    const bool lower = !(plog <= 4.56);
-    if (lower) {
-      laytrop = laytrop + 1;
-      factor = (332.0 - tavel) / 36.0;
-      indfor = imin(2, imax(1, (int)factor));
-      forfrac = factor - (double)indfor;
-      selffac = water * forfac;
-      factor = (tavel - 188.0) / 7.2;
-      indself = imin(9, imax(1, (int)factor - 7));
-      selffrac = factor - (double)(indself + 7);
-    } else {
-      factor = (tavel - 188.0) / 36.0;
-      indfor = 3;
-      forfrac = factor - 1.0;
+    if (COLUMN_PART && !(plog <= 4.56)) laytrop = laytrop + 1;  // rrtmg_sw_setcoef.f90:218
+    double factor = 0.;
+    if (LAYER_PART) {
+      int jp = (int)(CB_MULADD_2R(-5., (plog + 0.04), 36.));
+      if (jp < 1) jp = 1; else if (jp > 58) jp = 58;
+      const double fp = 5. * (tb[T.preflog + jp - 1] - plog);
+      const double tr0 = tb[T.tref + jp - 1], tr1 = tb[T.tref + jp];
+      int jt = (int)(3. + (tavel - tr0) / 15.);
+      if (jt < 1) jt = 1; else if (jt > 4) jt = 4;
+      const double ft = ((tavel - tr0) / 15.) - (double)(jt - 3);
+      int jt1 = (int)(3. + (tavel - tr1) / 15.);
+      if (jt1 < 1) jt1 = 1; else if (jt1 > 4) jt1 = 4;
+      const double ft1 = ((tavel - tr1) / 15.) - (double)(jt1 - 3);
+      const double water = wkl[0] / coldry;
+      const double scalefac = pavel * stpfac / tavel;
+      const double forfac = scalefac / (1. + water);
+      double forfrac, selffac = 0., selffrac = 0.;
+      int indfor, indself = 0;
+      const bool lower = !(plog <= 4.56);
+      if (lower) {
+        factor = (332.0 - tavel) / 36.0;
+        indfor = imin(2, imax(1, (int)factor));
+        forfrac = factor - (double)indfor;
+        selffac = water * forfac;
+        factor = (tavel - 188.0) / 7.2;
+        indself = imin(9, imax(1, (int)factor - 7));
+        selffrac = factor - (double)(indself + 7);
+      } else {
+        factor = (tavel - 188.0) / 36.0;
+        indfor = 3;
+        forfrac = factor - 1.0;
+      }
+      const double colh2o = 1.e-20 * wkl[0];
+      double colco2 = 1.e-20 * wkl[1];
+      const double colo3 = 1.e-20 * wkl[2];
+      double colch4 = 1.e-20 * wkl[5], colo2 = 1.e-20 * wkl[6];
+      const double colmol = 1.e-20 * coldry + colh2o;
+      if (colco2 == 0.) colco2 = 1.e-32 * coldry;
+      if (colch4 == 0.) colch4 = 1.e-32 * coldry;
+      if (colo2 == 0.) colo2 = 1.e-32 * coldry;
+      const double compfp = 1. - fp;
+      WS(F_FAC10, l) = compfp * ft;
+      WS(F_FAC00, l) = compfp * (1. - ft);
+      WS(F_FAC11, l) = fp * ft1;
+      WS(F_FAC01, l) = fp * (1. - ft1);
+      WS(F_COLH2O, l) = colh2o; WS(F_COLCO2, l) = colco2; WS(F_COLO3, l) = colo3; WS(F_COLCH4, l) = colch4;
+      WS(F_COLO2, l) = colo2; WS(F_COLMOL, l) = colmol;
+      WS(F_SELFFAC, l) = selffac; WS(F_SELFFRAC, l) = selffrac; WS(F_FORFAC, l) = forfac; WS(F_FORFRAC, l) = forfrac;
+      W.idx[(size_t)l * ncc + c] = pack_idx(jp, jt, jt1, indself, indfor);
     }
-    const double colh2o = 1.e-20 * wkl[0];
-    double colco2 = 1.e-20 * wkl[1];
-    const double colo3 = 1.e-20 * wkl[2];
-    double colch4 = 1.e-20 * wkl[5], colo2 = 1.e-20 * wkl[6];
-    const double colmol = 1.e-20 * coldry + colh2o;
-    if (colco2 == 0.) colco2 = 1.e-32 * coldry;
-    if (colch4 == 0.) colch4 = 1.e-32 * coldry;
-    if (colo2 == 0.) colo2 = 1.e-32 * coldry;
-    const double compfp = 1. - fp;
-    WS(F_FAC10, l) = compfp * ft;
-    WS(F_FAC00, l) = compfp * (1. - ft);
-    WS(F_FAC11, l) = fp * ft1;
-    WS(F_FAC01, l) = fp * (1. - ft1);
-    WS(F_COLH2O, l) = colh2o; WS(F_COLCO2, l) = colco2; WS(F_COLO3, l) = colo3; WS(F_COLCH4, l) = colch4;
-    WS(F_COLO2, l) = colo2; WS(F_COLMOL, l) = colmol;
-    WS(F_SELFFAC, l) = selffac; WS(F_SELFFRAC, l) = selffrac; WS(F_FORFAC, l) = forfac; WS(F_FORFRAC, l) = forfrac;
-    W.idx[(size_t)l * ncc + c] = pack_idx(jp, jt, jt1, indself, indfor);
     // ---- cloud optics
-    if (clouds) {
+    if (COLUMN_PART && clouds) {
       const double eps = 1.e-06, cldmin = 1.e-20;
       const double cldfrac = in.cldfr[o];
       if (!fl.mcica && cldfrac > 1.e-06 && cldfrac < T.oneminus) *W.err = 10;  // 'PARTIAL CLOUD NOT ALLOWED' (rad.nomcica.f90:616-620)
@@ -312,7 +324,7 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
       }
     }
     // ---- ECMWF aerosols (iaer = 6), rad.nomcica.f90:693-727
-    if (fl.iaer == 6) {
+    if (LAYER_PART && fl.iaer == 6) {
       for (int ib = 0; ib < 14; ++ib) {
         double ta = 0., om = 0., as = 0.;
         for (int ia = 0; ia < 6; ++ia) {
@@ -334,6 +346,7 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
     }
   }
 #undef WS
+  if (!COLUMN_PART) return;
   W.laytrop[c] = laytrop;
   W.anycld[c] = (clouds && anycld) ? 1 : 0;
   // Layer whose key-species ratio selects each band's solar source function.  The Fortran updates `laysolfr`
@@ -834,8 +847,10 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
       }
     }
     const size_t lev = (size_t)(l + 1);
-    part[0 * pstride + lev * ncc] = sfu;
-    part[1 * pstride + lev * ncc] = sfd;
+    if (cloudy_col) {  // cloud-free column: total == clear, not stored (sw_reduce_level copies)
+      part[0 * pstride + lev * ncc] = sfu;
+      part[1 * pstride + lev * ncc] = sfd;
+    }
     part[2 * pstride + lev * ncc] = scu;
     part[3 * pstride + lev * ncc] = scd;
   }
@@ -873,13 +888,15 @@ CB_HD void sw_reduce_level(const Work& W, const Unit* units, int nunits, int nla
                            const Out& out) {
   const int ncc = W.ncc;
   const size_t pstride = (size_t)(nlay + 1) * ncc;
+  const int q0 = W.anycld[c] != 0 ? 0 : 2;  // cloud-free column: only the clear-sky sums were stored
   double tot[4] = {0., 0., 0., 0.};
   for (int b = 16; b <= 29; ++b)
     for (int k = 0; k < nunits; ++k) {
       if (units[k].band != b) continue;
       const double* p = W.part + (size_t)k * 4 * pstride + (size_t)lev * ncc + c;
-      for (int q = 0; q < 4; ++q) tot[q] = tot[q] + p[q * pstride];
+      for (int q = q0; q < 4; ++q) tot[q] = tot[q] + p[q * pstride];
     }
+  if (q0 == 2) { tot[0] = tot[2]; tot[1] = tot[3]; }
   const size_t o = (size_t)lev * ncol + (c0 + c);
   out.uflx[o] = tot[0];
   out.dflx[o] = tot[1];

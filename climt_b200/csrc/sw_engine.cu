@@ -25,10 +25,18 @@ struct UnitList {
   int n;
 };
 
-__global__ void __launch_bounds__(kBlock) k_sw_prep(const __grid_constant__ Tables T, const __grid_constant__ In in,
-                                                    const Flags fl, const __grid_constant__ Work W, int c0, int n) {
+// inatm_sw + setcoef_sw (+ ECMWF aerosol mix): one thread per (column, layer)
+__global__ void __launch_bounds__(kBlock) k_sw_prep_layer(const __grid_constant__ Tables T, const __grid_constant__ In in, const Flags fl,
+                                                          const __grid_constant__ Work W, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < n) sw_prep_column(T, in, fl, W, c0, c);
+  const int l = blockIdx.y;
+  if (c < n) sw_prep_column<true, false>(T, in, fl, W, c0, c, l, l + 1);
+}
+// what couples the layers of a column (laytrop, cloud optics, solar-source layers): one thread per column
+__global__ void __launch_bounds__(kBlock) k_sw_prep(const __grid_constant__ Tables T, const __grid_constant__ In in, const Flags fl,
+                                                    const __grid_constant__ Work W, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) sw_prep_column<false, true>(T, in, fl, W, c0, c, 0, in.nlay);
 }
 
 #ifndef CB_SW_TAU_MIN_BLOCKS
@@ -244,6 +252,7 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
   const int nlay = in.nlay;
   const int gx = (n + kBlock - 1) / kBlock;
   if (mc && e->irng == 0) { k_sw_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
+  k_sw_prep_layer<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
   k_sw_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
   if (e->timing) cudaEventRecord(e->ev0, st);
   k_sw_taumol<<<dim3(gx, e->UL_tau.n, CB_SW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, sol, in, W, e->UL_tau, c0, n);
@@ -252,7 +261,7 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
   if (e->timing) cudaEventRecord(e->ev1, st);
   k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, e->UL, out, nlay, out_ncol, c0, n);
   k_sw_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
-  e->launches += 5;
+  e->launches += 6;
   if (e->timing) {
     CUDA_OK(cudaEventSynchronize(e->ev1));
     float ms = 0.f;

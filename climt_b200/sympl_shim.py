@@ -92,9 +92,11 @@ except Exception:  # ImportError or a broken install
                     star, star_shape = s, ss
             tend, diag = self.array_call(raw)
 
-            def wrap(arr, prop):
+            def wrap(arr, prop, name=None):
                 dims, shape, k = [], [], 0
-                for d in prop["dims"]:
+                # sympl: a tendency without explicit dims takes the dims of the input quantity of the same name
+                pdims = prop["dims"] if "dims" in prop else self.input_properties[name]["dims"]
+                for d in pdims:
                     if d == "*":
                         dims += list(star)
                         shape += list(star_shape)
@@ -103,7 +105,7 @@ except Exception:  # ImportError or a broken install
                         shape.append(arr.shape[k])
                     k += 1
                 return DataArray(np.asarray(arr).reshape(shape), dims, {"units": prop.get("units", "")})
-            return ({k: wrap(v, self.tendency_properties[k]) for k, v in tend.items()},
+            return ({k: wrap(v, self.tendency_properties[k], k) for k, v in tend.items()},
                     {k: wrap(v, self.diagnostic_properties[k]) for k, v in diag.items()})
 
     def initialize_numpy_arrays_with_properties(output_properties, raw_input_state, input_properties):

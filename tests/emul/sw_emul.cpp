@@ -66,7 +66,9 @@ extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* 
     if (mc && irng == 0)
       for (int c = 0; c < ncol; ++c)
         if (cb::mcica::mask_column_kiss(in.play, in.cldfr, ncol, nlay, 112, 4, fl.icld, seed, W.mask, ncol, 0, c)) err = 9;
-    for (int c = 0; c < ncol; ++c) sw_prep_column(T, in, fl, W, 0, c);
+    for (int c = 0; c < ncol; ++c)
+      for (int l = nlay - 1; l >= 0; --l) sw_prep_column<true, false>(T, in, fl, W, 0, c, l, l + 1);
+    for (int c = 0; c < ncol; ++c) sw_prep_column<false, true>(T, in, fl, W, 0, c, 0, nlay);
     Unit tunits[kMaxUnits];
     const int ntau = build_units(tunits, CB_SW_TAU_UMAX);
     for (int k2 = 0; k2 < ntau; ++k2) {

@@ -94,7 +94,7 @@ def test_async_host_calls_overlap_and_match_sync(monkeypatch):
         np.testing.assert_array_equal(out_sw[k], ref_sw[k], err_msg=k)
     h2d, d2h = lw.last_transfer_bytes
     L, n = nlay, ncol
-    assert h2d == 8 * n * (16 * L + 2 * (L + 1) + 1 + 16 + 16 * L)   # 12 gases/p/T + 4 cloud physics fields; no taucld (inflag=2)
+    assert h2d == 8 * n * (17 * L + 2 * (L + 1) + 1 + 16 + 16 * L)   # 12 p/T/gas + 5 cloud-physics layer fields, emis, tauaer; no taucld (inflag=2)
     assert d2h == 8 * n * (4 * (L + 1) + 2 * L)
     h2d_sw, _ = sw.last_transfer_bytes
     assert h2d_sw == 8 * n * (13 * L + 2 * (L + 1) + 6)             # no direct cloud optics, no aerosol arrays (iaer=0)
