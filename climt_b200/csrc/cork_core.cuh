@@ -363,35 +363,35 @@ CB_HD void sw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
       double tau = tau_abs[u], ssa = 0.0;
       if (Tb.rayleigh) {
         const double tot = tau_abs[u] + tau_ray;
-        ssa = tot > 0 ? tau_ray / tot : 0.0;
+        ssa = tot > 0 ? fdiv(tau_ray, tot) : 0.0;
         tau = tot;
       }
       const double tau_total = tau + tau_c;
       const double scat_gas = tau * ssa, scat_cloud = tau_c * ssa_c;
       const double scat_total = scat_gas + scat_cloud;
-      const double ssa_t = tau_total > 0 ? scat_total / tau_total : 0.0;
-      const double g_t = scat_total > 0 ? (scat_gas * 0.0 + scat_cloud * g_c) / scat_total : 0.0;
+      const double ssa_t = tau_total > 0 ? fdiv(scat_total, tau_total) : 0.0;
+      const double g_t = scat_total > 0 ? fdiv(scat_gas * 0.0 + scat_cloud * g_c, scat_total) : 0.0;
       st += w[u] * tau_total;
       if (night) continue;
       // _delta_scale (sw/kernels.py:18-35)
       const double f = g_t * g_t;
       const double tau_s = tau_total * (1.0 - ssa_t * f);
-      const double w0 = (1.0 - ssa_t * f) > 1e-30 ? ssa_t * (1.0 - f) / (1.0 - ssa_t * f) : 0.0;
-      const double gs = (1.0 - f) > 1e-30 ? (g_t - f) / (1.0 - f) : 0.0;
+      const double w0 = (1.0 - ssa_t * f) > 1e-30 ? fdiv(ssa_t * (1.0 - f), 1.0 - ssa_t * f) : 0.0;
+      const double gs = (1.0 - f) > 1e-30 ? fdiv(g_t - f, 1.0 - f) : 0.0;
       // _sw_dif_and_source (sw/kernels.py:38-118)
       const double gamma1 = (8.0 - w0 * (5.0 + 3.0 * gs)) * 0.25;
       const double gamma2 = 3.0 * (w0 * (1.0 - gs)) * 0.25;
       const double kk = sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), MIN_K));
       const double e1 = exp(-tau_s * kk);
       const double e2 = e1 * e1;
-      const double RT = 1.0 / (kk * (1.0 + e2) + gamma1 * (1.0 - e2));
+      const double RT = frcp(kk * (1.0 + e2) + gamma1 * (1.0 - e2));
       const double Rdif = RT * gamma2 * (1.0 - e2);
       const double Tdif = RT * 2.0 * kk * e1;
-      const double Tnoscat = exp(-tau_s / mu0_s);
+      const double Tnoscat = exp(-fdiv(tau_s, mu0_s));
       const double k_mu = kk * mu0_s;
       double denom_dir = 1.0 - k_mu * k_mu;
       if (fabs(denom_dir) < 1e-30) denom_dir = 1e-30;
-      const double RTd = w0 * RT / denom_dir;
+      const double RTd = fdiv(w0 * RT, denom_dir);
       const double gamma3 = (2.0 - 3.0 * mu0_s * gs) * 0.25;
       const double gamma4 = 1.0 - gamma3;
       const double alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
@@ -423,7 +423,7 @@ CB_HD void sw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
     for (int u = 0; u < U; ++u) {
       double* __restrict__ s = scr + (size_t)(7 * u) * fs + (size_t)l * ncc;
       const double Rdif = s[0 * fs], Tdif = s[1 * fs], src_up = s[2 * fs], src_dn = s[3 * fs];
-      const double denom = 1.0 / (1.0 - Rdif * alb[u]);
+      const double denom = frcp(1.0 - Rdif * alb[u]);
       s[2 * fs] = denom; s[5 * fs] = alb[u]; s[6 * fs] = src[u];
       const double a1 = Rdif + Tdif * Tdif * alb[u] * denom;
       const double s1 = src_up + Tdif * denom * (src[u] + alb[u] * src_dn);

@@ -28,7 +28,7 @@ struct HostPipe {
   double* d_in[2] = {nullptr, nullptr};
   double* d_out[2] = {nullptr, nullptr};
   size_t in_cap = 0, out_cap = 0;
-  int chunk = 4096;
+  int chunk = 2048;  // columns per pipeline chunk (r01 B200 sweep: 1024-2048 best for LW+SW overlapped, 4096 for a lone engine)
 
   cudaError_t init() {
     if (s_in) return cudaSuccess;

@@ -596,17 +596,17 @@ CB_HD void reftra(const double* __restrict__ exp_tbl, double bpade, double zg, d
   const double zgamma2 = 3. * (zw * (1. - zg)) * 0.25;
   const double zgamma3 = (2. - zg3 * prmuz) * 0.25;
   const double zgamma4 = 1. - zgamma3;
-  const double r = zg / (1. - zg);
-  const double zwo = zw / (1. - (1. - zw) * (r * r));
+  const double r = fdiv(zg, 1. - zg);
+  const double zwo = fdiv(zw, 1. - (1. - zw) * (r * r));
   if (zwo >= zwcrit) {
     const double za = zgamma1 * prmuz;
     const double za1 = za - zgamma3;
     const double zgt = zgamma1 * zto1;
-    const double ze1 = fmin(zto1 / prmuz, 500.);
+    const double ze1 = fmin(fdiv(zto1, prmuz), 500.);
     const double ze2 = exp_neg(exp_tbl, bpade, ze1);
-    pref = (zgt - za1 * (1. - ze2)) / (1. + zgt);
+    pref = fdiv(zgt - za1 * (1. - ze2), 1. + zgt);
     ptra = 1. - pref;
-    prefd = zgt / (1. + zgt);
+    prefd = fdiv(zgt, 1. + zgt);
     ptrad = 1. - prefd;
     if (ze2 == 1.0) { pref = 0.0; ptra = 1.0; prefd = 0.0; ptrad = 1.0; }
   } else {
@@ -623,22 +623,22 @@ CB_HD void reftra(const double* __restrict__ exp_tbl, double bpade, double zg, d
     const double zt1 = zrp1 * (za1 + zrk * zgamma4);
     const double zt2 = zrm1 * (za1 - zrk * zgamma4);
     const double zt3 = zrk2 * (zgamma4 + za1 * prmuz);
-    const double zbeta = (zgamma1 - zrk) / zrkg;
+    const double zbeta = fdiv(zgamma1 - zrk, zrkg);
     const double ze1 = fmin(zrk * zto1, 500.);
-    const double ze2 = fmin(zto1 / prmuz, 500.);
-    const double zem1 = exp_neg(exp_tbl, bpade, ze1), zep1 = 1. / zem1;
-    const double zem2 = exp_neg(exp_tbl, bpade, ze2), zep2 = 1. / zem2;
+    const double ze2 = fmin(fdiv(zto1, prmuz), 500.);
+    const double zem1 = exp_neg(exp_tbl, bpade, ze1), zep1 = frcp(zem1);
+    const double zem2 = exp_neg(exp_tbl, bpade, ze2), zep2 = frcp(zem2);
     const double zdenr = zr4 * zep1 + zr5 * zem1;
     const double zdent = zr4 * zep1 + zr5 * zem1;  // zt4 = zr4, zt5 = zr5
     if (zdenr >= -eps && zdenr <= eps) {
       pref = eps;
       ptra = zem2;
     } else {
-      pref = zw * (zr1 * zep1 - zr2 * zem1 - zr3 * zem2) / zdenr;
-      ptra = zem2 - zem2 * zw * (zt1 * zep1 - zt2 * zem1 - zt3 * zep2) / zdent;
+      pref = fdiv(zw * (zr1 * zep1 - zr2 * zem1 - zr3 * zem2), zdenr);
+      ptra = zem2 - fdiv(zem2 * zw * (zt1 * zep1 - zt2 * zem1 - zt3 * zep2), zdent);
     }
     const double zemm = zem1 * zem1;
-    const double zdend = 1. / ((1. - zbeta * zemm) * zrkg);
+    const double zdend = frcp((1. - zbeta * zemm) * zrkg);
     prefd = zgamma2 * (1. - zemm) * zdend;
     ptrad = zrk2 * zem1 * zdend;
   }
@@ -739,18 +739,18 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
       const double pclfr = on ? pclfr_l : 0., ptauc = on ? ptauc_l : 0., pomgc = on ? pomgc_l : 1., pasyc = on ? pasyc_l : 0.;
       double ztauc = taur + taug + ptaua;
       double zomcc = taur * 1.0 + ptaua * pomga;
-      double zgcc = pasya * pomga * ptaua / zomcc;
-      zomcc = zomcc / ztauc;
+      double zgcc = fdiv(pasya * pomga * ptaua, zomcc);
+      zomcc = fdiv(zomcc, ztauc);
       const double zf = zgcc * zgcc;
       const double zwf = zomcc * zf;
       ztauc = (1.0 - zwf) * ztauc;
-      zomcc = (zomcc - zwf) / (1.0 - zwf);
-      zgcc = (zgcc - zf) / (1.0 - zf);
+      zomcc = fdiv(zomcc - zwf, 1.0 - zwf);
+      zgcc = fdiv(zgcc - zf, 1.0 - zf);
       double refc, refdc, trac, tradc;
       reftra(exp_tbl, bpade, zgcc, prmu0, ztauc, zomcc, refc, refdc, trac, tradc);
-      const double dbtc = exp_neg(exp_tbl, bpade, ztauc / prmu0);
+      const double dbtc = exp_neg(exp_tbl, bpade, fdiv(ztauc, prmu0));
       {
-        const double zreflect = 1. / (1. - rupdc[u] * refdc);
+        const double zreflect = frcp(1. - rupdc[u] * refdc);
         const double rn = refc + (tradc * ((trac - dbtc) * rupdc[u] + dbtc * rupc[u])) * zreflect;
         const double rdn = refdc + tradc * tradc * rupdc[u] * zreflect;
         rupc[u] = rn; rupdc[u] = rdn;
@@ -761,8 +761,8 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
         // cloudy (overcast) two-stream of this layer and the cloud-fraction mix (spcvrt.f90:516-588)
         const double ztauo = ztauc + ptauc;
         double zomco = ztauc * zomcc + ptauc * pomgc;
-        const double zgco = (ptauc * pomgc * pasyc + ztauc * zomcc * zgcc) / zomco;
-        zomco = zomco / ztauo;
+        const double zgco = fdiv(ptauc * pomgc * pasyc + ztauc * zomcc * zgcc, zomco);
+        zomco = fdiv(zomco, ztauo);
         double refo = 0., refdo = 0., trao = 1., trado = 1.;
         if (pclfr > 1.e-12) reftra(exp_tbl, bpade, zgco, prmu0, ztauo, zomco, refo, refdo, trao, trado);
         const double zclear = 1.0 - pclfr, zcloud = pclfr;
@@ -770,9 +770,9 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
         const double refd = zclear * refdc + zcloud * refdo;
         const double tra = zclear * trac + zcloud * trao;
         const double trad = zclear * tradc + zcloud * trado;
-        const double dbtmo = exp_neg(exp_tbl, bpade, ztauo / prmu0);
+        const double dbtmo = exp_neg(exp_tbl, bpade, fdiv(ztauo, prmu0));
         const double dbt = zclear * dbtc + zcloud * dbtmo;
-        const double zreflect = 1. / (1. - rupd[u] * refd);
+        const double zreflect = frcp(1. - rupd[u] * refd);
         const double rn = ref + (trad * ((tra - dbt) * rupd[u] + dbt * rup[u])) * zreflect;
         const double rdn = refd + trad * trad * rupd[u] * zreflect;
         rup[u] = rn; rupd[u] = rdn;
@@ -807,7 +807,7 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
         }
       }
       {
-        const double zreflect = 1. / (1. - rdndc[u] * prupdc);
+        const double zreflect = frcp(1. - rdndc[u] * prupdc);
         const double fu = (tdbtc[u] * prupc + (tdnc[u] - tdbtc[u]) * prupdc) * zreflect;
         const double fd = tdbtc[u] + (tdnc[u] - tdbtc[u] + tdbtc[u] * prupc * rdndc[u]) * zreflect;
         scu = scu + zinc[u] * fu;
@@ -818,7 +818,7 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
             tdnc[u] = trac;
             rdndc[u] = refdc;
           } else {
-            const double zr = 1. / (1. - refdc * rdndc[u]);
+            const double zr = frcp(1. - refdc * rdndc[u]);
             const double t = tdbtc[u] * trac + (tradc * ((tdnc[u] - tdbtc[u]) + tdbtc[u] * refc * rdndc[u])) * zr;
             const double rd = refdc + tradc * tradc * rdndc[u] * zr;
             tdnc[u] = t; rdndc[u] = rd;
@@ -827,7 +827,7 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
         }
       }
       if (cloudy_col) {
-        const double zreflect = 1. / (1. - rdnd[u] * prupd);
+        const double zreflect = frcp(1. - rdnd[u] * prupd);
         const double fu = (tdbt[u] * prup + (tdn[u] - tdbt[u]) * prupd) * zreflect;
         const double fd = tdbt[u] + (tdn[u] - tdbt[u] + tdbt[u] * prup * rdnd[u]) * zreflect;
         sfu = sfu + zinc[u] * fu;
@@ -837,7 +837,7 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
             tdn[u] = tra;
             rdnd[u] = refd;
           } else {
-            const double zr = 1. / (1. - refd * rdnd[u]);
+            const double zr = frcp(1. - refd * rdnd[u]);
             const double t = tdbt[u] * tra + (trad * ((tdn[u] - tdbt[u]) + tdbt[u] * ref * rdnd[u])) * zr;
             const double rd = refd + trad * trad * rdnd[u] * zr;
             tdn[u] = t; rdnd[u] = rd;

@@ -16,14 +16,17 @@ from climt_b200.engine import LWEngine, SWEngine, LW_IN, LW_OUT, SW_IN, lw_shape
 
 ncol, nlay = int(os.environ.get("NCOL", 8192)), int(os.environ.get("NLAY", 60))
 clouds = os.environ.get("CLOUDS", "0") == "1"
-st, sts = SY.make_lw_state(ncol, nlay, clouds=clouds), SY.make_sw_state(ncol, nlay, clouds=clouds)
+mcica = os.environ.get("MCICA", "0") == "1"  # BASELINE configs[2]: McICA clouds, kissvec RNG (per-column seeds, generated on the device)
+st = SY.make_lw_state(ncol, nlay, clouds=clouds or mcica)
+sts = SY.make_sw_state(ncol, nlay, clouds=clouds or mcica, overcast_only=not mcica)
 abi, abis = H.to_abi(st), H.to_abi_sw(sts)
 _, outs = lw_shapes(ncol, nlay)
-eng, engs = LWEngine(), SWEngine()
+kw = dict(icld=2, mcica=True, irng=0, permuteseed=112) if mcica else {}
+eng, engs = LWEngine(**kw), SWEngine(**kw)
 d_in = {k: torch.from_numpy(abi[k]).cuda() for k in LW_IN}
 ds_in = {k: torch.from_numpy(abis[k]).cuda() for k in SW_IN}
 d_out = {k: torch.empty(outs[k], dtype=torch.float64, device="cuda") for k in LW_OUT}
-res = {"so": os.environ.get("CLIMT_B200_SO", "default"), "ncol": ncol, "nlay": nlay, "clouds": clouds}
+res = {"so": os.environ.get("CLIMT_B200_SO", "default"), "ncol": ncol, "nlay": nlay, "clouds": clouds, "mcica": mcica}
 for name, fn in (("lw", lambda: eng.run_device(ncol, nlay, d_in, d_out)),
                  ("sw", lambda: engs.run_device(ncol, nlay, ds_in, d_out, dyofyr=1))):
     for _ in range(3):
