@@ -252,9 +252,11 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
                         cudaStream_t st) {
   const int nlay = in.nlay;
   const int gx = (n + kBlock - 1) / kBlock;
-  if (mc && e->irng == 0) { k_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
+  if (mc && e->irng == 0) { k_mask_kiss<<<(n + 31) / 32, 32, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
   k_prep_layer<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
-  k_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
+  // column-serial kernels: one warp per block so that even 8 192 columns spread over every SM
+  const int gw = (n + 31) / 32;
+  k_prep<<<gw, 32, 0, st>>>(e->T, in, e->fl, W, c0, n);
   if (e->timing) cudaEventRecord(e->ev0, st);
   k_lw_taumol<<<dim3(gx, e->UL_tau.n, CB_LW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, in, W, e->UL_tau, c0, n);
   if (mc) k_units<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);

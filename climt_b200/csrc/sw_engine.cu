@@ -17,7 +17,7 @@ using namespace cb::sw;
 namespace {
 using cb::kBlock;
 #ifndef CB_SW_RT_MIN_BLOCKS
-#define CB_SW_RT_MIN_BLOCKS 4  // transfer kernel: 128 registers, no spills (ptxas), 16 warps per SM
+#define CB_SW_RT_MIN_BLOCKS 6  // transfer kernel: 80 registers, 24 warps per SM (r01 B200 sweep: 4 -> 2.55 ms, 5 -> 2.30, 6 -> 2.25)
 #endif
 
 struct UnitList {
@@ -251,9 +251,11 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
                         int out_ncol, bool mc, cudaStream_t st) {
   const int nlay = in.nlay;
   const int gx = (n + kBlock - 1) / kBlock;
-  if (mc && e->irng == 0) { k_sw_mask_kiss<<<gx, kBlock, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
+  if (mc && e->irng == 0) { k_sw_mask_kiss<<<(n + 31) / 32, 32, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
   k_sw_prep_layer<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
-  k_sw_prep<<<gx, kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
+  // column-serial kernels: one warp per block so that even 8 192 columns spread over every SM
+  const int gw = (n + 31) / 32;
+  k_sw_prep<<<gw, 32, 0, st>>>(e->T, in, e->fl, W, c0, n);
   if (e->timing) cudaEventRecord(e->ev0, st);
   k_sw_taumol<<<dim3(gx, e->UL_tau.n, CB_SW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, sol, in, W, e->UL_tau, c0, n);
   if (mc) k_sw_transfer<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
