@@ -28,6 +28,9 @@ WORKLOAD = "RRTMG LW+SW clear-sky, 128x64 columns x 60 levels, fp64 (grid of BAS
 # reference ABI, every array the wrappers read/write, L=60
 ALG_BYTES_LW = (49 * NLAY + 2 * (NLAY + 1) + 17 + 4 * (NLAY + 1) + 2 * NLAY) * 8
 ALG_BYTES_SW = (117 * NLAY + 2 * (NLAY + 1) + 6 + 4 * (NLAY + 1) + 2 * NLAY) * 8
+# measured DRAM bytes (read + write) of one transfer-kernel launch on this grid: filled from the ncu captures under profiles/
+NCU_DRAM_BYTES_LW = 3.821e9   # profiles/r01_lw_transfer_ncu_selected.txt (k_units, 8192 x 60)
+NCU_DRAM_BYTES_SW = 7.351e9   # profiles/r01_sw_transfer_ncu_selected.txt (k_sw_transfer, 8192 x 60)
 
 
 def measured_peaks():
@@ -215,16 +218,19 @@ def main():
     # dominant kernels (g-point units) timed alone with CUDA events on their launch stream
     eng.enable_timing(True)
     engs.enable_timing(True)
-    unit_ms, unit_ms_sw = [], []
+    unit_ms, unit_ms_sw, tau_ms, tau_ms_sw = [], [], [], []
     for _ in range(max(3, min(K, 10))):
         eng.run_device(NCOL, NLAY, d_in, d_out)
         engs.run_device(NCOL, NLAY, ds_in, ds_out, dyofyr=1)
         torch.cuda.synchronize()
         unit_ms.append(eng.last_unit_kernel_ms)
         unit_ms_sw.append(engs.last_unit_kernel_ms)
+        tau_ms.append(eng.last_taumol_kernel_ms)
+        tau_ms_sw.append(engs.last_taumol_kernel_ms)
     eng.enable_timing(False)
     engs.enable_timing(False)
     unit_ms, unit_ms_sw = float(np.mean(unit_ms)), float(np.mean(unit_ms_sw))
+    tau_ms, tau_ms_sw = float(np.mean(tau_ms)), float(np.mean(tau_ms_sw))
 
     # e2e: host buffers in pinned memory through the host-pointer C ABI (H2D + kernels + D2H per step)
     pin_in = {k: torch.from_numpy(abi[k]).pin_memory() for k in LW_IN}
@@ -255,35 +261,40 @@ def main():
     (h2d_lw, d2h_lw), (h2d_sw, d2h_sw) = eng.last_transfer_bytes, engs.last_transfer_bytes
     h2d, d2h = h2d_lw + h2d_sw, d2h_lw + d2h_sw
 
-    t = torch.tensor([ms, e2e_s * 1e3, unit_ms, unit_ms_sw, part_ms["lw"], part_ms["sw"]], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_s * 1e3, unit_ms, unit_ms_sw, part_ms["lw"], part_ms["sw"], tau_ms, tau_ms_sw], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, unit_ms, unit_ms_sw, lw_ms, sw_ms = [float(x) for x in t.tolist()]
+    ms, e2e_ms, unit_ms, unit_ms_sw, lw_ms, sw_ms, tau_ms, tau_ms_sw = [float(x) for x in t.tolist()]
     if rank == 0:
         sampler.stop.set()
         sampler.join(timeout=2)
         peaks, which = measured_peaks()
         value = world * NCOL * K / (ms * 1e-3)
-        dom = "k_sw_units" if unit_ms_sw >= unit_ms else "k_units(lw)"
+        # dominant kernel = the transfer kernel of the slower engine, timed alone with CUDA events on its launch stream
+        sw_dom = unit_ms_sw >= unit_ms
+        dom = "k_sw_transfer" if sw_dom else "k_units (lw transfer)"
         dom_ms = max(unit_ms_sw, unit_ms)
-        dom_bytes = ALG_BYTES_SW if unit_ms_sw >= unit_ms else ALG_BYTES_LW
+        dom_bytes = ALG_BYTES_SW if sw_dom else ALG_BYTES_LW
         achieved = dom_bytes * NCOL / (dom_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at this grid size from the committed `ncu --set full`
+        # captures (profiles/r01_sw_transfer_ncu_selected.txt, profiles/r01_lw_transfer_ncu_selected.txt)
+        traffic = NCU_DRAM_BYTES_SW if sw_dom else NCU_DRAM_BYTES_LW
         line = {
             "metric": "RRTMG LW+SW columns/s (60 lev)", "value": value, "unit": "columns/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "columns_per_gpu": NCOL, "levels": NLAY, "gpoints": "140 LW + 112 SW",
                        "lw_only_columns_per_s": world * NCOL / (lw_ms * 1e-3), "sw_only_columns_per_s": world * NCOL / (sw_ms * 1e-3),
-                       "cache": "working set per step (inputs 0.7 GB + per-g scratch > 5 GB) exceeds the 126 MB L2",
+                       "cache": "working set per step (per-g-point scratch rows > 10 GB, inputs 0.2 GB) exceeds the 126 MB L2: nothing survives between timed iterations",
                        "parallelism": f"columns block-sharded over {world} GPU(s), one all-gather of outputs"},
             "e2e": {"value": world * NCOL * K / (e2e_ms * 1e-3), "unit": "columns/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
                          "kernel": dom, "kernel_ms": dom_ms, "alg_bytes_per_column": dom_bytes,
-                         "lw_units_ms": unit_ms, "sw_units_ms": unit_ms_sw,
-                         "note": "fp64-issue / gather-latency bound, not HBM bound (SURVEY.md 8d)"},
+                         "lw_transfer_ms": unit_ms, "sw_transfer_ms": unit_ms_sw, "lw_taumol_ms": tau_ms, "sw_taumol_ms": tau_ms_sw,
+                         "note": "achieved = algorithmic bytes of the engine call (reference ABI, SURVEY.md 8d) x columns / kernel time; the kernel is bound by its fp64 dependency chain, not HBM (DESIGN.md 3)"},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline and world == 1:

@@ -73,7 +73,7 @@ class SwInputs(ctypes.Structure):
         "cicewp", "cliqwp", "reice", "reliq", "tauaer", "ssaaer", "asmaer", "ecaer")]
 
 
-EXPORTS = ["cb200_lw_run_host_async", "cb200_lw_wait", "cb200_lw_last_transfer_bytes", "cb200_sw_run_host_async", "cb200_sw_wait",
+EXPORTS = ["cb200_lw_last_taumol_kernel_ms", "cb200_sw_last_taumol_kernel_ms", "cb200_lw_run_host_async", "cb200_lw_wait", "cb200_lw_last_transfer_bytes", "cb200_sw_run_host_async", "cb200_sw_wait",
            "cb200_sw_last_transfer_bytes", "cb200_cork_create", "cb200_cork_destroy", "cb200_cork_last_error", "cb200_cork_last_launches", "cb200_cork_enable_timing",
            "cb200_cork_last_unit_kernel_ms", "cb200_cork_lw_run_device", "cb200_cork_sw_run_device", "cb200_cork_lw_run_host",
            "cb200_cork_sw_run_host",
@@ -120,6 +120,10 @@ def lib():
     L.cb200_lw_enable_timing.argtypes = [vp, ctypes.c_int]
     L.cb200_lw_last_unit_kernel_ms.argtypes = [vp]
     L.cb200_lw_last_unit_kernel_ms.restype = ctypes.c_double
+    L.cb200_lw_last_taumol_kernel_ms.argtypes = [vp]
+    L.cb200_lw_last_taumol_kernel_ms.restype = ctypes.c_double
+    L.cb200_sw_last_taumol_kernel_ms.argtypes = [vp]
+    L.cb200_sw_last_taumol_kernel_ms.restype = ctypes.c_double
     L.cb200_sw_create.argtypes = [ctypes.POINTER(vp), ctypes.c_char_p, _dp, ctypes.c_int]
     L.cb200_sw_destroy.argtypes = [vp]
     L.cb200_sw_destroy.restype = None

@@ -20,7 +20,7 @@ using cb::kBlock;
 #define CB_CORK_MIN_BLOCKS 3
 #endif
 #ifndef CB_CORK_UMAX
-#define CB_CORK_UMAX 4  // g-points per thread: largest of {8, 4, 2, 1} <= CB_CORK_UMAX dividing ngpt
+#define CB_CORK_UMAX 8  // g-points per thread: largest of {8, 4, 2, 1} <= CB_CORK_UMAX dividing ngpt (r01 B200: U=8 12.8 ms, U=4 14.4 ms per 65536 x 60 LW call)
 #endif
 
 __global__ void __launch_bounds__(kBlock) k_cork_prep(const __grid_constant__ Table Tb, const Consts K, const __grid_constant__ In in,

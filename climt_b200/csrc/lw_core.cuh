@@ -235,7 +235,7 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
     }
     // ---- McICA: cldprmc (rrtmg_lw_cldprmc.f90:160-247).  Every cloudy sub-column of a layer carries the layer's
     // water paths, so the per-g-point optical depth only depends on the g-point's band: one value per (layer, band).
-    if (COLUMN_PART && clouds && fl.mcica) {
+    if (LAYER_PART && fl.icld >= 1 && fl.mcica) {  // layer-independent: no routine-local survives from layer to layer here
       const double cldmin = 1.e-20;
       const double ciwp = in.cicewp[o], clwp = in.cliqwp[o];
       const double* tc = in.taucld ? in.taucld + 16 * ((size_t)l * ncol + gc) : nullptr;  // null = all zero
@@ -288,8 +288,6 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
         }
         W.cld[((size_t)ib * nlay + l) * ncc + c] = tau;
       }
-      if (in.cldfr[o] >= cldmin) anycld = true;
-      ncbands = 16;
     }
     // ---- cldprop for this layer, rrtmg_lw_cldprop.f90:163-270 (taucloud parked in W.cld slot 0)
     if (COLUMN_PART && clouds && !fl.mcica) {
@@ -391,31 +389,35 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
   }
 #undef WS
   if (!COLUMN_PART) return;
+  if (clouds && fl.mcica) { anycld = true; ncbands = 16; }  // `clouds` already means: some layer has cldfr >= 1e-20 (:247)
   const double wvsh = (amw * wvttl) / (amd * amttl);
   const double pwvcm = wvsh * (1.e3 * in.plev[gc]) / (1.e2 * T.grav);
   W.pwvcm[c] = pwvcm;
   W.laytrop[c] = laytrop;
   W.ncbands[c] = (clouds && anycld) ? ncbands : 0;
-  if (clouds && anycld) {
-    // rtrn prologue, rrtmg_lw_rtrn.f90:300-316 (note: secdiff is indexed by the CLOUD band index there)
-    double secdiff[16];
-    secdiff_all(pwvcm, secdiff);
-    for (int l = 0; l < nlay; ++l) {
-      const double cldfrac = in.cldfr[(size_t)l * ncol + gc];
-      for (int ib = 0; ib < 16; ++ib) {
-        const size_t o0 = ((size_t)ib * nlay + l) * ncc + c;
-        const size_t o1 = ((size_t)(16 + ib) * nlay + l) * ncc + c;
-        if (ib < ncbands && (fl.mcica || cldfrac >= 1.e-6)) {
-          const double od = secdiff[ib] * W.cld[o0];
-          const double transcld = exp(-od);
-          const double abscld = 1. - transcld;
-          W.cld[o0] = od;
-          W.cld[o1] = fl.mcica ? abscld : abscld * cldfrac;  // McICA: efclfrac = abscld * 1 (rtrnmc.f90:307)
-        } else {
-          W.cld[o0] = 0.0;
-          W.cld[o1] = 0.0;
-        }
-      }
+}
+
+// rtrn prologue for one (column, layer), rrtmg_lw_rtrn.f90:300-316: cloud optical depth along the diffusivity angle and
+// effective cloud fraction per cloud band.  Runs after prep_column (needs pwvcm and the column's ncbands).
+// Note: secdiff is indexed by the CLOUD band index there.
+CB_HD void prep_cloud_scale(const In& in, const Flags& fl, const Work& W, int c0, int c, int l) {
+  const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
+  const int ncbands = W.ncbands[c];
+  if (ncbands == 0) return;
+  const double pwvcm = W.pwvcm[c];
+  const double cldfrac = in.cldfr[(size_t)l * ncol + (c0 + c)];
+  for (int ib = 0; ib < 16; ++ib) {
+    const size_t o0 = ((size_t)ib * nlay + l) * ncc + c;
+    const size_t o1 = ((size_t)(16 + ib) * nlay + l) * ncc + c;
+    if (ib < ncbands && (fl.mcica || cldfrac >= 1.e-6)) {
+      const double od = secdiff_band(pwvcm, ib) * W.cld[o0];
+      const double transcld = exp(-od);
+      const double abscld = 1. - transcld;
+      W.cld[o0] = od;
+      W.cld[o1] = fl.mcica ? abscld : abscld * cldfrac;  // McICA: efclfrac = abscld * 1 (rtrnmc.f90:307)
+    } else {
+      W.cld[o0] = 0.0;
+      W.cld[o1] = 0.0;
     }
   }
 }

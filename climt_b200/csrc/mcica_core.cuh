@@ -15,6 +15,8 @@
 namespace cb {
 namespace mcica {
 
+constexpr int kMaxLayers = 203;  // parrrtm.f90:31 / parrrsw.f90:27 (mxlay)
+
 struct Kiss {  // kissvec, mcica_subcol_gen_lw.f90:530-562 (wrap-around 32-bit integer arithmetic)
   unsigned s1, s2, s3, s4;
   CB_HD double next() {
@@ -54,15 +56,20 @@ CB_HD int mask_column_kiss(const double* __restrict__ play, const double* __rest
                            int nsub, int nwords, int icld, int changeSeed, unsigned* __restrict__ mask, int ncc,
                            int c0, int c) {
   const size_t gc = (size_t)(c0 + c);
-  for (int l = 0; l < nlay; ++l)
-    for (int w = 0; w < nwords; ++w) mask[((size_t)l * nwords + w) * ncc + c] = 0u;
-  if (icld == 0) return 0;
-  if (nlay < 4) return 1;
+  if (icld == 0 || nlay < 4 || nlay > kMaxLayers) {
+    for (int l = 0; l < nlay; ++l)
+      for (int w = 0; w < nwords; ++w) mask[((size_t)l * nwords + w) * ncc + c] = 0u;
+    return icld == 0 ? 0 : 1;
+  }
   Kiss k;
   {
     const double p0 = play[gc] * 1.e2, p1 = play[(size_t)ncol + gc] * 1.e2, p2 = play[2 * (size_t)ncol + gc] * 1.e2,
                  p3 = play[3 * (size_t)ncol + gc] * 1.e2;
-    if (p0 < p1) return 1;
+    if (p0 < p1) {
+      for (int l = 0; l < nlay; ++l)
+        for (int w = 0; w < nwords; ++w) mask[((size_t)l * nwords + w) * ncc + c] = 0u;
+      return 1;
+    }
     k.s1 = (unsigned)(int)((p0 - (double)(int)p0) * 1000000000.0);
     k.s2 = (unsigned)(int)((p1 - (double)(int)p1) * 1000000000.0);
     k.s3 = (unsigned)(int)((p2 - (double)(int)p2) * 1000000000.0);
@@ -72,18 +79,26 @@ CB_HD int mask_column_kiss(const double* __restrict__ play, const double* __rest
   ColumnMasker m;
   m.icld = icld;
   const double cldmin = 1.0e-20;
-  for (int s = 0; s < nsub; ++s) {
-    m.begin_subcolumn();
-    double r3 = 0.;
-    if (icld == 3) r3 = k.next();
-    double cf_below = 0.;
-    for (int l = 0; l < nlay; ++l) {
-      double cf = cldfr[(size_t)l * ncol + gc];
-      if (cf < cldmin) cf = 0.;
-      const double r = icld == 3 ? r3 : k.next();
-      if (m.step(r, l, cf, cf_below)) mask[((size_t)l * nwords + (s >> 5)) * ncc + c] |= 1u << (s & 31);
-      cf_below = cf;
+  // The generator is consumed in (sub-column, layer) order, the mask is stored (layer, word): the column's cloud fractions
+  // and the 32 sub-columns of the current word live in thread-local arrays (L1), each mask word is written once.
+  unsigned wd[kMaxLayers];
+  for (int w = 0; w < nwords; ++w) {
+    for (int l = 0; l < nlay; ++l) wd[l] = 0u;
+    const int s1 = (w + 1) * 32 < nsub ? (w + 1) * 32 : nsub;
+    for (int s = w * 32; s < s1; ++s) {
+      m.begin_subcolumn();
+      double r3 = 0.;
+      if (icld == 3) r3 = k.next();
+      double cf_below = 0.;
+      for (int l = 0; l < nlay; ++l) {
+        double cf = cldfr[(size_t)l * ncol + gc];
+        if (cf < cldmin) cf = 0.;
+        const double r = icld == 3 ? r3 : k.next();
+        if (m.step(r, l, cf, cf_below)) wd[l] |= 1u << (s & 31);
+        cf_below = cf;
+      }
     }
+    for (int l = 0; l < nlay; ++l) mask[((size_t)l * nwords + w) * ncc + c] = wd[l];
   }
   return 0;
 }

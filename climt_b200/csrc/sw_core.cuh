@@ -181,8 +181,9 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
       WS(F_SELFFAC, l) = selffac; WS(F_SELFFRAC, l) = selffrac; WS(F_FORFAC, l) = forfac; WS(F_FORFRAC, l) = forfrac;
       W.idx[(size_t)l * ncc + c] = pack_idx(jp, jt, jt1, indself, indfor);
     }
-    // ---- cloud optics
-    if (COLUMN_PART && clouds) {
+    // ---- cloud optics (cldprop_sw / cldprmc_sw): every routine-local is (re)assigned for all 14 bands in each layer that is
+    // entered, for every supported flag combination -> layer-independent
+    if (LAYER_PART && fl.icld >= 1) {
       const double eps = 1.e-06, cldmin = 1.e-20;
       const double cldfrac = in.cldfr[o];
       if (!fl.mcica && cldfrac > 1.e-06 && cldfrac < T.oneminus) *W.err = 10;  // 'PARTIAL CLOUD NOT ALLOWED' (rad.nomcica.f90:616-620)
@@ -316,7 +317,6 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
           }
         }
       }
-      if (cldfrac > 1.e-12) anycld = true;
       for (int ib = 0; ib < 14; ++ib) {
         W.cld[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c] = taucloud[ib];
         W.cld[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c] = ssacloud[ib];
@@ -347,6 +347,7 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
   }
 #undef WS
   if (!COLUMN_PART) return;
+  anycld = clouds;  // `clouds` already means: some layer has cldfr > 1e-12
   W.laytrop[c] = laytrop;
   W.anycld[c] = (clouds && anycld) ? 1 : 0;
   // Layer whose key-species ratio selects each band's solar source function.  The Fortran updates `laysolfr`

@@ -146,6 +146,10 @@ class LWEngine:
         return self._L.cb200_lw_last_unit_kernel_ms(self._h)
 
     @property
+    def last_taumol_kernel_ms(self):
+        return self._L.cb200_lw_last_taumol_kernel_ms(self._h)
+
+    @property
     def last_launches(self):
         return self._L.cb200_lw_last_launches(self._h)
 
@@ -277,6 +281,10 @@ class SWEngine:
     @property
     def last_unit_kernel_ms(self):
         return self._L.cb200_sw_last_unit_kernel_ms(self._h)
+
+    @property
+    def last_taumol_kernel_ms(self):
+        return self._L.cb200_sw_last_taumol_kernel_ms(self._h)
 
     @property
     def last_launches(self):

@@ -77,7 +77,8 @@ int cb200_lw_last_launches(cb200_lw_engine* e);
 /* device time [ms] of the dominant kernel (g-point units) in the last run_host/run_device call when
  * timing was enabled with cb200_lw_enable_timing(e, 1); measured with CUDA events on the launch stream. */
 int cb200_lw_enable_timing(cb200_lw_engine* e, int on);
-double cb200_lw_last_unit_kernel_ms(cb200_lw_engine* e);
+double cb200_lw_last_unit_kernel_ms(cb200_lw_engine* e);   /* transfer kernel (k_units), CUDA events on its launch stream */
+double cb200_lw_last_taumol_kernel_ms(cb200_lw_engine* e); /* k_lw_taumol */
 
 /* ---- reference-named entry points (one process-global engine; tables from $CLIMT_B200_LW_TABLES or
  *      <dir of this library>/../data/_cache/rrtmg_lw_reduced.blob) ---- */
@@ -128,7 +129,8 @@ int cb200_sw_check(cb200_sw_engine* e);
 const char* cb200_sw_last_error(cb200_sw_engine* e);
 int cb200_sw_last_launches(cb200_sw_engine* e);
 int cb200_sw_enable_timing(cb200_sw_engine* e, int on);
-double cb200_sw_last_unit_kernel_ms(cb200_sw_engine* e);
+double cb200_sw_last_unit_kernel_ms(cb200_sw_engine* e);   /* k_sw_transfer */
+double cb200_sw_last_taumol_kernel_ms(cb200_sw_engine* e); /* k_sw_taumol */
 
 void rrtmg_sw_set_constants(double* pi, double* grav, double* planck, double* boltz, double* clight, double* avogad,
                             double* alosmt, double* gascon, double* sbcnst, double* secdy);

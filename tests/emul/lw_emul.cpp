@@ -66,6 +66,9 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
     for (int c = 0; c < ncol; ++c)
       for (int l = nlay - 1; l >= 0; --l) prep_column<true, false>(T, in, fl, W, 0, c, l, l + 1);
     for (int c = 0; c < ncol; ++c) prep_column<false, true>(T, in, fl, W, 0, c, 0, nlay);
+    if (fl.icld >= 1)
+      for (int c = 0; c < ncol; ++c)
+        for (int l = 0; l < nlay; ++l) prep_cloud_scale(in, fl, W, 0, c, l);
     Unit tunits[kMaxUnits];
     const int ntau = build_units(tunits, CB_LW_TAU_UMAX);
     for (int k2 = 0; k2 < ntau; ++k2) {
