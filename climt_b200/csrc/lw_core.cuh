@@ -827,8 +827,8 @@ CB_HD double planck_band(const double* __restrict__ tp /* totplnk row of band */
 //   lw_taumol_unit<B,U>    band-specialised, layers independent: taug and Planck fractions of U g-points (taumol) for a
 //                          chunk of layers -> two scratch rows per g-point
 //   lw_transfer_unit<U,MC> ONE code body for every band: rtrn / rtrnmc (down sweep, surface, up sweep)
-constexpr int NSCR = 2;               // scratch rows per g-point
-constexpr int R_TAU = 0, R_FRAC = 1;  // written by lw_taumol_unit, read by both sweeps of lw_transfer_unit
+constexpr int NSCR = 6;               // scratch rows per g-point
+constexpr int R_TAU = 4, R_FRAC = 5;  // written by lw_taumol_unit (rows 0-3: atrans, bbugas, atot, bbutot of the down sweep)
 
 CB_HD int band_gstart(int ib) {  // first g-point of band ib (0-based), for code that is generic in the band
   switch (ib) {
@@ -862,90 +862,18 @@ CB_HD void lw_taumol_unit(const Tables& T, const In& in, const Work& W, int c0, 
   }
 }
 
-// Layer properties of one g-point (rrtmg_lw_rtrn.f90:343-452): absorptivities and Planck-weighted sources of the gas-only and
-// gas+cloud paths, for the downward (dplankdn) and the upward (dplankup) direction.  Both sweeps call it with the same inputs
-// (the up sweep recomputes instead of re-reading: the transfer kernel is HBM-bound, r01 ncu 60 % of the measured peak, and
-// has issue slots to spare), so they see bit-identical values.
-struct LayerProps {
-  double atrans, bbd, bbugas, gassrc, atot, bbdtot, bbutot;
-};
-CB_HD void lw_layer_props(const double* __restrict__ tau_tbl, const double* __restrict__ et_tbl, double bpade, double plfrac,
-                          double odepth, double blay, double dplankup, double dplankdn, bool cloudy, double odcld, LayerProps& p) {
-  const double rec_6 = 0.166667, tblint = 10000.0;
-  if (cloudy) {
-    double odtot = odepth + odcld;
-    if (odtot < 0.06) {
-      p.atrans = odepth - 0.5 * odepth * odepth;
-      const double odepth_rec = rec_6 * odepth;
-      p.gassrc = plfrac * (blay + dplankdn * odepth_rec) * p.atrans;
-      p.atot = odtot - 0.5 * odtot * odtot;
-      const double odtot_rec = rec_6 * odtot;
-      p.bbdtot = plfrac * (blay + dplankdn * odtot_rec);
-      p.bbd = plfrac * (blay + dplankdn * odepth_rec);
-      p.bbugas = plfrac * (blay + dplankup * odepth_rec);
-      p.bbutot = plfrac * (blay + dplankup * odtot_rec);
-    } else if (odepth <= 0.06) {
-      p.atrans = odepth - 0.5 * odepth * odepth;
-      const double odepth_rec = rec_6 * odepth;
-      p.gassrc = plfrac * (blay + dplankdn * odepth_rec) * p.atrans;
-      odtot = odepth + odcld;
-      const double tblind = odtot / (bpade + odtot);
-      const int ittot = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
-      const Row<2> ett = ldrow<2>(et_tbl + 2 * ittot);
-      const double tfactot = ett[1];
-      p.bbdtot = plfrac * (blay + tfactot * dplankdn);
-      p.bbd = plfrac * (blay + dplankdn * odepth_rec);
-      p.atot = 1. - ett[0];
-      p.bbugas = plfrac * (blay + dplankup * odepth_rec);
-      p.bbutot = plfrac * (blay + tfactot * dplankup);
-    } else {
-      double tblind = odepth / (bpade + odepth);
-      const int itgas = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
-      odepth = CB_LDG(tau_tbl + itgas);
-      const Row<2> etg = ldrow<2>(et_tbl + 2 * itgas);
-      p.atrans = 1. - etg[0];
-      const double tfacgas = etg[1];
-      p.gassrc = p.atrans * plfrac * (blay + tfacgas * dplankdn);
-      odtot = odepth + odcld;
-      tblind = odtot / (bpade + odtot);
-      const int ittot = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
-      const Row<2> ett = ldrow<2>(et_tbl + 2 * ittot);
-      const double tfactot = ett[1];
-      p.bbdtot = plfrac * (blay + tfactot * dplankdn);
-      p.bbd = plfrac * (blay + tfacgas * dplankdn);
-      p.atot = 1. - ett[0];
-      p.bbugas = plfrac * (blay + tfacgas * dplankup);
-      p.bbutot = plfrac * (blay + tfactot * dplankup);
-    }
-  } else {
-    if (odepth <= 0.06) {
-      p.atrans = odepth - 0.5 * odepth * odepth;
-      odepth = rec_6 * odepth;
-      p.bbd = plfrac * (blay + dplankdn * odepth);
-      p.bbugas = plfrac * (blay + dplankup * odepth);
-    } else {
-      const double tblind = odepth / (bpade + odepth);
-      const int itr = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
-      const Row<2> et = ldrow<2>(et_tbl + 2 * itr);
-      const double transc = et[0];
-      p.atrans = 1. - transc;
-      const double tausfac = et[1];
-      p.bbd = plfrac * (blay + tausfac * dplankdn);
-      p.bbugas = plfrac * (blay + tausfac * dplankup);
-    }
-    p.gassrc = 0.; p.atot = 0.; p.bbdtot = 0.; p.bbutot = 0.;
-  }
-}
-
 // rtrn / rtrnmc for U consecutive g-points of band ib (0-based) -- generic in the band (rrtmg_lw_rtrn.f90:300-557)
 template <int U, bool MC>
 CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int ib, int g0, int unit) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
   const double* __restrict__ tb = T.base;
-  const double bpade = T.bpade;
+  const double rec_6 = 0.166667, tblint = 10000.0, bpade = T.bpade;
   const double* __restrict__ tau_tbl = tb + T.tau_tbl;
+  const double* __restrict__ exp_tbl = tb + T.exp_tbl;
+  const double* __restrict__ tfn_tbl = tb + T.tfn_tbl;
   const double* __restrict__ et_tbl = tb + T.et_tbl;
+  (void)exp_tbl; (void)tfn_tbl;
   const double* __restrict__ tp = tb + T.totplnk + (size_t)ib * 181;
   const size_t wstride = (size_t)nlay * ncc;
   const int ncb = W.ncbands[c];
@@ -959,51 +887,12 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
     ibc = ib;
   }
   const int gabs = band_gstart(ib) + g0;  // absolute g-point of u = 0
-  const double* __restrict__ scr0 = W.scr + ((size_t)gabs * NSCR) * wstride + c;
-  const size_t gstride = (size_t)NSCR * wstride;
-  double* __restrict__ part = W.part + (size_t)unit * 4 * (nlay + 1) * ncc + c;
-  const size_t pstride = (size_t)(nlay + 1) * ncc;
-
-  // cloud state of layer l for this unit: cloudy flag, sub-column bits (McICA), band cloud optics
-  struct Cloud {
-    bool cloudy;
-    unsigned mbits;
-    double odcld, efclfrac, cldfrac;
-  };
-  auto cloud_of = [&](int l) {
-    Cloud k{false, 0u, 0., 0., 0.};
-    const size_t o = (size_t)l * ncol + gc;
-    // non-McICA: a layer is cloudy when its cloud fraction is >= 1e-6 (rtrn.f90:302); McICA: when ANY sub-column of the
-    // layer is cloudy (rtrnmc.f90:298-309), each g-point then sees cloud fraction 0 or 1.
-    if (MC) {
-      if (ncb > 0) {
-        const size_t ms = (size_t)W.mstride;
-        const unsigned* mw = W.mask + ((size_t)l * 5) * ms + W.moff + c;
-        const unsigned w0 = mw[0], w1 = mw[ms], w2 = mw[2 * ms], w3 = mw[3 * ms], w4 = mw[4 * ms];
-        k.cloudy = (w0 | w1 | w2 | w3 | w4) != 0u;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int g = gabs + u;
-          const unsigned w = (g >> 5) == 0 ? w0 : ((g >> 5) == 1 ? w1 : ((g >> 5) == 2 ? w2 : ((g >> 5) == 3 ? w3 : w4)));
-          k.mbits |= ((w >> (g & 31)) & 1u) << u;
-        }
-      }
-    } else {
-      k.cloudy = ncb > 0 && in.cldfr[o] >= 1.e-6;
-    }
-    if (k.cloudy) {
-      k.cldfrac = MC ? 1.0 : in.cldfr[o];
-      k.odcld = W.cld[((size_t)ibc * nlay + l) * ncc + c];
-      k.efclfrac = W.cld[((size_t)(16 + ibc) * nlay + l) * ncc + c];
-    }
-    return k;
-  };
-
-  // ---- downward sweep (rtrn.f90:320-452)
   double radld[U], radclrd[U], frac1[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) { radld[u] = 0.; radclrd[u] = 0.; frac1[u] = 0.; }
   int iclddn = 0;
+  double* __restrict__ part = W.part + (size_t)unit * 4 * (nlay + 1) * ncc + c;
+  const size_t pstride = (size_t)(nlay + 1) * ncc;
   double plev_up = planck_band(tp, in.tlev[(size_t)nlay * ncol + gc]);  // planklev(nlay)
   for (int lev = nlay; lev >= 1; --lev) {
     const int l = lev - 1;
@@ -1014,27 +903,116 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
     const double dplankup = plev_up - blay;
     const double dplankdn = plev_dn - blay;
     plev_up = plev_dn;
-    const Cloud k = cloud_of(l);
-    if (k.cloudy) iclddn = 1;
+    // non-McICA: a layer is cloudy when its cloud fraction is >= 1e-6 (rtrn.f90:302); McICA: when ANY sub-column
+    // of the layer is cloudy (rtrnmc.f90:298-309), each g-point then sees cloud fraction 0 or 1.
+    bool cloudy;
+    unsigned mbits = 0u;
+    double odcld_l = 0., efclfrac_l = 0., cldfrac_l = 0.;
+    if (MC) {
+      cloudy = false;
+      if (ncb > 0) {
+        const size_t ms = (size_t)W.mstride;
+        const unsigned* mw = W.mask + ((size_t)l * 5) * ms + W.moff + c;
+        const unsigned w0 = mw[0], w1 = mw[ms], w2 = mw[2 * ms], w3 = mw[3 * ms], w4 = mw[4 * ms];
+        cloudy = (w0 | w1 | w2 | w3 | w4) != 0u;
+        // the unit's <= 4 g-points never straddle a 32-bit word boundary twice; fetch their bits
+        for (int u = 0; u < U; ++u) {
+          const int g = gabs + u;
+          const unsigned w = (g >> 5) == 0 ? w0 : ((g >> 5) == 1 ? w1 : ((g >> 5) == 2 ? w2 : ((g >> 5) == 3 ? w3 : w4)));
+          mbits |= ((w >> (g & 31)) & 1u) << u;
+        }
+      }
+    } else {
+      cloudy = ncb > 0 && in.cldfr[o] >= 1.e-6;
+    }
+    if (cloudy) {
+      iclddn = 1;
+      cldfrac_l = MC ? 1.0 : in.cldfr[o];
+      odcld_l = W.cld[((size_t)ibc * nlay + l) * ncc + c];
+      efclfrac_l = W.cld[((size_t)(16 + ibc) * nlay + l) * ncc + c];
+    }
     double sum_d = 0., sum_dc = 0.;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const bool on = !MC || ((k.mbits >> u) & 1u);
-      const double odcld = on ? k.odcld : 0., efclfrac = on ? k.efclfrac : 0., cldfrac = on ? k.cldfrac : 0.;
-      const double* __restrict__ scr = scr0 + (size_t)u * gstride + (size_t)l * ncc;
+      const bool on = !MC || ((mbits >> u) & 1u);
+      const double odcld = on ? odcld_l : 0., efclfrac = on ? efclfrac_l : 0., cldfrac = on ? cldfrac_l : 0.;
+      double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
       const double plfrac = scr[R_FRAC * wstride];
       double odepth = secdiff * (scr[R_TAU * wstride] + taua);
       if (odepth < 0.0) odepth = 0.0;
-      LayerProps p;
-      lw_layer_props(tau_tbl, et_tbl, bpade, plfrac, odepth, blay, dplankup, dplankdn, k.cloudy, odcld, p);
-      if (k.cloudy) {
-        radld[u] = radld[u] - radld[u] * (p.atrans + efclfrac * (1. - p.atrans)) + p.gassrc + cldfrac * (p.bbdtot * p.atot - p.gassrc);
+      double atrans, bbd, bbugas;
+      if (cloudy) {
+        double odtot = odepth + odcld;
+        double gassrc, bbdtot, atot, bbutot;
+        if (odtot < 0.06) {
+          atrans = odepth - 0.5 * odepth * odepth;
+          const double odepth_rec = rec_6 * odepth;
+          gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
+          atot = odtot - 0.5 * odtot * odtot;
+          const double odtot_rec = rec_6 * odtot;
+          bbdtot = plfrac * (blay + dplankdn * odtot_rec);
+          bbd = plfrac * (blay + dplankdn * odepth_rec);
+          bbugas = plfrac * (blay + dplankup * odepth_rec);
+          bbutot = plfrac * (blay + dplankup * odtot_rec);
+        } else if (odepth <= 0.06) {
+          atrans = odepth - 0.5 * odepth * odepth;
+          const double odepth_rec = rec_6 * odepth;
+          gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
+          odtot = odepth + odcld;
+          const double tblind = odtot / (bpade + odtot);
+          const int ittot = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
+          const Row<2> ett = ldrow<2>(et_tbl + 2 * ittot);
+          const double tfactot = ett[1];
+          bbdtot = plfrac * (blay + tfactot * dplankdn);
+          bbd = plfrac * (blay + dplankdn * odepth_rec);
+          atot = 1. - ett[0];
+          bbugas = plfrac * (blay + dplankup * odepth_rec);
+          bbutot = plfrac * (blay + tfactot * dplankup);
+        } else {
+          double tblind = odepth / (bpade + odepth);
+          const int itgas = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
+          odepth = CB_LDG(tau_tbl + itgas);
+          const Row<2> etg = ldrow<2>(et_tbl + 2 * itgas);
+          atrans = 1. - etg[0];
+          const double tfacgas = etg[1];
+          gassrc = atrans * plfrac * (blay + tfacgas * dplankdn);
+          odtot = odepth + odcld;
+          tblind = odtot / (bpade + odtot);
+          const int ittot = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
+          const Row<2> ett = ldrow<2>(et_tbl + 2 * ittot);
+          const double tfactot = ett[1];
+          bbdtot = plfrac * (blay + tfactot * dplankdn);
+          bbd = plfrac * (blay + tfacgas * dplankdn);
+          atot = 1. - ett[0];
+          bbugas = plfrac * (blay + tfacgas * dplankup);
+          bbutot = plfrac * (blay + tfactot * dplankup);
+        }
+        radld[u] = radld[u] - radld[u] * (atrans + efclfrac * (1. - atrans)) + gassrc + cldfrac * (bbdtot * atot - gassrc);
+        scr[2 * wstride] = atot;
+        scr[3 * wstride] = bbutot;
       } else {
-        radld[u] = radld[u] + (p.bbd - radld[u]) * p.atrans;
+        if (odepth <= 0.06) {
+          atrans = odepth - 0.5 * odepth * odepth;
+          odepth = rec_6 * odepth;
+          bbd = plfrac * (blay + dplankdn * odepth);
+          bbugas = plfrac * (blay + dplankup * odepth);
+        } else {
+          const double tblind = odepth / (bpade + odepth);
+          const int itr = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
+          const Row<2> et = ldrow<2>(et_tbl + 2 * itr);
+          const double transc = et[0];
+          atrans = 1. - transc;
+          const double tausfac = et[1];
+          bbd = plfrac * (blay + tausfac * dplankdn);
+          bbugas = plfrac * (blay + tausfac * dplankup);
+        }
+        radld[u] = radld[u] + (bbd - radld[u]) * atrans;
       }
+      scr[0] = atrans;
+      scr[wstride] = bbugas;
       sum_d = sum_d + radld[u];
       if (iclddn == 1) {
-        radclrd[u] = radclrd[u] + (p.bbd - radclrd[u]) * p.atrans;
+        radclrd[u] = radclrd[u] + (bbd - radclrd[u]) * atrans;
       } else {
         radclrd[u] = radld[u];
       }
@@ -1047,7 +1025,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
   // top of atmosphere: no downward flux
   part[1 * pstride + (size_t)nlay * ncc] = 0.0;
   if (ncb > 0) part[3 * pstride + (size_t)nlay * ncc] = 0.0;
-  // ---- surface (rtrn.f90:455-470)
+  // surface (rtrn.f90:455-470)
   const double tbound = in.tsfc[gc];
   const double semiss = in.emis[(size_t)ib * ncol + gc];
   const double plankbnd = semiss * planck_band(tp, tbound);
@@ -1066,35 +1044,50 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
     part[0] = s;
     if (ncb > 0) part[2 * pstride] = sc;
   }
-  // ---- upward sweep (rtrn.f90:478-521); layer properties recomputed from the same taug / fracs rows
+  // upward sweep (rtrn.f90:478-521)
   for (int lev = 1; lev <= nlay; ++lev) {
     const int l = lev - 1;
     const size_t o = (size_t)l * ncol + gc;
-    const double taua = in.tauaer[((size_t)ib * nlay + l) * ncol + gc];
-    const double blay = planck_band(tp, in.tlay[o]);
-    const double dplankup = planck_band(tp, in.tlev[o + ncol]) - blay;  // planklev(lev) - planklay(lev)
-    const double dplankdn = planck_band(tp, in.tlev[o]) - blay;         // planklev(lev-1) - planklay(lev)
-    const Cloud k = cloud_of(l);
+    bool cloudy;
+    unsigned mbits = 0u;
+    if (MC) {
+      cloudy = false;
+      if (ncb > 0) {
+        const size_t ms = (size_t)W.mstride;
+        const unsigned* mw = W.mask + ((size_t)l * 5) * ms + W.moff + c;
+        const unsigned w0 = mw[0], w1 = mw[ms], w2 = mw[2 * ms], w3 = mw[3 * ms], w4 = mw[4 * ms];
+        cloudy = (w0 | w1 | w2 | w3 | w4) != 0u;
+        for (int u = 0; u < U; ++u) {
+          const int g = gabs + u;
+          const unsigned w = (g >> 5) == 0 ? w0 : ((g >> 5) == 1 ? w1 : ((g >> 5) == 2 ? w2 : ((g >> 5) == 3 ? w3 : w4)));
+          mbits |= ((w >> (g & 31)) & 1u) << u;
+        }
+      }
+    } else {
+      cloudy = ncb > 0 && in.cldfr[o] >= 1.e-6;
+    }
+    double efclfrac_l = 0., cldfrac_l = 0.;
+    if (cloudy) {
+      cldfrac_l = MC ? 1.0 : in.cldfr[o];
+      efclfrac_l = W.cld[((size_t)(16 + ibc) * nlay + l) * ncc + c];
+    }
     double s = 0., sc = 0.;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const bool on = !MC || ((k.mbits >> u) & 1u);
-      const double odcld = on ? k.odcld : 0., efclfrac = on ? k.efclfrac : 0., cldfrac = on ? k.cldfrac : 0.;
-      const double* __restrict__ scr = scr0 + (size_t)u * gstride + (size_t)l * ncc;
-      const double plfrac = scr[R_FRAC * wstride];
-      double odepth = secdiff * (scr[R_TAU * wstride] + taua);
-      if (odepth < 0.0) odepth = 0.0;
-      LayerProps p;
-      lw_layer_props(tau_tbl, et_tbl, bpade, plfrac, odepth, blay, dplankup, dplankdn, k.cloudy, odcld, p);
-      if (k.cloudy) {
-        const double gassrc = p.bbugas * p.atrans;
-        radlu[u] = radlu[u] - radlu[u] * (p.atrans + efclfrac * (1. - p.atrans)) + gassrc + cldfrac * (p.bbutot * p.atot - gassrc);
+      const bool on = !MC || ((mbits >> u) & 1u);
+      const double efclfrac = on ? efclfrac_l : 0., cldfrac = on ? cldfrac_l : 0.;
+      const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
+      const double atrans = scr[0], bbugas = scr[wstride];
+      if (cloudy) {
+        const double atot = scr[2 * wstride], bbutot = scr[3 * wstride];
+        const double gassrc = bbugas * atrans;
+        radlu[u] = radlu[u] - radlu[u] * (atrans + efclfrac * (1. - atrans)) + gassrc + cldfrac * (bbutot * atot - gassrc);
       } else {
-        radlu[u] = radlu[u] + (p.bbugas - radlu[u]) * p.atrans;
+        radlu[u] = radlu[u] + (bbugas - radlu[u]) * atrans;
       }
       s = s + radlu[u];
       if (iclddn == 1) {
-        radclru[u] = radclru[u] + (p.bbugas - radclru[u]) * p.atrans;
+        radclru[u] = radclru[u] + (bbugas - radclru[u]) * atrans;
       } else {
         radclru[u] = radlu[u];
       }
