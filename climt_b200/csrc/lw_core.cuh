@@ -73,8 +73,9 @@ struct Work {  // all sized for a chunk of ncc columns
   int* ncbands;  // [ncc]   0 = column has no cloudy layer
   double* pwvcm; // [ncc]
   double* cld;   // [2][16][nlay][ncc]  odcld, efclfrac
-  double* scr;   // [140][4][nlay][ncc] atrans, bbugas, atot, bbutot
+  double* scr;   // [140][NSCR][nlay][ncc] atrans, bbugas, atot, bbutot, taug, fracs
   double* part;  // [nunits][4][nlay+1][ncc] up, dn, upclr, dnclr  (un-weighted sums over the unit's g-points)
+  double* ovl;   // [14][nlay+2][ncc] maximum-random overlap factors of rtrnmr (OV_* rows), non-McICA icld = 2, 3 only
   unsigned* mask; // [nlay][5][mstride] McICA cloud mask (+ moff), bit (g & 31) of word (g >> 5) set = sub-column g cloudy
   int mstride, moff;
   int* err;      // [1]
@@ -102,6 +103,8 @@ CB_HD void secdiff_all(double pwvcm, double* secdiff /*[16]*/) {
     }
   }
 }
+CB_HD double fmax2(double a, double b) { return a > b ? a : b; }
+CB_HD double fmin2(double a, double b) { return a < b ? a : b; }
 CB_HD double secdiff_band(double pwvcm, int ib /*0-based*/) {
   // a0 + a1*exp(a2*pwvcm) clamped to [1.5, 1.8] for bands 2-3 and 5-9, 1.66 otherwise (rrtmg_lw_rtrn.f90:246-270).
   // A switch, not indexed arrays: ib is a run-time value in the band-generic transfer kernel and indexed local arrays
@@ -122,6 +125,8 @@ CB_HD double secdiff_band(double pwvcm, int ib /*0-based*/) {
   if (s < 1.50) s = 1.50;
   return s;
 }
+
+CB_HD void prep_overlap(const In& in, const Work& W, int c0, int c);  // below
 
 // Two launch modes (r01 ncu: the one-thread-per-column version cost as much as a transfer kernel -- 64 blocks on 148 SMs,
 // 60 serial layers): LAYER_PART = inatm + setcoef of layers [l0, l1), independent per layer (one thread per (column, layer));
@@ -395,6 +400,122 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
   W.pwvcm[c] = pwvcm;
   W.laytrop[c] = laytrop;
   W.ncbands[c] = (clouds && anycld) ? ncbands : 0;
+  if (clouds && anycld && !fl.mcica && fl.icld >= 2) prep_overlap(in, W, c0, c);
+}
+
+// Maximum-random overlap factors of one column (rrtmg_lw_rtrnmr.f90:322-479): functions of the cloud-fraction profile only,
+// shared by every g-point.  Rows: up sweep (index lev+1 = 1..nlay+1) and down sweep (index lev-1 = 0..nlay).
+enum OvlRow { OV_CLD1 = 0, OV_CLD2, OV_CLR1, OV_CLR2, OV_CMB1, OV_CMB2, OV_CLD1D, OV_CLD2D, OV_CLR1D, OV_CLR2D, OV_CMB1D, OV_CMB2D,
+              OV_IST, OV_ISTD, OV_NROWS };
+CB_HD void prep_overlap(const In& in, const Work& W, int c0, int c) {
+  const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
+  const size_t gc = (size_t)(c0 + c);
+  const size_t rs = (size_t)(nlay + 2) * ncc;
+#define OV(r, i) W.ovl[(size_t)(r) * rs + (size_t)(i) * ncc + c]
+  // cldfrac(0) is read by the Fortran at :400-401 (one element before the array, always multiplied by zero): taken as 0
+  auto cf = [&](int lev) { return lev >= 1 && lev <= nlay ? in.cldfr[(size_t)(lev - 1) * ncol + gc] : 0.0; };
+  auto cloudy = [&](int lev) { return cf(lev) >= 1.e-6; };
+  for (int r = 0; r < OV_NROWS; ++r)
+    for (int i = 0; i <= nlay + 1; ++i) OV(r, i) = 0.0;
+  double rat1 = 0., rat2 = 0.;
+  OV(OV_IST, 1) = 1.;
+  OV(OV_ISTD, nlay) = 1.;
+  for (int lev = 1; lev <= nlay; ++lev) {
+    if (cloudy(lev)) {
+      OV(OV_IST, lev + 1) = 0.;
+      double cld1 = 0., cld2 = 0., clr1 = 0., clr2 = 0.;
+      if (lev == nlay) {
+        // all six factors of lev+1 are zero
+      } else if (cf(lev + 1) >= cf(lev)) {
+        if (OV(OV_IST, lev) == 1.) {
+          if (cf(lev) < 1.) clr2 = (cf(lev + 1) - cf(lev)) / (1. - cf(lev));
+          OV(OV_CLR2, lev) = 0.;
+          OV(OV_CLD2, lev) = 0.;
+        } else {
+          const double fmax = fmax2(cf(lev), cf(lev - 1));
+          if (cf(lev + 1) > fmax) {
+            clr1 = rat2;
+            clr2 = (cf(lev + 1) - fmax) / (1. - fmax);
+          } else if (cf(lev + 1) < fmax) {
+            clr1 = (cf(lev + 1) - cf(lev)) / (cf(lev - 1) - cf(lev));
+          } else {
+            clr1 = rat2;
+          }
+        }
+        if (clr1 > 0. || clr2 > 0.) { rat1 = 1.; rat2 = 0.; }
+        else { rat1 = 0.; rat2 = 0.; }
+      } else {
+        if (OV(OV_IST, lev) == 1.) {
+          cld2 = (cf(lev) - cf(lev + 1)) / cf(lev);
+          OV(OV_CLR2, lev) = 0.;
+          OV(OV_CLD2, lev) = 0.;
+        } else {
+          const double fmin = fmin2(cf(lev), cf(lev - 1));
+          if (cf(lev + 1) <= fmin) {
+            cld1 = rat1;
+            cld2 = (fmin - cf(lev + 1)) / fmin;
+          } else {
+            cld1 = (cf(lev) - cf(lev + 1)) / (cf(lev) - fmin);
+          }
+        }
+        if (cld1 > 0. || cld2 > 0.) { rat1 = 0.; rat2 = 1.; }
+        else { rat1 = 0.; rat2 = 0.; }
+      }
+      OV(OV_CLD1, lev + 1) = cld1; OV(OV_CLD2, lev + 1) = cld2; OV(OV_CLR1, lev + 1) = clr1; OV(OV_CLR2, lev + 1) = clr2;
+      OV(OV_CMB1, lev + 1) = clr1 * OV(OV_CLD2, lev) * cf(lev - 1);
+      OV(OV_CMB2, lev + 1) = cld1 * OV(OV_CLR2, lev) * (1. - cf(lev - 1));
+    } else {
+      OV(OV_IST, lev + 1) = 1.;
+    }
+  }
+  for (int lev = nlay; lev >= 1; --lev) {
+    if (cloudy(lev)) {
+      OV(OV_ISTD, lev - 1) = 0.;
+      double cld1 = 0., cld2 = 0., clr1 = 0., clr2 = 0.;
+      if (lev == 1) {
+      } else if (cf(lev - 1) >= cf(lev)) {
+        if (OV(OV_ISTD, lev) == 1.) {
+          if (cf(lev) < 1.) clr2 = (cf(lev - 1) - cf(lev)) / (1. - cf(lev));
+          OV(OV_CLR2D, lev) = 0.;
+          OV(OV_CLD2D, lev) = 0.;
+        } else {
+          const double fmax = fmax2(cf(lev), cf(lev + 1));
+          if (cf(lev - 1) > fmax) {
+            clr1 = rat2;
+            clr2 = (cf(lev - 1) - fmax) / (1. - fmax);
+          } else if (cf(lev - 1) < fmax) {
+            clr1 = (cf(lev - 1) - cf(lev)) / (cf(lev + 1) - cf(lev));
+          } else {
+            clr1 = rat2;
+          }
+        }
+        if (clr1 > 0. || clr2 > 0.) { rat1 = 1.; rat2 = 0.; }
+        else { rat1 = 0.; rat2 = 0.; }
+      } else {
+        if (OV(OV_ISTD, lev) == 1.) {
+          cld2 = (cf(lev) - cf(lev - 1)) / cf(lev);
+          OV(OV_CLR2D, lev) = 0.;
+          OV(OV_CLD2D, lev) = 0.;
+        } else {
+          const double fmin = fmin2(cf(lev), cf(lev + 1));
+          if (cf(lev - 1) <= fmin) {
+            cld1 = rat1;
+            cld2 = (fmin - cf(lev - 1)) / fmin;
+          } else {
+            cld1 = (cf(lev) - cf(lev - 1)) / (cf(lev) - fmin);
+          }
+        }
+        if (cld1 > 0. || cld2 > 0.) { rat1 = 0.; rat2 = 1.; }
+        else { rat1 = 0.; rat2 = 0.; }
+      }
+      OV(OV_CLD1D, lev - 1) = cld1; OV(OV_CLD2D, lev - 1) = cld2; OV(OV_CLR1D, lev - 1) = clr1; OV(OV_CLR2D, lev - 1) = clr2;
+      OV(OV_CMB1D, lev - 1) = clr1 * OV(OV_CLD2D, lev) * cf(lev + 1);
+      OV(OV_CMB2D, lev - 1) = cld1 * OV(OV_CLR2D, lev) * (1. - cf(lev + 1));
+    } else {
+      OV(OV_ISTD, lev - 1) = 1.;
+    }
+  }
+#undef OV
 }
 
 // rtrn prologue for one (column, layer), rrtmg_lw_rtrn.f90:300-316: cloud optical depth along the diffusivity angle and
@@ -863,7 +984,8 @@ CB_HD void lw_taumol_unit(const Tables& T, const In& in, const Work& W, int c0, 
 }
 
 // rtrn / rtrnmc for U consecutive g-points of band ib (0-based) -- generic in the band (rrtmg_lw_rtrn.f90:300-557)
-template <int U, bool MC>
+// MR: maximum-random overlap of the fractional clouds (rtrnmr, rrtmg_lw_rtrnmr.f90:481-700) instead of rtrn's random overlap.
+template <int U, bool MC, bool MR = false>
 CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int ib, int g0, int unit) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
@@ -888,6 +1010,10 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
   }
   const int gabs = band_gstart(ib) + g0;  // absolute g-point of u = 0
   double radld[U], radclrd[U], frac1[U];
+  double mr_cld[U], mr_clr[U], mr_rad[U];  // MR: cloudy / clear parts of the radiance and the overlap correction (cldradd, clrradd, rad)
+#pragma unroll
+  for (int u = 0; u < U; ++u) { mr_cld[u] = 0.; mr_clr[u] = 0.; mr_rad[u] = 0.; }
+  const size_t ovs = (size_t)(nlay + 2) * ncc;  // row stride of W.ovl
 #pragma unroll
   for (int u = 0; u < U; ++u) { radld[u] = 0.; radclrd[u] = 0.; frac1[u] = 0.; }
   int iclddn = 0;
@@ -930,6 +1056,13 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       cldfrac_l = MC ? 1.0 : in.cldfr[o];
       odcld_l = W.cld[((size_t)ibc * nlay + l) * ncc + c];
       efclfrac_l = W.cld[((size_t)(16 + ibc) * nlay + l) * ncc + c];
+    }
+    double ov_ist = 0., ov_cld1 = 0., ov_cld2 = 0., ov_clr1 = 0., ov_clr2 = 0., ov_cmb1 = 0., ov_cmb2 = 0.;
+    if (MR && cloudy) {  // factors of the downward path at index lev-1, istcldd(lev)
+      const double* ov = W.ovl + (size_t)(lev - 1) * ncc + c;
+      ov_ist = W.ovl[OV_ISTD * ovs + (size_t)lev * ncc + c];
+      ov_cld1 = ov[OV_CLD1D * ovs]; ov_cld2 = ov[OV_CLD2D * ovs]; ov_clr1 = ov[OV_CLR1D * ovs]; ov_clr2 = ov[OV_CLR2D * ovs];
+      ov_cmb1 = ov[OV_CMB1D * ovs]; ov_cmb2 = ov[OV_CMB2D * ovs];
     }
     double sum_d = 0., sum_dc = 0.;
 #pragma unroll
@@ -987,7 +1120,27 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
           bbugas = plfrac * (blay + tfacgas * dplankup);
           bbutot = plfrac * (blay + tfactot * dplankup);
         }
-        radld[u] = radld[u] - radld[u] * (atrans + efclfrac * (1. - atrans)) + gassrc + cldfrac * (bbdtot * atot - gassrc);
+        if (MR) {
+          // rtrnmr.f90:591-616
+          if (ov_ist == 1.) {
+            mr_cld[u] = cldfrac * radld[u];
+            mr_clr[u] = radld[u] - mr_cld[u];
+            mr_rad[u] = 0.;
+          }
+          const double ttot = 1. - atot;
+          const double cldsrc = bbdtot * atot;
+          mr_cld[u] = mr_cld[u] * ttot + cldfrac * cldsrc;
+          mr_clr[u] = mr_clr[u] * (1. - atrans) + (1. - cldfrac) * gassrc;
+          radld[u] = mr_cld[u] + mr_clr[u];
+          const double radmod = mr_rad[u] * (ov_clr1 * (1. - atrans) + ov_cld1 * ttot) - ov_cmb1 * gassrc + ov_cmb2 * cldsrc;
+          const double oldcld = mr_cld[u] - radmod;
+          const double oldclr = mr_clr[u] + radmod;
+          mr_rad[u] = -radmod + ov_clr2 * oldclr - ov_cld2 * oldcld;
+          mr_cld[u] = mr_cld[u] + mr_rad[u];
+          mr_clr[u] = mr_clr[u] - mr_rad[u];
+        } else {
+          radld[u] = radld[u] - radld[u] * (atrans + efclfrac * (1. - atrans)) + gassrc + cldfrac * (bbdtot * atot - gassrc);
+        }
         scr[2 * wstride] = atot;
         scr[3 * wstride] = bbutot;
       } else {
@@ -1071,6 +1224,13 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       cldfrac_l = MC ? 1.0 : in.cldfr[o];
       efclfrac_l = W.cld[((size_t)(16 + ibc) * nlay + l) * ncc + c];
     }
+    double ov_ist = 0., ov_cld1 = 0., ov_cld2 = 0., ov_clr1 = 0., ov_clr2 = 0., ov_cmb1 = 0., ov_cmb2 = 0.;
+    if (MR && cloudy) {  // factors of the upward path at index lev+1, istcld(lev)
+      const double* ov = W.ovl + (size_t)(lev + 1) * ncc + c;
+      ov_ist = W.ovl[OV_IST * ovs + (size_t)lev * ncc + c];
+      ov_cld1 = ov[OV_CLD1 * ovs]; ov_cld2 = ov[OV_CLD2 * ovs]; ov_clr1 = ov[OV_CLR1 * ovs]; ov_clr2 = ov[OV_CLR2 * ovs];
+      ov_cmb1 = ov[OV_CMB1 * ovs]; ov_cmb2 = ov[OV_CMB2 * ovs];
+    }
     double s = 0., sc = 0.;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -1081,7 +1241,27 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       if (cloudy) {
         const double atot = scr[2 * wstride], bbutot = scr[3 * wstride];
         const double gassrc = bbugas * atrans;
-        radlu[u] = radlu[u] - radlu[u] * (atrans + efclfrac * (1. - atrans)) + gassrc + cldfrac * (bbutot * atot - gassrc);
+        if (MR) {
+          // rtrnmr.f90:655-677
+          if (ov_ist == 1.) {
+            mr_cld[u] = cldfrac * radlu[u];
+            mr_clr[u] = radlu[u] - mr_cld[u];
+            mr_rad[u] = 0.;
+          }
+          const double ttot = 1. - atot;
+          const double cldsrc = bbutot * atot;
+          mr_cld[u] = mr_cld[u] * ttot + cldfrac * cldsrc;
+          mr_clr[u] = mr_clr[u] * (1.0 - atrans) + (1. - cldfrac) * gassrc;
+          radlu[u] = mr_cld[u] + mr_clr[u];
+          const double radmod = mr_rad[u] * (ov_clr1 * (1.0 - atrans) + ov_cld1 * ttot) - ov_cmb1 * gassrc + ov_cmb2 * cldsrc;
+          const double oldcld = mr_cld[u] - radmod;
+          const double oldclr = mr_clr[u] + radmod;
+          mr_rad[u] = -radmod + ov_clr2 * oldclr - ov_cld2 * oldcld;
+          mr_cld[u] = mr_cld[u] + mr_rad[u];
+          mr_clr[u] = mr_clr[u] - mr_rad[u];
+        } else {
+          radlu[u] = radlu[u] - radlu[u] * (atrans + efclfrac * (1. - atrans)) + gassrc + cldfrac * (bbutot * atot - gassrc);
+        }
       } else {
         radlu[u] = radlu[u] + (bbugas - radlu[u]) * atrans;
       }

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kBlock, CB_LW_TAU_MIN_BLOCKS)
 }
 
 // rtrn / rtrnmc: one block = 128 adjacent columns x one unit (<= CB_LW_UMAX g-points of one band); one code body for all bands
-template <bool MC>
+template <bool MC, bool MR>
 __global__ void __launch_bounds__(kBlock, CB_LW_RT_MIN_BLOCKS)
     k_units(const __grid_constant__ Tables T, const __grid_constant__ In in, const __grid_constant__ Work W,
             const __grid_constant__ UnitList UL, int c0, int n) {
@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(kBlock, CB_LW_RT_MIN_BLOCKS)
   if (c >= n) return;
   const int k = blockIdx.y;
   const Unit un = UL.u[k];
-  if (CB_LW_UMAX >= 4 && un.u == 4) lw_transfer_unit<4, MC>(T, in, W, c0, c, un.band - 1, un.g0, k);
-  else lw_transfer_unit<2, MC>(T, in, W, c0, c, un.band - 1, un.g0, k);
+  if (CB_LW_UMAX >= 4 && un.u == 4) lw_transfer_unit<4, MC, MR>(T, in, W, c0, c, un.band - 1, un.g0, k);
+  else lw_transfer_unit<2, MC, MR>(T, in, W, c0, c, un.band - 1, un.g0, k);
 }
 
 // McICA cloud mask with the per-column kissvec generator: one thread per column
@@ -152,7 +152,7 @@ struct cb200_lw_engine {
 
   void free_work() {
     cudaFree(W.ws); cudaFree(W.idx); cudaFree(W.laytrop); cudaFree(W.ncbands); cudaFree(W.pwvcm);
-    cudaFree(W.cld); cudaFree(W.scr); cudaFree(W.part); cudaFree(W.err); cudaFree(W.mask);
+    cudaFree(W.cld); cudaFree(W.scr); cudaFree(W.part); cudaFree(W.ovl); cudaFree(W.err); cudaFree(W.mask);
     W = Work{};
     cap_ncc = cap_nlay = 0;
   }
@@ -169,6 +169,7 @@ struct cb200_lw_engine {
     CUDA_OK(cudaMalloc(&W.cld, sizeof(double) * 32 * L * n));
     CUDA_OK(cudaMalloc(&W.scr, sizeof(double) * 140 * NSCR * L * n));
     CUDA_OK(cudaMalloc(&W.part, sizeof(double) * UL.n * 4 * (L + 1) * n));
+    CUDA_OK(cudaMalloc(&W.ovl, sizeof(double) * OV_NROWS * (L + 2) * n));
     CUDA_OK(cudaMalloc(&W.mask, sizeof(unsigned) * 5 * L * n));
     CUDA_OK(cudaMalloc(&W.err, sizeof(int)));
     CUDA_OK(cudaMemset(W.err, 0, sizeof(int)));
@@ -229,7 +230,6 @@ extern "C" void cb200_lw_destroy(cb200_lw_engine* e) {
 extern "C" int cb200_lw_set_options(cb200_lw_engine* e, int icld, int idrv, int inflag, int iceflag, int liqflag) {
   if (icld < 0 || icld > 3) icld = 2;  // rrtmg_lw_rad.nomcica.f90:437
   if (idrv != 0) { e->error = "calculate_change_up_flux (idrv=1) is not implemented in the CUDA engine yet"; return -2; }
-  if (icld >= 2 && !e->fl.mcica) { e->error = "maximum-random / maximum cloud overlap (icld=2,3) without McICA (rtrnmr) is not implemented in the CUDA engine yet"; return -2; }
   e->fl = Flags{icld, idrv, inflag, iceflag, liqflag, e->fl.mcica};
   return 0;
 }
@@ -272,8 +272,10 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
   if (e->timing) cudaEventRecord(e->ev0, st);
   k_lw_taumol<<<dim3(gx, e->UL_tau.n, CB_LW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, in, W, e->UL_tau, c0, n);
   if (e->timing) cudaEventRecord(e->evm, st);
-  if (mc) k_units<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
-  else k_units<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+  // non-McICA: icld = 1 -> rtrn (random overlap); icld = 2, 3 -> rtrnmr (maximum-random), rrtmg_lw_rad.nomcica.f90:527-541
+  if (mc) k_units<true, false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+  else if (e->fl.icld >= 2) k_units<false, true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+  else k_units<false, false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
   if (e->timing) cudaEventRecord(e->ev1, st);
   k_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(e->T, W, e->UL, out, nlay, out_ncol, c0, n);
   k_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);

@@ -46,7 +46,8 @@ typedef struct cb200_lw_outputs {
  * Returns 0 on success; on failure *out is NULL and cb200_global_error() explains. */
 int cb200_lw_create(cb200_lw_engine** out, const char* table_blob, const double constants[11], int device);
 void cb200_lw_destroy(cb200_lw_engine* e);
-/* icld: 0 clear, 1 random, 2 maximum-random, 3 maximum; idrv: 0/1; inflag/iceflag/liqflag as RRTMG
+/* icld: 0 clear, 1 random (rtrn), 2 maximum-random, 3 maximum (both rtrnmr, as in rrtmg_lw_rad.nomcica.f90:527-541; with McICA the
+ * overlap is applied by the sub-column generator instead); idrv: 0 only; inflag/iceflag/liqflag as RRTMG
  * (module globals in _rrtmg_lw.pyx:8-14 in the reference; per engine here). */
 int cb200_lw_set_options(cb200_lw_engine* e, int icld, int idrv, int inflag, int iceflag, int liqflag);
 /* McICA (rrtmg_lw_rad.f90 + mcica_subcol_gen_lw.f90): enabled 0/1; irng 0 = kissvec (per-column seeds, generated on the

@@ -1607,6 +1607,387 @@ static void rtrn(Col& c, int istart, int iend, int idrv, Flux& F) {
   F.htrc(nlayers) = 0.0;
 }
 
+// rtrnmr -- rrtmg_lw_rtrnmr.f90:32-779: rtrn with maximum-random cloud overlap (non-McICA icld = 2, 3; also what the
+// reference calls for icld = 0, where no layer is cloudy).  cldfrac(0), read at :400-401 for lev = 1 (one element before
+// the array; always multiplied by faccld2(1) = facclr2(1) = 0 there), is taken as 0.
+static void rtrnmr(Col& c, int istart, int iend, int idrv, Flux& F) {
+  const int nlayers = c.nlayers, ncbands = c.ncbands;
+  const double wtdiff = 0.5, rec_6 = 0.166667;
+  const double tblint = 10000.0, bpade = S.bpade;
+  const std::vector<double>&tau_tbl = S.tau_tbl, &exp_tbl = S.exp_tbl, &tfn_tbl = S.tfn_tbl;
+  int n = nlayers + 2;
+  A1 urad(n, 0), drad(n, 0), clrurad(n, 0), clrdrad(n, 0), d_urad_dt(n, 0), d_clrurad_dt(n, 0);
+  A1 atrans(n), atot(n), bbugas(n), bbutot(n);
+  A2 odcld(n, 16);
+  A1 faccld1(n + 1), faccld2(n + 1), facclr1(n + 1), facclr2(n + 1), faccmb1(n + 1), faccmb2(n + 1);
+  A1 faccld1d(n + 1, 0), faccld2d(n + 1, 0), facclr1d(n + 1, 0), facclr2d(n + 1, 0), faccmb1d(n + 1, 0), faccmb2d(n + 1, 0);
+  std::vector<int> istcld(n + 2, 0), istcldd(n + 2, 0);
+  double fmax, fmin, rat1 = 0., rat2 = 0.;
+  double clrradd = 0., cldradd = 0., clrradu = 0., cldradu = 0., oldclr = 0., oldcld = 0., rad = 0., cldsrc, radmod, ttot;
+  std::vector<int> icldlyr(n, 0);
+  double secdiff[17];
+  for (int ibnd = 1; ibnd <= nbndlw; ++ibnd) {
+    if (ibnd == 1 || ibnd == 4 || ibnd >= 10)
+      secdiff[ibnd] = 1.66;
+    else {
+      secdiff[ibnd] = a0_[ibnd - 1] + a1_[ibnd - 1] * std::exp(a2_[ibnd - 1] * c.pwvcm);
+      if (secdiff[ibnd] > 1.80) secdiff[ibnd] = 1.80;
+      if (secdiff[ibnd] < 1.50) secdiff[ibnd] = 1.50;
+    }
+  }
+  for (int lay = 0; lay <= nlayers; ++lay) {
+    urad(lay) = 0.0; drad(lay) = 0.0; F.totuflux(lay) = 0.0; F.totdflux(lay) = 0.0;
+    clrurad(lay) = 0.0; clrdrad(lay) = 0.0; F.totuclfl(lay) = 0.0; F.totdclfl(lay) = 0.0;
+    d_urad_dt(lay) = 0.0; d_clrurad_dt(lay) = 0.0; F.dtotuflux_dt(lay) = 0.0; F.dtotuclfl_dt(lay) = 0.0;
+    if (lay == 0) continue;
+    for (int ib = 1; ib <= ncbands; ++ib) {
+      if (c.cldfrac(lay) >= 1.e-6) {
+        odcld(lay, ib) = secdiff[ib] * c.taucloud(lay, ib);
+        icldlyr[lay] = 1;
+      } else {
+        odcld(lay, ib) = 0.0;
+        icldlyr[lay] = 0;
+      }
+    }
+  }
+  // Maximum/Random cloud overlap parameters (:322-479)
+  auto cf = [&](int lev) { return lev >= 1 && lev <= nlayers ? c.cldfrac(lev) : 0.0; };
+  istcld[1] = 1;
+  istcldd[nlayers] = 1;
+  for (int lev = 1; lev <= nlayers; ++lev) {
+    if (icldlyr[lev] == 1) {
+      istcld[lev + 1] = 0;
+      if (lev == nlayers) {
+        faccld1(lev + 1) = 0.; faccld2(lev + 1) = 0.; facclr1(lev + 1) = 0.; facclr2(lev + 1) = 0.;
+        faccmb1(lev + 1) = 0.; faccmb2(lev + 1) = 0.;
+      } else if (cf(lev + 1) >= cf(lev)) {
+        faccld1(lev + 1) = 0.;
+        faccld2(lev + 1) = 0.;
+        if (istcld[lev] == 1) {
+          facclr1(lev + 1) = 0.;
+          facclr2(lev + 1) = 0.;
+          if (cf(lev) < 1.) facclr2(lev + 1) = (cf(lev + 1) - cf(lev)) / (1. - cf(lev));
+          facclr2(lev) = 0.;
+          faccld2(lev) = 0.;
+        } else {
+          fmax = std::max(cf(lev), cf(lev - 1));
+          if (cf(lev + 1) > fmax) {
+            facclr1(lev + 1) = rat2;
+            facclr2(lev + 1) = (cf(lev + 1) - fmax) / (1. - fmax);
+          } else if (cf(lev + 1) < fmax) {
+            facclr1(lev + 1) = (cf(lev + 1) - cf(lev)) / (cf(lev - 1) - cf(lev));
+            facclr2(lev + 1) = 0.;
+          } else {
+            facclr1(lev + 1) = rat2;
+            facclr2(lev + 1) = 0.;
+          }
+        }
+        if (facclr1(lev + 1) > 0. || facclr2(lev + 1) > 0.) { rat1 = 1.; rat2 = 0.; }
+        else { rat1 = 0.; rat2 = 0.; }
+      } else {
+        facclr1(lev + 1) = 0.;
+        facclr2(lev + 1) = 0.;
+        if (istcld[lev] == 1) {
+          faccld1(lev + 1) = 0.;
+          faccld2(lev + 1) = (cf(lev) - cf(lev + 1)) / cf(lev);
+          facclr2(lev) = 0.;
+          faccld2(lev) = 0.;
+        } else {
+          fmin = std::min(cf(lev), cf(lev - 1));
+          if (cf(lev + 1) <= fmin) {
+            faccld1(lev + 1) = rat1;
+            faccld2(lev + 1) = (fmin - cf(lev + 1)) / fmin;
+          } else {
+            faccld1(lev + 1) = (cf(lev) - cf(lev + 1)) / (cf(lev) - fmin);
+            faccld2(lev + 1) = 0.;
+          }
+        }
+        if (faccld1(lev + 1) > 0. || faccld2(lev + 1) > 0.) { rat1 = 0.; rat2 = 1.; }
+        else { rat1 = 0.; rat2 = 0.; }
+      }
+      faccmb1(lev + 1) = facclr1(lev + 1) * faccld2(lev) * cf(lev - 1);
+      faccmb2(lev + 1) = faccld1(lev + 1) * facclr2(lev) * (1. - cf(lev - 1));
+    } else {
+      istcld[lev + 1] = 1;
+    }
+  }
+  for (int lev = nlayers; lev >= 1; --lev) {
+    if (icldlyr[lev] == 1) {
+      istcldd[lev - 1] = 0;
+      if (lev == 1) {
+        faccld1d(lev - 1) = 0.; faccld2d(lev - 1) = 0.; facclr1d(lev - 1) = 0.; facclr2d(lev - 1) = 0.;
+        faccmb1d(lev - 1) = 0.; faccmb2d(lev - 1) = 0.;
+      } else if (cf(lev - 1) >= cf(lev)) {
+        faccld1d(lev - 1) = 0.;
+        faccld2d(lev - 1) = 0.;
+        if (istcldd[lev] == 1) {
+          facclr1d(lev - 1) = 0.;
+          facclr2d(lev - 1) = 0.;
+          if (cf(lev) < 1.) facclr2d(lev - 1) = (cf(lev - 1) - cf(lev)) / (1. - cf(lev));
+          facclr2d(lev) = 0.;
+          faccld2d(lev) = 0.;
+        } else {
+          fmax = std::max(cf(lev), cf(lev + 1));
+          if (cf(lev - 1) > fmax) {
+            facclr1d(lev - 1) = rat2;
+            facclr2d(lev - 1) = (cf(lev - 1) - fmax) / (1. - fmax);
+          } else if (cf(lev - 1) < fmax) {
+            facclr1d(lev - 1) = (cf(lev - 1) - cf(lev)) / (cf(lev + 1) - cf(lev));
+            facclr2d(lev - 1) = 0.;
+          } else {
+            facclr1d(lev - 1) = rat2;
+            facclr2d(lev - 1) = 0.;
+          }
+        }
+        if (facclr1d(lev - 1) > 0. || facclr2d(lev - 1) > 0.) { rat1 = 1.; rat2 = 0.; }
+        else { rat1 = 0.; rat2 = 0.; }
+      } else {
+        facclr1d(lev - 1) = 0.;
+        facclr2d(lev - 1) = 0.;
+        if (istcldd[lev] == 1) {
+          faccld1d(lev - 1) = 0.;
+          faccld2d(lev - 1) = (cf(lev) - cf(lev - 1)) / cf(lev);
+          facclr2d(lev) = 0.;
+          faccld2d(lev) = 0.;
+        } else {
+          fmin = std::min(cf(lev), cf(lev + 1));
+          if (cf(lev - 1) <= fmin) {
+            faccld1d(lev - 1) = rat1;
+            faccld2d(lev - 1) = (fmin - cf(lev - 1)) / fmin;
+          } else {
+            faccld1d(lev - 1) = (cf(lev) - cf(lev - 1)) / (cf(lev) - fmin);
+            faccld2d(lev - 1) = 0.;
+          }
+        }
+        if (faccld1d(lev - 1) > 0. || faccld2d(lev - 1) > 0.) { rat1 = 0.; rat2 = 1.; }
+        else { rat1 = 0.; rat2 = 0.; }
+      }
+      faccmb1d(lev - 1) = facclr1d(lev - 1) * faccld2d(lev) * cf(lev + 1);
+      faccmb2d(lev - 1) = faccld1d(lev - 1) * facclr2d(lev) * (1. - cf(lev + 1));
+    } else {
+      istcldd[lev - 1] = 1;
+    }
+  }
+  int igc = 1;
+  for (int iband = istart; iband <= iend; ++iband) {
+    int ib = 1;
+    if (ncbands == 1) ib = ipat_[0][iband - 1];
+    else if (ncbands == 5) ib = ipat_[1][iband - 1];
+    else if (ncbands == 16) ib = ipat_[2][iband - 1];
+    do {  // g-point loop (label 1000)
+      double radld = 0., radclrd = 0.;
+      int iclddn = 0;
+      for (int lev = nlayers; lev >= 1; --lev) {
+        double plfrac = c.fracs(lev, igc);
+        double blay = c.planklay(lev, iband);
+        double dplankup = c.planklev(lev, iband) - blay;
+        double dplankdn = c.planklev(lev - 1, iband) - blay;
+        double odepth = secdiff[iband] * c.taut(lev, igc);
+        if (odepth < 0.0) odepth = 0.0;
+        double bbd;
+        if (icldlyr[lev] == 1) {
+          iclddn = 1;
+          double odtot = odepth + odcld(lev, ib);
+          double gassrc, bbdtot;
+          if (odtot < 0.06) {
+            atrans(lev) = odepth - 0.5 * odepth * odepth;
+            double odepth_rec = rec_6 * odepth;
+            gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans(lev);
+            atot(lev) = odtot - 0.5 * odtot * odtot;
+            double odtot_rec = rec_6 * odtot;
+            bbdtot = plfrac * (blay + dplankdn * odtot_rec);
+            bbd = plfrac * (blay + dplankdn * odepth_rec);
+            bbugas(lev) = plfrac * (blay + dplankup * odepth_rec);
+            bbutot(lev) = plfrac * (blay + dplankup * odtot_rec);
+          } else if (odepth <= 0.06) {
+            atrans(lev) = odepth - 0.5 * odepth * odepth;
+            double odepth_rec = rec_6 * odepth;
+            gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans(lev);
+            odtot = odepth + odcld(lev, ib);
+            double tblind = odtot / (bpade + odtot);
+            int ittot = f2i(tblint * tblind + 0.5);
+            double tfactot = tfn_tbl[ittot];
+            bbdtot = plfrac * (blay + tfactot * dplankdn);
+            bbd = plfrac * (blay + dplankdn * odepth_rec);
+            atot(lev) = 1. - exp_tbl[ittot];
+            bbugas(lev) = plfrac * (blay + dplankup * odepth_rec);
+            bbutot(lev) = plfrac * (blay + tfactot * dplankup);
+          } else {
+            double tblind = odepth / (bpade + odepth);
+            int itgas = f2i(tblint * tblind + 0.5);
+            odepth = tau_tbl[itgas];
+            atrans(lev) = 1. - exp_tbl[itgas];
+            double tfacgas = tfn_tbl[itgas];
+            gassrc = atrans(lev) * plfrac * (blay + tfacgas * dplankdn);
+            odtot = odepth + odcld(lev, ib);
+            tblind = odtot / (bpade + odtot);
+            int ittot = f2i(tblint * tblind + 0.5);
+            double tfactot = tfn_tbl[ittot];
+            bbdtot = plfrac * (blay + tfactot * dplankdn);
+            bbd = plfrac * (blay + tfacgas * dplankdn);
+            atot(lev) = 1. - exp_tbl[ittot];
+            bbugas(lev) = plfrac * (blay + tfacgas * dplankup);
+            bbutot(lev) = plfrac * (blay + tfactot * dplankup);
+          }
+          // :591-616
+          if (istcldd[lev] == 1) {
+            cldradd = c.cldfrac(lev) * radld;
+            clrradd = radld - cldradd;
+            oldcld = cldradd;
+            oldclr = clrradd;
+            rad = 0.;
+          }
+          ttot = 1. - atot(lev);
+          cldsrc = bbdtot * atot(lev);
+          cldradd = cldradd * ttot + c.cldfrac(lev) * cldsrc;
+          clrradd = clrradd * (1. - atrans(lev)) + (1. - c.cldfrac(lev)) * gassrc;
+          radld = cldradd + clrradd;
+          drad(lev - 1) = drad(lev - 1) + radld;
+          radmod = rad * (facclr1d(lev - 1) * (1. - atrans(lev)) + faccld1d(lev - 1) * ttot) - faccmb1d(lev - 1) * gassrc +
+                   faccmb2d(lev - 1) * cldsrc;
+          oldcld = cldradd - radmod;
+          oldclr = clrradd + radmod;
+          rad = -radmod + facclr2d(lev - 1) * oldclr - faccld2d(lev - 1) * oldcld;
+          cldradd = cldradd + rad;
+          clrradd = clrradd - rad;
+        } else {
+          if (odepth <= 0.06) {
+            atrans(lev) = odepth - 0.5 * odepth * odepth;
+            odepth = rec_6 * odepth;
+            bbd = plfrac * (blay + dplankdn * odepth);
+            bbugas(lev) = plfrac * (blay + dplankup * odepth);
+          } else {
+            double tblind = odepth / (bpade + odepth);
+            int itr = f2i(tblint * tblind + 0.5);
+            double transc = exp_tbl[itr];
+            atrans(lev) = 1. - transc;
+            double tausfac = tfn_tbl[itr];
+            bbd = plfrac * (blay + tausfac * dplankdn);
+            bbugas(lev) = plfrac * (blay + tausfac * dplankup);
+          }
+          radld = radld + (bbd - radld) * atrans(lev);
+          drad(lev - 1) = drad(lev - 1) + radld;
+        }
+        if (iclddn == 1) {
+          radclrd = radclrd + (bbd - radclrd) * atrans(lev);
+          clrdrad(lev - 1) = clrdrad(lev - 1) + radclrd;
+        } else {
+          radclrd = radld;
+          clrdrad(lev - 1) = drad(lev - 1);
+        }
+      }
+      double rad0 = c.fracs(1, igc) * c.plankbnd[iband];
+      double d_rad0_dt = 0., d_radlu_dt = 0., d_radclru_dt = 0.;
+      if (idrv == 1) d_rad0_dt = c.fracs(1, igc) * c.dplankbnd_dt[iband];
+      double reflect = 1. - c.semiss[iband];
+      double radlu = rad0 + reflect * radld;
+      double radclru = rad0 + reflect * radclrd;
+      urad(0) = urad(0) + radlu;
+      clrurad(0) = clrurad(0) + radclru;
+      if (idrv == 1) {
+        d_radlu_dt = d_rad0_dt;
+        d_urad_dt(0) = d_urad_dt(0) + d_radlu_dt;
+        d_radclru_dt = d_rad0_dt;
+        d_clrurad_dt(0) = d_clrurad_dt(0) + d_radclru_dt;
+      }
+      for (int lev = 1; lev <= nlayers; ++lev) {
+        if (icldlyr[lev] == 1) {
+          double gassrc = bbugas(lev) * atrans(lev);
+          if (istcld[lev] == 1) {
+            cldradu = c.cldfrac(lev) * radlu;
+            clrradu = radlu - cldradu;
+            oldcld = cldradu;
+            oldclr = clrradu;
+            rad = 0.;
+          }
+          ttot = 1. - atot(lev);
+          cldsrc = bbutot(lev) * atot(lev);
+          cldradu = cldradu * ttot + c.cldfrac(lev) * cldsrc;
+          clrradu = clrradu * (1.0 - atrans(lev)) + (1. - c.cldfrac(lev)) * gassrc;
+          radlu = cldradu + clrradu;
+          urad(lev) = urad(lev) + radlu;
+          radmod = rad * (facclr1(lev + 1) * (1.0 - atrans(lev)) + faccld1(lev + 1) * ttot) - faccmb1(lev + 1) * gassrc +
+                   faccmb2(lev + 1) * cldsrc;
+          oldcld = cldradu - radmod;
+          oldclr = clrradu + radmod;
+          rad = -radmod + facclr2(lev + 1) * oldclr - faccld2(lev + 1) * oldcld;
+          cldradu = cldradu + rad;
+          clrradu = clrradu - rad;
+          if (idrv == 1) {
+            d_radlu_dt = d_radlu_dt * c.cldfrac(lev) * (1.0 - atot(lev)) +
+                         d_radlu_dt * (1.0 - c.cldfrac(lev)) * (1.0 - atrans(lev));
+            d_urad_dt(lev) = d_urad_dt(lev) + d_radlu_dt;
+          }
+        } else {
+          radlu = radlu + (bbugas(lev) - radlu) * atrans(lev);
+          urad(lev) = urad(lev) + radlu;
+          if (idrv == 1) {
+            d_radlu_dt = d_radlu_dt * (1.0 - atrans(lev));
+            d_urad_dt(lev) = d_urad_dt(lev) + d_radlu_dt;
+          }
+        }
+        if (iclddn == 1) {
+          radclru = radclru + (bbugas(lev) - radclru) * atrans(lev);
+          clrurad(lev) = clrurad(lev) + radclru;
+        } else {
+          radclru = radlu;
+          clrurad(lev) = urad(lev);
+        }
+        if (idrv == 1) {
+          if (iclddn == 1) {
+            d_radclru_dt = d_radclru_dt * (1.0 - atrans(lev));
+            d_clrurad_dt(lev) = d_clrurad_dt(lev) + d_radclru_dt;
+          } else {
+            d_radclru_dt = d_radlu_dt;
+            d_clrurad_dt(lev) = d_urad_dt(lev);
+          }
+        }
+      }
+      igc = igc + 1;
+    } while (igc <= ngs_[iband - 1]);
+    for (int lev = nlayers; lev >= 0; --lev) {
+      double uflux = urad(lev) * wtdiff, dflux = drad(lev) * wtdiff;
+      urad(lev) = 0.0;
+      drad(lev) = 0.0;
+      F.totuflux(lev) = F.totuflux(lev) + uflux * delwave_[iband - 1];
+      F.totdflux(lev) = F.totdflux(lev) + dflux * delwave_[iband - 1];
+      double uclfl = clrurad(lev) * wtdiff, dclfl = clrdrad(lev) * wtdiff;
+      clrurad(lev) = 0.0;
+      clrdrad(lev) = 0.0;
+      F.totuclfl(lev) = F.totuclfl(lev) + uclfl * delwave_[iband - 1];
+      F.totdclfl(lev) = F.totdclfl(lev) + dclfl * delwave_[iband - 1];
+    }
+    if (idrv == 1)
+      for (int lev = nlayers; lev >= 0; --lev) {
+        double duflux_dt = d_urad_dt(lev) * wtdiff;
+        d_urad_dt(lev) = 0.0;
+        F.dtotuflux_dt(lev) = F.dtotuflux_dt(lev) + duflux_dt * delwave_[iband - 1] * S.fluxfac;
+        double duclfl_dt = d_clrurad_dt(lev) * wtdiff;
+        d_clrurad_dt(lev) = 0.0;
+        F.dtotuclfl_dt(lev) = F.dtotuclfl_dt(lev) + duclfl_dt * delwave_[iband - 1] * S.fluxfac;
+      }
+  }
+  F.totuflux(0) = F.totuflux(0) * S.fluxfac;
+  F.totdflux(0) = F.totdflux(0) * S.fluxfac;
+  F.fnet(0) = F.totuflux(0) - F.totdflux(0);
+  F.totuclfl(0) = F.totuclfl(0) * S.fluxfac;
+  F.totdclfl(0) = F.totdclfl(0) * S.fluxfac;
+  F.fnetc(0) = F.totuclfl(0) - F.totdclfl(0);
+  for (int lev = 1; lev <= nlayers; ++lev) {
+    F.totuflux(lev) = F.totuflux(lev) * S.fluxfac;
+    F.totdflux(lev) = F.totdflux(lev) * S.fluxfac;
+    F.fnet(lev) = F.totuflux(lev) - F.totdflux(lev);
+    F.totuclfl(lev) = F.totuclfl(lev) * S.fluxfac;
+    F.totdclfl(lev) = F.totdclfl(lev) * S.fluxfac;
+    F.fnetc(lev) = F.totuclfl(lev) - F.totdclfl(lev);
+    int l = lev - 1;
+    F.htr(l) = S.heatfac * (F.fnet(l) - F.fnet(lev)) / (c.pz(l) - c.pz(lev));
+    F.htrc(l) = S.heatfac * (F.fnetc(l) - F.fnetc(lev)) / (c.pz(l) - c.pz(lev));
+  }
+  F.htr(nlayers) = 0.0;
+  F.htrc(nlayers) = 0.0;
+}
+
 }  // namespace orc
 
 // =============================================================================================
@@ -1693,8 +2074,7 @@ extern "C" int orc_lw_nomcica(int ncol, int nlay, int* icld, int idrv, const dou
       // cloud copy (cldfrac = 0) rtrnmr's clear path is arithmetically rtrn's clear path.
       rtrn(c, istart, iend, idrv, F);
     } else {
-      g_err = "oracle: rtrnmr (maximum-random overlap) not restated yet";
-      return 3;
+      rtrnmr(c, istart, iend, idrv, F);
     }
     for (int k = 0; k <= nlay; ++k) {
       size_t o = (size_t)(iplon - 1) + (size_t)ncol * k;

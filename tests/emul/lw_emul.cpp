@@ -20,10 +20,11 @@ static void run_taumol(const Tables& T, const In& in, const Work& W, int n, int 
 }
 
 template <int U>
-static void run_transfer(const Tables& T, const In& in, const Work& W, int n, int ib, int g0, int unit, bool mc) {
+static void run_transfer(const Tables& T, const In& in, const Work& W, int n, int ib, int g0, int unit, bool mc, bool mr) {
   for (int c = 0; c < n; ++c) {
-    if (mc) lw_transfer_unit<U, true>(T, in, W, 0, c, ib, g0, unit);
-    else lw_transfer_unit<U, false>(T, in, W, 0, c, ib, g0, unit);
+    if (mc) lw_transfer_unit<U, true, false>(T, in, W, 0, c, ib, g0, unit);
+    else if (mr) lw_transfer_unit<U, false, true>(T, in, W, 0, c, ib, g0, unit);
+    else lw_transfer_unit<U, false, false>(T, in, W, 0, c, ib, g0, unit);
   }
 }
 
@@ -52,13 +53,13 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
     Work W;
     W.ncc = ncol;
     std::vector<double> ws((size_t)NF * nlay * ncol), pw(ncol), cld((size_t)32 * nlay * ncol),
-        scr((size_t)140 * NSCR * nlay * ncol), part((size_t)nunits * 4 * (nlay + 1) * ncol);
+        scr((size_t)140 * NSCR * nlay * ncol), ovl((size_t)OV_NROWS * (nlay + 2) * ncol), part((size_t)nunits * 4 * (nlay + 1) * ncol);
     std::vector<int> idx((size_t)nlay * ncol), lt(ncol), ncb(ncol);
     std::vector<unsigned> mask((size_t)5 * nlay * ncol, 0u);
     int err = 0;
     W.mask = mask.data(); W.mstride = ncol; W.moff = 0;
     W.ws = ws.data(); W.idx = idx.data(); W.laytrop = lt.data(); W.ncbands = ncb.data(); W.pwvcm = pw.data();
-    W.cld = cld.data(); W.scr = scr.data(); W.part = part.data(); W.err = &err;
+    W.cld = cld.data(); W.scr = scr.data(); W.ovl = ovl.data(); W.part = part.data(); W.err = &err;
     if (mc && irng == 1) { cb::mcica::mask_mt_host(in.cldfr, ncol, nlay, 140, 5, fl.icld, seed, mask); W.mask = mask.data(); }
     if (mc && irng == 0)
       for (int c = 0; c < ncol; ++c)
@@ -82,8 +83,9 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
     }
     for (int k2 = 0; k2 < nunits; ++k2) {
       const Unit un = units[k2];
-      if (un.u == 4) run_transfer<4>(T, in, W, ncol, un.band - 1, un.g0, k2, mc);
-      else run_transfer<2>(T, in, W, ncol, un.band - 1, un.g0, k2, mc);
+      const bool mr = !mc && fl.icld >= 2;
+      if (un.u == 4) run_transfer<4>(T, in, W, ncol, un.band - 1, un.g0, k2, mc, mr);
+      else run_transfer<2>(T, in, W, ncol, un.band - 1, un.g0, k2, mc, mr);
     }
     for (int c = 0; c < ncol; ++c)
       for (int lev = 0; lev <= nlay; ++lev) lw_reduce_level(T, W, units, nunits, nlay, 0, c, lev, ncol, out);

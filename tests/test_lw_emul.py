@@ -96,3 +96,51 @@ def test_oracle_mcica_golden():
     o = lw_mcica(H.lw_oracle(cloud_overlap=1), st, seed, irng=1)
     for name, k in (("downwelling_longwave_flux_in_air", "dflx"), ("air_temperature_tendency_from_longwave", "hr")):
         np.testing.assert_allclose(o[k], g[f"TestRRTMGLongwaveMCICA-3d/diag/{name}"].reshape(-1, 50), rtol=0, atol=1e-8)
+
+
+# ---- maximum-random overlap without McICA: rtrnmr (rrtmg_lw_rtrnmr.f90).  No golden exists for it in the reference, so the
+# restatement is pinned by (a) agreement of the two independently structured implementations and (b) its physics: it must
+# reduce to the golden-pinned rtrn when no two cloudy layers touch, and to a single thicker cloud when equal fractions stack.
+@pytest.mark.parametrize("icld", [2, 3])
+def test_maximum_random_overlap_kernels_match_oracle(icld):
+    st = SY.make_lw_state(40, 60, seed=31 + icld, clouds=True, aerosol=True)
+    ref = H.run_lw_oracle(H.lw_oracle(cloud_overlap=icld), st)
+    rc, got = H.run_lw_emul(st, flags=(icld, 0, 2, 1, 1))
+    assert rc == 0
+    for k in ("uflx", "dflx", "uflxc", "dflxc"):
+        assert H.rel_err(got[k], ref[k]) < TOL, k
+    rnd = H.run_lw_oracle(H.lw_oracle(cloud_overlap=1), st)
+    np.testing.assert_array_equal(ref["uflxc"], rnd["uflxc"])          # clear-sky stream does not know about overlap
+    assert np.abs(ref["dflx"] - rnd["dflx"]).max() > 1.0                 # ... the total-sky one does (W m-2)
+
+
+def test_maximum_random_overlap_reduces_to_random_for_isolated_cloud_layers():
+    st = SY.make_lw_state(16, 40, seed=3, clouds=True)
+    rng = np.random.default_rng(0)
+    st["cldfr"][:] = 0.0
+    for l in (8, 12, 17, 25):                                             # no two cloudy layers adjacent
+        st["cldfr"][l, :] = rng.uniform(0.1, 0.9, 16)
+    st["cicewp"][:] = rng.uniform(5, 30, st["cicewp"].shape)
+    st["cliqwp"][:] = rng.uniform(5, 30, st["cliqwp"].shape)
+    rnd = H.run_lw_oracle(H.lw_oracle(cloud_overlap=1), st)              # rtrn: pinned by the reference goldens
+    for impl in ("oracle", "kernel"):
+        mr = H.run_lw_oracle(H.lw_oracle(cloud_overlap=2), st) if impl == "oracle" else H.run_lw_emul(st, flags=(2, 0, 2, 1, 1))[1]
+        for k in ("uflx", "dflx"):
+            # rtrn folds the cloud into an effective fraction with exp(), rtrnmr splits the radiance with the tabulated
+            # transmittance: same physics, ~5e-6 apart
+            assert H.rel_err(mr[k], rnd[k]) < 2e-5, (impl, k, H.rel_err(mr[k], rnd[k]))
+
+
+def test_maximum_overlap_of_equal_fractions_beats_random_overlap_cloud_cover():
+    st = SY.make_lw_state(8, 40, seed=5, clouds=False)
+    for k in ("cicewp", "cliqwp"):
+        st[k][:] = 20.0
+    st["reice"][:] = 40.0
+    st["reliq"][:] = 10.0
+    st["cldfr"][10:13, :] = 0.4                                           # three stacked layers, same fraction
+    rnd = H.run_lw_oracle(H.lw_oracle(cloud_overlap=1), st)
+    rc, mr = H.run_lw_emul(st, flags=(2, 0, 2, 1, 1))
+    assert rc == 0
+    # maximum overlap: total cover 0.4; random: 1 - 0.6^3 = 0.78 -> less downward longwave at the surface, more OLR
+    assert np.all(mr["dflx"][0] < rnd["dflx"][0] - 5.0) and np.all(mr["uflx"][-1] > rnd["uflx"][-1])
+    assert np.all(mr["dflx"][0] > mr["dflxc"][0])

@@ -141,3 +141,17 @@ def test_mcica_component_matches_reference_golden():
     for name in ("upwelling_longwave_flux_in_air", "downwelling_longwave_flux_in_air", "air_temperature_tendency_from_longwave"):
         np.testing.assert_allclose(diag[name], g[f"TestRRTMGLongwaveMCICA-3d/diag/{name}"].reshape(diag[name].shape[0], -1),
                                    rtol=0, atol=1e-8)
+
+
+@pytest.mark.parametrize("icld", [2, 3])
+def test_cuda_lw_maximum_random_overlap_matches_oracle(icld):
+    """rtrnmr (non-McICA icld = 2, 3) on the GPU vs the oracle; chunked so both host-pipeline slots are used."""
+    from climt_b200.engine import LWEngine
+    st = SY.make_lw_state(700, 60, seed=40 + icld, clouds=True, aerosol=True)
+    ref = H.run_lw_oracle(H.lw_oracle(cloud_overlap=icld), st)
+    eng = LWEngine(icld=icld)
+    got = eng.run_host(700, 60, H.to_abi(st))
+    eng.close()
+    for k in ("uflx", "dflx", "uflxc", "dflxc"):
+        assert H.rel_err(got[k], ref[k]) < RTOL, (k, H.rel_err(got[k], ref[k]))
+    np.testing.assert_allclose(got["hr"], ref["hr"], rtol=1e-5, atol=1e-7)
