@@ -189,6 +189,7 @@ def main():
     gathered = [torch.empty((world * 2 * nrow, NCOL), dtype=torch.float64, device="cuda") for _ in range(2)] if world > 1 else None
     pending = [None, None]
     istep = [0]
+    s_lw, s_sw = torch.cuda.Stream(), torch.cuda.Stream()
 
     def step_device(lw=True, sw=True):
         b = istep[0] & 1
@@ -196,9 +197,19 @@ def main():
         if pending[b] is not None:
             pending[b].wait()
             pending[b] = None
-        if lw:
+        if lw and sw:
+            # the two engines are independent: issue them on two streams so that one engine's kernels fill the tail waves of
+            # the other's (each call is asynchronous on the stream it is given)
+            cur = torch.cuda.current_stream()
+            for st_, fn in ((s_lw, lambda: eng.run_device(NCOL, NLAY, d_in, d_outs[b], stream=s_lw.cuda_stream)),
+                            (s_sw, lambda: engs.run_device(NCOL, NLAY, ds_in, ds_outs[b], dyofyr=1, stream=s_sw.cuda_stream))):
+                st_.wait_stream(cur)
+                fn()
+            cur.wait_stream(s_lw)
+            cur.wait_stream(s_sw)
+        elif lw:
             eng.run_device(NCOL, NLAY, d_in, d_outs[b])
-        if sw:
+        elif sw:
             engs.run_device(NCOL, NLAY, ds_in, ds_outs[b], dyofyr=1)
         if world > 1:
             pending[b] = dist.all_gather_into_tensor(gathered[b], packed[b], async_op=True)
