@@ -1,19 +1,21 @@
 // climt_b200 -- RRTMG longwave engine, per-thread core (sm_100a device code; also host-compilable
 // so tests can single-step the very same code on the CPU without a GPU).
 //
-// Work decomposition (B200-first, not the reference's column-serial loop nest):
-//   prep_column   one thread per column     inatm + setcoef + cldprop   -> per-layer coefficients in HBM workspace
-//   lw_unit<B,U>  one thread per (column, unit); a unit = U (<=4) consecutive g-points of band B.
-//                 Lanes of a warp are 32 ADJACENT COLUMNS working on the SAME g-points, so all band-specific
-//                 code is warp-uniform, every state/workspace access is a coalesced 256-byte row, and table
-//                 gathers hit the same few L1 lines (neighbouring columns share jp/jt).  The vertical
-//                 recurrence runs in registers; the per-g transmittance/source pairs needed by the upward
-//                 sweep go through a (column-fastest) scratch row that is written once and read once.
-//   lw_reduce     one thread per (column, level): fixed-order sum of the per-unit partial fluxes (deterministic,
-//                 no atomics), band weights, W m-2; then heating rates.
+// Work decomposition (B200-first, not the reference's column-serial loop nest).  Lanes of a warp are always
+// ADJACENT COLUMNS, so every access to the caller's state and to the workspace is a contiguous 256-byte row.
+//   prep_column<LAYER,COLUMN>  inatm + setcoef per (column, layer); what couples the layers (pwvcm, laytrop, cldprop) per column
+//   prep_overlap / prep_cloud_scale   maximum-random overlap factors (rtrnmr) / rtrn cloud prologue
+//   lw_taumol_unit<B,U>        one thread per (column, unit of <=4 g-points of band B, chunk of layers): taug + Planck fractions;
+//                              all band-specific code is block-uniform, table gathers of neighbouring columns share L1 lines
+//   lw_transfer_unit<U,MC,MR>  one thread per (column, unit of <=2 g-points), band-generic: rtrn / rtrnmc / rtrnmr sweeps with
+//                              the recurrences in registers
+//   lw_reduce_level            one thread per (column, level): fixed-order sum of the per-unit partial fluxes (deterministic,
+//                              no atomics), band weights, W m-2
+//   lw_heating                 one thread per (column, layer): heating rates
 //
 // Reference being replaced (cited per function): climt/_lib/rrtmg_lw/rrtmg_lw_rad.nomcica.f90 (inatm, driver),
-// rrtmg_lw_setcoef.f90, rrtmg_lw_cldprop.f90, rrtmg_lw_taumol.f90, rrtmg_lw_rtrn.f90.
+// rrtmg_lw_setcoef.f90, rrtmg_lw_cldprop.f90, rrtmg_lw_cldprmc.f90, rrtmg_lw_taumol.f90, rrtmg_lw_rtrn.f90, rrtmg_lw_rtrnmc.f90,
+// rrtmg_lw_rtrnmr.f90.
 // The 16 hand-specialised taugbNN routines are expressed here as ONE generic evaluator driven by a
 // compile-time band description (struct Region) -- see region<B,LOWER>().
 #pragma once
@@ -88,21 +90,6 @@ CB_HD int pack_idx(int jp, int jt, int jt1, int inds, int indf, int indm) {
 // ---------------------------------------------------------------------------------------------
 // prep_column: inatm (rrtmg_lw_rad.nomcica.f90:572-900) + setcoef (rrtmg_lw_setcoef.f90:257-412) +
 // cldprop (rrtmg_lw_cldprop.f90:31-276) + the cloud prologue of rtrn (rrtmg_lw_rtrn.f90:260-318).
-CB_HD void secdiff_all(double pwvcm, double* secdiff /*[16]*/) {
-  const double a0[16] = {1.66, 1.55, 1.58, 1.66, 1.54, 1.454, 1.89, 1.33, 1.668, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66};
-  const double a1[16] = {0.00, 0.25, 0.22, 0.00, 0.13, 0.446, -0.10, 0.40, -0.006, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
-  const double a2[16] = {0.00, -12.0, -11.7, 0.00, -0.72, -0.243, 0.19, -0.062, 0.414, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
-  for (int ib = 0; ib < 16; ++ib) {
-    if (ib == 0 || ib == 3 || ib >= 9) {
-      secdiff[ib] = 1.66;
-    } else {
-      double s = a0[ib] + a1[ib] * exp(a2[ib] * pwvcm);
-      if (s > 1.80) s = 1.80;
-      if (s < 1.50) s = 1.50;
-      secdiff[ib] = s;
-    }
-  }
-}
 CB_HD double fmax2(double a, double b) { return a > b ? a : b; }
 CB_HD double fmin2(double a, double b) { return a < b ? a : b; }
 CB_HD double secdiff_band(double pwvcm, int ib /*0-based*/) {

@@ -1,10 +1,12 @@
 // climt_b200 -- RRTMG shortwave engine, per-thread core (sm_100a device code; host-compilable for the
 // test-only emulation).  Same decomposition as the longwave engine (lw_core.cuh):
-//   sw_prep_column  one thread per column: inatm_sw + setcoef_sw + cldprop_sw (+ ECMWF aerosol mix)
-//   sw_unit<B,U>    one thread per (column, unit of <=4 g-points of band B): taumol_sw + delta-scaling + reftra_sw
-//                   fused with the upward adding pass of vrtqdr_sw (surface -> top), then the downward pass
-//                   (top -> surface) that turns the stored layer properties into fluxes.  Lanes = adjacent columns.
-//   sw_reduce       fixed-order sum of the per-unit partial fluxes, then heating rates.
+//   sw_prep_column<LAYER,COLUMN>  inatm_sw + setcoef_sw + cldprop_sw (+ ECMWF aerosol mix) per (column, layer); laytrop and the
+//                           solar-source layers per column
+//   sw_taumol_unit<B,U>     one thread per (column, unit of <=4 g-points of band B, chunk of layers): taumol_sw
+//   sw_transfer_unit<U,MC>  one thread per (column, unit of <=2 g-points), band-generic: delta-scaling + reftra_sw for the clear
+//                           and cloudy paths, upward adding pass of vrtqdr_sw (surface -> top), then the downward pass that
+//                           turns the stored layer properties into fluxes.  Lanes = adjacent columns.
+//   sw_reduce_level / sw_heating   fixed-order sum of the per-unit partial fluxes, heating rates.
 //
 // Reference being replaced: climt/_lib/rrtmg_sw/rrtmg_sw_rad.nomcica.f90 (driver, inatm_sw), rrtmg_sw_setcoef.f90,
 // rrtmg_sw_cldprop.f90, rrtmg_sw_taumol.f90, rrtmg_sw_spcvrt.f90, rrtmg_sw_reftra.f90, rrtmg_sw_vrtqdr.f90.
@@ -116,7 +118,7 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
     for (int l = 0; l < nlay; ++l) any = any || in.cldfr[(size_t)l * ncol + gc] > 1.e-12;
     clouds = any;
   }
-  // cldprop_sw locals persist across layers like the Fortran routine-locals
+  // cldprop_sw work arrays (each is reassigned for all 14 bands in every layer that enters the cloud block)
   double extcoice[14], gice[14], ssacoice[14], forwice[14], extcoliq[14], gliq[14], ssacoliq[14], forwliq[14];
   for (int i = 0; i < 14; ++i) { extcoice[i] = gice[i] = ssacoice[i] = forwice[i] = extcoliq[i] = gliq[i] = ssacoliq[i] = forwliq[i] = 0.; }
 #define WS(f, l) W.ws[((size_t)(f) * nlay + (l)) * ncc + c]
