@@ -1007,12 +1007,34 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
   double* __restrict__ part = W.part + (size_t)unit * 4 * (nlay + 1) * ncc + c;
   const size_t pstride = (size_t)(nlay + 1) * ncc;
   double plev_up = planck_band(tp, in.tlev[(size_t)nlay * ncol + gc]);  // planklev(nlay)
+  // The loads of a layer do not depend on the recurrence: fetch layer lev-1 while layer lev is computed (the kernel's top
+  // stall is memory latency at 24 warps per SM).
+  struct LayerIn {
+    double taua, tlay, tlev, tau[U], frac[U];
+  };
+  auto fetch = [&](int l) {
+    LayerIn v;
+    const size_t o = (size_t)l * ncol + gc;
+    v.taua = in.tauaer[((size_t)ib * nlay + l) * ncol + gc];
+    v.tlay = in.tlay[o];
+    v.tlev = in.tlev[o];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
+      v.tau[u] = scr[R_TAU * wstride];
+      v.frac[u] = scr[R_FRAC * wstride];
+    }
+    return v;
+  };
+  LayerIn nxt = fetch(nlay - 1);
   for (int lev = nlay; lev >= 1; --lev) {
     const int l = lev - 1;
     const size_t o = (size_t)l * ncol + gc;
-    const double taua = in.tauaer[((size_t)ib * nlay + l) * ncol + gc];
-    const double blay = planck_band(tp, in.tlay[o]);
-    const double plev_dn = planck_band(tp, in.tlev[o]);  // planklev(lev-1)
+    const LayerIn cur = nxt;
+    if (lev > 1) nxt = fetch(l - 1);
+    const double taua = cur.taua;
+    const double blay = planck_band(tp, cur.tlay);
+    const double plev_dn = planck_band(tp, cur.tlev);  // planklev(lev-1)
     const double dplankup = plev_up - blay;
     const double dplankdn = plev_dn - blay;
     plev_up = plev_dn;
@@ -1057,8 +1079,8 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       const bool on = !MC || ((mbits >> u) & 1u);
       const double odcld = on ? odcld_l : 0., efclfrac = on ? efclfrac_l : 0., cldfrac = on ? cldfrac_l : 0.;
       double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
-      const double plfrac = scr[R_FRAC * wstride];
-      double odepth = secdiff * (scr[R_TAU * wstride] + taua);
+      const double plfrac = cur.frac[u];
+      double odepth = secdiff * (cur.tau[u] + taua);
       if (odepth < 0.0) odepth = 0.0;
       double atrans, bbd, bbugas;
       if (cloudy) {
@@ -1184,10 +1206,26 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
     part[0] = s;
     if (ncb > 0) part[2 * pstride] = sc;
   }
-  // upward sweep (rtrn.f90:478-521)
+  // upward sweep (rtrn.f90:478-521), the (atrans, bbugas) rows of the next layer fetched one layer ahead
+  struct UpIn {
+    double atrans[U], bbugas[U];
+  };
+  auto fetch_up = [&](int l) {
+    UpIn v;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
+      v.atrans[u] = scr[0];
+      v.bbugas[u] = scr[wstride];
+    }
+    return v;
+  };
+  UpIn unx = fetch_up(0);
   for (int lev = 1; lev <= nlay; ++lev) {
     const int l = lev - 1;
     const size_t o = (size_t)l * ncol + gc;
+    const UpIn ucur = unx;
+    if (lev < nlay) unx = fetch_up(l + 1);
     bool cloudy;
     unsigned mbits = 0u;
     if (MC) {
@@ -1224,7 +1262,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       const bool on = !MC || ((mbits >> u) & 1u);
       const double efclfrac = on ? efclfrac_l : 0., cldfrac = on ? cldfrac_l : 0.;
       const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
-      const double atrans = scr[0], bbugas = scr[wstride];
+      const double atrans = ucur.atrans[u], bbugas = ucur.bbugas[u];
       if (cloudy) {
         const double atot = scr[2 * wstride], bbutot = scr[3 * wstride];
         const double gassrc = bbugas * atrans;
