@@ -9,6 +9,7 @@ import logging
 
 import numpy as np
 
+from . import device_state
 from .constants import rrtmg_constants
 from .engine import LWEngine
 from .rrtmg_common import (rrtmg_cloud_ice_props_dict, rrtmg_cloud_liquid_props_dict,
@@ -66,8 +67,9 @@ class RRTMGLongwave(TendencyComponent):
     def __init__(self, calculate_change_up_flux=False, cloud_overlap_method=None,
                  cloud_optical_properties="liquid_and_ice_clouds", cloud_ice_properties="ebert_curry_two",
                  cloud_liquid_water_properties="radius_dependent_absorption", calculate_interface_temperature=True,
-                 mcica=False, random_number_generator="mersenne_twister", device=0, **kwargs):
+                 mcica=False, random_number_generator="mersenne_twister", device=0, asynchronous=False, **kwargs):
         self.input_properties = dict(RRTMGLongwave.input_properties)
+        self._asynchronous = asynchronous  # device-resident calls only: do not synchronise / validate after each call
         self._calc_dflxdt = 1 if calculate_change_up_flux else 0
         self._mcica = mcica
         if mcica:
@@ -95,6 +97,8 @@ class RRTMGLongwave(TendencyComponent):
         super().__init__(**kwargs)
 
     def array_call(self, state):
+        if device_state.is_device_state(state):
+            return self._array_call_device(state)
         state = {k: np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v for k, v in state.items()}
         Q = mass_to_volume_mixing_ratio(state["specific_humidity"], 18.02)
         n_layers, n_columns = state["air_temperature"].shape
@@ -143,4 +147,49 @@ class RRTMGLongwave(TendencyComponent):
             self._engine.set_mcica(True, self._random_number_generator, self._permute_seed)
         self._engine.run_host(n_columns, n_layers, arrays, out)
         diagnostics["air_temperature_tendency_from_longwave"] = tendencies["air_temperature"]
+        return tendencies, diagnostics
+
+    _ABI_FROM_STATE = {
+        "play": "air_pressure", "plev": "air_pressure_on_interface_levels", "tlay": "air_temperature",
+        "tsfc": "surface_temperature", "o3vmr": "mole_fraction_of_ozone_in_air",
+        "co2vmr": "mole_fraction_of_carbon_dioxide_in_air", "ch4vmr": "mole_fraction_of_methane_in_air",
+        "n2ovmr": "mole_fraction_of_nitrous_oxide_in_air", "o2vmr": "mole_fraction_of_oxygen_in_air",
+        "cfc11vmr": "mole_fraction_of_cfc11_in_air", "cfc12vmr": "mole_fraction_of_cfc12_in_air",
+        "cfc22vmr": "mole_fraction_of_cfc22_in_air", "ccl4vmr": "mole_fraction_of_carbon_tetrachloride_in_air",
+        "emis": "surface_longwave_emissivity", "cldfr": "cloud_area_fraction_in_atmosphere_layer",
+        "taucld": "longwave_optical_thickness_due_to_cloud", "cicewp": "mass_content_of_cloud_ice_in_atmosphere_layer",
+        "cliqwp": "mass_content_of_cloud_liquid_water_in_atmosphere_layer", "reice": "cloud_ice_particle_size",
+        "reliq": "cloud_water_droplet_radius", "tauaer": "longwave_optical_thickness_due_to_aerosol",
+    }
+
+    def _array_call_device(self, state):
+        """State of torch CUDA tensors (already in this component's units and (levels, columns) layout): everything stays in
+        HBM; returns torch CUDA tensors.  See climt_b200/device_state.py."""
+        import torch
+        st = {k: (device_state.dense(v) if isinstance(v, torch.Tensor) else v) for k, v in state.items()}
+        n_layers, n_columns = st["air_temperature"].shape
+        Q, T_interface, _ = device_state.marshal(st["specific_humidity"], st["air_temperature"], st["surface_temperature"],
+                                                 st["air_pressure"], st["air_pressure_on_interface_levels"],
+                                                 want_tlev=self._calc_Tint)
+        if not self._calc_Tint:
+            T_interface = st["air_temperature_on_interface_levels"]
+        tensors = {k: st[v] for k, v in self._ABI_FROM_STATE.items()}
+        tensors.update(h2ovmr=Q, tlev=T_interface)
+        dev = st["air_temperature"].device
+        new = lambda nlev: torch.empty((nlev, n_columns), dtype=torch.float64, device=dev)  # noqa: E731
+        out = {"uflx": new(n_layers + 1), "dflx": new(n_layers + 1), "hr": new(n_layers), "uflxc": new(n_layers + 1),
+               "dflxc": new(n_layers + 1), "hrc": new(n_layers)}
+        if self._mcica:
+            self._permute_seed = np.random.randint(0, 1024) if self._random_number_generator == 0 else np.random.randint(0, 2 ** 31 - 1)
+            self._engine.set_mcica(True, self._random_number_generator, self._permute_seed)
+        self._engine.run_device(n_columns, n_layers, tensors, out)
+        device_state.finish(self._engine, self._asynchronous)
+        tendencies = {"air_temperature": out["hr"]}
+        diagnostics = {
+            "upwelling_longwave_flux_in_air": out["uflx"], "downwelling_longwave_flux_in_air": out["dflx"],
+            "upwelling_longwave_flux_in_air_assuming_clear_sky": out["uflxc"],
+            "downwelling_longwave_flux_in_air_assuming_clear_sky": out["dflxc"],
+            "air_temperature_tendency_from_longwave_assuming_clear_sky": out["hrc"],
+            "air_temperature_tendency_from_longwave": out["hr"],
+        }
         return tendencies, diagnostics

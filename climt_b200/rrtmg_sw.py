@@ -7,6 +7,7 @@ import logging
 
 import numpy as np
 
+from . import device_state
 from .constants import get_constant, rrtmg_constants
 from .engine import SWEngine
 from .rrtmg_common import (rrtmg_aerosol_input_dict, rrtmg_cloud_ice_props_dict, rrtmg_cloud_liquid_props_dict,
@@ -74,7 +75,8 @@ class RRTMGShortwave(TendencyComponent):
                  cloud_ice_properties="ebert_curry_two", cloud_liquid_water_properties="radius_dependent_absorption",
                  solar_variability_method=0, use_solar_constant_from_fortran=False, ignore_day_of_year=False,
                  facular_sunspot_amplitude=None, solar_variability_by_band=None, aerosol_type="no_aerosol", mcica=False,
-                 random_number_generator="mersenne_twister", device=0, **kwargs):
+                 random_number_generator="mersenne_twister", device=0, asynchronous=False, **kwargs):
+        self._asynchronous = asynchronous  # device-resident calls only: do not synchronise / validate after each call
         self._mcica = mcica
         if mcica:
             self._permute_seed = None
@@ -112,6 +114,8 @@ class RRTMGShortwave(TendencyComponent):
         super().__init__(**kwargs)
 
     def array_call(self, state):
+        if device_state.is_device_state(state):
+            return self._array_call_device(state)
         st = {k: np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v for k, v in state.items()}
         Q = mass_to_volume_mixing_ratio(st["specific_humidity"], 18.02)
         assert st["air_pressure"].shape[0] + 1 == st["air_pressure_on_interface_levels"].shape[0]
@@ -165,4 +169,59 @@ class RRTMGShortwave(TendencyComponent):
                               adjes=float(np.asarray(st["flux_adjustment_for_earth_sun_distance"]).item()),
                               dyofyr=day_of_year, solcycfrac=float(np.asarray(st["solar_cycle_fraction"]).item()))
         diagnostics["air_temperature_tendency_from_shortwave"][:] = tendencies["air_temperature"]
+        return tendencies, diagnostics
+
+    _ABI_FROM_STATE = {
+        "play": "air_pressure", "plev": "air_pressure_on_interface_levels", "tlay": "air_temperature",
+        "tsfc": "surface_temperature", "o3vmr": "mole_fraction_of_ozone_in_air",
+        "co2vmr": "mole_fraction_of_carbon_dioxide_in_air", "ch4vmr": "mole_fraction_of_methane_in_air",
+        "n2ovmr": "mole_fraction_of_nitrous_oxide_in_air", "o2vmr": "mole_fraction_of_oxygen_in_air",
+        "asdir": "surface_albedo_for_direct_shortwave", "asdif": "surface_albedo_for_diffuse_shortwave",
+        "aldir": "surface_albedo_for_direct_near_infrared", "aldif": "surface_albedo_for_diffuse_near_infrared",
+        "cldfr": "cloud_area_fraction_in_atmosphere_layer", "taucld": "shortwave_optical_thickness_due_to_cloud",
+        "ssacld": "single_scattering_albedo_due_to_cloud", "asmcld": "cloud_asymmetry_parameter",
+        "fsfcld": "cloud_forward_scattering_fraction", "cicewp": "mass_content_of_cloud_ice_in_atmosphere_layer",
+        "cliqwp": "mass_content_of_cloud_liquid_water_in_atmosphere_layer", "reice": "cloud_ice_particle_size",
+        "reliq": "cloud_water_droplet_radius", "tauaer": "shortwave_optical_thickness_due_to_aerosol",
+        "ssaaer": "single_scattering_albedo_due_to_aerosol", "asmaer": "aerosol_asymmetry_parameter",
+        "ecaer": "aerosol_optical_depth_at_55_micron",
+    }
+
+    def _array_call_device(self, state):
+        """State of torch CUDA tensors (this component's units, (levels, columns) layout): zero copy, torch CUDA outputs.
+        Scalars (time / day_of_year, flux_adjustment_for_earth_sun_distance, solar_cycle_fraction) stay host values."""
+        import torch
+        st = {k: (device_state.dense(v) if isinstance(v, torch.Tensor) and v.is_cuda else v) for k, v in state.items()}
+        n_layers, n_columns = st["air_temperature"].shape
+        Q, Tint, coszen = device_state.marshal(st["specific_humidity"], st["air_temperature"], st["surface_temperature"],
+                                               st["air_pressure"], st["air_pressure_on_interface_levels"],
+                                               zenith=st["zenith_angle"])
+        if self._ignore_day_of_year:
+            day_of_year = 0
+        else:
+            t = st.get("time")
+            day_of_year = t.timetuple().tm_yday if t is not None else int(st.get("day_of_year", 1))
+        tensors = {k: st[v] for k, v in self._ABI_FROM_STATE.items()}
+        tensors.update(h2ovmr=Q, tlev=Tint, coszen=coszen)
+        dev = st["air_temperature"].device
+        new = lambda nlev: torch.empty((nlev, n_columns), dtype=torch.float64, device=dev)  # noqa: E731
+        out = {"uflx": new(n_layers + 1), "dflx": new(n_layers + 1), "hr": new(n_layers), "uflxc": new(n_layers + 1),
+               "dflxc": new(n_layers + 1), "hrc": new(n_layers)}
+        if self._mcica:
+            self._permute_seed = np.random.randint(0, 1024) if self._random_number_generator == 0 else np.random.randint(0, 2 ** 31 - 1)
+            self._engine.set_mcica(True, self._random_number_generator, self._permute_seed)
+
+        def scalar(v):
+            return float(v.reshape(-1)[0].item()) if isinstance(v, torch.Tensor) else float(np.asarray(v).reshape(-1)[0])
+        self._engine.run_device(n_columns, n_layers, tensors, out, adjes=scalar(st["flux_adjustment_for_earth_sun_distance"]),
+                                dyofyr=day_of_year, solcycfrac=scalar(st["solar_cycle_fraction"]))
+        device_state.finish(self._engine, self._asynchronous)
+        tendencies = {"air_temperature": out["hr"]}
+        diagnostics = {
+            "upwelling_shortwave_flux_in_air": out["uflx"], "downwelling_shortwave_flux_in_air": out["dflx"],
+            "upwelling_shortwave_flux_in_air_assuming_clear_sky": out["uflxc"],
+            "downwelling_shortwave_flux_in_air_assuming_clear_sky": out["dflxc"],
+            "air_temperature_tendency_from_shortwave_assuming_clear_sky": out["hrc"],
+            "air_temperature_tendency_from_shortwave": out["hr"],
+        }
         return tendencies, diagnostics

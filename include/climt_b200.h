@@ -230,6 +230,13 @@ int cb200_cork_lw_run_host(cb200_cork_engine* e, int ncol, int nlev, double diff
 int cb200_cork_sw_run_host(cb200_cork_engine* e, int ncol, int nlev, const double* solar_flux, const cb200_cork_inputs* in,
                            const cb200_cork_outputs* out);
 
+/* ============================== device-side marshal ==============================
+ * What the components' array_call computes in numpy before calling the engines, for state that already lives in HBM:
+ * h2ovmr = q * 28.964 / 18.02 (climt/_core/util.py:47-86), tlev by ln-p weights with tlev[0] = tsfc, tlev[nlay] = t[nlay-1]
+ * (climt/_core/util.py:89-142), coszen = cos(zenith) (rrtmg/sw/component.py:591).  Any output pointer may be NULL. */
+int cb200_marshal_device(int device, int ncol, int nlay, const double* q, const double* t, const double* tsfc, const double* p,
+                         const double* p_int, const double* zenith, double* h2ovmr, double* tlev, double* coszen, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
