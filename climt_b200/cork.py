@@ -1,13 +1,14 @@
-"""CORK correlated-k radiation -- drop-ins for climt.CorkLongwaveRadiation / climt.CorkShortwaveRadiation.
+"""CORK radiation -- drop-ins for climt.CorkLongwaveRadiation / climt.CorkShortwaveRadiation.
 
-Mirrors climt/_components/cork/lw/component.py:20-373 and cork/sw/component.py:20-496 for ``optics="correlated_k"``
-(additive overlap): same constructor arguments, property dictionaries, aliases, units and ``array_call`` return
-values.  The optical-depth interpolation, Planck sources, transport sweeps, flux sums and heating rates run in the
-CUDA engine (csrc/cork_engine.cu) behind the C ABI of include/climt_b200.h; there is no CPU implementation here.
+Mirrors climt/_components/cork/lw/component.py:20-466 and cork/sw/component.py:20-532 for ``optics="correlated_k"``
+(additive overlap) and ``optics="parmentier"`` (picket-fence analytic optics, the constructors' default): same
+constructor arguments, property dictionaries, aliases, units and ``array_call`` return values.  The optical depths
+(k-table interpolation or Freedman/Parmentier fits), Planck sources, transport sweeps, flux sums and heating rates
+run in the CUDA engine (csrc/cork_engine.cu) behind the C ABI of include/climt_b200.h; there is no CPU
+implementation here.
 
-Not provided (raise NotImplementedError at construction): ``optics="parmentier"`` (picket-fence analytic optics,
-cork/optics/parmentier.py -- scalar Python in the reference, outside BASELINE.json's configs), ESFT-overlap tables,
-and ``diagnostics_level >= 1`` (per-g-point diagnostic dumps).
+Not provided (raise NotImplementedError at construction): ESFT-overlap tables and ``diagnostics_level >= 1``
+(per-g-point diagnostic dumps).
 """
 import ctypes
 import os
@@ -84,7 +85,8 @@ class CorkTable(ctypes.Structure):
         ("rayleigh_coefficient", _dp), ("co2_logk", ctypes.c_int), ("premixed", ctypes.c_int)]
 
 
-CORK_IN = ("T", "p", "p_int", "T_surf", "q_h2o", "co2_vmr", "gas_q", "emissivity", "tau_cloud", "zenith", "albedo", "ssa_cloud", "g_cloud")
+CORK_IN = ("T", "p", "p_int", "T_surf", "q_h2o", "co2_vmr", "gas_q", "emissivity", "tau_cloud", "zenith", "albedo", "ssa_cloud", "g_cloud",
+           "T_irr", "T_int", "bond_albedo")
 CORK_OUT = ("up_broad", "down_broad", "heating_rate", "up_band", "down_band", "tau_band", "trans_band", "hr_band")
 
 
@@ -94,6 +96,77 @@ class CorkInputs(ctypes.Structure):
 
 class CorkOutputs(ctypes.Structure):
     _fields_ = [(n, _dp) for n in CORK_OUT]
+
+
+PICKET_MAX_REGIONS = 8
+
+
+class PicketCoeffs(ctypes.Structure):
+    """cb200_picket_coeffs (include/climt_b200.h)."""
+    _ab = ctypes.c_double * 2 * PICKET_MAX_REGIONS
+    _fields_ = [("nregion", ctypes.c_int), ("T_eff_boundaries", ctypes.c_double * (PICKET_MAX_REGIONS + 1)),
+                ("log10_gamma_v1_ab", _ab), ("log10_gamma_v2_ab", _ab), ("log10_gamma_v3_ab", _ab), ("beta_ab", _ab),
+                ("log10_gamma_P_quad", ctypes.c_double * 3)] + [
+        (n, ctypes.c_double) for n in ("T_boundary", "a_hi", "b_hi", "c_hi", "a_lo", "b_lo", "c_lo")]
+
+
+def _load_npz(kind, name_or_path, package_dir):
+    path = name_or_path if os.path.isfile(name_or_path) else os.path.join(_DATA, package_dir, f"{name_or_path}.npz")
+    if not os.path.isfile(path):
+        raise FileNotFoundError(f"No {kind} named {name_or_path!r}")
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+def load_parmentier_coefficients(name_or_path):
+    """cork/optics/parmentier.py:77-97: "solar_composition" (shipped) or the path of an .npz file."""
+    return _load_npz("Parmentier coefficient table", name_or_path, "parmentier")
+
+
+def load_freedman2014_coefficients():
+    """cork/optics/parmentier.py:36-52."""
+    return _load_npz("Rosseland-mean fit", "freedman2014", "parmentier")
+
+
+def load_stellar_spectrum(name_or_path):
+    """cork/optics/stellar.py:7-29: "sun", "trappist1" or a path -> wavenumber [cm-1], irradiance [W m-2 / cm-1]."""
+    z = _load_npz("stellar spectrum", name_or_path, "stellar_spectra")
+    return {"wavenumber": np.array(z["wavenumber"]), "irradiance": np.array(z["irradiance"])}
+
+
+def integrate_spectrum_over_bands(spectrum, band_wavenumber_limits):
+    """cork/optics/stellar.py:32-62 (trapezoid over the band, end points interpolated); host-side, constructor only."""
+    wn, irr = spectrum["wavenumber"], spectrum["irradiance"]
+    flux = np.zeros(band_wavenumber_limits.shape[0])
+    for b, (wn_lo, wn_hi) in enumerate(band_wavenumber_limits):
+        mask = (wn > wn_lo) & (wn < wn_hi)
+        wn_band = np.concatenate(([wn_lo], wn[mask], [wn_hi]))
+        irr_band = np.concatenate(([np.interp(wn_lo, wn, irr)], irr[mask], [np.interp(wn_hi, wn, irr)]))
+        flux[b] = np.trapezoid(irr_band, wn_band)
+    return flux
+
+
+def make_picket_coeffs(coefficients, freedman):
+    c = PicketCoeffs()
+    bounds = np.asarray(coefficients["T_eff_boundaries"], dtype=np.float64)
+    nreg = len(bounds) - 1
+    if not 1 <= nreg <= PICKET_MAX_REGIONS:
+        raise ValueError(f"Parmentier coefficient table: 1..{PICKET_MAX_REGIONS} T_eff regions supported, got {nreg}")
+    c.nregion = nreg
+    for i, v in enumerate(bounds):
+        c.T_eff_boundaries[i] = float(v)
+    for name in ("log10_gamma_v1_ab", "log10_gamma_v2_ab", "log10_gamma_v3_ab", "beta_ab"):
+        ab = np.asarray(coefficients[name], dtype=np.float64)
+        if ab.shape != (nreg, 2):
+            raise ValueError(f"{name}: expected shape {(nreg, 2)}, got {ab.shape}")
+        dst = getattr(c, name)
+        for i in range(nreg):
+            dst[i][0], dst[i][1] = float(ab[i, 0]), float(ab[i, 1])
+    for i in range(3):
+        c.log10_gamma_P_quad[i] = float(np.asarray(coefficients["log10_gamma_P_quad"])[i])
+    for n in ("T_boundary", "a_hi", "b_hi", "c_hi", "a_lo", "b_lo", "c_lo"):
+        setattr(c, n, float(freedman[n]))
+    return c
 
 
 def table_flags(table):
@@ -110,6 +183,8 @@ def _bind(L):
     vp = ctypes.c_void_p
     L.cb200_cork_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(CorkTable), ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                     ctypes.c_int]
+    L.cb200_cork_create_picket.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(PicketCoeffs), ctypes.c_int, ctypes.c_double,
+                                           ctypes.c_double, ctypes.c_double, ctypes.c_int]
     L.cb200_cork_destroy.argtypes = [vp]
     L.cb200_cork_destroy.restype = None
     L.cb200_cork_last_error.argtypes = [vp]
@@ -178,15 +253,27 @@ def make_ctable(table, co2_logk=CO2_INTERP_LOGK):
 class CorkEngine:
     """Handle of one cb200_cork_engine (one k-table resident in HBM)."""
 
-    def __init__(self, table, g=None, cpd=None, sigma=None, device=0):
+    def __init__(self, table, g=None, cpd=None, sigma=None, device=0, picket=None):
+        """table: a k-table (name, path or dict); or None with picket=("lw" | "sw", coefficients, freedman) for the
+        picket-fence engines (cb200_cork_create_picket)."""
         self._L = _native.lib()
         _bind(self._L)
-        self.table = load_k_table(table) if isinstance(table, (str, os.PathLike)) else table
-        self.ctable, self._keep = make_ctable(self.table)
         g = get_constant("gravitational_acceleration", "m/s^2") if g is None else g
         cpd = get_constant("heat_capacity_of_dry_air_at_constant_pressure", "J/kg/K") if cpd is None else cpd
         sigma = get_constant("stefan_boltzmann_constant", "W/m^2/K^4") if sigma is None else sigma
+        self.sigma = sigma
         self._h = ctypes.c_void_p()
+        if picket is not None:
+            which, coefficients, freedman = picket
+            self.table = None
+            self.picket = make_picket_coeffs(coefficients, freedman)
+            if self._L.cb200_cork_create_picket(ctypes.byref(self._h), ctypes.byref(self.picket), 1 if which == "lw" else 0,
+                                                g, cpd, sigma, device):
+                raise RuntimeError(self._L.cb200_global_error().decode())
+            self.nband, self.ngpt, self.ngas = (2 if which == "lw" else 3), 1, 1
+            return
+        self.table = load_k_table(table) if isinstance(table, (str, os.PathLike)) else table
+        self.ctable, self._keep = make_ctable(self.table)
         if self._L.cb200_cork_create(ctypes.byref(self._h), ctypes.byref(self.ctable), g, cpd, sigma, device):
             raise RuntimeError(self._L.cb200_global_error().decode())
         self.nband, self.ngpt, self.ngas = self.ctable.nband, self.ctable.ngpt, self.ctable.ngas
@@ -209,7 +296,7 @@ class CorkEngine:
         L, n, nb = nlev, ncol, self.nband
         ins = {"T": (L, n), "p": (L, n), "p_int": (L + 1, n), "T_surf": (n,), "q_h2o": (L, n), "co2_vmr": (L, n),
                "gas_q": (self.ngas, L, n), "emissivity": (nb, n), "tau_cloud": (L, n, nb), "zenith": (n,), "albedo": (n,),
-               "ssa_cloud": (L, n, nb), "g_cloud": (L, n, nb)}
+               "ssa_cloud": (L, n, nb), "g_cloud": (L, n, nb), "T_irr": (n,), "T_int": (n,), "bond_albedo": (n,)}
         outs = {"up_broad": (L + 1, n), "down_broad": (L + 1, n), "heating_rate": (L, n), "up_band": (nb, L + 1, n),
                 "down_band": (nb, L + 1, n), "tau_band": (nb, L, n), "trans_band": (nb, L, n), "hr_band": (nb, L, n)}
         return ins, outs
@@ -247,13 +334,16 @@ class CorkEngine:
     def solar_flux(self, earth_sun_factor):
         """solar_source_per_gpoint * earth_sun_factor with numpy's dtype rules, as the reference evaluates it
         (cork/sw/component.py:371-372: a float32 table gives a float32 product), handed to the engine as float64."""
-        if "solar_source_per_gpoint" not in self.table:
+        if self.table is None or "solar_source_per_gpoint" not in self.table:
             raise ValueError("cork: this table has no solar_source_per_gpoint (not a shortwave table)")
         return np.ascontiguousarray(np.asarray(self.table["solar_source_per_gpoint"]) * float(earth_sun_factor), dtype=np.float64)
 
-    def sw_host(self, ncol, nlev, arrays, out=None, earth_sun_factor=1.0, bands=True):
+    def sw_host(self, ncol, nlev, arrays, out=None, earth_sun_factor=1.0, bands=True, solar_flux=None):
+        """solar_flux: (nband, ngpt) W m-2 already scaled (picket-fence engines: mandatory); else the table's * earth_sun_factor"""
         pin, pout, out, keep = self._pack_host(ncol, nlev, arrays, out, "sw", bands)
-        sf = self.solar_flux(earth_sun_factor)
+        sf = self.solar_flux(earth_sun_factor) if solar_flux is None else np.ascontiguousarray(solar_flux, dtype=np.float64)
+        if sf.shape != (self.nband, self.ngpt):
+            raise ValueError(f"solar_flux: expected shape {(self.nband, self.ngpt)}, got {sf.shape}")
         rc = self._L.cb200_cork_sw_run_host(self._h, ncol, nlev, sf.ctypes.data_as(_dp), ctypes.byref(pin), ctypes.byref(pout))
         if rc:
             raise (ValueError if rc == -3 else RuntimeError)(self._err())
@@ -283,8 +373,9 @@ class CorkEngine:
     def lw_device(self, ncol, nlev, tensors, out, diffusivity_factor=DIFFUSIVITY_FACTOR, stream=None):
         self._run_device(self._L.cb200_cork_lw_run_device, ncol, nlev, diffusivity_factor, tensors, out, stream)
 
-    def sw_device(self, ncol, nlev, tensors, out, earth_sun_factor=1.0, stream=None):
-        self._run_device(self._L.cb200_cork_sw_run_device, ncol, nlev, self.solar_flux(earth_sun_factor), tensors, out, stream)
+    def sw_device(self, ncol, nlev, tensors, out, earth_sun_factor=1.0, stream=None, solar_flux=None):
+        sf = self.solar_flux(earth_sun_factor) if solar_flux is None else np.ascontiguousarray(solar_flux, dtype=np.float64)
+        self._run_device(self._L.cb200_cork_sw_run_device, ncol, nlev, sf, tensors, out, stream)
 
     def enable_timing(self, on=True):
         self._L.cb200_cork_enable_timing(self._h, 1 if on else 0)
@@ -315,24 +406,33 @@ def _p(dims, units, alias=None):
 class _CorkBase(TendencyComponent):
     _which = "lw"
 
-    def _setup(self, optics, table, kwargs, device):
-        if optics == "parmentier":
-            raise NotImplementedError("optics='parmentier' (analytic picket-fence optics) is not part of the CUDA engine; "
-                                      "use optics='correlated_k' with a k-table")
-        if optics != "correlated_k":
+    def _setup(self, optics, table, kwargs, device, coefficients="solar_composition"):
+        if optics not in ("parmentier", "correlated_k"):
             raise ValueError(f"Unknown optics mode: {optics}")
         self._optics_mode = optics
+        self._diagnostics_level = kwargs.pop("diagnostics_level", 0)
+        if self._diagnostics_level:
+            raise NotImplementedError("diagnostics_level >= 1 (per-g-point dumps) is not provided by the CUDA engine")
+        if optics == "parmentier":  # cork/lw/component.py:41-44, cork/sw/component.py:32-35
+            self._coefficients = load_parmentier_coefficients(coefficients)
+            self._freedman_coeffs = load_freedman2014_coefficients()
+            self._num_bands = 2 if self._which == "lw" else 3
+            self._has_co2_axis = False
+            self._engine = CorkEngine(None, device=device, picket=(self._which, self._coefficients, self._freedman_coeffs))
+            _num_bands[self._which] = self._num_bands
+            return
         self._table = load_k_table(table) if isinstance(table, (str, os.PathLike)) else table
         k = self._table["k_coefficients"]
         self._num_bands, self._num_gpts = k.shape[1], k.shape[2]
         (self._gas_names, _has_h2o, self._has_co2_axis, self._fully_premixed, self._premixed_bg) = table_flags(self._table)
-        self._diagnostics_level = kwargs.pop("diagnostics_level", 0)
-        if self._diagnostics_level:
-            raise NotImplementedError("diagnostics_level >= 1 (per-g-point dumps) is not provided by the CUDA engine")
         self._engine = CorkEngine(self._table, device=device)
         _num_bands[self._which] = self._num_bands
 
     def _gas_props(self, props, with_co2):
+        if self._optics_mode == "parmentier":  # cork/lw/component.py:96-106, cork/sw/component.py:115-125
+            props["irradiation_temperature"] = _p(["*"], "degK", "T_irr")
+            props["internal_temperature"] = _p(["*"], "degK", "T_int")
+            return
         if self._premixed_bg:
             props["specific_humidity"] = _p(["mid_levels", "*"], "kg/kg", "h2o")
             if with_co2 and self._has_co2_axis:
@@ -344,6 +444,10 @@ class _CorkBase(TendencyComponent):
 
     def _gas_arrays(self, state, nlev, arrays):
         """the gas part of array_call (cork/lw/component.py:243-287): what goes to the engine, in its units"""
+        if self._optics_mode == "parmentier":
+            arrays["T_irr"] = state["T_irr"].reshape(-1)
+            arrays["T_int"] = state["T_int"].reshape(-1)
+            return
         if self._fully_premixed:
             return
         if self._premixed_bg:
@@ -366,13 +470,13 @@ class _CorkBase(TendencyComponent):
 
 
 class CorkLongwaveRadiation(_CorkBase):
-    """Drop-in for climt.CorkLongwaveRadiation (cork/lw/component.py:20-373), optics="correlated_k"."""
+    """Drop-in for climt.CorkLongwaveRadiation (cork/lw/component.py:20-466)."""
     _which = "lw"
 
     def __init__(self, optics="parmentier", table=None, coefficients="solar_composition", rosseland_mean_fit="freedman2014",
                  diffusivity_factor=DIFFUSIVITY_FACTOR, device=0, **kwargs):
         self._diffusivity_factor = diffusivity_factor
-        self._setup(optics, table, kwargs, device)
+        self._setup(optics, table, kwargs, device, coefficients)
         super().__init__(**kwargs)
 
     @property
@@ -438,15 +542,28 @@ class CorkLongwaveRadiation(_CorkBase):
 
 
 class CorkShortwaveRadiation(_CorkBase):
-    """Drop-in for climt.CorkShortwaveRadiation (cork/sw/component.py:20-496), optics="correlated_k"."""
+    """Drop-in for climt.CorkShortwaveRadiation (cork/sw/component.py:20-532)."""
     _which = "sw"
 
     def __init__(self, optics="parmentier", table=None, coefficients="solar_composition", stellar_spectrum="sun",
                  rosseland_mean_fit="freedman2014", device=0, **kwargs):
         self._bond_albedo_feedback = kwargs.pop("bond_albedo_feedback", False)
-        self._setup(optics, table, kwargs, device)
-        self._solar_source = self._table["solar_source_per_gpoint"]
-        self._rayleigh = self._table.get("rayleigh_coefficient", None)
+        self._setup(optics, table, kwargs, device, coefficients)
+        if optics == "parmentier":
+            # fallback solar flux for un-irradiated columns: the stellar spectrum over three equal-width bands
+            # (cork/sw/component.py:36-62)
+            try:
+                spec = load_stellar_spectrum(stellar_spectrum)
+                wn = spec["wavenumber"]
+                wn_lo, wn_hi = wn.min(), wn.max()
+                bw = (wn_hi - wn_lo) / 3.0
+                limits = np.array([[wn_lo, wn_lo + bw], [wn_lo + bw, wn_lo + 2 * bw], [wn_lo + 2 * bw, wn_hi]])
+                self._solar_flux_per_band = integrate_spectrum_over_bands(spec, limits)
+            except (FileNotFoundError, KeyError):
+                self._solar_flux_per_band = np.array([1361.0 / 3.0] * 3)
+        else:
+            self._solar_source = self._table["solar_source_per_gpoint"]
+            self._rayleigh = self._table.get("rayleigh_coefficient", None)
         super().__init__(**kwargs)
 
     @property
@@ -489,6 +606,27 @@ class CorkShortwaveRadiation(_CorkBase):
     def num_shortwave_bands(self):
         return self._num_bands
 
+    def _parmentier_call(self, ncol, nlev, arrays, earth_sun_factor):
+        """The picket-fence branch of CorkShortwaveRadiation.array_call (cork/sw/component.py:242-306): stellar flux from
+        the hottest irradiation temperature, one engine pass, and with bond_albedo_feedback a second pass whose T_eff uses
+        the Bond albedo of the first (bond_albedo_from_fluxes, cork/optics/parmentier.py:156-163)."""
+        sigma = self._engine.sigma
+        T_irr_max = arrays["T_irr"].max()
+        if T_irr_max > 0:
+            F0 = sigma * T_irr_max**4
+            per_band = np.array([F0 / 3.0] * 3)
+        else:
+            per_band = self._solar_flux_per_band
+        solar_flux = per_band.reshape(3, 1) * np.ones((3, 1)) * earth_sun_factor
+        o = None
+        for it in range(2 if self._bond_albedo_feedback else 1):
+            if it:
+                up_toa, down_toa = o["up_broad"][-1, :], o["down_broad"][-1, :]
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    arrays["bond_albedo"] = np.clip(np.where(down_toa > 0, up_toa / down_toa, 0.0), 0.0, 1.0)
+            o = self._engine.sw_host(ncol, nlev, arrays, solar_flux=solar_flux, out=o)
+        return o
+
     def array_call(self, state):
         T, p_int = _alias(state, "T", "air_temperature"), _alias(state, "p_int", "air_pressure_on_interface_levels")
         st = _AliasView(state, self.input_properties)
@@ -503,7 +641,10 @@ class CorkShortwaveRadiation(_CorkBase):
         arrays["ssa_cloud"] = st["ssa_cloud"].reshape(nlev, ncol, nb)
         arrays["g_cloud"] = st["g_cloud"].reshape(nlev, ncol, nb)
         esf = float(np.asarray(st["earth_sun_factor"]).reshape(-1)[0])  # cork/sw/component.py:370
-        o = self._engine.sw_host(ncol, nlev, arrays, earth_sun_factor=esf)
+        if self._optics_mode == "parmentier":
+            o = self._parmentier_call(ncol, nlev, arrays, esf)
+        else:
+            o = self._engine.sw_host(ncol, nlev, arrays, earth_sun_factor=esf)
         hr = o["heating_rate"].reshape(shape_T)
         diagnostics = {
             "upwelling_shortwave_flux_in_air": o["up_broad"].reshape(shape_pint),

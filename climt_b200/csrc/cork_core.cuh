@@ -24,7 +24,19 @@ namespace cork {
 constexpr double kMolarMassDryAir = 28.970;  // cork/common.py:9
 constexpr double kMolarMassH2O = 18.015;     // cork/common.py:11
 
+// Picket-fence ("parmentier") optics: the coefficient files of cork/optics/parmentier.py, by value
+// (freedman2014.npz, solar_composition.npz; same members as cb200_picket_coeffs).
+constexpr int kPicketMaxRegions = 8;
+struct Picket {
+  int nregion;
+  double bounds[kPicketMaxRegions + 1];
+  double gv1[kPicketMaxRegions][2], gv2[kPicketMaxRegions][2], gv3[kPicketMaxRegions][2], beta[kPicketMaxRegions][2];
+  double quad[3];
+  double T_boundary, a_hi, b_hi, c_hi, a_lo, b_lo, c_lo;
+};
+
 struct Table {
+  int optics;                             // 0 = correlated-k table, 1 = picket fence (no table: `pk` below)
   int ngas, nband, ngpt, nT, nP, nX, nC;  // nX / nC are 1 when the axis is absent
   int hasX, hasC, has_cont, co2_logk;
   int U, nchunk;                          // g-points per unit; units per band
@@ -40,6 +52,7 @@ struct Table {
   const double* log_cont;                 // [iT][iP][iX][band]  = log(max(continuum_kappa, 1e-40))
   const double* solar;                    // [band][g]
   const double* rayleigh;                 // [band] or null
+  Picket pk;                              // optics == 1
 };
 
 struct Consts {
@@ -60,6 +73,9 @@ struct In {
   const double *zenith, *albedo;
   const double *ssa_cloud, *g_cloud;  // (nlev, ncol, nband), with tau_cloud
   const double* solar_flux;           // (nband, ngpt): solar_source * earth_sun_factor, prepared by the caller
+  // picket fence
+  const double *T_irr, *T_int;        // (ncol) irradiation / internal temperature
+  const double* bond_albedo;          // (ncol) or null (= 0): SW Bond-albedo feedback, second pass
 };
 
 struct Out {
@@ -100,6 +116,45 @@ CB_HD Br bracket(const double* __restrict__ grid, int n, double v) {
   return {i, f};
 }
 
+// ---- picket-fence optics ----------------------------------------------------------------------------------------
+// Freedman et al. (2014) Rosseland mean opacity [m2 kg-1] (compute_rosseland_mean_opacity, cork/optics/parmentier.py:55-74)
+CB_HD double picket_kappa_R(const Picket& P, double T, double p) {
+  const double log_T = log10(fmax(T, 10.0));
+  const double log_P = log10(fmax(p * 10.0, 1.0));
+  const double log_k = T < P.T_boundary ? P.a_lo * log_T + P.b_lo * log_P + P.c_lo : P.a_hi * log_T + P.b_hi * log_P + P.c_hi;
+  return pow(10.0, log_k) * 0.1;
+}
+
+struct PicketCol {
+  double gv[3], beta, R;
+};
+// Per-column ratio coefficients: T_eff of Lee et al. (2021) Eq. 20 with mu* = 1/4 (cork/lw/component.py:386-396,
+// cork/sw/component.py:511-514) and lookup_ratio_coefficients (cork/optics/parmentier.py:100-153).  The region search
+// keeps the reference's fall-back to region 0 when no interval contains T_eff.
+CB_HD PicketCol picket_column(const Picket& P, double T_irr, double T_int, double A_B) {
+  double T_eff = pow(pow(T_int, 4.0) + (1.0 - A_B) * 0.25 * pow(T_irr, 4.0), 0.25);
+  T_eff = fmax(T_eff, 100.0);
+  const double X = log10(fmax(T_eff, 10.0));
+  int r = 0;
+  for (int i = 0; i < P.nregion; ++i)
+    if (T_eff >= P.bounds[i] && T_eff < P.bounds[i + 1]) { r = i; break; }
+  PicketCol o;
+  o.gv[0] = pow(10.0, P.gv1[r][0] + P.gv1[r][1] * X);
+  o.gv[1] = pow(10.0, P.gv2[r][0] + P.gv2[r][1] * X);
+  o.gv[2] = pow(10.0, P.gv3[r][0] + P.gv3[r][1] * X);
+  o.beta = fmin(fmax(P.beta[r][0] + P.beta[r][1] * X, 0.01), 0.99);
+  const double gamma_P = fmax(pow(10.0, P.quad[0] + P.quad[1] * X + P.quad[2] * (X * X)), 1.0);
+  const double gm1 = gamma_P - 1.0;
+  const double disc = gm1 * gm1 + 4.0 * o.beta * (1.0 - o.beta) * gm1;
+  if (disc < 0) {
+    o.R = 1.0;
+  } else {
+    const double den = 2.0 * o.beta * (1.0 - o.beta);
+    o.R = fmax(1.0 + gm1 / den + sqrt(disc) / den, 1.0);
+  }
+  return o;
+}
+
 // ---- prep: interpolation coordinates and layer amounts of one (column, level) ------------------------------------
 // (_additive_co2_fast, correlated_k.py:526-548; component glue cork/lw/component.py:259-287)
 CB_HD void prep_cell(const Table& Tb, const Consts& K, const In& in, const Work& W, int c0, int c, int l) {
@@ -107,6 +162,12 @@ CB_HD void prep_cell(const Table& Tb, const Consts& K, const In& in, const Work&
   const size_t o = (size_t)l * ncol + c0 + c;
   const size_t fs = (size_t)nlev * ncc;
   double* ws = W.ws + (size_t)l * ncc + c;
+  if (Tb.optics == 1) {  // picket fence: Rosseland mean opacity and layer mass (cork/lw/component.py:402-410)
+    ws[F_FT * fs] = picket_kappa_R(Tb.pk, in.T[o], in.p[o]);
+    ws[F_AMT0 * fs] = fabs(in.p_int[(size_t)(l + 1) * ncol + c0 + c] - in.p_int[o]) / K.g;
+    W.idx[(size_t)l * ncc + c] = 0;
+    return;
+  }
   const Br bT = bracket(Tb.T_grid, Tb.nT, in.T[o]);
   const Br bP = bracket(Tb.p_grid_log, Tb.nP, log(fmax(in.p[o], 1.0)));
   Br bX{0, 0.0}, bC{0, 0.0};
@@ -234,7 +295,9 @@ CB_HD void gas_tau(const Table& Tb, const double* __restrict__ ws, size_t fs, in
 
 // ---- longwave unit -------------------------------------------------------------------------------------------------
 // scratch rows per unit: 2U  (trans, planck source per g-point)
-template <int U, typename KT>
+// OPT = 1: picket-fence optics (U = 1; band 0 = kappa_1 with Planck share beta, band 1 = kappa_2 with 1 - beta;
+// CorkLongwaveRadiation._parmentier_optics, cork/lw/component.py:375-422) in place of the k-table and planck_fraction.
+template <int U, typename KT, int OPT = 0>
 CB_HD void lw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W, int c0, int c, int band, int chunk, int unit) {
   const int ncol = in.ncol, nlev = in.nlev, ncc = W.ncc;
   const size_t gc = (size_t)c0 + c;
@@ -245,13 +308,25 @@ CB_HD void lw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
 #pragma unroll
   for (int u = 0; u < U; ++u) w[u] = CB_LDG(Tb.weights + band * Tb.ngpt + g0 + u);
   const int bpf = band < Tb.nband_pf ? band : Tb.nband_pf - 1;
-  const double* __restrict__ pf = Tb.planck + (size_t)bpf * Tb.ngpt_pf + g0;
+  const double* __restrict__ pf = OPT ? nullptr : Tb.planck + (size_t)bpf * Tb.ngpt_pf + g0;
   const size_t pfT = (size_t)Tb.nband_pf * Tb.ngpt_pf;
   double* __restrict__ part = W.part + (size_t)unit * 3 * ps + c;
   double* __restrict__ scr = W.scr + (size_t)unit * W.nscr * fs + c;
+  double pk_frac = 0.0, pk_c2 = 0.0, pk_R = 1.0;
+  if (OPT == 1) {
+    const PicketCol pc = picket_column(Tb.pk, in.T_irr[gc], in.T_int[gc], 0.0);
+    pk_frac = band == 0 ? pc.beta : 1.0 - pc.beta;
+    pk_c2 = pc.beta / pc.R + 1.0 - pc.beta;  // compute_thermal_opacities, cork/optics/parmentier.py:31-33
+    pk_R = pc.R;
+  }
   // surface source and upward boundary (lw/kernels.py:29-47, 92-95)
   double up[U];
-  {
+  if (OPT == 1) {
+    const double Ts = in.T_surf[gc];
+    const double em = in.emissivity[(size_t)band * ncol + gc];
+    up[0] = em * (pk_frac * (K.sigma * pow(Ts, 4.0)));  // cork/lw/component.py:418-420
+    part[0] = w[0] * up[0];
+  } else {
     const double Ts = in.T_surf[gc];
     const Br bs = bracket(Tb.T_grid, Tb.nT, Ts);
     const double planck = K.sigma * ((Ts * Ts) * (Ts * Ts));
@@ -272,19 +347,27 @@ CB_HD void lw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
     const double* __restrict__ ws = W.ws + (size_t)l * ncc + c;
     const int idx = W.idx[(size_t)l * ncc + c];
     double tau[U];
-    gas_tau<U, KT>(Tb, ws, fs, idx, band, chunk, tau);
     const double tc = in.tau_cloud ? in.tau_cloud[((size_t)l * ncol + gc) * Tb.nband + band] : 0.0;
     const int iT = idx & 255;
     const double fT = ws[F_FT * fs];
     const double Tl = in.T[(size_t)l * ncol + gc];
-    const double planck = K.sigma * ((Tl * Tl) * (Tl * Tl));
+    double planck;
     double f0[U], f1[U];
-    ldk<U>(pf + iT * pfT, f0); ldk<U>(pf + (iT + 1) * pfT, f1);
+    if (OPT == 1) {
+      const double kappa_2 = ws[F_FT * fs] * pk_c2;  // ws[F_FT] holds kappa_R here (prep_cell)
+      tau[0] = (band == 0 ? pk_R * kappa_2 : kappa_2) * ws[F_AMT0 * fs];
+      planck = K.sigma * pow(Tl, 4.0);
+      f0[0] = pk_frac; f1[0] = 0.0;
+    } else {
+      gas_tau<U, KT>(Tb, ws, fs, idx, band, chunk, tau);
+      planck = K.sigma * ((Tl * Tl) * (Tl * Tl));
+      ldk<U>(pf + iT * pfT, f0); ldk<U>(pf + (iT + 1) * pfT, f1);
+    }
     double su = 0.0, st = 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const double t = tau[u] + tc;
-      const double src = (f0[u] * (1.0 - fT) + f1[u] * fT) * planck;
+      const double src = OPT == 1 ? f0[u] * planck : (f0[u] * (1.0 - fT) + f1[u] * fT) * planck;
       const double trans = exp(-K.D * t);
       up[u] = up[u] * trans + src * (1.0 - trans);
       su += w[u] * up[u];
@@ -315,7 +398,9 @@ CB_HD void lw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
 
 // ---- shortwave unit ------------------------------------------------------------------------------------------------
 // scratch rows per unit: 7U  (Rdif, Tdif, src_up -> denom, src_dn, direct beam at layer base, albedo, src)
-template <int U, typename KT>
+// OPT = 1: picket-fence optics (U = 1; three purely absorbing visible bands, kappa_v = gamma_v * kappa_R;
+// CorkShortwaveRadiation._parmentier_sw_optics, cork/sw/component.py:498-532).
+template <int U, typename KT, int OPT = 0>
 CB_HD void sw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W, int c0, int c, int band, int chunk, int unit) {
   const int ncol = in.ncol, nlev = in.nlev, ncc = W.ncc;
   const size_t gc = (size_t)c0 + c;
@@ -335,6 +420,8 @@ CB_HD void sw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
     scale[u] = CB_LDG(in.solar_flux + band * Tb.ngpt + g0 + u) * mu0 * w[u];
   }
   const double ray = Tb.rayleigh ? CB_LDG(Tb.rayleigh + band) : 0.0;
+  double pk_gv = 0.0;
+  if (OPT == 1) pk_gv = picket_column(Tb.pk, in.T_irr[gc], in.T_int[gc], in.bond_albedo ? in.bond_albedo[gc] : 0.0).gv[band];
   const double MIN_K = 1.0e-12, MIN_MU0 = 1.0e-8;
   const double mu0_s = fmax(mu0, MIN_MU0);
   // pass 1: top -> surface.  layer optics, two-stream coefficients, direct beam (sw/kernels.py:233-249)
@@ -345,7 +432,8 @@ CB_HD void sw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
     const double* __restrict__ ws = W.ws + (size_t)l * ncc + c;
     const int idx = W.idx[(size_t)l * ncc + c];
     double tau_abs[U];
-    gas_tau<U, KT>(Tb, ws, fs, idx, band, chunk, tau_abs);
+    if (OPT == 1) tau_abs[0] = (pk_gv * ws[F_FT * fs]) * ws[F_AMT0 * fs];  // kappa_v * mass, cork/sw/component.py:525-530
+    else gas_tau<U, KT>(Tb, ws, fs, idx, band, chunk, tau_abs);
     double tau_ray = 0.0;
     if (Tb.rayleigh) {
       const double dp = fabs(in.p_int[(size_t)(l + 1) * ncol + gc] - in.p_int[(size_t)l * ncol + gc]);

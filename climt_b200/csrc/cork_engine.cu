@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(kBlock) k_cork_prep(const __grid_constant__ Ta
 }
 
 // One block = 128 adjacent columns x one unit (U g-points of one band)
-template <int U, bool LW, typename KT>
+template <int U, bool LW, typename KT, int OPT = 0>
 __global__ void __launch_bounds__(kBlock, CB_CORK_MIN_BLOCKS)
     k_cork_units(const __grid_constant__ Table Tb, const Consts K, const __grid_constant__ In in, const __grid_constant__ Work W,
                  int c0, int n) {
@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(kBlock, CB_CORK_MIN_BLOCKS)
   if (c >= n) return;
   const int unit = blockIdx.y;
   const int band = unit / Tb.nchunk, chunk = unit - band * Tb.nchunk;
-  if (LW) lw_unit<U, KT>(Tb, K, in, W, c0, c, band, chunk, unit);
-  else sw_unit<U, KT>(Tb, K, in, W, c0, c, band, chunk, unit);
+  if (LW) lw_unit<U, KT, OPT>(Tb, K, in, W, c0, c, band, chunk, unit);
+  else sw_unit<U, KT, OPT>(Tb, K, in, W, c0, c, band, chunk, unit);
 }
 
 __global__ void __launch_bounds__(kBlock) k_cork_reduce(const __grid_constant__ Table Tb, const __grid_constant__ Work W,
@@ -149,6 +149,45 @@ extern "C" int cb200_cork_create(cb200_cork_engine** out, const cb200_cork_table
   return 0;
 }
 
+extern "C" int cb200_cork_create_picket(cb200_cork_engine** out, const cb200_picket_coeffs* c, int longwave, double g, double cpd,
+                                        double sigma, int device) {
+  *out = nullptr;
+  static_assert(sizeof(cb200_picket_coeffs) == sizeof(Picket) && CB200_PICKET_MAX_REGIONS == kPicketMaxRegions, "picket layout");
+  if (!c || c->nregion < 1 || c->nregion > kPicketMaxRegions) {
+    cb::set_global_error("cork picket: need 1.." + std::to_string(kPicketMaxRegions) + " T_eff regions");
+    return -1;
+  }
+  auto* e = new cb200_cork_engine();
+  e->device = device;
+  e->K = Consts{g, cpd, sigma, 1.66};
+  e->premixed = true;
+  e->is_lw = longwave != 0;
+  e->is_sw = !e->is_lw;
+  Table& T = e->T;
+  T = Table{};
+  T.optics = 1;
+  T.ngas = 1; T.nband = e->is_lw ? 2 : 3; T.ngpt = 1; T.U = 1; T.nchunk = 1;
+  T.nT = T.nP = T.nX = T.nC = 1;
+  std::memcpy(&T.pk, c, sizeof(Picket));
+  e->nunits = T.nband;
+  const double ones[3] = {1.0, 1.0, 1.0};  // weights = np.ones((nband, 1)) (cork/lw/component.py:241, sw/component.py:265)
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce == cudaSuccess) ce = cudaMalloc(&e->d_blob, sizeof(ones));
+  if (ce == cudaSuccess) ce = cudaMemcpy(e->d_blob, ones, sizeof(ones), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    cb::set_global_error(std::string("cork picket create: ") + cudaGetErrorString(ce));
+    cudaFree(e->d_blob);
+    delete e;
+    return -1;
+  }
+  T.weights = static_cast<const double*>(e->d_blob);
+  if (const char* mc = std::getenv("CLIMT_B200_MAX_CHUNK")) e->max_chunk = std::max(128, std::atoi(mc));
+  cudaEventCreate(&e->ev0);
+  cudaEventCreate(&e->ev1);
+  *out = e;
+  return 0;
+}
+
 extern "C" void cb200_cork_destroy(cb200_cork_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
@@ -175,6 +214,7 @@ In make_in(int ncol, int nlev, const cb200_cork_inputs* p, const double* d_solar
   in.emissivity = p->emissivity; in.tau_cloud = p->tau_cloud;
   in.zenith = p->zenith; in.albedo = p->albedo; in.ssa_cloud = p->ssa_cloud; in.g_cloud = p->g_cloud;
   in.solar_flux = d_solar;
+  in.T_irr = p->T_irr; in.T_int = p->T_int; in.bond_albedo = p->bond_albedo;
   return in;
 }
 
@@ -190,6 +230,7 @@ int validate(cb200_cork_engine* e, bool lw, int ncol, int nlev, const cb200_cork
   if (lw && (!in->T_surf || !in->emissivity)) { e->error = "cork lw: T_surf and emissivity are required"; return -3; }
   if (!lw && (!in->zenith || !in->albedo)) { e->error = "cork sw: zenith and albedo are required"; return -3; }
   if (!lw && in->tau_cloud && (!in->ssa_cloud || !in->g_cloud)) { e->error = "cork sw: ssa_cloud and g_cloud must accompany tau_cloud"; return -3; }
+  if (e->T.optics == 1 && (!in->T_irr || !in->T_int)) { e->error = "cork picket: T_irr and T_int are required"; return -3; }
   if (e->T.hasX && !in->q_h2o) { e->error = "k-table has an h2o_vmr_grid axis but specific humidity was not provided"; return -3; }  // correlated_k.py:262-265
   if (e->T.hasC && !in->co2_vmr) { e->error = "k-table has a co2_vmr_grid axis but co2_vmr was not provided"; return -3; }   // :272-275
   if (!e->premixed && !in->gas_q) { e->error = "cork: a non-premixed table needs the gas mass mixing ratios"; return -3; }
@@ -214,7 +255,10 @@ int launch_chunk(cb200_cork_engine* e, bool lw, const Consts& K, const In& in_, 
     else if (!e->k_f64) k_cork_units<U, false, float><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);        \
     else k_cork_units<U, false, double><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);                      \
     break;
-  switch (e->T.U) {
+  if (e->T.optics == 1) {
+    if (lw) k_cork_units<1, true, float, 1><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);
+    else k_cork_units<1, false, float, 1><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);
+  } else switch (e->T.U) {
     CB_LAUNCH(1) CB_LAUNCH(2) CB_LAUNCH(4) CB_LAUNCH(8)
   }
 #undef CB_LAUNCH
@@ -235,6 +279,7 @@ int launch_chunk(cb200_cork_engine* e, bool lw, const Consts& K, const In& in_, 
 int upload_solar(cb200_cork_engine* e, const double* h_solar, cudaStream_t st) {
   const size_t n = (size_t)e->T.nband * e->T.ngpt;
   if (!e->d_solar) CUDA_OK(cudaMalloc(&e->d_solar, n * sizeof(double)));
+  if (!h_solar && !e->T.solar) { e->error = "cork picket sw: the solar_flux argument is required"; return -3; }
   if (h_solar) CUDA_OK(cudaMemcpyAsync(e->d_solar, h_solar, n * sizeof(double), cudaMemcpyHostToDevice, st));
   else CUDA_OK(cudaMemcpyAsync(e->d_solar, e->T.solar, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
   return 0;
@@ -244,7 +289,7 @@ int run_device(cb200_cork_engine* e, bool lw, int ncol, int nlev, double scalar,
                const cb200_cork_outputs* pout, cudaStream_t st) {
   if (int rc = validate(e, lw, ncol, nlev, pin, pout)) return rc;
   CUDA_OK(cudaSetDevice(e->device));
-  if (!lw && upload_solar(e, h_solar, st)) return -1;
+  if (!lw) if (int rc = upload_solar(e, h_solar, st)) return rc;
   int chunk = ncol < e->max_chunk ? ncol : e->max_chunk;
   chunk = (chunk + kBlock - 1) / kBlock * kBlock;
   if (e->ensure_work(chunk, nlev)) return -1;
@@ -272,14 +317,17 @@ int run_host(cb200_cork_engine* e, bool lw, int ncol, int nlev, double scalar, c
   CUDA_OK(cudaSetDevice(e->device));
   cb::HostPipe& P = e->pipe;
   CUDA_OK(P.init());
-  if (!lw && upload_solar(e, h_solar, P.s_cmp)) return -1;
+  if (!lw) if (int rc = upload_solar(e, h_solar, P.s_cmp)) return rc;
   const int L = nlev, nb = e->T.nband;
   // inputs in cb200_cork_inputs order: T p p_int T_surf q_h2o co2_vmr gas_q emissivity tau_cloud zenith albedo ssa_cloud g_cloud
-  const int irows[13] = {L, L, L + 1, 1, L, L, e->T.ngas * L, nb, L, 1, 1, L, L};
-  const int inner[13] = {1, 1, 1, 1, 1, 1, 1, 1, nb, 1, 1, nb, nb};
+  //                                    T_irr T_int bond_albedo
+  constexpr int NI = 16;
+  const int irows[NI] = {L, L, L + 1, 1, L, L, e->T.ngas * L, nb, L, 1, 1, L, L, 1, 1, 1};
+  const int inner[NI] = {1, 1, 1, 1, 1, 1, 1, 1, nb, 1, 1, nb, nb, 1, 1, 1};
   const double* const* hp = reinterpret_cast<const double* const*>(hin);
-  bool used[13];
-  for (int i = 0; i < 13; ++i) used[i] = hp[i] != nullptr;
+  bool used[NI];
+  for (int i = 0; i < NI; ++i) used[i] = hp[i] != nullptr;
+  used[13] = used[13] && e->T.optics == 1; used[14] = used[14] && e->T.optics == 1; used[15] = used[15] && e->T.optics == 1 && !lw;
   used[3] = used[3] && lw; used[7] = used[7] && lw;
   used[9] = used[9] && !lw; used[10] = used[10] && !lw; used[11] = used[11] && !lw; used[12] = used[12] && !lw;
   used[4] = used[4] && e->T.hasX; used[5] = used[5] && e->T.hasC; used[6] = used[6] && !e->premixed;
@@ -288,7 +336,7 @@ int run_host(cb200_cork_engine* e, bool lw, int ncol, int nlev, double scalar, c
   const int orows[8] = {L + 1, L + 1, L, nb * (L + 1), nb * (L + 1), nb * L, nb * L, nb * L};
   double* const* hop = reinterpret_cast<double* const*>(hout);
   size_t irow_tot = 0, orow_tot = 0;
-  for (int i = 0; i < 13; ++i) if (used[i]) irow_tot += (size_t)irows[i] * inner[i];
+  for (int i = 0; i < NI; ++i) if (used[i]) irow_tot += (size_t)irows[i] * inner[i];
   for (int i = 0; i < 8; ++i) if (hop[i]) orow_tot += (size_t)orows[i];
   int chunk = ncol < P.chunk ? ncol : P.chunk;
   const int wchunk = (chunk + kBlock - 1) / kBlock * kBlock;
@@ -309,7 +357,7 @@ int run_host(cb200_cork_engine* e, bool lw, int ncol, int nlev, double scalar, c
     cb200_cork_inputs din;
     const double** dp = reinterpret_cast<const double**>(&din);
     size_t off = 0;
-    for (int i = 0; i < 13; ++i) {
+    for (int i = 0; i < NI; ++i) {
       if (!used[i]) { dp[i] = nullptr; continue; }
       CUDA_OK(P.gather(P.d_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
       dp[i] = P.d_in[s] + off;
@@ -341,7 +389,7 @@ int run_host(cb200_cork_engine* e, bool lw, int ncol, int nlev, double scalar, c
 
 }  // namespace
 
-static_assert(sizeof(cb200_cork_inputs) == 13 * sizeof(double*), "cb200_cork_inputs layout");
+static_assert(sizeof(cb200_cork_inputs) == 16 * sizeof(double*), "cb200_cork_inputs layout");
 static_assert(sizeof(cb200_cork_outputs) == 8 * sizeof(double*), "cb200_cork_outputs layout");
 
 extern "C" int cb200_cork_lw_run_device(cb200_cork_engine* e, int ncol, int nlev, double D, const cb200_cork_inputs* in,

@@ -200,6 +200,8 @@ typedef struct cb200_cork_inputs {
   const double* tau_cloud;                /* (nlev, ncol, nband) or NULL (= 0) */
   const double *zenith, *albedo;          /* SW: (ncol) radians / - */
   const double *ssa_cloud, *g_cloud;      /* SW: (nlev, ncol, nband), required when tau_cloud is given */
+  const double *T_irr, *T_int;            /* picket-fence engines: irradiation / internal temperature (ncol), K */
+  const double* bond_albedo;              /* picket-fence SW: Bond albedo (ncol) entering T_eff, or NULL (= 0) */
 } cb200_cork_inputs;
 
 typedef struct cb200_cork_outputs {
@@ -211,6 +213,26 @@ typedef struct cb200_cork_outputs {
 
 /* g [m s-2], cpd [J kg-1 K-1], sigma [W m-2 K-4] as sympl's get_constant gives them (lw/component.py:224-226) */
 int cb200_cork_create(cb200_cork_engine** out, const cb200_cork_table* table, double g, double cpd, double sigma, int device);
+
+/* Picket-fence optics (optics="parmentier", the reference constructors' default) instead of a k-table.  Replaces
+ *   compute_rosseland_mean_opacity, lookup_ratio_coefficients, compute_thermal_opacities   climt/_components/cork/optics/parmentier.py:8-153
+ *   CorkLongwaveRadiation._parmentier_optics      climt/_components/cork/lw/component.py:375-422  (2 thermal bands x 1 g-point)
+ *   CorkShortwaveRadiation._parmentier_sw_optics  climt/_components/cork/sw/component.py:498-532  (3 visible bands x 1 g-point)
+ * -- scalar Python loops over (column, level) in the reference -- followed by the same transport kernels as the k-table engines.
+ * The members are the arrays of climt/_data/cork/parmentier/{solar_composition,freedman2014}.npz. */
+#define CB200_PICKET_MAX_REGIONS 8
+typedef struct cb200_picket_coeffs {
+  int nregion;                                         /* len(T_eff_boundaries) - 1, <= CB200_PICKET_MAX_REGIONS */
+  double T_eff_boundaries[CB200_PICKET_MAX_REGIONS + 1];
+  double log10_gamma_v1_ab[CB200_PICKET_MAX_REGIONS][2], log10_gamma_v2_ab[CB200_PICKET_MAX_REGIONS][2],
+      log10_gamma_v3_ab[CB200_PICKET_MAX_REGIONS][2], beta_ab[CB200_PICKET_MAX_REGIONS][2];
+  double log10_gamma_P_quad[3];
+  double T_boundary, a_hi, b_hi, c_hi, a_lo, b_lo, c_lo;  /* Freedman et al. (2014) fit */
+} cb200_picket_coeffs;
+/* longwave != 0: 2-band thermal engine (run with cb200_cork_lw_run_*); else 3-band visible engine (cb200_cork_sw_run_*, whose
+ * solar_flux argument -- (3, 1) doubles -- is then mandatory).  Inputs T_irr and T_int are required by both. */
+int cb200_cork_create_picket(cb200_cork_engine** out, const cb200_picket_coeffs* coeffs, int longwave, double g, double cpd,
+                             double sigma, int device);
 void cb200_cork_destroy(cb200_cork_engine* e);
 const char* cb200_cork_last_error(cb200_cork_engine* e);
 int cb200_cork_last_launches(cb200_cork_engine* e);

@@ -204,7 +204,7 @@ def run_cork_emul(table, which, arrays, scalar, umax=4):
             a = np.ascontiguousarray(a, dtype=np.float64)
             keep.append(a)
         ins.append(a)
-    inp = (_dp * 13)(*[a.ctypes.data_as(_dp) if a is not None else None for a in ins])
+    inp = (_dp * len(ins))(*[a.ctypes.data_as(_dp) if a is not None else None for a in ins])
     outp = (_dp * 8)(*[out[k].ctypes.data_as(_dp) for k in cork.CORK_OUT])
     scal = np.array([CORK_G, CORK_CPD, CORK_SIGMA, scalar if which == "lw" else 1.66])
     solar = cork_solar_flux(table, scalar) if which == "sw" else np.zeros(1)
@@ -214,3 +214,71 @@ def run_cork_emul(table, which, arrays, scalar, umax=4):
                            ctypes.cast(inp, ctypes.POINTER(_dp)), ctypes.cast(outp, ctypes.POINTER(_dp)))
     assert rc == 0
     return out
+
+
+# ---- CORK picket fence (optics="parmentier") ------------------------------------------------------------------------
+PARMENTIER_GOLDEN = os.path.join(HERE, "golden", "parmentier_reference.npz")
+
+
+def picket_coefficients():
+    from climt_b200 import cork
+    return cork.load_parmentier_coefficients("solar_composition"), cork.load_freedman2014_coefficients()
+
+
+def parmentier_case(z, case):
+    return {k.split("/")[-1]: z[k] for k in z.files if k.startswith(case + "/in/")}
+
+
+def picket_arrays(s, which, bond_albedo=None):
+    a = {"T": s["T"], "p": s["p"], "p_int": s["p_int"], "T_irr": s["T_irr"], "T_int": s["T_int"]}
+    if which == "lw":
+        a.update(T_surf=s["T_surf"], emissivity=s["emissivity"], tau_cloud=s["tau_cloud_lw"])
+    else:
+        a.update(zenith=s["zenith"], albedo=s["albedo"], tau_cloud=s["tau_cloud_sw"], ssa_cloud=s["ssa_cloud"], g_cloud=s["g_cloud"])
+        if bond_albedo is not None:
+            a["bond_albedo"] = bond_albedo
+    return a
+
+
+def run_picket_emul(which, arrays, scalar, solar_flux=None):
+    """The picket-fence engine's per-thread code compiled for the host.  scalar = D (lw); solar_flux (3, 1) for sw."""
+    from climt_b200 import cork
+    lib = cork_emul_lib()
+    co, fr = picket_coefficients()
+    pc = cork.make_picket_coeffs(co, fr)
+    nlev, ncol = arrays["T"].shape
+    nb = 2 if which == "lw" else 3
+    shapes = {"up_broad": (nlev + 1, ncol), "down_broad": (nlev + 1, ncol), "heating_rate": (nlev, ncol), "up_band": (nb, nlev + 1, ncol),
+              "down_band": (nb, nlev + 1, ncol), "tau_band": (nb, nlev, ncol), "trans_band": (nb, nlev, ncol), "hr_band": (nb, nlev, ncol)}
+    out = {k: np.zeros(v) for k, v in shapes.items()}
+    ins = [None if arrays.get(k) is None else np.ascontiguousarray(arrays[k], dtype=np.float64) for k in cork.CORK_IN]
+    inp = (_dp * len(ins))(*[a.ctypes.data_as(_dp) if a is not None else None for a in ins])
+    outp = (_dp * 8)(*[out[k].ctypes.data_as(_dp) for k in cork.CORK_OUT])
+    scal = np.array([CORK_G, CORK_CPD, CORK_SIGMA, scalar if which == "lw" else 1.66])
+    solar = np.ascontiguousarray(solar_flux, dtype=np.float64) if solar_flux is not None else np.zeros(3)
+    lib.emul_picket_run.argtypes = [ctypes.POINTER(cork.PicketCoeffs), ctypes.c_int, _dp, _dp, ctypes.c_int, ctypes.c_int,
+                                    ctypes.POINTER(_dp), ctypes.POINTER(_dp)]
+    rc = lib.emul_picket_run(ctypes.byref(pc), 1 if which == "lw" else 0, scal.ctypes.data_as(_dp), solar.ctypes.data_as(_dp), ncol, nlev,
+                             ctypes.cast(inp, ctypes.POINTER(_dp)), ctypes.cast(outp, ctypes.POINTER(_dp)))
+    assert rc == 0
+    return out
+
+
+# golden diagnostic name -> (engine output, band axis moved to the end?)
+PICKET_LW_DIAG = {"T": ("heating_rate", False), "upwelling_longwave_flux_in_air": ("up_broad", False),
+                  "downwelling_longwave_flux_in_air": ("down_broad", False),
+                  "upwelling_longwave_flux_in_air_per_band": ("up_band", True),
+                  "downwelling_longwave_flux_in_air_per_band": ("down_band", True),
+                  "longwave_optical_depth_per_band": ("tau_band", True), "longwave_transmittance_per_band": ("trans_band", True),
+                  "air_temperature_tendency_from_longwave_per_band": ("hr_band", True)}
+PICKET_SW_DIAG = {"T": ("heating_rate", False), "upwelling_shortwave_flux_in_air": ("up_broad", False),
+                  "downwelling_shortwave_flux_in_air": ("down_broad", False),
+                  "upwelling_shortwave_flux_in_air_per_band": ("up_band", True),
+                  "downwelling_shortwave_flux_in_air_per_band": ("down_band", True),
+                  "shortwave_optical_depth_per_band": ("tau_band", True),
+                  "air_temperature_tendency_from_shortwave_per_band": ("hr_band", True)}
+
+
+def flux_scaled_err(got, ref, scale):
+    """max |got - ref| / scale: for quantities that are differences of fluxes (heating rates), measured against the flux scale"""
+    return float(np.max(np.abs(got - ref)) / scale)
