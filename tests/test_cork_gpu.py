@@ -147,8 +147,10 @@ def test_components_through_state_dicts():
     sw = cork.CorkShortwaveRadiation(optics="correlated_k", table="earth_low_res_sw")
     tend, diag = sw(state)
     np.testing.assert_allclose(diag["downwelling_shortwave_flux_in_air"].values.reshape(nlev + 1, ncol), GOLD["cloudy/sw/down_broad"], rtol=RTOL, atol=1e-9)
+    with pytest.raises(ValueError):
+        cork.CorkLongwaveRadiation(optics="line_by_line")   # cork/lw/component.py:60-61
     with pytest.raises(NotImplementedError):
-        cork.CorkLongwaveRadiation()  # optics="parmentier" is the reference's default; not part of the CUDA engine
+        cork.CorkLongwaveRadiation(optics="correlated_k", table="earth_low_res_lw", diagnostics_level=1)
 
 
 def test_grey_limit_matches_gray_engine():
