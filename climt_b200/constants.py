@@ -24,6 +24,13 @@ DEFAULTS = {
     "reference_air_pressure": (1.0132e5, "Pa"),
     "top_of_model_pressure": (20.0, "Pa"),       # climt/__init__.py:51
     "stellar_irradiance": (1367.0, "W m^-2"),
+    # water as the condensible (sympl's defaults; read by EmanuelConvection, climt/_components/emanuel/component.py:236-246).
+    # No golden of the reference pins these five: its Emanuel caches hold only zeros.
+    "heat_capacity_of_vapor_phase": (1846.0, "J kg^-1 K^-1"),
+    "gas_constant_of_vapor_phase": (461.5, "J kg^-1 K^-1"),
+    "latent_heat_of_condensation": (2.5e6, "J kg^-1"),
+    "density_of_liquid_phase": (1e3, "kg m^-3"),
+    "specific_enthalpy_of_vapor_phase": (2500.0, "J kg^-1"),
 }
 
 _registry = {k: v[0] for k, v in DEFAULTS.items()}

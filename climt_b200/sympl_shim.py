@@ -8,7 +8,7 @@ table, re-wrapping of outputs) for the drop-in components to be exercised throug
 import numpy as np
 
 try:  # pragma: no cover - not available in the build image
-    from sympl import TendencyComponent, DataArray, initialize_numpy_arrays_with_properties  # noqa: F401
+    from sympl import TendencyComponent, ImplicitTendencyComponent, DataArray, initialize_numpy_arrays_with_properties  # noqa: F401
     HAVE_SYMPL = True
 except Exception:  # ImportError or a broken install
     HAVE_SYMPL = False
@@ -33,7 +33,7 @@ except Exception:  # ImportError or a broken install
               "g m^-2": ("kg m^-2", 1e-3), "kg m^-2": ("kg m^-2", 1.0),
               "micrometer": ("m", 1e-6), "m": ("m", 1.0),
               "degK": ("K", 1.0), "K": ("K", 1.0),
-              "g/g": ("1", 1.0), "kg/kg": ("1", 1.0), "dimensionless": ("1", 1.0), "mole/mole": ("1", 1.0),
+              "g/g": ("1", 1.0), "kg/kg": ("1", 1.0), "m s^-1": ("m s^-1", 1.0), "kg m^-2 s^-1": ("kg m^-2 s^-1", 1.0), "dimensionless": ("1", 1.0), "mole/mole": ("1", 1.0),
               "": ("1", 1.0), "1": ("1", 1.0),
               "W m^-2": ("W m^-2", 1.0), "degK day^-1": ("K day^-1", 1.0), "K day^-1": ("K day^-1", 1.0),
               "radians": ("rad", 1.0), "degrees": ("rad", np.pi / 180.0)}
@@ -82,7 +82,7 @@ except Exception:  # ImportError or a broken install
             if kwargs:
                 raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
 
-        def __call__(self, state):
+        def __call__(self, state, *extra):
             raw, star, star_shape = {}, (), ()
             for name, prop in self.input_properties.items():
                 if name not in state:
@@ -90,7 +90,7 @@ except Exception:  # ImportError or a broken install
                 raw[name], s, ss = _to_raw(state[name], prop["dims"], prop.get("units", ""))
                 if "*" in prop["dims"] and len(s) >= len(star):
                     star, star_shape = s, ss
-            tend, diag = self.array_call(raw)
+            tend, diag = self.array_call(raw, *extra)
 
             def wrap(arr, prop, name=None):
                 dims, shape, k = [], [], 0
@@ -107,6 +107,12 @@ except Exception:  # ImportError or a broken install
                 return DataArray(np.asarray(arr).reshape(shape), dims, {"units": prop.get("units", "")})
             return ({k: wrap(v, self.tendency_properties[k], k) for k, v in tend.items()},
                     {k: wrap(v, self.diagnostic_properties[k]) for k, v in diag.items()})
+
+    class ImplicitTendencyComponent(TendencyComponent):
+        """sympl.ImplicitTendencyComponent: `component(state, timestep)` -> array_call(raw_state, timestep)."""
+
+        def __call__(self, state, timestep):
+            return TendencyComponent.__call__(self, state, timestep)
 
     def initialize_numpy_arrays_with_properties(output_properties, raw_input_state, input_properties):
         dim_len = {}

@@ -83,3 +83,33 @@ def make_sw_state(ncol, nlay, seed=20260925, clouds=False, trace=True, aerosol=F
     if ecmwf:
         st["ecaer"] = rng.uniform(0, 0.02, (6, nlay, ncol))
     return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in st.items()}
+
+
+def make_emanuel_state(ncol, nlev, seed=20260925):
+    """Soundings for the Emanuel convection path, in the component's layout and units: (ncol, nlev) arrays, level 0 at the
+    surface, pressures in mbar.  Same grid, surface pressure and latitude law as make_lw_state; conditionally unstable
+    lapse rates, a moist boundary layer whose relative humidity varies from column to column (dry columns, columns that
+    only just trigger, deep convection), sheared winds, and a cloud-base mass flux carried over from a previous step in
+    about half of the columns."""
+    rng = np.random.default_rng(seed + 3)
+    lat = np.deg2rad(rng.uniform(-90, 90, ncol))
+    ps = rng.uniform(9.5e4, 1.03e5, ncol)
+    ak, bk = _s.hybrid_sigma_pressure_levels(nlev + 1, get_constant("reference_air_pressure"),
+                                             get_constant("top_of_model_pressure"))
+    p, p_int = _s.pressure_from_hybrid(ak, bk, ps)          # Pa, (nlev, ncol), surface first
+    ts = 302.0 - 45.0 * np.sin(lat) ** 2 + rng.normal(0, 2, ncol)
+    gamma = rng.uniform(0.17, 0.215, ncol)                   # R*lapse/g: 5.8 .. 7.3 K/km
+    t = np.maximum(ts[None, :] * (p / ps[None, :]) ** gamma[None, :], rng.uniform(190.0, 215.0, ncol)[None, :])
+    t = t + rng.normal(0, 0.3, p.shape)
+    es = 611.2 * np.exp(17.67 * (t - 273.15) / (t - 29.65))
+    qsat = 0.622 * es / (p - 0.378 * es)
+    rh_s = rng.uniform(0.2, 0.98, ncol)
+    sig = p / ps[None, :]
+    rh = np.clip(rh_s[None, :] * (0.25 + 0.75 * sig ** 1.5) * rng.uniform(0.85, 1.1, p.shape), 0.02, 0.99)
+    q = np.maximum(rh * np.minimum(qsat, 0.04), 1e-7)
+    u = 5.0 + 25.0 * (1.0 - sig) * np.cos(lat)[None, :] + rng.normal(0, 1.0, p.shape)
+    v = rng.normal(0, 2.0, p.shape) + 3.0 * (1.0 - sig)
+    cbmf = np.where(rng.uniform(size=ncol) < 0.5, rng.uniform(0.0, 0.03, ncol), 0.0)
+    st = {"air_temperature": t.T, "specific_humidity": q.T, "eastward_wind": u.T, "northward_wind": v.T,
+          "air_pressure": p.T / 100.0, "air_pressure_on_interface_levels": p_int.T / 100.0, "cloud_base_mass_flux": cbmf}
+    return {k: np.ascontiguousarray(a, dtype=np.float64) for k, a in st.items()}

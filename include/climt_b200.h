@@ -252,6 +252,67 @@ int cb200_cork_lw_run_host(cb200_cork_engine* e, int ncol, int nlev, double diff
 int cb200_cork_sw_run_host(cb200_cork_engine* e, int ncol, int nlev, const double* solar_flux, const cb200_cork_inputs* in,
                            const cb200_cork_outputs* out);
 
+/* ============================== Emanuel moist convection ==============================
+ * Replaces the per-column Fortran routine behind climt.EmanuelConvection and the numba port behind
+ * climt.EmanuelConvectionPython, together with the column loop and the saturation-humidity pre-step around them:
+ *   SUBROUTINE CONVECT (version 4.3c), TLIFT        climt/_lib/emanuel/convect43c.f90:146-1219
+ *   init_emanuel_convection / module parameters     climt/_lib/emanuel/convect43c.f90:91-137
+ *   convect() column loop (one Fortran call/column) climt/_components/emanuel/_emanuel_convection.pyx:96-201
+ *   EmanuelConvection.array_call, bolton_q_sat      climt/_components/emanuel/component.py:279-340, climt/_core/util.py:177-180
+ *   _convect_functional_np, compute_qs              climt/_components/emanuel/pure_python_v3.py:240-835, climt/_core/condensibles.py:104-123
+ * IPBL = 0 (the reference's shim hard-wires it) and no tracers (the components pass NTRA = 0).  Parameters are per engine
+ * instance (the reference keeps them in Fortran module variables).  Pressures in mbar, level 0 at the surface. */
+typedef struct cb200_emanuel_engine cb200_emanuel_engine;
+
+typedef struct cb200_emanuel_params {
+  double minorig;                      /* MINORIG: lowest level from which convection may originate (1-based, integral) */
+  double elcrit, tlcrit, entp, sigd, sigs, omtrain, omtsnow, coeffr, coeffs, cu, beta, dtmax, alpha, damp;
+  double cpd, cpv, cl, rv, rd, lv0, g, rowl, delt0;
+  double t_rain;                       /* rain/snow fall-speed switch: 273.0 (convect43c.f90:885) or 273.15 (pure_python_v3.py:586-587) */
+} cb200_emanuel_params;
+
+typedef struct cb200_emanuel_inputs {
+  const double *t, *q, *u, *v, *p, *ph; /* K, kg/kg, m/s, m/s, mbar (nlev), mbar (nlev+1) */
+  const double* qs;                     /* saturation specific humidity; read only when qs_mode = 0 */
+  const double* cbmf;                   /* (ncol) cloud-base mass flux of the previous step, kg m-2 s-1 */
+} cb200_emanuel_inputs;
+
+typedef struct cb200_emanuel_outputs {
+  double *ft, *fq, *fu, *fv;            /* tendencies: K s-1, kg/kg s-1, m s-2, m s-2 */
+  double *precip, *wd, *tprime, *qprime; /* (ncol) mm day-1, m s-1, K, kg/kg */
+  double* cbmf;                          /* (ncol) updated cloud-base mass flux; may alias inputs.cbmf */
+  double* cape;                          /* (ncol) J kg-1; 0 where the routine returns before computing it */
+  int* iflag;                            /* (ncol) int32 convective_state: 0 none, 1 convection, 2/3 no LCL / cloud base too high, 4 CFL */
+} cb200_emanuel_outputs;
+
+int cb200_emanuel_create(cb200_emanuel_engine** out, const cb200_emanuel_params* params, int device);
+void cb200_emanuel_destroy(cb200_emanuel_engine* e);
+const char* cb200_emanuel_last_error(cb200_emanuel_engine* e);
+int cb200_emanuel_last_launches(cb200_emanuel_engine* e);
+int cb200_emanuel_enable_timing(cb200_emanuel_engine* e, int on);
+double cb200_emanuel_last_kernel_ms(cb200_emanuel_engine* e);   /* k_emanuel, CUDA events on its launch stream */
+/* qs_mode: 0 = inputs.qs, 1 = bolton_q_sat(T, 100 p, rd, rv) (EmanuelConvection), 2 = compute_qs (EmanuelConvectionPython), fused
+ * into the kernel.  max_conv_lev: NL, the components pass nlev - 3 (component.py:297).
+ * Device-pointer call, asynchronous on `stream`.  layout 0: (nlev[+1], ncol) column-fastest, the layout of the radiation engines;
+ * layout 1: (ncol, nlev[+1]) C order, the component's ("*", "mid_levels") arrays (transposed on the device). */
+int cb200_emanuel_run_device(cb200_emanuel_engine* e, int ncol, int nlev, int max_conv_lev, double dt, int qs_mode, int layout,
+                             const cb200_emanuel_inputs* in, const cb200_emanuel_outputs* out, void* stream);
+/* Host-pointer call in the component's (ncol, nlev[+1]) layout: chunked 3-stream pipeline (H2D | kernels | D2H). */
+int cb200_emanuel_run_host(cb200_emanuel_engine* e, int ncol, int nlev, int max_conv_lev, double dt, int qs_mode,
+                           const cb200_emanuel_inputs* in, const cb200_emanuel_outputs* out);
+/* The reference's own symbols (bind(c) names of convect43c.f90:91-150; declared in _emanuel_convection.pyx:10-42): process-global
+ * parameters, ONE column per call, host pointers. */
+void init_emanuel_convection_fortran(int* pbl, int* least_conv_level, double* thresh_water_level, double* crit_temp,
+                                     double* entrain_coeff, double* downdraft_frac_area, double* precip_frac_outside_cloud,
+                                     double* rain_speed, double* snow_speed, double* rain_evap_coeff, double* snow_evap_coeff,
+                                     double* mom_tran_coeff, double* max_neg_temp_pert, double* beta, double* alpha, double* damp_amp,
+                                     double* Cpd, double* Cpv, double* Cl, double* gas_const_vapour, double* gas_const_air,
+                                     double* lat_heat, double* grav, double* density_water, double* reference_mass_flux_timescale);
+void emanuel_convection(double* temp, double* q, double* qs, double* u, double* v, double* pmid, double* pint, int* nlevs,
+                        int* max_conv_lev, int* num_tracers, double* dt, int* conv_state, double* dtemp, double* dq, double* du,
+                        double* dv, double* precip, double* downdraft_vel_scale, double* downdraft_temp_scale,
+                        double* downdraft_q_scale, double* cloud_base_mass_flux, double* cape, double* tracers, double* dtracers);
+
 /* ============================== device-side marshal ==============================
  * What the components' array_call computes in numpy before calling the engines, for state that already lives in HBM:
  * h2ovmr = q * 28.964 / 18.02 (climt/_core/util.py:47-86), tlev by ln-p weights with tlev[0] = tsfc, tlev[nlay] = t[nlay-1]

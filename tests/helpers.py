@@ -282,3 +282,77 @@ PICKET_SW_DIAG = {"T": ("heating_rate", False), "upwelling_shortwave_flux_in_air
 def flux_scaled_err(got, ref, scale):
     """max |got - ref| / scale: for quantities that are differences of fluxes (heating rates), measured against the flux scale"""
     return float(np.max(np.abs(got - ref)) / scale)
+
+
+# ---- Emanuel convection ---------------------------------------------------------------------------------------------
+EMANUEL_GOLDEN = os.path.join(HERE, "golden", "emanuel_reference.npz")
+
+
+def emanuel_case(z, case):
+    return {k.split("/")[-1]: z[k] for k in z.files if k.startswith(case + "/in/")}
+
+
+def emanuel_arrays(st, qs=None):
+    a = {"t": st["air_temperature"], "q": st["specific_humidity"], "u": st["eastward_wind"], "v": st["northward_wind"],
+         "p": st["air_pressure"], "ph": st["air_pressure_on_interface_levels"], "cbmf": st["cloud_base_mass_flux"]}
+    if qs is not None:
+        a["qs"] = qs
+    return a
+
+
+def emanuel_emul_lib():
+    so = os.path.join(HERE, "emul", "libcb_emul_emanuel.so")
+    src = os.path.join(HERE, "emul", "emanuel_emul.cpp")
+    deps = [src, os.path.join(HERE, "..", "climt_b200", "csrc", "emanuel_core.cuh"), os.path.join(HERE, "..", "climt_b200", "csrc", "cb_common.h"),
+            os.path.join(HERE, "..", "include", "climt_b200.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def run_emanuel_emul(params, arrays, dt, qs_mode, max_conv_lev=None):
+    """The CUDA engine's per-thread code compiled for the host; arrays in the component's (ncol, nlev) layout."""
+    from climt_b200 import emanuel as EM
+    lib = emanuel_emul_lib()
+    ncol, nlev = arrays["t"].shape
+    nl = nlev - 3 if max_conv_lev is None else max_conv_lev
+    p = EM.make_params(**params)
+    pin, keep = EM.EmanuelInputs(), []
+    for k in EM.EM_IN:
+        if arrays.get(k) is not None:
+            a = np.ascontiguousarray(arrays[k], dtype=np.float64)
+            keep.append(a)
+            setattr(pin, k, a.ctypes.data_as(_dp))
+    ins, outs = EM.EmanuelEngine.shapes(ncol, nlev)
+    out = {k: np.zeros(outs[k]) for k in EM.EM_OUT}
+    out["iflag"] = np.zeros(ncol, dtype=np.int32)
+    pout = EM.EmanuelOutputs()
+    for k in EM.EM_OUT:
+        setattr(pout, k, out[k].ctypes.data_as(_dp))
+    pout.iflag = out["iflag"].ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    lib.emul_emanuel_run.argtypes = [ctypes.POINTER(EM.EmanuelParams), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                     ctypes.POINTER(EM.EmanuelInputs), ctypes.POINTER(EM.EmanuelOutputs)]
+    rc = lib.emul_emanuel_run(ctypes.byref(p), ncol, nlev, nl, float(dt), int(qs_mode), ctypes.byref(pin), ctypes.byref(pout))
+    assert rc == 0
+    return out
+
+
+# engine output -> (tendency or diagnostic name of the components)
+EMANUEL_OUT = {"ft": "tendency_air_temperature", "fq": "tendency_specific_humidity", "fu": "tendency_eastward_wind",
+               "fv": "tendency_northward_wind", "iflag": "convective_state", "precip": "convective_precipitation_rate",
+               "wd": "convective_downdraft_velocity_scale", "tprime": "convective_downdraft_temperature_scale",
+               "qprime": "convective_downdraft_specific_humidity_scale", "cbmf": "cloud_base_mass_flux",
+               "cape": "atmosphere_convective_available_potential_energy"}
+
+
+def emanuel_compare(got, ref, rtol, what=""):
+    """got/ref: dicts keyed like the engine outputs.  The convective state must agree exactly; every other field to rtol of the
+    field's own scale (tendencies are sums of terms of either sign: a per-element relative test would measure cancellation)."""
+    assert np.array_equal(got["iflag"], ref["iflag"]), (what, "convective_state differs in", int((got["iflag"] != ref["iflag"]).sum()), "columns")
+    worst = 0.0
+    for k in ("ft", "fq", "fu", "fv", "precip", "wd", "tprime", "qprime", "cbmf", "cape"):
+        scale = float(np.max(np.abs(ref[k])))
+        err = float(np.max(np.abs(got[k] - ref[k]))) / scale if scale > 0 else float(np.max(np.abs(got[k])))
+        assert err < rtol, (what, k, err)
+        worst = max(worst, err)
+    return worst
