@@ -1,5 +1,5 @@
-// climt_b200 -- Emanuel moist convection engine: CUDA kernels (sm_100a), layout transposes, host pipeline, C ABI.
-// Per-thread code: emanuel_core.cuh.  Reference: climt/_lib/emanuel/convect43c.f90, climt/_components/emanuel/
+// climt_b200 -- Emanuel moist convection engine: CUDA kernel (sm_100a, one warp per column, persistent grid), host pipeline, C ABI.
+// Warp-cooperative code: emanuel_core.cuh.  Reference: climt/_lib/emanuel/convect43c.f90, climt/_components/emanuel/
 // _emanuel_convection.pyx, component.py, pure_python_v3.py (see include/climt_b200.h for the entry-point mapping).
 #include <cuda_runtime.h>
 
@@ -16,35 +16,20 @@
 using namespace cb::emanuel;
 
 namespace {
-#ifndef CB_EMANUEL_BLOCK
-#define CB_EMANUEL_BLOCK 64  // columns per block: one thread per column, branchy and latency-bound -> many small blocks spread over the SMs
+#ifndef CB_EMANUEL_WARPS
+#define CB_EMANUEL_WARPS 4  // columns (warps) per block; the block's shared memory is CB_EMANUEL_WARPS x V_COUNT x n1 doubles
 #endif
 
-__global__ void __launch_bounds__(CB_EMANUEL_BLOCK) k_emanuel(const Par par, const __grid_constant__ In in, const __grid_constant__ Work W,
-                                                              const __grid_constant__ Out out, int c0, int n, int NL, double dt) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < n) convect_column(par, in, W, out, c0, c, NL, dt);
-}
-
-// src (rows, cols) row-major -> dst (cols, rows) row-major; both leading dimensions explicit (elements)
-__global__ void __launch_bounds__(256) k_transpose(double* __restrict__ dst, size_t ldd, const double* __restrict__ src, size_t lds,
-                                                   int rows, int cols) {
-  __shared__ double tile[32][33];
-  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int r = by + j, c = bx + threadIdx.x;
-    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(size_t)r * lds + c];
-  }
-  __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int c = bx + j, r = by + threadIdx.x;
-    if (r < rows && c < cols) dst[(size_t)c * ldd + r] = tile[threadIdx.x][j];
-  }
-}
-
-void transpose(double* dst, size_t ldd, const double* src, size_t lds, int rows, int cols, cudaStream_t st) {
-  const dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-  k_transpose<<<grid, block, 0, st>>>(dst, ldd, src, lds, rows, cols);
+// One warp per column, persistent grid: warp slot w handles columns w, w + nslots, ... and owns slot w of the matrix workspace.
+__global__ void __launch_bounds__(32 * CB_EMANUEL_WARPS)
+    k_emanuel(const Par par, const __grid_constant__ In in, const __grid_constant__ Work W, const __grid_constant__ Out out, int c0, int n,
+              int NL, double dt) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * CB_EMANUEL_WARPS + warp, nslots = gridDim.x * CB_EMANUEL_WARPS;
+  double* sv = smem + (size_t)warp * V_COUNT * W.n1;
+  double* mw = W.m + (size_t)slot * M_COUNT * W.nm * W.nm;
+  for (int c = slot; c < n; c += nslots) convect_warp(par, in, W, out, (size_t)c0 + c, lane, sv, mw, NL, dt);
 }
 
 #define CUDA_OK(call)                                                                         \
@@ -62,10 +47,9 @@ struct cb200_emanuel_engine {
   int device = 0;
   Par par{};
   Work W{};
-  int cap_ncc = 0, cap_nlev = 0, cap_nl = 0;
-  double* d_nat = nullptr;  // native-layout staging of one chunk when the caller's layout is (ncol, nlev): inputs, then outputs
-  size_t nat_cap = 0;
-  int max_chunk = 32768;
+  int nslots = 0, cap_nl = 0, blocks_per_sm = 0, sm_count = 0;
+  size_t smem_bytes = 0;
+  int cap_nlev = 0;
   cb::HostPipe pipe;
   int32_t* d_iflag[2] = {nullptr, nullptr};
   int iflag_cap = 0;
@@ -76,26 +60,26 @@ struct cb200_emanuel_engine {
   double kernel_ms = 0.0;
 
   void free_work() {
-    cudaFree(W.v); cudaFree(W.m);
+    cudaFree(W.m);
     W = Work{};
-    cap_ncc = cap_nlev = cap_nl = 0;
+    nslots = cap_nl = cap_nlev = 0;
   }
-  int ensure_work(int ncc, int nlev, int NL) {
+  // shared memory per block and the persistent grid (blocks per SM from the occupancy calculator); one matrix slot per resident warp
+  int ensure_work(int nlev, int NL) {
     cb200_emanuel_engine* e = this;
-    if (ncc <= cap_ncc && nlev == cap_nlev && NL == cap_nl && W.v) return 0;
+    if (W.m && nlev == cap_nlev && NL == cap_nl) return 0;
     free_work();
-    W.ncc = ncc; W.n1 = nlev + 3; W.nm = NL + 2;
-    CUDA_OK(cudaMalloc(&W.v, sizeof(double) * (size_t)V_COUNT * W.n1 * ncc));
-    CUDA_OK(cudaMalloc(&W.m, sizeof(double) * (size_t)M_COUNT * W.nm * W.nm * ncc));
-    cap_ncc = ncc; cap_nlev = nlev; cap_nl = NL;
-    return 0;
-  }
-  int ensure_native(size_t doubles) {
-    cb200_emanuel_engine* e = this;
-    if (doubles <= nat_cap) return 0;
-    cudaFree(d_nat); d_nat = nullptr; nat_cap = 0;
-    CUDA_OK(cudaMalloc(&d_nat, doubles * sizeof(double)));
-    nat_cap = doubles;
+    W.n1 = nlev + 4;
+    W.nm = NL + 2;
+    smem_bytes = sizeof(double) * (size_t)CB_EMANUEL_WARPS * V_COUNT * W.n1;
+    if (smem_bytes > 200 * 1024) { error = "emanuel: too many levels for the shared-memory column slices"; return -3; }
+    CUDA_OK(cudaFuncSetAttribute(k_emanuel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_emanuel, 32 * CB_EMANUEL_WARPS, smem_bytes));
+    if (blocks_per_sm < 1) { error = "emanuel: kernel does not fit on an SM"; return -1; }
+    CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    nslots = sm_count * blocks_per_sm * CB_EMANUEL_WARPS;
+    CUDA_OK(cudaMalloc(&W.m, sizeof(double) * (size_t)nslots * M_COUNT * W.nm * W.nm));
+    cap_nlev = nlev; cap_nl = NL;
     return 0;
   }
 };
@@ -120,7 +104,6 @@ extern "C" int cb200_emanuel_create(cb200_emanuel_engine** out, const cb200_eman
     delete e;
     return -1;
   }
-  if (const char* mc = std::getenv("CLIMT_B200_EMANUEL_CHUNK")) e->max_chunk = std::max(64, std::atoi(mc));
   *out = e;
   return 0;
 }
@@ -129,7 +112,6 @@ extern "C" void cb200_emanuel_destroy(cb200_emanuel_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   e->free_work();
-  cudaFree(e->d_nat);
   cudaFree(e->d_iflag[0]); cudaFree(e->d_iflag[1]);
   e->pipe.destroy();
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -159,10 +141,13 @@ int validate(cb200_emanuel_engine* e, int ncol, int nlev, int NL, double dt, int
   return 0;
 }
 
-// kernels of one chunk; `in` / `out` already in the native (level, column) layout
-int launch_chunk(cb200_emanuel_engine* e, const In& in, const Out& out, int c0, int n, int NL, double dt, cudaStream_t st) {
+// one launch over n columns starting at column c0 of the arrays `in` / `out` describe
+int launch(cb200_emanuel_engine* e, const In& in, const Out& out, int c0, int n, int NL, double dt, cudaStream_t st) {
   if (e->timing) cudaEventRecord(e->ev0, st);
-  k_emanuel<<<(n + CB_EMANUEL_BLOCK - 1) / CB_EMANUEL_BLOCK, CB_EMANUEL_BLOCK, 0, st>>>(e->par, in, e->W, out, c0, n, NL, dt);
+  int blocks = (n + CB_EMANUEL_WARPS - 1) / CB_EMANUEL_WARPS;
+  const int resident = e->sm_count * e->blocks_per_sm;
+  if (blocks > resident) blocks = resident;
+  k_emanuel<<<blocks, 32 * CB_EMANUEL_WARPS, e->smem_bytes, st>>>(e->par, in, e->W, out, c0, n, NL, dt);
   e->launches += 1;
   if (e->timing) {
     cudaEventRecord(e->ev1, st);
@@ -174,32 +159,24 @@ int launch_chunk(cb200_emanuel_engine* e, const In& in, const Out& out, int c0, 
   return 0;
 }
 
-// One chunk whose arrays are in the component's (column, level) layout on the device: transpose in, compute, transpose out.
-// src arrays start at the chunk's first column; per-column scalars are layout-free.
-int run_chunk_reference_layout(cb200_emanuel_engine* e, int n, int nlev, int NL, double dt, int qs_mode, const cb200_emanuel_inputs& in,
-                               const cb200_emanuel_outputs& out, cudaStream_t st) {
-  const size_t L = (size_t)nlev, nn = (size_t)n;
-  if (e->ensure_native((6 * L + 1 + L + 4 * L) * nn)) return -1;
-  double* d = e->d_nat;
-  double *nt = d, *nq = nt + L * nn, *nu = nq + L * nn, *nv = nu + L * nn, *np = nv + L * nn, *nph = np + L * nn,
-         *nqs = nph + (L + 1) * nn, *oft = nqs + L * nn, *ofq = oft + L * nn, *ofu = ofq + L * nn, *ofv = ofu + L * nn;
-  transpose(nt, nn, in.t, L, n, nlev, st);
-  transpose(nq, nn, in.q, L, n, nlev, st);
-  transpose(nu, nn, in.u, L, n, nlev, st);
-  transpose(nv, nn, in.v, L, n, nlev, st);
-  transpose(np, nn, in.p, L, n, nlev, st);
-  transpose(nph, nn, in.ph, L + 1, n, nlev + 1, st);
-  if (qs_mode == QS_GIVEN) transpose(nqs, nn, in.qs, L, n, nlev, st);
-  e->launches += qs_mode == QS_GIVEN ? 7 : 6;
-  In ni{nlev, nn, nt, nq, nu, nv, np, nph, qs_mode == QS_GIVEN ? nqs : nullptr, in.cbmf, qs_mode};
-  Out no{nn, oft, ofq, ofu, ofv, out.precip, out.wd, out.tprime, out.qprime, out.cbmf, out.cape, out.iflag};
-  if (launch_chunk(e, ni, no, 0, n, NL, dt, st)) return -1;
-  transpose(out.ft, L, oft, nn, nlev, n, st);
-  transpose(out.fq, L, ofq, nn, nlev, n, st);
-  transpose(out.fu, L, ofu, nn, nlev, n, st);
-  transpose(out.fv, L, ofv, nn, nlev, n, st);
-  e->launches += 4;
-  return 0;
+// strides of the two layouts: 0 = (level, column) column-fastest over `ld` columns, 1 = (column, level) level-fastest
+In make_in(int nlev, int layout, size_t ld, const cb200_emanuel_inputs& p, int qs_mode) {
+  const size_t L = (size_t)nlev;
+  In in{};
+  in.nlev = nlev;
+  if (layout == 0) { in.ls = ld; in.cs = 1; in.ls_i = ld; in.cs_i = 1; }
+  else { in.ls = 1; in.cs = L; in.ls_i = 1; in.cs_i = L + 1; }
+  in.t = p.t; in.q = p.q; in.u = p.u; in.v = p.v; in.p = p.p; in.ph = p.ph; in.qs = qs_mode == QS_GIVEN ? p.qs : nullptr; in.cbmf = p.cbmf;
+  in.qs_mode = qs_mode;
+  return in;
+}
+Out make_out(int nlev, int layout, size_t ld, const cb200_emanuel_outputs& p) {
+  Out o{};
+  if (layout == 0) { o.ls = ld; o.cs = 1; }
+  else { o.ls = 1; o.cs = (size_t)nlev; }
+  o.ft = p.ft; o.fq = p.fq; o.fu = p.fu; o.fv = p.fv; o.precip = p.precip; o.wd = p.wd; o.tprime = p.tprime; o.qprime = p.qprime;
+  o.cbmf = p.cbmf; o.cape = p.cape; o.iflag = p.iflag;
+  return o;
 }
 
 }  // namespace
@@ -209,34 +186,18 @@ extern "C" int cb200_emanuel_run_device(cb200_emanuel_engine* e, int ncol, int n
   if (int rc = validate(e, ncol, nlev, max_conv_lev, dt, qs_mode, in, out)) return rc;
   if (layout != 0 && layout != 1) { e->error = "emanuel: layout must be 0 (level, column) or 1 (column, level)"; return -3; }
   CUDA_OK(cudaSetDevice(e->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  int chunk = ncol < e->max_chunk ? ncol : e->max_chunk;
-  chunk = (chunk + 31) / 32 * 32;
-  if (e->ensure_work(chunk, nlev, max_conv_lev)) return -1;
+  if (int rc = e->ensure_work(nlev, max_conv_lev)) return rc;
   e->launches = 0;
   e->kernel_ms = 0.0;
-  const size_t L = (size_t)nlev;
-  for (int c0 = 0; c0 < ncol; c0 += chunk) {
-    const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
-    if (layout == 0) {
-      In ni{nlev, (size_t)ncol, in->t, in->q, in->u, in->v, in->p, in->ph, in->qs, in->cbmf, qs_mode};
-      Out no{(size_t)ncol, out->ft, out->fq, out->fu, out->fv, out->precip, out->wd, out->tprime, out->qprime, out->cbmf, out->cape,
-             out->iflag};
-      if (launch_chunk(e, ni, no, c0, n, max_conv_lev, dt, st)) return -1;
-    } else {
-      cb200_emanuel_inputs ci{in->t + c0 * L, in->q + c0 * L, in->u + c0 * L, in->v + c0 * L, in->p + c0 * L, in->ph + c0 * (L + 1),
-                              in->qs ? in->qs + c0 * L : nullptr, in->cbmf + c0};
-      cb200_emanuel_outputs co{out->ft + c0 * L, out->fq + c0 * L, out->fu + c0 * L, out->fv + c0 * L, out->precip + c0, out->wd + c0,
-                               out->tprime + c0, out->qprime + c0, out->cbmf + c0, out->cape + c0, out->iflag + c0};
-      if (run_chunk_reference_layout(e, n, nlev, max_conv_lev, dt, qs_mode, ci, co, st)) return -1;
-    }
-  }
+  if (launch(e, make_in(nlev, layout, (size_t)ncol, *in, qs_mode), make_out(nlev, layout, (size_t)ncol, *out), 0, ncol, max_conv_lev, dt,
+             (cudaStream_t)stream))
+    return -1;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 // Host-pointer call in the component's layout ((ncol, nlev) C order): chunked 3-stream pipeline.  A chunk of columns is one
-// contiguous block of every array, so H2D / D2H are plain copies; the transposes run on the device.
+// contiguous block of every array, so H2D / D2H are plain copies and the kernel reads the chunk in place.
 extern "C" int cb200_emanuel_run_host(cb200_emanuel_engine* e, int ncol, int nlev, int max_conv_lev, double dt, int qs_mode,
                                       const cb200_emanuel_inputs* hin, const cb200_emanuel_outputs* hout) {
   if (int rc = validate(e, ncol, nlev, max_conv_lev, dt, qs_mode, hin, hout)) return rc;
@@ -244,10 +205,8 @@ extern "C" int cb200_emanuel_run_host(cb200_emanuel_engine* e, int ncol, int nle
   cb::HostPipe& P = e->pipe;
   CUDA_OK(P.init());
   int chunk = P.chunk * 4;  // convection moves 15x fewer bytes per column than radiation: larger chunks keep the grid filled
-  if (chunk > e->max_chunk) chunk = e->max_chunk;
   if (chunk > ncol) chunk = ncol;
-  const int wchunk = (chunk + 31) / 32 * 32;
-  if (e->ensure_work(wchunk, nlev, max_conv_lev)) return -1;
+  if (int rc = e->ensure_work(nlev, max_conv_lev)) return rc;
   const size_t L = (size_t)nlev;
   const size_t in_per_col = 6 * L + 1 + 1 + (qs_mode == QS_GIVEN ? L : 0), out_per_col = 4 * L + 6;
   CUDA_OK(P.ensure(in_per_col * chunk, out_per_col * chunk));
@@ -280,7 +239,7 @@ extern "C" int cb200_emanuel_run_host(cb200_emanuel_engine* e, int ncol, int nle
                                o + 4 * L * n + 3 * n, o + 4 * L * n + 4 * n, o + 4 * L * n + 5 * n, e->d_iflag[s]};
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.in_done[s], 0));
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.out_done[s], 0));
-    if (run_chunk_reference_layout(e, (int)n, nlev, max_conv_lev, dt, qs_mode, di, dout, P.s_cmp)) return -1;
+    if (launch(e, make_in(nlev, 1, n, di, qs_mode), make_out(nlev, 1, n, dout), 0, (int)n, max_conv_lev, dt, P.s_cmp)) return -1;
     CUDA_OK(cudaEventRecord(P.cmp_done[s], P.s_cmp));
     CUDA_OK(cudaStreamWaitEvent(P.s_out, P.cmp_done[s], 0));
     double* hdst[10] = {hout->ft, hout->fq, hout->fu, hout->fv, hout->precip, hout->wd, hout->tprime, hout->qprime, hout->cbmf, hout->cape};

@@ -310,11 +310,12 @@ def emanuel_emul_lib():
     return ctypes.CDLL(so)
 
 
-def run_emanuel_emul(params, arrays, dt, qs_mode, max_conv_lev=None):
-    """The CUDA engine's per-thread code compiled for the host; arrays in the component's (ncol, nlev) layout."""
+def run_emanuel_emul(params, arrays, dt, qs_mode, max_conv_lev=None, layout=1):
+    """The CUDA engine's column code compiled for the host; arrays in the component's (ncol, nlev) layout (layout 1) or the
+    radiation engines' (nlev, ncol) layout (layout 0)."""
     from climt_b200 import emanuel as EM
     lib = emanuel_emul_lib()
-    ncol, nlev = arrays["t"].shape
+    ncol, nlev = arrays["t"].shape if layout == 1 else arrays["t"].shape[::-1]
     nl = nlev - 3 if max_conv_lev is None else max_conv_lev
     p = EM.make_params(**params)
     pin, keep = EM.EmanuelInputs(), []
@@ -323,7 +324,7 @@ def run_emanuel_emul(params, arrays, dt, qs_mode, max_conv_lev=None):
             a = np.ascontiguousarray(arrays[k], dtype=np.float64)
             keep.append(a)
             setattr(pin, k, a.ctypes.data_as(_dp))
-    ins, outs = EM.EmanuelEngine.shapes(ncol, nlev)
+    ins, outs = EM.EmanuelEngine.shapes(ncol, nlev, layout)
     out = {k: np.zeros(outs[k]) for k in EM.EM_OUT}
     out["iflag"] = np.zeros(ncol, dtype=np.int32)
     pout = EM.EmanuelOutputs()
@@ -331,8 +332,8 @@ def run_emanuel_emul(params, arrays, dt, qs_mode, max_conv_lev=None):
         setattr(pout, k, out[k].ctypes.data_as(_dp))
     pout.iflag = out["iflag"].ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
     lib.emul_emanuel_run.argtypes = [ctypes.POINTER(EM.EmanuelParams), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
-                                     ctypes.POINTER(EM.EmanuelInputs), ctypes.POINTER(EM.EmanuelOutputs)]
-    rc = lib.emul_emanuel_run(ctypes.byref(p), ncol, nlev, nl, float(dt), int(qs_mode), ctypes.byref(pin), ctypes.byref(pout))
+                                     ctypes.c_int, ctypes.POINTER(EM.EmanuelInputs), ctypes.POINTER(EM.EmanuelOutputs)]
+    rc = lib.emul_emanuel_run(ctypes.byref(p), ncol, nlev, nl, float(dt), int(qs_mode), int(layout), ctypes.byref(pin), ctypes.byref(pout))
     assert rc == 0
     return out
 

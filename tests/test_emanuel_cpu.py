@@ -52,6 +52,11 @@ def test_kernel_code_on_host_matches_the_reference_numba_port(case):
     # saturation humidity handed in (qs_mode 0) == computed in the kernel (qs_mode 2)
     got0 = H.run_emanuel_emul(OE.PYTHON_DEFAULTS, H.emanuel_arrays(st, qs=st["qs_python"]), float(st["timestep"]), qs_mode=0)
     H.emanuel_compare(got0, got, 1e-12, case + " qs given")
+    # the radiation engines' (level, column) layout, read in place through strides: bit-identical
+    a0 = {k: (np.ascontiguousarray(v.T) if v.ndim == 2 else v) for k, v in H.emanuel_arrays(st).items()}
+    got_t = H.run_emanuel_emul(OE.PYTHON_DEFAULTS, a0, float(st["timestep"]), qs_mode=2, layout=0)
+    for k, v in got.items():
+        assert np.array_equal(got_t[k].T if v.ndim == 2 else got_t[k], v), k
 
 
 @pytest.mark.parametrize("case", CASES[:2])

@@ -100,7 +100,7 @@ def test_gmd_grid_size_and_device_layouts(gold):
     eng = emanuel.EmanuelEngine(par)
     arrays = H.emanuel_arrays(st)
     host = eng.run_host(arrays, dt, qs_mode=emanuel.QS_BOLTON)
-    assert eng.last_launches >= 2 * 11
+    assert eng.last_launches >= 2      # several pipeline chunks, one kernel launch each
     sub = slice(0, 2048)
     sst = {k: v[sub] for k, v in st.items()}
     rt, rd = OE.fortran_component_call(sst, dt, SYMPL)
