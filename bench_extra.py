@@ -3,6 +3,7 @@
 
   python bench_extra.py --workload mcica   # configs[2] per-GPU share: RRTMG LW+SW with McICA clouds (KISS RNG), 16384 col x 72 lev
   python bench_extra.py --workload cork    # configs[3] per-GPU share: CORK correlated-k LW+SW, 65536 col x 60 lev
+  python bench_extra.py --workload gmd     # configs[4] per-GPU share: RRTMG LW+SW + Emanuel convection, 8100 col x 60 lev
   python -m torch.distributed.run --nproc-per-node N ... bench_extra.py --workload cork --gpus N   # weak scaling, columns sharded
 
 Same measurement rules as bench.py: W >= 3 warm-up steps, CUDA events around K steps, max over ranks, inputs resident in HBM
@@ -25,7 +26,7 @@ from bench import ClockSampler  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", choices=["mcica", "cork"], required=True)
+    ap.add_argument("--workload", choices=["mcica", "cork", "gmd"], required=True)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -89,6 +90,86 @@ def main():
                 reps += 1
             dt = time.perf_counter() - t0
             return reps * n / dt, f"{n} of the workload's {ncol} columns x {reps} repetitions in {dt:.1f} s (C++ restatement, 1 core)"
+    elif args.workload == "gmd":
+        # One radiative-convective physics step of the aquaplanet configuration: RRTMG LW + SW (clear sky, as bench.py) and Emanuel
+        # convection on the same columns.  Device leg: one state resident in HBM in the (level, column) layout; the convection
+        # engine reads the radiation engines' temperature / pressure tensors in place (layout 0).
+        from climt_b200.engine import LWEngine, SWEngine, LW_IN, LW_OUT, SW_IN, lw_shapes
+        from climt_b200 import emanuel
+        ncol, nlay, dt_conv = args.ncol or 8100, 60, 1200.0
+        st = SY.make_lw_state(ncol, nlay, seed=20260925 + rank)
+        sts = SY.make_sw_state(ncol, nlay, seed=20260925 + rank)
+        es = SY.make_emanuel_state(ncol, nlay, seed=20260925 + rank)
+        abi, abis = H.to_abi(st), H.to_abi_sw(sts)
+        # the convection state on the radiation grid: same pressures, the convecting soundings' temperature and humidity
+        from climt_b200 import state as S
+        st["tlay"] = np.ascontiguousarray(es["air_temperature"].T)
+        st["tlev"] = np.ascontiguousarray(S.get_interface_values(st["tlay"], st["tsfc"], st["play"], st["plev"]))
+        sts = dict(sts, tlay=st["tlay"], tlev=st["tlev"])
+        abi, abis = H.to_abi(st), H.to_abi_sw(sts)
+        lw, sw = LWEngine(device=local), SWEngine(device=local)
+        epar = dict(minorig=1, elcrit=0.0011, tlcrit=-55.0, entp=1.5, sigd=0.05, sigs=0.12, omtrain=50.0, omtsnow=5.5, coeffr=1.0,
+                    coeffs=0.8, cu=0.7, beta=10.0, dtmax=0.9, alpha=0.1, damp=0.1, cpd=1004.64, cpv=1846.0, cl=2500.0, rv=461.5, rd=287.0,
+                    lv0=2.5e6, g=9.80665, rowl=1e3, delt0=300.0, t_rain=273.0)
+        em = emanuel.EmanuelEngine(epar, device=local)
+        _, outs = lw_shapes(ncol, nlay)
+        d_in = {k: torch.from_numpy(abi[k]).cuda() for k in LW_IN}
+        ds_in = {k: (d_in[k] if k in d_in and k in ("play", "plev", "tlay", "tlev", "tsfc") else torch.from_numpy(abis[k]).cuda()) for k in SW_IN}
+        d_out = {k: torch.empty(outs[k], dtype=torch.float64, device="cuda") for k in LW_OUT}
+        ds_out = {k: torch.empty(outs[k], dtype=torch.float64, device="cuda") for k in LW_OUT}
+        tr = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).cuda()  # noqa: E731
+        de_in = {"t": d_in["tlay"], "p": d_in["play"], "ph": d_in["plev"], "q": tr(es["specific_humidity"]), "u": tr(es["eastward_wind"]),
+                 "v": tr(es["northward_wind"]), "cbmf": torch.from_numpy(es["cloud_base_mass_flux"]).cuda()}
+        _, eouts = em.shapes(ncol, nlay, 0)
+        de_out = {k: torch.empty(eouts[k], dtype=torch.int32 if k == "iflag" else torch.float64, device="cuda") for k in eouts}
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=a.dtype)).pin_memory().numpy()  # noqa: E731
+        h_in, hs_in = {k: pin(abi[k]) for k in LW_IN}, {k: pin(abis[k]) for k in SW_IN}
+        h_out, hs_out = {k: pin(np.empty(outs[k])) for k in LW_OUT}, {k: pin(np.empty(outs[k])) for k in LW_OUT}
+        # host leg of the convection call: the component's (column, level) arrays
+        he_in = {"t": pin(np.ascontiguousarray(st["tlay"].T)), "q": pin(es["specific_humidity"]), "u": pin(es["eastward_wind"]),
+                 "v": pin(es["northward_wind"]), "p": pin(np.ascontiguousarray(st["play"].T)), "ph": pin(np.ascontiguousarray(st["plev"].T)),
+                 "cbmf": pin(es["cloud_base_mass_flux"])}
+        _, eouts1 = em.shapes(ncol, nlay, 1)
+        he_out = {k: pin(np.empty(eouts1[k], dtype=np.int32 if k == "iflag" else np.float64)) for k in eouts1}
+
+        def step_device():
+            lw.run_device(ncol, nlay, d_in, d_out)
+            sw.run_device(ncol, nlay, ds_in, ds_out, dyofyr=1)
+            em.run_device(ncol, nlay, de_in, de_out, dt_conv, qs_mode=emanuel.QS_BOLTON, layout=0)
+
+        def step_host():
+            lw.run_host(ncol, nlay, h_in, h_out, wait=False)
+            sw.run_host(ncol, nlay, hs_in, hs_out, dyofyr=1, wait=False)
+            em.run_host(he_in, dt_conv, qs_mode=emanuel.QS_BOLTON, out=he_out)
+            lw.wait()
+            sw.wait()
+        name = "RRTMG LW+SW + Emanuel convection columns/s (60 lev)"
+        workload = (f"radiative-convective physics step: RRTMG LW+SW clear sky + Emanuel convection (dt 1200 s), {ncol} columns x 60 levels per GPU "
+                    "(BASELINE.json configs[4] is 360 x 180 = 64800 columns on 8 GPUs)")
+        launches = lambda: lw.last_launches + sw.last_launches + em.last_launches  # noqa: E731
+        e_h2d = sum(v.nbytes for v in he_in.values())
+        e_d2h = sum(v.nbytes for v in he_out.values())
+        xfer = lambda: tuple(a + b + c for a, b, c in zip(lw.last_transfer_bytes, sw.last_transfer_bytes, (e_h2d, e_d2h)))  # noqa: E731
+
+        def cpu():
+            from oracle import emanuel as OE
+            n = 128
+            sub = {k: v[:, :n] if v.ndim == 2 else (v[:, :n, :] if v.ndim == 3 and v.shape[-1] in (14, 16) else v[..., :n]) for k, v in st.items()}
+            subs = {k: v[:, :n] if v.ndim == 2 else (v[:, :n, :] if v.ndim == 3 and v.shape[-1] in (14, 16) else v[..., :n]) for k, v in sts.items()}
+            sube = {k: v[:n] for k, v in es.items()}
+            sube["air_temperature"] = np.ascontiguousarray(st["tlay"].T)[:n]
+            sube["air_pressure"] = np.ascontiguousarray(st["play"].T)[:n]
+            sube["air_pressure_on_interface_levels"] = np.ascontiguousarray(st["plev"].T)[:n]
+            olw, osw = H.lw_oracle(), H.sw_oracle()
+            consts = {k: epar[k] for k in ("cpd", "cpv", "cl", "rv", "rd", "lv0", "g", "rowl")}
+            t0, reps = time.perf_counter(), 0
+            while time.perf_counter() - t0 < 10.0:
+                H.run_lw_oracle(olw, sub)
+                osw(subs, dyofyr=1)
+                OE.fortran_component_call(sube, dt_conv, consts)
+                reps += 1
+            dt = time.perf_counter() - t0
+            return reps * n / dt, f"{n} of the workload's {ncol} columns x {reps} repetitions in {dt:.1f} s (C++ restatements of RRTMG and CONVECT, 1 core)"
     else:
         from climt_b200 import cork
         ncol, nlay = args.ncol or 65536, 60
