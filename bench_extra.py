@@ -91,12 +91,18 @@ def main():
             dt = time.perf_counter() - t0
             return reps * n / dt, f"{n} of the workload's {ncol} columns x {reps} repetitions in {dt:.1f} s (C++ restatement, 1 core)"
     elif args.workload == "gmd":
-        # One radiative-convective physics step of the aquaplanet configuration: RRTMG LW + SW (clear sky, as bench.py) and Emanuel
-        # convection on the same columns.  Device leg: one state resident in HBM in the (level, column) layout; the convection
-        # engine reads the radiation engines' temperature / pressure tensors in place (layout 0).
+        # One radiative-convective physics step of the aquaplanet configuration: Instellation (zenith angle) -> RRTMG LW + SW (clear
+        # sky, as bench.py) -> SlabSurface (surface energy balance from the engines' surface fluxes), and Emanuel convection on the
+        # same columns.  Device leg: one state resident in HBM in the (level, column) layout; the shortwave engine reads the cosine
+        # Instellation wrote, the convection engine reads the radiation engines' temperature / pressure tensors in place (layout 0),
+        # the slab reads row 0 of the flux outputs in place.
         from climt_b200.engine import LWEngine, SWEngine, LW_IN, LW_OUT, SW_IN, lw_shapes
-        from climt_b200 import emanuel
+        import datetime
+        from climt_b200 import emanuel, instellation as INST, slab_surface as SLAB
         ncol, nlay, dt_conv = args.ncol or 8100, 60, 1200.0
+        when = datetime.datetime(2026, 3, 20, 12, 0)
+        jc = INST.julian_centuries(when)
+        sfc = SY.make_surface_state(ncol, seed=20260925 + rank)
         st = SY.make_lw_state(ncol, nlay, seed=20260925 + rank)
         sts = SY.make_sw_state(ncol, nlay, seed=20260925 + rank)
         es = SY.make_emanuel_state(ncol, nlay, seed=20260925 + rank)
@@ -131,28 +137,39 @@ def main():
                  "cbmf": pin(es["cloud_base_mass_flux"])}
         _, eouts1 = em.shapes(ncol, nlay, 1)
         he_out = {k: pin(np.empty(eouts1[k], dtype=np.int32 if k == "iflag" else np.float64)) for k in eouts1}
+        d_sfc = {k: torch.from_numpy(v).cuda() for k, v in sfc.items()}
+        h_sfc = {k: pin(v) for k, v in sfc.items()}
+        flux_names = {"downwelling_shortwave_flux_in_air": (1, "dflx"), "downwelling_longwave_flux_in_air": (0, "dflx"),
+                      "upwelling_shortwave_flux_in_air": (1, "uflx"), "upwelling_longwave_flux_in_air": (0, "uflx")}
+        d_slab = dict(d_sfc, **{k: (ds_out if w else d_out)[f] for k, (w, f) in flux_names.items()})
+        slab_result = {}
 
         def step_device():
+            _, ds_in["coszen"] = INST.instellation_device(d_sfc["latitude"], d_sfc["longitude"], jc, want_coszen=True)
             lw.run_device(ncol, nlay, d_in, d_out)
             sw.run_device(ncol, nlay, ds_in, ds_out, dyofyr=1)
             em.run_device(ncol, nlay, de_in, de_out, dt_conv, qs_mode=emanuel.QS_BOLTON, layout=0)
+            slab_result["device"] = SLAB.slab_surface_device(d_slab, flux_layout="level_major")
 
         def step_host():
+            hs_in["coszen"][:] = np.cos(INST.instellation_host(h_sfc["latitude"], h_sfc["longitude"], jc, local))
             lw.run_host(ncol, nlay, h_in, h_out, wait=False)
             sw.run_host(ncol, nlay, hs_in, hs_out, dyofyr=1, wait=False)
             em.run_host(he_in, dt_conv, qs_mode=emanuel.QS_BOLTON, out=he_out)
             lw.wait()
             sw.wait()
+            # the engines' host outputs are (interface_levels, column): row 0 is the surface value of every column
+            slab_result["host"] = SLAB.slab_surface_host(dict(h_sfc, **{k: (hs_out if w else h_out)[f][0] for k, (w, f) in flux_names.items()}), local)
         name = "RRTMG LW+SW + Emanuel convection columns/s (60 lev)"
-        workload = (f"radiative-convective physics step: RRTMG LW+SW clear sky + Emanuel convection (dt 1200 s), {ncol} columns x 60 levels per GPU "
-                    "(BASELINE.json configs[4] is 360 x 180 = 64800 columns on 8 GPUs)")
-        launches = lambda: lw.last_launches + sw.last_launches + em.last_launches  # noqa: E731
-        e_h2d = sum(v.nbytes for v in he_in.values())
-        e_d2h = sum(v.nbytes for v in he_out.values())
+        workload = (f"radiative-convective physics step: Instellation -> RRTMG LW+SW clear sky -> SlabSurface, + Emanuel convection (dt 1200 s), "
+                    f"{ncol} columns x 60 levels per GPU (BASELINE.json configs[4] is 360 x 180 = 64800 columns on 8 GPUs)")
+        launches = lambda: lw.last_launches + sw.last_launches + em.last_launches + 2  # noqa: E731  (+ k_instellation, k_slab_surface)
+        e_h2d = sum(v.nbytes for v in he_in.values()) + 2 * 8 * ncol + (15 * 8 + 4) * ncol
+        e_d2h = sum(v.nbytes for v in he_out.values()) + 8 * ncol + 2 * 8 * ncol
         xfer = lambda: tuple(a + b + c for a, b, c in zip(lw.last_transfer_bytes, sw.last_transfer_bytes, (e_h2d, e_d2h)))  # noqa: E731
 
         def cpu():
-            from oracle import emanuel as OE
+            from oracle import emanuel as OE, adjacent as OA
             n = 128
             sub = {k: v[:, :n] if v.ndim == 2 else (v[:, :n, :] if v.ndim == 3 and v.shape[-1] in (14, 16) else v[..., :n]) for k, v in st.items()}
             subs = {k: v[:, :n] if v.ndim == 2 else (v[:, :n, :] if v.ndim == 3 and v.shape[-1] in (14, 16) else v[..., :n]) for k, v in sts.items()}
@@ -164,9 +181,13 @@ def main():
             consts = {k: epar[k] for k in ("cpd", "cpv", "cl", "rv", "rd", "lv0", "g", "rowl")}
             t0, reps = time.perf_counter(), 0
             while time.perf_counter() - t0 < 10.0:
-                H.run_lw_oracle(olw, sub)
-                osw(subs, dyofyr=1)
+                subs["coszen"] = np.cos(OA.instellation(sfc["latitude"][:n], sfc["longitude"][:n], when))
+                ol = H.run_lw_oracle(olw, sub)
+                os_ = osw(subs, dyofyr=1)
                 OE.fortran_component_call(sube, dt_conv, consts)
+                OA.slab_surface(dict({k: v[:n] for k, v in sfc.items()}, downwelling_shortwave_flux_in_air=os_["swdflx"][0],
+                                     downwelling_longwave_flux_in_air=ol["dflx"][0], upwelling_shortwave_flux_in_air=os_["swuflx"][0],
+                                     upwelling_longwave_flux_in_air=ol["uflx"][0]))
                 reps += 1
             dt = time.perf_counter() - t0
             return reps * n / dt, f"{n} of the workload's {ncol} columns x {reps} repetitions in {dt:.1f} s (C++ restatements of RRTMG and CONVECT, 1 core)"

@@ -8,7 +8,7 @@ table, re-wrapping of outputs) for the drop-in components to be exercised throug
 import numpy as np
 
 try:  # pragma: no cover - not available in the build image
-    from sympl import TendencyComponent, ImplicitTendencyComponent, DataArray, initialize_numpy_arrays_with_properties  # noqa: F401
+    from sympl import TendencyComponent, ImplicitTendencyComponent, DiagnosticComponent, DataArray, initialize_numpy_arrays_with_properties  # noqa: F401
     HAVE_SYMPL = True
 except Exception:  # ImportError or a broken install
     HAVE_SYMPL = False
@@ -36,7 +36,10 @@ except Exception:  # ImportError or a broken install
               "g/g": ("1", 1.0), "kg/kg": ("1", 1.0), "m s^-1": ("m s^-1", 1.0), "kg m^-2 s^-1": ("kg m^-2 s^-1", 1.0), "dimensionless": ("1", 1.0), "mole/mole": ("1", 1.0),
               "": ("1", 1.0), "1": ("1", 1.0),
               "W m^-2": ("W m^-2", 1.0), "degK day^-1": ("K day^-1", 1.0), "K day^-1": ("K day^-1", 1.0),
-              "radians": ("rad", 1.0), "degrees": ("rad", np.pi / 180.0)}
+              "radians": ("rad", 1.0), "degrees": ("rad", np.pi / 180.0),
+              "degrees_north": ("degrees_north", 1.0), "degrees_east": ("degrees_east", 1.0),
+              "J kg^-1 degK^-1": ("J kg^-1 K^-1", 1.0), "J kg^-1 K^-1": ("J kg^-1 K^-1", 1.0), "kg m^-3": ("kg m^-3", 1.0),
+              "degK s^-1": ("K s^-1", 1.0), "K s^-1": ("K s^-1", 1.0)}
 
     def _unit_factor(src, dst):
         if src == dst:
@@ -51,7 +54,8 @@ except Exception:  # ImportError or a broken install
 
     def _to_raw(da, dims, units):
         """DataArray -> numpy in the component's dims; '*' collects every other dim (C order)."""
-        vals = da.values * _unit_factor(da.attrs.get("units", ""), units)
+        numeric = da.values.dtype.kind in "fiub"  # string-valued quantities (area_type) pass through unconverted
+        vals = da.values * _unit_factor(da.attrs.get("units", ""), units) if numeric else da.values
         named = [d for d in dims if d != "*"]
         for d in named:
             if d not in da.dims:
@@ -71,12 +75,13 @@ except Exception:  # ImportError or a broken install
                 shape.append(v.shape[k])
                 k += 1
         star_shape = tuple(da.values.shape[da.dims.index(x)] for x in star)
-        return np.ascontiguousarray(v.reshape(shape), dtype=np.float64), tuple(star), star_shape
+        return np.ascontiguousarray(v.reshape(shape), dtype=np.float64 if numeric else None), tuple(star), star_shape
 
     class TendencyComponent:
         input_properties = {}
         tendency_properties = {}
         diagnostic_properties = {}
+        _diagnostic_only = False
 
         def __init__(self, **kwargs):
             if kwargs:
@@ -90,7 +95,10 @@ except Exception:  # ImportError or a broken install
                 raw[name], s, ss = _to_raw(state[name], prop["dims"], prop.get("units", ""))
                 if "*" in prop["dims"] and len(s) >= len(star):
                     star, star_shape = s, ss
-            tend, diag = self.array_call(raw, *extra)
+            if "time" in state:
+                raw["time"] = state["time"]
+            result = self.array_call(raw, *extra)
+            tend, diag = ({}, result) if self._diagnostic_only else result
 
             def wrap(arr, prop, name=None):
                 dims, shape, k = [], [], 0
@@ -105,8 +113,14 @@ except Exception:  # ImportError or a broken install
                         shape.append(arr.shape[k])
                     k += 1
                 return DataArray(np.asarray(arr).reshape(shape), dims, {"units": prop.get("units", "")})
-            return ({k: wrap(v, self.tendency_properties[k], k) for k, v in tend.items()},
-                    {k: wrap(v, self.diagnostic_properties[k]) for k, v in diag.items()})
+            diag = {k: wrap(v, self.diagnostic_properties[k]) for k, v in diag.items()}
+            if self._diagnostic_only:
+                return diag
+            return {k: wrap(v, self.tendency_properties[k], k) for k, v in tend.items()}, diag
+
+    class DiagnosticComponent(TendencyComponent):
+        """sympl.DiagnosticComponent: `component(state)` -> diagnostics dict; array_call returns the diagnostics only."""
+        _diagnostic_only = True
 
     class ImplicitTendencyComponent(TendencyComponent):
         """sympl.ImplicitTendencyComponent: `component(state, timestep)` -> array_call(raw_state, timestep)."""

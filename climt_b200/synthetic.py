@@ -113,3 +113,21 @@ def make_emanuel_state(ncol, nlev, seed=20260925):
     st = {"air_temperature": t.T, "specific_humidity": q.T, "eastward_wind": u.T, "northward_wind": v.T,
           "air_pressure": p.T / 100.0, "air_pressure_on_interface_levels": p_int.T / 100.0, "cloud_base_mass_flux": cbmf}
     return {k: np.ascontiguousarray(a, dtype=np.float64) for k, a in st.items()}
+
+
+def make_surface_state(ncol, seed=20260925, aquaplanet=True):
+    """Latitude / longitude of the columns and the slab-surface fields (SlabSurface's inputs other than the radiative fluxes):
+    an aquaplanet (every column open sea, 50 m mixed layer -- BASELINE.json configs[4]) or a random mix of the four area types."""
+    rng = np.random.default_rng(seed + 5)
+    st = {
+        "latitude": rng.uniform(-90.0, 90.0, ncol), "longitude": rng.uniform(0.0, 360.0, ncol),
+        "surface_upward_latent_heat_flux": rng.uniform(0.0, 250.0, ncol),
+        "surface_upward_sensible_heat_flux": rng.uniform(-20.0, 80.0, ncol),
+        "surface_thermal_capacity": np.full(ncol, 4.1813e3), "surface_material_density": np.full(ncol, 1.0e3),
+        "upward_heat_flux_at_ground_level_in_soil": np.zeros(ncol), "heat_flux_into_sea_water_due_to_sea_ice": np.zeros(ncol),
+        "area_type": np.full(ncol, 2, dtype=np.int32) if aquaplanet else rng.integers(0, 4, ncol).astype(np.int32),
+        "soil_layer_thickness": np.full(ncol, 50.0), "ocean_mixed_layer_thickness": np.full(ncol, 50.0),
+        "heat_capacity_of_soil": np.full(ncol, 2000.0), "sea_water_density": np.full(ncol, 1.029e3),
+        "ocean_heat_transport_convergence": rng.uniform(-30.0, 30.0, ncol),
+    }
+    return {k: np.ascontiguousarray(a) for k, a in st.items()}

@@ -320,6 +320,31 @@ void emanuel_convection(double* temp, double* q, double* qs, double* u, double* 
 int cb200_marshal_device(int device, int ncol, int nlay, const double* q, const double* t, const double* tsfc, const double* p,
                          const double* p_int, const double* zenith, double* h2ovmr, double* tlev, double* coszen, void* stream);
 
+/* ============================== column steps either side of the radiation call ==============================
+ * Instellation: replaces `_instellation_kernel_np` and its scalar helpers (climt/_components/instellation/component.py:84-191).
+ * julian_centuries = days since 2000-01-01 12:00 / 36525 (component.py:53, 66-76; the `fractional_day` argument of the reference
+ * kernel is unused by it).  lat_deg, lon_deg (ncol) -> zenith (ncol) [rad, clamped to pi/2]; coszen (device call only, may be NULL)
+ * = cos(zenith), the shortwave engine's input.  cb200_instellation_orbit is the per-call scalar part (host arithmetic, no GPU). */
+void cb200_instellation_orbit(double julian_centuries, double* sin_dec, double* cos_dec, double* right_ascension, double* gmst);
+int cb200_instellation_run_device(int device, int ncol, const double* lat_deg, const double* lon_deg, double julian_centuries,
+                                  double* zenith, double* coszen, void* stream);
+int cb200_instellation_run_host(int device, int ncol, const double* lat_deg, const double* lon_deg, double julian_centuries,
+                                double* zenith);
+
+/* SlabSurface: replaces `_slab_surface_kernel_np` (climt/_components/slab_surface.py:449-517), include_ekman=False.
+ * Every array has ncol entries except the four flux arrays, whose surface value for column i is element i * flux_stride
+ * (component layout ("*", "interface_levels"): flux_stride = nlev + 1; the engines' (nlev + 1, ncol) outputs: flux_stride = 1).
+ * area_type: int32 codes of AREA_MAP (slab_surface.py:7): 0 land, 1 land_ice, 2 sea, 3 sea_ice. */
+typedef struct cb200_slab_inputs {
+  const double *sw_down, *lw_down, *sw_up, *lw_up, *lh, *sh;
+  const int* area_type;
+  const double *up_heat_soil, *heat_flux_sea_ice, *sea_water_dens, *surf_dens, *heat_cap_soil, *surf_therm_cap, *ocean_mix_thick,
+      *soil_layer_thick, *ocean_heat_transport;
+} cb200_slab_inputs;
+int cb200_slab_surface_run_device(int device, int ncol, long flux_stride, const cb200_slab_inputs* in, double* tend_ts,
+                                  double* depth, void* stream);
+int cb200_slab_surface_run_host(int device, int ncol, long flux_stride, const cb200_slab_inputs* in, double* tend_ts, double* depth);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,184 @@
+"""Instellation and SlabSurface: the column steps that produce the shortwave engine's zenith angle and consume
+the engines' surface fluxes.
+
+CPU: the oracle (oracle/adjacent.py) against golden vectors produced by running the reference's own component classes
+(tests/golden/make_adjacent_golden.py) and against the reference's cached outputs; the host arithmetic of the C ABI
+(cb200_instellation_orbit) against the oracle.  GPU: the drop-in components through the C ABI against the same goldens.
+Tolerances: zenith angle 1e-12 rad absolute (fp64; sin/cos/acos of CUDA's libm vs numba's differ in the last bits, and acos
+amplifies them near the poles of the clamp) where BASELINE.json asks 1e-6 relative; SlabSurface bit-exact (one IEEE division)."""
+import datetime
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import adjacent as OA
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(H.os.path.join(H.HERE, "golden", "adjacent_reference.npz"))
+
+
+INST_CASES = ("j2000", "equinox", "solstice", "past", "cache_default")
+SLAB_CASES = ("mixed", "flux_1d", "one")
+
+
+def _time(z, case):
+    return datetime.datetime(*[int(x) for x in z[f"instellation/{case}/time"]])
+
+
+def _slab_in(z, case):
+    pre = f"slab/{case}/in/"
+    return {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+
+
+@pytest.mark.parametrize("case", INST_CASES)
+def test_instellation_oracle_matches_the_reference_component(gold, case):
+    lat, lon = gold[f"instellation/{case}/lat"], gold[f"instellation/{case}/lon"]
+    zen = OA.instellation(lat, lon, _time(gold, case))
+    ref = gold[f"instellation/{case}/zenith"]
+    assert ref.shape == lat.shape
+    np.testing.assert_allclose(zen, ref, rtol=0, atol=1e-13)
+    assert (ref < np.pi / 2).any() or case == "cache_default"  # the day side is exercised, not only the clamp
+
+
+def test_instellation_reference_caches(gold):
+    """TestInstellation-{column,3d}: default state, 2000-01-01 00:00, lat = lon = 0 -> night, clamped to pi/2"""
+    for kind in ("column", "3d"):
+        ref = gold[f"cache/TestInstellation-{kind}/0/zenith_angle"]
+        zen = OA.instellation(np.zeros(ref.shape), np.zeros(ref.shape), datetime.datetime(2000, 1, 1))
+        if kind == "column":
+            np.testing.assert_allclose(zen, ref, rtol=0, atol=1e-14)
+        assert np.all(ref[..., 0] == np.pi / 2) or kind == "3d"
+
+
+@pytest.mark.parametrize("case", SLAB_CASES)
+def test_slab_oracle_matches_the_reference_component(gold, case):
+    tend, depth, oht = OA.slab_surface(_slab_in(gold, case))
+    np.testing.assert_array_equal(tend, gold[f"slab/{case}/out/tendency"])
+    np.testing.assert_array_equal(depth, gold[f"slab/{case}/out/depth"])
+    np.testing.assert_array_equal(oht, gold[f"slab/{case}/out/ocean_heat_transport_convergence"])
+    if case == "mixed":
+        assert (tend != 0).sum() > 50 and (tend == 0).sum() > 50   # ice / zero-capacity branches and the generic one
+
+
+def test_slab_reference_caches(gold):
+    for kind in ("column", "3d"):
+        assert np.all(gold[f"cache/TestSlabSurface-{kind}/0/surface_temperature"] == 0.0)
+        assert np.all(gold[f"cache/TestSlabSurface-{kind}/1/depth_of_slab_surface"] == 50.0)
+
+
+@pytest.mark.parametrize("case", INST_CASES)
+def test_orbit_scalars_of_the_c_abi(gold, case):
+    """host arithmetic only (no GPU): the per-call scalars the library hands to k_instellation"""
+    from climt_b200 import instellation as I
+    jc = I.julian_centuries(_time(gold, case))
+    assert jc == OA.julian_centuries(_time(gold, case))
+    np.testing.assert_allclose(I.orbit(jc), OA.orbit(jc), rtol=0, atol=2e-15)
+
+
+def test_ekman_variant_is_rejected_loudly():
+    from climt_b200.slab_surface import SlabSurface
+    with pytest.raises(NotImplementedError):
+        SlabSurface(include_ekman=True)
+
+
+def test_area_type_codes():
+    from climt_b200.slab_surface import area_type_codes
+    np.testing.assert_array_equal(area_type_codes(np.array(["sea", "land", "lake", "sea_ice", "land_ice"])), [2, 0, 0, 3, 1])
+    np.testing.assert_array_equal(area_type_codes(np.array([3, 1], dtype=np.int64)), [3, 1])
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", INST_CASES)
+def test_instellation_drop_in_matches_the_reference_component(gold, case):
+    from climt_b200.instellation import Instellation
+    lat, lon = gold[f"instellation/{case}/lat"], gold[f"instellation/{case}/lon"]
+    out = Instellation().array_call({"latitude": lat, "longitude": lon, "time": _time(gold, case)})
+    ref = gold[f"instellation/{case}/zenith"]
+    assert out["zenith_angle"].shape == ref.shape
+    np.testing.assert_allclose(out["zenith_angle"], ref, rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_instellation_through_call_and_on_the_device(gold):
+    import torch
+    from climt_b200.instellation import Instellation, instellation_device, julian_centuries
+    from climt_b200.sympl_shim import DataArray, HAVE_SYMPL
+    case = "solstice"
+    lat, lon, ref = gold[f"instellation/{case}/lat"], gold[f"instellation/{case}/lon"], gold[f"instellation/{case}/zenith"]
+    if not HAVE_SYMPL:
+        st = {"latitude": DataArray(lat, ("lat", "lon"), {"units": "degrees_north"}),
+              "longitude": DataArray(lon, ("lat", "lon"), {"units": "degrees_east"}), "time": _time(gold, case)}
+        d = Instellation()(st)
+        assert d["zenith_angle"].dims == ("lat", "lon") and d["zenith_angle"].attrs["units"] == "radians"
+        np.testing.assert_allclose(d["zenith_angle"].values, ref, rtol=0, atol=1e-12)
+    tl, to = torch.from_numpy(lat).cuda(), torch.from_numpy(lon).cuda()
+    out = Instellation().array_call({"latitude": tl, "longitude": to, "time": _time(gold, case)})["zenith_angle"]
+    assert out.is_cuda and tuple(out.shape) == lat.shape
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=1e-12)
+    zen, cz = instellation_device(tl, to, julian_centuries(_time(gold, case)), want_coszen=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(zen.cpu().numpy(), out.cpu().numpy().reshape(-1))
+    np.testing.assert_allclose(cz.cpu().numpy(), np.cos(ref).reshape(-1), rtol=0, atol=1e-12)
+    # a GMD-sized grid against the oracle
+    rng = np.random.default_rng(5)
+    lat2, lon2 = rng.uniform(-90, 90, 64800), rng.uniform(0, 360, 64800)
+    when = datetime.datetime(2026, 10, 17, 6, 30)
+    got = Instellation().array_call({"latitude": lat2, "longitude": lon2, "time": when})["zenith_angle"]
+    np.testing.assert_allclose(got, OA.instellation(lat2, lon2, when), rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", SLAB_CASES)
+def test_slab_drop_in_matches_the_reference_component(gold, case):
+    from climt_b200.slab_surface import SlabSurface
+    tend, diag = SlabSurface().array_call(_slab_in(gold, case))
+    np.testing.assert_array_equal(tend["surface_temperature"], gold[f"slab/{case}/out/tendency"])
+    np.testing.assert_array_equal(diag["depth_of_slab_surface"], gold[f"slab/{case}/out/depth"])
+    np.testing.assert_array_equal(diag["ocean_heat_transport_convergence"], gold[f"slab/{case}/out/ocean_heat_transport_convergence"])
+
+
+@pytest.mark.gpu
+def test_slab_on_the_device_in_both_flux_layouts(gold):
+    import torch
+    from climt_b200.slab_surface import SlabSurface, area_type_codes
+    s = _slab_in(gold, "mixed")
+    ref_t, ref_d = gold["slab/mixed/out/tendency"], gold["slab/mixed/out/depth"]
+    dev = {k: torch.from_numpy(area_type_codes(v) if k == "area_type" else np.ascontiguousarray(v)).cuda() for k, v in s.items()}
+    tend, diag = SlabSurface().array_call(dev)
+    assert tend["surface_temperature"].is_cuda
+    np.testing.assert_array_equal(tend["surface_temperature"].cpu().numpy(), ref_t)
+    np.testing.assert_array_equal(diag["depth_of_slab_surface"].cpu().numpy(), ref_d)
+    # the radiation engines' (interface_levels, column) outputs, read in place
+    lm = dict(dev)
+    for k in list(lm):
+        if k.endswith("_flux_in_air"):
+            lm[k] = dev[k].t().contiguous()
+    tend2, _ = SlabSurface(flux_layout="level_major").array_call(lm)
+    np.testing.assert_array_equal(tend2["surface_temperature"].cpu().numpy(), ref_t)
+
+
+@pytest.mark.gpu
+def test_slab_through_call_with_string_area_types(gold):
+    from climt_b200.slab_surface import SlabSurface
+    from climt_b200.sympl_shim import DataArray, HAVE_SYMPL
+    if HAVE_SYMPL:
+        pytest.skip("exercised through the shim only")
+    s = _slab_in(gold, "mixed")
+    comp = SlabSurface()
+    ny, nx = 1, s["area_type"].size
+    st = {}
+    for name, prop in comp.input_properties.items():
+        a = s[name]
+        if a.ndim == 2:  # ("*", "interface_levels") -> (interface_levels, lat, lon), the model's own order
+            st[name] = DataArray(np.ascontiguousarray(a.T).reshape(-1, ny, nx), ("interface_levels", "lat", "lon"), {"units": prop["units"]})
+        else:
+            st[name] = DataArray(a.reshape(ny, nx), ("lat", "lon"), {"units": prop["units"]})
+    tend, diag = comp(st)
+    assert tend["surface_temperature"].dims == ("lat", "lon") and tend["surface_temperature"].attrs["units"] == "degK s^-1"
+    np.testing.assert_array_equal(tend["surface_temperature"].values.reshape(-1), gold["slab/mixed/out/tendency"])
+    np.testing.assert_array_equal(diag["depth_of_slab_surface"].values.reshape(-1), gold["slab/mixed/out/depth"])
