@@ -58,18 +58,26 @@ def _load_netcdf_table(path):
     return out
 
 
+def resolve_k_table_path(name_or_path):
+    """a path, or the name of a table shipped under ``climt_b200/data/cork/`` (.npz, then .nc like the reference, then .cb2k)"""
+    path = os.fspath(name_or_path)
+    if os.path.isfile(path):
+        return path
+    for ext in (".npz", ".nc", ".cb2k"):
+        cand = os.path.join(_DATA, f"{name_or_path}{ext}")
+        if os.path.isfile(cand):
+            return cand
+    raise FileNotFoundError(f"No k-table named {name_or_path!r} (.npz or .nc)")
+
+
 def load_k_table(name_or_path):
     """Same contract as the reference's load_k_table (cork/optics/correlated_k.py:186-218): a path to a ``.npz`` /
-    ``.nc`` file, or the name of a table shipped under ``climt_b200/data/cork/``; returns a dict of arrays."""
-    path = name_or_path
-    if not os.path.isfile(path):
-        for ext in (".npz", ".nc"):
-            cand = os.path.join(_DATA, f"{name_or_path}{ext}")
-            if os.path.isfile(cand):
-                path = cand
-                break
-        else:
-            raise FileNotFoundError(f"No k-table named {name_or_path!r} (.npz or .nc)")
+    ``.nc`` file, or the name of a table shipped under ``climt_b200/data/cork/``; returns a dict of arrays.
+    Also reads the engine's own container (``.cb2k``, climt_b200/table_store.py)."""
+    path = resolve_k_table_path(name_or_path)
+    if path.endswith(".cb2k"):
+        from . import table_store
+        return table_store.container_to_ktable(table_store.read_container(path))
     if path.endswith(".nc"):
         return _load_netcdf_table(path)
     with np.load(path, allow_pickle=True) as z:
@@ -274,7 +282,13 @@ class CorkEngine:
             return
         self.table = load_k_table(table) if isinstance(table, (str, os.PathLike)) else table
         self.ctable, self._keep = make_ctable(self.table)
-        if self._L.cb200_cork_create(ctypes.byref(self._h), ctypes.byref(self.ctable), g, cpd, sigma, device):
+        if isinstance(table, (str, os.PathLike)) and os.fspath(table).endswith(".cb2k"):
+            # the engine's own container: the library reads, classifies and re-lays out the file itself (no numpy on this path)
+            self._L.cb200_cork_create_from_file.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p] + [ctypes.c_double] * 3 + [ctypes.c_int]
+            rc = self._L.cb200_cork_create_from_file(ctypes.byref(self._h), os.fspath(table).encode(), g, cpd, sigma, device)
+        else:
+            rc = self._L.cb200_cork_create(ctypes.byref(self._h), ctypes.byref(self.ctable), g, cpd, sigma, device)
+        if rc:
             raise RuntimeError(self._L.cb200_global_error().decode())
         self.nband, self.ngpt, self.ngas = self.ctable.nband, self.ctable.ngpt, self.ctable.ngas
 

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -147,6 +148,108 @@ extern "C" int cb200_cork_create(cb200_cork_engine** out, const cb200_cork_table
   cudaEventCreate(&e->ev1);
   *out = e;
   return 0;
+}
+
+// ---- the engine's own on-disk table format (writer and format description: climt_b200/table_store.py) ----
+namespace {
+struct FileEntry {
+  char name[48];
+  int32_t dtype, ndim;
+  int64_t shape[7], offset, nbytes;
+};
+static_assert(sizeof(FileEntry) == 128, "container entry is 128 bytes");
+
+struct KTableFile {
+  std::vector<char> raw;
+  std::vector<FileEntry> entries;
+  std::vector<std::vector<double>> promoted;  // float32 grids promoted to double (exact)
+  const FileEntry* find(const char* name) const {
+    for (const auto& e : entries)
+      if (std::strncmp(e.name, name, sizeof(e.name)) == 0) return &e;
+    return nullptr;
+  }
+  size_t count(const FileEntry* e) const {
+    size_t n = 1;
+    for (int i = 0; i < e->ndim; ++i) n *= (size_t)e->shape[i];
+    return n;
+  }
+  const double* f64(const char* name) {
+    const FileEntry* e = find(name);
+    if (!e || e->dtype > 1) return nullptr;
+    if (e->dtype == 0) return reinterpret_cast<const double*>(raw.data() + e->offset);
+    const float* f = reinterpret_cast<const float*>(raw.data() + e->offset);
+    promoted.emplace_back(f, f + count(e));
+    return promoted.back().data();
+  }
+  int i32(const char* name, int dflt) const {
+    const FileEntry* e = find(name);
+    return (e && e->dtype == 2 && e->nbytes >= 4) ? *reinterpret_cast<const int32_t*>(raw.data() + e->offset) : dflt;
+  }
+};
+
+std::string read_ktable_file(const char* path, KTableFile& f) {
+  FILE* fp = std::fopen(path, "rb");
+  if (!fp) return std::string("cork: cannot open ") + path;
+  std::fseek(fp, 0, SEEK_END);
+  const long size = std::ftell(fp);
+  std::fseek(fp, 0, SEEK_SET);
+  f.raw.resize(size > 0 ? (size_t)size : 0);
+  const size_t got = f.raw.empty() ? 0 : std::fread(f.raw.data(), 1, f.raw.size(), fp);
+  std::fclose(fp);
+  if (got != f.raw.size() || f.raw.size() < 16 || std::memcmp(f.raw.data(), "CB2KTB01", 8) != 0)
+    return std::string("cork: ") + path + " is not a CB2KTB01 table container";
+  int64_t n = 0;
+  std::memcpy(&n, f.raw.data() + 8, 8);
+  if (n < 0 || 16 + (size_t)n * sizeof(FileEntry) > f.raw.size()) return std::string("cork: truncated header in ") + path;
+  f.entries.resize((size_t)n);
+  std::memcpy(f.entries.data(), f.raw.data() + 16, (size_t)n * sizeof(FileEntry));
+  for (auto& e : f.entries) {
+    e.name[sizeof(e.name) - 1] = 0;
+    static const size_t item[4] = {8, 4, 4, 1};
+    if (e.dtype < 0 || e.dtype > 3 || e.ndim < 0 || e.ndim > 7 || e.offset < 0 || e.nbytes < 0 || (e.offset % 64) != 0 ||
+        (size_t)e.offset + (size_t)e.nbytes > f.raw.size() || f.count(&e) * item[e.dtype] != (size_t)e.nbytes)
+      return std::string("cork: bad entry '") + e.name + "' in " + path;
+  }
+  return "";
+}
+}  // namespace
+
+extern "C" int cb200_cork_create_from_file(cb200_cork_engine** out, const char* path, double g, double cpd, double sigma, int device) {
+  *out = nullptr;
+  KTableFile f;
+  const std::string bad = read_ktable_file(path, f);
+  if (!bad.empty()) { cb::set_global_error(bad); return -1; }
+  if (f.i32("_overlap_additive", 1) == 0) {
+    cb::set_global_error("cork: ESFT-overlap k-tables are not supported by the CUDA engine (additive overlap only)");
+    return -1;
+  }
+  const FileEntry* k = f.find("k_coefficients");
+  if (!k || k->dtype > 1 || k->ndim < 5) { cb::set_global_error("cork: k_coefficients missing or not (gas, band, g, T, P[, X[, C]])"); return -1; }
+  cb200_cork_table t;
+  std::memset(&t, 0, sizeof(t));
+  t.ngas = (int)k->shape[0]; t.nband = (int)k->shape[1]; t.ngpt = (int)k->shape[2]; t.nT = (int)k->shape[3]; t.nP = (int)k->shape[4];
+  t.nX = k->ndim >= 6 ? (int)k->shape[5] : 0;
+  t.nC = k->ndim == 7 ? (int)k->shape[6] : 0;
+  if (k->dtype == 1) t.k_coefficients_f32 = reinterpret_cast<const float*>(f.raw.data() + k->offset);
+  else t.k_coefficients_f64 = reinterpret_cast<const double*>(f.raw.data() + k->offset);
+  t.temperature_grid = f.f64("temperature_grid");
+  t.pressure_grid_log = f.f64("pressure_grid_log");
+  t.h2o_vmr_grid = t.nX ? f.f64("h2o_vmr_grid") : nullptr;
+  t.co2_vmr_grid = t.nC ? f.f64("co2_vmr_grid") : nullptr;
+  t.gpoint_weights = f.f64("gpoint_weights");
+  if (const FileEntry* pf = f.find("planck_fraction")) {
+    if (pf->ndim != 3) { cb::set_global_error("cork: planck_fraction must be (band, g, T)"); return -1; }
+    t.planck_fraction = f.f64("planck_fraction");
+    t.nband_pf = (int)pf->shape[0];
+    t.ngpt_pf = (int)pf->shape[1];
+  }
+  if (const FileEntry* ck = f.find("continuum_kappa"))
+    if (ck->ndim == 4 && t.nX) t.continuum_kappa = f.f64("continuum_kappa");
+  t.solar_source_per_gpoint = f.f64("solar_source_per_gpoint");
+  t.rayleigh_coefficient = f.f64("rayleigh_coefficient");
+  t.co2_logk = f.i32("_co2_logk", 1);
+  t.premixed = f.i32("_premixed", 0);
+  return cb200_cork_create(out, &t, g, cpd, sigma, device);
 }
 
 extern "C" int cb200_cork_create_picket(cb200_cork_engine** out, const cb200_picket_coeffs* c, int longwave, double g, double cpd,

@@ -212,6 +212,11 @@ typedef struct cb200_cork_outputs {
 } cb200_cork_outputs;
 
 /* g [m s-2], cpd [J kg-1 K-1], sigma [W m-2 K-4] as sympl's get_constant gives them (lw/component.py:224-226) */
+/* The same, from the engine's own on-disk container (.cb2k: typed, 64-byte-aligned arrays under the reference's names plus the
+ * table classification resolved at conversion time; format and converter: climt_b200/table_store.py, tools/convert_tables.py).
+ * Replaces load_k_table + the constructor's classification (cork/optics/correlated_k.py:120-218, cork/lw/component.py:46-59) for
+ * a host without numpy / scipy. */
+int cb200_cork_create_from_file(cb200_cork_engine** out, const char* path, double g, double cpd, double sigma, int device);
 int cb200_cork_create(cb200_cork_engine** out, const cb200_cork_table* table, double g, double cpd, double sigma, int device);
 
 /* Picket-fence optics (optics="parmentier", the reference constructors' default) instead of a k-table.  Replaces
