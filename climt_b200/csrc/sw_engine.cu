@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <future>
 #include <string>
 #include <vector>
 
@@ -129,7 +130,9 @@ struct cb200_sw_engine {
   int max_chunk = 8192;
   cb::HostPipe pipe;
   size_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the last host-pointer call
+  bool skip_zero_inputs = true;         // CLIMT_B200_SKIP_ZERO_INPUTS=0 turns the all-zero scan of the host call off
   bool host_pending = false;
+  std::future<int> enqueue;  // the chunk loop of a run_host_async call, running on its own host thread
   int* h_err = nullptr;
   std::string error;
   int launches = 0;
@@ -187,6 +190,7 @@ extern "C" int cb200_sw_create(cb200_sw_engine** out, const char* table_blob, co
     e->UL.n = build_units(e->UL.u, CB_SW_UMAX);
     e->UL_tau.n = build_units(e->UL_tau.u, CB_SW_TAU_UMAX);
     if (const char* mc = std::getenv("CLIMT_B200_MAX_CHUNK")) e->max_chunk = std::max(128, std::atoi(mc));
+    if (const char* z = std::getenv("CLIMT_B200_SKIP_ZERO_INPUTS")) e->skip_zero_inputs = std::atoi(z) != 0;
     cudaMallocHost(&e->h_err, sizeof(int));
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
@@ -202,7 +206,9 @@ extern "C" int cb200_sw_create(cb200_sw_engine** out, const char* table_blob, co
 
 extern "C" void cb200_sw_destroy(cb200_sw_engine* e) {
   if (!e) return;
+  if (e->enqueue.valid()) e->enqueue.wait();  // a host call still being enqueued
   cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
   e->free_work();
   cudaFree(e->d_tables);
   e->pipe.destroy();
@@ -358,13 +364,12 @@ extern "C" int cb200_sw_check(cb200_sw_engine* e) {
 
 // Host-pointer call: column chunks through the three-stream pipeline of cb::HostPipe.  Arrays the option flags make
 // dead are not transferred (cloud inputs when icld = 0; direct cloud optics unless inflag = 0; aerosol arrays by iaer).
-extern "C" int cb200_sw_run_host_async(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
-                                       const cb200_sw_inputs* hin, const cb200_sw_outputs* hout) {
+static int sw_host_enqueue(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
+                           const cb200_sw_inputs* hin, const cb200_sw_outputs* hout) {
   if (ncol <= 0 || nlay <= 0 || nlay > 203) { e->error = "bad ncol/nlay (1 <= nlay <= 203, parrrsw.f90:27)"; return -3; }
   CUDA_OK(cudaSetDevice(e->device));
   cb::HostPipe& P = e->pipe;
   CUDA_OK(P.init());
-  if (e->host_pending) { e->error = "a previous run_host_async call has not been waited for"; return -3; }
   const int L = nlay;
   const int irows[29] = {L, L + 1, L, L + 1, 1, L, L, L, L, L, L, 1, 1, 1, 1, 1, L, L, L, L, L,
                          L, L, L, L, 14 * L, 14 * L, 14 * L, 6 * L};
@@ -381,10 +386,14 @@ extern "C" int cb200_sw_run_host_async(cb200_sw_engine* e, int ncol, int nlay, d
   if (e->fl.inflag != 0) for (int i = 17; i <= 20; ++i) used[i] = false;
   if (e->fl.iaer != 10) for (int i = 25; i <= 27; ++i) used[i] = false;
   if (e->fl.iaer != 6) used[28] = false;
+  // a cloud fraction that is zero in a chunk's columns is set in HBM by a memset instead of crossing PCIe, and so are the cloud
+  // arrays that are dead without cloud (same scheme as the longwave call, lw_engine.cu)
+  bool zero[29];
+  for (int i = 0; i < 29; ++i) zero[i] = false;
   size_t irow_tot = 0, orow_tot = 0;
   for (int i = 0; i < 29; ++i) if (used[i]) irow_tot += (size_t)irows[i] * inner[i];
   for (int i = 0; i < 6; ++i) orow_tot += (size_t)orows[i];
-  e->h2d_bytes = irow_tot * (size_t)ncol * sizeof(double);
+  e->h2d_bytes = 0;
   e->d2h_bytes = orow_tot * (size_t)ncol * sizeof(double);
   int chunk = ncol < P.chunk ? ncol : P.chunk;
   const int wchunk = (chunk + kBlock - 1) / kBlock * kBlock;
@@ -409,34 +418,63 @@ extern "C" int cb200_sw_run_host_async(cb200_sw_engine* e, int ncol, int nlay, d
   for (int c0 = 0; c0 < ncol; c0 += chunk, ++k) {
     const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
     const int s = k & 1;
+    if (e->skip_zero_inputs && clouds) {
+      const cb::ZeroView zv{reinterpret_cast<const double* const*>(hin)[16], (size_t)L, (size_t)ncol, (size_t)c0, (size_t)n};
+      bool zz;
+      cb::all_zero_parallel(&zv, 1, &zz);
+      for (int i = 16; i <= 24; ++i) zero[i] = zz;
+    }
     CUDA_OK(cudaStreamWaitEvent(P.s_in, P.cmp_done[s], 0));
+    P.mark(P.s_in, k, 0);
     cb200_sw_inputs din;
     const double** dp = reinterpret_cast<const double**>(&din);
     size_t off = 0;
     for (int i = 0; i < 29; ++i) {
       if (!used[i]) { dp[i] = nullptr; continue; }
-      CUDA_OK(P.gather(P.d_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
+      if (zero[i]) {
+        CUDA_OK(cudaMemsetAsync(P.d_in[s] + off, 0, (size_t)irows[i] * inner[i] * n * sizeof(double), P.s_in));
+      } else {
+        CUDA_OK(P.gather(P.d_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
+        e->h2d_bytes += (size_t)irows[i] * inner[i] * n * sizeof(double);
+      }
       dp[i] = P.d_in[s] + off;
       off += (size_t)irows[i] * inner[i] * n;
     }
     CUDA_OK(cudaEventRecord(P.in_done[s], P.s_in));
+    P.mark(P.s_in, k, 1);
     cb200_sw_outputs dout;
     double** dop = reinterpret_cast<double**>(&dout);
     off = 0;
     for (int i = 0; i < 6; ++i) { dop[i] = P.d_out[s] + off; off += (size_t)orows[i] * n; }
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.in_done[s], 0));
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.out_done[s], 0));
+    P.mark(P.s_cmp, k, 2);
     const In in = make_in(n, nlay, &din);
     Out out{dout.uflx, dout.dflx, dout.hr, dout.uflxc, dout.dflxc, dout.hrc};
     if (mc && e->irng == 1) W.moff = c0;
     if (launch_chunk(e, sol, in, out, W, 0, n, n, mc, P.s_cmp)) return -1;
     CUDA_OK(cudaEventRecord(P.cmp_done[s], P.s_cmp));
+    P.mark(P.s_cmp, k, 3);
     CUDA_OK(cudaStreamWaitEvent(P.s_out, P.cmp_done[s], 0));
     for (int i = 0; i < 6; ++i) CUDA_OK(P.scatter(hop[i], dop[i], orows[i], ncol, c0, n));
     CUDA_OK(cudaEventRecord(P.out_done[s], P.s_out));
+    P.mark(P.s_out, k, 4);
   }
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// The asynchronous form returns at once: the chunk loop runs on a host thread of its own (see cb200_lw_run_host_async).
+extern "C" int cb200_sw_run_host_async(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
+                                       const cb200_sw_inputs* hin, const cb200_sw_outputs* hout) {
+  if (e->host_pending) { e->error = "a previous run_host_async call has not been waited for"; return -3; }
+  if (ncol <= 0 || nlay <= 0 || nlay > 203) { e->error = "bad ncol/nlay (1 <= nlay <= 203, parrrsw.f90:27)"; return -3; }
+  const cb200_sw_inputs in = *hin;
+  const cb200_sw_outputs out = *hout;
   e->host_pending = true;
+  e->enqueue = std::async(std::launch::async, [e, ncol, nlay, adjes, dyofyr, solcycfrac, in, out] {
+    return sw_host_enqueue(e, ncol, nlay, adjes, dyofyr, solcycfrac, &in, &out);
+  });
   return 0;
 }
 
@@ -444,14 +482,19 @@ extern "C" int cb200_sw_run_host_async(cb200_sw_engine* e, int ncol, int nlay, d
 extern "C" int cb200_sw_wait(cb200_sw_engine* e) {
   if (!e->host_pending) return 0;
   e->host_pending = false;
+  if (e->enqueue.valid())
+    if (int rc = e->enqueue.get()) return rc;
   CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(e->pipe.s_out));
+  e->pipe.trace_dump("SW");
   return cb200_sw_check(e);
 }
 
 extern "C" int cb200_sw_run_host(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
                                  const cb200_sw_inputs* hin, const cb200_sw_outputs* hout) {
-  if (int rc = cb200_sw_run_host_async(e, ncol, nlay, adjes, dyofyr, solcycfrac, hin, hout)) return rc;
+  if (e->host_pending) { e->error = "a previous run_host_async call has not been waited for"; return -3; }
+  if (int rc = sw_host_enqueue(e, ncol, nlay, adjes, dyofyr, solcycfrac, hin, hout)) return rc;
+  e->host_pending = true;
   return cb200_sw_wait(e);
 }
 

@@ -100,6 +100,8 @@ class LWEngine:
         """Complete a run_host(..., wait=False) call: the outputs are filled on return."""
         rc = self._L.cb200_lw_wait(self._h)
         pend, self._pending = getattr(self, "_pending", None), None
+        if rc == -3:
+            raise ValueError(self._err())
         if rc < 0:
             raise RuntimeError(self._err())
         if rc > 0:
@@ -237,6 +239,8 @@ class SWEngine:
         """Complete a run_host(..., wait=False) call: the outputs are filled on return."""
         rc = self._L.cb200_sw_wait(self._h)
         pend, self._pending = getattr(self, "_pending", None), None
+        if rc == -3:
+            raise ValueError(self._err())
         if rc < 0:
             raise RuntimeError(self._err())
         if rc > 0:

@@ -100,7 +100,9 @@ def ktable_to_container_arrays(table):
     for name in K_TABLE_ARRAYS:
         if name in table and table[name] is not None:
             a = np.asarray(table[name])
-            out[name] = a if a.dtype == np.float32 and name == "k_coefficients" else a.astype(np.float64)
+            # dtypes are kept: the reference's arithmetic depends on them (float32 solar_source_per_gpoint * Python float is a
+            # float32 product, cork/sw/component.py:371-372); the library promotes what it needs in fp64 exactly
+            out[name] = a if a.dtype in (np.float32, np.float64) else a.astype(np.float64)
     gas_names, _, _, fully_premixed, premixed_bg = table_flags(table)
     out["gas_names"] = ",".join(gas_names)
     for name in K_TABLE_TEXT:

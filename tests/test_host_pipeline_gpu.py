@@ -94,9 +94,65 @@ def test_async_host_calls_overlap_and_match_sync(monkeypatch):
         np.testing.assert_array_equal(out_sw[k], ref_sw[k], err_msg=k)
     h2d, d2h = lw.last_transfer_bytes
     L, n = nlay, ncol
-    assert h2d == 8 * n * (17 * L + 2 * (L + 1) + 1 + 16 + 16 * L)   # 12 p/T/gas + 5 cloud-physics layer fields, emis, tauaer; no taucld (inflag=2)
+    # 12 p/T/gas + 5 cloud-physics layer fields, emis; no taucld (inflag=2); the all-zero tauaer is set by a memset
+    assert h2d == 8 * n * (17 * L + 2 * (L + 1) + 1 + 16)
     assert d2h == 8 * n * (4 * (L + 1) + 2 * L)
     h2d_sw, _ = sw.last_transfer_bytes
     assert h2d_sw == 8 * n * (13 * L + 2 * (L + 1) + 6)             # no direct cloud optics, no aerosol arrays (iaer=0)
+    lw.close()
+    sw.close()
+
+
+def test_all_zero_inputs_do_not_cross_pcie_and_results_are_unchanged(monkeypatch):
+    """Halocarbons, aerosol optical depth and cloud arrays that are zero everywhere are replaced by a device memset; a single
+    non-zero element anywhere makes the array travel again.  Bit-identical to the device-pointer call either way."""
+    from climt_b200.engine import LWEngine, SWEngine
+    monkeypatch.setenv("CLIMT_B200_HOST_CHUNK", "256")
+    ncol, nlay = 1000, 40
+    L, n = nlay, ncol
+    abi = H.to_abi(SY.make_lw_state(ncol, nlay, seed=5, clouds=False))
+    abis = H.to_abi_sw(SY.make_sw_state(ncol, nlay, seed=5, clouds=False))
+    for k in ("cfc11vmr", "cfc12vmr", "cfc22vmr", "ccl4vmr"):
+        abi[k][:] = 0.0
+    assert not abi["tauaer"].any() and not abi["cldfr"].any()
+    lw, sw = LWEngine(), SWEngine()
+    host = lw.run_host(ncol, nlay, abi)
+    assert lw.last_transfer_bytes[0] == 8 * n * (8 * L + 2 * (L + 1) + 1 + 16)
+    dev = _device_lw(lw, ncol, nlay, abi)
+    hs = sw.run_host(ncol, nlay, abis, dyofyr=100)
+    assert sw.last_transfer_bytes[0] == 8 * n * (8 * L + 2 * (L + 1) + 6)
+    ds = _device_sw(sw, ncol, nlay, abis, dyofyr=100)
+    for k in dev:
+        np.testing.assert_array_equal(host[k], dev[k], err_msg=k)
+        np.testing.assert_array_equal(hs[k], ds[k], err_msg=k)
+    # the scan switched off: every live array travels, same bits
+    monkeypatch.setenv("CLIMT_B200_SKIP_ZERO_INPUTS", "0")
+    lw0 = LWEngine()
+    host0 = lw0.run_host(ncol, nlay, abi)
+    assert lw0.last_transfer_bytes[0] == 8 * n * (17 * L + 2 * (L + 1) + 1 + 16 + 16 * L)
+    for k in dev:
+        np.testing.assert_array_equal(host0[k], dev[k], err_msg=k)
+    lw0.close()
+    monkeypatch.delenv("CLIMT_B200_SKIP_ZERO_INPUTS")
+    # one aerosol element and one CFC-12 element in the last chunk's last column
+    abi2 = {k: v.copy() for k, v in abi.items()}
+    abi2["tauaer"].reshape(-1)[-1] = 0.35
+    abi2["tauaer"][:, 3, -1] = 0.2
+    abi2["cfc12vmr"][2, -1] = 5e-10
+    host2 = lw.run_host(ncol, nlay, abi2)
+    base, last = 8 * n * (8 * L + 2 * (L + 1) + 1 + 16), n - 3 * 256   # the scan works chunk by chunk: only the last chunk's share travels
+    assert lw.last_transfer_bytes[0] == base + 8 * last * (L + 16 * L)
+    dev2 = _device_lw(lw, ncol, nlay, abi2)
+    for k in dev2:
+        np.testing.assert_array_equal(host2[k], dev2[k], err_msg=k)
+    assert np.abs(host2["dflx"][:, -1] - host["dflx"][:, -1]).max() > 1e-6
+    np.testing.assert_array_equal(host2["dflx"][:, :-1], host["dflx"][:, :-1])
+    # -0.0 is not "zero": the array is transferred (and gives the same fluxes)
+    abi3 = {k: v.copy() for k, v in abi.items()}
+    abi3["cfc22vmr"][0, 0] = -0.0
+    host3 = lw.run_host(ncol, nlay, abi3)
+    assert lw.last_transfer_bytes[0] == base + 8 * 256 * L
+    for k in dev:
+        np.testing.assert_array_equal(host3[k], dev[k], err_msg=k)
     lw.close()
     sw.close()

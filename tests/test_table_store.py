@@ -42,7 +42,9 @@ def test_converted_table_equals_the_reference_format_table(tmp_path, name):
     for k in TS.K_TABLE_ARRAYS:
         assert (k in src and src[k] is not None) == (k in back), k
         if k in back:
-            np.testing.assert_array_equal(np.asarray(back[k], dtype=np.float64), np.asarray(src[k], dtype=np.float64))
+            np.testing.assert_array_equal(back[k], src[k])
+            if np.asarray(src[k]).dtype.kind == "f":
+                assert np.asarray(back[k]).dtype == np.asarray(src[k]).dtype, k   # the reference's float32 products depend on it
     assert cork.table_flags(back) == cork.table_flags(src)
     raw = TS.read_container(dst)
     _, _, _, fully, bg = cork.table_flags(src)
