@@ -192,7 +192,19 @@ struct HostPipe {
     std::fprintf(stderr, "PIPE %s returned to caller at host %.3f ms\n", tag, now_ms() - epoch_host());
     marks.clear();
   }
-  int chunk = 2048;  // columns per pipeline chunk (r01 B200 sweep: 1024-2048 best for LW+SW overlapped, 4096 for a lone engine)
+  int chunk = 4096;  // columns per full pipeline chunk (r01 B200, 8192 x 60, LW + SW overlapped: 2048 -> 6.33, 4096 -> 6.02, 8192 -> 5.99 ms with the ramp)
+
+  // Columns of chunk k: the first two chunks are a quarter and a half of `chunk`, so that the kernels start after a short first
+  // copy instead of idling through a full-sized one (r01 trace: 0.63 ms of 5.7 with uniform 4096-column chunks).
+  bool ramp = true;
+  int chunk_size(int k, int remaining) const {
+    int n = chunk;
+    if (ramp && k == 0) n = chunk / 4;
+    else if (ramp && k == 1) n = chunk / 2;
+    n = n / 128 * 128;
+    if (n < 128) n = 128;
+    return n < remaining ? n : remaining;
+  }
 
   cudaError_t init() {
     if (s_in) return cudaSuccess;
@@ -207,6 +219,7 @@ struct HostPipe {
     }
     if (const char* hc = std::getenv("CLIMT_B200_HOST_CHUNK")) chunk = std::max(128, std::atoi(hc));
     if (const char* tr = std::getenv("CLIMT_B200_PIPE_TRACE")) trace = std::atoi(tr) != 0;
+    if (const char* rp = std::getenv("CLIMT_B200_HOST_RAMP")) ramp = std::atoi(rp) != 0;
     return cudaSuccess;
   }
   cudaError_t ensure(size_t in_doubles, size_t out_doubles) {

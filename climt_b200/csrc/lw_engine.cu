@@ -416,8 +416,8 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
     W.mstride = ncol;
   }
   int k = 0;
-  for (int c0 = 0; c0 < ncol; c0 += chunk, ++k) {
-    const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
+  for (int c0 = 0, n = 0; c0 < ncol; c0 += n, ++k) {
+    n = P.chunk_size(k, ncol - c0);
     const int s = k & 1;
     if (e->skip_zero_inputs) {
       const int cand[6] = {11, 12, 13, 14, 22, 16};

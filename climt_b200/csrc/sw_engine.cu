@@ -415,8 +415,8 @@ static int sw_host_enqueue(cb200_sw_engine* e, int ncol, int nlay, double adjes,
     W.mstride = ncol;
   }
   int k = 0;
-  for (int c0 = 0; c0 < ncol; c0 += chunk, ++k) {
-    const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
+  for (int c0 = 0, n = 0; c0 < ncol; c0 += n, ++k) {
+    n = P.chunk_size(k, ncol - c0);
     const int s = k & 1;
     if (e->skip_zero_inputs && clouds) {
       const cb::ZeroView zv{reinterpret_cast<const double* const*>(hin)[16], (size_t)L, (size_t)ncol, (size_t)c0, (size_t)n};
