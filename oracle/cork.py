@@ -17,6 +17,7 @@ _fp = ctypes.POINTER(ctypes.c_float)
 
 MOLAR_MASS_DRY_AIR = 28.970   # cork/common.py:9-17
 MOLAR_MASS_H2O = 18.015
+MOLAR_MASS = {"h2o": 18.015, "co2": 44.010, "o3": 47.998, "ch4": 16.043, "n2o": 44.013, "o2": 31.998}
 
 
 def build(force=False):
@@ -135,15 +136,39 @@ def _band_diag(tau, weights, up_band, down_band, p_int, g, cpd):
     return tau_band, hr_band
 
 
+def gas_setup(table, s, p_int, g, with_co2):
+    """Table classification (cork/lw/component.py:46-59) and the gas part of array_call (:243-287; cork/sw/component.py:308-347):
+    -> gas_amounts (ngas, nlev, ncol), h2o_vmr or None, co2_vmr or None.  s["q"] (or s["h2o"]) is the specific humidity, every other
+    gas s[<name>] a mole fraction."""
+    names = [str(x) for x in table["gas_names"]] if "gas_names" in table else ["effective"]
+    has_h2o, has_co2 = "h2o_vmr_grid" in table, "co2_vmr_grid" in table
+    fully = names == ["effective"] and not has_h2o
+    bg = (names == ["effective"] and has_h2o) or str(np.asarray(table.get("background_is_premixed", ""))).lower() == "true"
+    nlev, ncol = p_int.shape[0] - 1, p_int.shape[1]
+    gas_amounts = np.zeros((len(names), nlev, ncol))
+    h2o_vmr = co2_vmr = None
+    q = s["q"] if "q" in s else s.get("h2o")
+    if fully:
+        gas_amounts[0] = column_amount(np.ones((nlev, ncol)), p_int, g)
+    elif bg:
+        gas_amounts[0] = column_amount(np.ones((nlev, ncol)), p_int, g)
+        M = MOLAR_MASS_H2O / MOLAR_MASS_DRY_AIR
+        h2o_vmr = q / np.maximum(q + (1.0 - q) * M, 1e-30)
+        if has_co2 and with_co2:
+            co2_vmr = s["co2"]
+    else:
+        for ig, gas in enumerate(names):
+            qg = q if gas == "h2o" else s[gas] * (MOLAR_MASS.get(gas, MOLAR_MASS_DRY_AIR) / MOLAR_MASS_DRY_AIR)
+            gas_amounts[ig] = column_amount(np.ascontiguousarray(qg), p_int, g)
+    return gas_amounts, h2o_vmr, co2_vmr
+
+
 def lw_call(table, s, g, cpd, sigma, D=1.66):
     """s: T, p, p_int [Pa], T_surf, q (specific humidity), co2 (VMR), emissivity (nband, ncol), tau_cloud_lw (nlev, ncol, nband)."""
     T, p, p_int = s["T"], s["p"], s["p_int"]
     nlev, ncol = T.shape
-    gas_amounts = np.zeros((1, nlev, ncol))
-    gas_amounts[0] = column_amount(np.ones((nlev, ncol)), p_int, g)
-    M = MOLAR_MASS_H2O / MOLAR_MASS_DRY_AIR
-    h2o_vmr = s["q"] / np.maximum(s["q"] + (1.0 - s["q"]) * M, 1e-30)
-    tau_gas = optical_depth(table, T, p, gas_amounts, h2o_vmr=h2o_vmr, co2_vmr=s["co2"])
+    gas_amounts, h2o_vmr, co2_vmr = gas_setup(table, s, p_int, g, with_co2=True)
+    tau_gas = optical_depth(table, T, p, gas_amounts, h2o_vmr=h2o_vmr, co2_vmr=co2_vmr)
     weights = np.asarray(table["gpoint_weights"], dtype=np.float64)
     nband, ngpt = tau_gas.shape[:2]
     planck_src, surf_src = planck_sources(table, T, s["T_surf"], sigma, nband, ngpt)
@@ -159,10 +184,7 @@ def sw_call(table, s, g, cpd):
     """s: T, p, p_int, q, zenith [rad], albedo, earth_sun_factor, tau_cloud_sw / ssa_cloud / g_cloud (nlev, ncol, nband)."""
     T, p, p_int = s["T"], s["p"], s["p_int"]
     nlev, ncol = T.shape
-    gas_amounts = np.zeros((1, nlev, ncol))
-    gas_amounts[0] = column_amount(np.ones((nlev, ncol)), p_int, g)
-    M = MOLAR_MASS_H2O / MOLAR_MASS_DRY_AIR
-    h2o_vmr = s["q"] / np.maximum(s["q"] + (1.0 - s["q"]) * M, 1e-30)
+    gas_amounts, h2o_vmr, _ = gas_setup(table, s, p_int, g, with_co2=False)
     tau_abs = optical_depth(table, T, p, gas_amounts, h2o_vmr=h2o_vmr)
     weights = np.asarray(table["gpoint_weights"], dtype=np.float64)
     nband, ngpt = tau_abs.shape[:2]
