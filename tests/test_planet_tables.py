@@ -3,7 +3,9 @@ TRAPPIST-1e hab2 (fully premixed, 5-D), TRAPPIST-1e hab1 (premixed with an H2O a
 through `optics="correlated_k"`: golden vectors produced by the reference's own component classes on the reference's own NetCDF
 tables (tests/golden/make_planet_golden.py), which this package ships unchanged.
 CPU: the oracle (table classification + glue of oracle/cork.py, kernels of cork_oracle.cpp) against the goldens.
-GPU: the drop-in components against the goldens.  Tolerance 1e-6 relative (BASELINE.json); asserted at 1e-9 / observed ~1e-13."""
+GPU: the drop-in components against the goldens.  Tolerance 1e-6 relative (BASELINE.json); asserted at 1e-9 of the flux scale
+(observed ~1e-11); heating rates are compared as the flux divergence they come from (tendency x dp x cp / g), because a thin
+top layer turns a 1e-11 flux difference into a much larger relative one."""
 import numpy as np
 import pytest
 
@@ -92,8 +94,16 @@ def test_drop_in_components_match_the_reference_components(gold, case):
         assert set(names) == set(diag) | {"T"}
         flux = gold[f"{case}/{which}/{'upwelling_longwave_flux_in_air' if which == 'lw' else 'downwelling_shortwave_flux_in_air'}"]
         fscale = float(np.abs(flux).max())
+        dp_w = np.abs(np.diff(s["p_int"], axis=0)) * H.CORK_CPD / H.CORK_G      # heating rate [K/s] x dp_w = flux divergence [W m-2]
         for name in names:
             ref = gold[f"{case}/{which}/{name}"]
-            got = tend["T"] if name == "T" else diag[name]
-            scale = fscale if "flux" in name else (float(np.abs(ref).max()) if (name == "T" or "tendency" in name) else 0.0)
-            _close(np.asarray(got), ref, f"{case} {which} {name}", scale)
+            got = np.asarray(tend["T"] if name == "T" else diag[name])
+            assert got.shape == ref.shape, (name, got.shape, ref.shape)
+            if name == "T" or "tendency" in name:
+                w = dp_w if ref.ndim == 2 else dp_w[..., None]
+                w = w / 86400.0 if "tendency" in name else w                    # the *_tendency_from_* diagnostics are per day
+                assert float(np.abs((got - ref) * w).max()) <= RTOL * fscale, (case, which, name)
+            elif "flux" in name:
+                np.testing.assert_allclose(got, ref, rtol=RTOL, atol=RTOL * fscale, err_msg=f"{case} {which} {name}")
+            else:
+                np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-300, err_msg=f"{case} {which} {name}")
