@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("CLIMT_B200_SO") or os.path.join(_HERE, "libclimt_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lw_engine.cu", "sw_engine.cu", "gray_engine.cu", "cork_engine.cu", "marshal.cu", "emanuel_engine.cu", "adjacent_engine.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lw_engine.cu", "sw_engine.cu", "gray_engine.cu", "cork_engine.cu", "marshal.cu", "emanuel_engine.cu", "adjacent_engine.cu", "simple_physics.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("cb_common.h", "engine_common.h", "lw_core.cuh", "lw_tables.h", "sw_core.cuh", "sw_tables.h",
                                                           "mcica_core.cuh", "mcica_host.h", "cork_core.cuh", "cork_tables.h", "emanuel_core.cuh")] + [
     os.path.join(_HERE, "..", "include", "climt_b200.h")]
@@ -73,7 +73,8 @@ class SwInputs(ctypes.Structure):
         "cicewp", "cliqwp", "reice", "reliq", "tauaer", "ssaaer", "asmaer", "ecaer")]
 
 
-EXPORTS = ["cb200_cork_create_from_file", "cb200_instellation_orbit", "cb200_instellation_run_device", "cb200_instellation_run_host", "cb200_slab_surface_run_device",
+EXPORTS = ["cb200_simple_physics_run_device", "cb200_simple_physics_run_host", "set_fortran_constants", "simple_physics",
+           "cb200_cork_create_from_file", "cb200_instellation_orbit", "cb200_instellation_run_device", "cb200_instellation_run_host", "cb200_slab_surface_run_device",
            "cb200_slab_surface_run_host", "cb200_emanuel_create", "cb200_emanuel_destroy", "cb200_emanuel_last_error", "cb200_emanuel_last_launches", "cb200_emanuel_enable_timing",
            "cb200_emanuel_last_kernel_ms", "cb200_emanuel_run_device", "cb200_emanuel_run_host", "init_emanuel_convection_fortran", "emanuel_convection",
            "cb200_cork_create_picket", "cb200_marshal_device", "cb200_lw_last_taumol_kernel_ms", "cb200_sw_last_taumol_kernel_ms", "cb200_lw_run_host_async", "cb200_lw_wait", "cb200_lw_last_transfer_bytes", "cb200_sw_run_host_async", "cb200_sw_wait",

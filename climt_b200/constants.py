@@ -31,6 +31,12 @@ DEFAULTS = {
     "latent_heat_of_condensation": (2.5e6, "J kg^-1"),
     "density_of_liquid_phase": (1e3, "kg m^-3"),
     "specific_enthalpy_of_vapor_phase": (2500.0, "J kg^-1"),
+    # read by SimplePhysics (climt/_components/simple_physics/component.py:196-207).  Radius and rotation rate enter only its
+    # internal-SST branch (simulate_cyclone=True without an external surface temperature); values as in
+    # climt/_data/atmospheric_properties/earth.toml:5-6.  No golden of the reference pins these three.
+    "planetary_radius": (6.371e6, "m"),
+    "planetary_rotation_rate": (7.292e-5, "s^-1"),
+    "density_of_liquid_water": (1e3, "kg m^-3"),
 }
 
 _registry = {k: v[0] for k, v in DEFAULTS.items()}

@@ -8,7 +8,7 @@ table, re-wrapping of outputs) for the drop-in components to be exercised throug
 import numpy as np
 
 try:  # pragma: no cover - not available in the build image
-    from sympl import TendencyComponent, ImplicitTendencyComponent, DiagnosticComponent, DataArray, initialize_numpy_arrays_with_properties  # noqa: F401
+    from sympl import TendencyComponent, ImplicitTendencyComponent, DiagnosticComponent, Stepper, DataArray, initialize_numpy_arrays_with_properties  # noqa: F401
     HAVE_SYMPL = True
 except Exception:  # ImportError or a broken install
     HAVE_SYMPL = False
@@ -82,6 +82,7 @@ except Exception:  # ImportError or a broken install
         tendency_properties = {}
         diagnostic_properties = {}
         _diagnostic_only = False
+        _stepper = False
 
         def __init__(self, **kwargs):
             if kwargs:
@@ -98,7 +99,12 @@ except Exception:  # ImportError or a broken install
             if "time" in state:
                 raw["time"] = state["time"]
             result = self.array_call(raw, *extra)
-            tend, diag = ({}, result) if self._diagnostic_only else result
+            if self._diagnostic_only:
+                tend, diag = {}, result
+            elif self._stepper:
+                diag, tend = result
+            else:
+                tend, diag = result
 
             def wrap(arr, prop, name=None):
                 dims, shape, k = [], [], 0
@@ -121,6 +127,21 @@ except Exception:  # ImportError or a broken install
     class DiagnosticComponent(TendencyComponent):
         """sympl.DiagnosticComponent: `component(state)` -> diagnostics dict; array_call returns the diagnostics only."""
         _diagnostic_only = True
+
+    class Stepper(TendencyComponent):
+        """sympl.Stepper: `component(state, timestep)` -> (diagnostics, new_state); array_call returns them in that order and
+        `output_properties` quantities take the dims of the input of the same name."""
+        output_properties = {}
+        _stepper = True
+
+        def __call__(self, state, timestep):
+            saved = self.tendency_properties
+            self.tendency_properties = self.output_properties
+            try:
+                new_state, diag = TendencyComponent.__call__(self, state, timestep)
+            finally:
+                self.tendency_properties = saved
+            return diag, new_state
 
     class ImplicitTendencyComponent(TendencyComponent):
         """sympl.ImplicitTendencyComponent: `component(state, timestep)` -> array_call(raw_state, timestep)."""

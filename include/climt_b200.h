@@ -350,6 +350,40 @@ int cb200_slab_surface_run_device(int device, int ncol, long flux_stride, const 
                                   double* depth, void* stream);
 int cb200_slab_surface_run_host(int device, int ncol, long flux_stride, const cb200_slab_inputs* in, double* tend_ts, double* depth);
 
+/* SimplePhysics: replaces the Reed-Jablonowski package (climt/_lib/simple_physics/simple_physics_custom.f90:28-565) and the level
+ * flip / layer thickness of its Cython shim (climt/_components/simple_physics/_simple_physics.pyx:84-180).  A sympl Stepper: the new
+ * T, q, u, v after large-scale condensation, bulk surface fluxes and implicit boundary-layer diffusion over dtime, plus three
+ * diagnostics.  Arrays (nlev[+1], ncol) column-fastest; order 0: level 0 is the surface (the component's arrays as they are),
+ * order 1: level 0 is the model top (the Fortran's own order).  pressures Pa, latitude as the component passes it (degrees).
+ * ts / qsurf / lat may be NULL when the switches make them dead.  workspace: 2 * nlev * ncol doubles (boundary layer only). */
+typedef struct cb200_simple_physics_params {
+  double gravit, cpair, rair, latvap, rh2o, radius, omega, rhow;  /* set_fortran_constants (simple_physics_custom.f90:28-57) */
+  double pbltop, pblconst, C, Cd0, Cd1, Cm;
+  int test;                    /* the component's simulate_cyclone flag (_simple_physics.pyx:168): 1 = baroclinic-wave SST */
+  int do_lsc, do_pbl, do_surf_flux, use_ts_ext, use_qsurf_ext;
+  int clamp_latent_heat_flux;  /* 1: negative latent heat fluxes are reported as 0 (simple_physics/component.py:257) */
+} cb200_simple_physics_params;
+typedef struct cb200_simple_physics_inputs {
+  const double *t, *q, *u, *v, *pmid, *pint, *ps, *ts, *qsurf, *lat;
+} cb200_simple_physics_inputs;
+typedef struct cb200_simple_physics_outputs {
+  double *t, *q, *u, *v, *precl, *sens_ht_flux, *lat_ht_flux;   /* precl [m s-1], fluxes [W m-2]: (ncol) */
+} cb200_simple_physics_outputs;
+int cb200_simple_physics_run_device(int device, int ncol, int nlev, int order, double dtime, const cb200_simple_physics_params* p,
+                                    const cb200_simple_physics_inputs* in, const cb200_simple_physics_outputs* out,
+                                    double* workspace, void* stream);
+int cb200_simple_physics_run_host(int device, int ncol, int nlev, int order, double dtime, const cb200_simple_physics_params* p,
+                                  const cb200_simple_physics_inputs* in, const cb200_simple_physics_outputs* out);
+/* The reference's own symbols (declared in _simple_physics.pyx:6-27): process-global constants, host pointers, arrays
+ * (pver, pcols) with the model top first, t / q / u / v updated in place. */
+void set_fortran_constants(double* g, double* cpd, double* r_air, double* latent_heat, double* r_cond, double* radius,
+                           double* rotation, double* density_cond, double* top_pbl, double* pbl_decay, double* drag_coeff_sens_lat,
+                           double* Cd0_ext, double* Cd1_ext, double* Cm_ext);
+void simple_physics(int* pcols, int* pver, double* dtime, double* lat, double* t, double* q, double* u, double* v, double* pmid,
+                    double* pint, double* pdel, double* rpdel, double* ps, double* precl, int* test, int* do_lsc, int* do_pbl,
+                    int* do_surf_flux, int* use_ts_ext, double* ts, int* use_qsurf_ext, double* qsurf, double* sens_ht_flux,
+                    double* lat_ht_flux);
+
 #ifdef __cplusplus
 }
 #endif

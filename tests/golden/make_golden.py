@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Convert the reference's golden NetCDF-3 caches for the radiation hot path into one .npz.
 
-Source: /root/reference/tests/cached_component_output/Test{RRTMG*,GrayLongwaveRadiation}-{column,3d}-{0,1}.cache
+Source: /root/reference/tests/cached_component_output/Test{RRTMG*,GrayLongwaveRadiation,SimplePhysics}-{column,3d}-{0,1}.cache
 (written by the reference's own test harness, tests/test_components.py:63-75,186-193;
 `-0` = tendencies, `-1` = diagnostics).  The `*_stepping` caches need sympl's
 AdamsBashforth stepper and are not used.  Run here (the GPU box has no /root/reference):
@@ -19,7 +19,9 @@ from scipy.io import netcdf_file
 SRC = "/root/reference/tests/cached_component_output"
 CLASSES = ["TestRRTMGLongwave", "TestRRTMGLongwaveMCICA", "TestRRTMGLongwaveWithClouds",
            "TestRRTMGLongwaveWithExternalInterfaceTemperature", "TestRRTMGShortwave",
-           "TestRRTMGShortwaveMCICA", "TestGrayLongwaveRadiation"]
+           "TestRRTMGShortwaveMCICA", "TestGrayLongwaveRadiation",
+           # a Stepper: part 0 = its diagnostics (stored under "tend"), part 1 = the new state (stored under "diag")
+           "TestSimplePhysics"]
 
 
 def main():
