@@ -3,7 +3,7 @@
 
   python bench_extra.py --workload mcica   # configs[2] per-GPU share: RRTMG LW+SW with McICA clouds (KISS RNG), 16384 col x 72 lev
   python bench_extra.py --workload cork    # configs[3] per-GPU share: CORK correlated-k LW+SW, 65536 col x 60 lev
-  python bench_extra.py --workload gmd     # configs[4] per-GPU share: RRTMG LW+SW + Emanuel convection, 8100 col x 60 lev
+  python bench_extra.py --workload gmd     # configs[4] per-GPU share: the GMD radiative-convective physics step (Instellation, RRTMG LW+SW, Emanuel, SimplePhysics, SlabSurface), 8100 col x 60 lev
   python -m torch.distributed.run --nproc-per-node N ... bench_extra.py --workload cork --gpus N   # weak scaling, columns sharded
 
 Same measurement rules as bench.py: W >= 3 warm-up steps, CUDA events around K steps, max over ranks, inputs resident in HBM
@@ -98,7 +98,7 @@ def main():
         # the slab reads row 0 of the flux outputs in place.
         from climt_b200.engine import LWEngine, SWEngine, LW_IN, LW_OUT, SW_IN, lw_shapes
         import datetime
-        from climt_b200 import emanuel, instellation as INST, slab_surface as SLAB
+        from climt_b200 import emanuel, instellation as INST, simple_physics as SP, slab_surface as SLAB
         ncol, nlay, dt_conv = args.ncol or 8100, 60, 1200.0
         when = datetime.datetime(2026, 3, 20, 12, 0)
         jc = INST.julian_centuries(when)
@@ -143,12 +143,20 @@ def main():
                       "upwelling_shortwave_flux_in_air": (1, "uflx"), "upwelling_longwave_flux_in_air": (0, "uflx")}
         d_slab = dict(d_sfc, **{k: (ds_out if w else d_out)[f] for k, (w, f) in flux_names.items()})
         slab_result = {}
+        # SimplePhysics (condensation, surface fluxes, boundary layer) on the same columns: pressures in Pa, surface first
+        sp_par = SP.SimplePhysics(device=local).params()
+        hsp_in = {"t": h_in["tlay"], "q": pin(np.ascontiguousarray(es["specific_humidity"].T)), "u": pin(np.ascontiguousarray(es["eastward_wind"].T)),
+                  "v": pin(np.ascontiguousarray(es["northward_wind"].T)), "pmid": pin(st["play"] * 100.0), "pint": pin(st["plev"] * 100.0),
+                  "ps": pin(st["plev"][0] * 100.0), "ts": pin(st["tsfc"].copy()), "qsurf": pin(np.zeros(ncol)), "lat": h_sfc["latitude"]}
+        dsp_in = {k: (d_in["tlay"] if k == "t" else (de_in[k] if k in ("q", "u", "v") else torch.from_numpy(v).cuda())) for k, v in hsp_in.items()}
 
         def step_device():
             _, ds_in["coszen"] = INST.instellation_device(d_sfc["latitude"], d_sfc["longitude"], jc, want_coszen=True)
             lw.run_device(ncol, nlay, d_in, d_out)
             sw.run_device(ncol, nlay, ds_in, ds_out, dyofyr=1)
             em.run_device(ncol, nlay, de_in, de_out, dt_conv, qs_mode=emanuel.QS_BOLTON, layout=0)
+            o = SP.simple_physics_device(sp_par, dsp_in, dt_conv)
+            d_slab["surface_upward_latent_heat_flux"], d_slab["surface_upward_sensible_heat_flux"] = o["lat_ht_flux"], o["sens_ht_flux"]
             slab_result["device"] = SLAB.slab_surface_device(d_slab, flux_layout="level_major")
 
         def step_host():
@@ -156,20 +164,25 @@ def main():
             lw.run_host(ncol, nlay, h_in, h_out, wait=False)
             sw.run_host(ncol, nlay, hs_in, hs_out, dyofyr=1, wait=False)
             em.run_host(he_in, dt_conv, qs_mode=emanuel.QS_BOLTON, out=he_out)
+            o = SP.simple_physics_host(sp_par, hsp_in, dt_conv, device=local)
             lw.wait()
             sw.wait()
             # the engines' host outputs are (interface_levels, column): row 0 is the surface value of every column
-            slab_result["host"] = SLAB.slab_surface_host(dict(h_sfc, **{k: (hs_out if w else h_out)[f][0] for k, (w, f) in flux_names.items()}), local)
+            slab_result["host"] = SLAB.slab_surface_host(dict(h_sfc, surface_upward_latent_heat_flux=o["lat_ht_flux"], surface_upward_sensible_heat_flux=o["sens_ht_flux"],
+                                                              **{k: (hs_out if w else h_out)[f][0] for k, (w, f) in flux_names.items()}), local)
         name = "RRTMG LW+SW + Emanuel convection columns/s (60 lev)"
-        workload = (f"radiative-convective physics step: Instellation -> RRTMG LW+SW clear sky -> SlabSurface, + Emanuel convection (dt 1200 s), "
+        workload = (f"radiative-convective physics step (the components of examples/gmd_radiative_convective.py): Instellation -> RRTMG LW+SW clear sky, "
+                    f"Emanuel convection, SimplePhysics -> SlabSurface (dt 1200 s), "
                     f"{ncol} columns x 60 levels per GPU (BASELINE.json configs[4] is 360 x 180 = 64800 columns on 8 GPUs)")
-        launches = lambda: lw.last_launches + sw.last_launches + em.last_launches + 2  # noqa: E731  (+ k_instellation, k_slab_surface)
-        e_h2d = sum(v.nbytes for v in he_in.values()) + 2 * 8 * ncol + (15 * 8 + 4) * ncol
-        e_d2h = sum(v.nbytes for v in he_out.values()) + 8 * ncol + 2 * 8 * ncol
+        launches = lambda: lw.last_launches + sw.last_launches + em.last_launches + 3  # noqa: E731  (+ k_instellation, k_simple_physics, k_slab_surface)
+        e_h2d = sum(v.nbytes for v in he_in.values()) + 2 * 8 * ncol + (15 * 8 + 4) * ncol + sum(v.nbytes for v in hsp_in.values())
+        e_d2h = sum(v.nbytes for v in he_out.values()) + 8 * ncol + 2 * 8 * ncol + (4 * nlay + 3) * 8 * ncol
         xfer = lambda: tuple(a + b + c for a, b, c in zip(lw.last_transfer_bytes, sw.last_transfer_bytes, (e_h2d, e_d2h)))  # noqa: E731
 
         def cpu():
-            from oracle import emanuel as OE, adjacent as OA
+            from oracle import emanuel as OE, adjacent as OA, simple_physics as OSP
+            from climt_b200.constants import DEFAULTS as CDEF
+            csp = {k: v[0] for k, v in CDEF.items()}
             n = 128
             sub = {k: v[:, :n] if v.ndim == 2 else (v[:, :n, :] if v.ndim == 3 and v.shape[-1] in (14, 16) else v[..., :n]) for k, v in st.items()}
             subs = {k: v[:, :n] if v.ndim == 2 else (v[:, :n, :] if v.ndim == 3 and v.shape[-1] in (14, 16) else v[..., :n]) for k, v in sts.items()}
@@ -185,12 +198,17 @@ def main():
                 ol = H.run_lw_oracle(olw, sub)
                 os_ = osw(subs, dyofyr=1)
                 OE.fortran_component_call(sube, dt_conv, consts)
+                OSP.component_call({"air_temperature": sub["tlay"], "specific_humidity": hsp_in["q"][:, :n], "eastward_wind": hsp_in["u"][:, :n],
+                                    "northward_wind": hsp_in["v"][:, :n], "air_pressure": hsp_in["pmid"][:, :n],
+                                    "air_pressure_on_interface_levels": hsp_in["pint"][:, :n], "surface_air_pressure": hsp_in["ps"][:n],
+                                    "surface_temperature": hsp_in["ts"][:n], "surface_specific_humidity": hsp_in["qsurf"][:n],
+                                    "latitude": sfc["latitude"][:n]}, dt_conv, csp)
                 OA.slab_surface(dict({k: v[:n] for k, v in sfc.items()}, downwelling_shortwave_flux_in_air=os_["swdflx"][0],
                                      downwelling_longwave_flux_in_air=ol["dflx"][0], upwelling_shortwave_flux_in_air=os_["swuflx"][0],
                                      upwelling_longwave_flux_in_air=ol["uflx"][0]))
                 reps += 1
             dt = time.perf_counter() - t0
-            return reps * n / dt, f"{n} of the workload's {ncol} columns x {reps} repetitions in {dt:.1f} s (C++ restatements of RRTMG and CONVECT, 1 core)"
+            return reps * n / dt, f"{n} of the workload's {ncol} columns x {reps} repetitions in {dt:.1f} s (C++ restatements of RRTMG and CONVECT, numpy restatements of the small steps, 1 core)"
     else:
         from climt_b200 import cork
         ncol, nlay = args.ncol or 65536, 60
