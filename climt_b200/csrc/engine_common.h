@@ -57,6 +57,8 @@ class WorkerPool {
   WorkerPool() {
     unsigned hw = std::thread::hardware_concurrency();
     int n = (int)(hw ? hw : 4u) / 2;
+    // one process per GPU under torchrun: share the host cores between the ranks of the box
+    if (const char* lws = std::getenv("LOCAL_WORLD_SIZE")) { const int r = std::atoi(lws); if (r > 1) n /= r; }
     if (const char* e = std::getenv("CLIMT_B200_HOST_THREADS")) n = std::atoi(e);
     n = n < 1 ? 1 : (n > 8 ? 8 : n);
     for (int t = 1; t < n; ++t) threads_.emplace_back([this] { loop(); });

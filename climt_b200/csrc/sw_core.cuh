@@ -114,9 +114,10 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
   bool anycld = false;
   if (COLUMN_PART && clouds) {
     // no cloudy layer -> nothing downstream reads the cloud optics (anycld = 0): skip cldprop_sw altogether
-    bool any = false;
-    for (int l = 0; l < nlay; ++l) any = any || in.cldfr[(size_t)l * ncol + gc] > 1.e-12;
-    clouds = any;
+    int any = 0;  // no short circuit: the loads of different layers stay independent of each other
+#pragma unroll 4
+    for (int l = 0; l < nlay; ++l) any |= (int)(in.cldfr[(size_t)l * ncol + gc] > 1.e-12);
+    clouds = any != 0;
   }
   // cldprop_sw work arrays (each is reassigned for all 14 bands in every layer that enters the cloud block)
   double extcoice[14], gice[14], ssacoice[14], forwice[14], extcoliq[14], gliq[14], ssacoliq[14], forwliq[14];
@@ -355,28 +356,31 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
   // Layer whose key-species ratio selects each band's solar source function.  The Fortran updates `laysolfr`
   // while looping over layers and assigns the source when `lay == laysolfr`; the last assignment wins
   // (lower-atmosphere form e.g. taumol18 :586-590, upper form e.g. taumol16 :334-337; band 26 :1455 has no trigger).
+  // One pass over the layers serves all 14 bands (jp of layers lay-1, lay, lay+1 in registers): 60 independent loads instead of the
+  // 14 x 60 dependent ones of a band-by-band search (r01 launch list: this kernel was 92 us of a 2.7 ms step).
   {
     const int layreffr[14] = {18, 30, 6, 3, 3, 8, 2, 6, 1, 2, 0, 32, 58, 49};
     const bool lower_src[14] = {false, false, true, true, true, true, true, true, true, true, true, false, false, false};
-    for (int b = 0; b < 14; ++b) {
-      int ls;
-      if (lower_src[b]) {
-        ls = laytrop;
-        for (int lay = 1; lay <= laytrop; ++lay) {
-          const int jp0 = W.idx[(size_t)(lay - 1) * ncc + c] & 63;
-          const int jp1 = lay < nlay ? (W.idx[(size_t)lay * ncc + c] & 63) : 0;
-          if (b != 10 && jp0 < layreffr[b] && jp1 >= layreffr[b]) ls = imin(lay + 1, laytrop);
-        }
-      } else {
-        ls = nlay;
-        for (int lay = laytrop + 1; lay <= nlay; ++lay) {
-          const int jpm = lay >= 2 ? (W.idx[(size_t)(lay - 2) * ncc + c] & 63) : 0;
-          const int jp0 = W.idx[(size_t)(lay - 1) * ncc + c] & 63;
-          if (jpm < layreffr[b] && jp0 >= layreffr[b]) ls = lay;
+    int ls[14];
+#pragma unroll
+    for (int b = 0; b < 14; ++b) ls[b] = lower_src[b] ? laytrop : nlay;
+    int jpm = 0;                                   // jp(lay - 1); 0 below the first layer
+    int jp0 = W.idx[c] & 63;                       // jp(lay)
+    for (int lay = 1; lay <= nlay; ++lay) {
+      const int jp1 = lay < nlay ? (W.idx[(size_t)lay * ncc + c] & 63) : 0;   // jp(lay + 1); 0 above the last layer
+#pragma unroll
+      for (int b = 0; b < 14; ++b) {
+        if (lower_src[b]) {
+          if (lay <= laytrop && b != 10 && jp0 < layreffr[b] && jp1 >= layreffr[b]) ls[b] = imin(lay + 1, laytrop);
+        } else {
+          if (lay > laytrop && jpm < layreffr[b] && jp0 >= layreffr[b]) ls[b] = lay;
         }
       }
-      W.laysolfr[(size_t)b * ncc + c] = ls;
+      jpm = jp0;
+      jp0 = jp1;
     }
+#pragma unroll
+    for (int b = 0; b < 14; ++b) W.laysolfr[(size_t)b * ncc + c] = ls[b];
   }
 }
 
