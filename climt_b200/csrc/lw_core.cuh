@@ -140,23 +140,33 @@ CB_HD void prep_column(const Tables& T, const In& in, const Flags& fl, const Wor
     // no layer reaches the cloud threshold -> nothing downstream reads the cloud optics: skip cldprop altogether
     int any = 0;  // no short circuit: the loads of different layers stay independent of each other
     const double thr = fl.mcica ? 1.e-20 : 1.e-6;
-#pragma unroll 4
-    for (int l = 0; l < nlay; ++l) any |= (int)(in.cldfr[(size_t)l * ncol + gc] >= thr);
+#pragma unroll 8
+    for (int l = 0; l < nlay; ++l) any |= (int)(CB_LDG(in.cldfr + (size_t)l * ncol + gc) >= thr);
     clouds = any != 0;
   }
   if (COLUMN_PART && !LAYER_PART && !clouds) {
     // Cloud-free column: what is left of the column pass are three sums over the layers.  No store in the loop, so the loads of
     // several layers are in flight together; the additions keep the layer order (bit-identical to the general loop below).
-#pragma unroll 4
-    for (int l = 0; l < nlay; ++l) {
-      const size_t o = (size_t)l * ncol + gc;
-      const double h2o = CB_LDG(in.h2o + o);
-      const double amm = (1. - h2o) * amd + h2o * amw;
-      const double coldry = (CB_LDG(in.plev + o) - CB_LDG(in.plev + o + ncol)) * 1.e3 * T.avogad / (1.e2 * T.grav * amm * (1. + h2o));
-      const double w0 = coldry * h2o;
-      amttl = amttl + coldry + w0;
-      wvttl = wvttl + w0;
-      if (!(log(CB_LDG(in.play + o)) <= 4.56)) laytrop = laytrop + 1;
+    // (the loads of 8 layers are issued together, then consumed: left to itself the compiler keeps one layer's loads per trip)
+    constexpr int NB = 8;
+    for (int l = 0; l < nlay; l += NB) {
+      double h[NB], pa[NB], pb[NB], pm[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const size_t o = (size_t)(l + j < nlay ? l + j : nlay - 1) * ncol + gc;
+        h[j] = CB_LDG(in.h2o + o); pa[j] = CB_LDG(in.plev + o); pb[j] = CB_LDG(in.plev + o + ncol); pm[j] = CB_LDG(in.play + o);
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (l + j >= nlay) break;
+        const double h2o = h[j];
+        const double amm = (1. - h2o) * amd + h2o * amw;
+        const double coldry = (pa[j] - pb[j]) * 1.e3 * T.avogad / (1.e2 * T.grav * amm * (1. + h2o));
+        const double w0 = coldry * h2o;
+        amttl = amttl + coldry + w0;
+        wvttl = wvttl + w0;
+        if (!(log(pm[j]) <= 4.56)) laytrop = laytrop + 1;
+      }
     }
     const double wvsh = (amw * wvttl) / (amd * amttl);
     W.pwvcm[c] = wvsh * (1.e3 * in.plev[gc]) / (1.e2 * T.grav);

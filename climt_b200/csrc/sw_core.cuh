@@ -115,14 +115,27 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
   if (COLUMN_PART && clouds) {
     // no cloudy layer -> nothing downstream reads the cloud optics (anycld = 0): skip cldprop_sw altogether
     int any = 0;  // no short circuit: the loads of different layers stay independent of each other
-#pragma unroll 4
-    for (int l = 0; l < nlay; ++l) any |= (int)(in.cldfr[(size_t)l * ncol + gc] > 1.e-12);
+#pragma unroll 8
+    for (int l = 0; l < nlay; ++l) any |= (int)(CB_LDG(in.cldfr + (size_t)l * ncol + gc) > 1.e-12);
     clouds = any != 0;
   }
   // cldprop_sw work arrays (each is reassigned for all 14 bands in every layer that enters the cloud block)
   double extcoice[14], gice[14], ssacoice[14], forwice[14], extcoliq[14], gliq[14], ssacoliq[14], forwliq[14];
   for (int i = 0; i < 14; ++i) { extcoice[i] = gice[i] = ssacoice[i] = forwice[i] = extcoliq[i] = gliq[i] = ssacoliq[i] = forwliq[i] = 0.; }
 #define WS(f, l) W.ws[((size_t)(f) * nlay + (l)) * ncc + c]
+  if (COLUMN_PART && !LAYER_PART && !clouds) {
+    // cloud-free column: all that is left of the layer loop is the tropopause count; pressures of 8 layers are loaded together
+    constexpr int NB = 8;
+    for (int l = 0; l < nlay; l += NB) {
+      double pm[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) pm[j] = CB_LDG(in.play + (size_t)(l + j < nlay ? l + j : nlay - 1) * ncol + gc);
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (l + j < nlay && !(log(pm[j]) <= 4.56)) laytrop = laytrop + 1;
+    }
+    l0 = l1;  // skip the general loop
+  }
   for (int l = l0; l < l1; ++l) {
     const size_t o = (size_t)l * ncol + gc;
     const double pavel = in.play[o], tavel = in.tlay[o];
@@ -366,18 +379,27 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
     for (int b = 0; b < 14; ++b) ls[b] = lower_src[b] ? laytrop : nlay;
     int jpm = 0;                                   // jp(lay - 1); 0 below the first layer
     int jp0 = W.idx[c] & 63;                       // jp(lay)
-    for (int lay = 1; lay <= nlay; ++lay) {
-      const int jp1 = lay < nlay ? (W.idx[(size_t)lay * ncc + c] & 63) : 0;   // jp(lay + 1); 0 above the last layer
+    constexpr int NB = 8;
+    for (int base = 1; base <= nlay; base += NB) {
+      int nxt[NB];                                 // jp(lay + 1) of the next 8 layers, loaded together; 0 above the last layer
 #pragma unroll
-      for (int b = 0; b < 14; ++b) {
-        if (lower_src[b]) {
-          if (lay <= laytrop && b != 10 && jp0 < layreffr[b] && jp1 >= layreffr[b]) ls[b] = imin(lay + 1, laytrop);
-        } else {
-          if (lay > laytrop && jpm < layreffr[b] && jp0 >= layreffr[b]) ls[b] = lay;
+      for (int j = 0; j < NB; ++j) nxt[j] = base + j < nlay ? (W.idx[(size_t)(base + j) * ncc + c] & 63) : 0;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int lay = base + j;
+        if (lay > nlay) break;
+        const int jp1 = nxt[j];
+#pragma unroll
+        for (int b = 0; b < 14; ++b) {
+          if (lower_src[b]) {
+            if (lay <= laytrop && b != 10 && jp0 < layreffr[b] && jp1 >= layreffr[b]) ls[b] = imin(lay + 1, laytrop);
+          } else {
+            if (lay > laytrop && jpm < layreffr[b] && jp0 >= layreffr[b]) ls[b] = lay;
+          }
         }
+        jpm = jp0;
+        jp0 = jp1;
       }
-      jpm = jp0;
-      jp0 = jp1;
     }
 #pragma unroll
     for (int b = 0; b < 14; ++b) W.laysolfr[(size_t)b * ncc + c] = ls[b];
