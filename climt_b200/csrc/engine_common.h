@@ -120,6 +120,16 @@ struct ZeroView {
 // optical depth and cloud arrays: ~60 % of the longwave call's input bytes in the default configuration) by a device-side
 // memset -- the same values in HBM, so results are unchanged.  The scan of chunk k + 1 overlaps the GPU work of chunk k.
 // -0.0 counts as non-zero (the array is then simply transferred).
+// Self-check of the scan: if it runs slower than 20 GB/s three times in a row (a host with few free cores: PCIe would have moved
+// the bytes faster), the caller stops scanning and transfers everything.
+struct ScanGuard {
+  int slow = 0;
+  bool note(size_t bytes, double seconds) {  // -> false: stop scanning
+    if (bytes < (8u << 20)) return true;  // small scans are dominated by the wake-up of the pool, not by bandwidth
+    slow = (double)bytes < 20e9 * seconds ? slow + 1 : 0;
+    return slow < 3;
+  }
+};
 inline void all_zero_parallel(const ZeroView* view, int nview, bool* zero) {
   struct Block { int v; size_t r0, r1; };
   std::vector<Block> blocks;

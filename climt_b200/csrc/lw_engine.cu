@@ -143,6 +143,7 @@ struct cb200_lw_engine {
   cb::HostPipe pipe;
   size_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the last host-pointer call
   bool skip_zero_inputs = true;         // CLIMT_B200_SKIP_ZERO_INPUTS=0 turns the all-zero scan of the host call off
+  cb::ScanGuard scan_guard;             // ... and so does a host on which the scan is slower than the copy it saves
   bool host_pending = false;
   std::future<int> enqueue;  // the chunk loop of a run_host_async call, running on its own host thread
   int* h_err = nullptr;
@@ -424,8 +425,14 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
       const int nc = clouds ? 6 : 5;
       cb::ZeroView zv[6];
       bool zz[6];
-      for (int j = 0; j < nc; ++j) zv[j] = cb::ZeroView{hp[cand[j]], (size_t)irows[cand[j]], (size_t)ncol, (size_t)c0, (size_t)n};
+      size_t zbytes = 0;
+      for (int j = 0; j < nc; ++j) {
+        zv[j] = cb::ZeroView{hp[cand[j]], (size_t)irows[cand[j]], (size_t)ncol, (size_t)c0, (size_t)n};
+        zbytes += (size_t)irows[cand[j]] * n * sizeof(double);
+      }
+      const double t0 = cb::HostPipe::now_ms();
       cb::all_zero_parallel(zv, nc, zz);
+      if (!e->scan_guard.note(zbytes, (cb::HostPipe::now_ms() - t0) * 1e-3)) e->skip_zero_inputs = false;
       for (int j = 0; j < nc; ++j) zero[cand[j]] = zz[j];
       // no cloud in these columns: water paths and particle sizes are never read (cldprop / cldprmc skip layers below cldmin)
       for (int i = 17; i <= 21; ++i) zero[i] = clouds && zero[16];
