@@ -1346,7 +1346,7 @@ struct Unit {
 #ifndef CB_LW_TAU_UMAX
 #define CB_LW_TAU_UMAX 4  // g-points per thread of the taumol kernel (2 or 4)
 #endif
-constexpr int kMaxUnits = 72;
+constexpr int kMaxUnits = 140;  // one g-point per unit at most
 inline int build_units(Unit* out, int umax) {  // host only
   int n = 0;
   // heavy (two-key-species, lower-atmosphere-rich) work first so the tail of the grid is made of light blocks

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kBlock, CB_LW_RT_MIN_BLOCKS)
   const int k = blockIdx.y;
   const Unit un = UL.u[k];
   if (CB_LW_UMAX >= 4 && un.u == 4) lw_transfer_unit<4, MC, MR>(T, in, W, c0, c, un.band - 1, un.g0, k);
+  else if (CB_LW_UMAX == 1) lw_transfer_unit<1, MC, MR>(T, in, W, c0, c, un.band - 1, un.g0, k);
   else lw_transfer_unit<2, MC, MR>(T, in, W, c0, c, un.band - 1, un.g0, k);
 }
 

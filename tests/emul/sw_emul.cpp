@@ -83,6 +83,7 @@ extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* 
     for (int k2 = 0; k2 < nunits; ++k2) {
       const Unit un = units[k2];
       if (un.u == 4) run_transfer<4>(T, sol, in, fl, W, ncol, un.band - 16, un.g0, k2, mc);
+      else if (un.u == 1) run_transfer<1>(T, sol, in, fl, W, ncol, un.band - 16, un.g0, k2, mc);
       else run_transfer<2>(T, sol, in, fl, W, ncol, un.band - 16, un.g0, k2, mc);
     }
     for (int c = 0; c < ncol; ++c)
