@@ -708,13 +708,9 @@ CB_HD void sw_taumol_unit(const Tables& T, const Solar& sol, const In& in, const
 }
 
 // spcvrt_sw / spcvmc_sw for U consecutive g-points of band ib (rrtmg_sw_spcvrt.f90:329-661) -- generic in the band.
-// PAIR (device only, U = 1): the two g-points of a unit are worked by the two half-warps of a warp (lane and lane ^ 16 hold the
-// same column); their fluxes are added with one shuffle per level -- in the order (even g-point) + (odd g-point), i.e. bit for
-// bit the sums the U = 2 form makes -- and only the lower half-warp stores them.  One g-point of state per thread (32 warps per
-// SM instead of 24) without doubling the partial-flux rows.
-template <int U, bool MC, bool PAIR = false>
+template <int U, bool MC>
 CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int c0, int c,
-                            int ib, int g0, int unit, unsigned pair_mask = 0u, bool pair_store = true) {
+                            int ib, int g0, int unit) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
   const double* __restrict__ tb = T.base;
@@ -880,21 +876,12 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
       }
     }
     const size_t lev = (size_t)(l + 1);
-#if defined(__CUDA_ARCH__)
-    if (PAIR) {  // outside every column-dependent branch: all lanes of pair_mask arrive here once per level
-      const double o0 = __shfl_xor_sync(pair_mask, sfu, 16), o1 = __shfl_xor_sync(pair_mask, sfd, 16);
-      const double o2 = __shfl_xor_sync(pair_mask, scu, 16), o3 = __shfl_xor_sync(pair_mask, scd, 16);
-      sfu = sfu + o0; sfd = sfd + o1; scu = scu + o2; scd = scd + o3;
+    if (cloudy_col) {  // cloud-free column: total == clear, not stored (sw_reduce_level copies)
+      part[0 * pstride + lev * ncc] = sfu;
+      part[1 * pstride + lev * ncc] = sfd;
     }
-#endif
-    if (!PAIR || pair_store) {
-      if (cloudy_col) {  // cloud-free column: total == clear, not stored (sw_reduce_level copies)
-        part[0 * pstride + lev * ncc] = sfu;
-        part[1 * pstride + lev * ncc] = sfd;
-      }
-      part[2 * pstride + lev * ncc] = scu;
-      part[3 * pstride + lev * ncc] = scd;
-    }
+    part[2 * pstride + lev * ncc] = scu;
+    part[3 * pstride + lev * ncc] = scd;
   }
 }
 
@@ -902,13 +889,11 @@ struct Unit {
   int band, g0, u;  // band = 16..29
 };
 #ifndef CB_SW_UMAX
-#define CB_SW_UMAX 2      // g-points per unit of the transfer kernel (1, 2 or 4).  With CB_SW_PAIR a unit of 2 is worked by two
-                          // half-warps, one g-point per thread.  r01 B200, 8192 x 60 clear sky, SW step: 2.57 ms at 2 g-points per
-                          // thread (24 warps/SM); 2.50 ms at 1 per thread and per unit (32 warps/SM, twice the partial-flux rows;
-                          // cloudy 4.61 -> 4.28, McICA 16384 x 72 12.45 -> 11.62)
-#endif
-#ifndef CB_SW_PAIR
-#define CB_SW_PAIR 1
+#define CB_SW_UMAX 1      // g-points per thread (= per unit) of the transfer kernel (1, 2 or 4).  r01 B200, 8192 x 60 clear sky, SW step:
+                          // 2.57 ms at 2 (24 warps/SM) -> 2.50 ms at 1 (32 warps/SM; the transfer kernel alone 1.90 -> 1.66 ms, part of it
+                          // returned by twice the partial-flux rows); cloudy 4.61 -> 4.28 ms, McICA 16384 x 72 12.45 -> 11.62 ms.
+                          // Splitting a 2-g-point unit over half-warps (shuffle) or over warp pairs (shared memory + a barrier per
+                          // level) to keep the rows of the 2-g-point form was measured too: 1.87 / 1.83 ms for the kernel -- not kept.
 #endif
 #ifndef CB_SW_TAU_UMAX
 #define CB_SW_TAU_UMAX 4  // g-points per thread of the taumol kernel (2 or 4)

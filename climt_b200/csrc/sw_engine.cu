@@ -18,8 +18,8 @@ using namespace cb::sw;
 namespace {
 using cb::kBlock;
 #ifndef CB_SW_RT_MIN_BLOCKS
-#define CB_SW_RT_MIN_BLOCKS 8  // transfer kernel, one g-point per thread: 32 warps per SM (r01 B200 sweep at 2 g-points: 4 -> 2.55 ms, 5 -> 2.30,
-                               // 6 -> 2.25; at 1 g-point: 6 -> 1.83, 8 -> 1.66, 10 -> 1.93 ms for the transfer kernel alone)
+#define CB_SW_RT_MIN_BLOCKS 8  // transfer kernel, one g-point per thread: 32 warps per SM (r01 B200 sweep at 2 g-points per thread: 4 -> 2.55 ms,
+                               // 5 -> 2.30, 6 -> 2.25; at 1 g-point: 6 -> 1.83, 8 -> 1.66, 10 -> 1.93 ms for the transfer kernel alone)
 #endif
 
 struct UnitList {
@@ -76,21 +76,10 @@ template <bool MC>
 __global__ void __launch_bounds__(kBlock, CB_SW_RT_MIN_BLOCKS)
     k_sw_transfer(const __grid_constant__ Tables T, const __grid_constant__ Solar sol, const __grid_constant__ In in, const Flags fl,
                   const __grid_constant__ Work W, const __grid_constant__ UnitList UL, int c0, int n) {
-  const int k = blockIdx.y;
-  const Unit un = UL.u[k];
-#if CB_SW_PAIR && CB_SW_UMAX == 2
-  {  // 64 columns x 2 g-points per block: lanes 0-15 of a warp take the unit's first g-point, lanes 16-31 the second (every
-     // shortwave band has an even number of g-points, so every unit is a full pair)
-    const int lane = threadIdx.x & 31;
-    const int cp = blockIdx.x * (kBlock / 2) + (threadIdx.x >> 5) * 16 + (lane & 15);
-    const unsigned pmask = __ballot_sync(0xffffffffu, cp < n);
-    if (cp >= n) return;
-    sw_transfer_unit<1, MC, true>(T, sol, in, fl, W, c0, cp, un.band - 16, un.g0 + (lane >> 4), k, pmask, lane < 16);
-    return;
-  }
-#endif
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
+  const int k = blockIdx.y;
+  const Unit un = UL.u[k];
   if (CB_SW_UMAX >= 4 && un.u == 4) sw_transfer_unit<4, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, k);
   else if (CB_SW_UMAX == 1) sw_transfer_unit<1, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, k);
   else sw_transfer_unit<2, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, k);
@@ -282,9 +271,8 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
   if (e->timing) cudaEventRecord(e->ev0, st);
   k_sw_taumol<<<dim3(gx, e->UL_tau.n, CB_SW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, sol, in, W, e->UL_tau, c0, n);
   if (e->timing) cudaEventRecord(e->evm, st);
-  const int gxt = (CB_SW_PAIR && CB_SW_UMAX == 2) ? (n + kBlock / 2 - 1) / (kBlock / 2) : gx;  // paired form: 64 columns per block
-  if (mc) k_sw_transfer<true><<<dim3(gxt, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
-  else k_sw_transfer<false><<<dim3(gxt, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+  if (mc) k_sw_transfer<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+  else k_sw_transfer<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
   if (e->timing) cudaEventRecord(e->ev1, st);
   k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, e->UL, out, nlay, out_ncol, c0, n);
   k_sw_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
