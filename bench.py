@@ -30,7 +30,7 @@ ALG_BYTES_LW = (49 * NLAY + 2 * (NLAY + 1) + 17 + 4 * (NLAY + 1) + 2 * NLAY) * 8
 ALG_BYTES_SW = (117 * NLAY + 2 * (NLAY + 1) + 6 + 4 * (NLAY + 1) + 2 * NLAY) * 8
 # measured DRAM bytes (read + write) of one transfer-kernel launch on this grid: filled from the ncu captures under profiles/
 NCU_DRAM_BYTES_LW = 3.821e9   # profiles/r01_lw_transfer_ncu_selected.txt (k_units, 8192 x 60)
-NCU_DRAM_BYTES_SW = 7.351e9   # profiles/r01_sw_transfer_ncu_selected.txt (k_sw_transfer, 8192 x 60)
+NCU_DRAM_BYTES_SW = 7.731e9   # profiles/r01_sw_transfer_1g_ncu_selected.txt (k_sw_transfer, one g-point per thread, 8192 x 60)
 
 
 def measured_peaks():
