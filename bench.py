@@ -315,7 +315,7 @@ def main():
         dom_bytes = ALG_BYTES_SW if sw_dom else ALG_BYTES_LW
         achieved = dom_bytes * NCOL / (dom_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at this grid size from the committed `ncu --set full`
-        # captures (profiles/r01_sw_transfer_ncu_selected.txt, profiles/r01_lw_transfer_ncu_selected.txt)
+        # captures (profiles/r01_sw_transfer_1g_ncu_selected.txt, profiles/r01_lw_transfer_ncu_selected.txt)
         traffic = NCU_DRAM_BYTES_SW if sw_dom else NCU_DRAM_BYTES_LW
         line = {
             "metric": "RRTMG LW+SW columns/s (60 lev)", "value": value, "unit": "columns/s", "n_gpus": world,
@@ -332,7 +332,10 @@ def main():
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
                          "kernel": dom, "kernel_ms": dom_ms, "alg_bytes_per_column": dom_bytes,
                          "lw_transfer_ms": unit_ms, "sw_transfer_ms": unit_ms_sw, "lw_taumol_ms": tau_ms, "sw_taumol_ms": tau_ms_sw,
-                         "note": "achieved = algorithmic bytes of the engine call (reference ABI, SURVEY.md 8d) x columns / kernel time; the kernel is bound by its fp64 dependency chain, not HBM (DESIGN.md 3)"},
+                         "traffic_gbs": traffic / (dom_ms * 1e-3) / 1e9,
+                         "note": "achieved = algorithmic bytes of the engine call (reference ABI, SURVEY.md 8d) x columns / kernel time. "
+                                 "`traffic` = DRAM bytes one launch really moves (ncu): per-g-point scratch rows carried between the two "
+                                 "vertical sweeps, ~16x the algorithmic bytes -- traffic_gbs is that over the same kernel time (DESIGN.md 3)"},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline and world == 1:
