@@ -73,7 +73,7 @@ class SwInputs(ctypes.Structure):
         "cicewp", "cliqwp", "reice", "reliq", "tauaer", "ssaaer", "asmaer", "ecaer")]
 
 
-EXPORTS = ["cb200_simple_physics_run_device", "cb200_simple_physics_run_host", "set_fortran_constants", "simple_physics",
+EXPORTS = ["cb200_berger_scalars", "cb200_berger_run_device", "cb200_berger_run_host", "cb200_simple_physics_run_device", "cb200_simple_physics_run_host", "set_fortran_constants", "simple_physics",
            "cb200_cork_create_from_file", "cb200_instellation_orbit", "cb200_instellation_run_device", "cb200_instellation_run_host", "cb200_slab_surface_run_device",
            "cb200_slab_surface_run_host", "cb200_emanuel_create", "cb200_emanuel_destroy", "cb200_emanuel_last_error", "cb200_emanuel_last_launches", "cb200_emanuel_enable_timing",
            "cb200_emanuel_last_kernel_ms", "cb200_emanuel_run_device", "cb200_emanuel_run_host", "init_emanuel_convection_fortran", "emanuel_convection",

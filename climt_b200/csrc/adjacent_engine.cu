@@ -1,4 +1,6 @@
-// climt_b200 -- the two column steps either side of the radiation call, sm_100a.
+// climt_b200 -- the small column steps either side of the radiation call, sm_100a.
+//   BergerSolarInsolation (zenith angle and insolation from Berger 1978 orbital parameters)
+//     _get_solar_parameters_np            climt/_components/berger_solar_insolation.py:635-680
 //   Instellation  (produces the zenith angle the shortwave engine consumes)
 //     _instellation_kernel_np, _obliquity_star_jit, _sun_ecliptic_longitude_jit, _gmst_jit
 //                                         climt/_components/instellation/component.py:84-191
@@ -36,6 +38,19 @@ __global__ void __launch_bounds__(128) k_instellation(int ncol, const double* __
   if (z > kPi / 2.0) z = kPi / 2.0;  // night side: the reference clamps the angle, component.py:124-128
   zenith[i] = z;
   if (coszen) coszen[i] = cos(z);  // what RRTMGShortwave.array_call evaluates from it (rrtmg/sw/component.py:591)
+}
+
+// BergerSolarInsolation: the per-column part of _get_solar_parameters_np (climt/_components/berger_solar_insolation.py:669-679).
+// The reference takes sin / cos of the latitude as it arrives, in degrees (:673); kept.
+__global__ void __launch_bounds__(128) k_berger(int ncol, const double* __restrict__ lat, const double* __restrict__ lon,
+                                                double fractional_day, double sin_delta, double cos_delta, double scale,
+                                                double* __restrict__ insolation, double* __restrict__ zenith) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncol) return;
+  const double H = 2 * kPi * (fractional_day + lon[i] / 360.0);
+  const double cos_mu = sin(lat[i]) * sin_delta - cos(lat[i]) * cos_delta * cos(H);
+  zenith[i] = acos(cos_mu);
+  insolation[i] = scale * cos_mu;
 }
 
 __global__ void __launch_bounds__(128) k_slab_surface(int ncol, long flux_stride, const cb200_slab_inputs in,
@@ -115,6 +130,61 @@ extern "C" int cb200_instellation_run_host(int device, int ncol, const double* l
   int rc = cb200_instellation_run_device(device, ncol, d, d + n, julian_centuries, d + 2 * n, nullptr, nullptr);
   if (rc == 0) {
     cudaMemcpyAsync(zenith, d + 2 * n, n * 8, cudaMemcpyDeviceToHost, 0);
+    if ((e = cudaStreamSynchronize(0)) != cudaSuccess) rc = fail(e);
+  }
+  cudaFree(d);
+  return rc;
+}
+
+// Per-call scalars of _get_solar_parameters_np (:651-667), host arithmetic in the reference's order of operations.
+// out: sin_delta, cos_delta, inverse_rho_squared, rho
+extern "C" void cb200_berger_scalars(double lambda_m0, double eccentricity, double omega_tilde, double obliquity,
+                                     double years_since_vernal_equinox, double* out) {
+  const double e = eccentricity, e2 = e * e;
+  const double lambda_m = lambda_m0 + years_since_vernal_equinox * 2.0 * kPi;
+  const double temp = lambda_m - (omega_tilde + kPi);
+  const double sin_temp = sin(temp);
+  const double lmbda = lambda_m + e * (2.0 * sin_temp + e * (1.25 * sin(2 * temp) + e * ((13.0 / 12.0) * sin(3 * temp) - 0.25 * sin_temp)));
+  const double inverse_rho = (1 + e * cos(lmbda - (omega_tilde + kPi))) / (1 - e2);
+  const double decl = asin(sin(obliquity) * sin(lmbda));
+  out[0] = sin(decl);
+  out[1] = cos(decl);
+  out[2] = inverse_rho * inverse_rho;
+  out[3] = 1.0 / inverse_rho;
+}
+
+extern "C" int cb200_berger_run_device(int device, int ncol, const double* lat, const double* lon, double lambda_m0,
+                                       double eccentricity, double omega_tilde, double obliquity,
+                                       double years_since_vernal_equinox, double fractional_day, double solar_constant,
+                                       double* insolation, double* zenith, double* rho, void* stream) {
+  if (ncol <= 0) { cb::set_global_error("berger: bad ncol"); return -3; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(e);
+  double sc[4];
+  cb200_berger_scalars(lambda_m0, eccentricity, omega_tilde, obliquity, years_since_vernal_equinox, sc);
+  if (rho) *rho = sc[3];
+  k_berger<<<(ncol + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ncol, lat, lon, fractional_day, sc[0], sc[1], solar_constant * sc[2],
+                                                                 insolation, zenith);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fail(e);
+}
+
+extern "C" int cb200_berger_run_host(int device, int ncol, const double* lat, const double* lon, double lambda_m0,
+                                     double eccentricity, double omega_tilde, double obliquity, double years_since_vernal_equinox,
+                                     double fractional_day, double solar_constant, double* insolation, double* zenith, double* rho) {
+  if (ncol <= 0) { cb::set_global_error("berger: bad ncol"); return -3; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(e);
+  const size_t n = (size_t)ncol;
+  double* d = nullptr;
+  if ((e = cudaMalloc(&d, 4 * n * sizeof(double))) != cudaSuccess) return fail(e);
+  cudaMemcpyAsync(d, lat, n * 8, cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(d + n, lon, n * 8, cudaMemcpyHostToDevice, 0);
+  int rc = cb200_berger_run_device(device, ncol, d, d + n, lambda_m0, eccentricity, omega_tilde, obliquity, years_since_vernal_equinox,
+                                   fractional_day, solar_constant, d + 2 * n, d + 3 * n, rho, nullptr);
+  if (rc == 0) {
+    cudaMemcpyAsync(insolation, d + 2 * n, n * 8, cudaMemcpyDeviceToHost, 0);
+    cudaMemcpyAsync(zenith, d + 3 * n, n * 8, cudaMemcpyDeviceToHost, 0);
     if ((e = cudaStreamSynchronize(0)) != cudaSuccess) rc = fail(e);
   }
   cudaFree(d);

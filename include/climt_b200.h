@@ -336,6 +336,20 @@ int cb200_instellation_run_device(int device, int ncol, const double* lat_deg, c
 int cb200_instellation_run_host(int device, int ncol, const double* lat_deg, const double* lon_deg, double julian_centuries,
                                 double* zenith);
 
+/* BergerSolarInsolation: replaces the numba kernel `_get_solar_parameters_np` (climt/_components/berger_solar_insolation.py:635-680).
+ * The four orbital parameters of the year come from the caller (the reference evaluates Berger's series in plain numpy, once per
+ * year: :579-625); lat / lon as the component passes them (the reference takes sin / cos of the latitude in degrees, :673).
+ * -> insolation [W m-2], zenith [rad] (ncol); *rho = normalised earth-sun distance.  cb200_berger_scalars: the per-call scalars
+ * (sin / cos of the declination, 1 / rho^2, rho), host arithmetic. */
+void cb200_berger_scalars(double lambda_m0, double eccentricity, double omega_tilde, double obliquity, double years_since_vernal_equinox,
+                          double* out4);
+int cb200_berger_run_device(int device, int ncol, const double* lat, const double* lon, double lambda_m0, double eccentricity,
+                            double omega_tilde, double obliquity, double years_since_vernal_equinox, double fractional_day,
+                            double solar_constant, double* insolation, double* zenith, double* rho, void* stream);
+int cb200_berger_run_host(int device, int ncol, const double* lat, const double* lon, double lambda_m0, double eccentricity,
+                          double omega_tilde, double obliquity, double years_since_vernal_equinox, double fractional_day,
+                          double solar_constant, double* insolation, double* zenith, double* rho);
+
 /* SlabSurface: replaces `_slab_surface_kernel_np` (climt/_components/slab_surface.py:449-517), include_ekman=False.
  * Every array has ncol entries except the four flux arrays, whose surface value for column i is element i * flux_stride
  * (component layout ("*", "interface_levels"): flux_stride = nlev + 1; the engines' (nlev + 1, ncol) outputs: flux_stride = 1).

@@ -3,6 +3,9 @@
   orbit, instellation     climt/_components/instellation/component.py:36-61 (array_call), :84-132 (_instellation_kernel_np),
                           :135-150 (_obliquity_star_jit), :153-177 (_sun_ecliptic_longitude_jit), :180-191 (_gmst_jit)
   slab_surface            climt/_components/slab_surface.py:164-447 (array_call, include_ekman=False), :449-517 (kernel)
+  berger                  climt/_components/berger_solar_insolation.py:538-693 (array_call, _driver, the Berger 1978 series in
+                          _get_orbital_parameters_functional, the numba kernel _get_solar_parameters_np); coefficients from the
+                          data file climt_b200/data/berger1978.npz (tools/extract_berger_tables.py)
 
 Pinned by tests/golden/adjacent_reference.npz, which tests/golden/make_adjacent_golden.py produced by running the reference's
 own component classes (tests/test_adjacent_cpu.py).
@@ -80,3 +83,44 @@ def slab_surface(state):
         val = np.where(hc != 0, net / np.where(hc != 0, hc, 1.0), 0.0)
     val = np.where(land_ice | sea_ice, 0.0, val)
     return val.reshape(shape), d.reshape(shape), oht.reshape(shape)
+
+
+def berger_orbit(t, tables):
+    """_get_orbital_parameters_functional (:579-625): t = years since 1950 -> lambda_m0, eccentricity, omega_tilde, obliquity"""
+    a2d = float(tables["arcsec_to_degree"])
+    obliquity = 23.320556 + np.sum(tables["A"] * a2d * np.cos((tables["f"] * a2d * t + tables["delta"]) * np.pi / 180.0))
+    obliquity = obliquity * np.pi / 180.0
+    cos_sum = np.sum(tables["P"] * np.cos(tables["alpha"] * a2d * t + tables["zeta"]))
+    sin_sum = np.sum(tables["P"] * np.sin(tables["alpha"] * a2d * t + tables["zeta"]))
+    e2 = cos_sum * cos_sum + sin_sum * sin_sum
+    e = np.sqrt(e2)
+    e3 = e * e2
+    pi_val = np.arctan2(sin_sum, cos_sum)
+    if pi_val < 0:
+        pi_val += 2.0 * np.pi
+    omega = pi_val * 180.0 / np.pi + 50.439273 * a2d * t + 3.392506
+    omega += np.sum(tables["F"] * np.sin((tables["f_prime"] * a2d * t + tables["delta_prime"]) * np.pi / 180.0))
+    omega = (omega % 360.0) * np.pi / 180.0
+    beta = np.sqrt(1.0 - e2)
+    lambda_m0 = 2.0 * ((0.5 * e + 0.125 * e3) * (1.0 + beta) * np.sin(omega + np.pi) - 0.25 * e2 * (0.5 + beta) * np.sin(2 * (omega + np.pi))
+                       + 0.125 * e3 * (1.0 / 3.0 + beta) * np.sin(3 * (omega + np.pi)))
+    return lambda_m0, e, omega, obliquity
+
+
+def berger(lat, lon, time, solar_constant, tables):
+    """BergerSolarInsolation.array_call: -> dict of the five diagnostics (lat / lon as given: the reference does not convert them)"""
+    lat, lon = np.asarray(lat, dtype=np.float64), np.asarray(lon, dtype=np.float64)
+    lambda_m0, e, omega, obliquity = berger_orbit(float(time.year - 1950), tables)
+    y0, y1 = type(time)(time.year, 3, 20, 12), type(time)(time.year + 1, 3, 20, 12)
+    ysve = (time - y0).total_seconds() / (y1 - y0).total_seconds()
+    fday = (time - type(time)(time.year, time.month, time.day)).total_seconds() / 86400.0
+    lambda_m = lambda_m0 + ysve * 2.0 * np.pi
+    temp = lambda_m - (omega + np.pi)
+    st = np.sin(temp)
+    lmbda = lambda_m + e * (2.0 * st + e * (1.25 * np.sin(2 * temp) + e * ((13.0 / 12.0) * np.sin(3 * temp) - 0.25 * st)))
+    inv_rho = (1 + e * np.cos(lmbda - (omega + np.pi))) / (1 - e * e)
+    decl = np.arcsin(np.sin(obliquity) * np.sin(lmbda))
+    H = 2 * np.pi * (fday + lon / 360.0)
+    cos_mu = np.sin(lat) * np.sin(decl) - np.cos(lat) * np.cos(decl) * np.cos(H)
+    return {"solar_insolation": solar_constant * (inv_rho * inv_rho) * cos_mu, "solar_zenith_angle": np.arccos(cos_mu),
+            "obliquity": obliquity, "eccentricity": e, "normalized_earth_sun_distance": 1.0 / inv_rho}

@@ -182,3 +182,60 @@ def test_slab_through_call_with_string_area_types(gold):
     assert tend["surface_temperature"].dims == ("lat", "lon") and tend["surface_temperature"].attrs["units"] == "degK s^-1"
     np.testing.assert_array_equal(tend["surface_temperature"].values.reshape(-1), gold["slab/mixed/out/tendency"])
     np.testing.assert_array_equal(diag["depth_of_slab_surface"].values.reshape(-1), gold["slab/mixed/out/depth"])
+
+
+# ------------------------------------------------------------------------------------------------ BergerSolarInsolation
+BERGER_DIAG = ("solar_insolation", "solar_zenith_angle", "obliquity", "eccentricity", "normalized_earth_sun_distance")
+
+
+def _berger_tables():
+    with np.load(H.os.path.join(H.os.path.dirname(H.HERE), "climt_b200", "data", "berger1978.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("case", INST_CASES)
+def test_berger_oracle_matches_the_reference_component(gold, case):
+    t = datetime.datetime(*[int(x) for x in gold[f"berger/{case}/time"]])
+    out = OA.berger(gold[f"berger/{case}/lat"], gold[f"berger/{case}/lon"], t, 1367.0, _berger_tables())
+    for k in BERGER_DIAG:
+        ref = gold[f"berger/{case}/{k}"]
+        np.testing.assert_allclose(out[k], ref, rtol=1e-13, atol=1e-10 if k == "solar_insolation" else 1e-13, err_msg=k)
+
+
+def test_berger_reference_cache_and_host_orbit(gold):
+    """TestBergerSolarInsolation-column: default state (lat = lon = 0, 2000-01-01 00:00); and the product's per-year numpy series
+    (the same host arithmetic as the reference's) against the oracle's and the golden scalars"""
+    from climt_b200 import berger_solar_insolation as B
+    out = OA.berger(np.zeros((1, 1)), np.zeros((1, 1)), datetime.datetime(2000, 1, 1), 1367.0, _berger_tables())
+    for k in BERGER_DIAG:
+        np.testing.assert_allclose(out[k], gold[f"cache/TestBergerSolarInsolation-column/0/{k}"], rtol=1e-12, atol=1e-9, err_msg=k)
+    for year in (1987, 2000, 2021, 2035):
+        np.testing.assert_array_equal(B.orbital_parameters(float(year - 1950)), OA.berger_orbit(float(year - 1950), _berger_tables()))
+    for case in INST_CASES:
+        t = datetime.datetime(*[int(x) for x in gold[f"berger/{case}/time"]])
+        lm0, ecc, om, obl = B.orbital_parameters(float(t.year - 1950))
+        assert obl == float(gold[f"berger/{case}/obliquity"]) and ecc == float(gold[f"berger/{case}/eccentricity"])
+        L = B._native.lib()
+        L.cb200_berger_scalars.argtypes = [B.ctypes.c_double] * 5 + [B._dp]
+        L.cb200_berger_scalars.restype = None
+        sc = (B.ctypes.c_double * 4)()
+        L.cb200_berger_scalars(float(lm0), float(ecc), float(om), float(obl), B.years_since_vernal_equinox(t), sc)   # host arithmetic only
+        np.testing.assert_allclose(sc[3], float(gold[f"berger/{case}/normalized_earth_sun_distance"]), rtol=1e-14)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", INST_CASES)
+def test_berger_drop_in_matches_the_reference_component(gold, case):
+    import torch
+    from climt_b200.berger_solar_insolation import BergerSolarInsolation
+    t = datetime.datetime(*[int(x) for x in gold[f"berger/{case}/time"]])
+    lat, lon = gold[f"berger/{case}/lat"], gold[f"berger/{case}/lon"]
+    comp = BergerSolarInsolation()
+    out = comp.array_call({"latitude": lat, "longitude": lon, "time": t})
+    assert set(out) == set(BERGER_DIAG) and out["solar_insolation"].shape == lat.shape
+    for k in BERGER_DIAG:
+        np.testing.assert_allclose(out[k], gold[f"berger/{case}/{k}"], rtol=1e-12, atol=1e-9 if k == "solar_insolation" else 1e-12, err_msg=k)
+    dev = comp.array_call({"latitude": torch.from_numpy(lat).cuda(), "longitude": torch.from_numpy(lon).cuda(), "time": t})
+    assert dev["solar_zenith_angle"].is_cuda
+    np.testing.assert_array_equal(dev["solar_insolation"].cpu().numpy(), out["solar_insolation"])
+    np.testing.assert_array_equal(dev["solar_zenith_angle"].cpu().numpy(), out["solar_zenith_angle"])
