@@ -357,3 +357,13 @@ def emanuel_compare(got, ref, rtol, what=""):
         assert err < rtol, (what, k, err)
         worst = max(worst, err)
     return worst
+
+
+def host_pipe_emul_lib():
+    """host-side helpers of the engines' host-pointer path (worker pool, all-zero scan), compiled without CUDA"""
+    so = os.path.join(HERE, "emul", "libcb_emul_hostpipe.so")
+    src = os.path.join(HERE, "emul", "host_pipe_emul.cpp")
+    deps = [src, os.path.join(HERE, "..", "climt_b200", "csrc", "engine_common.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-pthread", "-shared", "-o", so, src])
+    return ctypes.CDLL(so)
