@@ -61,7 +61,7 @@ class RRTMGShortwave(TendencyComponent):
         "solar_cycle_fraction": _p([], "dimensionless"),
         "flux_adjustment_for_earth_sun_distance": _p([], "dimensionless"),
     }
-    tendency_properties = {"air_temperature": {"dims": ["mid_levels", "*"], "units": "degK day^-1"}}
+    tendency_properties = {"air_temperature": {"units": "degK day^-1"}}  # dims follow the input of the same name, as in the reference
     diagnostic_properties = {
         "upwelling_shortwave_flux_in_air": _p(["interface_levels", "*"], "W m^-2"),
         "downwelling_shortwave_flux_in_air": _p(["interface_levels", "*"], "W m^-2"),

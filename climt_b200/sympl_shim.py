@@ -157,5 +157,6 @@ except Exception:  # ImportError or a broken install
                     dim_len[d] = n
         out = {}
         for name, prop in output_properties.items():
-            out[name] = np.zeros([dim_len[d] for d in prop["dims"]], dtype=np.float64)
+            dims = prop["dims"] if "dims" in prop else input_properties[name]["dims"]   # sympl: dims of the input of the same name
+            out[name] = np.zeros([dim_len[d] for d in dims], dtype=np.float64)
         return out
