@@ -65,6 +65,7 @@ def reference_classes():
         "RRTMGShortwave": imp("climt._components.rrtmg.sw.component").RRTMGShortwave,
         "GrayLongwaveRadiation": imp("climt._components.radiation").GrayLongwaveRadiation,
         "EmanuelConvection": imp("climt._components.emanuel.component").EmanuelConvection,
+        "EmanuelConvectionPython": imp("climt._components.emanuel.pure_python_v3").EmanuelConvectionPython,
         "SimplePhysics": imp("climt._components.simple_physics.component").SimplePhysics,
         "Instellation": imp("climt._components.instellation.component").Instellation,
         "BergerSolarInsolation": imp("climt._components.berger_solar_insolation").BergerSolarInsolation,

@@ -19,6 +19,7 @@ def _cls(name):
                             slab_surface)
     return {"RRTMGLongwave": rrtmg_lw.RRTMGLongwave, "RRTMGShortwave": rrtmg_sw.RRTMGShortwave,
             "GrayLongwaveRadiation": gray.GrayLongwaveRadiation, "EmanuelConvection": emanuel.EmanuelConvection,
+            "EmanuelConvectionPython": emanuel.EmanuelConvectionPython,
             "SimplePhysics": simple_physics.SimplePhysics, "Instellation": instellation.Instellation,
             "BergerSolarInsolation": berger_solar_insolation.BergerSolarInsolation, "SlabSurface": slab_surface.SlabSurface,
             "CorkLongwaveRadiation": cork.CorkLongwaveRadiation, "CorkShortwaveRadiation": cork.CorkShortwaveRadiation}[name]
