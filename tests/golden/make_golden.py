@@ -38,6 +38,16 @@ def main():
                     key = f"{cls}-{kind}/{'tend' if part == 0 else 'diag'}/{name}"
                     out[key] = np.array(var[:], dtype=np.float64)
                 nc.close()
+    # The `*_stepping` caches hold the diagnostics AND the whole state after one Adams-Bashforth step of 10 s on the component's
+    # default state: every input the reference's get_default_state produced (pressures, ozone, gases, cloud defaults) plus the
+    # stepped temperature.  Column versions only; stored as "<TestClass>-column_stepping/{diag,state}/<quantity>".
+    for cls in ("TestRRTMGLongwave", "TestRRTMGShortwave"):
+        for part, tag in ((0, "diag"), (1, "state")):
+            path = os.path.join(SRC, f"{cls}-column_stepping-{part}.cache")
+            nc = netcdf_file(path, "r", mmap=False)
+            for name, var in nc.variables.items():
+                out[f"{cls}-column_stepping/{tag}/{name}"] = np.array(var.data if var.shape == () else var[:], dtype=np.float64)
+            nc.close()
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_caches.npz")
     np.savez_compressed(dst, **out)
     print(f"{len(out)} arrays -> {dst} ({os.path.getsize(dst)/1e3:.1f} kB)")

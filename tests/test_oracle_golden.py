@@ -41,3 +41,39 @@ def test_crib_values():
     g = H.golden()
     up = g["TestRRTMGLongwave-column/diag/upwelling_longwave_flux_in_air"][:, 0, 0]
     assert abs(up[0] - 459.29431776) < 1e-7 and abs(up[-1] - 443.9333446703) < 1e-7
+
+
+@pytest.mark.parametrize("cls,builder", [("TestRRTMGLongwave", "default_rrtmg_lw_state"), ("TestRRTMGShortwave", "default_rrtmg_sw_state")])
+def test_default_state_inputs_match_the_reference_state(cls, builder):
+    """The `*_stepping` caches carry the whole state the reference's get_default_state built for the component (grid pressures,
+    ozone profile, gas defaults, cloud and aerosol defaults): the inputs of every golden comparison above, checked one by one."""
+    from climt_b200 import state as S
+    g = H.golden()
+    st = getattr(S, builder)(30, 1)
+    pre = f"{cls}-column_stepping/state/"
+    checked = 0
+    for key in g.files:
+        if not key.startswith(pre):
+            continue
+        name = key[len(pre):]
+        if name not in st or name == "air_temperature":      # (the cache's temperature is the stepped one)
+            continue
+        ref = np.asarray(g[key], dtype=np.float64)
+        mine = np.asarray(st[name], dtype=np.float64)
+        np.testing.assert_allclose(mine.reshape(-1), ref.reshape(-1), rtol=1e-14, atol=0, err_msg=name)
+        checked += 1
+    assert checked >= 20, checked
+    ak, bk = S.hybrid_sigma_pressure_levels(31, 1.0132e5, 20.0)
+    np.testing.assert_allclose(ak, g[pre + "atmosphere_hybrid_sigma_pressure_a_coordinate_on_interface_levels"], rtol=1e-14, atol=1e-12)
+    np.testing.assert_allclose(bk, g[pre + "atmosphere_hybrid_sigma_pressure_b_coordinate_on_interface_levels"], rtol=1e-14, atol=1e-16)
+
+
+def test_one_adams_bashforth_step_of_the_oracle_tendency_matches_the_stepping_cache():
+    """TestRRTMGLongwave-column_stepping: AdamsBashforth(RRTMGLongwave) on the default state, dt = 10 s (tests/test_components.py:
+    145-152, 241-254).  Its first step is forward Euler on the tendency in K/day: T + 10 s * hr / 86400."""
+    g = H.golden()
+    out = H.run_lw_oracle(H.lw_oracle(), H.default_lw_abi_state(30, 1))
+    ref_T = g["TestRRTMGLongwave-column_stepping/state/air_temperature"][:, 0, 0]
+    np.testing.assert_allclose(290.0 + 10.0 * out["hr"][:, 0] / 86400.0, ref_T, rtol=0, atol=2e-13)
+    assert np.abs(ref_T - 290.0).max() > 1e-4
+    np.testing.assert_allclose(out["uflx"][:, 0], g["TestRRTMGLongwave-column_stepping/diag/upwelling_longwave_flux_in_air"][:, 0, 0], rtol=0, atol=1e-8)
