@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("CLIMT_B200_SO") or os.path.join(_HERE, "libclimt_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lw_engine.cu", "sw_engine.cu", "gray_engine.cu", "cork_engine.cu", "marshal.cu", "emanuel_engine.cu", "adjacent_engine.cu", "simple_physics.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("cb_common.h", "engine_common.h", "lw_core.cuh", "lw_tables.h", "sw_core.cuh", "sw_tables.h",
-                                                          "mcica_core.cuh", "mcica_host.h", "cork_core.cuh", "cork_tables.h", "emanuel_core.cuh")] + [
+                                                          "mcica_core.cuh", "mcica_host.h", "cork_core.cuh", "cork_tables.h", "emanuel_core.cuh", "simple_physics_core.cuh")] + [
     os.path.join(_HERE, "..", "include", "climt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "--fmad=true"]

@@ -367,3 +367,34 @@ def host_pipe_emul_lib():
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-pthread", "-shared", "-o", so, src])
     return ctypes.CDLL(so)
+
+
+def simple_physics_emul_lib():
+    """k_simple_physics' per-column code compiled for the host (tests/emul/simple_physics_emul.cpp)"""
+    so = os.path.join(HERE, "emul", "libcb_emul_simple_physics.so")
+    src = os.path.join(HERE, "emul", "simple_physics_emul.cpp")
+    deps = [src] + [os.path.join(HERE, "..", "climt_b200", "csrc", f) for f in ("simple_physics_core.cuh", "cb_common.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def run_simple_physics_emul(state, dtime, params, order=0):
+    """state keyed by the component's input names, (nlev[+1], ncol) arrays -> the seven outputs of the C ABI"""
+    from climt_b200 import simple_physics as SP
+    lib = simple_physics_emul_lib()
+    nlev, ncol = state["air_temperature"].shape
+    keep, s = [], SP._InHost()
+    for k, name in SP._STATE.items():
+        a = np.ascontiguousarray(state[name], dtype=np.float64)
+        keep.append(a)
+        setattr(s, k, a.ctypes.data_as(_dp))
+    out = {k: np.full((nlev, ncol) if k in ("t", "q", "u", "v") else (ncol,), np.nan) for k in SP._OUT}
+    o = SP._OutHost()
+    for k in SP._OUT:
+        setattr(o, k, out[k].ctypes.data_as(_dp))
+    lib.emul_simple_physics_run.argtypes = [ctypes.c_int] * 3 + [ctypes.c_double, ctypes.POINTER(SP.Params), ctypes.POINTER(SP._InHost),
+                                                                 ctypes.POINTER(SP._OutHost)]
+    rc = lib.emul_simple_physics_run(ncol, nlev, order, float(dtime), ctypes.byref(params), ctypes.byref(s), ctypes.byref(o))
+    assert rc == 0
+    return out

@@ -113,13 +113,44 @@ def test_unprovided_combination_is_rejected():
         SimplePhysics(boundary_layer=True, surface_fluxes=False)
 
 
-# ------------------------------------------------------------------------------------------------ GPU
 OPTION_SETS = [dict(), dict(boundary_layer=False), dict(large_scale_condensation=False, use_external_surface_specific_humidity=True),
                dict(use_external_surface_temperature=False), dict(use_external_surface_temperature=False, simulate_cyclone=True),
                dict(boundary_layer=False, surface_fluxes=False), dict(top_of_boundary_layer=70000.0, boundary_layer_influence_height=1e4,
                                                                       drag_coefficient_heat_fluxes=0.002)]
 
 
+def _params(options):
+    """cb200_simple_physics_params as the drop-in fills it (no engine is created: the constructor only checks the library exists)"""
+    from climt_b200.simple_physics import SimplePhysics
+    return SimplePhysics(**options).params()
+
+
+@pytest.mark.parametrize("options", OPTION_SETS)
+def test_kernel_code_on_the_host_matches_the_oracle(options):
+    """the per-column code of k_simple_physics (csrc/simple_physics_core.cuh) compiled for the host, NaN-poisoned workspace"""
+    st = random_state(45, 97, 21)
+    diag_ref, new_ref = OS.component_call(st, DT, C, **options)
+    out = H.run_simple_physics_emul(st, DT, _params(options))
+    for k, name in (("t", "air_temperature"), ("q", "specific_humidity"), ("u", "eastward_wind"), ("v", "northward_wind")):
+        _assert_close(out[k], new_ref[name], name)
+    for k, name in (("precl", "stratiform_precipitation_rate"), ("sens_ht_flux", "surface_upward_sensible_heat_flux"),
+                    ("lat_ht_flux", "surface_upward_latent_heat_flux")):
+        _assert_close(out[k], diag_ref[name], name)
+    # the Fortran's own level order (model top first), as the reference-named symbol passes it
+    flipped = {k: (v[::-1].copy() if v.ndim == 2 else v) for k, v in st.items()}
+    out1 = H.run_simple_physics_emul(flipped, DT, _params(options), order=1)
+    for k in ("t", "q", "u", "v"):
+        np.testing.assert_array_equal(out1[k][::-1], out[k])
+
+
+def test_kernel_code_reproduces_the_reference_cache():
+    g = H.golden()
+    out = H.run_simple_physics_emul(default_state(30), DT, _params({}))
+    np.testing.assert_allclose(out["t"][:, 0], g["TestSimplePhysics-column/diag/air_temperature"][:, 0, 0], rtol=3e-16, atol=0)
+    assert out["precl"][0] == 0.0 and out["sens_ht_flux"][0] == 0.0 and out["lat_ht_flux"][0] == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ GPU
 def _assert_close(got, ref, name):
     scale = float(np.abs(ref).max()) or 1.0
     np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-13 * scale, err_msg=name)
