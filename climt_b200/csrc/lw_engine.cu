@@ -437,6 +437,8 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
       for (int j = 0; j < nc; ++j) zero[cand[j]] = zz[j];
       // no cloud in these columns: water paths and particle sizes are never read (cldprop / cldprmc skip layers below cldmin)
       for (int i = 17; i <= 21; ++i) zero[i] = clouds && zero[16];
+    } else {
+      for (int i = 0; i < 23; ++i) zero[i] = false;  // (the guard may have stopped the scan in the middle of a call)
     }
     // H2D: the slot is free once the chunk that last used it has been computed
     CUDA_OK(cudaStreamWaitEvent(P.s_in, P.cmp_done[s], 0));
