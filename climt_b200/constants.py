@@ -37,6 +37,8 @@ DEFAULTS = {
     "planetary_radius": (6.371e6, "m"),
     "planetary_rotation_rate": (7.292e-5, "s^-1"),
     "density_of_liquid_water": (1e3, "kg m^-3"),
+    # read by SlabSurface(include_ekman=True) (climt/_components/slab_surface.py:343); sympl's default, no golden pins it
+    "heat_capacity_of_sea_water": (3.985e3, "J kg^-1 K^-1"),
 }
 
 _registry = {k: v[0] for k, v in DEFAULTS.items()}

@@ -5,8 +5,10 @@ Host path: numpy arrays in the component's dims (fluxes ("*", "interface_levels"
 value of each flux column crosses PCIe.  Device path: torch CUDA tensors; the flux arguments may be the
 radiation engines' (interface_levels, column) outputs (`flux_layout="level_major"`), read in place.
 
-`include_ekman=True` (wind-stress curl / divergence on the 2-D lat-lon grid, slab_surface.py:296-403) couples neighbouring
-columns through `_core/horizontal_operators.py`; that is outside the column hot path and is rejected loudly.
+`include_ekman=True` (slab_surface.py:296-403) adds an Ekman heat-transport convergence from the wind-stress field.  That part
+couples neighbouring columns through finite differences on the 2-D lat-lon grid and is host numpy in the reference
+(`_core/horizontal_operators.py`); it is host numpy here too (`ekman_terms`), feeding the same column kernel.  Host path only:
+a device-resident state with include_ekman=True is rejected.
 """
 import ctypes
 
@@ -38,6 +40,37 @@ class SlabInputsHost(ctypes.Structure):
 
 class SlabInputsDevice(ctypes.Structure):
     _fields_ = [(n, _vp) for n, _ in SlabInputsHost._fields_]
+
+
+def _grads(field, lat, lon, radius):
+    """d/dx, d/dy on the sphere by centred differences (climt/_core/horizontal_operators.py:19-33); zeros on degenerate grids"""
+    latr, lonr = np.deg2rad(lat), np.deg2rad(lon)
+    if field.shape[0] < 3 or field.shape[1] < 3:
+        z = np.zeros_like(field, dtype=float)
+        return z, z
+    dfdlat = np.gradient(field, axis=0) / np.gradient(latr, axis=0)
+    dfdlon = np.gradient(field, axis=1) / np.gradient(lonr, axis=1)
+    return dfdlon / (radius * np.cos(latr)), dfdlat / radius
+
+
+def ekman_terms(lat2d, lon2d, tau_x, tau_y, surface_temperature, sea_water_density, area_code, eq_cap_latitude, omega, c_sw, radius):
+    """Ekman heat-transport convergence [W m-2] and Ekman pumping [m s-1] on the (lat, lon) grid, as SlabSurface.array_call
+    forms them (slab_surface.py:296-403): wind stress zeroed outside open ocean before differentiating, Coriolis parameter
+    capped below `eq_cap_latitude`, mass transport with the full 1/f variation, pumping with the local-f approximation."""
+    open_ocean = area_code.reshape(lat2d.shape) == AREA_MAP["sea"]
+    tau_x = np.where(open_ocean, tau_x, 0.0)
+    tau_y = np.where(open_ocean, tau_y, 0.0)
+    f = 2.0 * omega * np.sin(np.deg2rad(lat2d))
+    f_floor = 2.0 * omega * np.sin(np.deg2rad(eq_cap_latitude))
+    f_capped = np.where(f >= 0.0, 1.0, -1.0) * np.maximum(np.abs(f), f_floor)
+    Mx, My = tau_y / f_capped, -tau_x / f_capped
+    dtauy_dx, _ = _grads(tau_y, lat2d, lon2d, radius)
+    _, dtaux_dy = _grads(tau_x, lat2d, lon2d, radius)
+    w_ek = (dtauy_dx - dtaux_dy) / (f_capped * sea_water_density)
+    dfx_dx, _ = _grads(surface_temperature * Mx, lat2d, lon2d, radius)
+    _, dfy_dy = _grads(surface_temperature * My, lat2d, lon2d, radius)
+    q_ekman = -c_sw * (dfx_dx + dfy_dy)
+    return np.where(open_ocean, q_ekman, 0.0), np.where(open_ocean, w_ek, 0.0)
 
 
 def area_type_codes(area_type):
@@ -159,23 +192,58 @@ class SlabSurface(TendencyComponent):
     }
 
     def __init__(self, include_ekman=False, equatorial_ekman_cap_latitude=5.0, device=0, flux_layout="column_major", **kwargs):
-        if include_ekman:
-            raise NotImplementedError("SlabSurface(include_ekman=True) differentiates the wind stress on the 2-D lat-lon grid "
-                                      "(climt/_core/horizontal_operators.py): not a column operation, not part of this engine")
-        self._include_ekman, self._eq_cap = False, equatorial_ekman_cap_latitude
+        self._include_ekman, self._eq_cap = include_ekman, equatorial_ekman_cap_latitude
         self._device, self._flux_layout = device, flux_layout
+        if include_ekman:  # slab_surface.py:125-158: four 2-D inputs and two diagnostics more
+            self.input_properties = dict(self.input_properties)
+            self.input_properties.update({
+                "surface_downward_eastward_stress": {"dims": ["lat", "lon"], "units": "N m^-2"},
+                "surface_downward_northward_stress": {"dims": ["lat", "lon"], "units": "N m^-2"},
+                "latitude": {"dims": ["lat", "lon"], "units": "degrees_north"},
+                "longitude": {"dims": ["lat", "lon"], "units": "degrees_east"},
+            })
+            self.diagnostic_properties = dict(self.diagnostic_properties)
+            self.diagnostic_properties.update({
+                "ekman_heat_transport_convergence": {"dims": ["*"], "units": "W m^-2"},
+                "ekman_pumping": {"dims": ["*"], "units": "m s^-1"},
+            })
         _native.lib()
         super().__init__(**kwargs)
+
+    def _ekman(self, state, code):
+        """(q_ekman, w_ek) flattened to the column axis (slab_surface.py:296-403)"""
+        from .constants import get_constant
+        lat2d = np.asarray(state["latitude"], dtype=float)
+        lon2d = np.asarray(state["longitude"], dtype=float)
+        if lat2d.ndim == 1:  # a flattened single-column view: the operators return zeros below 3 points per dimension
+            lat2d, lon2d = lat2d.reshape(-1, 1), lon2d.reshape(-1, 1)
+        shp = lat2d.shape
+        q, w = ekman_terms(lat2d, lon2d, np.asarray(state["surface_downward_eastward_stress"], dtype=float).reshape(shp),
+                           np.asarray(state["surface_downward_northward_stress"], dtype=float).reshape(shp),
+                           np.asarray(state["surface_temperature"], dtype=float).reshape(shp),
+                           np.asarray(state["sea_water_density"], dtype=float).reshape(shp), code, self._eq_cap,
+                           get_constant("planetary_rotation_rate", "s^-1"), get_constant("heat_capacity_of_sea_water", "J/kg/degK"),
+                           get_constant("planetary_radius", "m"))
+        return q.reshape(-1), w.reshape(-1)
 
     def array_call(self, state):
         at = state["area_type"]
         if type(at).__module__.startswith("torch") and getattr(at, "is_cuda", False):
+            if self._include_ekman:
+                raise NotImplementedError("SlabSurface(include_ekman=True) on a device-resident state: the Ekman terms are finite "
+                                          "differences across columns, evaluated on the host as in the reference")
             tend, depth = slab_surface_device(state, self._flux_layout)
             oht = state["ocean_heat_transport_convergence"]
             return ({"surface_temperature": tend.reshape(at.shape)},
                     {"depth_of_slab_surface": depth.reshape(at.shape), "ocean_heat_transport_convergence": oht.reshape(at.shape)})
         shape = np.asarray(at).shape
-        tend, depth = slab_surface_host(state, self._device)
         oht = np.asarray(state["ocean_heat_transport_convergence"], dtype=np.float64)
+        extra = {}
+        if self._include_ekman:
+            q_ek, w_ek = self._ekman(state, area_type_codes(at))
+            oht = oht.reshape(-1) + q_ek   # the total q-flux applied to sea cells, also what the diagnostic reports (:423-436)
+            state = dict(state, ocean_heat_transport_convergence=oht)
+            extra = {"ekman_heat_transport_convergence": q_ek.reshape(shape), "ekman_pumping": w_ek.reshape(shape)}
+        tend, depth = slab_surface_host(state, self._device)
         return ({"surface_temperature": tend.reshape(shape)},
-                {"depth_of_slab_surface": depth.reshape(shape), "ocean_heat_transport_convergence": oht.reshape(shape)})
+                dict({"depth_of_slab_surface": depth.reshape(shape), "ocean_heat_transport_convergence": oht.reshape(shape)}, **extra))

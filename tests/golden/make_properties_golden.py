@@ -109,6 +109,7 @@ def main():
                           ("titan", {"optics": "correlated_k", "table": tdir + f"titan_{which}.nc"})):
             out[name]["instances"][label] = props(C[name](**kw))
     out["CorkLongwaveRadiation"]["instances"]["tour_gray"] = props(C["CorkLongwaveRadiation"](optics="correlated_k", table=tdir + "tour_gray_lw.nc"))
+    out["SlabSurface"]["instances"] = {"ekman": props(C["SlabSurface"](include_ekman=True))}
     dst = os.path.join(HERE, "reference_properties.json")
     with open(dst, "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)

@@ -78,10 +78,45 @@ def test_orbit_scalars_of_the_c_abi(gold, case):
     np.testing.assert_allclose(I.orbit(jc), OA.orbit(jc), rtol=0, atol=2e-15)
 
 
-def test_ekman_variant_is_rejected_loudly():
+def _ekman_in(z):
+    pre = "slab_ekman/in/"
+    return {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+
+
+def _check_ekman(tend, diag, gold):
+    np.testing.assert_array_equal(diag["ekman_heat_transport_convergence"], gold["slab_ekman/out/ekman_heat_transport_convergence"])
+    np.testing.assert_array_equal(diag["ekman_pumping"], gold["slab_ekman/out/ekman_pumping"])
+    np.testing.assert_array_equal(diag["ocean_heat_transport_convergence"], gold["slab_ekman/out/ocean_heat_transport_convergence"])
+    np.testing.assert_array_equal(diag["depth_of_slab_surface"], gold["slab_ekman/out/depth_of_slab_surface"])
+    np.testing.assert_array_equal(tend["surface_temperature"], gold["slab_ekman/out/tendency"])
+
+
+def test_ekman_option_on_the_host_matches_the_reference_component(gold, monkeypatch):
+    """SlabSurface(include_ekman=True): the Ekman terms are host numpy here as in the reference; the column kernel is stood in
+    for by the oracle in this CPU test (the GPU test below runs the same call on the real kernel)"""
+    from climt_b200 import slab_surface as SL
+    q = gold["slab_ekman/out/ekman_heat_transport_convergence"]
+    assert (q != 0).sum() > 100 and np.abs(gold["slab_ekman/out/ekman_pumping"]).max() > 0
+
+    def oracle_kernel(state, device=0):
+        t, d, _ = OA.slab_surface(state)
+        return t.reshape(-1), d.reshape(-1)
+    monkeypatch.setattr(SL, "slab_surface_host", oracle_kernel)
+    comp = SL.SlabSurface(include_ekman=True, equatorial_ekman_cap_latitude=4.0)
+    assert comp.input_properties["latitude"]["dims"] == ["lat", "lon"] and "ekman_pumping" in comp.diagnostic_properties
+    assert "ekman_pumping" not in SL.SlabSurface.diagnostic_properties      # the class-level dicts stay those of the plain slab
+    tend, diag = comp.array_call(_ekman_in(gold))
+    _check_ekman(tend, diag, gold)
+
+
+def test_ekman_option_needs_host_arrays():
     from climt_b200.slab_surface import SlabSurface
-    with pytest.raises(NotImplementedError):
-        SlabSurface(include_ekman=True)
+
+    class FakeCuda:
+        is_cuda = True
+    FakeCuda.__module__ = "torch"
+    with pytest.raises(NotImplementedError, match="device-resident"):
+        SlabSurface(include_ekman=True).array_call({"area_type": FakeCuda()})
 
 
 def test_area_type_codes():
@@ -140,6 +175,13 @@ def test_slab_drop_in_matches_the_reference_component(gold, case):
     np.testing.assert_array_equal(tend["surface_temperature"], gold[f"slab/{case}/out/tendency"])
     np.testing.assert_array_equal(diag["depth_of_slab_surface"], gold[f"slab/{case}/out/depth"])
     np.testing.assert_array_equal(diag["ocean_heat_transport_convergence"], gold[f"slab/{case}/out/ocean_heat_transport_convergence"])
+
+
+@pytest.mark.gpu
+def test_slab_ekman_option_matches_the_reference_component(gold):
+    from climt_b200.slab_surface import SlabSurface
+    tend, diag = SlabSurface(include_ekman=True, equatorial_ekman_cap_latitude=4.0).array_call(_ekman_in(gold))
+    _check_ekman(tend, diag, gold)
 
 
 @pytest.mark.gpu

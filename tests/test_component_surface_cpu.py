@@ -52,12 +52,16 @@ def test_constructor_keywords_and_defaults(name):
         assert mine[k] == v, (name, k, mine[k], v)
 
 
-@pytest.mark.parametrize("name", [n for n in sorted(REF) if "instances" not in REF[n]])
+def test_slab_surface_with_ekman_option():
+    _compare(_cls("SlabSurface")(include_ekman=True), REF["SlabSurface"]["instances"]["ekman"], "SlabSurface[ekman]")
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(REF) if not n.startswith("Cork")])
 def test_class_level_properties(name):
     _compare(_cls(name), REF[name], name)
 
 
-@pytest.mark.parametrize("name,label", [(n, lab) for n in sorted(REF) if "instances" in REF[n] for lab in sorted(REF[n]["instances"])])
+@pytest.mark.parametrize("name,label", [(n, lab) for n in sorted(REF) if n.startswith("Cork") for lab in sorted(REF[n]["instances"])])
 def test_cork_instance_properties(monkeypatch, name, label):
     """CORK properties depend on the optics mode and on the table class; constructing a drop-in creates an engine, so the native
     create calls are stubbed out here (no GPU in the CPU suite)"""
