@@ -26,6 +26,12 @@ static void run_transfer(const Tables& T, const Solar& sol, const In& in, const 
   }
 }
 
+// development hook (tools/adding_scan_study.py): when set, the per-g-point scratch rows [112][NSCR][nlay][ncol] of the last run are
+// copied here after the transfer pass
+static double* g_scr_export = nullptr;
+extern "C" void emul_sw_export_scratch(double* dst) { g_scr_export = dst; }
+extern "C" int emul_sw_nscr() { return NSCR; }
+
 // scal = {adjes, scon, solcycfrac, indsolvar0, indsolvar1, bndsolvar[14]}; iopt = {icld, iaer, inflag, iceflag, liqflag, isolvar, dyofyr, mcica, irng, permuteseed}
 extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* iopt, const double* scal, int ncol, int nlay,
                            const double* const* inp /*29 pointers in struct In order*/, double* const* outp /*6*/) {
@@ -86,6 +92,7 @@ extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* 
       else if (un.u == 1) run_transfer<1>(T, sol, in, fl, W, ncol, un.band - 16, un.g0, k2, mc);
       else run_transfer<2>(T, sol, in, fl, W, ncol, un.band - 16, un.g0, k2, mc);
     }
+    if (g_scr_export) std::memcpy(g_scr_export, scr.data(), scr.size() * sizeof(double));
     for (int c = 0; c < ncol; ++c)
       for (int lev = 0; lev <= nlay; ++lev) sw_reduce_level(W, units, nunits, nlay, 0, c, lev, ncol, out);
     for (int c = 0; c < ncol; ++c)
