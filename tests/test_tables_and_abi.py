@@ -80,3 +80,14 @@ def test_product_does_not_import_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
                 assert not re.search(r'#include\s+"[^"]*oracle/', txt), f
                 assert "liborc" not in txt, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/climt_b200.h must compile as C99 (no C++-isms, no torch / CUDA types)"""
+    import subprocess
+    src = tmp_path / "h.c"
+    src.write_text('#include "climt_b200.h"\nint main(void) { return 0; }\n')
+    inc = os.path.join(os.path.dirname(H.HERE), "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    hdr = open(os.path.join(inc, "climt_b200.h")).read()
+    assert "torch" not in hdr and "cudaStream_t" not in hdr.replace("a cudaStream_t", "").replace("(a cudaStream_t", "")
