@@ -295,7 +295,8 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     # bytes the engines actually moved (arrays the option flags make dead -- direct cloud optics under inflag=2, SW aerosol
-    # arrays under iaer=0 -- are not transferred), counted by the engines from the copies they issue
+    # arrays under iaer=0 -- are not transferred, and inputs that are zero everywhere in a chunk -- this state's aerosol optical
+    # depth and cloud arrays -- are set by a device memset), counted by the engines from the copies they issue
     (h2d_lw, d2h_lw), (h2d_sw, d2h_sw) = eng.last_transfer_bytes, engs.last_transfer_bytes
     h2d, d2h = h2d_lw + h2d_sw, d2h_lw + d2h_sw
 
