@@ -327,7 +327,10 @@ def main():
                        "cache": "working set per step (per-g-point scratch rows > 10 GB, inputs 0.2 GB) exceeds the 126 MB L2: nothing survives between timed iterations",
                        "parallelism": f"columns block-sharded over {world} GPU(s), one all-gather of outputs"},
             "e2e": {"value": world * NCOL * K / (e2e_ms * 1e-3), "unit": "columns/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
+                    "d2h_bytes_per_step": d2h,
+                    "note": "host-pointer C ABI, pinned buffers; bytes as counted by the engines: inputs that are zero everywhere "
+                            "(this clear-sky state's aerosol optical depth and cloud arrays) are scanned on the host inside the "
+                            "timed region and set by a device memset instead of being copied"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
