@@ -233,3 +233,54 @@ def test_reference_named_symbols_top_down_in_place():
     _assert_close(u[::-1], ref_n["eastward_wind"], "u")
     _assert_close(precl, ref_d["stratiform_precipitation_rate"], "precl")
     _assert_close(np.where(lath < 0, 0, lath), ref_d["surface_upward_latent_heat_flux"], "lath")
+
+
+def test_boundary_layer_sweeps_solve_the_tridiagonal_system_they_claim():
+    """The Fortran's forward / backward sweeps (simple_physics_custom.f90:470-520) are a Thomas solve of
+    -CA(k) x(k+1) + (1 + CA(k) + CC(k)) x(k) - CC(k) x(k-1) = x_old(k).  Here the same system is assembled as a dense matrix from
+    the state after the surface-flux step and handed to numpy.linalg.solve: an independent check of the sweep algebra (indices,
+    elimination factors, the theta <-> T conversion) in both the oracle and the kernel code."""
+    st = random_state(30, 16, 33, saturated=False)
+    opts = dict(large_scale_condensation=False)
+    K = OS.constants(OS.DEFAULTS, C)
+    _, base = OS.component_call(st, DT, C, boundary_layer=False, **opts)       # state at the entry of the boundary-layer step
+    _, full = OS.component_call(st, DT, C, **opts)
+    emul = H.run_simple_physics_emul(st, DT, _params(opts))
+    flip = lambda a: np.asarray(a)[::-1]                                        # noqa: E731  top-down, as the Fortran indexes
+    pmid, pint = flip(st["air_pressure"]), flip(st["air_pressure_on_interface_levels"])
+    nlev, ncol = pmid.shape
+    t0 = flip(st["air_temperature"])
+    q0 = flip(st["specific_humidity"])
+    zvir = K["rh2o"] / K["rair"] - 1.0
+    za = K["rair"] / K["gravit"] * t0[-1] * (1.0 + zvir * q0[-1]) * 0.5 * (np.log(st["surface_air_pressure"]) - np.log(pint[nlev - 1]))
+    wind = np.hypot(st["eastward_wind"][0], st["northward_wind"][0])
+    Ke_s = K["C"] * wind * za
+    Km_s = np.where(wind < 20.0, (K["Cd0"] + K["Cd1"] * wind) * wind * za, K["Cm"] * wind * za)
+    taper = np.where(pint >= K["pbltop"], 1.0, np.exp(-(K["pbltop"] - pint) ** 2 / K["pblconst"] ** 2))
+    tb = flip(base["air_temperature"])
+    kap = K["rair"] / K["cpair"]
+    for name, Ksfc, to_x, from_x in (("specific_humidity", Ke_s, None, None), ("eastward_wind", Km_s, None, None),
+                                     ("air_temperature", Ke_s, (100000.0 / pmid) ** kap, (pmid / 100000.0) ** kap)):
+        x_old = flip(base[name]) * (to_x if to_x is not None else 1.0)
+        want = np.zeros_like(x_old)
+        for c in range(ncol):
+            A = np.zeros((nlev, nlev))
+            for k in range(nlev):
+                ca = cc = 0.0
+                if k < nlev - 1:
+                    rho = pint[k + 1, c] / (K["rair"] * (tb[k + 1, c] + tb[k, c]) / 2.0)
+                    ca = DT * K["gravit"] ** 2 * Ksfc[c] * taper[k + 1, c] * rho ** 2 / ((pmid[k + 1, c] - pmid[k, c]) * (pint[k + 1, c] - pint[k, c]))
+                    A[k, k + 1] = -ca
+                if k > 0:
+                    rho = pint[k, c] / (K["rair"] * (tb[k, c] + tb[k - 1, c]) / 2.0)
+                    cc = DT * K["gravit"] ** 2 * Ksfc[c] * taper[k, c] * rho ** 2 / ((pmid[k, c] - pmid[k - 1, c]) * (pint[k + 1, c] - pint[k, c]))
+                    A[k, k - 1] = -cc
+                A[k, k] = 1.0 + ca + cc
+            want[:, c] = np.linalg.solve(A, x_old[:, c])
+        if from_x is not None:
+            want = want * from_x
+        scale = float(np.abs(want).max())
+        np.testing.assert_allclose(flip(full[name]), want, rtol=1e-10, atol=1e-12 * scale, err_msg=name)
+        key = {"specific_humidity": "q", "eastward_wind": "u", "air_temperature": "t"}[name]
+        np.testing.assert_allclose(emul[key][::-1], want, rtol=1e-10, atol=1e-12 * scale, err_msg=name + " (kernel code)")
+    assert np.abs(full["eastward_wind"] - base["eastward_wind"]).max() > 0.05     # the diffusion did something
