@@ -165,7 +165,7 @@ def _shipped_files():
     for dp, dn, files in os.walk(DATA_DIR):
         dn[:] = [d for d in dn if d != "_cache"]
         for f in sorted(files):
-            if f != "MANIFEST.json" and not f.endswith(".cb2k"):
+            if f != "MANIFEST.json":
                 out.append(os.path.relpath(os.path.join(dp, f), DATA_DIR))
     return sorted(out)
 
@@ -180,7 +180,7 @@ def build_manifest():
         man["files"][rel] = {"sha256": file_sha256(os.path.join(DATA_DIR, rel)), "bytes": os.path.getsize(os.path.join(DATA_DIR, rel))}
     cork_dir = os.path.join(DATA_DIR, "cork")
     for f in sorted(os.listdir(cork_dir)):
-        if f.endswith((".npz", ".nc")):
+        if f.endswith((".npz", ".nc", ".cb2k")):
             t = load_k_table(os.path.join(cork_dir, f))
             k = np.asarray(t["k_coefficients"])
             man["k_tables"][f] = {"content_sha256": content_sha256(ktable_to_container_arrays(t)), "k_shape": list(k.shape),

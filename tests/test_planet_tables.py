@@ -1,7 +1,8 @@
 """Every correlated-k table class the reference ships -- Mars / Venus (H2O axis over a premixed background), Titan and
 TRAPPIST-1e hab2 (fully premixed, 5-D), TRAPPIST-1e hab1 (premixed with an H2O axis, "effective" gas), the grey per-gas fixture --
 through `optics="correlated_k"`: golden vectors produced by the reference's own component classes on the reference's own NetCDF
-tables (tests/golden/make_planet_golden.py), which this package ships unchanged.
+tables (tests/golden/make_planet_golden.py), which this package ships converted to its own container (`.cb2k`, same arrays
+and dtypes: climt_b200/table_store.py).
 CPU: the oracle (table classification + glue of oracle/cork.py, kernels of cork_oracle.cpp) against the goldens.
 GPU: the drop-in components against the goldens.  Tolerance 1e-6 relative (BASELINE.json); asserted at 1e-9 of the flux scale
 (observed ~1e-11); heating rates are compared as the flux divergence they come from (tendency x dp x cp / g), because a thin
