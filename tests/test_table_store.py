@@ -33,33 +33,61 @@ def test_container_round_trip_and_alignment(tmp_path):
         TS.read_container(str(tmp_path / "bad.cb2k"))
 
 
+def _write_reference_formats(table, stem):
+    """the table as the reference would hold it on disk: `.npz` (scripts/convert_ck_table_to_npz.py) and NetCDF-3 `.nc`
+    (scripts/cork_table_builder/netcdf_writer.py: one dimension per axis, text attributes, gas names as an attribute)"""
+    from scipy.io import netcdf_file
+    np.savez(stem + ".npz", **table)
+    with netcdf_file(stem + ".nc", "w") as nc:
+        for name in TS.K_TABLE_ARRAYS:
+            if name in table and table[name] is not None:
+                a = np.asarray(table[name])
+                dims = []
+                for i, n in enumerate(a.shape):
+                    d = f"{name}_d{i}"
+                    nc.createDimension(d, n)
+                    dims.append(d)
+                v = nc.createVariable(name, a.dtype.char, tuple(dims))
+                v[:] = a
+        nc.gas_names = ",".join(str(g) for g in table["gas_names"]) if "gas_names" in table else "effective"
+        for name in TS.K_TABLE_TEXT:
+            if name in table:
+                setattr(nc, name, str(np.asarray(table[name])))
+    return stem + ".npz", stem + ".nc"
+
+
 @pytest.mark.parametrize("name", SHIPPED)
 def test_converted_table_equals_the_reference_format_table(tmp_path, name):
-    src = cork.load_k_table(name)
-    dst = TS.convert_k_table(name, str(tmp_path / f"{name}.cb2k"))
-    back = cork.load_k_table(dst)                                   # load_k_table reads the container too
-    assert np.asarray(back["k_coefficients"]).dtype == np.asarray(src["k_coefficients"]).dtype   # float32 tables stay float32
-    for k in TS.K_TABLE_ARRAYS:
-        assert (k in src and src[k] is not None) == (k in back), k
-        if k in back:
-            np.testing.assert_array_equal(back[k], src[k])
-            if np.asarray(src[k]).dtype.kind == "f":
-                assert np.asarray(back[k]).dtype == np.asarray(src[k]).dtype, k   # the reference's float32 products depend on it
-    assert cork.table_flags(back) == cork.table_flags(src)
-    raw = TS.read_container(dst)
-    _, _, _, fully, bg = cork.table_flags(src)
-    assert int(raw["_premixed"][0]) == int(fully or bg) and int(raw["_co2_logk"][0]) == 1 and int(raw["_overlap_additive"][0]) == 1
-    # the content digest does not depend on the container the table came from
-    assert TS.content_sha256(TS.ktable_to_container_arrays(back)) == TS.content_sha256(TS.ktable_to_container_arrays(src))
+    """reference formats -> container: arrays, dtypes and the classification survive, whichever format the table came in"""
+    shipped = cork.load_k_table(name)                                # the shipped tables are containers themselves
+    for src_path in _write_reference_formats(shipped, str(tmp_path / name)):
+        src = cork.load_k_table(src_path)
+        dst = TS.convert_k_table(src_path, str(tmp_path / (name + "_out.cb2k")))
+        back = cork.load_k_table(dst)                                # load_k_table reads the container too
+        assert np.asarray(back["k_coefficients"]).dtype == np.asarray(src["k_coefficients"]).dtype   # float32 tables stay float32
+        for k in TS.K_TABLE_ARRAYS:
+            assert (k in src and src[k] is not None) == (k in back), k
+            if k in back:
+                np.testing.assert_array_equal(back[k], src[k])
+                np.testing.assert_array_equal(back[k], shipped[k])
+                if np.asarray(src[k]).dtype.kind == "f":
+                    assert np.asarray(back[k]).dtype == np.asarray(src[k]).dtype, k   # the reference's float32 products depend on it
+        assert cork.table_flags(back) == cork.table_flags(src) == cork.table_flags(shipped)
+        raw = TS.read_container(dst)
+        _, _, _, fully, bg = cork.table_flags(src)
+        assert int(raw["_premixed"][0]) == int(fully or bg) and int(raw["_co2_logk"][0]) == 1 and int(raw["_overlap_additive"][0]) == 1
+        # the content digest does not depend on the container the table came from
+        assert TS.content_sha256(TS.ktable_to_container_arrays(back)) == TS.content_sha256(TS.ktable_to_container_arrays(shipped))
 
 
 def test_manifest_pins_every_shipped_and_derived_table():
     assert TS.verify_manifest() == []
     man = TS.build_manifest()
-    assert set(f"{n}.npz" for n in SHIPPED) <= set(man["k_tables"])
-    assert man["k_tables"]["earth_low_res_lw.npz"]["k_shape"] == [1, 14, 8, 12, 8, 7, 10]
-    assert man["k_tables"]["earth_low_res_lw.npz"]["k_dtype"] == "float32"
-    assert {"rrtmg_lw_raw.npz", "rrtmg_sw_raw.npz", "ozone_profile.npy"} <= set(man["files"])
+    assert set(f"{n}.cb2k" for n in SHIPPED) <= set(man["k_tables"])
+    assert {"mars_lw.cb2k", "titan_sw.cb2k", "trappist1e_hab1_lw.cb2k"} <= set(man["k_tables"])
+    assert man["k_tables"]["earth_low_res_lw.cb2k"]["k_shape"] == [1, 14, 8, 12, 8, 7, 10]
+    assert man["k_tables"]["earth_low_res_lw.cb2k"]["k_dtype"] == "float32"
+    assert {"rrtmg_lw_raw.npz", "rrtmg_sw_raw.npz", "ozone_profile.npy", "berger1978.npz"} <= set(man["files"])
     assert man["derived"]["rrtmg_lw_reduced"]["arrays"] > 100
 
 
@@ -67,15 +95,14 @@ def test_manifest_detects_a_changed_table(tmp_path, monkeypatch):
     import shutil
     d = tmp_path / "data"
     shutil.copytree(TS.DATA_DIR, d, ignore=shutil.ignore_patterns("_cache"))
-    with np.load(d / "cork" / "test_2band_lw.npz", allow_pickle=True) as z:
-        t = {k: z[k] for k in z.files}
-    t["k_coefficients"] = t["k_coefficients"] * 1.0000001
-    np.savez(d / "cork" / "test_2band_lw.npz", **t)
+    t = TS.read_container(str(d / "cork" / "test_2band_lw.cb2k"))
+    t["k_coefficients"] = (t["k_coefficients"] * 1.0000001).astype(t["k_coefficients"].dtype)
+    TS.write_container(str(d / "cork" / "test_2band_lw.cb2k"), t)
     monkeypatch.setattr(TS, "DATA_DIR", str(d))
     monkeypatch.setattr(TS, "MANIFEST", str(d / "MANIFEST.json"))
     monkeypatch.setattr(cork, "_DATA", str(d / "cork"))
     bad = TS.verify_manifest()
-    assert any("k_tables/test_2band_lw.npz" in b for b in bad) and any("files/cork/test_2band_lw.npz" in b for b in bad)
+    assert any("k_tables/test_2band_lw.cb2k" in b for b in bad) and any("files/cork/test_2band_lw.cb2k" in b for b in bad)
     assert not any("earth_low_res" in b for b in bad)
 
 
