@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("CLIMT_B200_SO") or os.path.join(_HERE, "libclimt_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lw_engine.cu", "sw_engine.cu", "gray_engine.cu", "cork_engine.cu", "marshal.cu", "emanuel_engine.cu", "adjacent_engine.cu", "simple_physics.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("cb_common.h", "engine_common.h", "lw_core.cuh", "lw_tables.h", "sw_core.cuh", "sw_tables.h",
-                                                          "mcica_core.cuh", "mcica_host.h", "cork_core.cuh", "cork_tables.h", "emanuel_core.cuh", "simple_physics_core.cuh")] + [
+                                                          "mcica_core.cuh", "mcica_host.h", "mcica_compat.h", "cork_core.cuh", "cork_tables.h", "emanuel_core.cuh", "simple_physics_core.cuh")] + [
     os.path.join(_HERE, "..", "include", "climt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "--fmad=true"]
@@ -73,7 +73,8 @@ class SwInputs(ctypes.Structure):
         "cicewp", "cliqwp", "reice", "reliq", "tauaer", "ssaaer", "asmaer", "ecaer")]
 
 
-EXPORTS = ["cb200_berger_scalars", "cb200_berger_run_device", "cb200_berger_run_host", "cb200_simple_physics_run_device", "cb200_simple_physics_run_host", "set_fortran_constants", "simple_physics",
+EXPORTS = ["mcica_subcol_lw_wrapper", "rrtmg_lw_mcica_wrapper", "mcica_subcol_sw_wrapper", "rrtmg_sw_mcica_wrapper",
+           "cb200_lw_set_derivative_outputs", "cb200_berger_scalars", "cb200_berger_run_device", "cb200_berger_run_host", "cb200_simple_physics_run_device", "cb200_simple_physics_run_host", "set_fortran_constants", "simple_physics",
            "cb200_cork_create_from_file", "cb200_instellation_orbit", "cb200_instellation_run_device", "cb200_instellation_run_host", "cb200_slab_surface_run_device",
            "cb200_slab_surface_run_host", "cb200_emanuel_create", "cb200_emanuel_destroy", "cb200_emanuel_last_error", "cb200_emanuel_last_launches", "cb200_emanuel_enable_timing",
            "cb200_emanuel_last_kernel_ms", "cb200_emanuel_run_device", "cb200_emanuel_run_host", "init_emanuel_convection_fortran", "emanuel_convection",
@@ -108,6 +109,7 @@ def lib():
     L.cb200_lw_destroy.restype = None
     L.cb200_lw_set_options.argtypes = [vp] + [ctypes.c_int] * 5
     L.cb200_lw_set_mcica.argtypes = [vp] + [ctypes.c_int] * 3
+    L.cb200_lw_set_derivative_outputs.argtypes = [vp, _dp, _dp]
     L.cb200_lw_run_device.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(LwInputs),
                                       ctypes.POINTER(LwOutputs), vp]
     L.cb200_lw_run_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(LwInputs),

@@ -62,6 +62,7 @@ struct In {  // reference ABI layout: (nlay[+1], ncol) column-fastest; emis (16,
 };
 struct Out {
   double *uflx, *dflx, *hr, *uflxc, *dflxc, *hrc;
+  double *duflx_dt = nullptr, *duflxc_dt = nullptr;  // idrv = 1: d(upward flux)/d(surface temperature), (nlay+1, ncol)
 };
 struct Flags {
   int icld, idrv, inflag, iceflag, liqflag;
@@ -76,7 +77,8 @@ struct Work {  // all sized for a chunk of ncc columns
   double* pwvcm; // [ncc]
   double* cld;   // [2][16][nlay][ncc]  odcld, efclfrac
   double* scr;   // [140][NSCR][nlay][ncc] atrans, bbugas, atot, bbutot, taug, fracs
-  double* part;  // [nunits][4][nlay+1][ncc] up, dn, upclr, dnclr  (un-weighted sums over the unit's g-points)
+  double* part;  // [nunits][npart][nlay+1][ncc] up, dn, upclr, dnclr [, d_up, d_upclr]  (un-weighted sums over the unit's g-points)
+  int npart;     // 4, or 6 with the surface-temperature derivative of the upward flux (idrv = 1)
   double* ovl;   // [14][nlay+2][ncc] maximum-random overlap factors of rtrnmr (OV_* rows), non-McICA icld = 2, 3 only
   unsigned* mask; // [nlay][5][mstride] McICA cloud mask (+ moff), bit (g & 31) of word (g >> 5) set = sub-column g cloudy
   int mstride, moff;
@@ -1004,7 +1006,9 @@ CB_HD void lw_taumol_unit(const Tables& T, const In& in, const Work& W, int c0, 
 
 // rtrn / rtrnmc for U consecutive g-points of band ib (0-based) -- generic in the band (rrtmg_lw_rtrn.f90:300-557)
 // MR: maximum-random overlap of the fractional clouds (rtrnmr, rrtmg_lw_rtrnmr.f90:481-700) instead of rtrn's random overlap.
-template <int U, bool MC, bool MR = false>
+// DRV: also the derivative of the upward flux with respect to the surface temperature (idrv = 1, rtrn.f90:458-461,473-476,
+// 492-512; the same lines in rtrnmc.f90:447-510 and rtrnmr.f90:629-711): one more multiplicative recurrence in the up sweep.
+template <int U, bool MC, bool MR = false, bool DRV = false>
 CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int ib, int g0, int unit) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
@@ -1036,7 +1040,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
 #pragma unroll
   for (int u = 0; u < U; ++u) { radld[u] = 0.; radclrd[u] = 0.; frac1[u] = 0.; }
   int iclddn = 0;
-  double* __restrict__ part = W.part + (size_t)unit * 4 * (nlay + 1) * ncc + c;
+  double* __restrict__ part = W.part + (size_t)unit * W.npart * (nlay + 1) * ncc + c;
   const size_t pstride = (size_t)(nlay + 1) * ncc;
   double plev_up = planck_band(tp, in.tlev[(size_t)nlay * ncol + gc]);  // planklev(nlay)
   // The loads of a layer do not depend on the recurrence: fetch layer lev-1 while layer lev is computed (the kernel's top
@@ -1225,8 +1229,11 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
   const double plankbnd = semiss * planck_band(tp, tbound);
   const double reflect = 1. - semiss;
   double radlu[U], radclru[U];
+  double d_radlu[U], d_radclru[U];  // DRV
   {
-    double s = 0., sc = 0.;
+    double s = 0., sc = 0., sd = 0.;
+    // dplankbnd_dt (setcoef.f90:197-200): the same 1-K table interpolation on totplnkderiv
+    const double dplankbnd_dt = DRV ? semiss * planck_band(tb + T.totplnkderiv + (size_t)ib * 181, tbound) : 0.;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const double rad0 = frac1[u] * plankbnd;
@@ -1234,9 +1241,16 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       radclru[u] = rad0 + reflect * radclrd[u];
       s = s + radlu[u];
       sc = sc + radclru[u];
+      d_radlu[u] = frac1[u] * dplankbnd_dt;
+      d_radclru[u] = d_radlu[u];
+      sd = sd + d_radlu[u];
     }
     part[0] = s;
     if (ncb > 0) part[2 * pstride] = sc;
+    if (DRV) {
+      part[4 * pstride] = sd;
+      if (ncb > 0) part[5 * pstride] = sd;
+    }
   }
   // upward sweep (rtrn.f90:478-521), the (atrans, bbugas) rows of the next layer fetched one layer ahead
   struct UpIn {
@@ -1288,7 +1302,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       ov_cld1 = ov[OV_CLD1 * ovs]; ov_cld2 = ov[OV_CLD2 * ovs]; ov_clr1 = ov[OV_CLR1 * ovs]; ov_clr2 = ov[OV_CLR2 * ovs];
       ov_cmb1 = ov[OV_CMB1 * ovs]; ov_cmb2 = ov[OV_CMB2 * ovs];
     }
-    double s = 0., sc = 0.;
+    double s = 0., sc = 0., sd = 0., sdc = 0.;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const bool on = !MC || ((mbits >> u) & 1u);
@@ -1298,6 +1312,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       if (cloudy) {
         const double atot = scr[2 * wstride], bbutot = scr[3 * wstride];
         const double gassrc = bbugas * atrans;
+        if (DRV) d_radlu[u] = d_radlu[u] * cldfrac * (1.0 - atot) + d_radlu[u] * (1.0 - cldfrac) * (1.0 - atrans);
         if (MR) {
           // rtrnmr.f90:655-677
           if (ov_ist == 1.) {
@@ -1321,17 +1336,25 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
         }
       } else {
         radlu[u] = radlu[u] + (bbugas - radlu[u]) * atrans;
+        if (DRV) d_radlu[u] = d_radlu[u] * (1.0 - atrans);
       }
       s = s + radlu[u];
       if (iclddn == 1) {
         radclru[u] = radclru[u] + (bbugas - radclru[u]) * atrans;
+        if (DRV) d_radclru[u] = d_radclru[u] * (1.0 - atrans);
       } else {
         radclru[u] = radlu[u];
+        if (DRV) d_radclru[u] = d_radlu[u];
       }
       sc = sc + radclru[u];
+      if (DRV) { sd = sd + d_radlu[u]; sdc = sdc + d_radclru[u]; }
     }
     part[(size_t)lev * ncc] = s;
     if (ncb > 0) part[2 * pstride + (size_t)lev * ncc] = sc;
+    if (DRV) {
+      part[4 * pstride + (size_t)lev * ncc] = sd;
+      if (ncb > 0) part[5 * pstride + (size_t)lev * ncc] = sdc;
+    }
   }
 }
 
@@ -1372,24 +1395,35 @@ CB_HD void lw_reduce_level(const Tables& T, const Work& W, const Unit* units, in
   const size_t pstride = (size_t)(nlay + 1) * ncc;
   const double wtdiff = 0.5;
   // cloud-free column: the clear-sky streams equal the total ones bit for bit and were not stored (lw_transfer_unit)
-  const int nq = W.ncbands[c] > 0 ? 4 : 2;
+  const bool cloudy_col = W.ncbands[c] > 0;
+  const int nq = cloudy_col ? 4 : 2;
+  const bool drv = out.duflx_dt != nullptr;
   double tot[4] = {0., 0., 0., 0.};
+  double dtot[2] = {0., 0.};
   for (int b = 1; b <= 16; ++b) {
     double bs[4] = {0., 0., 0., 0.};
+    double ds[2] = {0., 0.};
     for (int k = 0; k < nunits; ++k) {
       if (units[k].band != b) continue;
-      const double* p = W.part + (size_t)k * 4 * pstride + (size_t)lev * ncc + c;
+      const double* p = W.part + (size_t)k * W.npart * pstride + (size_t)lev * ncc + c;
       for (int q = 0; q < nq; ++q) bs[q] = bs[q] + p[q * pstride];
+      if (drv) {
+        ds[0] = ds[0] + p[4 * pstride];
+        if (cloudy_col) ds[1] = ds[1] + p[5 * pstride];
+      }
     }
     const double dw = CB_LDG(T.base + T.delwave + (b - 1));
     for (int q = 0; q < nq; ++q) tot[q] = tot[q] + (bs[q] * wtdiff) * dw;
+    // rtrn.f90:546-555: the derivative sums carry fluxfac band by band
+    if (drv) for (int q = 0; q < 2; ++q) dtot[q] = dtot[q] + ((ds[q] * wtdiff) * dw) * T.fluxfac;
   }
-  if (nq == 2) { tot[2] = tot[0]; tot[3] = tot[1]; }
+  if (nq == 2) { tot[2] = tot[0]; tot[3] = tot[1]; dtot[1] = dtot[0]; }
   const size_t o = (size_t)lev * ncol + (c0 + c);
   out.uflx[o] = tot[0] * T.fluxfac;
   out.dflx[o] = tot[1] * T.fluxfac;
   out.uflxc[o] = tot[2] * T.fluxfac;
   out.dflxc[o] = tot[3] * T.fluxfac;
+  if (drv) { out.duflx_dt[o] = dtot[0]; out.duflxc_dt[o] = dtot[1]; }
 }
 // heating rates (rtrn.f90:569-581)
 CB_HD void lw_heating(const Tables& T, const In& in, const Out& out, int gcol, int l) {

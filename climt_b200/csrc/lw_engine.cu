@@ -13,6 +13,7 @@
 #include "engine_common.h"
 #include "lw_tables.h"
 #include "mcica_host.h"
+#include "mcica_compat.h"
 
 using namespace cb::lw;
 
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kBlock, CB_LW_TAU_MIN_BLOCKS)
 }
 
 // rtrn / rtrnmc: one block = 128 adjacent columns x one unit (<= CB_LW_UMAX g-points of one band); one code body for all bands
-template <bool MC, bool MR>
+template <bool MC, bool MR, bool DRV = false>
 __global__ void __launch_bounds__(kBlock, CB_LW_RT_MIN_BLOCKS)
     k_units(const __grid_constant__ Tables T, const __grid_constant__ In in, const __grid_constant__ Work W,
             const __grid_constant__ UnitList UL, int c0, int n) {
@@ -87,9 +88,9 @@ __global__ void __launch_bounds__(kBlock, CB_LW_RT_MIN_BLOCKS)
   if (c >= n) return;
   const int k = blockIdx.y;
   const Unit un = UL.u[k];
-  if (CB_LW_UMAX >= 4 && un.u == 4) lw_transfer_unit<4, MC, MR>(T, in, W, c0, c, un.band - 1, un.g0, k);
-  else if (CB_LW_UMAX == 1) lw_transfer_unit<1, MC, MR>(T, in, W, c0, c, un.band - 1, un.g0, k);
-  else lw_transfer_unit<2, MC, MR>(T, in, W, c0, c, un.band - 1, un.g0, k);
+  if (CB_LW_UMAX >= 4 && un.u == 4) lw_transfer_unit<4, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, k);
+  else if (CB_LW_UMAX == 1) lw_transfer_unit<1, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, k);
+  else lw_transfer_unit<2, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, k);
 }
 
 // McICA cloud mask with the per-column kissvec generator: one thread per column
@@ -134,11 +135,14 @@ struct cb200_lw_engine {
   int irng = 1, permuteseed = 0;
   unsigned* d_mask_full = nullptr;
   size_t mask_full_cap = 0;
+  std::vector<unsigned> ext_mask;  // caller-supplied sub-column mask [nlay][5][ncol] (cb200_lw_set_subcolumn_mask), else empty
+  int ext_ncol = 0, ext_nlay = 0;
   UnitList UL;      // transfer kernel units (<= CB_LW_UMAX g-points); `part` holds one flux set per unit
   UnitList UL_tau;  // taumol kernel units (<= CB_LW_TAU_UMAX g-points)
   // workspace (grown on demand)
-  int cap_ncc = 0, cap_nlay = 0;
+  int cap_ncc = 0, cap_nlay = 0, cap_npart = 0;
   Work W{};
+  double *drv_up = nullptr, *drv_upc = nullptr;  // idrv = 1 outputs of the next run call (host or device pointers, like its outputs)
   int max_chunk = 16384;
   // host-pointer path
   cb::HostPipe pipe;
@@ -159,11 +163,12 @@ struct cb200_lw_engine {
     cudaFree(W.ws); cudaFree(W.idx); cudaFree(W.laytrop); cudaFree(W.ncbands); cudaFree(W.pwvcm);
     cudaFree(W.cld); cudaFree(W.scr); cudaFree(W.part); cudaFree(W.ovl); cudaFree(W.err); cudaFree(W.mask);
     W = Work{};
-    cap_ncc = cap_nlay = 0;
+    cap_ncc = cap_nlay = cap_npart = 0;
   }
   int ensure_work(int ncc, int nlay) {
     cb200_lw_engine* e = this;
-    if (ncc <= cap_ncc && nlay <= cap_nlay && W.ws) return 0;
+    const int npart = fl.idrv == 1 ? 6 : 4;
+    if (ncc <= cap_ncc && nlay <= cap_nlay && npart <= cap_npart && W.ws) { W.npart = npart; return 0; }
     free_work();
     const size_t n = (size_t)ncc, L = (size_t)nlay;
     CUDA_OK(cudaMalloc(&W.ws, sizeof(double) * NF * L * n));
@@ -173,7 +178,9 @@ struct cb200_lw_engine {
     CUDA_OK(cudaMalloc(&W.pwvcm, sizeof(double) * n));
     CUDA_OK(cudaMalloc(&W.cld, sizeof(double) * 32 * L * n));
     CUDA_OK(cudaMalloc(&W.scr, sizeof(double) * 140 * NSCR * L * n));
-    CUDA_OK(cudaMalloc(&W.part, sizeof(double) * UL.n * 4 * (L + 1) * n));
+    CUDA_OK(cudaMalloc(&W.part, sizeof(double) * UL.n * npart * (L + 1) * n));
+    W.npart = npart;
+    cap_npart = npart;
     CUDA_OK(cudaMalloc(&W.ovl, sizeof(double) * OV_NROWS * (L + 2) * n));
     CUDA_OK(cudaMalloc(&W.mask, sizeof(unsigned) * 5 * L * n));
     CUDA_OK(cudaMalloc(&W.err, sizeof(int)));
@@ -237,8 +244,17 @@ extern "C" void cb200_lw_destroy(cb200_lw_engine* e) {
 
 extern "C" int cb200_lw_set_options(cb200_lw_engine* e, int icld, int idrv, int inflag, int iceflag, int liqflag) {
   if (icld < 0 || icld > 3) icld = 2;  // rrtmg_lw_rad.nomcica.f90:437
-  if (idrv != 0) { e->error = "calculate_change_up_flux (idrv=1) is not implemented in the CUDA engine yet"; return -2; }
+  if (idrv != 0 && idrv != 1) { e->error = "idrv must be 0 or 1 (rrtmg_lw_rad.nomcica.f90:192)"; return -2; }
   e->fl = Flags{icld, idrv, inflag, iceflag, liqflag, e->fl.mcica};
+  return 0;
+}
+
+// idrv = 1 (calculate_change_up_flux): where the next run call writes d(upward flux)/d(surface temperature), total and clear
+// sky, (nlay+1, ncol) each -- duflx_dt / duflxc_dt of rrtmg_lw_c_binder.f90:176-256.  Host pointers for run_host, device
+// pointers for run_device, like that call's own outputs.  Cleared by passing nulls.
+extern "C" int cb200_lw_set_derivative_outputs(cb200_lw_engine* e, double* duflx_dt, double* duflxc_dt) {
+  e->drv_up = duflx_dt;
+  e->drv_upc = duflxc_dt;
   return 0;
 }
 
@@ -281,9 +297,16 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
   k_lw_taumol<<<dim3(gx, e->UL_tau.n, CB_LW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, in, W, e->UL_tau, c0, n);
   if (e->timing) cudaEventRecord(e->evm, st);
   // non-McICA: icld = 1 -> rtrn (random overlap); icld = 2, 3 -> rtrnmr (maximum-random), rrtmg_lw_rad.nomcica.f90:527-541
-  if (mc) k_units<true, false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
-  else if (e->fl.icld >= 2) k_units<false, true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
-  else k_units<false, false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+  const dim3 gu(gx, e->UL.n);
+  if (W.npart == 6) {
+    if (mc) k_units<true, false, true><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    else if (e->fl.icld >= 2) k_units<false, true, true><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    else k_units<false, false, true><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+  } else {
+    if (mc) k_units<true, false><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    else if (e->fl.icld >= 2) k_units<false, true><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    else k_units<false, false><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+  }
   if (e->timing) cudaEventRecord(e->ev1, st);
   k_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(e->T, W, e->UL, out, nlay, out_ncol, c0, n);
   k_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
@@ -303,7 +326,12 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
 // drawn on the host from the host copy of the cloud fraction and uploaded once, [lay][word][ncol].
 static int upload_mt_mask(cb200_lw_engine* e, const double* h_cldfr, int ncol, int nlay, cudaStream_t st) {
   std::vector<unsigned> h_mask;
-  cb::mcica::mask_mt_host(h_cldfr, ncol, nlay, 140, 5, e->fl.icld, e->permuteseed, h_mask);
+  if (!e->ext_mask.empty()) {
+    if (e->ext_ncol != ncol || e->ext_nlay != nlay) { e->error = "sub-column mask was set for a different ncol/nlay"; return -3; }
+    h_mask = e->ext_mask;
+  } else {
+    cb::mcica::mask_mt_host(h_cldfr, ncol, nlay, 140, 5, e->fl.icld, e->permuteseed, h_mask);
+  }
   if (h_mask.size() > e->mask_full_cap) {
     cudaFree(e->d_mask_full);
     e->d_mask_full = nullptr;
@@ -328,6 +356,11 @@ extern "C" int cb200_lw_run_device(cb200_lw_engine* e, int ncol, int nlay, const
   W.ncc = chunk;
   const In in = make_in(ncol, nlay, pin);
   Out out{pout->uflx, pout->dflx, pout->hr, pout->uflxc, pout->dflxc, pout->hrc};
+  if (e->fl.idrv == 1) {
+    if (!e->drv_up || !e->drv_upc) { e->error = "idrv = 1 needs cb200_lw_set_derivative_outputs before the run call"; return -3; }
+    out.duflx_dt = e->drv_up;
+    out.duflxc_dt = e->drv_upc;
+  }
   e->launches = 0;
   e->unit_ms = 0.0;
   e->taumol_ms = 0.0;
@@ -381,7 +414,10 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
   int inner[23];
   for (int i = 0; i < 23; ++i) inner[i] = 1;
   inner[17] = 16;  // taucld(nbndlw, ncol, nlay): band-fastest
-  const int orows[6] = {L + 1, L + 1, L, L + 1, L + 1, L};
+  const bool drv = e->fl.idrv == 1;
+  if (drv && (!e->drv_up || !e->drv_upc)) { e->error = "idrv = 1 needs cb200_lw_set_derivative_outputs before the run call"; return -3; }
+  const int nout = drv ? 8 : 6;
+  const int orows[8] = {L + 1, L + 1, L, L + 1, L + 1, L, L + 1, L + 1};
   bool used[23];
   for (int i = 0; i < 23; ++i) used[i] = true;
   const bool clouds = e->fl.icld >= 1;
@@ -397,14 +433,17 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
   for (int i = 0; i < 23; ++i) zero[i] = false;
   size_t irow_tot = 0, orow_tot = 0;
   for (int i = 0; i < 23; ++i) if (used[i]) irow_tot += (size_t)irows[i] * inner[i];
-  for (int i = 0; i < 6; ++i) orow_tot += (size_t)orows[i];
+  for (int i = 0; i < nout; ++i) orow_tot += (size_t)orows[i];
   e->h2d_bytes = 0;
   e->d2h_bytes = orow_tot * (size_t)ncol * sizeof(double);
   int chunk = ncol < P.chunk ? ncol : P.chunk;
   const int wchunk = (chunk + kBlock - 1) / kBlock * kBlock;
   if (e->ensure_work(wchunk, nlay)) return -1;
   CUDA_OK(P.ensure(irow_tot * (size_t)chunk, orow_tot * (size_t)chunk));
-  double* const* hop = reinterpret_cast<double* const*>(hout);
+  double* hop[8];
+  for (int i = 0; i < 6; ++i) hop[i] = reinterpret_cast<double* const*>(hout)[i];
+  hop[6] = e->drv_up;
+  hop[7] = e->drv_upc;
   Work W = e->W;
   W.ncc = wchunk;
   W.mstride = wchunk;
@@ -459,23 +498,24 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
     }
     CUDA_OK(cudaEventRecord(P.in_done[s], P.s_in));
     P.mark(P.s_in, k, 1);
-    cb200_lw_outputs dout;
-    double** dop = reinterpret_cast<double**>(&dout);
+    double* dop[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     off = 0;
-    for (int i = 0; i < 6; ++i) { dop[i] = P.d_out[s] + off; off += (size_t)orows[i] * n; }
+    for (int i = 0; i < nout; ++i) { dop[i] = P.d_out[s] + off; off += (size_t)orows[i] * n; }
     // compute: inputs landed, and the output slot has been drained
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.in_done[s], 0));
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.out_done[s], 0));
     P.mark(P.s_cmp, k, 2);
     const In in = make_in(n, nlay, &din);
-    Out out{dout.uflx, dout.dflx, dout.hr, dout.uflxc, dout.dflxc, dout.hrc};
+    Out out{dop[0], dop[1], dop[2], dop[3], dop[4], dop[5]};
+    out.duflx_dt = dop[6];
+    out.duflxc_dt = dop[7];
     if (mc && e->irng == 1) W.moff = c0;
     if (launch_chunk(e, in, out, W, 0, n, n, mc, P.s_cmp)) return -1;
     CUDA_OK(cudaEventRecord(P.cmp_done[s], P.s_cmp));
     P.mark(P.s_cmp, k, 3);
     // D2H
     CUDA_OK(cudaStreamWaitEvent(P.s_out, P.cmp_done[s], 0));
-    for (int i = 0; i < 6; ++i) CUDA_OK(P.scatter(hop[i], dop[i], orows[i], ncol, c0, n));
+    for (int i = 0; i < nout; ++i) CUDA_OK(P.scatter(hop[i], dop[i], orows[i], ncol, c0, n));
     CUDA_OK(cudaEventRecord(P.out_done[s], P.s_out));
     P.mark(P.s_out, k, 4);
   }
@@ -501,9 +541,15 @@ extern "C" int cb200_lw_run_host_async(cb200_lw_engine* e, int ncol, int nlay, c
 extern "C" int cb200_lw_wait(cb200_lw_engine* e) {
   if (!e->host_pending) return 0;
   e->host_pending = false;
-  if (e->enqueue.valid())
-    if (int rc = e->enqueue.get()) return rc;
+  int rc = 0;
+  if (e->enqueue.valid()) rc = e->enqueue.get();
   CUDA_OK(cudaSetDevice(e->device));
+  if (rc) {
+    // the chunk loop failed half-way: chunks already enqueued still copy from / into the caller's buffers -- drain them
+    // before the caller is told (and frees or reuses those buffers)
+    if (e->pipe.s_in) { cudaStreamSynchronize(e->pipe.s_in); cudaStreamSynchronize(e->pipe.s_cmp); cudaStreamSynchronize(e->pipe.s_out); }
+    return rc;
+  }
   CUDA_OK(cudaStreamSynchronize(e->pipe.s_out));
   e->pipe.trace_dump("LW");
   return cb200_lw_check(e);
@@ -512,7 +558,10 @@ extern "C" int cb200_lw_wait(cb200_lw_engine* e) {
 extern "C" int cb200_lw_run_host(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* hin,
                                  const cb200_lw_outputs* hout) {
   if (e->host_pending) { e->error = "a previous run_host_async call has not been waited for"; return -3; }
-  if (int rc = lw_host_enqueue(e, ncol, nlay, hin, hout)) return rc;
+  if (int rc = lw_host_enqueue(e, ncol, nlay, hin, hout)) {
+    if (e->pipe.s_in) { cudaStreamSynchronize(e->pipe.s_in); cudaStreamSynchronize(e->pipe.s_cmp); cudaStreamSynchronize(e->pipe.s_out); }
+    return rc;
+  }
   e->host_pending = true;
   return cb200_lw_wait(e);
 }
@@ -552,9 +601,31 @@ extern "C" void rrtmg_lw_ini_wrapper(double* cpdair) {
   if (g_engine) { cb200_lw_destroy(g_engine); g_engine = nullptr; }
   int dev = 0;
   if (const char* d = std::getenv("CLIMT_B200_DEVICE")) dev = std::atoi(d);
-  if (cb200_lw_create(&g_engine, default_blob().c_str(), g_consts, dev))
+  if (cb200_lw_create(&g_engine, default_blob().c_str(), g_consts, dev)) {
     std::fprintf(stderr, "climt_b200: rrtmg_lw_ini_wrapper failed: %s\n", cb200_global_error());
+    g_engine = nullptr;  // every later wrapper call NaN-fills its outputs and reports
+  }
 }
+
+// The reference wrappers are void and the Fortran under them ends the process with `stop` on invalid input.  Ending the
+// caller's interpreter is not acceptable for a library, returning stale buffers is worse: on ANY failure every output array
+// is filled with NaN, the message goes to stderr and stays readable through cb200_global_error().
+namespace {
+void lw_wrapper_fail(const std::string& msg, int ncol, int nlay, double* uflx, double* dflx, double* hr, double* uflxc,
+                     double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt, bool derivs) {
+  std::fprintf(stderr, "climt_b200: %s\n", msg.c_str());
+  cb::set_global_error(msg);
+  const size_t n1 = (size_t)ncol * (nlay + 1), n0 = (size_t)ncol * nlay;
+  cb::mcica::nan_fill(uflx, n1); cb::mcica::nan_fill(dflx, n1); cb::mcica::nan_fill(hr, n0);
+  cb::mcica::nan_fill(uflxc, n1); cb::mcica::nan_fill(dflxc, n1); cb::mcica::nan_fill(hrc, n0);
+  if (derivs) { cb::mcica::nan_fill(duflx_dt, n1); cb::mcica::nan_fill(duflxc_dt, n1); }
+}
+int lw_ngb(int g) {  // 0-based band of 0-based g-point g (ngb, rrtmg_lw_init.f90:306-311)
+  int b = 0;
+  while (b < 15 && g >= kGS[b + 1]) ++b;
+  return b;
+}
+}  // namespace
 
 extern "C" void rrtmg_lw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* idrv, double* play, double* plev,
                                          double* tlay, double* tlev, double* tsfc, double* h2ovmr, double* o3vmr,
@@ -564,16 +635,99 @@ extern "C" void rrtmg_lw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* i
                                          double* taucld, double* cicewp, double* cliqwp, double* reice, double* reliq,
                                          double* tauaer, double* uflx, double* dflx, double* hr, double* uflxc,
                                          double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt) {
-  (void)duflx_dt; (void)duflxc_dt;
-  if (!g_engine) { std::fprintf(stderr, "climt_b200: rrtmg_lw_ini_wrapper has not been called\n"); return; }
+  const bool derivs = *idrv == 1;
+  auto fail = [&](const std::string& m) {
+    lw_wrapper_fail(m, *ncol, *nlay, uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt, derivs);
+  };
+  if (!g_engine) return fail("rrtmg_lw_ini_wrapper has not been called (or failed)");
   if (*icld < 0 || *icld > 3) *icld = 2;
-  if (cb200_lw_set_options(g_engine, *icld, *idrv, *inflglw, *iceflglw, *liqflglw)) {
-    std::fprintf(stderr, "climt_b200: %s\n", cb200_lw_last_error(g_engine));
-    return;
-  }
+  cb200_lw_set_mcica(g_engine, 0, 1, 0);
+  if (cb200_lw_set_options(g_engine, *icld, *idrv, *inflglw, *iceflglw, *liqflglw)) return fail(cb200_lw_last_error(g_engine));
   cb200_lw_inputs in{play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, cfc11vmr, cfc12vmr,
                      cfc22vmr, ccl4vmr, emis, cldfr, taucld, cicewp, cliqwp, reice, reliq, tauaer};
   cb200_lw_outputs out{uflx, dflx, hr, uflxc, dflxc, hrc};
-  if (cb200_lw_run_host(g_engine, *ncol, *nlay, &in, &out))
-    std::fprintf(stderr, "climt_b200: %s\n", cb200_lw_last_error(g_engine));
+  if (derivs) cb200_lw_set_derivative_outputs(g_engine, duflx_dt, duflxc_dt);
+  const int rc = cb200_lw_run_host(g_engine, *ncol, *nlay, &in, &out);
+  cb200_lw_set_derivative_outputs(g_engine, nullptr, nullptr);
+  if (rc) fail(cb200_lw_last_error(g_engine));
+}
+
+// Sub-column generator of the reference ABI (rrtmg_lw_c_binder.f90:50-92 -> mcica_subcol_gen_lw.f90:48-154): fills the
+// caller's (ngptlw, ncol, nlay) arrays.  Both generators run on the host here -- the Mersenne twister is one serial stream
+// by definition, and for kissvec the 4 x 140 x ncol x nlay doubles this ABI asks for dominate any generator cost.  (The
+// engine's own McICA path, cb200_lw_set_mcica + cb200_lw_run_*, keeps the mask as bits in HBM and never builds these arrays.)
+extern "C" void mcica_subcol_lw_wrapper(int* iplon, int* ncol, int* nlay, int* icld, int* permuteseed, int* irng,
+                                        double* play, double* cldfrac, double* ciwp, double* clwp, double* rei,
+                                        double* rel, double* tauc, double* cldfmcl, double* ciwpmcl, double* clwpmcl,
+                                        double* reicmcl, double* relqmcl, double* taucmcl) {
+  (void)iplon;
+  const int nc = *ncol, nl = *nlay;
+  if (*icld == 0) return;  // mcica_subcol_gen_lw.f90:119
+  const size_t n3 = (size_t)140 * nc * nl, n2 = (size_t)nc * nl;
+  auto fail = [&](const std::string& m) {
+    std::fprintf(stderr, "climt_b200: %s\n", m.c_str());
+    cb::set_global_error(m);
+    cb::mcica::nan_fill(cldfmcl, n3); cb::mcica::nan_fill(ciwpmcl, n3); cb::mcica::nan_fill(clwpmcl, n3);
+    cb::mcica::nan_fill(taucmcl, n3); cb::mcica::nan_fill(reicmcl, n2); cb::mcica::nan_fill(relqmcl, n2);
+  };
+  if (*icld < 0 || *icld > 3) return fail("MCICA_SUBCOL: INVALID ICLD");
+  if (*irng != 0) *irng = 1;  // :303
+  std::vector<unsigned> mask;
+  if (*irng == 1) {
+    cb::mcica::mask_mt_host(cldfrac, nc, nl, 140, 5, *icld, *permuteseed, mask);
+  } else {
+    mask.assign((size_t)nl * 5 * nc, 0u);
+    std::atomic<int> bad{0};
+    cb::WorkerPool::get().parallel_for((nc + 63) / 64, [&](int t) {
+      for (int c = t * 64; c < nc && c < (t + 1) * 64; ++c)
+        if (cb::mcica::mask_column_kiss(play, cldfrac, nc, nl, 140, 5, *icld, *permuteseed, mask.data(), nc, 0, c)) bad.store(1);
+    });
+    if (bad.load()) return fail("MCICA_SUBCOL: KISSVEC SEED GENERATOR REQUIRES PMID FROM BOTTOM FOUR LAYERS.");
+  }
+  int ngb[140];
+  for (int g = 0; g < 140; ++g) ngb[g] = lw_ngb(g);
+  cb::mcica::SubcolIn si{ciwp, clwp, rei, rel, {tauc, nullptr, nullptr, nullptr}, {0., 0., 0., 0.}};
+  cb::mcica::SubcolOut so{cldfmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl, {taucmcl, nullptr, nullptr, nullptr}};
+  cb::mcica::expand(mask.data(), nc, nl, 140, 5, 16, ngb, 1, si, so);
+}
+
+// rrtmg_lw_c_binder.f90:94-174 -> rrtmg_lw_rad.f90:80 (rtrnmc).  The per-g-point arrays are folded back into the engine's
+// form (one mask bit per sub-column + the layer's water paths / band optics, mcica_compat.h) and run through the same
+// kernels as cb200_lw_run_host with McICA enabled.
+extern "C" void rrtmg_lw_mcica_wrapper(int* ncol, int* nlay, int* icld, int* idrv, double* play, double* plev,
+                                       double* tlay, double* tlev, double* tsfc, double* h2ovmr, double* o3vmr,
+                                       double* co2vmr, double* ch4vmr, double* n2ovmr, double* o2vmr, double* cfc11vmr,
+                                       double* cfc12vmr, double* cfc22vmr, double* ccl4vmr, double* emis, int* inflglw,
+                                       int* iceflglw, int* liqflglw, double* cldfmcl, double* taucmcl, double* ciwpmcl,
+                                       double* clwpmcl, double* reicmcl, double* relqmcl, double* tauaer, double* uflx,
+                                       double* dflx, double* hr, double* uflxc, double* dflxc, double* hrc,
+                                       double* duflx_dt, double* duflxc_dt) {
+  const int nc = *ncol, nl = *nlay;
+  const bool derivs = *idrv == 1;
+  auto fail = [&](const std::string& m) {
+    lw_wrapper_fail(m, nc, nl, uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt, derivs);
+  };
+  if (!g_engine) return fail("rrtmg_lw_ini_wrapper has not been called (or failed)");
+  if (*icld < 0 || *icld > 3) *icld = 2;  // rrtmg_lw_rad.f90:451
+  if (cb200_lw_set_options(g_engine, *icld, *idrv, *inflglw, *iceflglw, *liqflglw)) return fail(cb200_lw_last_error(g_engine));
+  int ngb[140];
+  for (int g = 0; g < 140; ++g) ngb[g] = lw_ngb(g);
+  cb::mcica::CollapseOut co;
+  const double* const bandmcl[4] = {taucmcl, nullptr, nullptr, nullptr};
+  const std::string why = cb::mcica::collapse(nc, nl, 140, 5, 16, ngb, 1, cldfmcl, ciwpmcl, clwpmcl, bandmcl, co);
+  if (!why.empty()) return fail(why);
+  cb200_lw_set_mcica(g_engine, 1, 1, 0);
+  g_engine->ext_mask.swap(co.mask);
+  g_engine->ext_ncol = nc;
+  g_engine->ext_nlay = nl;
+  cb200_lw_inputs in{play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, cfc11vmr, cfc12vmr,
+                     cfc22vmr, ccl4vmr, emis, co.cldfr.data(), co.band[0].data(), co.ciwp.data(), co.clwp.data(), reicmcl,
+                     relqmcl, tauaer};
+  cb200_lw_outputs out{uflx, dflx, hr, uflxc, dflxc, hrc};
+  if (derivs) cb200_lw_set_derivative_outputs(g_engine, duflx_dt, duflxc_dt);
+  const int rc = cb200_lw_run_host(g_engine, nc, nl, &in, &out);
+  cb200_lw_set_derivative_outputs(g_engine, nullptr, nullptr);
+  g_engine->ext_mask.clear();
+  cb200_lw_set_mcica(g_engine, 0, 1, 0);
+  if (rc) fail(cb200_lw_last_error(g_engine));
 }

@@ -12,6 +12,7 @@
 #include "engine_common.h"
 #include "sw_tables.h"
 #include "mcica_host.h"
+#include "mcica_compat.h"
 
 using namespace cb::sw;
 
@@ -124,6 +125,8 @@ struct cb200_sw_engine {
   int irng = 1, permuteseed = 0;
   unsigned* d_mask_full = nullptr;
   size_t mask_full_cap = 0;
+  std::vector<unsigned> ext_mask;  // caller-supplied sub-column mask [nlay][4][ncol] (cb200_sw_set_subcolumn_mask), else empty
+  int ext_ncol = 0, ext_nlay = 0;
   SolarOptions solar;
   UnitList UL;      // transfer kernel units (<= CB_SW_UMAX g-points); `part` holds one flux set per unit
   UnitList UL_tau;  // taumol kernel units (<= CB_SW_TAU_UMAX g-points)
@@ -291,7 +294,12 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
 // Mersenne-twister McICA mask: serial stream, generated on the host for bit parity, uploaded once [lay][word][ncol]
 static int upload_mt_mask(cb200_sw_engine* e, const double* h_cldfr, int ncol, int nlay, cudaStream_t st) {
   std::vector<unsigned> h_mask;
-  cb::mcica::mask_mt_host(h_cldfr, ncol, nlay, 112, 4, e->fl.icld, e->permuteseed, h_mask);
+  if (!e->ext_mask.empty()) {
+    if (e->ext_ncol != ncol || e->ext_nlay != nlay) { e->error = "sub-column mask was set for a different ncol/nlay"; return -3; }
+    h_mask = e->ext_mask;
+  } else {
+    cb::mcica::mask_mt_host(h_cldfr, ncol, nlay, 112, 4, e->fl.icld, e->permuteseed, h_mask);
+  }
   if (h_mask.size() > e->mask_full_cap) {
     cudaFree(e->d_mask_full);
     e->d_mask_full = nullptr;
@@ -484,9 +492,15 @@ extern "C" int cb200_sw_run_host_async(cb200_sw_engine* e, int ncol, int nlay, d
 extern "C" int cb200_sw_wait(cb200_sw_engine* e) {
   if (!e->host_pending) return 0;
   e->host_pending = false;
-  if (e->enqueue.valid())
-    if (int rc = e->enqueue.get()) return rc;
+  int rc = 0;
+  if (e->enqueue.valid()) rc = e->enqueue.get();
   CUDA_OK(cudaSetDevice(e->device));
+  if (rc) {
+    // the chunk loop failed half-way: chunks already enqueued still copy from / into the caller's buffers -- drain them
+    // before the caller is told (and frees or reuses those buffers)
+    if (e->pipe.s_in) { cudaStreamSynchronize(e->pipe.s_in); cudaStreamSynchronize(e->pipe.s_cmp); cudaStreamSynchronize(e->pipe.s_out); }
+    return rc;
+  }
   CUDA_OK(cudaStreamSynchronize(e->pipe.s_out));
   e->pipe.trace_dump("SW");
   return cb200_sw_check(e);
@@ -495,7 +509,10 @@ extern "C" int cb200_sw_wait(cb200_sw_engine* e) {
 extern "C" int cb200_sw_run_host(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
                                  const cb200_sw_inputs* hin, const cb200_sw_outputs* hout) {
   if (e->host_pending) { e->error = "a previous run_host_async call has not been waited for"; return -3; }
-  if (int rc = sw_host_enqueue(e, ncol, nlay, adjes, dyofyr, solcycfrac, hin, hout)) return rc;
+  if (int rc = sw_host_enqueue(e, ncol, nlay, adjes, dyofyr, solcycfrac, hin, hout)) {
+    if (e->pipe.s_in) { cudaStreamSynchronize(e->pipe.s_in); cudaStreamSynchronize(e->pipe.s_cmp); cudaStreamSynchronize(e->pipe.s_out); }
+    return rc;
+  }
   e->host_pending = true;
   return cb200_sw_wait(e);
 }
@@ -532,9 +549,28 @@ extern "C" void rrtmg_sw_ini_wrapper(double* cpdair) {
   if (g_engine) { cb200_sw_destroy(g_engine); g_engine = nullptr; }
   int dev = 0;
   if (const char* d = std::getenv("CLIMT_B200_DEVICE")) dev = std::atoi(d);
-  if (cb200_sw_create(&g_engine, default_blob().c_str(), g_consts, dev))
+  if (cb200_sw_create(&g_engine, default_blob().c_str(), g_consts, dev)) {
     std::fprintf(stderr, "climt_b200: rrtmg_sw_ini_wrapper failed: %s\n", cb200_global_error());
+    g_engine = nullptr;  // every later wrapper call NaN-fills its outputs and reports
+  }
 }
+// Failure policy of the void reference-named wrappers: see lw_engine.cu (NaN-filled outputs + stderr + cb200_global_error()).
+namespace {
+void sw_wrapper_fail(const std::string& msg, int ncol, int nlay, double* uflx, double* dflx, double* hr, double* uflxc,
+                     double* dflxc, double* hrc) {
+  std::fprintf(stderr, "climt_b200: %s\n", msg.c_str());
+  cb::set_global_error(msg);
+  const size_t n1 = (size_t)ncol * (nlay + 1), n0 = (size_t)ncol * nlay;
+  cb::mcica::nan_fill(uflx, n1); cb::mcica::nan_fill(dflx, n1); cb::mcica::nan_fill(hr, n0);
+  cb::mcica::nan_fill(uflxc, n1); cb::mcica::nan_fill(dflxc, n1); cb::mcica::nan_fill(hrc, n0);
+}
+int sw_ngb(int g) {  // 0-based band (0 = band 16) of 0-based g-point g (ngb, rrtmg_sw_init.f90:286-293)
+  int b = 0;
+  while (b < 13 && g >= kGS[b + 1]) ++b;
+  return b;
+}
+}  // namespace
+
 extern "C" void rrtmg_sw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* iaer, double* play, double* plev,
                                          double* tlay, double* tlev, double* tsfc, double* h2ovmr, double* o3vmr,
                                          double* co2vmr, double* ch4vmr, double* n2ovmr, double* o2vmr, double* asdir,
@@ -545,14 +581,95 @@ extern "C" void rrtmg_sw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* i
                                          double* tauaer, double* ssaaer, double* asmaer, double* ecaer, double* swuflx,
                                          double* swdflx, double* swhr, double* swuflxc, double* swdflxc, double* swhrc,
                                          double* bndsolvar, double* indsolvar, double* solcycfrac) {
-  if (!g_engine) { std::fprintf(stderr, "climt_b200: rrtmg_sw_ini_wrapper has not been called\n"); return; }
+  auto fail = [&](const std::string& m) { sw_wrapper_fail(m, *ncol, *nlay, swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc); };
+  if (!g_engine) return fail("rrtmg_sw_ini_wrapper has not been called (or failed)");
   if (*icld < 0 || *icld > 3) *icld = 2;
   if (*iaer != 0 && *iaer != 6 && *iaer != 10) *iaer = 0;
+  cb200_sw_set_mcica(g_engine, 0, 1, 0);
   cb200_sw_set_options(g_engine, *icld, *iaer, *inflgsw, *iceflgsw, *liqflgsw);
   cb200_sw_set_solar(g_engine, *isolvar, *scon, indsolvar, bndsolvar);
   cb200_sw_inputs in{play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, asdir, asdif, aldir, aldif,
                      coszen, cldfr, taucld, ssacld, asmcld, fsfcld, cicewp, cliqwp, reice, reliq, tauaer, ssaaer, asmaer, ecaer};
   cb200_sw_outputs out{swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc};
   if (cb200_sw_run_host(g_engine, *ncol, *nlay, *adjes, *dyofyr, solcycfrac ? *solcycfrac : 0.0, &in, &out))
-    std::fprintf(stderr, "climt_b200: %s\n", cb200_sw_last_error(g_engine));
+    fail(cb200_sw_last_error(g_engine));
+}
+
+// Sub-column generator of the reference ABI (rrtmg_sw_c_binder.f90:59-107 -> mcica_subcol_gen_sw.f90:66-180): fills the
+// caller's (ngptsw, ncol, nlay) arrays; clear sub-columns get tau 0, ssa 1, asm 0, fsf 0 (:517-525).  Host side for the
+// reasons given at mcica_subcol_lw_wrapper (lw_engine.cu).
+extern "C" void mcica_subcol_sw_wrapper(int* iplon, int* ncol, int* nlay, int* icld, int* permuteseed, int* irng,
+                                        double* play, double* cldfrac, double* ciwp, double* clwp, double* rei,
+                                        double* rel, double* tauc, double* ssac, double* asmc, double* fsfc,
+                                        double* cldfmcl, double* ciwpmcl, double* clwpmcl, double* reicmcl,
+                                        double* relqmcl, double* taucmcl, double* ssacmcl, double* asmcmcl,
+                                        double* fsfcmcl) {
+  (void)iplon;
+  const int nc = *ncol, nl = *nlay;
+  if (*icld == 0) return;  // mcica_subcol_gen_sw.f90:143
+  const size_t n3 = (size_t)112 * nc * nl, n2 = (size_t)nc * nl;
+  auto fail = [&](const std::string& m) {
+    std::fprintf(stderr, "climt_b200: %s\n", m.c_str());
+    cb::set_global_error(m);
+    for (double* p : {cldfmcl, ciwpmcl, clwpmcl, taucmcl, ssacmcl, asmcmcl, fsfcmcl}) cb::mcica::nan_fill(p, n3);
+    cb::mcica::nan_fill(reicmcl, n2); cb::mcica::nan_fill(relqmcl, n2);
+  };
+  if (*icld < 0 || *icld > 3) return fail("MCICA_SUBCOL: INVALID ICLD");
+  if (*irng != 0) *irng = 1;
+  std::vector<unsigned> mask;
+  if (*irng == 1) {
+    cb::mcica::mask_mt_host(cldfrac, nc, nl, 112, 4, *icld, *permuteseed, mask);
+  } else {
+    mask.assign((size_t)nl * 4 * nc, 0u);
+    std::atomic<int> bad{0};
+    cb::WorkerPool::get().parallel_for((nc + 63) / 64, [&](int t) {
+      for (int c = t * 64; c < nc && c < (t + 1) * 64; ++c)
+        if (cb::mcica::mask_column_kiss(play, cldfrac, nc, nl, 112, 4, *icld, *permuteseed, mask.data(), nc, 0, c)) bad.store(1);
+    });
+    if (bad.load()) return fail("MCICA_SUBCOL: KISSVEC SEED GENERATOR REQUIRES PMID FROM BOTTOM FOUR LAYERS.");
+  }
+  int ngb[112];
+  for (int g = 0; g < 112; ++g) ngb[g] = sw_ngb(g);
+  cb::mcica::SubcolIn si{ciwp, clwp, rei, rel, {tauc, ssac, asmc, fsfc}, {0., 1., 0., 0.}};
+  cb::mcica::SubcolOut so{cldfmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl, {taucmcl, ssacmcl, asmcmcl, fsfcmcl}};
+  cb::mcica::expand(mask.data(), nc, nl, 112, 4, 14, ngb, 4, si, so);
+}
+
+// rrtmg_sw_c_binder.f90:109-201 -> rrtmg_sw_rad.f90:97 (spcvmc_sw): per-g-point arrays folded back into mask bits + layer
+// values (mcica_compat.h), then the same kernels as cb200_sw_run_host with McICA enabled.
+extern "C" void rrtmg_sw_mcica_wrapper(int* ncol, int* nlay, int* icld, int* iaer, double* play, double* plev,
+                                       double* tlay, double* tlev, double* tsfc, double* h2ovmr, double* o3vmr,
+                                       double* co2vmr, double* ch4vmr, double* n2ovmr, double* o2vmr, double* asdir,
+                                       double* asdif, double* aldir, double* aldif, double* coszen, double* adjes,
+                                       int* dyofyr, double* scon, int* isolvar, int* inflgsw, int* iceflgsw,
+                                       int* liqflgsw, double* cldfmcl, double* taucmcl, double* ssacmcl, double* asmcmcl,
+                                       double* fsfcmcl, double* ciwpmcl, double* clwpmcl, double* reicmcl,
+                                       double* relqmcl, double* tauaer, double* ssaaer, double* asmaer, double* ecaer,
+                                       double* swuflx, double* swdflx, double* swhr, double* swuflxc, double* swdflxc,
+                                       double* swhrc, double* bndsolvar, double* indsolvar, double* solcycfrac) {
+  const int nc = *ncol, nl = *nlay;
+  auto fail = [&](const std::string& m) { sw_wrapper_fail(m, nc, nl, swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc); };
+  if (!g_engine) return fail("rrtmg_sw_ini_wrapper has not been called (or failed)");
+  if (*icld < 0 || *icld > 3) *icld = 2;                  // rrtmg_sw_rad.f90:587
+  if (*iaer != 0 && *iaer != 6 && *iaer != 10) *iaer = 0;
+  cb200_sw_set_options(g_engine, *icld, *iaer, *inflgsw, *iceflgsw, *liqflgsw);
+  cb200_sw_set_solar(g_engine, *isolvar, *scon, indsolvar, bndsolvar);
+  int ngb[112];
+  for (int g = 0; g < 112; ++g) ngb[g] = sw_ngb(g);
+  cb::mcica::CollapseOut co;
+  const double* const bandmcl[4] = {taucmcl, ssacmcl, asmcmcl, fsfcmcl};
+  const std::string why = cb::mcica::collapse(nc, nl, 112, 4, 14, ngb, 4, cldfmcl, ciwpmcl, clwpmcl, bandmcl, co);
+  if (!why.empty()) return fail(why);
+  cb200_sw_set_mcica(g_engine, 1, 1, 0);
+  g_engine->ext_mask.swap(co.mask);
+  g_engine->ext_ncol = nc;
+  g_engine->ext_nlay = nl;
+  cb200_sw_inputs in{play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, asdir, asdif, aldir, aldif,
+                     coszen, co.cldfr.data(), co.band[0].data(), co.band[1].data(), co.band[2].data(), co.band[3].data(),
+                     co.ciwp.data(), co.clwp.data(), reicmcl, relqmcl, tauaer, ssaaer, asmaer, ecaer};
+  cb200_sw_outputs out{swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc};
+  const int rc = cb200_sw_run_host(g_engine, nc, nl, *adjes, *dyofyr, solcycfrac ? *solcycfrac : 0.0, &in, &out);
+  g_engine->ext_mask.clear();
+  cb200_sw_set_mcica(g_engine, 0, 1, 0);
+  if (rc) fail(cb200_sw_last_error(g_engine));
 }

@@ -49,7 +49,8 @@ class LWEngine:
 
     def set_options(self, icld, idrv, inflag, iceflag, liqflag):
         if self._L.cb200_lw_set_options(self._h, icld, idrv, inflag, iceflag, liqflag):
-            raise NotImplementedError(self._err())
+            raise ValueError(self._err())
+        self.idrv = int(idrv)
 
     def _err(self):
         return self._L.cb200_lw_last_error(self._h).decode()
@@ -84,6 +85,12 @@ class LWEngine:
             if a.shape != outs[k] or a.dtype != np.float64 or not a.flags.c_contiguous:
                 raise ValueError(f"output {k}: need C-contiguous float64 {outs[k]}")
             setattr(pout, k, a.ctypes.data_as(_dp))
+        if self.idrv == 1:  # calculate_change_up_flux: duflx_dt / duflxc_dt of rrtmg_lw_c_binder.f90:176-256
+            for k in ("duflx_dt", "duflxc_dt"):
+                a = out.setdefault(k, np.empty(outs["uflx"]))
+                if a.shape != outs["uflx"] or a.dtype != np.float64 or not a.flags.c_contiguous:
+                    raise ValueError(f"output {k}: need C-contiguous float64 {outs['uflx']}")
+            self._L.cb200_lw_set_derivative_outputs(self._h, out["duflx_dt"].ctypes.data_as(_dp), out["duflxc_dt"].ctypes.data_as(_dp))
         fn = self._L.cb200_lw_run_host_async if wait is False else self._L.cb200_lw_run_host
         rc = fn(self._h, ncol, nlay, ctypes.byref(pin), ctypes.byref(pout))
         if wait is False and rc == 0:
@@ -130,6 +137,13 @@ class LWEngine:
             if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == outs[k]):
                 raise ValueError(f"output {k}: need contiguous float64 CUDA tensor of shape {outs[k]}")
             setattr(pout, k, ctypes.cast(t.data_ptr(), _dp))
+        if self.idrv == 1:
+            for k in ("duflx_dt", "duflxc_dt"):
+                t = out[k]
+                if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == outs["uflx"]):
+                    raise ValueError(f"output {k}: need contiguous float64 CUDA tensor of shape {outs['uflx']}")
+            self._L.cb200_lw_set_derivative_outputs(self._h, ctypes.cast(out["duflx_dt"].data_ptr(), _dp),
+                                                    ctypes.cast(out["duflxc_dt"].data_ptr(), _dp))
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         rc = self._L.cb200_lw_run_device(self._h, ncol, nlay, ctypes.byref(pin), ctypes.byref(pout), ctypes.c_void_p(s))
         if rc:

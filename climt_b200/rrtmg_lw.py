@@ -146,6 +146,10 @@ class RRTMGLongwave(TendencyComponent):
                 self._permute_seed = np.random.randint(0, 2 ** 31 - 1)
             self._engine.set_mcica(True, self._random_number_generator, self._permute_seed)
         self._engine.run_host(n_columns, n_layers, arrays, out)
+        if self._calc_dflxdt:
+            # d(upward flux)/d(surface temperature) (idrv = 1).  The reference has no diagnostic for it (its component never hands
+            # the two arrays to the Cython call, lw/component.py:482-516 vs _rrtmg_lw.pyx:164-165), so it is kept on the instance.
+            self.change_up_flux = {"duflx_dt": out["duflx_dt"], "duflxc_dt": out["duflxc_dt"]}
         diagnostics["air_temperature_tendency_from_longwave"] = tendencies["air_temperature"]
         return tendencies, diagnostics
 
@@ -179,6 +183,9 @@ class RRTMGLongwave(TendencyComponent):
         new = lambda nlev: torch.empty((nlev, n_columns), dtype=torch.float64, device=dev)  # noqa: E731
         out = {"uflx": new(n_layers + 1), "dflx": new(n_layers + 1), "hr": new(n_layers), "uflxc": new(n_layers + 1),
                "dflxc": new(n_layers + 1), "hrc": new(n_layers)}
+        if self._calc_dflxdt:
+            out["duflx_dt"], out["duflxc_dt"] = new(n_layers + 1), new(n_layers + 1)
+            self.change_up_flux = {"duflx_dt": out["duflx_dt"], "duflxc_dt": out["duflxc_dt"]}
         if self._mcica:
             self._permute_seed = np.random.randint(0, 1024) if self._random_number_generator == 0 else np.random.randint(0, 2 ** 31 - 1)
             self._engine.set_mcica(True, self._random_number_generator, self._permute_seed)

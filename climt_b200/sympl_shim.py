@@ -90,10 +90,19 @@ except Exception:  # ImportError or a broken install
 
         def __call__(self, state, *extra):
             raw, star, star_shape = {}, (), ()
+            # sympl hands array_call the raw arrays under a quantity's alias when its properties declare one, and accepts outputs
+            # under the alias of ANY property dict of the component (GrayLongwaveRadiation returns its tendency as "sl", the alias
+            # of the input air_temperature, climt/_components/radiation.py:27-62,108)
+            alias_of = {}
+            for props in (self.input_properties, self.tendency_properties, self.diagnostic_properties,
+                          getattr(self, "output_properties", {})):
+                for name, prop in props.items():
+                    if "alias" in prop:
+                        alias_of[prop["alias"]] = name
             for name, prop in self.input_properties.items():
                 if name not in state:
                     raise KeyError(f"state is missing input quantity {name!r}")
-                raw[name], s, ss = _to_raw(state[name], prop["dims"], prop.get("units", ""))
+                raw[prop.get("alias", name)], s, ss = _to_raw(state[name], prop["dims"], prop.get("units", ""))
                 if "*" in prop["dims"] and len(s) >= len(star):
                     star, star_shape = s, ss
             if "time" in state:
@@ -119,6 +128,8 @@ except Exception:  # ImportError or a broken install
                         shape.append(arr.shape[k])
                     k += 1
                 return DataArray(np.asarray(arr).reshape(shape), dims, {"units": prop.get("units", "")})
+            diag = {alias_of.get(k, k): v for k, v in diag.items()}
+            tend = {alias_of.get(k, k): v for k, v in tend.items()}
             diag = {k: wrap(v, self.diagnostic_properties[k]) for k, v in diag.items()}
             if self._diagnostic_only:
                 return diag

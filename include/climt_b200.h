@@ -6,6 +6,13 @@
  *   rrtmg_set_constants        _lib/rrtmg_lw/rrlw_con.f90:46-71      (decl _components/rrtmg/lw/_rrtmg_lw.pyx:19-24)
  *   rrtmg_lw_ini_wrapper       _lib/rrtmg_lw/rrtmg_lw_c_binder.f90:39-48   (decl _rrtmg_lw.pyx:26)
  *   rrtmg_lw_nomcica_wrapper   _lib/rrtmg_lw/rrtmg_lw_c_binder.f90:176-256 (decl _rrtmg_lw.pyx:62-80)
+ *   mcica_subcol_lw_wrapper    _lib/rrtmg_lw/rrtmg_lw_c_binder.f90:50-92   (decl _rrtmg_lw.pyx:28-40, call :261-276)
+ *   rrtmg_lw_mcica_wrapper     _lib/rrtmg_lw/rrtmg_lw_c_binder.f90:94-174  (decl _rrtmg_lw.pyx:42-60, call :283-320)
+ *   (the five shortwave twins are listed at the shortwave section below)
+ *
+ * Failure of a reference-named (void) entry point: the Fortran under the reference's symbols ends the process with `stop`;
+ * here every output array of the call is filled with NaN, the message is printed to stderr and kept for
+ * cb200_global_error().  Nothing is ever left stale.
  *
  * Two flavours are exported:
  *  (1) handle-based, re-entrant entry points (cb200_lw_*): explicit constants, explicit options, per-instance
@@ -54,6 +61,10 @@ int cb200_lw_set_options(cb200_lw_engine* e, int icld, int idrv, int inflag, int
  * device), 1 = Mersenne twister (one serial stream per call, generated on the host for bit parity);
  * permuteseed as in mcica_subcol_lw_wrapper (rrtmg_lw_c_binder.f90:50-92).  Call before cb200_lw_set_options. */
 int cb200_lw_set_mcica(cb200_lw_engine* e, int enabled, int irng, int permuteseed);
+/* idrv = 1 (calculate_change_up_flux, rrtmg_lw_rtrn.f90:279-296,458-512,546-555): where the next run call writes
+ * d(upward flux)/d(surface temperature) [W m-2 K-1], total and clear sky, (nlay+1, ncol) each -- duflx_dt / duflxc_dt of
+ * rrtmg_lw_c_binder.f90:176-256.  Host pointers for run_host, device pointers for run_device; nulls clear them. */
+int cb200_lw_set_derivative_outputs(cb200_lw_engine* e, double* duflx_dt, double* duflxc_dt);
 /* Asynchronous on `stream` (a cudaStream_t, NULL = default stream); pointers are device pointers owned by
  * the caller.  Returns 0 or a negative launch/configuration error.  Input-validation errors that the Fortran
  * turns into `stop` are reported by cb200_lw_check() after the stream has been synchronised. */
@@ -93,11 +104,29 @@ void rrtmg_lw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* idrv, double
                               int* liqflglw, double* cldfr, double* taucld, double* cicewp, double* cliqwp,
                               double* reice, double* reliq, double* tauaer, double* uflx, double* dflx, double* hr,
                               double* uflxc, double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt);
+/* McICA, the reference's two-step form.  mcica_subcol_lw_wrapper (sub-column generator, mcica_subcol_gen_lw.f90:48-154) fills the
+ * caller's Fortran (140, ncol, nlay) arrays cldfmcl / ciwpmcl / clwpmcl / taucmcl and (ncol, nlay) reicmcl / relqmcl from the layer
+ * cloud fields; tauc is Fortran (16, ncol, nlay); irng is intent(inout) (anything but 0 becomes 1 = Mersenne twister);
+ * icld = 0 returns without touching the outputs (:119).  rrtmg_lw_mcica_wrapper (rrtmg_lw_rad.f90:80, rtrnmc) consumes them:
+ * sub-column cloud fractions must be 0 or 1 and the cloudy sub-columns of a layer must share one set of water paths / optical
+ * depths per band -- which is what the generator produces -- otherwise the call fails as described at the top of this file. */
+void mcica_subcol_lw_wrapper(int* iplon, int* ncol, int* nlay, int* icld, int* permuteseed, int* irng, double* play,
+                             double* cldfrac, double* ciwp, double* clwp, double* rei, double* rel, double* tauc,
+                             double* cldfmcl, double* ciwpmcl, double* clwpmcl, double* reicmcl, double* relqmcl,
+                             double* taucmcl);
+void rrtmg_lw_mcica_wrapper(int* ncol, int* nlay, int* icld, int* idrv, double* play, double* plev, double* tlay,
+                            double* tlev, double* tsfc, double* h2ovmr, double* o3vmr, double* co2vmr, double* ch4vmr,
+                            double* n2ovmr, double* o2vmr, double* cfc11vmr, double* cfc12vmr, double* cfc22vmr,
+                            double* ccl4vmr, double* emis, int* inflglw, int* iceflglw, int* liqflglw, double* cldfmcl,
+                            double* taucmcl, double* ciwpmcl, double* clwpmcl, double* reicmcl, double* relqmcl,
+                            double* tauaer, double* uflx, double* dflx, double* hr, double* uflxc, double* dflxc,
+                            double* hrc, double* duflx_dt, double* duflxc_dt);
 
 
 /* ============================== shortwave ==============================
  * Replaces (climt/_lib/rrtmg_sw/rrtmg_sw_c_binder.f90): rrtmg_sw_set_constants :19-46, rrtmg_sw_ini_wrapper :48-57,
- * rrtmg_sw_nomcica_wrapper :203-296 (decls in _components/rrtmg/sw/_rrtmg_sw.pyx:22-105).
+ * rrtmg_sw_nomcica_wrapper :203-296, mcica_subcol_sw_wrapper :59-107, rrtmg_sw_mcica_wrapper :109-201
+ * (decls in _components/rrtmg/sw/_rrtmg_sw.pyx:22-105; McICA call order :341-417).
  * Cloud arrays taucld/ssacld/asmcld/fsfcld are (nlay, ncol, 14) [Fortran (14,ncol,nlay)]; aerosol arrays
  * tauaer/ssaaer/asmaer (14, nlay, ncol); ecaer (6, nlay, ncol); albedos and coszen (ncol). */
 typedef struct cb200_sw_engine cb200_sw_engine;
@@ -145,6 +174,22 @@ void rrtmg_sw_nomcica_wrapper(int* ncol, int* nlay, int* icld, int* iaer, double
                               double* reice, double* reliq, double* tauaer, double* ssaaer, double* asmaer,
                               double* ecaer, double* swuflx, double* swdflx, double* swhr, double* swuflxc,
                               double* swdflxc, double* swhrc, double* bndsolvar, double* indsolvar, double* solcycfrac);
+/* McICA, two-step form (see the longwave pair): (112, ncol, nlay) arrays; tauc / ssac / asmc / fsfc are Fortran (14, ncol, nlay);
+ * clear sub-columns get tau 0, ssa 1, asm 0, fsf 0 (mcica_subcol_gen_sw.f90:517-525). */
+void mcica_subcol_sw_wrapper(int* iplon, int* ncol, int* nlay, int* icld, int* permuteseed, int* irng, double* play,
+                             double* cldfrac, double* ciwp, double* clwp, double* rei, double* rel, double* tauc,
+                             double* ssac, double* asmc, double* fsfc, double* cldfmcl, double* ciwpmcl, double* clwpmcl,
+                             double* reicmcl, double* relqmcl, double* taucmcl, double* ssacmcl, double* asmcmcl,
+                             double* fsfcmcl);
+void rrtmg_sw_mcica_wrapper(int* ncol, int* nlay, int* icld, int* iaer, double* play, double* plev, double* tlay,
+                            double* tlev, double* tsfc, double* h2ovmr, double* o3vmr, double* co2vmr, double* ch4vmr,
+                            double* n2ovmr, double* o2vmr, double* asdir, double* asdif, double* aldir, double* aldif,
+                            double* coszen, double* adjes, int* dyofyr, double* scon, int* isolvar, int* inflgsw,
+                            int* iceflgsw, int* liqflgsw, double* cldfmcl, double* taucmcl, double* ssacmcl,
+                            double* asmcmcl, double* fsfcmcl, double* ciwpmcl, double* clwpmcl, double* reicmcl,
+                            double* relqmcl, double* tauaer, double* ssaaer, double* asmaer, double* ecaer,
+                            double* swuflx, double* swdflx, double* swhr, double* swuflxc, double* swdflxc, double* swhrc,
+                            double* bndsolvar, double* indsolvar, double* solcycfrac);
 
 
 /* ============================== gray longwave ==============================

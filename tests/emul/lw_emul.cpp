@@ -19,18 +19,19 @@ static void run_taumol(const Tables& T, const In& in, const Work& W, int n, int 
   }
 }
 
-template <int U>
+template <int U, bool DRV>
 static void run_transfer(const Tables& T, const In& in, const Work& W, int n, int ib, int g0, int unit, bool mc, bool mr) {
   for (int c = 0; c < n; ++c) {
-    if (mc) lw_transfer_unit<U, true, false>(T, in, W, 0, c, ib, g0, unit);
-    else if (mr) lw_transfer_unit<U, false, true>(T, in, W, 0, c, ib, g0, unit);
-    else lw_transfer_unit<U, false, false>(T, in, W, 0, c, ib, g0, unit);
+    if (mc) lw_transfer_unit<U, true, false, DRV>(T, in, W, 0, c, ib, g0, unit);
+    else if (mr) lw_transfer_unit<U, false, true, DRV>(T, in, W, 0, c, ib, g0, unit);
+    else lw_transfer_unit<U, false, false, DRV>(T, in, W, 0, c, ib, g0, unit);
   }
 }
 
 // flags8 = {icld, idrv, inflag, iceflag, liqflag, mcica, irng, permuteseed}
 extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* flags5, int ncol, int nlay,
-                           const double* const* inp /*23 pointers in struct In order*/, double* const* outp /*6*/) {
+                           const double* const* inp /*23 pointers in struct In order*/,
+                           double* const* outp /*8: 6 fluxes / heating rates + duflx_dt, duflxc_dt (used when idrv = 1)*/) {
   try {
     Constants k;
     std::memcpy(&k, consts11, sizeof(k));
@@ -45,6 +46,8 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
     Out out;
     double** op = &out.uflx;
     for (int i = 0; i < 6; ++i) op[i] = outp[i];
+    const bool drv = flags5[1] == 1;
+    if (drv) { out.duflx_dt = outp[6]; out.duflxc_dt = outp[7]; }
     Flags fl{flags5[0], flags5[1], flags5[2], flags5[3], flags5[4], flags5[5]};
     const int irng = flags5[6], seed = flags5[7];
     const bool mc = fl.mcica && fl.icld >= 1;
@@ -53,7 +56,8 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
     Work W;
     W.ncc = ncol;
     std::vector<double> ws((size_t)NF * nlay * ncol), pw(ncol), cld((size_t)32 * nlay * ncol),
-        scr((size_t)140 * NSCR * nlay * ncol), ovl((size_t)OV_NROWS * (nlay + 2) * ncol), part((size_t)nunits * 4 * (nlay + 1) * ncol);
+        scr((size_t)140 * NSCR * nlay * ncol), ovl((size_t)OV_NROWS * (nlay + 2) * ncol), part((size_t)nunits * 6 * (nlay + 1) * ncol);
+    W.npart = drv ? 6 : 4;
     std::vector<int> idx((size_t)nlay * ncol), lt(ncol), ncb(ncol);
     std::vector<unsigned> mask((size_t)5 * nlay * ncol, 0u);
     int err = 0;
@@ -84,8 +88,13 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
     for (int k2 = 0; k2 < nunits; ++k2) {
       const Unit un = units[k2];
       const bool mr = !mc && fl.icld >= 2;
-      if (un.u == 4) run_transfer<4>(T, in, W, ncol, un.band - 1, un.g0, k2, mc, mr);
-      else run_transfer<2>(T, in, W, ncol, un.band - 1, un.g0, k2, mc, mr);
+      if (drv) {
+        if (un.u == 4) run_transfer<4, true>(T, in, W, ncol, un.band - 1, un.g0, k2, mc, mr);
+        else run_transfer<2, true>(T, in, W, ncol, un.band - 1, un.g0, k2, mc, mr);
+      } else {
+        if (un.u == 4) run_transfer<4, false>(T, in, W, ncol, un.band - 1, un.g0, k2, mc, mr);
+        else run_transfer<2, false>(T, in, W, ncol, un.band - 1, un.g0, k2, mc, mr);
+      }
     }
     for (int c = 0; c < ncol; ++c)
       for (int lev = 0; lev <= nlay; ++lev) lw_reduce_level(T, W, units, nunits, nlay, 0, c, lev, ncol, out);

@@ -126,7 +126,8 @@ def run_lw_emul(st, flags=(1, 0, 2, 1, 1), mcica=(0, 1, 0)):
     inp = (_dp * 23)(*[st[f].ctypes.data_as(_dp) for f in SY.LW_FIELDS])
     out = {n: np.zeros((nlay + 1, ncol)) for n in ("uflx", "dflx", "uflxc", "dflxc")}
     out.update({n: np.zeros((nlay, ncol)) for n in ("hr", "hrc")})
-    outp = (_dp * 6)(*[out[n].ctypes.data_as(_dp) for n in ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc")])
+    out.update({n: np.zeros((nlay + 1, ncol)) for n in ("duflx_dt", "duflxc_dt")})
+    outp = (_dp * 8)(*[out[n].ctypes.data_as(_dp) for n in ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc", "duflx_dt", "duflxc_dt")])
     rc = lib.emul_lw_run(RT.lw_blob_path().encode(), consts.ctypes.data_as(_dp), (ctypes.c_int * 8)(*flags),
                          ncol, nlay, inp, outp)
     return rc, out

@@ -144,3 +144,47 @@ def test_maximum_overlap_of_equal_fractions_beats_random_overlap_cloud_cover():
     # maximum overlap: total cover 0.4; random: 1 - 0.6^3 = 0.78 -> less downward longwave at the surface, more OLR
     assert np.all(mr["dflx"][0] < rnd["dflx"][0] - 5.0) and np.all(mr["uflx"][-1] > rnd["uflx"][-1])
     assert np.all(mr["dflx"][0] > mr["dflxc"][0])
+
+
+# ---- idrv = 1: d(upward flux)/d(surface temperature) (rrtmg_lw_rtrn.f90:279-296,458-512,546-555).  The reference holds no golden
+# for it (its component cannot even request it, _rrtmg_lw.pyx:164-165), so the restatement is pinned by what the quantity IS:
+# a centred finite difference of the oracle's own upward flux with respect to the surface temperature.
+def test_oracle_flux_derivative_is_the_finite_difference_of_its_upward_flux():
+    st = SY.make_lw_state(6, 40, seed=21, clouds=True, aerosol=True, emis_range=(0.85, 1.0))
+    o = H.run_lw_oracle(H.lw_oracle(cloud_overlap=1, idrv=1), st)
+    h = 0.05
+    up, dn = dict(st), dict(st)
+    up["tsfc"], dn["tsfc"] = st["tsfc"] + h, st["tsfc"] - h
+    # the interface temperature at the surface is a separate input (tlev[0]); only tbound moves, as in the Fortran's derivative
+    fu = H.run_lw_oracle(H.lw_oracle(cloud_overlap=1), up)
+    fd = H.run_lw_oracle(H.lw_oracle(cloud_overlap=1), dn)
+    for k, kk in (("duflx_dt", "uflx"), ("duflxc_dt", "uflxc")):
+        fdiff = (fu[kk] - fd[kk]) / (2 * h)
+        # 1 %: the flux uses a Planck table that is piecewise linear in 1-K steps (its finite difference is the step's mean slope)
+        # while the derivative interpolates a table of true derivatives (totplnkderiv) -- they differ by the curvature over < 1 K
+        assert np.max(np.abs(o[k] - fdiff)) < 1e-2 * np.max(np.abs(fdiff)), k
+    assert o["duflx_dt"][0].min() > 3.0          # ~ 4 sigma T^3 at the surface
+    assert np.all(np.diff(o["duflxc_dt"], axis=0) <= 1e-12)   # the clear-sky derivative can only be attenuated upwards
+
+
+@pytest.mark.parametrize("icld", [1, 2])
+def test_flux_derivative_kernels_match_oracle(icld):
+    st = SY.make_lw_state(9, 33, seed=30 + icld, clouds=True, aerosol=True, emis_range=(0.9, 1.0))
+    ref = H.run_lw_oracle(H.lw_oracle(cloud_overlap=icld, idrv=1), st)
+    rc, got = H.run_lw_emul(st, (icld, 1, 2, 1, 1))
+    assert rc == 0
+    for k in ("uflx", "dflx", "uflxc", "dflxc", "duflx_dt", "duflxc_dt"):
+        assert H.rel_err(got[k], ref[k]) < TOL, k
+    assert np.abs(got["duflx_dt"] - got["duflxc_dt"]).max() > 1e-3
+
+
+def test_mcica_flux_derivative_with_overcast_layers_equals_the_deterministic_one():
+    """rtrnmc's derivative (rrtmg_lw_rtrnmc.f90:447-510) has no oracle restatement; with every cloudy layer overcast all
+    sub-columns are cloudy, so it must reproduce rtrn's (cloud fraction 1) exactly."""
+    st = SY.make_lw_state(7, 30, seed=44, clouds=True)
+    st["cldfr"] = np.where(st["cldfr"] > 0, 1.0, 0.0)
+    rc0, det = H.run_lw_emul(st, (1, 1, 2, 1, 1))
+    rc1, mc = H.run_lw_emul(st, (1, 1, 2, 1, 1), mcica=(1, 1, 3))
+    assert rc0 == 0 and rc1 == 0
+    for k in ("uflx", "duflx_dt", "duflxc_dt"):
+        assert H.rel_err(mc[k], det[k]) < 1e-12, k
