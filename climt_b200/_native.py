@@ -73,7 +73,7 @@ class SwInputs(ctypes.Structure):
         "cicewp", "cliqwp", "reice", "reliq", "tauaer", "ssaaer", "asmaer", "ecaer")]
 
 
-EXPORTS = ["mcica_subcol_lw_wrapper", "rrtmg_lw_mcica_wrapper", "mcica_subcol_sw_wrapper", "rrtmg_sw_mcica_wrapper",
+EXPORTS = ["cb200_lw_zero_scan_state", "mcica_subcol_lw_wrapper", "rrtmg_lw_mcica_wrapper", "mcica_subcol_sw_wrapper", "rrtmg_sw_mcica_wrapper",
            "cb200_lw_set_derivative_outputs", "cb200_berger_scalars", "cb200_berger_run_device", "cb200_berger_run_host", "cb200_simple_physics_run_device", "cb200_simple_physics_run_host", "set_fortran_constants", "simple_physics",
            "cb200_cork_create_from_file", "cb200_instellation_orbit", "cb200_instellation_run_device", "cb200_instellation_run_host", "cb200_slab_surface_run_device",
            "cb200_slab_surface_run_host", "cb200_emanuel_create", "cb200_emanuel_destroy", "cb200_emanuel_last_error", "cb200_emanuel_last_launches", "cb200_emanuel_enable_timing",
@@ -110,6 +110,7 @@ def lib():
     L.cb200_lw_set_options.argtypes = [vp] + [ctypes.c_int] * 5
     L.cb200_lw_set_mcica.argtypes = [vp] + [ctypes.c_int] * 3
     L.cb200_lw_set_derivative_outputs.argtypes = [vp, _dp, _dp]
+    L.cb200_lw_zero_scan_state.argtypes = [vp]
     L.cb200_lw_run_device.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(LwInputs),
                                       ctypes.POINTER(LwOutputs), vp]
     L.cb200_lw_run_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(LwInputs),

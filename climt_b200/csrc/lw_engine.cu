@@ -566,6 +566,14 @@ extern "C" int cb200_lw_run_host(cb200_lw_engine* e, int ncol, int nlay, const c
   return cb200_lw_wait(e);
 }
 
+// 1: the host calls scan always-present-but-usually-zero inputs and memset them in HBM; 0: turned off by
+// CLIMT_B200_SKIP_ZERO_INPUTS=0; -1: turned off by the engine itself because the scan ran slower than the copy it saves
+// (cb::ScanGuard) -- sticky for the life of the engine, so a benchmark can report which regime it measured.
+extern "C" int cb200_lw_zero_scan_state(cb200_lw_engine* e) {
+  if (e->skip_zero_inputs) return 1;
+  return e->scan_guard.slow >= 3 ? -1 : 0;
+}
+
 extern "C" void cb200_lw_last_transfer_bytes(cb200_lw_engine* e, double* h2d, double* d2h) {
   *h2d = (double)e->h2d_bytes;
   *d2h = (double)e->d2h_bytes;

@@ -121,6 +121,11 @@ class LWEngine:
         self._L.cb200_lw_last_transfer_bytes(self._h, ctypes.byref(a), ctypes.byref(b))
         return int(a.value), int(b.value)
 
+    @property
+    def zero_scan_state(self):
+        """1 scanning, 0 disabled by the environment, -1 disabled by the engine's own guard (see include/climt_b200.h)"""
+        return int(self._L.cb200_lw_zero_scan_state(self._h))
+
     # -- device buffers (torch CUDA tensors), asynchronous ------------------------------------------
     def run_device(self, ncol, nlay, tensors, out, stream=None):
         import torch

@@ -131,3 +131,23 @@ def make_surface_state(ncol, seed=20260925, aquaplanet=True):
         "ocean_heat_transport_convergence": rng.uniform(-30.0, 30.0, ncol),
     }
     return {k: np.ascontiguousarray(a) for k, a in st.items()}
+
+
+def component_states(ncol, nlay, seed=20260925, clouds=False):
+    """The same synthetic atmosphere as make_lw_state / make_sw_state, as the raw state dicts sympl hands to
+    RRTMGLongwave.array_call / RRTMGShortwave.array_call (the components' own quantity names and units; pressures in mbar)."""
+    from .rrtmg_lw import RRTMGLongwave
+    from .rrtmg_sw import RRTMGShortwave
+    lw, sw = make_lw_state(ncol, nlay, seed=seed, clouds=clouds), make_sw_state(ncol, nlay, seed=seed, clouds=clouds)
+    short = {"h2ovmr": "h2o", "o3vmr": "o3", "co2vmr": "co2", "ch4vmr": "ch4", "n2ovmr": "n2o", "o2vmr": "o2", "cfc11vmr": "cfc11",
+             "cfc12vmr": "cfc12", "cfc22vmr": "cfc22", "ccl4vmr": "ccl4"}
+    out = []
+    for cls, st in ((RRTMGLongwave, lw), (RRTMGShortwave, sw)):
+        raw = {name: st[short.get(abi, abi)] for abi, name in cls._ABI_FROM_STATE.items()}
+        raw["specific_humidity"] = st["h2o"] * 18.02 / 28.964          # inverse of mass_to_volume_mixing_ratio (util.py:84)
+        out.append(raw)
+    out[1]["zenith_angle"] = np.arccos(sw["coszen"])
+    out[1]["solar_cycle_fraction"] = np.array(0.0)
+    out[1]["flux_adjustment_for_earth_sun_distance"] = np.array(1.0)
+    out[1]["day_of_year"] = 1
+    return out[0], out[1]

@@ -80,6 +80,9 @@ int cb200_lw_run_host_async(cb200_lw_engine* e, int ncol, int nlay, const cb200_
 int cb200_lw_wait(cb200_lw_engine* e);
 /* bytes the last host-pointer call moved over PCIe (arrays the option flags make dead are not transferred) */
 void cb200_lw_last_transfer_bytes(cb200_lw_engine* e, double* h2d, double* d2h);
+/* all-zero-input scan of the host calls: 1 active, 0 disabled by CLIMT_B200_SKIP_ZERO_INPUTS=0, -1 disabled by the engine
+ * (the scan measured slower than the PCIe copy it saves on this host; sticky) */
+int cb200_lw_zero_scan_state(cb200_lw_engine* e);
 /* 0 = ok; >0 = input out of the range the reference accepts (message via cb200_lw_last_error). */
 int cb200_lw_check(cb200_lw_engine* e);
 const char* cb200_lw_last_error(cb200_lw_engine* e);

@@ -72,3 +72,41 @@ def test_two_rank_gloo_all_gather_reassembles_global_field(ncol):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _packed_worker(rank, world, port, ncol, nlev, q):
+    """what bench.py --gpus N does per step: the 'engine' writes into row slices of the rank's packed buffer, one all-gather"""
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    arrays = {"t": rng.normal(size=(nlev, ncol)), "ts": rng.normal(size=ncol)}
+    mine = SH.shard_arrays(arrays, ncol, rank, world)
+    out = _fake_radiation(mine["t"], mine["ts"])
+    po = SH.PackedOutputs([("uflx", nlev + 1), ("hr", nlev)], ncol // world, world, device="cpu")
+    for k, v in out.items():
+        po.views[k].copy_(torch.from_numpy(v))      # the engines write here directly
+    po.gather_async()
+    ref = _fake_radiation(arrays["t"], arrays["ts"])
+    ok = all(np.array_equal(po.global_field(k).numpy(), ref[k]) for k in ref)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_packed_outputs_gather():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_packed_worker, args=(r, 2, port, 48, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
