@@ -26,7 +26,28 @@
 #define CB_MULADD_2R(a, b, c) (((a) * (b)) + (c))
 #endif
 
+// Branch-coverage hooks of the taumol evaluators (tools/taumol_coverage.py): compiled in only for the host emulation built with
+// -DCB_COVERAGE; in every other build -- the CUDA kernels included -- the macro is empty.
+#if defined(CB_COVERAGE) && !defined(__CUDA_ARCH__)
+extern "C" void cb_cov_hit(int engine, int band, int lower, int id);
+#define CB_COV(engine, band, lower, id) cb_cov_hit((engine), (band), (lower) ? 1 : 0, (id))
+#else
+#define CB_COV(engine, band, lower, id) ((void)0)
+#endif
 namespace cb {
+// what a coverage run records per (band, lower | upper atmosphere)
+enum CovId {
+  COV_REGION = 0,       // a layer was evaluated in this region
+  COV_KEY_NONZERO,      // key-species term > 0
+  COV_S0_LOW, COV_S0_MID, COV_S0_HIGH,   // binary-species stencil at the lower pressure level: specparm < 0.125 | between | > 0.875
+  COV_S1_LOW, COV_S1_MID, COV_S1_HIGH,   // ... at the upper pressure level
+  COV_SELF_NONZERO, COV_FOR_NONZERO,     // water-vapour self / foreign continuum contributes (> 0)
+  COV_MINOR0_NONZERO, COV_MINOR1_NONZERO, COV_MINOR2_NONZERO,   // minor gas k contributes
+  COV_MINOR0_ADJ, COV_MINOR1_ADJ, COV_MINOR2_ADJ,               // ... through the "too abundant to be minor" adjustment
+  COV_XSEC0_NONZERO, COV_XSEC1_NONZERO,  // halocarbon cross-section (LW) / extra absorber (SW) contributes
+  COV_PLANCK_INTERP,    // Planck fraction (LW) / solar source (SW) interpolated in the key-species ratio
+  COV_N
+};
 
 // U consecutive doubles of a table row (16-byte aligned by construction: even table offsets, even g-point counts,
 // unit starts that are multiples of 4) fetched with 128-bit read-only loads.
@@ -48,6 +69,27 @@ CB_HD Row<U> ldrow(const double* __restrict__ p) {
   } else {
 #pragma unroll
     for (int u = 0; u < U; ++u) r.v[u] = __ldg(p + u);
+  }
+#else
+  for (int u = 0; u < U; ++u) r.v[u] = p[u];
+#endif
+  return r;
+}
+
+// The same row through ordinary (coherent) loads: for tables staged in shared memory, where ld.global.nc is not allowed.
+template <int U>
+CB_HD Row<U> ldrow_plain(const double* __restrict__ p) {
+  Row<U> r;
+#if defined(__CUDA_ARCH__)
+  if (U == 4) {
+    const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+  } else if (U == 2) {
+    const double2 a = reinterpret_cast<const double2*>(p)[0];
+    r.v[0] = a.x; r.v[1] = a.y;
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u) r.v[u] = p[u];
   }
 #else
   for (int u = 0; u < U; ++u) r.v[u] = p[u];

@@ -171,6 +171,13 @@ struct HostPipe {
   double* d_in[2] = {nullptr, nullptr};
   double* d_out[2] = {nullptr, nullptr};
   size_t in_cap = 0, out_cap = 0;
+  // Pinned staging for callers whose arrays are ordinary pageable memory (numpy arrays handed down by sympl): the driver would
+  // otherwise bounce every strided 2-D copy through its own small staging buffer synchronously (r02, 8192 x 60 through
+  // RRTMGLongwave / RRTMGShortwave.array_call: 35 ms per step against 5.6 ms from pinned buffers).  Rows are copied into / out of
+  // these slots by the worker pool and cross PCIe as ONE contiguous asynchronous copy per array and chunk.
+  double* h_in[2] = {nullptr, nullptr};
+  double* h_out[2] = {nullptr, nullptr};
+  size_t hin_cap = 0, hout_cap = 0;
   // development trace (CLIMT_B200_PIPE_TRACE=1): timing events at the stage boundaries of every chunk, printed by trace_dump()
   struct Mark { cudaEvent_t ev; int chunk, kind; double host_ms; };
   bool trace = false;
@@ -252,8 +259,54 @@ struct HostPipe {
     }
     return cudaSuccess;
   }
+  cudaError_t ensure_staging(size_t in_doubles, size_t out_doubles) {
+    cudaError_t ce;
+    if (in_doubles > hin_cap) {
+      for (int i = 0; i < 2; ++i) { if (h_in[i]) cudaFreeHost(h_in[i]); h_in[i] = nullptr; }
+      hin_cap = 0;
+      for (int i = 0; i < 2; ++i)
+        if ((ce = cudaMallocHost(&h_in[i], in_doubles * sizeof(double))) != cudaSuccess) return ce;
+      hin_cap = in_doubles;
+    }
+    if (out_doubles > hout_cap) {
+      for (int i = 0; i < 2; ++i) { if (h_out[i]) cudaFreeHost(h_out[i]); h_out[i] = nullptr; }
+      hout_cap = 0;
+      for (int i = 0; i < 2; ++i)
+        if ((ce = cudaMallocHost(&h_out[i], out_doubles * sizeof(double))) != cudaSuccess) return ce;
+      hout_cap = out_doubles;
+    }
+    return cudaSuccess;
+  }
+  // Can the copy engine read / write this host pointer directly (page-locked: cudaMallocHost, cudaHostRegister, torch pin_memory)?
+  static bool dma_able(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+  }
+  // rows x n columns [c0, c0+n) of a pageable host (rows, ncol) array -> staging slot -> contiguous (rows, n) device block
+  cudaError_t gather_staged(double* dst_dev, double* stage, const double* src, int rows, int ncol, int c0, int n, int inner = 1) const {
+    const size_t w = (size_t)n * inner;
+    const int per = (int)std::max<size_t>(1, (256u << 10) / (w * sizeof(double)));
+    WorkerPool::get().parallel_for((rows + per - 1) / per, [&](int t) {
+      for (int r = t * per; r < rows && r < (t + 1) * per; ++r)
+        std::memcpy(stage + (size_t)r * w, src + ((size_t)r * ncol + c0) * inner, w * sizeof(double));
+    });
+    return cudaMemcpyAsync(dst_dev, stage, (size_t)rows * w * sizeof(double), cudaMemcpyHostToDevice, s_in);
+  }
+  cudaError_t scatter_staged_issue(double* stage, const double* src_dev, int rows, int n) const {
+    return cudaMemcpyAsync(stage, src_dev, (size_t)rows * n * sizeof(double), cudaMemcpyDeviceToHost, s_out);
+  }
+  static void scatter_staged_finish(double* dst, const double* stage, int rows, int ncol, int c0, int n) {
+    const int per = (int)std::max<size_t>(1, (256u << 10) / ((size_t)n * sizeof(double)));
+    WorkerPool::get().parallel_for((rows + per - 1) / per, [&](int t) {
+      for (int r = t * per; r < rows && r < (t + 1) * per; ++r)
+        std::memcpy(dst + (size_t)r * ncol + c0, stage + (size_t)r * n, (size_t)n * sizeof(double));
+    });
+  }
   void destroy() {
     for (int i = 0; i < 2; ++i) {
+      if (h_in[i]) cudaFreeHost(h_in[i]);
+      if (h_out[i]) cudaFreeHost(h_out[i]);
       cudaFree(d_in[i]); cudaFree(d_out[i]);
       if (in_done[i]) cudaEventDestroy(in_done[i]);
       if (cmp_done[i]) cudaEventDestroy(cmp_done[i]);

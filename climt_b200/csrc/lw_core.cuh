@@ -37,9 +37,17 @@ enum WsField {
   NF
 };
 
+// Layout of a band's g-point tables in HBM: for every group of TGW = 4 consecutive g-points ONE contiguous block that holds every
+// table of the band, row after row, TGW doubles per row (bands whose g-point count is not a multiple of 4 pad the last group):
+//   element (table X, row r, g-point g)  ->  base + (g / 4) * rows * 4 + (X + r) * 4 + (g % 4)
+// A taumol thread evaluates <= 4 g-points of one group: every table row it touches is one aligned 32-byte vector, neighbouring
+// rows are neighbouring sectors of the same 128-byte line, and the whole block of a single-key-species band (<= 14 KB) is one
+// cp.async.bulk copy into shared memory (lw_engine.cu: k_lw_taumol).
+constexpr int TGW = 4;
 struct BandOff {
-  int absa, absb, selfref, forref, fracrefa, fracrefb;
-  int m[5];  // minor-gas tables (slot meaning per band: see kMinorNames in lw_engine.cu)
+  int base, rows;  // first block (offset into Tables::base, in doubles) and rows per block
+  int absa, absb, selfref, forref, fracrefa, fracrefb;  // ROW offsets inside a block (-1: the band has no such table)
+  int m[5];  // minor-gas tables (slot meaning per band: see kMinorNames in lw_tables.h)
   int x[2];  // cross-section vectors
   double refrat_planck_a, refrat_planck_b, refrat_m_a, refrat_m_b, refrat_m_a3;
 };
@@ -758,13 +766,15 @@ CB_HD Stencil make_stencil(double specparm, double fs, double fa, double fb) {
 }
 
 // Gas optical depth and Planck fraction for U consecutive g-points [g0, g0+U) of band B in ONE layer.
-template <int B, bool LOWER, int U>
-CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstride /* = nlay*ncc */, int idx, double pavel,
-                     int g0, double* __restrict__ tau, double* __restrict__ frac) {
+// gb: the (band, g-point group) block of band tables holding g0 (+ (g0 % 4)), in HBM or -- STAGED -- staged in shared memory.
+template <int B, bool LOWER, int U, bool STAGED = false>
+CB_HD void eval_band(const Tables& T, const double* __restrict__ gb, const double* __restrict__ ws, size_t wstride /* = nlay*ncc */,
+                     int idx, double pavel, int g0, double* __restrict__ tau, double* __restrict__ frac) {
   constexpr Region R = region<B, LOWER>();
-  constexpr int ng = kNG[B - 1];
+  constexpr int ng = TGW;  // row stride of the band tables (the g-points of one group)
   const BandOff& O = T.b[B - 1];
   const double* __restrict__ tb = T.base;
+  auto ldtab = [](const double* __restrict__ p) { return STAGED ? ldrow_plain<U>(p) : ldrow<U>(p); };
 #define WSF(f) CB_LDG(ws + (size_t)(f) * wstride)
   const int jp = idx & 63, jt = (idx >> 6) & 7, jt1 = (idx >> 9) & 7;
   const int inds = (idx >> 12) & 15, indf = (idx >> 16) & 3, indm = (idx >> 18) & 31;
@@ -774,6 +784,7 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
   double cola = 0., colb = 0.;
   if (R.kind >= 1) cola = WSF(F_COLH2O + R.a);
   if (R.kind == 2) colb = WSF(F_COLH2O + R.b);
+  CB_COV(0, B, LOWER, COV_REGION);
 
   // ---- key species
   if (R.kind == 1) {
@@ -781,9 +792,9 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     constexpr int nsp = LOWER ? kNSPA[B - 1] : kNSPB[B - 1];
     const int row0 = LOWER ? ((jp - 1) * 5 + (jt - 1)) * nsp : ((jp - 13) * 5 + (jt - 1)) * nsp;
     const int row1 = LOWER ? (jp * 5 + (jt1 - 1)) * nsp : ((jp - 12) * 5 + (jt1 - 1)) * nsp;
-    const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
-    const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
-    const Row<U> k00 = ldrow<U>(a0), k10 = ldrow<U>(a0 + ng), k01 = ldrow<U>(a1), k11 = ldrow<U>(a1 + ng);
+    const double* __restrict__ a0 = gb + (size_t)((LOWER ? O.absa : O.absb) + row0) * ng;
+    const double* __restrict__ a1 = gb + (size_t)((LOWER ? O.absa : O.absb) + row1) * ng;
+    const Row<U> k00 = ldtab(a0), k10 = ldtab(a0 + ng), k01 = ldtab(a1), k11 = ldtab(a1 + ng);
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = cola * (fac00 * k00[u] + fac10 * k10[u] + fac01 * k01[u] + fac11 * k11[u]);
   } else if (R.kind == 2) {
@@ -797,48 +808,53 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     const int row1 = (LOWER ? (jp * 5 + (jt1 - 1)) * nsp : ((jp - 12) * 5 + (jt1 - 1)) * nsp) + s1.js - 1;
     const Stencil t0 = make_stencil<LOWER>(s0.specparm, s0.fs, fac00, fac10);
     const Stencil t1 = make_stencil<LOWER>(s1.specparm, s1.fs, fac01, fac11);
-    const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
-    const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
+    const double* __restrict__ a0 = gb + (size_t)((LOWER ? O.absa : O.absb) + row0) * ng;
+    const double* __restrict__ a1 = gb + (size_t)((LOWER ? O.absa : O.absb) + row1) * ng;
     double d0[U], d1[U];
     {
-      const Row<U> r0 = ldrow<U>(a0 + t0.off[0] * ng), r1 = ldrow<U>(a0 + t0.off[1] * ng), r2 = ldrow<U>(a0 + t0.off[2] * ng),
-                   r3 = ldrow<U>(a0 + t0.off[3] * ng);
+      const Row<U> r0 = ldtab(a0 + t0.off[0] * ng), r1 = ldtab(a0 + t0.off[1] * ng), r2 = ldtab(a0 + t0.off[2] * ng),
+                   r3 = ldtab(a0 + t0.off[3] * ng);
 #pragma unroll
       for (int u = 0; u < U; ++u) d0[u] = ((t0.w[0] * r0[u] + t0.w[1] * r1[u]) + t0.w[2] * r2[u]) + t0.w[3] * r3[u];
       if (LOWER && t0.n == 6) {
-        const Row<U> r4 = ldrow<U>(a0 + t0.off[4] * ng), r5 = ldrow<U>(a0 + t0.off[5] * ng);
+        const Row<U> r4 = ldtab(a0 + t0.off[4] * ng), r5 = ldtab(a0 + t0.off[5] * ng);
 #pragma unroll
         for (int u = 0; u < U; ++u) d0[u] = (d0[u] + t0.w[4] * r4[u]) + t0.w[5] * r5[u];
       }
     }
     {
-      const Row<U> r0 = ldrow<U>(a1 + t1.off[0] * ng), r1 = ldrow<U>(a1 + t1.off[1] * ng), r2 = ldrow<U>(a1 + t1.off[2] * ng),
-                   r3 = ldrow<U>(a1 + t1.off[3] * ng);
+      const Row<U> r0 = ldtab(a1 + t1.off[0] * ng), r1 = ldtab(a1 + t1.off[1] * ng), r2 = ldtab(a1 + t1.off[2] * ng),
+                   r3 = ldtab(a1 + t1.off[3] * ng);
 #pragma unroll
       for (int u = 0; u < U; ++u) d1[u] = ((t1.w[0] * r0[u] + t1.w[1] * r1[u]) + t1.w[2] * r2[u]) + t1.w[3] * r3[u];
       if (LOWER && t1.n == 6) {
-        const Row<U> r4 = ldrow<U>(a1 + t1.off[4] * ng), r5 = ldrow<U>(a1 + t1.off[5] * ng);
+        const Row<U> r4 = ldtab(a1 + t1.off[4] * ng), r5 = ldtab(a1 + t1.off[5] * ng);
 #pragma unroll
         for (int u = 0; u < U; ++u) d1[u] = (d1[u] + t1.w[4] * r4[u]) + t1.w[5] * r5[u];
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = s0.speccomb * d0[u] + s1.speccomb * d1[u];
+    CB_COV(0, B, LOWER, !LOWER ? COV_S0_MID : (s0.specparm < 0.125 ? COV_S0_LOW : (s0.specparm > 0.875 ? COV_S0_HIGH : COV_S0_MID)));
+    CB_COV(0, B, LOWER, !LOWER ? COV_S1_MID : (s1.specparm < 0.125 ? COV_S1_LOW : (s1.specparm > 0.875 ? COV_S1_HIGH : COV_S1_MID)));
   }
+  if (R.kind >= 1 && acc[0] > 0.) CB_COV(0, B, LOWER, COV_KEY_NONZERO);
   // ---- water-vapour self and foreign continua
   if (R.self) {
     const double selffac = WSF(F_SELFFAC), selffrac = WSF(F_SELFFRAC);
-    const double* __restrict__ s = tb + O.selfref + (size_t)(inds - 1) * ng + g0;
-    const Row<U> k0 = ldrow<U>(s), k1 = ldrow<U>(s + ng);
+    const double* __restrict__ s = gb + (size_t)(O.selfref + inds - 1) * ng;
+    const Row<U> k0 = ldtab(s), k1 = ldtab(s + ng);
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = acc[u] + selffac * (k0[u] + selffrac * (k1[u] - k0[u]));
+    if (selffac * (k0[0] + selffrac * (k1[0] - k0[0])) > 0.) CB_COV(0, B, LOWER, COV_SELF_NONZERO);
   }
   if (R.forn) {
     const double forfac = WSF(F_FORFAC), forfrac = WSF(F_FORFRAC);
-    const double* __restrict__ s = tb + O.forref + (size_t)(indf - 1) * ng + g0;
-    const Row<U> k0 = ldrow<U>(s), k1 = ldrow<U>(s + ng);
+    const double* __restrict__ s = gb + (size_t)(O.forref + indf - 1) * ng;
+    const Row<U> k0 = ldtab(s), k1 = ldtab(s + ng);
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = acc[u] + forfac * (k0[u] + forfrac * (k1[u] - k0[u]));
+    if (forfac * (k0[0] + forfrac * (k1[0] - k0[0])) > 0.) CB_COV(0, B, LOWER, COV_FOR_NONZERO);
   }
   // ---- minor gases
   if (R.nminor > 0) {
@@ -865,17 +881,19 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
           const double adjfac = M.base + pow(ratio - M.base, M.expo);
           const double ref2 = M.ref355 ? (double)3.55e-4f : ref;
           amount = adjfac * ref2 * coldry * 1.e-20;
+          CB_COV(0, B, LOWER, COV_MINOR0_ADJ + k);
         } else {
           amount = colx;
         }
       }
+      if (amount > 0.) CB_COV(0, B, LOWER, COV_MINOR0_NONZERO + k);
       if (M.binary) {
         constexpr double n = LOWER ? 8. : 4.;
         constexpr int nsp = LOWER ? 9 : 5;
         const double refr = M.refr == RM_A ? O.refrat_m_a : (M.refr == RM_B ? O.refrat_m_b : O.refrat_m_a3);
         const BinSpec sm = binspec(cola, refr, colb, n, T.oneminus);
-        const double* __restrict__ t = tb + O.m[M.slot] + ((size_t)(sm.js - 1) + nsp * (size_t)(indm - 1)) * ng + g0;
-        const Row<U> k00 = ldrow<U>(t), k10 = ldrow<U>(t + ng), k01 = ldrow<U>(t + nsp * ng), k11 = ldrow<U>(t + (nsp + 1) * ng);
+        const double* __restrict__ t = gb + ((size_t)O.m[M.slot] + (size_t)(sm.js - 1) + nsp * (size_t)(indm - 1)) * ng;
+        const Row<U> k00 = ldtab(t), k10 = ldtab(t + ng), k01 = ldtab(t + nsp * ng), k11 = ldtab(t + (nsp + 1) * ng);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const double m1 = k00[u] + sm.fs * (k10[u] - k00[u]);
@@ -883,8 +901,8 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
           acc[u] = acc[u] + amount * (m1 + minorfrac * (m2 - m1));
         }
       } else {
-        const double* __restrict__ t = tb + O.m[M.slot] + (size_t)(indm - 1) * ng + g0;
-        const Row<U> k0 = ldrow<U>(t), k1 = ldrow<U>(t + ng);
+        const double* __restrict__ t = gb + (size_t)(O.m[M.slot] + indm - 1) * ng;
+        const Row<U> k0 = ldtab(t), k1 = ldtab(t + ng);
 #pragma unroll
         for (int u = 0; u < U; ++u) acc[u] = acc[u] + amount * (k0[u] + minorfrac * (k1[u] - k0[u]));
       }
@@ -894,8 +912,9 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
 #pragma unroll
   for (int k = 0; k < R.nx; ++k) {
     const double wx = WSF(F_WX1 + R.xwx[k]);
-    const double* __restrict__ t = tb + O.x[R.xslot[k]] + g0;
-    const Row<U> xr = ldrow<U>(t);
+    if (wx > 0.) CB_COV(0, B, LOWER, COV_XSEC0_NONZERO + k);
+    const double* __restrict__ t = gb + (size_t)O.x[R.xslot[k]] * ng;
+    const Row<U> xr = ldtab(t);
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = acc[u] + wx * xr[u];
   }
@@ -937,15 +956,16 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
   } else if (R.planck == 1) {
     constexpr double n = LOWER ? 8. : 4.;
     const BinSpec sp = binspec(cola, LOWER ? O.refrat_planck_a : O.refrat_planck_b, colb, n, T.oneminus);
-    const double* __restrict__ f = tb + (LOWER ? O.fracrefa : O.fracrefb) + (size_t)(sp.js - 1) * ng + g0;
-    const Row<U> f0 = ldrow<U>(f), f1 = ldrow<U>(f + ng);
+    CB_COV(0, B, LOWER, COV_PLANCK_INTERP);
+    const double* __restrict__ f = gb + (size_t)((LOWER ? O.fracrefa : O.fracrefb) + sp.js - 1) * ng;
+    const Row<U> f0 = ldtab(f), f1 = ldtab(f + ng);
 #pragma unroll
     for (int u = 0; u < U; ++u) frac[u] = f0[u] + sp.fs * (f1[u] - f0[u]);
   } else {
     // band 6 and 12/15 have no "b" table; band 6 upper uses fracrefa (taumol.f90:1388)
     constexpr bool use_a = LOWER || B == 6;
-    const double* __restrict__ f = tb + (use_a ? O.fracrefa : O.fracrefb) + g0;
-    const Row<U> f0 = ldrow<U>(f);
+    const double* __restrict__ f = gb + (size_t)(use_a ? O.fracrefa : O.fracrefb) * ng;
+    const Row<U> f0 = ldtab(f);
 #pragma unroll
     for (int u = 0; u < U; ++u) frac[u] = f0[u];
   }
@@ -980,21 +1000,25 @@ CB_HD int band_gstart(int ib) {  // first g-point of band ib (0-based), for code
   }
 }
 
-template <int B, int U>
-CB_HD void lw_taumol_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int g0, int l0, int l1) {
+// staged: the (band, group) block of band tables already copied to shared memory (CUDA kernel only), else null -> read from HBM
+template <int B, int U, bool STAGED = false>
+CB_HD void lw_taumol_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int g0, int l0, int l1,
+                          const double* __restrict__ staged = nullptr) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
   const size_t wstride = (size_t)nlay * ncc;
   const int laytrop = W.laytrop[c];
   const int gabs = kGS[B - 1] + g0;
+  const BandOff& O = T.b[B - 1];
+  const double* __restrict__ gb = (STAGED ? staged : T.base + O.base + (size_t)(g0 / TGW) * O.rows * TGW) + (g0 % TGW);
   for (int l = l0; l < l1; ++l) {
     const int lev = l + 1;
     const int idx = W.idx[(size_t)l * ncc + c];
     const double pavel = in.play[(size_t)l * ncol + gc];
     double tau[U], frac[U];
     const double* ws = W.ws + (size_t)l * ncc + c;
-    if (lev <= laytrop) eval_band<B, true, U>(T, ws, wstride, idx, pavel, g0, tau, frac);
-    else eval_band<B, false, U>(T, ws, wstride, idx, pavel, g0, tau, frac);
+    if (lev <= laytrop) eval_band<B, true, U, STAGED>(T, gb, ws, wstride, idx, pavel, g0, tau, frac);
+    else eval_band<B, false, U, STAGED>(T, gb, ws, wstride, idx, pavel, g0, tau, frac);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;

@@ -11,6 +11,7 @@
 
 #include "../../include/climt_b200.h"
 #include "engine_common.h"
+#include "cb_async.cuh"
 #include "lw_tables.h"
 #include "mcica_host.h"
 #include "mcica_compat.h"
@@ -57,20 +58,44 @@ struct UnitList {
 #define CB_LW_LAYER_CHUNKS 4  // taumol: layers are independent -> blockIdx.z cuts them into chunks for more threads in flight
 #endif
 
+#ifndef CB_LW_STAGE
+#define CB_LW_STAGE 1  // stage the table block of single-key-species bands in shared memory (0: every band reads HBM through L1/L2)
+#endif
+// Bands whose lower- AND upper-atmosphere regions have at most one key species: their whole (band, 4-g-point group) table block
+// (k-distribution for both regions, continua, minor gases, Planck fractions: 8-14 KB) fits beside 4 resident blocks per SM.
+__host__ __device__ constexpr bool lw_band_staged(int B) {
+  return CB_LW_STAGE && (B == 1 || B == 2 || B == 6 || B == 8 || B == 10 || B == 11 || B == 14);
+}
+
 // taumol: one block = 128 adjacent columns x one unit (<= 4 g-points of one band) x one chunk of layers; every branch on
-// the band is block-uniform, all global accesses are column-contiguous.
+// the band is block-uniform, all global accesses are column-contiguous.  For the single-key-species bands the block first pulls
+// its table block into shared memory with ONE bulk asynchronous copy (cp.async.bulk -> UBLKCP, completion on an mbarrier): the
+// 4-12 table gathers per (layer, unit) then hit shared memory instead of L1/L2 (r01 ncu: L1 hit 47 %, L2 hit 45 %).
 __global__ void __launch_bounds__(kBlock, CB_LW_TAU_MIN_BLOCKS)
     k_lw_taumol(const __grid_constant__ Tables T, const __grid_constant__ In in, const __grid_constant__ Work W,
                 const __grid_constant__ UnitList UL, int c0, int n) {
+  extern __shared__ __align__(128) double s_tab[];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const Unit un = UL.u[blockIdx.y];
+  if (lw_band_staged(un.band)) {  // block-uniform
+    const BandOff& O = T.b[un.band - 1];
+    const unsigned bytes = (unsigned)O.rows * TGW * sizeof(double);
+    if (threadIdx.x == 0) cb::bulk::mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      cb::bulk::mbar_arrive_expect_tx(&s_bar, bytes);
+      cb::bulk::copy_g2s(s_tab, T.base + O.base + (size_t)(un.g0 / TGW) * O.rows * TGW, bytes, &s_bar);
+    }
+    cb::bulk::mbar_wait(&s_bar, 0);
+  }
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
-  const Unit un = UL.u[blockIdx.y];
   const int per = (in.nlay + gridDim.z - 1) / gridDim.z;
   const int l0 = blockIdx.z * per, l1 = min(in.nlay, l0 + per);
-#define CB_CASE(B)                                                       \
-  case B:                                                                \
-    if (un.u == 4) lw_taumol_unit<B, 4>(T, in, W, c0, c, un.g0, l0, l1);  \
-    else lw_taumol_unit<B, 2>(T, in, W, c0, c, un.g0, l0, l1);            \
+#define CB_CASE(B)                                                                                   \
+  case B:                                                                                            \
+    if (un.u == 4) lw_taumol_unit<B, 4, lw_band_staged(B)>(T, in, W, c0, c, un.g0, l0, l1, s_tab);    \
+    else lw_taumol_unit<B, 2, lw_band_staged(B)>(T, in, W, c0, c, un.g0, l0, l1, s_tab);              \
     break;
   switch (un.band) {
     CB_CASE(1) CB_CASE(2) CB_CASE(3) CB_CASE(4) CB_CASE(5) CB_CASE(6) CB_CASE(7) CB_CASE(8)
@@ -139,6 +164,7 @@ struct cb200_lw_engine {
   int ext_ncol = 0, ext_nlay = 0;
   UnitList UL;      // transfer kernel units (<= CB_LW_UMAX g-points); `part` holds one flux set per unit
   UnitList UL_tau;  // taumol kernel units (<= CB_LW_TAU_UMAX g-points)
+  size_t tau_smem = 0;  // dynamic shared memory of k_lw_taumol: the largest staged (band, group) table block
   // workspace (grown on demand)
   int cap_ncc = 0, cap_nlay = 0, cap_npart = 0;
   Work W{};
@@ -211,6 +237,8 @@ extern "C" int cb200_lw_create(cb200_lw_engine** out, const char* table_blob, co
     e->T.base = e->d_tables;
     e->UL.n = build_units(e->UL.u, CB_LW_UMAX);
     e->UL_tau.n = build_units(e->UL_tau.u, CB_LW_TAU_UMAX);
+    for (int b = 1; b <= 16; ++b)
+      if (lw_band_staged(b)) e->tau_smem = std::max(e->tau_smem, (size_t)e->T.b[b - 1].rows * TGW * sizeof(double));
     if (const char* mc = std::getenv("CLIMT_B200_MAX_CHUNK")) e->max_chunk = std::max(128, std::atoi(mc));
     if (const char* z = std::getenv("CLIMT_B200_SKIP_ZERO_INPUTS")) e->skip_zero_inputs = std::atoi(z) != 0;
     cudaMallocHost(&e->h_err, sizeof(int));
@@ -294,7 +322,7 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
   k_prep<<<gw, 32, 0, st>>>(e->T, in, e->fl, W, c0, n);
   if (e->fl.icld >= 1) { k_cld_scale<<<dim3(gx, nlay), kBlock, 0, st>>>(in, e->fl, W, c0, n); e->launches += 1; }
   if (e->timing) cudaEventRecord(e->ev0, st);
-  k_lw_taumol<<<dim3(gx, e->UL_tau.n, CB_LW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, in, W, e->UL_tau, c0, n);
+  k_lw_taumol<<<dim3(gx, e->UL_tau.n, CB_LW_LAYER_CHUNKS), kBlock, e->tau_smem, st>>>(e->T, in, W, e->UL_tau, c0, n);
   if (e->timing) cudaEventRecord(e->evm, st);
   // non-McICA: icld = 1 -> rtrn (random overlap); icld = 2, 3 -> rtrnmr (maximum-random), rrtmg_lw_rad.nomcica.f90:527-541
   const dim3 gu(gx, e->UL.n);
@@ -456,6 +484,22 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
     W.mask = e->d_mask_full;
     W.mstride = ncol;
   }
+  // pageable caller arrays go through the pipe's pinned staging slots (engine_common.h); page-locked ones are read / written in place
+  bool pg_in[23], pg_out[8], any_pg_in = false, any_pg_out = false;
+  for (int i = 0; i < 23; ++i) { pg_in[i] = used[i] && hp[i] && !cb::HostPipe::dma_able(hp[i]); any_pg_in |= pg_in[i]; }
+  for (int i = 0; i < nout; ++i) { pg_out[i] = !cb::HostPipe::dma_able(hop[i]); any_pg_out |= pg_out[i]; }
+  if (any_pg_in || any_pg_out) CUDA_OK(P.ensure_staging(any_pg_in ? irow_tot * (size_t)chunk : 0, any_pg_out ? orow_tot * (size_t)chunk : 0));
+  struct { int s, c0, n; bool valid; } prev{0, 0, 0, false};
+  auto drain_outputs = [&](int ps, int pc0, int pn) -> cudaError_t {  // staged outputs of a finished chunk -> the caller's arrays
+    cudaError_t ce = cudaEventSynchronize(P.out_done[ps]);
+    if (ce != cudaSuccess) return ce;
+    size_t o = 0;
+    for (int i = 0; i < nout; ++i) {
+      if (pg_out[i]) cb::HostPipe::scatter_staged_finish(hop[i], P.h_out[ps] + o, orows[i], ncol, pc0, pn);
+      o += (size_t)orows[i] * pn;
+    }
+    return cudaSuccess;
+  };
   int k = 0;
   for (int c0 = 0, n = 0; c0 < ncol; c0 += n, ++k) {
     n = P.chunk_size(k, ncol - c0);
@@ -481,6 +525,7 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
     }
     // H2D: the slot is free once the chunk that last used it has been computed
     CUDA_OK(cudaStreamWaitEvent(P.s_in, P.cmp_done[s], 0));
+    if (any_pg_in) CUDA_OK(cudaEventSynchronize(P.in_done[s]));  // the copies that last read this staging slot have left the host
     P.mark(P.s_in, k, 0);
     cb200_lw_inputs din;
     const double** dp = reinterpret_cast<const double**>(&din);
@@ -490,7 +535,8 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
       if (zero[i]) {
         CUDA_OK(cudaMemsetAsync(P.d_in[s] + off, 0, (size_t)irows[i] * inner[i] * n * sizeof(double), P.s_in));
       } else {
-        CUDA_OK(P.gather(P.d_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
+        if (pg_in[i]) CUDA_OK(P.gather_staged(P.d_in[s] + off, P.h_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
+        else CUDA_OK(P.gather(P.d_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
         e->h2d_bytes += (size_t)irows[i] * inner[i] * n * sizeof(double);
       }
       dp[i] = P.d_in[s] + off;
@@ -515,10 +561,21 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
     P.mark(P.s_cmp, k, 3);
     // D2H
     CUDA_OK(cudaStreamWaitEvent(P.s_out, P.cmp_done[s], 0));
-    for (int i = 0; i < nout; ++i) CUDA_OK(P.scatter(hop[i], dop[i], orows[i], ncol, c0, n));
+    {
+      size_t o = 0;
+      for (int i = 0; i < nout; ++i) {
+        if (pg_out[i]) CUDA_OK(P.scatter_staged_issue(P.h_out[s] + o, dop[i], orows[i], n));
+        else CUDA_OK(P.scatter(hop[i], dop[i], orows[i], ncol, c0, n));
+        o += (size_t)orows[i] * n;
+      }
+    }
     CUDA_OK(cudaEventRecord(P.out_done[s], P.s_out));
     P.mark(P.s_out, k, 4);
+    // the previous chunk's staged outputs are copied out while this chunk runs
+    if (any_pg_out && prev.valid) CUDA_OK(drain_outputs(prev.s, prev.c0, prev.n));
+    prev = {s, c0, n, true};
   }
+  if (any_pg_out && prev.valid) CUDA_OK(drain_outputs(prev.s, prev.c0, prev.n));
   CUDA_OK(cudaGetLastError());
   return 0;
 }

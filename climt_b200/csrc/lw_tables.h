@@ -103,11 +103,37 @@ inline void build_tables(const std::string& blob_path, const Constants& k, std::
     char pre[8];
     std::snprintf(pre, sizeof pre, "b%02d.", ib);
     BandOff& O = T.b[ib - 1];
-    auto opt = [&](const char* nm) { std::string key = std::string(pre) + nm; return b.has(key) ? putk(key) : -1; };
+    const int ng = kNG[ib - 1], ngrp = (ng + TGW - 1) / TGW;
+    // Every table of the band is (rows, ng) in the blob, g-point fastest.  Collect them, then write one block per group of TGW
+    // g-points holding all of them row after row (layout: see BandOff in lw_core.cuh).
+    std::vector<const BlobView::Ent*> ents;
+    int nrows = 0;
+    auto opt = [&](const char* nm) {
+      const std::string key = std::string(pre) + nm;
+      if (!b.has(key)) return -1;
+      const BlobView::Ent& e = b.get(key);
+      if (e.count % ng) throw std::runtime_error("table " + key + ": size is not a multiple of the band's g-point count");
+      ents.push_back(&e);
+      const int r0 = nrows;
+      nrows += (int)(e.count / ng);
+      return r0;
+    };
     O.absa = opt("absa"); O.absb = opt("absb"); O.selfref = opt("selfref"); O.forref = opt("forref");
     O.fracrefa = opt("fracrefa"); O.fracrefb = opt("fracrefb");
     for (int s = 0; s < 5; ++s) O.m[s] = kMinorNames[ib - 1][s] ? opt(kMinorNames[ib - 1][s]) : -1;
     for (int s = 0; s < 2; ++s) O.x[s] = kXsecNames[ib - 1][s] ? opt(kXsecNames[ib - 1][s]) : -1;
+    while (img.size() & 15) img.push_back(0.0);  // 128-byte aligned blocks (cp.async.bulk needs 16)
+    O.base = (int)img.size();
+    O.rows = nrows;
+    for (int q = 0; q < ngrp; ++q)
+      for (const BlobView::Ent* e : ents) {
+        const int rows = (int)(e->count / ng);
+        for (int r = 0; r < rows; ++r)
+          for (int j = 0; j < TGW; ++j) {
+            const int g = q * TGW + j;
+            img.push_back(g < ng ? e->p[(size_t)r * ng + g] : 0.0);
+          }
+      }
   }
   // reference ratios (rrtmg_lw_taumol.f90:506-509, 777-778, 1040-1042, 1410-1411, 1806-1807, 2211, 2420-2422,
   // 2737-2738, 2951)

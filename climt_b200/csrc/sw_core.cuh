@@ -477,6 +477,7 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
   const double colh2o = WSF(F_COLH2O);
   int js = 0;
   double fs = 0.;
+  CB_COV(1, B, LOWER, COV_REGION);
   // water-vapour continua (SW: un-premultiplied selffac/forfac, rrtmg_sw_setcoef.f90:232,238)
   double cont[U];
 #pragma unroll
@@ -491,10 +492,13 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
 #pragma unroll
       for (int u = 0; u < U; ++u)
         cont[u] = selffac * (s0[u] + selffrac * (s1[u] - s0[u])) + forfac * (f0[u] + forfrac * (f1[u] - f0[u]));
+      if (colh2o * selffac * (s0[0] + selffrac * (s1[0] - s0[0])) > 0.) CB_COV(1, B, LOWER, COV_SELF_NONZERO);
+      if (colh2o * forfac * (f0[0] + forfrac * (f1[0] - f0[0])) > 0.) CB_COV(1, B, LOWER, COV_FOR_NONZERO);
     } else {
       const Row<U> f0 = ldrow<U>(f), f1 = ldrow<U>(f + ng);
 #pragma unroll
       for (int u = 0; u < U; ++u) cont[u] = forfac * (f0[u] + forfrac * (f1[u] - f0[u]));
+      if (colh2o * cont[0] > 0.) CB_COV(1, B, LOWER, COV_FOR_NONZERO);
     }
   }
   if (R.kind == 2) {
@@ -508,6 +512,8 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     const double specmult = n * specparm;
     js = 1 + (int)specmult;
     fs = fmod(specmult, 1.);
+    CB_COV(1, B, LOWER, specparm < 0.125 ? COV_S0_LOW : (specparm > 0.875 ? COV_S0_HIGH : COV_S0_MID));  // (SW has one stencil: bins only)
+    if (speccomb > 0.) CB_COV(1, B, LOWER, COV_KEY_NONZERO);
     const double f000 = (1. - fs) * fac00, f010 = (1. - fs) * fac10, f100 = fs * fac00, f110 = fs * fac10;
     const double f001 = (1. - fs) * fac01, f011 = (1. - fs) * fac11, f101 = fs * fac01, f111 = fs * fac11;
     const int row0 = (LOWER ? ((jp - 1) * 5 + (jt - 1)) * nsp : ((jp - 13) * 5 + (jt - 1)) * nsp) + js - 1;
@@ -535,6 +541,7 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     const int row0 = LOWER ? ((jp - 1) * 5 + (jt - 1)) * nsp : ((jp - 13) * 5 + (jt - 1)) * nsp;
     const int row1 = LOWER ? (jp * 5 + (jt1 - 1)) * nsp : ((jp - 12) * 5 + (jt1 - 1)) * nsp;
     const double cola = WSF(F_COLH2O + R.a);
+    if (cola > 0.) CB_COV(1, B, LOWER, COV_KEY_NONZERO);
     const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
     const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
     const Row<U> k00 = ldrow<U>(a0), k10 = ldrow<U>(a0 + ng), k01 = ldrow<U>(a1), k11 = ldrow<U>(a1 + ng);
@@ -554,6 +561,7 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
   if (R.extra == X_CH4 || R.extra == X_O3 || R.extra == X_CO2 || R.extra == X_H2O) {
     const int gas = R.extra == X_CH4 ? CH4 : (R.extra == X_O3 ? O3 : (R.extra == X_CO2 ? CO2 : H2O));
     const double colx = WSF(F_COLH2O + gas);
+    if (colx > 0.) CB_COV(1, B, LOWER, COV_XSEC0_NONZERO);
     const double* __restrict__ x = tb + (R.xslot == 0 ? O.x0 : O.x1) + g0;
     const Row<U> xr = ldrow<U>(x);
 #pragma unroll
@@ -585,6 +593,7 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
   // solar source function at this layer (only evaluated at layer laysolfr)
   if (want_src) {
     constexpr bool interp = src_interp<B>();
+    if (interp) CB_COV(1, B, LOWER, COV_PLANCK_INTERP);
     auto val = [&](int off, int u) {
       if (interp) {
         const double* __restrict__ t = tb + off + (size_t)(js - 1) * ng + g0 + u;

@@ -424,6 +424,22 @@ static int sw_host_enqueue(cb200_sw_engine* e, int ncol, int nlay, double adjes,
     W.mask = e->d_mask_full;
     W.mstride = ncol;
   }
+  // pageable caller arrays go through the pipe's pinned staging slots (engine_common.h); page-locked ones are read / written in place
+  bool pg_in[29], pg_out[8], any_pg_in = false, any_pg_out = false;
+  for (int i = 0; i < 29; ++i) { pg_in[i] = used[i] && hp[i] && !cb::HostPipe::dma_able(hp[i]); any_pg_in |= pg_in[i]; }
+  for (int i = 0; i < 6; ++i) { pg_out[i] = !cb::HostPipe::dma_able(hop[i]); any_pg_out |= pg_out[i]; }
+  if (any_pg_in || any_pg_out) CUDA_OK(P.ensure_staging(any_pg_in ? irow_tot * (size_t)chunk : 0, any_pg_out ? orow_tot * (size_t)chunk : 0));
+  struct { int s, c0, n; bool valid; } prev{0, 0, 0, false};
+  auto drain_outputs = [&](int ps, int pc0, int pn) -> cudaError_t {  // staged outputs of a finished chunk -> the caller's arrays
+    cudaError_t ce = cudaEventSynchronize(P.out_done[ps]);
+    if (ce != cudaSuccess) return ce;
+    size_t o = 0;
+    for (int i = 0; i < 6; ++i) {
+      if (pg_out[i]) cb::HostPipe::scatter_staged_finish(hop[i], P.h_out[ps] + o, orows[i], ncol, pc0, pn);
+      o += (size_t)orows[i] * pn;
+    }
+    return cudaSuccess;
+  };
   int k = 0;
   for (int c0 = 0, n = 0; c0 < ncol; c0 += n, ++k) {
     n = P.chunk_size(k, ncol - c0);
@@ -435,6 +451,7 @@ static int sw_host_enqueue(cb200_sw_engine* e, int ncol, int nlay, double adjes,
       for (int i = 16; i <= 24; ++i) zero[i] = zz;
     }
     CUDA_OK(cudaStreamWaitEvent(P.s_in, P.cmp_done[s], 0));
+    if (any_pg_in) CUDA_OK(cudaEventSynchronize(P.in_done[s]));  // the copies that last read this staging slot have left the host
     P.mark(P.s_in, k, 0);
     cb200_sw_inputs din;
     const double** dp = reinterpret_cast<const double**>(&din);
@@ -444,7 +461,8 @@ static int sw_host_enqueue(cb200_sw_engine* e, int ncol, int nlay, double adjes,
       if (zero[i]) {
         CUDA_OK(cudaMemsetAsync(P.d_in[s] + off, 0, (size_t)irows[i] * inner[i] * n * sizeof(double), P.s_in));
       } else {
-        CUDA_OK(P.gather(P.d_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
+        if (pg_in[i]) CUDA_OK(P.gather_staged(P.d_in[s] + off, P.h_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
+        else CUDA_OK(P.gather(P.d_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
         e->h2d_bytes += (size_t)irows[i] * inner[i] * n * sizeof(double);
       }
       dp[i] = P.d_in[s] + off;
@@ -466,10 +484,21 @@ static int sw_host_enqueue(cb200_sw_engine* e, int ncol, int nlay, double adjes,
     CUDA_OK(cudaEventRecord(P.cmp_done[s], P.s_cmp));
     P.mark(P.s_cmp, k, 3);
     CUDA_OK(cudaStreamWaitEvent(P.s_out, P.cmp_done[s], 0));
-    for (int i = 0; i < 6; ++i) CUDA_OK(P.scatter(hop[i], dop[i], orows[i], ncol, c0, n));
+    {
+      size_t o = 0;
+      for (int i = 0; i < 6; ++i) {
+        if (pg_out[i]) CUDA_OK(P.scatter_staged_issue(P.h_out[s] + o, dop[i], orows[i], n));
+        else CUDA_OK(P.scatter(hop[i], dop[i], orows[i], ncol, c0, n));
+        o += (size_t)orows[i] * n;
+      }
+    }
     CUDA_OK(cudaEventRecord(P.out_done[s], P.s_out));
     P.mark(P.s_out, k, 4);
+    // the previous chunk's staged outputs are copied out while this chunk runs
+    if (any_pg_out && prev.valid) CUDA_OK(drain_outputs(prev.s, prev.c0, prev.n));
+    prev = {s, c0, n, true};
   }
+  if (any_pg_out && prev.valid) CUDA_OK(drain_outputs(prev.s, prev.c0, prev.n));
   CUDA_OK(cudaGetLastError());
   return 0;
 }

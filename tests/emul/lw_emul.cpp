@@ -106,3 +106,12 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
     return -1;
   }
 }
+
+#ifdef CB_COVERAGE
+// branch-coverage counters of the taumol evaluator (tools/taumol_coverage.py): [band 0..31][lower][id]
+static long g_cov[32][2][cb::COV_N];
+extern "C" void cb_cov_hit(int engine, int band, int lower, int id) { if (engine == 0 && band >= 0 && band < 32 && id < cb::COV_N) ++g_cov[band][lower][id]; }
+extern "C" void emul_cov_reset() { std::memset(g_cov, 0, sizeof g_cov); }
+extern "C" void emul_cov_get(long* out /*[32][2][COV_N]*/) { std::memcpy(out, g_cov, sizeof g_cov); }
+extern "C" int emul_cov_n() { return cb::COV_N; }
+#endif

@@ -41,12 +41,14 @@ for name, fn in (("lw", lambda: eng.run_device(ncol, nlay, d_in, d_out)),
     res[name + "_step_ms"] = e0.elapsed_time(e1) / 10
     e = eng if name == "lw" else engs
     e.enable_timing(True)
-    ms = []
+    ms, tms = [], []
     for _ in range(5):
         fn()
         torch.cuda.synchronize()
         ms.append(e.last_unit_kernel_ms)
+        tms.append(e.last_taumol_kernel_ms)
     e.enable_timing(False)
     res[name + "_units_ms"] = float(np.mean(ms))
+    res[name + "_taumol_ms"] = float(np.mean(tms))
 res["lw_checksum"] = float(d_out["dflx"].sum().item())
 print(json.dumps(res))
