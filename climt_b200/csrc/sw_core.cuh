@@ -27,8 +27,12 @@ enum WsField {
 };
 constexpr int NSCR = 16;  // per g-point scratch rows: 7 (ref, refd, tra, trad, dbt, rup, rupd) x {clear, total} + taug, taur
 
+// absa / absb / selfref / forref are stored like the longwave band tables (lw_core.cuh, BandOff): per group of 4 consecutive
+// g-points a contiguous block of rows x 4 doubles -- element (row r, g-point g) at X + (g / 4) * gs_X + r * 4 + (g % 4) -- so the
+// 2-8 table rows a taumol thread gathers per layer are neighbouring 32-byte sectors.  The per-g-point vectors keep (rows, ng).
 struct BandOff {
   int absa, absb, selfref, forref, sfluxref, irradnce, facbrght, snsptdrk;
+  int gs_absa, gs_absb, gs_selfref, gs_forref;  // group strides (rows * 4) of the four regrouped tables
   int raylv;   // per-g Rayleigh vector (bands 23, 25, 26, 27), rayla (band 24, (9, ng)) else -1
   int raylb;   // band 24 upper
   int x0, x1;  // absch4 | abso3a, abso3b | absco2, absh2o
@@ -102,7 +106,35 @@ constexpr int kNSPB[14] = {1, 5, 1, 1, 1, 5, 1, 0, 1, 0, 0, 1, 5, 1};
 // Two launch modes (see lw_core.cuh prep_column): LAYER_PART = inatm_sw + setcoef_sw + the ECMWF aerosol mix of layers
 // [l0, l1), independent per layer; COLUMN_PART = laytrop, cldprop_sw (routine-locals persist from layer to layer in the
 // Fortran), the solar-source layers.  <true, true> over [0, nlay) is the original single pass.
-template <bool LAYER_PART, bool COLUMN_PART>
+// ECMWF aerosols (iaer = 6), rad.nomcica.f90:693-727: band optical properties of one (column, layer) from the six aerosol types.
+// A function (and, on the device, a kernel of its own, launched only when iaer = 6) so that the option costs nothing when it is
+// off.  (It is NOT what makes k_sw_prep_layer a 255-register kernel -- that is the per-band cloud-optics arrays of cldprop_sw
+// in the same pass: ptxas reports the same 255 registers / 536-byte frame without this block.  The kernel is ~1 % of a step.)
+CB_HD void sw_aerosol_mix(const Tables& T, const In& in, const Work& W, int c0, int c, int l) {
+  const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
+  const size_t gc = (size_t)(c0 + c);
+  const double* tb = T.base;
+  for (int ib = 0; ib < 14; ++ib) {
+    double ta = 0., om = 0., as = 0.;
+    for (int ia = 0; ia < 6; ++ia) {
+      const double ec = in.ecaer[((size_t)ia * nlay + l) * ncol + gc];
+      const double rt = tb[T.rsrtaua + ib * 6 + ia], rp = tb[T.rsrpiza + ib * 6 + ia], ra = tb[T.rsrasya + ib * 6 + ia];
+      ta = ta + rt * ec;
+      om = om + rt * ec * rp;
+      as = as + rt * ec * rp * ra;
+    }
+    if (ta == 0.) { ta = 0.; as = 0.; om = 1.; }
+    else {
+      if (om != 0.) as = as / om;
+      if (ta != 0.) om = om / ta;
+    }
+    W.aer[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c] = ta;
+    W.aer[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c] = om;
+    W.aer[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c] = as;
+  }
+}
+
+template <bool LAYER_PART, bool COLUMN_PART, bool AER6 = true>
 CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const Work& W, int c0, int c, int l0, int l1) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
@@ -339,27 +371,7 @@ CB_HD void sw_prep_column(const Tables& T, const In& in, const Flags& fl, const 
         W.cld[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c] = asmcloud[ib];
       }
     }
-    // ---- ECMWF aerosols (iaer = 6), rad.nomcica.f90:693-727
-    if (LAYER_PART && fl.iaer == 6) {
-      for (int ib = 0; ib < 14; ++ib) {
-        double ta = 0., om = 0., as = 0.;
-        for (int ia = 0; ia < 6; ++ia) {
-          const double ec = in.ecaer[((size_t)ia * nlay + l) * ncol + gc];
-          const double rt = tb[T.rsrtaua + ib * 6 + ia], rp = tb[T.rsrpiza + ib * 6 + ia], ra = tb[T.rsrasya + ib * 6 + ia];
-          ta = ta + rt * ec;
-          om = om + rt * ec * rp;
-          as = as + rt * ec * rp * ra;
-        }
-        if (ta == 0.) { ta = 0.; as = 0.; om = 1.; }
-        else {
-          if (om != 0.) as = as / om;
-          if (ta != 0.) om = om / ta;
-        }
-        W.aer[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c] = ta;
-        W.aer[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c] = om;
-        W.aer[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c] = as;
-      }
-    }
+    if (LAYER_PART && AER6 && fl.iaer == 6) sw_aerosol_mix(T, in, W, c0, c, l);
   }
 #undef WS
   if (!COLUMN_PART) return;
@@ -467,6 +479,7 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
   constexpr Region R = region<B, LOWER>();
   constexpr int ib = B - 16;
   constexpr int ng = kNG[ib];
+  constexpr int RS = 4;  // row stride of the regrouped tables (see BandOff)
   const BandOff& O = T.b[ib];
   const double* __restrict__ tb = T.base;
 #define WSF(f) CB_LDG(ws + (size_t)(f) * wstride)
@@ -484,18 +497,18 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
   for (int u = 0; u < U; ++u) cont[u] = 0.;
   if (R.self || R.forn) {
     const double forfac = WSF(F_FORFAC), forfrac = WSF(F_FORFRAC);
-    const double* __restrict__ f = tb + O.forref + (size_t)(indf - 1) * ng + g0;
+    const double* __restrict__ f = tb + O.forref + (size_t)(g0 / RS) * O.gs_forref + (size_t)(indf - 1) * RS + (g0 % RS);
     if (R.self) {
       const double selffac = WSF(F_SELFFAC), selffrac = WSF(F_SELFFRAC);
-      const double* __restrict__ s = tb + O.selfref + (size_t)(inds - 1) * ng + g0;
-      const Row<U> s0 = ldrow<U>(s), s1 = ldrow<U>(s + ng), f0 = ldrow<U>(f), f1 = ldrow<U>(f + ng);
+      const double* __restrict__ s = tb + O.selfref + (size_t)(g0 / RS) * O.gs_selfref + (size_t)(inds - 1) * RS + (g0 % RS);
+      const Row<U> s0 = ldrow<U>(s), s1 = ldrow<U>(s + RS), f0 = ldrow<U>(f), f1 = ldrow<U>(f + RS);
 #pragma unroll
       for (int u = 0; u < U; ++u)
         cont[u] = selffac * (s0[u] + selffrac * (s1[u] - s0[u])) + forfac * (f0[u] + forfrac * (f1[u] - f0[u]));
       if (colh2o * selffac * (s0[0] + selffrac * (s1[0] - s0[0])) > 0.) CB_COV(1, B, LOWER, COV_SELF_NONZERO);
       if (colh2o * forfac * (f0[0] + forfrac * (f1[0] - f0[0])) > 0.) CB_COV(1, B, LOWER, COV_FOR_NONZERO);
     } else {
-      const Row<U> f0 = ldrow<U>(f), f1 = ldrow<U>(f + ng);
+      const Row<U> f0 = ldrow<U>(f), f1 = ldrow<U>(f + RS);
 #pragma unroll
       for (int u = 0; u < U; ++u) cont[u] = forfac * (f0[u] + forfrac * (f1[u] - f0[u]));
       if (colh2o * cont[0] > 0.) CB_COV(1, B, LOWER, COV_FOR_NONZERO);
@@ -518,10 +531,11 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     const double f001 = (1. - fs) * fac01, f011 = (1. - fs) * fac11, f101 = fs * fac01, f111 = fs * fac11;
     const int row0 = (LOWER ? ((jp - 1) * 5 + (jt - 1)) * nsp : ((jp - 13) * 5 + (jt - 1)) * nsp) + js - 1;
     const int row1 = (LOWER ? (jp * 5 + (jt1 - 1)) * nsp : ((jp - 12) * 5 + (jt1 - 1)) * nsp) + js - 1;
-    const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
-    const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
-    const Row<U> k000 = ldrow<U>(a0), k100 = ldrow<U>(a0 + ng), k010 = ldrow<U>(a0 + nsp * ng), k110 = ldrow<U>(a0 + (nsp + 1) * ng);
-    const Row<U> k001 = ldrow<U>(a1), k101 = ldrow<U>(a1 + ng), k011 = ldrow<U>(a1 + nsp * ng), k111 = ldrow<U>(a1 + (nsp + 1) * ng);
+    const double* __restrict__ ab = tb + (LOWER ? O.absa : O.absb) + (size_t)(g0 / RS) * (LOWER ? O.gs_absa : O.gs_absb) + (g0 % RS);
+    const double* __restrict__ a0 = ab + (size_t)row0 * RS;
+    const double* __restrict__ a1 = ab + (size_t)row1 * RS;
+    const Row<U> k000 = ldrow<U>(a0), k100 = ldrow<U>(a0 + RS), k010 = ldrow<U>(a0 + nsp * RS), k110 = ldrow<U>(a0 + (nsp + 1) * RS);
+    const Row<U> k001 = ldrow<U>(a1), k101 = ldrow<U>(a1 + RS), k011 = ldrow<U>(a1 + nsp * RS), k111 = ldrow<U>(a1 + (nsp + 1) * RS);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       double d = f000 * k000[u];
@@ -542,9 +556,10 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
     const int row1 = LOWER ? (jp * 5 + (jt1 - 1)) * nsp : ((jp - 12) * 5 + (jt1 - 1)) * nsp;
     const double cola = WSF(F_COLH2O + R.a);
     if (cola > 0.) CB_COV(1, B, LOWER, COV_KEY_NONZERO);
-    const double* __restrict__ a0 = tb + (LOWER ? O.absa : O.absb) + (size_t)row0 * ng + g0;
-    const double* __restrict__ a1 = tb + (LOWER ? O.absa : O.absb) + (size_t)row1 * ng + g0;
-    const Row<U> k00 = ldrow<U>(a0), k10 = ldrow<U>(a0 + ng), k01 = ldrow<U>(a1), k11 = ldrow<U>(a1 + ng);
+    const double* __restrict__ ab = tb + (LOWER ? O.absa : O.absb) + (size_t)(g0 / RS) * (LOWER ? O.gs_absa : O.gs_absb) + (g0 % RS);
+    const double* __restrict__ a0 = ab + (size_t)row0 * RS;
+    const double* __restrict__ a1 = ab + (size_t)row1 * RS;
+    const Row<U> k00 = ldrow<U>(a0), k10 = ldrow<U>(a0 + RS), k01 = ldrow<U>(a1), k11 = ldrow<U>(a1 + RS);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const double k4 = fac00 * k00[u] + fac10 * k10[u] + fac01 * k01[u] + fac11 * k11[u];
@@ -716,8 +731,55 @@ CB_HD void sw_taumol_unit(const Tables& T, const Solar& sol, const In& in, const
   }
 }
 
+// Layer optical properties of one g-point in one layer: delta-scaled clear-sky mix (gas + Rayleigh + aerosol), two-stream R/T and
+// direct-beam transmittance (spcvrt.f90:430-514), and -- cloudy column -- the same for the layer's overcast part mixed by the
+// cloud fraction (:516-588).  Used by both sweeps of sw_transfer_unit when the layer properties are recomputed instead of carried.
+struct SwLayer {
+  double refc, refdc, trac, tradc, dbtc;  // clear
+  double ref, refd, tra, trad, dbt;       // total (cloud-fraction mix); only set for cloudy columns
+};
+CB_HD SwLayer sw_layer_props(const double* __restrict__ exp_tbl, double bpade, double prmu0, double taug, double taur,
+                             double ptaua, double pomga, double pasya, bool cloudy_col, double pclfr, double ptauc,
+                             double pomgc, double pasyc) {
+  SwLayer L;
+  double ztauc = taur + taug + ptaua;
+  double zomcc = taur * 1.0 + ptaua * pomga;
+  double zgcc = fdiv(pasya * pomga * ptaua, zomcc);
+  zomcc = fdiv(zomcc, ztauc);
+  const double zf = zgcc * zgcc;
+  const double zwf = zomcc * zf;
+  ztauc = (1.0 - zwf) * ztauc;
+  zomcc = fdiv(zomcc - zwf, 1.0 - zwf);
+  zgcc = fdiv(zgcc - zf, 1.0 - zf);
+  reftra(exp_tbl, bpade, zgcc, prmu0, ztauc, zomcc, L.refc, L.refdc, L.trac, L.tradc);
+  L.dbtc = exp_neg(exp_tbl, bpade, fdiv(ztauc, prmu0));
+  L.ref = L.refd = L.tra = L.trad = L.dbt = 0.;
+  if (cloudy_col) {
+    // cloudy (overcast) two-stream of this layer and the cloud-fraction mix (spcvrt.f90:516-588)
+    const double ztauo = ztauc + ptauc;
+    double zomco = ztauc * zomcc + ptauc * pomgc;
+    const double zgco = fdiv(ptauc * pomgc * pasyc + ztauc * zomcc * zgcc, zomco);
+    zomco = fdiv(zomco, ztauo);
+    double refo = 0., refdo = 0., trao = 1., trado = 1.;
+    if (pclfr > 1.e-12) reftra(exp_tbl, bpade, zgco, prmu0, ztauo, zomco, refo, refdo, trao, trado);
+    const double zclear = 1.0 - pclfr, zcloud = pclfr;
+    L.ref = zclear * L.refc + zcloud * refo;
+    L.refd = zclear * L.refdc + zcloud * refdo;
+    L.tra = zclear * L.trac + zcloud * trao;
+    L.trad = zclear * L.tradc + zcloud * trado;
+    const double dbtmo = exp_neg(exp_tbl, bpade, fdiv(ztauo, prmu0));
+    L.dbt = zclear * L.dbtc + zcloud * dbtmo;
+  }
+  return L;
+}
+
+#ifndef CB_SW_RECOMPUTE
+#define CB_SW_RECOMPUTE 0  // 1: the downward sweep recomputes the layer properties from (taug, taur) instead of reading the five rows
+                           // the upward sweep stored: 4 instead of 14 scratch rows carried per g-point (clear sky), reftra twice
+#endif
+
 // spcvrt_sw / spcvmc_sw for U consecutive g-points of band ib (rrtmg_sw_spcvrt.f90:329-661) -- generic in the band.
-template <int U, bool MC>
+template <int U, bool MC, bool RECOMPUTE = (CB_SW_RECOMPUTE != 0)>
 CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int c0, int c,
                             int ib, int g0, int unit) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
@@ -736,86 +798,76 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
   const int gabs = band_gstart(ib) + g0;
   const size_t growstride = (size_t)NSCR * wstride;  // scratch stride between consecutive g-points
   double* __restrict__ scr0 = W.scr + ((size_t)gabs * NSCR) * wstride + c;
-  // ---- pass A: surface -> top.  layer optical properties, two-stream R/T, upward adding
-  double rupc[U], rupdc[U], rup[U], rupd[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) { rupc[u] = albdir; rupdc[u] = albdif; rup[u] = albdir; rupd[u] = albdif; }
-  for (int l = 0; l < nlay; ++l) {
-    // aerosol optical properties of this band/layer
-    double ptaua = 0., pomga = 1., pasya = 0.;
+  // aerosol / cloud optical properties of this band in layer l, and the McICA bits of the unit's g-points
+  struct BandLayer {
+    double ptaua, pomga, pasya, pclfr, ptauc, pomgc, pasyc;
+    unsigned mbits;
+  };
+  auto band_layer = [&](int l) {
+    BandLayer b{0., 1., 0., 0., 0., 1., 0., 0u};
     if (fl.iaer == 10) {
       const size_t oa = ((size_t)ib * nlay + l) * ncol + gc;
-      ptaua = in.tauaer[oa]; pomga = in.ssaaer[oa]; pasya = in.asmaer[oa];
+      b.ptaua = in.tauaer[oa]; b.pomga = in.ssaaer[oa]; b.pasya = in.asmaer[oa];
     } else if (fl.iaer == 6) {
-      ptaua = W.aer[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c];
-      pomga = W.aer[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c];
-      pasya = W.aer[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c];
+      b.ptaua = W.aer[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c];
+      b.pomga = W.aer[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c];
+      b.pasya = W.aer[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c];
     }
-    double pclfr_l = 0., ptauc_l = 0., pomgc_l = 1., pasyc_l = 0.;
-    unsigned mbits = 0u;
     if (cloudy_col) {
-      pclfr_l = MC ? 1.0 : in.cldfr[(size_t)l * ncol + gc];
-      ptauc_l = W.cld[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c];
-      pomgc_l = W.cld[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c];
-      pasyc_l = W.cld[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c];
+      b.pclfr = MC ? 1.0 : in.cldfr[(size_t)l * ncol + gc];
+      b.ptauc = W.cld[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c];
+      b.pomgc = W.cld[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c];
+      b.pasyc = W.cld[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c];
       if (MC) {
         const size_t ms = (size_t)W.mstride;
         const unsigned* mw = W.mask + ((size_t)l * 4) * ms + W.moff + c;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int g = gabs + u;
-          mbits |= ((mw[(size_t)(g >> 5) * ms] >> (g & 31)) & 1u) << u;
+          b.mbits |= ((mw[(size_t)(g >> 5) * ms] >> (g & 31)) & 1u) << u;
         }
       }
     }
+    return b;
+  };
+  auto layer = [&](const BandLayer& b, int u, double taug, double taur) {
+    // spcvmc: the sub-column is either overcast with its band's optics or clear (mcica_subcol_gen_sw.f90:523-548)
+    const bool on = !MC || ((b.mbits >> u) & 1u);
+    return sw_layer_props(exp_tbl, bpade, prmu0, taug, taur, b.ptaua, b.pomga, b.pasya, cloudy_col, on ? b.pclfr : 0.,
+                          on ? b.ptauc : 0., on ? b.pomgc : 1., on ? b.pasyc : 0.);
+  };
+  // ---- pass A: surface -> top.  layer optical properties, two-stream R/T, upward adding
+  double rupc[U], rupdc[U], rup[U], rupd[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) { rupc[u] = albdir; rupdc[u] = albdif; rup[u] = albdir; rupd[u] = albdif; }
+  for (int l = 0; l < nlay; ++l) {
+    const BandLayer b = band_layer(l);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       double* __restrict__ scr = scr0 + (size_t)u * growstride + (size_t)l * ncc;
       const double taug = scr[R_TAUG * wstride], taur = scr[R_TAUR * wstride];
-      // spcvmc: the sub-column is either overcast with its band's optics or clear (mcica_subcol_gen_sw.f90:523-548)
-      const bool on = !MC || ((mbits >> u) & 1u);
-      const double pclfr = on ? pclfr_l : 0., ptauc = on ? ptauc_l : 0., pomgc = on ? pomgc_l : 1., pasyc = on ? pasyc_l : 0.;
-      double ztauc = taur + taug + ptaua;
-      double zomcc = taur * 1.0 + ptaua * pomga;
-      double zgcc = fdiv(pasya * pomga * ptaua, zomcc);
-      zomcc = fdiv(zomcc, ztauc);
-      const double zf = zgcc * zgcc;
-      const double zwf = zomcc * zf;
-      ztauc = (1.0 - zwf) * ztauc;
-      zomcc = fdiv(zomcc - zwf, 1.0 - zwf);
-      zgcc = fdiv(zgcc - zf, 1.0 - zf);
-      double refc, refdc, trac, tradc;
-      reftra(exp_tbl, bpade, zgcc, prmu0, ztauc, zomcc, refc, refdc, trac, tradc);
-      const double dbtc = exp_neg(exp_tbl, bpade, fdiv(ztauc, prmu0));
+      const SwLayer L = layer(b, u, taug, taur);
       {
-        const double zreflect = frcp(1. - rupdc[u] * refdc);
-        const double rn = refc + (tradc * ((trac - dbtc) * rupdc[u] + dbtc * rupc[u])) * zreflect;
-        const double rdn = refdc + tradc * tradc * rupdc[u] * zreflect;
+        const double zreflect = frcp(1. - rupdc[u] * L.refdc);
+        const double rn = L.refc + (L.tradc * ((L.trac - L.dbtc) * rupdc[u] + L.dbtc * rupc[u])) * zreflect;
+        const double rdn = L.refdc + L.tradc * L.tradc * rupdc[u] * zreflect;
         rupc[u] = rn; rupdc[u] = rdn;
       }
-      scr[0 * wstride] = refc; scr[1 * wstride] = refdc; scr[2 * wstride] = trac; scr[3 * wstride] = tradc;
-      scr[4 * wstride] = dbtc; scr[5 * wstride] = rupc[u]; scr[6 * wstride] = rupdc[u];
+      if (!RECOMPUTE) {
+        scr[0 * wstride] = L.refc; scr[1 * wstride] = L.refdc; scr[2 * wstride] = L.trac; scr[3 * wstride] = L.tradc;
+        scr[4 * wstride] = L.dbtc;
+      }
+      scr[5 * wstride] = rupc[u]; scr[6 * wstride] = rupdc[u];
       if (cloudy_col) {
-        // cloudy (overcast) two-stream of this layer and the cloud-fraction mix (spcvrt.f90:516-588)
-        const double ztauo = ztauc + ptauc;
-        double zomco = ztauc * zomcc + ptauc * pomgc;
-        const double zgco = fdiv(ptauc * pomgc * pasyc + ztauc * zomcc * zgcc, zomco);
-        zomco = fdiv(zomco, ztauo);
-        double refo = 0., refdo = 0., trao = 1., trado = 1.;
-        if (pclfr > 1.e-12) reftra(exp_tbl, bpade, zgco, prmu0, ztauo, zomco, refo, refdo, trao, trado);
-        const double zclear = 1.0 - pclfr, zcloud = pclfr;
-        const double ref = zclear * refc + zcloud * refo;
-        const double refd = zclear * refdc + zcloud * refdo;
-        const double tra = zclear * trac + zcloud * trao;
-        const double trad = zclear * tradc + zcloud * trado;
-        const double dbtmo = exp_neg(exp_tbl, bpade, fdiv(ztauo, prmu0));
-        const double dbt = zclear * dbtc + zcloud * dbtmo;
-        const double zreflect = frcp(1. - rupd[u] * refd);
-        const double rn = ref + (trad * ((tra - dbt) * rupd[u] + dbt * rup[u])) * zreflect;
-        const double rdn = refd + trad * trad * rupd[u] * zreflect;
+        const double zreflect = frcp(1. - rupd[u] * L.refd);
+        const double rn = L.ref + (L.trad * ((L.tra - L.dbt) * rupd[u] + L.dbt * rup[u])) * zreflect;
+        const double rdn = L.refd + L.trad * L.trad * rupd[u] * zreflect;
         rup[u] = rn; rupd[u] = rdn;
-        scr[7 * wstride] = ref; scr[8 * wstride] = refd; scr[9 * wstride] = tra; scr[10 * wstride] = trad;
-        scr[11 * wstride] = dbt; scr[12 * wstride] = rup[u]; scr[13 * wstride] = rupd[u];
+        if (!RECOMPUTE) {
+          scr[7 * wstride] = L.ref; scr[8 * wstride] = L.refd; scr[9 * wstride] = L.tra; scr[10 * wstride] = L.trad;
+          scr[11 * wstride] = L.dbt;
+        }
+        scr[12 * wstride] = rup[u]; scr[13 * wstride] = rupd[u];
       }
     }
   }
@@ -831,17 +883,29 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
   for (int l = nlay - 1; l >= -1; --l) {
     // interface above layer l (level index l+1); l = -1 is the surface interface
     double sfu = 0., sfd = 0., scu = 0., scd = 0.;
+    BandLayer b{0., 1., 0., 0., 0., 1., 0., 0u};
+    if (RECOMPUTE && l >= 0) b = band_layer(l);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       double refc = 0., refdc = 0., trac = 0., tradc = 0., dbtc = 0., prupc = albdir, prupdc = albdif;
       double ref = 0., refd = 0., tra = 0., trad = 0., dbt = 0., prup = albdir, prupd = albdif;
       if (l >= 0) {
         const double* __restrict__ scr = scr0 + (size_t)u * growstride + (size_t)l * ncc;
-        refc = scr[0 * wstride]; refdc = scr[1 * wstride]; trac = scr[2 * wstride]; tradc = scr[3 * wstride];
-        dbtc = scr[4 * wstride]; prupc = scr[5 * wstride]; prupdc = scr[6 * wstride];
+        if (RECOMPUTE) {
+          const SwLayer L = layer(b, u, scr[R_TAUG * wstride], scr[R_TAUR * wstride]);
+          refc = L.refc; refdc = L.refdc; trac = L.trac; tradc = L.tradc; dbtc = L.dbtc;
+          ref = L.ref; refd = L.refd; tra = L.tra; trad = L.trad; dbt = L.dbt;
+        } else {
+          refc = scr[0 * wstride]; refdc = scr[1 * wstride]; trac = scr[2 * wstride]; tradc = scr[3 * wstride];
+          dbtc = scr[4 * wstride];
+        }
+        prupc = scr[5 * wstride]; prupdc = scr[6 * wstride];
         if (cloudy_col) {
-          ref = scr[7 * wstride]; refd = scr[8 * wstride]; tra = scr[9 * wstride]; trad = scr[10 * wstride];
-          dbt = scr[11 * wstride]; prup = scr[12 * wstride]; prupd = scr[13 * wstride];
+          if (!RECOMPUTE) {
+            ref = scr[7 * wstride]; refd = scr[8 * wstride]; tra = scr[9 * wstride]; trad = scr[10 * wstride];
+            dbt = scr[11 * wstride];
+          }
+          prup = scr[12 * wstride]; prupd = scr[13 * wstride];
         }
       }
       {

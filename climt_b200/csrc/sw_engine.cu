@@ -33,7 +33,13 @@ __global__ void __launch_bounds__(kBlock) k_sw_prep_layer(const __grid_constant_
                                                           const __grid_constant__ Work W, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int l = blockIdx.y;
-  if (c < n) sw_prep_column<true, false>(T, in, fl, W, c0, c, l, l + 1);
+  if (c < n) sw_prep_column<true, false, false>(T, in, fl, W, c0, c, l, l + 1);
+}
+// ECMWF aerosol mix (iaer = 6 only): one thread per (column, layer)
+__global__ void __launch_bounds__(kBlock) k_sw_aer_mix(const __grid_constant__ Tables T, const __grid_constant__ In in,
+                                                       const __grid_constant__ Work W, int c0, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) sw_aerosol_mix(T, in, W, c0, c, blockIdx.y);
 }
 // what couples the layers of a column (laytrop, cloud optics, solar-source layers): one thread per column
 __global__ void __launch_bounds__(kBlock) k_sw_prep(const __grid_constant__ Tables T, const __grid_constant__ In in, const Flags fl,
@@ -268,6 +274,7 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
   const int gx = (n + kBlock - 1) / kBlock;
   if (mc && e->irng == 0) { k_sw_mask_kiss<<<(n + 31) / 32, 32, 0, st>>>(in, W, e->fl.icld, e->permuteseed, c0, n); e->launches += 1; }
   k_sw_prep_layer<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, e->fl, W, c0, n);
+  if (e->fl.iaer == 6) { k_sw_aer_mix<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, W, c0, n); e->launches += 1; }
   // column-serial kernels: one warp per block so that even 8 192 columns spread over every SM
   const int gw = (n + 31) / 32;
   k_sw_prep<<<gw, 32, 0, st>>>(e->T, in, e->fl, W, c0, n);

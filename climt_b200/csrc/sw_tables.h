@@ -32,7 +32,24 @@ inline void build_tables(const std::string& blob_path, const Constants& k, std::
     std::snprintf(pre, sizeof pre, "b%02d.", ib + 16);
     BandOff& O = T.b[ib];
     auto opt = [&](const char* nm) { std::string key = std::string(pre) + nm; return b.has(key) ? putk(key) : -1; };
-    O.absa = opt("absa"); O.absb = opt("absb"); O.selfref = opt("selfref"); O.forref = opt("forref");
+    // (rows, ng) table -> one (rows, 4) block per group of 4 g-points (layout: BandOff in sw_core.cuh); returns offset, sets stride
+    const int ng = kNG[ib];
+    auto grouped = [&](const char* nm, int& gs) {
+      const std::string key = std::string(pre) + nm;
+      gs = 0;
+      if (!b.has(key)) return -1;
+      const BlobView::Ent& e = b.get(key);
+      const int rows = (int)(e.count / ng);
+      while (img.size() & 15) img.push_back(0.0);
+      const int off = (int)img.size();
+      gs = rows * 4;
+      for (int q = 0; q < (ng + 3) / 4; ++q)
+        for (int r = 0; r < rows; ++r)
+          for (int j = 0; j < 4; ++j) img.push_back(q * 4 + j < ng ? e.p[(size_t)r * ng + q * 4 + j] : 0.0);
+      return off;
+    };
+    O.absa = grouped("absa", O.gs_absa); O.absb = grouped("absb", O.gs_absb);
+    O.selfref = grouped("selfref", O.gs_selfref); O.forref = grouped("forref", O.gs_forref);
     O.sfluxref = opt("sfluxref"); O.irradnce = opt("irradnce"); O.facbrght = opt("facbrght"); O.snsptdrk = opt("snsptdrk");
     O.raylv = -1; O.raylb = opt("raylb"); O.rayl = 0.;
     std::string rk = std::string(pre) + "rayl";

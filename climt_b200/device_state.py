@@ -48,3 +48,15 @@ def finish(engine, asynchronous):
         import torch
         torch.cuda.current_stream().synchronize()
         engine.check()
+
+
+def keep_alive_on(stream, tensors):
+    """A call was enqueued on an explicit raw `stream` handle: tensors allocated inside that call (on torch's current stream)
+    must not be handed back to the caching allocator for reuse before that stream has consumed them -> record_stream."""
+    if stream is None:
+        return
+    import torch
+    s = torch.cuda.ExternalStream(int(stream))
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            t.record_stream(s)

@@ -10,7 +10,7 @@ import datetime
 
 import numpy as np
 
-from . import _native
+from . import _native, device_state
 from .sympl_shim import DiagnosticComponent
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -67,6 +67,7 @@ def instellation_device(lat_deg, lon_deg, jc, want_coszen=False, stream=None):
                                          zen.data_ptr(), cz.data_ptr() if cz is not None else None, s)
     if rc:
         raise RuntimeError(L.cb200_global_error().decode())
+    device_state.keep_alive_on(stream, [lat, lon, zen, cz])
     return (zen, cz) if want_coszen else zen
 
 

@@ -12,7 +12,7 @@ import ctypes
 
 import numpy as np
 
-from . import _native
+from . import _native, device_state
 from .constants import get_constant
 from .sympl_shim import Stepper
 
@@ -100,6 +100,7 @@ def simple_physics_device(params, tensors, dtime, order=0, stream=None):
     sp = stream if stream is not None else torch.cuda.current_stream().cuda_stream
     _check(L, L.cb200_simple_physics_run_device(t.device.index or 0, ncol, nlev, order, float(dtime), ctypes.byref(params),
                                                 ctypes.byref(s), ctypes.byref(o), work.data_ptr(), sp))
+    device_state.keep_alive_on(stream, keep + [work] + list(out.values()))
     return out
 
 

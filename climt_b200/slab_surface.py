@@ -14,7 +14,7 @@ import ctypes
 
 import numpy as np
 
-from . import _native
+from . import _native, device_state
 from .sympl_shim import TendencyComponent
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -117,6 +117,7 @@ def slab_surface_host(state, device=0):
     rc = L.cb200_slab_surface_run_host(device, n, stride, ctypes.byref(s), tend.ctypes.data_as(_dp), depth.ctypes.data_as(_dp))
     if rc:
         raise RuntimeError(L.cb200_global_error().decode())
+    device_state.keep_alive_on(stream, keep + [tend, depth])
     return tend, depth
 
 
@@ -160,6 +161,7 @@ def slab_surface_device(state, flux_layout="column_major", stream=None):
     rc = L.cb200_slab_surface_run_device(code.device.index or 0, n, stride, ctypes.byref(s), tend.data_ptr(), depth.data_ptr(), sp)
     if rc:
         raise RuntimeError(L.cb200_global_error().decode())
+    device_state.keep_alive_on(stream, keep + [tend, depth])
     return tend, depth
 
 
