@@ -37,4 +37,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 }  // namespace bulk
+
+// Block-wide barrier that lanes of one warp may reach from DIFFERENT program locations (lanes whose column is past the end of a
+// ragged chunk wait in a dummy loop while their neighbours are inside the transfer function).  __syncthreads() is bar.sync =
+// barrier.sync.aligned, which is undefined when the lanes of a warp diverge (r02: hung the first ragged launch); the unaligned
+// form counts arriving THREADS.  Barrier 1 (0 is __syncthreads'); nthreads must be a multiple of 32.
+__device__ __forceinline__ void barrier_unaligned(int nthreads) {
+  asm volatile("barrier.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
 }  // namespace cb

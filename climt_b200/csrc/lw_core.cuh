@@ -85,7 +85,7 @@ struct Work {  // all sized for a chunk of ncc columns
   double* pwvcm; // [ncc]
   double* cld;   // [2][16][nlay][ncc]  odcld, efclfrac
   double* scr;   // [140][NSCR][nlay][ncc] atrans, bbugas, atot, bbutot, taug, fracs
-  double* part;  // [nunits][npart][nlay+1][ncc] up, dn, upclr, dnclr [, d_up, d_upclr]  (un-weighted sums over the unit's g-points)
+  double* part;  // [ngroups][npart][nlay+1][ncc] up, dn, upclr, dnclr [, d_up, d_upclr]  (band-weighted sums over a group's units)
   int npart;     // 4, or 6 with the surface-temperature derivative of the upward flux (idrv = 1)
   double* ovl;   // [14][nlay+2][ncc] maximum-random overlap factors of rtrnmr (OV_* rows), non-McICA icld = 2, 3 only
   unsigned* mask; // [nlay][5][mstride] McICA cloud mask (+ moff), bit (g & 31) of word (g >> 5) set = sub-column g cloudy
@@ -1030,10 +1030,42 @@ CB_HD void lw_taumol_unit(const Tables& T, const In& in, const Work& W, int c0, 
 
 // rtrn / rtrnmc for U consecutive g-points of band ib (0-based) -- generic in the band (rrtmg_lw_rtrn.f90:300-557)
 // MR: maximum-random overlap of the fractional clouds (rtrnmr, rrtmg_lw_rtrnmr.f90:481-700) instead of rtrn's random overlap.
+// Where the two sweeps put the radiance sums of their g-points, one call per interface (down sweep: from the top down, up sweep:
+// from the surface up), already weighted by the band's wtdiff * delwave (rtrn.f90:529-543) so that units of different bands can
+// share rows.  The units of a GROUP of CB_LW_GROUP units share one set of rows `part[group][npart][nlay+1][ncc]`:
+//   * CUDA kernel (lw_engine.cu, LwPartSmem): the units of a group are the warps of one block; values are staged in shared memory a
+//     few interfaces at a time and summed over the warps in unit order before they reach HBM (r01: the per-unit rows and the
+//     kernel that re-read them were ~19 % of a step's DRAM traffic);
+//   * host emulation (LwPartDirect): the units of a group run one after the other and accumulate into the zeroed rows in the same
+//     order -- the same bits.
+// Rows: 0 up, 1 down, 2 up clear, 3 down clear [, 4 d(up)/dTs, 5 d(up clear)/dTs].  The clear-sky rows of a cloud-free column are
+// not stored (equal to the total ones bit for bit); the downward flux at the top interface is zero and not stored either.
+#ifndef CB_LW_GROUP
+#define CB_LW_GROUP 4  // 70 units of 2 g-points -> 18 groups (the last one half empty): 128-thread blocks, 6 per SM at 80 registers
+#endif
+struct LwPartDirect {
+  double* part;  // rows of this unit's group, at this column
+  size_t pstride;
+  int ncc;
+  CB_HD void put_dn(size_t lev, bool cloudy_col, double dn, double dnc) {
+    part[1 * pstride + lev * ncc] += dn;
+    if (cloudy_col) part[3 * pstride + lev * ncc] += dnc;
+  }
+  CB_HD void put_up(size_t lev, bool cloudy_col, double up, double upc, bool drv, double dup, double dupc) {
+    part[0 * pstride + lev * ncc] += up;
+    if (cloudy_col) part[2 * pstride + lev * ncc] += upc;
+    if (drv) {
+      part[4 * pstride + lev * ncc] += dup;
+      if (cloudy_col) part[5 * pstride + lev * ncc] += dupc;
+    }
+  }
+  CB_HD void end_sweep() {}
+};
+
 // DRV: also the derivative of the upward flux with respect to the surface temperature (idrv = 1, rtrn.f90:458-461,473-476,
 // 492-512; the same lines in rtrnmc.f90:447-510 and rtrnmr.f90:629-711): one more multiplicative recurrence in the up sweep.
-template <int U, bool MC, bool MR = false, bool DRV = false>
-CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int ib, int g0, int unit) {
+template <int U, bool MC, bool MR, bool DRV, class Sink>
+CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int ib, int g0, Sink& sink) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
   const double* __restrict__ tb = T.base;
@@ -1064,8 +1096,8 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
 #pragma unroll
   for (int u = 0; u < U; ++u) { radld[u] = 0.; radclrd[u] = 0.; frac1[u] = 0.; }
   int iclddn = 0;
-  double* __restrict__ part = W.part + (size_t)unit * W.npart * (nlay + 1) * ncc + c;
-  const size_t pstride = (size_t)(nlay + 1) * ncc;
+  const double wband = 0.5 * CB_LDG(tb + T.delwave + ib);  // wtdiff * delwave(iband)
+  const bool cloudy_col = ncb > 0;
   double plev_up = planck_band(tp, in.tlev[(size_t)nlay * ncol + gc]);  // planklev(nlay)
   // The loads of a layer do not depend on the recurrence: fetch layer lev-1 while layer lev is computed (the kernel's top
   // stall is memory latency at 24 warps per SM).
@@ -1241,12 +1273,9 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       sum_dc = sum_dc + radclrd[u];
       if (lev == 1) frac1[u] = plfrac;
     }
-    part[1 * pstride + (size_t)(lev - 1) * ncc] = sum_d;
-    if (ncb > 0) part[3 * pstride + (size_t)(lev - 1) * ncc] = sum_dc;  // cloud-free column: clear == total, not stored
+    sink.put_dn((size_t)(lev - 1), cloudy_col, sum_d * wband, sum_dc * wband);
   }
-  // top of atmosphere: no downward flux
-  part[1 * pstride + (size_t)nlay * ncc] = 0.0;
-  if (ncb > 0) part[3 * pstride + (size_t)nlay * ncc] = 0.0;
+  sink.end_sweep();  // (top of atmosphere: no downward flux -- lw_reduce_level knows)
   // surface (rtrn.f90:455-470)
   const double tbound = in.tsfc[gc];
   const double semiss = in.emis[(size_t)ib * ncol + gc];
@@ -1269,12 +1298,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       d_radclru[u] = d_radlu[u];
       sd = sd + d_radlu[u];
     }
-    part[0] = s;
-    if (ncb > 0) part[2 * pstride] = sc;
-    if (DRV) {
-      part[4 * pstride] = sd;
-      if (ncb > 0) part[5 * pstride] = sd;
-    }
+    sink.put_up(0, cloudy_col, s * wband, sc * wband, DRV, sd * wband, sd * wband);
   }
   // upward sweep (rtrn.f90:478-521), the (atrans, bbugas) rows of the next layer fetched one layer ahead
   struct UpIn {
@@ -1373,13 +1397,9 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
       sc = sc + radclru[u];
       if (DRV) { sd = sd + d_radlu[u]; sdc = sdc + d_radclru[u]; }
     }
-    part[(size_t)lev * ncc] = s;
-    if (ncb > 0) part[2 * pstride + (size_t)lev * ncc] = sc;
-    if (DRV) {
-      part[4 * pstride + (size_t)lev * ncc] = sd;
-      if (ncb > 0) part[5 * pstride + (size_t)lev * ncc] = sdc;
-    }
+    sink.put_up((size_t)lev, cloudy_col, s * wband, sc * wband, DRV, sd * wband, sdc * wband);
   }
+  sink.end_sweep();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1412,42 +1432,36 @@ inline int build_units(Unit* out, int umax) {  // host only
   return n;
 }
 
-// lw_reduce: band/g-point reduction in a fixed order (rtrn.f90:529-557) -> fluxes in W m-2.
-CB_HD void lw_reduce_level(const Tables& T, const Work& W, const Unit* units, int nunits, int nlay, int c0, int c,
-                           int lev, int ncol, const Out& out) {
+// lw_reduce: sum over the groups of units in a fixed order (deterministic; the band weights wtdiff * delwave of rtrn.f90:529-557
+// were applied by the units) -> fluxes in W m-2.
+CB_HD void lw_reduce_level(const Tables& T, const Work& W, int ngroups, int nlay, int c0, int c, int lev, int ncol, const Out& out) {
   const int ncc = W.ncc;
   const size_t pstride = (size_t)(nlay + 1) * ncc;
-  const double wtdiff = 0.5;
   // cloud-free column: the clear-sky streams equal the total ones bit for bit and were not stored (lw_transfer_unit)
   const bool cloudy_col = W.ncbands[c] > 0;
-  const int nq = cloudy_col ? 4 : 2;
   const bool drv = out.duflx_dt != nullptr;
-  double tot[4] = {0., 0., 0., 0.};
-  double dtot[2] = {0., 0.};
-  for (int b = 1; b <= 16; ++b) {
-    double bs[4] = {0., 0., 0., 0.};
-    double ds[2] = {0., 0.};
-    for (int k = 0; k < nunits; ++k) {
-      if (units[k].band != b) continue;
-      const double* p = W.part + (size_t)k * W.npart * pstride + (size_t)lev * ncc + c;
-      for (int q = 0; q < nq; ++q) bs[q] = bs[q] + p[q * pstride];
-      if (drv) {
-        ds[0] = ds[0] + p[4 * pstride];
-        if (cloudy_col) ds[1] = ds[1] + p[5 * pstride];
-      }
+  const bool top = lev == nlay;  // no downward flux at the top interface (not stored)
+  double tot[6] = {0., 0., 0., 0., 0., 0.};
+  for (int k = 0; k < ngroups; ++k) {
+    const double* p = W.part + (size_t)k * W.npart * pstride + (size_t)lev * ncc + c;
+    tot[0] = tot[0] + p[0];
+    if (!top) tot[1] = tot[1] + p[pstride];
+    if (cloudy_col) {
+      tot[2] = tot[2] + p[2 * pstride];
+      if (!top) tot[3] = tot[3] + p[3 * pstride];
     }
-    const double dw = CB_LDG(T.base + T.delwave + (b - 1));
-    for (int q = 0; q < nq; ++q) tot[q] = tot[q] + (bs[q] * wtdiff) * dw;
-    // rtrn.f90:546-555: the derivative sums carry fluxfac band by band
-    if (drv) for (int q = 0; q < 2; ++q) dtot[q] = dtot[q] + ((ds[q] * wtdiff) * dw) * T.fluxfac;
+    if (drv) {
+      tot[4] = tot[4] + p[4 * pstride];
+      if (cloudy_col) tot[5] = tot[5] + p[5 * pstride];
+    }
   }
-  if (nq == 2) { tot[2] = tot[0]; tot[3] = tot[1]; dtot[1] = dtot[0]; }
+  if (!cloudy_col) { tot[2] = tot[0]; tot[3] = tot[1]; tot[5] = tot[4]; }
   const size_t o = (size_t)lev * ncol + (c0 + c);
   out.uflx[o] = tot[0] * T.fluxfac;
   out.dflx[o] = tot[1] * T.fluxfac;
   out.uflxc[o] = tot[2] * T.fluxfac;
   out.dflxc[o] = tot[3] * T.fluxfac;
-  if (drv) { out.duflx_dt[o] = dtot[0]; out.duflxc_dt[o] = dtot[1]; }
+  if (drv) { out.duflx_dt[o] = tot[4] * T.fluxfac; out.duflxc_dt[o] = tot[5] * T.fluxfac; }
 }
 // heating rates (rtrn.f90:569-581)
 CB_HD void lw_heating(const Tables& T, const In& in, const Out& out, int gcol, int l) {

@@ -104,18 +104,87 @@ __global__ void __launch_bounds__(kBlock, CB_LW_TAU_MIN_BLOCKS)
 #undef CB_CASE
 }
 
-// rtrn / rtrnmc: one block = 128 adjacent columns x one unit (<= CB_LW_UMAX g-points of one band); one code body for all bands
+constexpr int kPartK = 4;  // interfaces staged in shared memory between two flushes of LwPartSmem
+
+// Device-side sink of the sweeps' radiance sums (interface: LwPartDirect in lw_core.cuh).  The CB_LW_GROUP warps of a block are
+// the units of one group, the same 32 columns in every warp.  A put parks the thread's values in shared memory; every kPartK
+// interfaces the block meets, each warp sums a share of the (interface, row) pairs over the warps IN UNIT ORDER (deterministic,
+// = the serial emulation's order) and writes one coalesced 256-byte row per pair.
+struct LwPartSmem {
+  double* buf;   // shared: [kPartK][4][nthreads]
+  double* part;  // rows of this block's group at this thread's column
+  size_t pstride, lev_first;
+  int ncc, nthreads, nw, tid, warp, lane, count;
+  int nv;   // values per put of the current sweep: down 2 (rows 1, 3), up 2 or 4 (rows 0, 2, 4, 5); odd ones are clear-sky rows
+  int dir;  // +1: up sweep, interfaces arrive bottom-up; -1: down sweep, top-down
+  bool valid, cloudy;
+  __device__ void stage(size_t lev, double v0, double v1, double v2, double v3) {
+    if (count == 0) lev_first = lev;
+    double* b = buf + (size_t)count * 4 * nthreads + tid;
+    b[0] = v0; b[nthreads] = v1;
+    if (nv == 4) { b[2 * nthreads] = v2; b[3 * nthreads] = v3; }
+    if (++count == kPartK) flush();
+  }
+  __device__ void put_dn(size_t lev, bool cloudy_col, double dn, double dnc) {
+    if (count == 0) { nv = 2; dir = -1; }
+    cloudy = cloudy_col;
+    stage(lev, dn, dnc, 0., 0.);
+  }
+  __device__ void put_up(size_t lev, bool cloudy_col, double up, double upc, bool drv, double dup, double dupc) {
+    if (count == 0) { nv = drv ? 4 : 2; dir = 1; }
+    cloudy = cloudy_col;
+    stage(lev, up, upc, dup, dupc);
+  }
+  __device__ void flush() {
+    cb::barrier_unaligned(nthreads);
+    for (int p = warp; p < count * nv; p += nw) {
+      const int k = p / nv, q = p - k * nv;
+      const double* b = buf + ((size_t)k * 4 + q) * nthreads + lane;
+      double s = b[0];
+      for (int w = 1; w < nw; ++w) s = s + b[w * 32];
+      const int row = dir < 0 ? 1 + 2 * q : (q < 2 ? 2 * q : 2 + q);
+      // (column validity and cloudiness are properties of the lane's column: the same in every warp of the block)
+      if (valid && (!(q & 1) || cloudy)) part[row * pstride + (size_t)((long)lev_first + (long)dir * k) * ncc] = s;
+    }
+    cb::barrier_unaligned(nthreads);
+    count = 0;
+  }
+  __device__ void end_sweep() {
+    if (count) flush();
+  }
+};
+
+// rtrn / rtrnmc / rtrnmr: one block = 32 adjacent columns x CB_LW_GROUP units (one warp each, <= CB_LW_UMAX g-points of one band);
+// one code body for all bands
 template <bool MC, bool MR, bool DRV = false>
-__global__ void __launch_bounds__(kBlock, CB_LW_RT_MIN_BLOCKS)
+__global__ void __launch_bounds__(32 * CB_LW_GROUP, (CB_LW_RT_MIN_BLOCKS * 4 + CB_LW_GROUP - 1) / CB_LW_GROUP)
     k_units(const __grid_constant__ Tables T, const __grid_constant__ In in, const __grid_constant__ Work W,
             const __grid_constant__ UnitList UL, int c0, int n) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  const int k = blockIdx.y;
+  __shared__ double s_part[kPartK * 4 * 32 * CB_LW_GROUP];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int group = blockIdx.y;
+  const int k = group * CB_LW_GROUP + threadIdx.y;
+  LwPartSmem sink;
+  sink.buf = s_part;
+  sink.pstride = (size_t)(in.nlay + 1) * W.ncc;
+  sink.part = W.part + (size_t)group * W.npart * sink.pstride + c;
+  sink.ncc = W.ncc;
+  sink.nthreads = 32 * CB_LW_GROUP; sink.nw = CB_LW_GROUP;
+  sink.tid = threadIdx.y * 32 + threadIdx.x; sink.warp = threadIdx.y; sink.lane = threadIdx.x;
+  sink.count = 0; sink.lev_first = 0; sink.nv = 2; sink.dir = 1;
+  sink.valid = c < n; sink.cloudy = false;
+  if (c >= n || k >= UL.n) {  // no work, but the block's meetings need every thread: the same sequence of puts
+    const bool cl = c < n && W.ncbands[c] > 0;
+    for (int lev = in.nlay; lev >= 1; --lev) sink.put_dn((size_t)(lev - 1), cl, 0., 0.);
+    sink.end_sweep();
+    for (int lev = 0; lev <= in.nlay; ++lev) sink.put_up((size_t)lev, cl, 0., 0., DRV, 0., 0.);
+    sink.end_sweep();
+    return;
+  }
   const Unit un = UL.u[k];
-  if (CB_LW_UMAX >= 4 && un.u == 4) lw_transfer_unit<4, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, k);
-  else if (CB_LW_UMAX == 1) lw_transfer_unit<1, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, k);
-  else lw_transfer_unit<2, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, k);
+  if (CB_LW_UMAX >= 4 && un.u == 4) lw_transfer_unit<4, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, sink);
+  else if (CB_LW_UMAX == 1) lw_transfer_unit<1, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, sink);
+  else lw_transfer_unit<2, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, sink);
 }
 
 // McICA cloud mask with the per-column kissvec generator: one thread per column
@@ -131,7 +200,7 @@ __global__ void __launch_bounds__(kBlock) k_reduce(const __grid_constant__ Table
                                                    int ncol, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int lev = blockIdx.y;
-  if (c < n) lw_reduce_level(T, W, UL.u, UL.n, nlay, c0, c, lev, ncol, out);
+  if (c < n) lw_reduce_level(T, W, (UL.n + CB_LW_GROUP - 1) / CB_LW_GROUP, nlay, c0, c, lev, ncol, out);
 }
 
 __global__ void __launch_bounds__(kBlock) k_heat(const __grid_constant__ Tables T, const __grid_constant__ In in,
@@ -204,7 +273,7 @@ struct cb200_lw_engine {
     CUDA_OK(cudaMalloc(&W.pwvcm, sizeof(double) * n));
     CUDA_OK(cudaMalloc(&W.cld, sizeof(double) * 32 * L * n));
     CUDA_OK(cudaMalloc(&W.scr, sizeof(double) * 140 * NSCR * L * n));
-    CUDA_OK(cudaMalloc(&W.part, sizeof(double) * UL.n * npart * (L + 1) * n));
+    CUDA_OK(cudaMalloc(&W.part, sizeof(double) * ((UL.n + CB_LW_GROUP - 1) / CB_LW_GROUP) * npart * (L + 1) * n));
     W.npart = npart;
     cap_npart = npart;
     CUDA_OK(cudaMalloc(&W.ovl, sizeof(double) * OV_NROWS * (L + 2) * n));
@@ -325,15 +394,15 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
   k_lw_taumol<<<dim3(gx, e->UL_tau.n, CB_LW_LAYER_CHUNKS), kBlock, e->tau_smem, st>>>(e->T, in, W, e->UL_tau, c0, n);
   if (e->timing) cudaEventRecord(e->evm, st);
   // non-McICA: icld = 1 -> rtrn (random overlap); icld = 2, 3 -> rtrnmr (maximum-random), rrtmg_lw_rad.nomcica.f90:527-541
-  const dim3 gu(gx, e->UL.n);
+  const dim3 gu((n + 31) / 32, (e->UL.n + CB_LW_GROUP - 1) / CB_LW_GROUP), bu(32, CB_LW_GROUP);
   if (W.npart == 6) {
-    if (mc) k_units<true, false, true><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
-    else if (e->fl.icld >= 2) k_units<false, true, true><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
-    else k_units<false, false, true><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    if (mc) k_units<true, false, true><<<gu, bu, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    else if (e->fl.icld >= 2) k_units<false, true, true><<<gu, bu, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    else k_units<false, false, true><<<gu, bu, 0, st>>>(e->T, in, W, e->UL, c0, n);
   } else {
-    if (mc) k_units<true, false><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
-    else if (e->fl.icld >= 2) k_units<false, true><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
-    else k_units<false, false><<<gu, kBlock, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    if (mc) k_units<true, false><<<gu, bu, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    else if (e->fl.icld >= 2) k_units<false, true><<<gu, bu, 0, st>>>(e->T, in, W, e->UL, c0, n);
+    else k_units<false, false><<<gu, bu, 0, st>>>(e->T, in, W, e->UL, c0, n);
   }
   if (e->timing) cudaEventRecord(e->ev1, st);
   k_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(e->T, W, e->UL, out, nlay, out_ncol, c0, n);

@@ -78,7 +78,7 @@ struct Work {
   double* aer;    // [3][14][nlay][ncc]  aerosol tau, ssa, asym (iaer = 6 only)
   double* scr;    // [112][NSCR][nlay][ncc]
   double* src;    // [112][ncc]  solar source function of each g-point (taken at layer laysolfr of its band)
-  double* part;   // [nunits][4][nlay+1][ncc]   fu, fd, cu, cd  (already weighted by the incoming flux)
+  double* part;   // [ngroups][4][nlay+1][ncc]   fu, fd, cu, cd  (already weighted by the incoming flux), summed over a group's units
   unsigned* mask; // [nlay][4][mstride] (+ moff) McICA cloud mask, bit (g & 31) of word (g >> 5)
   int mstride, moff;
   int* err;
@@ -778,10 +778,35 @@ CB_HD SwLayer sw_layer_props(const double* __restrict__ exp_tbl, double bpade, d
                            // the upward sweep stored: 4 instead of 14 scratch rows carried per g-point (clear sky), reftra twice
 #endif
 
+// Where the downward sweep puts the flux contributions of its g-points, one call per interface from the top down.  The partial
+// sums of a GROUP of CB_SW_GROUP units share one set of rows `part[group][4][nlay+1][ncc]`:
+//   * CUDA kernel (sw_engine.cu, SwPartSmem): the units of a group are the warps of one block; values are staged in shared memory a
+//     few levels at a time and summed over the warps in unit order before they reach HBM -- r01: the per-unit rows and the
+//     kernel that re-read them were 19 % of a step's DRAM traffic;
+//   * host emulation (SwPartDirect): the units of a group run one after the other and accumulate into the zeroed rows in the
+//     same order, so both give the same bits.
+#ifndef CB_SW_GROUP
+#define CB_SW_GROUP 4
+#endif
+struct SwPartDirect {
+  double* part;  // rows of this unit's group, at this column
+  size_t pstride;
+  int ncc;
+  CB_HD void put(size_t lev, bool cloudy_col, double sfu, double sfd, double scu, double scd) {
+    if (cloudy_col) {  // cloud-free column: total == clear, not stored (sw_reduce_level copies)
+      part[0 * pstride + lev * ncc] += sfu;
+      part[1 * pstride + lev * ncc] += sfd;
+    }
+    part[2 * pstride + lev * ncc] += scu;
+    part[3 * pstride + lev * ncc] += scd;
+  }
+  CB_HD void finish() {}
+};
+
 // spcvrt_sw / spcvmc_sw for U consecutive g-points of band ib (rrtmg_sw_spcvrt.f90:329-661) -- generic in the band.
-template <int U, bool MC, bool RECOMPUTE = (CB_SW_RECOMPUTE != 0)>
+template <int U, bool MC, class Sink, bool RECOMPUTE = (CB_SW_RECOMPUTE != 0)>
 CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int c0, int c,
-                            int ib, int g0, int unit) {
+                            int ib, int g0, Sink& sink) {
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
   const double* __restrict__ tb = T.base;
@@ -878,8 +903,6 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
   double tdnc[U], rdndc[U], tdbtc[U], tdn[U], rdnd[U], tdbt[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) { tdnc[u] = 1.; rdndc[u] = 0.; tdbtc[u] = 1.; tdn[u] = 1.; rdnd[u] = 0.; tdbt[u] = 1.; }
-  double* __restrict__ part = W.part + (size_t)unit * 4 * (nlay + 1) * ncc + c;
-  const size_t pstride = (size_t)(nlay + 1) * ncc;
   for (int l = nlay - 1; l >= -1; --l) {
     // interface above layer l (level index l+1); l = -1 is the surface interface
     double sfu = 0., sfd = 0., scu = 0., scd = 0.;
@@ -948,14 +971,9 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
         }
       }
     }
-    const size_t lev = (size_t)(l + 1);
-    if (cloudy_col) {  // cloud-free column: total == clear, not stored (sw_reduce_level copies)
-      part[0 * pstride + lev * ncc] = sfu;
-      part[1 * pstride + lev * ncc] = sfd;
-    }
-    part[2 * pstride + lev * ncc] = scu;
-    part[3 * pstride + lev * ncc] = scd;
+    sink.put((size_t)(l + 1), cloudy_col, sfu, sfd, scu, scd);
   }
+  sink.finish();
 }
 
 struct Unit {
@@ -989,19 +1007,17 @@ inline int build_units(Unit* out, int umax) {  // host only
   return n;
 }
 
-// fixed-order reduction over units (the Fortran accumulates g-point by g-point in band order, spcvrt.f90:614-618)
-CB_HD void sw_reduce_level(const Work& W, const Unit* units, int nunits, int nlay, int c0, int c, int lev, int ncol,
-                           const Out& out) {
+// fixed-order reduction over the groups of units: deterministic (the unit list order; a group sums its units in that order), not
+// the Fortran's band order (spcvrt.f90:614-618) -- the sum is the same to rounding
+CB_HD void sw_reduce_level(const Work& W, int ngroups, int nlay, int c0, int c, int lev, int ncol, const Out& out) {
   const int ncc = W.ncc;
   const size_t pstride = (size_t)(nlay + 1) * ncc;
   const int q0 = W.anycld[c] != 0 ? 0 : 2;  // cloud-free column: only the clear-sky sums were stored
   double tot[4] = {0., 0., 0., 0.};
-  for (int b = 16; b <= 29; ++b)
-    for (int k = 0; k < nunits; ++k) {
-      if (units[k].band != b) continue;
-      const double* p = W.part + (size_t)k * 4 * pstride + (size_t)lev * ncc + c;
-      for (int q = q0; q < 4; ++q) tot[q] = tot[q] + p[q * pstride];
-    }
+  for (int k = 0; k < ngroups; ++k) {
+    const double* p = W.part + (size_t)k * 4 * pstride + (size_t)lev * ncc + c;
+    for (int q = q0; q < 4; ++q) tot[q] = tot[q] + p[q * pstride];
+  }
   if (q0 == 2) { tot[0] = tot[2]; tot[1] = tot[3]; }
   const size_t o = (size_t)lev * ncol + (c0 + c);
   out.uflx[o] = tot[0];

@@ -10,6 +10,7 @@
 
 #include "../../include/climt_b200.h"
 #include "engine_common.h"
+#include "cb_async.cuh"
 #include "sw_tables.h"
 #include "mcica_host.h"
 #include "mcica_compat.h"
@@ -77,19 +78,73 @@ __global__ void __launch_bounds__(kBlock, CB_SW_TAU_MIN_BLOCKS)
 #undef CB_CASE
 }
 
-// spcvrt_sw / spcvmc_sw: one block = 128 adjacent columns x one unit (<= CB_SW_UMAX g-points of one band); the same code
-// for every band, so the instruction working set of an SM is one function body.
+constexpr int kPartK = 4;  // interfaces staged in shared memory between two flushes of SwPartSmem
+
+// Device-side sink of the downward sweep's flux contributions (interface: SwPartDirect in sw_core.cuh).  The CB_SW_GROUP warps of
+// a block are the units of one group, the same 32 columns in every warp.  A put() parks the thread's four values in shared
+// memory; every kPartK interfaces the block meets, each warp sums a share of the (interface, quantity) pairs over the warps IN
+// UNIT ORDER (deterministic, = the serial emulation's order) and writes one coalesced 256-byte row per pair.  The warps of a block
+// may drift apart by up to kPartK interfaces between two meetings.
+struct SwPartSmem {
+  double* buf;   // shared: [kPartK][4][nthreads]
+  double* part;  // rows of this block's group at this thread's column
+  size_t pstride, lev_first;
+  int ncc, nthreads, nw, tid, warp, lane, count;
+  bool valid, cloudy;
+  __device__ void put(size_t lev, bool cloudy_col, double sfu, double sfd, double scu, double scd) {
+    if (count == 0) lev_first = lev;  // interfaces arrive top-down: lev, lev - 1, ...
+    cloudy = cloudy_col;
+    double* b = buf + (size_t)count * 4 * nthreads + tid;
+    b[0] = sfu; b[nthreads] = sfd; b[2 * nthreads] = scu; b[3 * nthreads] = scd;
+    if (++count == kPartK) flush();
+  }
+  __device__ void flush() {
+    cb::barrier_unaligned(nthreads);
+    for (int p = warp; p < count * 4; p += nw) {
+      const int k = p >> 2, q = p & 3;
+      const double* b = buf + ((size_t)k * 4 + q) * nthreads + lane;
+      double s = b[0];
+      for (int w = 1; w < nw; ++w) s = s + b[w * 32];
+      // (column validity and cloudiness are properties of the lane's column: the same in every warp of the block)
+      if (valid && (q >= 2 || cloudy)) part[q * pstride + (lev_first - k) * ncc] = s;
+    }
+    cb::barrier_unaligned(nthreads);
+    count = 0;
+  }
+  __device__ void finish() {
+    if (count) flush();
+  }
+};
+
+// spcvrt_sw / spcvmc_sw: one block = 32 adjacent columns x CB_SW_GROUP units (one warp each, <= CB_SW_UMAX g-points of one band);
+// the same code for every band, so the instruction working set of an SM is one function body.
 template <bool MC>
-__global__ void __launch_bounds__(kBlock, CB_SW_RT_MIN_BLOCKS)
+__global__ void __launch_bounds__(32 * CB_SW_GROUP, CB_SW_RT_MIN_BLOCKS * 4 / CB_SW_GROUP)
     k_sw_transfer(const __grid_constant__ Tables T, const __grid_constant__ Solar sol, const __grid_constant__ In in, const Flags fl,
                   const __grid_constant__ Work W, const __grid_constant__ UnitList UL, int c0, int n) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  const int k = blockIdx.y;
+  __shared__ double s_part[kPartK * 4 * 32 * CB_SW_GROUP];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int group = blockIdx.y;
+  const int k = group * CB_SW_GROUP + threadIdx.y;
+  SwPartSmem sink;
+  sink.buf = s_part;
+  sink.pstride = (size_t)(in.nlay + 1) * W.ncc;
+  sink.part = W.part + (size_t)group * 4 * sink.pstride + c;
+  sink.ncc = W.ncc;
+  sink.nthreads = 32 * CB_SW_GROUP; sink.nw = CB_SW_GROUP;
+  sink.tid = threadIdx.y * 32 + threadIdx.x; sink.warp = threadIdx.y; sink.lane = threadIdx.x;
+  sink.count = 0; sink.lev_first = 0;
+  sink.valid = c < n; sink.cloudy = false;
+  if (c >= n || k >= UL.n) {  // no work, but the block's meetings need every thread: same number of put() calls
+    sink.cloudy = c < n && W.anycld[c] != 0;
+    for (int l = in.nlay; l >= 0; --l) sink.put((size_t)l, sink.cloudy, 0., 0., 0., 0.);
+    sink.finish();
+    return;
+  }
   const Unit un = UL.u[k];
-  if (CB_SW_UMAX >= 4 && un.u == 4) sw_transfer_unit<4, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, k);
-  else if (CB_SW_UMAX == 1) sw_transfer_unit<1, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, k);
-  else sw_transfer_unit<2, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, k);
+  if (CB_SW_UMAX >= 4 && un.u == 4) sw_transfer_unit<4, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, sink);
+  else if (CB_SW_UMAX == 1) sw_transfer_unit<1, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, sink);
+  else sw_transfer_unit<2, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, sink);
 }
 
 __global__ void __launch_bounds__(kBlock) k_sw_mask_kiss(const __grid_constant__ In in, const __grid_constant__ Work W,
@@ -103,7 +158,7 @@ __global__ void __launch_bounds__(kBlock) k_sw_reduce(const __grid_constant__ Wo
                                                       const Out out, int nlay, int ncol, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int lev = blockIdx.y;
-  if (c < n) sw_reduce_level(W, UL.u, UL.n, nlay, c0, c, lev, ncol, out);
+  if (c < n) sw_reduce_level(W, (UL.n + CB_SW_GROUP - 1) / CB_SW_GROUP, nlay, c0, c, lev, ncol, out);
 }
 
 __global__ void __launch_bounds__(kBlock) k_sw_heat(const __grid_constant__ Tables T, const __grid_constant__ In in,
@@ -172,7 +227,7 @@ struct cb200_sw_engine {
     CUDA_OK(cudaMalloc(&W.aer, sizeof(double) * 42 * L * n));
     CUDA_OK(cudaMalloc(&W.scr, sizeof(double) * 112 * NSCR * L * n));
     CUDA_OK(cudaMalloc(&W.src, sizeof(double) * 112 * n));
-    CUDA_OK(cudaMalloc(&W.part, sizeof(double) * UL.n * 4 * (L + 1) * n));
+    CUDA_OK(cudaMalloc(&W.part, sizeof(double) * ((UL.n + CB_SW_GROUP - 1) / CB_SW_GROUP) * 4 * (L + 1) * n));
     CUDA_OK(cudaMalloc(&W.mask, sizeof(unsigned) * 4 * L * n));
     CUDA_OK(cudaMalloc(&W.err, sizeof(int)));
     CUDA_OK(cudaMemset(W.err, 0, sizeof(int)));
@@ -281,8 +336,9 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
   if (e->timing) cudaEventRecord(e->ev0, st);
   k_sw_taumol<<<dim3(gx, e->UL_tau.n, CB_SW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, sol, in, W, e->UL_tau, c0, n);
   if (e->timing) cudaEventRecord(e->evm, st);
-  if (mc) k_sw_transfer<true><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
-  else k_sw_transfer<false><<<dim3(gx, e->UL.n), kBlock, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+  const dim3 gt((n + 31) / 32, (e->UL.n + CB_SW_GROUP - 1) / CB_SW_GROUP), bt(32, CB_SW_GROUP);
+  if (mc) k_sw_transfer<true><<<gt, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+  else k_sw_transfer<false><<<gt, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
   if (e->timing) cudaEventRecord(e->ev1, st);
   k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, e->UL, out, nlay, out_ncol, c0, n);
   k_sw_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);

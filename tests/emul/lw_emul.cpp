@@ -22,9 +22,12 @@ static void run_taumol(const Tables& T, const In& in, const Work& W, int n, int 
 template <int U, bool DRV>
 static void run_transfer(const Tables& T, const In& in, const Work& W, int n, int ib, int g0, int unit, bool mc, bool mr) {
   for (int c = 0; c < n; ++c) {
-    if (mc) lw_transfer_unit<U, true, false, DRV>(T, in, W, 0, c, ib, g0, unit);
-    else if (mr) lw_transfer_unit<U, false, true, DRV>(T, in, W, 0, c, ib, g0, unit);
-    else lw_transfer_unit<U, false, false, DRV>(T, in, W, 0, c, ib, g0, unit);
+    // the units of a group accumulate into the group's (zeroed) rows in unit order, like the warps of a block on the device
+    const size_t pstride = (size_t)(in.nlay + 1) * W.ncc;
+    LwPartDirect sink{W.part + (size_t)(unit / CB_LW_GROUP) * W.npart * pstride + c, pstride, W.ncc};
+    if (mc) lw_transfer_unit<U, true, false, DRV>(T, in, W, 0, c, ib, g0, sink);
+    else if (mr) lw_transfer_unit<U, false, true, DRV>(T, in, W, 0, c, ib, g0, sink);
+    else lw_transfer_unit<U, false, false, DRV>(T, in, W, 0, c, ib, g0, sink);
   }
 }
 
@@ -97,7 +100,7 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
       }
     }
     for (int c = 0; c < ncol; ++c)
-      for (int lev = 0; lev <= nlay; ++lev) lw_reduce_level(T, W, units, nunits, nlay, 0, c, lev, ncol, out);
+      for (int lev = 0; lev <= nlay; ++lev) lw_reduce_level(T, W, (nunits + CB_LW_GROUP - 1) / CB_LW_GROUP, nlay, 0, c, lev, ncol, out);
     for (int c = 0; c < ncol; ++c)
       for (int l = 0; l < nlay; ++l) lw_heating(T, in, out, c, l);
     return err;

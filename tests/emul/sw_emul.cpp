@@ -21,8 +21,11 @@ static void run_taumol(const Tables& T, const Solar& sol, const In& in, const Wo
 template <int U>
 static void run_transfer(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int n, int ib, int g0, int unit, bool mc) {
   for (int c = 0; c < n; ++c) {
-    if (mc) sw_transfer_unit<U, true>(T, sol, in, fl, W, 0, c, ib, g0, unit);
-    else sw_transfer_unit<U, false>(T, sol, in, fl, W, 0, c, ib, g0, unit);
+    // the units of a group accumulate into the group's (zeroed) rows in unit order, like the warps of a block on the device
+    const size_t pstride = (size_t)(in.nlay + 1) * W.ncc;
+    SwPartDirect sink{W.part + (size_t)(unit / CB_SW_GROUP) * 4 * pstride + c, pstride, W.ncc};
+    if (mc) sw_transfer_unit<U, true>(T, sol, in, fl, W, 0, c, ib, g0, sink);
+    else sw_transfer_unit<U, false>(T, sol, in, fl, W, 0, c, ib, g0, sink);
   }
 }
 
@@ -94,7 +97,7 @@ extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* 
     }
     if (g_scr_export) std::memcpy(g_scr_export, scr.data(), scr.size() * sizeof(double));
     for (int c = 0; c < ncol; ++c)
-      for (int lev = 0; lev <= nlay; ++lev) sw_reduce_level(W, units, nunits, nlay, 0, c, lev, ncol, out);
+      for (int lev = 0; lev <= nlay; ++lev) sw_reduce_level(W, (nunits + CB_SW_GROUP - 1) / CB_SW_GROUP, nlay, 0, c, lev, ncol, out);
     for (int c = 0; c < ncol; ++c)
       for (int l = 0; l < nlay; ++l) sw_heating(T, in, out, c, l);
     return err;
