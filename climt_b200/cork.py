@@ -208,11 +208,59 @@ def _bind(L):
     L.cb200_cork_sw_run_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, _dp, pi, po]
 
 
+def esft_weights(gpoint_weights, ngas):
+    """Combined g-point weights of the ESFT overlap (cork/optics/correlated_k.py:343-372): for N gases with G g-points each,
+    G**N weights per band, the products of the per-gas weights multiplied in gas order (digit `gas` of the combined index in
+    base G selects that gas's g-point) -- the same multiplication order as the reference, so the same bits."""
+    w = np.asarray(gpoint_weights, dtype=np.float64)
+    nband, ngpt = w.shape
+    idx = np.arange(ngpt ** ngas)
+    out = np.ones((nband, idx.size))
+    rem = idx.copy()
+    for _ in range(ngas):
+        out = out * w[:, rem % ngpt]
+        rem //= ngpt
+    return out
+
+
+def is_esft(table):
+    return str(table.get("overlap_method", np.array("additive"))) == "esft"
+
+
+def expand_esft_table(table):
+    """An ESFT-overlap table (cork/optics/correlated_k.py:564-594: every combination of one g-point per gas is a g-point of the
+    band, optical depths add over the gases) restated as an additive-overlap table on the G**N combined g-points, which is what
+    the engine evaluates:
+      * k[gas, band, idx] = k[gas, band, digit_gas(idx)] (base-G digits, gas 0 the lowest) -- the engine's sum over gases, in gas
+        order, is then term for term the reference's `tau[ib, idx] += k_interp[ig, ib, g_idx] * amount[ig]`;
+      * weights = the products of the per-gas weights (`compute_esft_weights`, :343-372);
+      * Planck fractions and the solar source are looked up at `idx % G` (cork/lw/kernels.py:43,65; cork/sw/component.py:373-385);
+      * the band-grey continuum is not part of the ESFT path (:564-594 never reads it) and is dropped.
+    With one gas the expansion is the identity (apart from the continuum)."""
+    k = np.asarray(table["k_coefficients"])
+    ngas, nband, ngpt = k.shape[:3]
+    ncomb = ngpt ** ngas
+    idx = np.arange(ncomb)
+    out = dict(table)
+    kx = np.empty((ngas, nband, ncomb) + k.shape[3:], dtype=k.dtype)
+    for ig in range(ngas):
+        kx[ig] = k[ig][:, (idx // ngpt ** ig) % ngpt]
+    out["k_coefficients"] = kx
+    out["gpoint_weights"] = esft_weights(table["gpoint_weights"], ngas)
+    for name in ("planck_fraction", "solar_source_per_gpoint"):
+        if name in table and table[name] is not None:
+            a = np.asarray(table[name])
+            out[name] = np.ascontiguousarray(a[:, idx % a.shape[1]])
+    out.pop("continuum_kappa", None)
+    out["overlap_method"] = np.array("additive")
+    out["_esft_expanded_from"] = np.array([ngas, ngpt])
+    return out
+
+
 def make_ctable(table, co2_logk=CO2_INTERP_LOGK):
     """dict of arrays -> (cb200_cork_table, keep-alive list).  float32 k stays float32; grids are promoted to float64 exactly."""
-    overlap = str(table.get("overlap_method", np.array("additive")))
-    if overlap == "esft":
-        raise NotImplementedError("ESFT-overlap k-tables are not supported by the CUDA engine (additive overlap only)")
+    if is_esft(table):
+        table = expand_esft_table(table)
     k = np.asarray(table["k_coefficients"])
     if k.ndim not in (5, 6, 7):
         raise ValueError(f"k_coefficients must have 5, 6 or 7 dimensions, got {k.ndim}")
@@ -281,8 +329,11 @@ class CorkEngine:
             self.nband, self.ngpt, self.ngas = (2 if which == "lw" else 3), 1, 1
             return
         self.table = load_k_table(table) if isinstance(table, (str, os.PathLike)) else table
+        esft = is_esft(self.table)
+        if esft:  # evaluated as an additive table on the combined g-points (expand_esft_table)
+            self.table = expand_esft_table(self.table)
         self.ctable, self._keep = make_ctable(self.table)
-        if isinstance(table, (str, os.PathLike)) and os.fspath(table).endswith(".cb2k"):
+        if not esft and isinstance(table, (str, os.PathLike)) and os.fspath(table).endswith(".cb2k"):
             # the engine's own container: the library reads, classifies and re-lays out the file itself (no numpy on this path)
             self._L.cb200_cork_create_from_file.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p] + [ctypes.c_double] * 3 + [ctypes.c_int]
             rc = self._L.cb200_cork_create_from_file(ctypes.byref(self._h), os.fspath(table).encode(), g, cpd, sigma, device)
@@ -436,6 +487,8 @@ class _CorkBase(TendencyComponent):
             _num_bands[self._which] = self._num_bands
             return
         self._table = load_k_table(table) if isinstance(table, (str, os.PathLike)) else table
+        if is_esft(self._table):
+            self._table = expand_esft_table(self._table)
         k = self._table["k_coefficients"]
         self._num_bands, self._num_gpts = k.shape[1], k.shape[2]
         (self._gas_names, _has_h2o, self._has_co2_axis, self._fully_premixed, self._premixed_bg) = table_flags(self._table)

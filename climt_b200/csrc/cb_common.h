@@ -121,6 +121,44 @@ inline double frcp(double b) { return 1.0 / b; }
 inline double fdiv(double a, double b) { return a / b; }
 #endif
 
+// Cache-residency hints of the slab form of the transfer kernels (lw_engine.cu / sw_engine.cu): the rows a warp carries from one
+// vertical sweep to the other live in a slab that is meant to stay in the L2, so
+//   * what streams through once (the taumol rows, the partial-flux rows) is loaded / stored "evict first" (ld/st.global.cs) and
+//     fetched a few layers ahead into the L2 only (prefetch.global.L2: no registers held while the line travels);
+//   * slab rows are stored with an L2 evict_last policy and read back for the last time with evict_first.
+// Plain loads and stores on the host (tests/emul).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned long long policy_keep() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long policy_drop() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_policy(double* p, double v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double ld_policy(const double* p, unsigned long long pol) {
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+#else
+inline double ld_stream(const double* p) { return *p; }
+inline void st_stream(double* p, double v) { *p = v; }
+inline void prefetch_l2(const void*) {}
+inline unsigned long long policy_keep() { return 0; }
+inline unsigned long long policy_drop() { return 0; }
+inline void st_policy(double* p, double v, unsigned long long) { *p = v; }
+inline double ld_policy(const double* p, unsigned long long) { return *p; }
+#endif
+
 // Fortran real->integer assignment / int(): truncation toward zero.
 CB_HD int f2i(double x) { return (int)x; }
 CB_HD int imin(int a, int b) { return a < b ? a : b; }

@@ -1064,8 +1064,24 @@ struct LwPartDirect {
 
 // DRV: also the derivative of the upward flux with respect to the surface temperature (idrv = 1, rtrn.f90:458-461,473-476,
 // 492-512; the same lines in rtrnmc.f90:447-510 and rtrnmr.f90:629-711): one more multiplicative recurrence in the up sweep.
-template <int U, bool MC, bool MR, bool DRV, class Sink>
-CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int ib, int g0, Sink& sink) {
+// Where the down sweep parks what the up sweep needs again (rows 0-3 of NSCR).  Default (p == nullptr): the unit's own rows of
+// W.scr.  The slab form of the CUDA kernel (lw_engine.cu, k_units_slab) points it at a per-warp slab reused for every unit the
+// warp processes: written top-down, read back bottom-up (last in, first out), so a slab that fits the warp's share of the L2
+// never reaches HBM.
+struct Carry {
+  double* p;          // at this thread's lane
+  size_t rs, ls, us;  // strides between rows, layers and the g-points of a unit
+};
+// SLAB: the carried rows live in an L2-resident slab (cy given): cache-residency hints of cb_common.h on every access, the taumol
+// rows fetched kSlabAhead layers ahead into the L2.
+constexpr int kSlabAhead = 4;
+template <int U, bool MC, bool MR, bool DRV, class Sink, bool SLAB = false>
+CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0, int c, int ib, int g0, Sink& sink,
+                            Carry cy = Carry{nullptr, 0, 0, 0}) {
+  const unsigned long long pol_keep = SLAB ? policy_keep() : 0ull, pol_drop = SLAB ? policy_drop() : 0ull;
+  auto cst = [&](double* p, double v) { if (SLAB) st_policy(p, v, pol_keep); else *p = v; };
+  auto cld = [&](const double* p) { return SLAB ? ld_policy(p, pol_drop) : *p; };
+  auto sld = [&](const double* p) { return SLAB ? ld_stream(p) : *p; };
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
   const double* __restrict__ tb = T.base;
@@ -1088,6 +1104,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
     ibc = ib;
   }
   const int gabs = band_gstart(ib) + g0;  // absolute g-point of u = 0
+  if (!cy.p) cy = Carry{W.scr + ((size_t)gabs * NSCR) * wstride + c, wstride, (size_t)ncc, (size_t)NSCR * wstride};
   double radld[U], radclrd[U], frac1[U];
   double mr_cld[U], mr_clr[U], mr_rad[U];  // MR: cloudy / clear parts of the radiance and the overlap correction (cldradd, clrradd, rad)
 #pragma unroll
@@ -1113,8 +1130,12 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
-      v.tau[u] = scr[R_TAU * wstride];
-      v.frac[u] = scr[R_FRAC * wstride];
+      if (SLAB && l >= kSlabAhead) {
+        prefetch_l2(scr + R_TAU * wstride - (size_t)kSlabAhead * ncc);
+        prefetch_l2(scr + R_FRAC * wstride - (size_t)kSlabAhead * ncc);
+      }
+      v.tau[u] = sld(scr + R_TAU * wstride);
+      v.frac[u] = sld(scr + R_FRAC * wstride);
     }
     return v;
   };
@@ -1170,7 +1191,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
     for (int u = 0; u < U; ++u) {
       const bool on = !MC || ((mbits >> u) & 1u);
       const double odcld = on ? odcld_l : 0., efclfrac = on ? efclfrac_l : 0., cldfrac = on ? cldfrac_l : 0.;
-      double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
+      double* __restrict__ cr = cy.p + (size_t)u * cy.us + (size_t)l * cy.ls;
       const double plfrac = cur.frac[u];
       double odepth = secdiff * (cur.tau[u] + taua);
       if (odepth < 0.0) odepth = 0.0;
@@ -1242,8 +1263,8 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
         } else {
           radld[u] = radld[u] - radld[u] * (atrans + efclfrac * (1. - atrans)) + gassrc + cldfrac * (bbdtot * atot - gassrc);
         }
-        scr[2 * wstride] = atot;
-        scr[3 * wstride] = bbutot;
+        cst(cr + 2 * cy.rs, atot);
+        cst(cr + 3 * cy.rs, bbutot);
       } else {
         if (odepth <= 0.06) {
           atrans = odepth - 0.5 * odepth * odepth;
@@ -1262,8 +1283,8 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
         }
         radld[u] = radld[u] + (bbd - radld[u]) * atrans;
       }
-      scr[0] = atrans;
-      scr[wstride] = bbugas;
+      cst(cr, atrans);
+      cst(cr + cy.rs, bbugas);
       sum_d = sum_d + radld[u];
       if (iclddn == 1) {
         radclrd[u] = radclrd[u] + (bbd - radclrd[u]) * atrans;
@@ -1308,9 +1329,9 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
     UpIn v;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
-      v.atrans[u] = scr[0];
-      v.bbugas[u] = scr[wstride];
+      const double* __restrict__ cr = cy.p + (size_t)u * cy.us + (size_t)l * cy.ls;
+      v.atrans[u] = cld(cr);
+      v.bbugas[u] = cld(cr + cy.rs);
     }
     return v;
   };
@@ -1355,10 +1376,10 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
     for (int u = 0; u < U; ++u) {
       const bool on = !MC || ((mbits >> u) & 1u);
       const double efclfrac = on ? efclfrac_l : 0., cldfrac = on ? cldfrac_l : 0.;
-      const double* __restrict__ scr = W.scr + (((size_t)(gabs + u) * NSCR) * nlay + l) * ncc + c;
+      const double* __restrict__ cr = cy.p + (size_t)u * cy.us + (size_t)l * cy.ls;
       const double atrans = ucur.atrans[u], bbugas = ucur.bbugas[u];
       if (cloudy) {
-        const double atot = scr[2 * wstride], bbutot = scr[3 * wstride];
+        const double atot = cld(cr + 2 * cy.rs), bbutot = cld(cr + 3 * cy.rs);
         const double gassrc = bbugas * atrans;
         if (DRV) d_radlu[u] = d_radlu[u] * cldfrac * (1.0 - atot) + d_radlu[u] * (1.0 - cldfrac) * (1.0 - atrans);
         if (MR) {

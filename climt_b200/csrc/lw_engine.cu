@@ -118,6 +118,7 @@ struct LwPartSmem {
   int nv;   // values per put of the current sweep: down 2 (rows 1, 3), up 2 or 4 (rows 0, 2, 4, 5); odd ones are clear-sky rows
   int dir;  // +1: up sweep, interfaces arrive bottom-up; -1: down sweep, top-down
   bool valid, cloudy;
+  bool stream = false;  // slab form of the kernel: the rows are written "evict first" so that they do not displace the slabs in the L2
   __device__ void stage(size_t lev, double v0, double v1, double v2, double v3) {
     if (count == 0) lev_first = lev;
     double* b = buf + (size_t)count * 4 * nthreads + tid;
@@ -144,7 +145,10 @@ struct LwPartSmem {
       for (int w = 1; w < nw; ++w) s = s + b[w * 32];
       const int row = dir < 0 ? 1 + 2 * q : (q < 2 ? 2 * q : 2 + q);
       // (column validity and cloudiness are properties of the lane's column: the same in every warp of the block)
-      if (valid && (!(q & 1) || cloudy)) part[row * pstride + (size_t)((long)lev_first + (long)dir * k) * ncc] = s;
+      if (valid && (!(q & 1) || cloudy)) {
+        double* o = part + row * pstride + (size_t)((long)lev_first + (long)dir * k) * ncc;
+        if (stream) cb::st_stream(o, s); else *o = s;
+      }
     }
     cb::barrier_unaligned(nthreads);
     count = 0;
@@ -185,6 +189,51 @@ __global__ void __launch_bounds__(32 * CB_LW_GROUP, (CB_LW_RT_MIN_BLOCKS * 4 + C
   if (CB_LW_UMAX >= 4 && un.u == 4) lw_transfer_unit<4, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, sink);
   else if (CB_LW_UMAX == 1) lw_transfer_unit<1, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, sink);
   else lw_transfer_unit<2, MC, MR, DRV>(T, in, W, c0, c, un.band - 1, un.g0, sink);
+}
+
+// The slab form of the transfer kernel: a persistent grid (blocks per SM chosen by the host) walks the (column tile, group of
+// units) work items; each warp keeps the rows it carries from the down sweep to the up sweep in a slab of its own that it reuses
+// item after item, laid out [layer][g-point][row][lane].  The rows are read back in the reverse order of their writing, so with the
+// slabs of all resident warps inside the L2 they never reach HBM.
+#ifndef CB_LW_SLAB_MIN_BLOCKS
+#define CB_LW_SLAB_MIN_BLOCKS 4
+#endif
+template <bool MC, bool MR, bool DRV = false>
+__global__ void __launch_bounds__(32 * CB_LW_GROUP, CB_LW_SLAB_MIN_BLOCKS)
+    k_units_slab(const __grid_constant__ Tables T, const __grid_constant__ In in, const __grid_constant__ Work W,
+                 const __grid_constant__ UnitList UL, double* __restrict__ slabs, int c0, int n) {
+  __shared__ double s_part[kPartK * 4 * 32 * CB_LW_GROUP];
+  const int ntiles = (n + 31) / 32, ngroups = (UL.n + CB_LW_GROUP - 1) / CB_LW_GROUP;
+  const int nlay = in.nlay;
+  Carry cy;
+  cy.rs = 32; cy.us = 4 * 32; cy.ls = CB_LW_UMAX * 4 * 32;
+  cy.p = slabs + ((size_t)blockIdx.x * CB_LW_GROUP + threadIdx.y) * ((size_t)nlay * CB_LW_UMAX * 4 * 32) + threadIdx.x;
+  for (int w = blockIdx.x; w < ntiles * ngroups; w += gridDim.x) {
+    const int tile = w % ntiles, group = w / ntiles;
+    const int c = tile * 32 + threadIdx.x;
+    const int k = group * CB_LW_GROUP + threadIdx.y;
+    LwPartSmem sink;
+    sink.buf = s_part;
+    sink.pstride = (size_t)(nlay + 1) * W.ncc;
+    sink.part = W.part + (size_t)group * W.npart * sink.pstride + c;
+    sink.ncc = W.ncc;
+    sink.nthreads = 32 * CB_LW_GROUP; sink.nw = CB_LW_GROUP;
+    sink.tid = threadIdx.y * 32 + threadIdx.x; sink.warp = threadIdx.y; sink.lane = threadIdx.x;
+    sink.count = 0; sink.lev_first = 0; sink.nv = 2; sink.dir = 1;
+    sink.valid = c < n; sink.cloudy = false; sink.stream = true;
+    if (c >= n || k >= UL.n) {
+      const bool cl = c < n && W.ncbands[c] > 0;
+      for (int lev = nlay; lev >= 1; --lev) sink.put_dn((size_t)(lev - 1), cl, 0., 0.);
+      sink.end_sweep();
+      for (int lev = 0; lev <= nlay; ++lev) sink.put_up((size_t)lev, cl, 0., 0., DRV, 0., 0.);
+      sink.end_sweep();
+      continue;
+    }
+    const Unit un = UL.u[k];
+    if (CB_LW_UMAX >= 4 && un.u == 4) lw_transfer_unit<4, MC, MR, DRV, LwPartSmem, true>(T, in, W, c0, c, un.band - 1, un.g0, sink, cy);
+    else if (CB_LW_UMAX == 1) lw_transfer_unit<1, MC, MR, DRV, LwPartSmem, true>(T, in, W, c0, c, un.band - 1, un.g0, sink, cy);
+    else lw_transfer_unit<2, MC, MR, DRV, LwPartSmem, true>(T, in, W, c0, c, un.band - 1, un.g0, sink, cy);
+  }
 }
 
 // McICA cloud mask with the per-column kissvec generator: one thread per column
@@ -239,6 +288,10 @@ struct cb200_lw_engine {
   Work W{};
   double *drv_up = nullptr, *drv_upc = nullptr;  // idrv = 1 outputs of the next run call (host or device pointers, like its outputs)
   int max_chunk = 16384;
+  int slab_bps = 0;          // > 0: the slab form of the transfer kernel with this many 4-warp blocks per SM (CLIMT_B200_LW_SLAB)
+  double* d_slabs = nullptr;
+  size_t slabs_cap = 0;
+  int n_sm = 148;
   // host-pointer path
   cb::HostPipe pipe;
   size_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the last host-pointer call
@@ -310,6 +363,8 @@ extern "C" int cb200_lw_create(cb200_lw_engine** out, const char* table_blob, co
       if (lw_band_staged(b)) e->tau_smem = std::max(e->tau_smem, (size_t)e->T.b[b - 1].rows * TGW * sizeof(double));
     if (const char* mc = std::getenv("CLIMT_B200_MAX_CHUNK")) e->max_chunk = std::max(128, std::atoi(mc));
     if (const char* z = std::getenv("CLIMT_B200_SKIP_ZERO_INPUTS")) e->skip_zero_inputs = std::atoi(z) != 0;
+    if (const char* sb = std::getenv("CLIMT_B200_LW_SLAB")) e->slab_bps = std::max(0, std::atoi(sb));
+    cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
     cudaMallocHost(&e->h_err, sizeof(int));
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
@@ -331,6 +386,7 @@ extern "C" void cb200_lw_destroy(cb200_lw_engine* e) {
   e->free_work();
   cudaFree(e->d_tables);
   cudaFree(e->d_mask_full);
+  cudaFree(e->d_slabs);
   e->pipe.destroy();
   if (e->h_err) cudaFreeHost(e->h_err);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -395,7 +451,28 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
   if (e->timing) cudaEventRecord(e->evm, st);
   // non-McICA: icld = 1 -> rtrn (random overlap); icld = 2, 3 -> rtrnmr (maximum-random), rrtmg_lw_rad.nomcica.f90:527-541
   const dim3 gu((n + 31) / 32, (e->UL.n + CB_LW_GROUP - 1) / CB_LW_GROUP), bu(32, CB_LW_GROUP);
-  if (W.npart == 6) {
+  if (e->slab_bps > 0) {
+    const int nb = (int)std::min<size_t>((size_t)gu.x * gu.y, (size_t)e->n_sm * e->slab_bps);
+    const size_t need = (size_t)nb * CB_LW_GROUP * nlay * CB_LW_UMAX * 4 * 32;
+    if (need > e->slabs_cap) {
+      cudaStreamSynchronize(st);
+      cudaFree(e->d_slabs);
+      e->d_slabs = nullptr;
+      e->slabs_cap = 0;
+      CUDA_OK(cudaMalloc(&e->d_slabs, need * sizeof(double)));
+      e->slabs_cap = need;
+    }
+    double* sl = e->d_slabs;
+    if (W.npart == 6) {
+      if (mc) k_units_slab<true, false, true><<<nb, bu, 0, st>>>(e->T, in, W, e->UL, sl, c0, n);
+      else if (e->fl.icld >= 2) k_units_slab<false, true, true><<<nb, bu, 0, st>>>(e->T, in, W, e->UL, sl, c0, n);
+      else k_units_slab<false, false, true><<<nb, bu, 0, st>>>(e->T, in, W, e->UL, sl, c0, n);
+    } else {
+      if (mc) k_units_slab<true, false><<<nb, bu, 0, st>>>(e->T, in, W, e->UL, sl, c0, n);
+      else if (e->fl.icld >= 2) k_units_slab<false, true><<<nb, bu, 0, st>>>(e->T, in, W, e->UL, sl, c0, n);
+      else k_units_slab<false, false><<<nb, bu, 0, st>>>(e->T, in, W, e->UL, sl, c0, n);
+    }
+  } else if (W.npart == 6) {
     if (mc) k_units<true, false, true><<<gu, bu, 0, st>>>(e->T, in, W, e->UL, c0, n);
     else if (e->fl.icld >= 2) k_units<false, true, true><<<gu, bu, 0, st>>>(e->T, in, W, e->UL, c0, n);
     else k_units<false, false, true><<<gu, bu, 0, st>>>(e->T, in, W, e->UL, c0, n);

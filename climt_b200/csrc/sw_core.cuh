@@ -803,10 +803,26 @@ struct SwPartDirect {
   CB_HD void finish() {}
 };
 
+// Where the upward sweep parks what the downward sweep needs again (rows 0-13 of NSCR: five layer properties + rup, rupd, clear
+// and total).  Default (p == nullptr): the unit's own rows of W.scr.  The slab form of the CUDA kernel (sw_engine.cu,
+// k_sw_transfer_slab) points it at a per-warp slab that the warp reuses for every unit it processes: the rows are written bottom-up
+// and read back top-down (last in, first out), so a slab that fits the L2 share of its warp never reaches HBM.
+struct Carry {
+  double* p;          // at this thread's lane
+  size_t rs, ls, us;  // strides between rows, layers and the g-points of a unit
+};
+
 // spcvrt_sw / spcvmc_sw for U consecutive g-points of band ib (rrtmg_sw_spcvrt.f90:329-661) -- generic in the band.
-template <int U, bool MC, class Sink, bool RECOMPUTE = (CB_SW_RECOMPUTE != 0)>
+// SLAB: the carried rows live in an L2-resident slab (cy given): cache-residency hints of cb_common.h on every access, the taumol
+// rows fetched kSlabAhead layers ahead into the L2.
+constexpr int kSlabAhead = 4;
+template <int U, bool MC, class Sink, bool RECOMPUTE = (CB_SW_RECOMPUTE != 0), bool SLAB = false>
 CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int c0, int c,
-                            int ib, int g0, Sink& sink) {
+                            int ib, int g0, Sink& sink, Carry cy = Carry{nullptr, 0, 0, 0}) {
+  const unsigned long long pol_keep = SLAB ? policy_keep() : 0ull, pol_drop = SLAB ? policy_drop() : 0ull;
+  auto cst = [&](double* p, double v) { if (SLAB) st_policy(p, v, pol_keep); else *p = v; };
+  auto cld = [&](const double* p) { return SLAB ? ld_policy(p, pol_drop) : *p; };
+  auto sld = [&](const double* p) { return SLAB ? ld_stream(p) : *p; };
   const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
   const size_t gc = (size_t)(c0 + c);
   const double* __restrict__ tb = T.base;
@@ -823,6 +839,7 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
   const int gabs = band_gstart(ib) + g0;
   const size_t growstride = (size_t)NSCR * wstride;  // scratch stride between consecutive g-points
   double* __restrict__ scr0 = W.scr + ((size_t)gabs * NSCR) * wstride + c;
+  if (!cy.p) cy = Carry{scr0, wstride, (size_t)ncc, growstride};
   // aerosol / cloud optical properties of this band in layer l, and the McICA bits of the unit's g-points
   struct BandLayer {
     double ptaua, pomga, pasya, pclfr, ptauc, pomgc, pasyc;
@@ -869,8 +886,13 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
     const BandLayer b = band_layer(l);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      double* __restrict__ scr = scr0 + (size_t)u * growstride + (size_t)l * ncc;
-      const double taug = scr[R_TAUG * wstride], taur = scr[R_TAUR * wstride];
+      const double* __restrict__ scr = scr0 + (size_t)u * growstride + (size_t)l * ncc;
+      double* __restrict__ cr = cy.p + (size_t)u * cy.us + (size_t)l * cy.ls;
+      if (SLAB && l + kSlabAhead < nlay) {
+        prefetch_l2(scr + R_TAUG * wstride + (size_t)kSlabAhead * ncc);
+        prefetch_l2(scr + R_TAUR * wstride + (size_t)kSlabAhead * ncc);
+      }
+      const double taug = sld(scr + R_TAUG * wstride), taur = sld(scr + R_TAUR * wstride);
       const SwLayer L = layer(b, u, taug, taur);
       {
         const double zreflect = frcp(1. - rupdc[u] * L.refdc);
@@ -879,20 +901,20 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
         rupc[u] = rn; rupdc[u] = rdn;
       }
       if (!RECOMPUTE) {
-        scr[0 * wstride] = L.refc; scr[1 * wstride] = L.refdc; scr[2 * wstride] = L.trac; scr[3 * wstride] = L.tradc;
-        scr[4 * wstride] = L.dbtc;
+        cst(cr + 0 * cy.rs, L.refc); cst(cr + 1 * cy.rs, L.refdc); cst(cr + 2 * cy.rs, L.trac); cst(cr + 3 * cy.rs, L.tradc);
+        cst(cr + 4 * cy.rs, L.dbtc);
       }
-      scr[5 * wstride] = rupc[u]; scr[6 * wstride] = rupdc[u];
+      cst(cr + 5 * cy.rs, rupc[u]); cst(cr + 6 * cy.rs, rupdc[u]);
       if (cloudy_col) {
         const double zreflect = frcp(1. - rupd[u] * L.refd);
         const double rn = L.ref + (L.trad * ((L.tra - L.dbt) * rupd[u] + L.dbt * rup[u])) * zreflect;
         const double rdn = L.refd + L.trad * L.trad * rupd[u] * zreflect;
         rup[u] = rn; rupd[u] = rdn;
         if (!RECOMPUTE) {
-          scr[7 * wstride] = L.ref; scr[8 * wstride] = L.refd; scr[9 * wstride] = L.tra; scr[10 * wstride] = L.trad;
-          scr[11 * wstride] = L.dbt;
+          cst(cr + 7 * cy.rs, L.ref); cst(cr + 8 * cy.rs, L.refd); cst(cr + 9 * cy.rs, L.tra); cst(cr + 10 * cy.rs, L.trad);
+          cst(cr + 11 * cy.rs, L.dbt);
         }
-        scr[12 * wstride] = rup[u]; scr[13 * wstride] = rupd[u];
+        cst(cr + 12 * cy.rs, rup[u]); cst(cr + 13 * cy.rs, rupd[u]);
       }
     }
   }
@@ -914,21 +936,22 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
       double ref = 0., refd = 0., tra = 0., trad = 0., dbt = 0., prup = albdir, prupd = albdif;
       if (l >= 0) {
         const double* __restrict__ scr = scr0 + (size_t)u * growstride + (size_t)l * ncc;
+        const double* __restrict__ cr = cy.p + (size_t)u * cy.us + (size_t)l * cy.ls;
         if (RECOMPUTE) {
           const SwLayer L = layer(b, u, scr[R_TAUG * wstride], scr[R_TAUR * wstride]);
           refc = L.refc; refdc = L.refdc; trac = L.trac; tradc = L.tradc; dbtc = L.dbtc;
           ref = L.ref; refd = L.refd; tra = L.tra; trad = L.trad; dbt = L.dbt;
         } else {
-          refc = scr[0 * wstride]; refdc = scr[1 * wstride]; trac = scr[2 * wstride]; tradc = scr[3 * wstride];
-          dbtc = scr[4 * wstride];
+          refc = cld(cr + 0 * cy.rs); refdc = cld(cr + 1 * cy.rs); trac = cld(cr + 2 * cy.rs); tradc = cld(cr + 3 * cy.rs);
+          dbtc = cld(cr + 4 * cy.rs);
         }
-        prupc = scr[5 * wstride]; prupdc = scr[6 * wstride];
+        prupc = cld(cr + 5 * cy.rs); prupdc = cld(cr + 6 * cy.rs);
         if (cloudy_col) {
           if (!RECOMPUTE) {
-            ref = scr[7 * wstride]; refd = scr[8 * wstride]; tra = scr[9 * wstride]; trad = scr[10 * wstride];
-            dbt = scr[11 * wstride];
+            ref = cld(cr + 7 * cy.rs); refd = cld(cr + 8 * cy.rs); tra = cld(cr + 9 * cy.rs); trad = cld(cr + 10 * cy.rs);
+            dbt = cld(cr + 11 * cy.rs);
           }
-          prup = scr[12 * wstride]; prupd = scr[13 * wstride];
+          prup = cld(cr + 12 * cy.rs); prupd = cld(cr + 13 * cy.rs);
         }
       }
       {

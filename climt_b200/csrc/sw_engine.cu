@@ -91,6 +91,7 @@ struct SwPartSmem {
   size_t pstride, lev_first;
   int ncc, nthreads, nw, tid, warp, lane, count;
   bool valid, cloudy;
+  bool stream = false;  // slab form of the kernel: the rows are written "evict first" so that they do not displace the slabs in the L2
   __device__ void put(size_t lev, bool cloudy_col, double sfu, double sfd, double scu, double scd) {
     if (count == 0) lev_first = lev;  // interfaces arrive top-down: lev, lev - 1, ...
     cloudy = cloudy_col;
@@ -106,7 +107,10 @@ struct SwPartSmem {
       double s = b[0];
       for (int w = 1; w < nw; ++w) s = s + b[w * 32];
       // (column validity and cloudiness are properties of the lane's column: the same in every warp of the block)
-      if (valid && (q >= 2 || cloudy)) part[q * pstride + (lev_first - k) * ncc] = s;
+      if (valid && (q >= 2 || cloudy)) {
+        double* o = part + q * pstride + (lev_first - k) * ncc;
+        if (stream) cb::st_stream(o, s); else *o = s;
+      }
     }
     cb::barrier_unaligned(nthreads);
     count = 0;
@@ -145,6 +149,48 @@ __global__ void __launch_bounds__(32 * CB_SW_GROUP, CB_SW_RT_MIN_BLOCKS * 4 / CB
   if (CB_SW_UMAX >= 4 && un.u == 4) sw_transfer_unit<4, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, sink);
   else if (CB_SW_UMAX == 1) sw_transfer_unit<1, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, sink);
   else sw_transfer_unit<2, MC>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, sink);
+}
+
+// The slab form of the transfer kernel: a persistent grid (blocks per SM chosen by the host) walks the (column tile, group of
+// units) work items; each warp keeps the rows it carries from the upward to the downward sweep in a slab of its own that it
+// reuses item after item, laid out [layer][row][lane].  The rows are read back in the reverse order of their writing, so with
+// the slabs of all resident warps inside the L2 the rows never reach HBM: the in-flight footprint is
+// (resident warps) x nlay x (7 | 14 rows) x 256 B instead of the whole chunk's 112 x 14 x nlay x ncc x 8 B.
+#ifndef CB_SW_SLAB_MIN_BLOCKS
+#define CB_SW_SLAB_MIN_BLOCKS 4
+#endif
+template <bool MC>
+__global__ void __launch_bounds__(32 * CB_SW_GROUP, CB_SW_SLAB_MIN_BLOCKS)
+    k_sw_transfer_slab(const __grid_constant__ Tables T, const __grid_constant__ Solar sol, const __grid_constant__ In in, const Flags fl,
+                       const __grid_constant__ Work W, const __grid_constant__ UnitList UL, double* __restrict__ slabs, int c0, int n) {
+  __shared__ double s_part[kPartK * 4 * 32 * CB_SW_GROUP];
+  const int ntiles = (n + 31) / 32, ngroups = (UL.n + CB_SW_GROUP - 1) / CB_SW_GROUP;
+  const int nlay = in.nlay;
+  Carry cy;
+  cy.rs = 32; cy.ls = 14 * 32; cy.us = 0;  // (one g-point per unit in this form)
+  cy.p = slabs + ((size_t)blockIdx.x * CB_SW_GROUP + threadIdx.y) * ((size_t)nlay * 14 * 32) + threadIdx.x;
+  for (int w = blockIdx.x; w < ntiles * ngroups; w += gridDim.x) {
+    const int tile = w % ntiles, group = w / ntiles;
+    const int c = tile * 32 + threadIdx.x;
+    const int k = group * CB_SW_GROUP + threadIdx.y;
+    SwPartSmem sink;
+    sink.buf = s_part;
+    sink.pstride = (size_t)(nlay + 1) * W.ncc;
+    sink.part = W.part + (size_t)group * 4 * sink.pstride + c;
+    sink.ncc = W.ncc;
+    sink.nthreads = 32 * CB_SW_GROUP; sink.nw = CB_SW_GROUP;
+    sink.tid = threadIdx.y * 32 + threadIdx.x; sink.warp = threadIdx.y; sink.lane = threadIdx.x;
+    sink.count = 0; sink.lev_first = 0;
+    sink.valid = c < n; sink.cloudy = false; sink.stream = true;
+    if (c >= n || k >= UL.n) {
+      sink.cloudy = c < n && W.anycld[c] != 0;
+      for (int l = nlay; l >= 0; --l) sink.put((size_t)l, sink.cloudy, 0., 0., 0., 0.);
+      sink.finish();
+      continue;
+    }
+    const Unit un = UL.u[k];
+    sw_transfer_unit<1, MC, SwPartSmem, false, true>(T, sol, in, fl, W, c0, c, un.band - 16, un.g0, sink, cy);
+  }
 }
 
 __global__ void __launch_bounds__(kBlock) k_sw_mask_kiss(const __grid_constant__ In in, const __grid_constant__ Work W,
@@ -194,6 +240,10 @@ struct cb200_sw_engine {
   int cap_ncc = 0, cap_nlay = 0;
   Work W{};
   int max_chunk = 8192;
+  int slab_bps = 0;          // > 0: the slab form of the transfer kernel with this many 4-warp blocks per SM (CLIMT_B200_SW_SLAB)
+  double* d_slabs = nullptr;
+  size_t slabs_cap = 0;
+  int n_sm = 148;
   cb::HostPipe pipe;
   size_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the last host-pointer call
   bool skip_zero_inputs = true;         // CLIMT_B200_SKIP_ZERO_INPUTS=0 turns the all-zero scan of the host call off
@@ -257,6 +307,8 @@ extern "C" int cb200_sw_create(cb200_sw_engine** out, const char* table_blob, co
     e->UL_tau.n = build_units(e->UL_tau.u, CB_SW_TAU_UMAX);
     if (const char* mc = std::getenv("CLIMT_B200_MAX_CHUNK")) e->max_chunk = std::max(128, std::atoi(mc));
     if (const char* z = std::getenv("CLIMT_B200_SKIP_ZERO_INPUTS")) e->skip_zero_inputs = std::atoi(z) != 0;
+    if (const char* sb = std::getenv("CLIMT_B200_SW_SLAB")) e->slab_bps = CB_SW_UMAX == 1 ? std::max(0, std::atoi(sb)) : 0;
+    cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
     cudaMallocHost(&e->h_err, sizeof(int));
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
@@ -279,6 +331,7 @@ extern "C" void cb200_sw_destroy(cb200_sw_engine* e) {
   cudaFree(e->d_tables);
   e->pipe.destroy();
   cudaFree(e->d_mask_full);
+  cudaFree(e->d_slabs);
   if (e->h_err) cudaFreeHost(e->h_err);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -337,7 +390,20 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
   k_sw_taumol<<<dim3(gx, e->UL_tau.n, CB_SW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, sol, in, W, e->UL_tau, c0, n);
   if (e->timing) cudaEventRecord(e->evm, st);
   const dim3 gt((n + 31) / 32, (e->UL.n + CB_SW_GROUP - 1) / CB_SW_GROUP), bt(32, CB_SW_GROUP);
-  if (mc) k_sw_transfer<true><<<gt, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+  if (e->slab_bps > 0) {
+    const int nblocks = (int)std::min<size_t>((size_t)gt.x * gt.y, (size_t)e->n_sm * e->slab_bps);
+    const size_t need = (size_t)nblocks * CB_SW_GROUP * nlay * 14 * 32;
+    if (need > e->slabs_cap) {
+      cudaStreamSynchronize(st);
+      cudaFree(e->d_slabs);
+      e->d_slabs = nullptr;
+      e->slabs_cap = 0;
+      CUDA_OK(cudaMalloc(&e->d_slabs, need * sizeof(double)));
+      e->slabs_cap = need;
+    }
+    if (mc) k_sw_transfer_slab<true><<<nblocks, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, e->d_slabs, c0, n);
+    else k_sw_transfer_slab<false><<<nblocks, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, e->d_slabs, c0, n);
+  } else if (mc) k_sw_transfer<true><<<gt, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
   else k_sw_transfer<false><<<gt, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
   if (e->timing) cudaEventRecord(e->ev1, st);
   k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, e->UL, out, nlay, out_ncol, c0, n);

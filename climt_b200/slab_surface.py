@@ -117,7 +117,6 @@ def slab_surface_host(state, device=0):
     rc = L.cb200_slab_surface_run_host(device, n, stride, ctypes.byref(s), tend.ctypes.data_as(_dp), depth.ctypes.data_as(_dp))
     if rc:
         raise RuntimeError(L.cb200_global_error().decode())
-    device_state.keep_alive_on(stream, keep + [tend, depth])
     return tend, depth
 
 
