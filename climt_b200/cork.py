@@ -7,7 +7,8 @@ constructor arguments, property dictionaries, aliases, units and ``array_call`` 
 run in the CUDA engine (csrc/cork_engine.cu) behind the C ABI of include/climt_b200.h; there is no CPU
 implementation here.
 
-Not provided (raise NotImplementedError at construction): ESFT-overlap tables and ``diagnostics_level >= 1``
+ESFT-overlap tables are evaluated as additive tables on the combined g-points (expand_esft_table); ``diagnostics_level >= 1``
+returns the reference's per-band g-point averages of the kernel diagnostics (cb200_cork_set_diagnostics).  (Round 1 rejected both.)
 (per-g-point diagnostic dumps).
 """
 import ctypes
@@ -109,6 +110,20 @@ class CorkOutputs(ctypes.Structure):
 PICKET_MAX_REGIONS = 8
 
 
+class CorkDiagnostics(ctypes.Structure):
+    """cb200_cork_diagnostics (include/climt_b200.h)."""
+    _fields_ = [("level", ctypes.c_int), ("field", _dp * 10), ("weight_sum", _dp)]
+
+
+# diagnostics_level >= 1: field index in cb200_cork_diagnostics -> (component diagnostic, interface-level field?, minimum level)
+LW_DIAG = {0: ("lw_layer_transmittance", False, 1), 1: ("lw_up_per_gpoint", True, 1), 2: ("lw_down_per_gpoint", True, 1)}
+SW_DIAG = {0: ("sw_layer_diffuse_reflectance", False, 1), 1: ("sw_layer_diffuse_transmittance", False, 1),
+           2: ("sw_layer_direct_transmittance", False, 1), 3: ("sw_direct_beam_profile", True, 1),
+           4: ("sw_layer_direct_reflectance", False, 2), 5: ("sw_layer_direct_source_transmittance", False, 2),
+           6: ("sw_delta_scaled_optical_depth", False, 2), 7: ("sw_delta_scaled_ssa", False, 2),
+           8: ("sw_delta_scaled_asymmetry", False, 2), 9: ("sw_combined_albedo", True, 2)}
+
+
 class PicketCoeffs(ctypes.Structure):
     """cb200_picket_coeffs (include/climt_b200.h)."""
     _ab = ctypes.c_double * 2 * PICKET_MAX_REGIONS
@@ -206,6 +221,7 @@ def _bind(L):
     L.cb200_cork_sw_run_device.argtypes = [vp, ctypes.c_int, ctypes.c_int, _dp, pi, po, vp]
     L.cb200_cork_lw_run_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, pi, po]
     L.cb200_cork_sw_run_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, _dp, pi, po]
+    L.cb200_cork_set_diagnostics.argtypes = [vp, ctypes.POINTER(CorkDiagnostics)]
 
 
 def esft_weights(gpoint_weights, ngas):
@@ -389,12 +405,32 @@ class CorkEngine:
             setattr(pout, k, a.ctypes.data_as(_dp))
         return pin, pout, out, keep
 
-    def lw_host(self, ncol, nlev, arrays, out=None, diffusivity_factor=DIFFUSIVITY_FACTOR, bands=True):
+    def _host_diagnostics(self, which, level, ncol, nlev):
+        """diagnostics_level >= 1: numpy fields for the next host call -> {component diagnostic name: (nband, nlev[+1], ncol)}"""
+        d, fields = CorkDiagnostics(), {}
+        d.level = int(level)
+        for j, (name, iface, minlevel) in (LW_DIAG if which == "lw" else SW_DIAG).items():
+            if level >= minlevel:
+                a = np.zeros((self.nband, nlev + 1 if iface else nlev, ncol))
+                fields[name] = a
+                d.field[j] = a.ctypes.data_as(_dp)
+        if level > 0 and self.table is not None:  # `weights.sum(axis=1)` in the table's own dtype (cork/lw/component.py:342)
+            wsum = np.ascontiguousarray(np.asarray(self.table["gpoint_weights"]).sum(axis=1), dtype=np.float64)
+            d.weight_sum = wsum.ctypes.data_as(_dp)
+        if self._L.cb200_cork_set_diagnostics(self._h, ctypes.byref(d) if level > 0 else None):
+            raise RuntimeError(self._err())
+        return fields
+
+    def lw_host(self, ncol, nlev, arrays, out=None, diffusivity_factor=DIFFUSIVITY_FACTOR, bands=True, diagnostics_level=0):
+        """diagnostics_level >= 1: returns (out, {diagnostic name: (nband, nlev[+1], ncol)})"""
         pin, pout, out, keep = self._pack_host(ncol, nlev, arrays, out, "lw", bands)
+        fields = self._host_diagnostics("lw", diagnostics_level, ncol, nlev)
         rc = self._L.cb200_cork_lw_run_host(self._h, ncol, nlev, float(diffusivity_factor), ctypes.byref(pin), ctypes.byref(pout))
+        if diagnostics_level:
+            self._L.cb200_cork_set_diagnostics(self._h, None)
         if rc:
             raise (ValueError if rc == -3 else RuntimeError)(self._err())
-        return out
+        return (out, fields) if diagnostics_level else out
 
     def solar_flux(self, earth_sun_factor):
         """solar_source_per_gpoint * earth_sun_factor with numpy's dtype rules, as the reference evaluates it
@@ -403,16 +439,20 @@ class CorkEngine:
             raise ValueError("cork: this table has no solar_source_per_gpoint (not a shortwave table)")
         return np.ascontiguousarray(np.asarray(self.table["solar_source_per_gpoint"]) * float(earth_sun_factor), dtype=np.float64)
 
-    def sw_host(self, ncol, nlev, arrays, out=None, earth_sun_factor=1.0, bands=True, solar_flux=None):
-        """solar_flux: (nband, ngpt) W m-2 already scaled (picket-fence engines: mandatory); else the table's * earth_sun_factor"""
+    def sw_host(self, ncol, nlev, arrays, out=None, earth_sun_factor=1.0, bands=True, solar_flux=None, diagnostics_level=0):
+        """solar_flux: (nband, ngpt) W m-2 already scaled (picket-fence engines: mandatory); else the table's * earth_sun_factor.
+        diagnostics_level >= 1: returns (out, {diagnostic name: (nband, nlev[+1], ncol)})"""
         pin, pout, out, keep = self._pack_host(ncol, nlev, arrays, out, "sw", bands)
         sf = self.solar_flux(earth_sun_factor) if solar_flux is None else np.ascontiguousarray(solar_flux, dtype=np.float64)
         if sf.shape != (self.nband, self.ngpt):
             raise ValueError(f"solar_flux: expected shape {(self.nband, self.ngpt)}, got {sf.shape}")
+        fields = self._host_diagnostics("sw", diagnostics_level, ncol, nlev)
         rc = self._L.cb200_cork_sw_run_host(self._h, ncol, nlev, sf.ctypes.data_as(_dp), ctypes.byref(pin), ctypes.byref(pout))
+        if diagnostics_level:
+            self._L.cb200_cork_set_diagnostics(self._h, None)
         if rc:
             raise (ValueError if rc == -3 else RuntimeError)(self._err())
-        return out
+        return (out, fields) if diagnostics_level else out
 
     def _run_device(self, fn, ncol, nlev, scalar, tensors, out, stream):
         """scalar: float (lw diffusivity) or a float64 numpy (nband, ngpt) solar flux (sw)"""
@@ -476,8 +516,6 @@ class _CorkBase(TendencyComponent):
             raise ValueError(f"Unknown optics mode: {optics}")
         self._optics_mode = optics
         self._diagnostics_level = kwargs.pop("diagnostics_level", 0)
-        if self._diagnostics_level:
-            raise NotImplementedError("diagnostics_level >= 1 (per-g-point dumps) is not provided by the CUDA engine")
         if optics == "parmentier":  # cork/lw/component.py:41-44, cork/sw/component.py:32-35
             self._coefficients = load_parmentier_coefficients(coefficients)
             self._freedman_coeffs = load_freedman2014_coefficients()
@@ -576,6 +614,8 @@ class CorkLongwaveRadiation(_CorkBase):
             "longwave_optical_depth_per_band": _p(band_m, "dimensionless"),
             "longwave_transmittance_per_band": _p(band_m, "dimensionless"),
             "air_temperature_tendency_from_longwave_per_band": _p(band_m, "degK day^-1"),
+            **({"lw_layer_transmittance": _p(band_m, "dimensionless"), "lw_up_per_gpoint": _p(band_i, "W m^-2"),
+                "lw_down_per_gpoint": _p(band_i, "W m^-2")} if self._diagnostics_level >= 1 else {}),  # cork/lw/component.py:189-202
         }
 
     @property
@@ -593,7 +633,11 @@ class CorkLongwaveRadiation(_CorkBase):
         self._gas_arrays(st, nlev, arrays)
         arrays["emissivity"] = st["emissivity"].reshape(self._num_bands, ncol)
         arrays["tau_cloud"] = st["tau_cloud_lw"].reshape(nlev, ncol, self._num_bands)
-        o = self._engine.lw_host(ncol, nlev, arrays, diffusivity_factor=self._diffusivity_factor)
+        o = self._engine.lw_host(ncol, nlev, arrays, diffusivity_factor=self._diffusivity_factor,
+                                 diagnostics_level=self._diagnostics_level)
+        fields = {}
+        if self._diagnostics_level:
+            o, fields = o
         hr = o["heating_rate"].reshape(shape_T)
         diagnostics = {
             "upwelling_longwave_flux_in_air": o["up_broad"].reshape(shape_pint),
@@ -605,6 +649,8 @@ class CorkLongwaveRadiation(_CorkBase):
             "longwave_transmittance_per_band": self._band_last(o["trans_band"], shape_T),
             "air_temperature_tendency_from_longwave_per_band": self._band_last(o["hr_band"], shape_T),
         }
+        for name, a in fields.items():  # cork/lw/component.py:341-358
+            diagnostics[name] = self._band_last(a, shape_pint if a.shape[1] == nlev + 1 else shape_T)
         return {_tend_key(state): hr}, diagnostics
 
 
@@ -667,6 +713,9 @@ class CorkShortwaveRadiation(_CorkBase):
             "air_temperature_tendency_from_shortwave": _p(["mid_levels", "*"], "degK day^-1"),
             "shortwave_optical_depth_per_band": _p(band_m, "dimensionless"),
             "air_temperature_tendency_from_shortwave_per_band": _p(band_m, "degK day^-1"),
+            # cork/sw/component.py:201-216
+            **({name: _p(band_i if iface else band_m, "W m^-2" if name == "sw_direct_beam_profile" else "dimensionless")
+                for name, iface, minlevel in SW_DIAG.values() if self._diagnostics_level >= minlevel}),
         }
 
     @property
@@ -688,10 +737,12 @@ class CorkShortwaveRadiation(_CorkBase):
         o = None
         for it in range(2 if self._bond_albedo_feedback else 1):
             if it:
-                up_toa, down_toa = o["up_broad"][-1, :], o["down_broad"][-1, :]
+                oo = o[0] if isinstance(o, tuple) else o
+                up_toa, down_toa = oo["up_broad"][-1, :], oo["down_broad"][-1, :]
                 with np.errstate(divide="ignore", invalid="ignore"):
                     arrays["bond_albedo"] = np.clip(np.where(down_toa > 0, up_toa / down_toa, 0.0), 0.0, 1.0)
-            o = self._engine.sw_host(ncol, nlev, arrays, solar_flux=solar_flux, out=o)
+            o = self._engine.sw_host(ncol, nlev, arrays, solar_flux=solar_flux, out=o[0] if isinstance(o, tuple) else o,
+                                     diagnostics_level=self._diagnostics_level)
         return o
 
     def array_call(self, state):
@@ -711,7 +762,10 @@ class CorkShortwaveRadiation(_CorkBase):
         if self._optics_mode == "parmentier":
             o = self._parmentier_call(ncol, nlev, arrays, esf)
         else:
-            o = self._engine.sw_host(ncol, nlev, arrays, earth_sun_factor=esf)
+            o = self._engine.sw_host(ncol, nlev, arrays, earth_sun_factor=esf, diagnostics_level=self._diagnostics_level)
+        fields = {}
+        if self._diagnostics_level:
+            o, fields = o
         hr = o["heating_rate"].reshape(shape_T)
         diagnostics = {
             "upwelling_shortwave_flux_in_air": o["up_broad"].reshape(shape_pint),
@@ -722,6 +776,8 @@ class CorkShortwaveRadiation(_CorkBase):
             "shortwave_optical_depth_per_band": self._band_last(o["tau_band"], shape_T),
             "air_temperature_tendency_from_shortwave_per_band": self._band_last(o["hr_band"], shape_T),
         }
+        for name, a in fields.items():  # cork/sw/component.py:455-492
+            diagnostics[name] = self._band_last(a, shape_pint if a.shape[1] == nlev + 1 else shape_T)
         return {_tend_key(state): hr}, diagnostics
 
 

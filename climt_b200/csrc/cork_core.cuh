@@ -83,7 +83,16 @@ struct Out {
   double* heating;                // (nlev, ncol) K s-1
   double *up_band, *down_band;    // (nband, nlev+1, ncol) or null
   double *tau_band, *trans_band, *hr_band;  // (nband, nlev, ncol) or null (trans_band: LW only)
+  // diagnostics_level >= 1 (cork/lw/component.py:341-358, cork/sw/component.py:455-492): per-band g-point averages / sums of the
+  // kernels' per-g-point quantities, band-major like up_band; null = not wanted.  Indexed by DiagLw / DiagSw.
+  double* diag[10];
+  int diag_ncol, diag_c0;  // their column stride and the first column of the running chunk in them
 };
+// LW: weighted averages  sum_g w x / sum_g w  of the layer transmittance and of the WEIGHTED per-g-point fluxes (lw/kernels.py:103-116)
+enum DiagLw { DL_TRANS = 0, DL_UP, DL_DOWN, DL_N };
+// SW: weighted averages of the layer quantities, plain sums over g of the interface quantities (sw/kernels.py:299-394)
+enum DiagSw { DS_RDIF = 0, DS_TDIF, DS_TNOSCAT, DS_DIRECT, DS_RDIR, DS_TDIR, DS_TAU_D, DS_SSA_D, DS_G_D, DS_COMB_ALB, DS_N };
+CB_HD bool diag_sw_is_interface(int j) { return j == DS_DIRECT || j == DS_COMB_ALB; }
 
 // workspace of one column chunk (ncc columns)
 enum WsField { F_FT = 0, F_FP, F_FX, F_FC, F_AMT0 };  // + ngas amounts
@@ -94,6 +103,11 @@ struct Work {
   double* scr;    // [unit][row][lev][ncc]
   double* part;   // [unit][3][lev+1][ncc]   0 = up, 1 = down, 2 = tau (lev rows used)
   int nscr;       // scratch rows per unit
+  double* dpart;  // [unit][ndiag][lev+1][ncc] per-unit sums of the diagnostics (diagnostics_level >= 1 only)
+  int ndiag;      // DL_N | DS_N
+  int diag_level; // 0, 1, 2
+  const double* wsum;  // (nband) sum of each band's g-point weights as the caller evaluated it (the reference sums the table's own
+                       // dtype: a float32 table gives a float32 sum, cork/lw/component.py:342), or null -> summed here in float64
 };
 
 CB_HD int pack_idx(int iT, int iP, int iX, int iC) { return iT | (iP << 8) | (iX << 16) | (iC << 24); }
@@ -297,7 +311,7 @@ CB_HD void gas_tau(const Table& Tb, const double* __restrict__ ws, size_t fs, in
 // scratch rows per unit: 2U  (trans, planck source per g-point)
 // OPT = 1: picket-fence optics (U = 1; band 0 = kappa_1 with Planck share beta, band 1 = kappa_2 with 1 - beta;
 // CorkLongwaveRadiation._parmentier_optics, cork/lw/component.py:375-422) in place of the k-table and planck_fraction.
-template <int U, typename KT, int OPT = 0>
+template <int U, typename KT, int OPT = 0, bool DIAG = false>
 CB_HD void lw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W, int c0, int c, int band, int chunk, int unit) {
   const int ncol = in.ncol, nlev = in.nlev, ncc = W.ncc;
   const size_t gc = (size_t)c0 + c;
@@ -312,6 +326,7 @@ CB_HD void lw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
   const size_t pfT = (size_t)Tb.nband_pf * Tb.ngpt_pf;
   double* __restrict__ part = W.part + (size_t)unit * 3 * ps + c;
   double* __restrict__ scr = W.scr + (size_t)unit * W.nscr * fs + c;
+  double* __restrict__ dpart = DIAG ? W.dpart + (size_t)unit * DL_N * ps + c : nullptr;
   double pk_frac = 0.0, pk_c2 = 0.0, pk_R = 1.0;
   if (OPT == 1) {
     const PicketCol pc = picket_column(Tb.pk, in.T_irr[gc], in.T_int[gc], 0.0);
@@ -326,6 +341,7 @@ CB_HD void lw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
     const double em = in.emissivity[(size_t)band * ncol + gc];
     up[0] = em * (pk_frac * (K.sigma * pow(Ts, 4.0)));  // cork/lw/component.py:418-420
     part[0] = w[0] * up[0];
+    if (DIAG) dpart[DL_UP * ps] = w[0] * (w[0] * up[0]);
   } else {
     const double Ts = in.T_surf[gc];
     const Br bs = bracket(Tb.T_grid, Tb.nT, Ts);
@@ -333,14 +349,16 @@ CB_HD void lw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
     double f0[U], f1[U];
     ldk<U>(pf + bs.i * pfT, f0); ldk<U>(pf + (bs.i + 1) * pfT, f1);
     const double em = in.emissivity[(size_t)band * ncol + gc];
-    double s = 0.0;
+    double s = 0.0, sdu = 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const double frac = f0[u] * (1.0 - bs.f) + f1[u] * bs.f;
       up[u] = em * (frac * planck);
       s += w[u] * up[u];
+      if (DIAG) sdu += w[u] * (w[u] * up[u]);
     }
     part[0] = s;
+    if (DIAG) dpart[DL_UP * ps] = sdu;
   }
   // pass 1: surface -> top.  optical depth, Planck source, upward sweep
   for (int l = 0; l < nlev; ++l) {
@@ -363,7 +381,7 @@ CB_HD void lw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
       planck = K.sigma * ((Tl * Tl) * (Tl * Tl));
       ldk<U>(pf + iT * pfT, f0); ldk<U>(pf + (iT + 1) * pfT, f1);
     }
-    double su = 0.0, st = 0.0;
+    double su = 0.0, st = 0.0, sdt = 0.0, sdu = 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const double t = tau[u] + tc;
@@ -372,27 +390,32 @@ CB_HD void lw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
       up[u] = up[u] * trans + src * (1.0 - trans);
       su += w[u] * up[u];
       st += w[u] * t;
+      if (DIAG) { sdt += w[u] * trans; sdu += w[u] * (w[u] * up[u]); }
       scr[(size_t)(2 * u) * fs + (size_t)l * ncc] = trans;
       scr[(size_t)(2 * u + 1) * fs + (size_t)l * ncc] = src;
     }
     part[(size_t)(l + 1) * ncc] = su;
     part[2 * ps + (size_t)l * ncc] = st;
+    if (DIAG) { dpart[DL_TRANS * ps + (size_t)l * ncc] = sdt; dpart[DL_UP * ps + (size_t)(l + 1) * ncc] = sdu; }
   }
   // pass 2: top -> surface (lw/kernels.py:108-117)
   double dn[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) dn[u] = 0.0;
   part[ps + (size_t)nlev * ncc] = 0.0;
+  if (DIAG) dpart[DL_DOWN * ps + (size_t)nlev * ncc] = 0.0;
   for (int l = nlev - 1; l >= 0; --l) {
-    double sd = 0.0;
+    double sd = 0.0, sdd = 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const double trans = scr[(size_t)(2 * u) * fs + (size_t)l * ncc];
       const double src = scr[(size_t)(2 * u + 1) * fs + (size_t)l * ncc];
       dn[u] = dn[u] * trans + src * (1.0 - trans);
       sd += w[u] * dn[u];
+      if (DIAG) sdd += w[u] * (w[u] * dn[u]);
     }
     part[ps + (size_t)l * ncc] = sd;
+    if (DIAG) dpart[DL_DOWN * ps + (size_t)l * ncc] = sdd;
   }
 }
 
@@ -400,7 +423,7 @@ CB_HD void lw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
 // scratch rows per unit: 7U  (Rdif, Tdif, src_up -> denom, src_dn, direct beam at layer base, albedo, src)
 // OPT = 1: picket-fence optics (U = 1; three purely absorbing visible bands, kappa_v = gamma_v * kappa_R;
 // CorkShortwaveRadiation._parmentier_sw_optics, cork/sw/component.py:498-532).
-template <int U, typename KT, int OPT = 0>
+template <int U, typename KT, int OPT = 0, bool DIAG = false>
 CB_HD void sw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W, int c0, int c, int band, int chunk, int unit) {
   const int ncol = in.ncol, nlev = in.nlev, ncc = W.ncc;
   const size_t gc = (size_t)c0 + c;
@@ -409,16 +432,20 @@ CB_HD void sw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
   const int g0 = chunk * U;
   double* __restrict__ part = W.part + (size_t)unit * 3 * ps + c;
   double* __restrict__ scr = W.scr + (size_t)unit * W.nscr * fs + c;
+  double* __restrict__ dpart = DIAG ? W.dpart + (size_t)unit * DS_N * ps + c : nullptr;
+  const bool diag2 = DIAG && W.diag_level >= 2;
   const double mu0 = cos(in.zenith[gc]);
   const bool night = mu0 <= 1e-4;  // sw/kernels.py:218-219: no contribution
   const double alb_s = in.albedo[gc];
-  double w[U], scale[U];
+  double w[U], scale[U], sol[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     w[u] = CB_LDG(Tb.weights + band * Tb.ngpt + g0 + u);
+    sol[u] = CB_LDG(in.solar_flux + band * Tb.ngpt + g0 + u);
     // scale = solar_flux * mu0 * w (sw/kernels.py:257)
-    scale[u] = CB_LDG(in.solar_flux + band * Tb.ngpt + g0 + u) * mu0 * w[u];
+    scale[u] = sol[u] * mu0 * w[u];
   }
+  (void)sol;
   const double ray = Tb.rayleigh ? CB_LDG(Tb.rayleigh + band) : 0.0;
   double pk_gv = 0.0;
   if (OPT == 1) pk_gv = picket_column(Tb.pk, in.T_irr[gc], in.T_int[gc], in.bond_albedo ? in.bond_albedo[gc] : 0.0).gv[band];
@@ -428,6 +455,12 @@ CB_HD void sw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
   double dir[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) dir[u] = 1.0;
+  if (DIAG) {  // direct beam at the top interface: unit flux x solar_flux x mu0 (sw/kernels.py:355); zero at night (:318-319)
+    double sdir = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) sdir += night ? 0.0 : (1.0 * sol[u]) * mu0;
+    dpart[DS_DIRECT * ps + (size_t)nlev * ncc] = sdir;
+  }
   for (int l = nlev - 1; l >= 0; --l) {
     const double* __restrict__ ws = W.ws + (size_t)l * ncc + c;
     const int idx = W.idx[(size_t)l * ncc + c];
@@ -445,6 +478,8 @@ CB_HD void sw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
       tau_c = in.tau_cloud[oc]; ssa_c = in.ssa_cloud[oc]; g_c = in.g_cloud[oc];
     }
     double st = 0.0;
+    double dsum[DS_N];
+    if (DIAG) for (int j = 0; j < DS_N; ++j) dsum[j] = 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       // gas + Rayleigh (sw/component.py:356-368), then gas + cloud mixing (:388-412)
@@ -495,11 +530,25 @@ CB_HD void sw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
       dir[u] = Tnoscat * above;
       double* __restrict__ s = scr + (size_t)(7 * u) * fs + (size_t)l * ncc;
       s[0 * fs] = Rdif; s[1 * fs] = Tdif; s[2 * fs] = Rdir * above; s[3 * fs] = Tdir * above; s[4 * fs] = dir[u];
+      if (DIAG) {
+        dsum[DS_RDIF] += w[u] * Rdif; dsum[DS_TDIF] += w[u] * Tdif; dsum[DS_TNOSCAT] += w[u] * Tnoscat;
+        dsum[DS_DIRECT] += (dir[u] * sol[u]) * mu0;
+        if (diag2) {
+          dsum[DS_RDIR] += w[u] * Rdir; dsum[DS_TDIR] += w[u] * Tdir;
+          dsum[DS_TAU_D] += w[u] * tau_s; dsum[DS_SSA_D] += w[u] * w0; dsum[DS_G_D] += w[u] * gs;
+        }
+      }
     }
     part[2 * ps + (size_t)l * ncc] = st;
+    if (DIAG) {  // (night: every sum is still zero, as in the reference, whose column loop `continue`s)
+      for (int j = 0; j < DS_COMB_ALB; ++j) dpart[(size_t)j * ps + (size_t)l * ncc] = dsum[j];
+    }
   }
   if (night) {
-    for (int l = 0; l <= nlev; ++l) { part[(size_t)l * ncc] = 0.0; part[ps + (size_t)l * ncc] = 0.0; }
+    for (int l = 0; l <= nlev; ++l) {
+      part[(size_t)l * ncc] = 0.0; part[ps + (size_t)l * ncc] = 0.0;
+      if (DIAG) dpart[DS_COMB_ALB * ps + (size_t)l * ncc] = 0.0;
+    }
     return;
   }
   // pass 2: surface -> top.  combined albedo and source below each interface (_adding, sw/kernels.py:150-164)
@@ -507,16 +556,25 @@ CB_HD void sw_unit(const Table& Tb, const Consts& K, const In& in, const Work& W
 #pragma unroll
   for (int u = 0; u < U; ++u) { alb[u] = alb_s; src[u] = dir[u] * alb_s; }
   for (int l = 0; l < nlev; ++l) {
+    double salb = 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       double* __restrict__ s = scr + (size_t)(7 * u) * fs + (size_t)l * ncc;
       const double Rdif = s[0 * fs], Tdif = s[1 * fs], src_up = s[2 * fs], src_dn = s[3 * fs];
       const double denom = frcp(1.0 - Rdif * alb[u]);
       s[2 * fs] = denom; s[5 * fs] = alb[u]; s[6 * fs] = src[u];
+      if (DIAG) salb += alb[u];  // combined albedo below interface l (sw/kernels.py:360-367: the same recurrence)
       const double a1 = Rdif + Tdif * Tdif * alb[u] * denom;
       const double s1 = src_up + Tdif * denom * (src[u] + alb[u] * src_dn);
       alb[u] = a1; src[u] = s1;
     }
+    if (DIAG) dpart[DS_COMB_ALB * ps + (size_t)l * ncc] = diag2 ? salb : 0.0;
+  }
+  if (DIAG) {
+    double salb = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) salb += alb[u];
+    dpart[DS_COMB_ALB * ps + (size_t)nlev * ncc] = diag2 ? salb : 0.0;
   }
   // pass 3: top -> surface.  diffuse fluxes (sw/kernels.py:170-186) and the weighted band sums (:257-260)
   double fdn[U];
@@ -571,6 +629,29 @@ CB_HD void reduce_level(const Table& Tb, const Work& W, int nlev, int ncol, int 
   }
   out.up_broad[(size_t)lev * ncol + gc] = ub;
   out.down_broad[(size_t)lev * ncol + gc] = db;
+}
+
+// diagnostics_level >= 1: the per-band g-point averages (weighted, / sum of the band's weights) or sums of the per-unit sums
+// (cork/lw/component.py:341-358; cork/sw/component.py:463-492)
+CB_HD void reduce_diag_level(const Table& Tb, const Work& W, int nlev, int c, int lev, bool lw, const Out& out) {
+  const int ncc = W.ncc;
+  const size_t ps = (size_t)(nlev + 1) * ncc;
+  const size_t gc = (size_t)out.diag_c0 + c;
+  for (int b = 0; b < Tb.nband; ++b) {
+    double wsum = 0.0;
+    if (W.wsum) wsum = W.wsum[b];
+    else for (int g = 0; g < Tb.ngpt; ++g) wsum += Tb.weights[b * Tb.ngpt + g];
+    for (int j = 0; j < W.ndiag; ++j) {
+      if (!out.diag[j]) continue;
+      const bool iface = lw ? (j != DL_TRANS) : diag_sw_is_interface(j);
+      if (!iface && lev == nlev) continue;
+      double v = 0.0;
+      for (int ch = 0; ch < Tb.nchunk; ++ch)
+        v += W.dpart[((size_t)(b * Tb.nchunk + ch) * W.ndiag + j) * ps + (size_t)lev * ncc + c];
+      if (lw || !iface) v = v / wsum;
+      out.diag[j][((size_t)b * (iface ? nlev + 1 : nlev) + lev) * out.diag_ncol + gc] = v;
+    }
+  }
 }
 
 // heating rates of one layer: broadband (K s-1) and per band (K day-1), transmittance per band

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kBlock) k_cork_prep(const __grid_constant__ Ta
 }
 
 // One block = 128 adjacent columns x one unit (U g-points of one band)
-template <int U, bool LW, typename KT, int OPT = 0>
+template <int U, bool LW, typename KT, int OPT = 0, bool DIAG = false>
 __global__ void __launch_bounds__(kBlock, CB_CORK_MIN_BLOCKS)
     k_cork_units(const __grid_constant__ Table Tb, const Consts K, const __grid_constant__ In in, const __grid_constant__ Work W,
                  int c0, int n) {
@@ -39,14 +39,20 @@ __global__ void __launch_bounds__(kBlock, CB_CORK_MIN_BLOCKS)
   if (c >= n) return;
   const int unit = blockIdx.y;
   const int band = unit / Tb.nchunk, chunk = unit - band * Tb.nchunk;
-  if (LW) lw_unit<U, KT, OPT>(Tb, K, in, W, c0, c, band, chunk, unit);
-  else sw_unit<U, KT, OPT>(Tb, K, in, W, c0, c, band, chunk, unit);
+  if (LW) lw_unit<U, KT, OPT, DIAG>(Tb, K, in, W, c0, c, band, chunk, unit);
+  else sw_unit<U, KT, OPT, DIAG>(Tb, K, in, W, c0, c, band, chunk, unit);
 }
 
 __global__ void __launch_bounds__(kBlock) k_cork_reduce(const __grid_constant__ Table Tb, const __grid_constant__ Work W,
                                                         const __grid_constant__ Out out, int nlev, int ncol, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < n) reduce_level(Tb, W, nlev, ncol, c0, c, blockIdx.y, out);
+}
+// diagnostics_level >= 1 only
+__global__ void __launch_bounds__(kBlock) k_cork_reduce_diag(const __grid_constant__ Table Tb, const __grid_constant__ Work W,
+                                                             const __grid_constant__ Out out, int nlev, int n, int lw) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) reduce_diag_level(Tb, W, nlev, c, blockIdx.y, lw != 0, out);
 }
 
 __global__ void __launch_bounds__(kBlock) k_cork_heat(const __grid_constant__ Table Tb, const Consts K, const __grid_constant__ In in,
@@ -83,11 +89,34 @@ struct cb200_cork_engine {
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double unit_ms = 0.0;
+  cb200_cork_diagnostics diag{};  // level 0 = off (cb200_cork_set_diagnostics)
+  double* d_wsum = nullptr;      // (nband) the caller's weight sums, or null
+  double* d_diag = nullptr;      // host calls: the diagnostics of the whole call, copied back at its end
+  size_t d_diag_cap = 0;
+  size_t dpart_cap = 0;
 
   void free_work() {
-    cudaFree(W.ws); cudaFree(W.idx); cudaFree(W.scr); cudaFree(W.part);
+    cudaFree(W.ws); cudaFree(W.idx); cudaFree(W.scr); cudaFree(W.part); cudaFree(W.dpart);
     W = Work{};
     cap_ncc = cap_nlev = 0;
+    dpart_cap = 0;
+  }
+  // diagnostics_level >= 1: the per-unit sums of the diagnostics (sized like `part`)
+  int ensure_dpart(bool lw, int ncc, int nlev) {
+    cb200_cork_engine* e = this;
+    W.ndiag = lw ? (int)DL_N : (int)DS_N;
+    W.diag_level = diag.level;
+    W.wsum = diag.weight_sum ? d_wsum : nullptr;
+    const size_t need = (size_t)nunits * W.ndiag * (nlev + 1) * ncc;
+    if (need > dpart_cap) {
+      cudaDeviceSynchronize();
+      cudaFree(W.dpart);
+      W.dpart = nullptr;
+      dpart_cap = 0;
+      CUDA_OK(cudaMalloc(&W.dpart, need * sizeof(double)));
+      dpart_cap = need;
+    }
+    return 0;
   }
   int ensure_work(int ncc, int nlev) {
     cb200_cork_engine* e = this;
@@ -298,6 +327,8 @@ extern "C" void cb200_cork_destroy(cb200_cork_engine* e) {
   e->pipe.destroy();
   cudaFree(e->d_blob);
   cudaFree(e->d_solar);
+  cudaFree(e->d_wsum);
+  cudaFree(e->d_diag);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   delete e;
@@ -322,7 +353,20 @@ In make_in(int ncol, int nlev, const cb200_cork_inputs* p, const double* d_solar
 }
 
 Out make_out(const cb200_cork_outputs* p) {
-  return Out{p->up_broad, p->down_broad, p->heating_rate, p->up_band, p->down_band, p->tau_band, p->trans_band, p->hr_band};
+  Out o{};
+  o.up_broad = p->up_broad; o.down_broad = p->down_broad; o.heating = p->heating_rate; o.up_band = p->up_band;
+  o.down_band = p->down_band; o.tau_band = p->tau_band; o.trans_band = p->trans_band; o.hr_band = p->hr_band;
+  return o;
+}
+// the diagnostics fields a level provides: LW 3 at level >= 1; SW 4 at level 1, all 10 at level >= 2 (sw/kernels.py:381-394)
+bool diag_field_on(bool lw, int level, int j) {
+  if (level <= 0) return false;
+  if (lw) return j < (int)DL_N;
+  return level >= 2 ? j < (int)DS_N : j <= (int)DS_DIRECT;
+}
+size_t diag_rows(bool lw, int j, int nband, int nlev) {
+  const bool iface = lw ? (j != (int)DL_TRANS) : diag_sw_is_interface(j);
+  return (size_t)nband * (iface ? nlev + 1 : nlev);
 }
 
 int validate(cb200_cork_engine* e, bool lw, int ncol, int nlev, const cb200_cork_inputs* in, const cb200_cork_outputs* out) {
@@ -351,22 +395,29 @@ int launch_chunk(cb200_cork_engine* e, bool lw, const Consts& K, const In& in_, 
   k_cork_prep<<<dim3(gx, nlev), kBlock, 0, st>>>(e->T, K, in, W, c0, n);
   if (e->timing) cudaEventRecord(e->ev0, st);
   const dim3 grid(gx, e->nunits);
+  const bool dg = W.diag_level > 0;
+#define CB_LAUNCH4(U, D)                                                                                         \
+    if (lw && !e->k_f64) k_cork_units<U, true, float, 0, D><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);     \
+    else if (lw) k_cork_units<U, true, double, 0, D><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);            \
+    else if (!e->k_f64) k_cork_units<U, false, float, 0, D><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);     \
+    else k_cork_units<U, false, double, 0, D><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);
 #define CB_LAUNCH(U)                                                                                          \
   case U:                                                                                                     \
-    if (lw && !e->k_f64) k_cork_units<U, true, float><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);        \
-    else if (lw) k_cork_units<U, true, double><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);               \
-    else if (!e->k_f64) k_cork_units<U, false, float><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);        \
-    else k_cork_units<U, false, double><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);                      \
+    if (dg) { CB_LAUNCH4(U, true) } else { CB_LAUNCH4(U, false) }                                             \
     break;
   if (e->T.optics == 1) {
-    if (lw) k_cork_units<1, true, float, 1><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);
+    if (lw && dg) k_cork_units<1, true, float, 1, true><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);
+    else if (lw) k_cork_units<1, true, float, 1><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);
+    else if (dg) k_cork_units<1, false, float, 1, true><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);
     else k_cork_units<1, false, float, 1><<<grid, kBlock, 0, st>>>(e->T, K, in, W, c0, n);
   } else switch (e->T.U) {
     CB_LAUNCH(1) CB_LAUNCH(2) CB_LAUNCH(4) CB_LAUNCH(8)
   }
 #undef CB_LAUNCH
+#undef CB_LAUNCH4
   if (e->timing) cudaEventRecord(e->ev1, st);
   k_cork_reduce<<<dim3(gx, nlev + 1), kBlock, 0, st>>>(e->T, W, out, nlev, out_ncol, c0, n);
+  if (dg) { k_cork_reduce_diag<<<dim3(gx, nlev + 1), kBlock, 0, st>>>(e->T, W, out, nlev, n, lw ? 1 : 0); e->launches += 1; }
   k_cork_heat<<<dim3(gx, nlev), kBlock, 0, st>>>(e->T, K, in, out, c0, n, lw ? 1 : 0);
   e->launches += 4;
   if (e->timing) {
@@ -402,11 +453,19 @@ int run_device(cb200_cork_engine* e, bool lw, int ncol, int nlev, double scalar,
   Consts K = e->K;
   if (lw) K.D = scalar;
   const In in = make_in(ncol, nlev, pin, e->d_solar);
-  const Out out = make_out(pout);
+  Out out = make_out(pout);
+  W.diag_level = 0;
+  if (e->diag.level > 0) {  // device pointers of the caller
+    if (e->ensure_dpart(lw, chunk, nlev)) return -1;
+    W.dpart = e->W.dpart; W.ndiag = e->W.ndiag; W.diag_level = e->W.diag_level; W.wsum = e->W.wsum;
+    for (int j = 0; j < W.ndiag; ++j) out.diag[j] = diag_field_on(lw, e->diag.level, j) ? e->diag.field[j] : nullptr;
+    out.diag_ncol = ncol;
+  }
   e->launches = 0;
   e->unit_ms = 0.0;
   for (int c0 = 0; c0 < ncol; c0 += chunk) {
     const int n = (ncol - c0) < chunk ? (ncol - c0) : chunk;
+    out.diag_c0 = c0;
     if (launch_chunk(e, lw, K, in, out, W, c0, n, ncol, st)) return -1;
   }
   CUDA_OK(cudaGetLastError());
@@ -448,6 +507,27 @@ int run_host(cb200_cork_engine* e, bool lw, int ncol, int nlev, double scalar, c
   Work W = e->W;
   W.ncc = wchunk;
   W.nscr = lw ? 2 * e->T.U : 7 * e->T.U;
+  W.diag_level = 0;
+  // diagnostics_level >= 1: the fields of the whole call are kept on the device and copied back once the chunks are done (a
+  // debugging mode -- it does not go through the chunk pipeline)
+  double* ddiag[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (e->diag.level > 0) {
+    if (e->ensure_dpart(lw, wchunk, nlev)) return -1;
+    W.dpart = e->W.dpart; W.ndiag = e->W.ndiag; W.diag_level = e->W.diag_level; W.wsum = e->W.wsum;
+    size_t tot = 0;
+    for (int j = 0; j < W.ndiag; ++j)
+      if (diag_field_on(lw, e->diag.level, j) && e->diag.field[j]) tot += diag_rows(lw, j, nb, L) * (size_t)ncol;
+    if (tot > e->d_diag_cap) {
+      cudaFree(e->d_diag);
+      e->d_diag = nullptr;
+      e->d_diag_cap = 0;
+      CUDA_OK(cudaMalloc(&e->d_diag, tot * sizeof(double)));
+      e->d_diag_cap = tot;
+    }
+    size_t off = 0;
+    for (int j = 0; j < W.ndiag; ++j)
+      if (diag_field_on(lw, e->diag.level, j) && e->diag.field[j]) { ddiag[j] = e->d_diag + off; off += diag_rows(lw, j, nb, L) * (size_t)ncol; }
+  }
   Consts K = e->K;
   if (lw) K.D = scalar;
   e->launches = 0;
@@ -477,7 +557,9 @@ int run_host(cb200_cork_engine* e, bool lw, int ncol, int nlev, double scalar, c
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.in_done[s], 0));
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.out_done[s], 0));
     const In in = make_in(n, nlev, &din, e->d_solar);
-    const Out out = make_out(&dout);
+    Out out = make_out(&dout);
+    for (int j = 0; j < 10; ++j) out.diag[j] = ddiag[j];
+    out.diag_ncol = ncol; out.diag_c0 = c0;
     if (launch_chunk(e, lw, K, in, out, W, 0, n, n, P.s_cmp)) return -1;
     CUDA_OK(cudaEventRecord(P.cmp_done[s], P.s_cmp));
     CUDA_OK(cudaStreamWaitEvent(P.s_out, P.cmp_done[s], 0));
@@ -486,11 +568,27 @@ int run_host(cb200_cork_engine* e, bool lw, int ncol, int nlev, double scalar, c
     CUDA_OK(cudaEventRecord(P.out_done[s], P.s_out));
   }
   CUDA_OK(cudaStreamSynchronize(P.s_out));
+  if (e->diag.level > 0) {
+    CUDA_OK(cudaStreamSynchronize(P.s_cmp));
+    for (int j = 0; j < W.ndiag; ++j)
+      if (ddiag[j]) CUDA_OK(cudaMemcpy(e->diag.field[j], ddiag[j], diag_rows(lw, j, nb, L) * (size_t)ncol * sizeof(double), cudaMemcpyDeviceToHost));
+  }
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 }  // namespace
+
+extern "C" int cb200_cork_set_diagnostics(cb200_cork_engine* e, const cb200_cork_diagnostics* d) {
+  if (!d || d->level <= 0) { e->diag = cb200_cork_diagnostics{}; return 0; }
+  e->diag = *d;
+  if (d->weight_sum) {
+    CUDA_OK(cudaSetDevice(e->device));
+    if (!e->d_wsum) CUDA_OK(cudaMalloc(&e->d_wsum, sizeof(double) * e->T.nband));
+    CUDA_OK(cudaMemcpy(e->d_wsum, d->weight_sum, sizeof(double) * e->T.nband, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
 
 static_assert(sizeof(cb200_cork_inputs) == 16 * sizeof(double*), "cb200_cork_inputs layout");
 static_assert(sizeof(cb200_cork_outputs) == 8 * sizeof(double*), "cb200_cork_outputs layout");

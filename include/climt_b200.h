@@ -291,6 +291,23 @@ const char* cb200_cork_last_error(cb200_cork_engine* e);
 int cb200_cork_last_launches(cb200_cork_engine* e);
 int cb200_cork_enable_timing(cb200_cork_engine* e, int on);
 double cb200_cork_last_unit_kernel_ms(cb200_cork_engine* e);
+/* diagnostics_level >= 1 of the reference constructors (cork/lw/component.py:63,189-202,341-358; cork/sw/component.py:455-492;
+ * kernels: lw/kernels.py:103-116, sw/kernels.py:299-394): per-band g-point averages (weighted by the g-point weights, divided by
+ * their sum) of the layer quantities and of the longwave per-g-point fluxes, plain sums over g of the shortwave interface
+ * quantities -- what the components hand back after reducing the kernels' (nband, ngpt, ...) dumps.  Band-major like up_band:
+ * layer fields (nband, nlev, ncol), interface fields (nband, nlev+1, ncol).  The pointers are DEVICE pointers for the *_run_device
+ * calls and HOST pointers for the *_run_host calls that follow; NULL fields are skipped.  level 0 / NULL switches it off.
+ *   longwave  field[0] layer transmittance, [1] weighted upward flux per g-point (interface), [2] downward (interface)
+ *   shortwave field[0] Rdif, [1] Tdif, [2] Tnoscat, [3] direct beam flux (interface)                        -- level 1
+ *             field[4] Rdir, [5] Tdir, [6] tau_delta, [7] ssa_delta, [8] g_delta, [9] combined albedo (interface) -- level 2 */
+typedef struct cb200_cork_diagnostics {
+  int level;
+  double* field[10];
+  const double* weight_sum; /* HOST (nband): the sum of each band's g-point weights as the caller evaluates `weights.sum(axis=1)`
+                             * (cork/lw/component.py:342) -- in the table's own dtype, so a float32 table divides by a float32 sum;
+                             * NULL = summed by the engine in float64.  Read at the set call. */
+} cb200_cork_diagnostics;
+int cb200_cork_set_diagnostics(cb200_cork_engine* e, const cb200_cork_diagnostics* d);
 /* Device-pointer calls, asynchronous on `stream`.  diffusivity_factor: D in trans = exp(-D tau) (lw/kernels.py:6). */
 int cb200_cork_lw_run_device(cb200_cork_engine* e, int ncol, int nlev, double diffusivity_factor, const cb200_cork_inputs* in,
                              const cb200_cork_outputs* out, void* stream);

@@ -188,10 +188,13 @@ def cork_solar_flux(table, earth_sun_factor):
     return np.ascontiguousarray(np.asarray(table["solar_source_per_gpoint"]) * float(earth_sun_factor), dtype=np.float64)
 
 
-def run_cork_emul(table, which, arrays, scalar, umax=4):
-    """The CUDA engine's per-thread code, compiled for the host.  scalar = D (lw) or earth_sun_factor (sw)."""
+def run_cork_emul(table, which, arrays, scalar, umax=4, diagnostics_level=0):
+    """The CUDA engine's per-thread code, compiled for the host.  scalar = D (lw) or earth_sun_factor (sw).
+    diagnostics_level >= 1: returns (out, {component diagnostic name: (nband, nlev[+1], ncol)})"""
     from climt_b200 import cork
     lib = cork_emul_lib()
+    if cork.is_esft(table):
+        table = cork.expand_esft_table(table)
     ct, keep = cork.make_ctable(table)
     nlev, ncol = arrays["T"].shape
     nb = ct.nband
@@ -209,6 +212,21 @@ def run_cork_emul(table, which, arrays, scalar, umax=4):
     outp = (_dp * 8)(*[out[k].ctypes.data_as(_dp) for k in cork.CORK_OUT])
     scal = np.array([CORK_G, CORK_CPD, CORK_SIGMA, scalar if which == "lw" else 1.66])
     solar = cork_solar_flux(table, scalar) if which == "sw" else np.zeros(1)
+    if diagnostics_level:
+        fields, ptrs = {}, [None] * 10
+        for j, (name, iface, minlevel) in (cork.LW_DIAG if which == "lw" else cork.SW_DIAG).items():
+            if diagnostics_level >= minlevel:
+                fields[name] = np.full((nb, nlev + 1 if iface else nlev, ncol), np.nan)
+                ptrs[j] = fields[name].ctypes.data_as(_dp)
+        diagp = (_dp * 10)(*ptrs)
+        wsum = np.ascontiguousarray(np.asarray(table["gpoint_weights"]).sum(axis=1), dtype=np.float64)
+        lib.emul_cork_run_diag.argtypes = [ctypes.POINTER(cork.CorkTable), ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_int, ctypes.c_int,
+                                           ctypes.POINTER(_dp), ctypes.POINTER(_dp), ctypes.c_int, ctypes.POINTER(_dp), _dp]
+        rc = lib.emul_cork_run_diag(ctypes.byref(ct), 1 if which == "lw" else 0, umax, scal.ctypes.data_as(_dp), solar.ctypes.data_as(_dp),
+                                    ncol, nlev, ctypes.cast(inp, ctypes.POINTER(_dp)), ctypes.cast(outp, ctypes.POINTER(_dp)),
+                                    int(diagnostics_level), ctypes.cast(diagp, ctypes.POINTER(_dp)), wsum.ctypes.data_as(_dp))
+        assert rc == 0
+        return out, fields
     lib.emul_cork_run.argtypes = [ctypes.POINTER(cork.CorkTable), ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_int, ctypes.c_int,
                                   ctypes.POINTER(_dp), ctypes.POINTER(_dp)]
     rc = lib.emul_cork_run(ctypes.byref(ct), 1 if which == "lw" else 0, umax, scal.ctypes.data_as(_dp), solar.ctypes.data_as(_dp), ncol, nlev,

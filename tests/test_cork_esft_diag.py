@@ -84,6 +84,42 @@ def test_oracle_on_the_expanded_table_matches_the_reference_esft_path(gold, tabl
         np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12 * float(np.abs(ref).max()), err_msg=f"{case} sw {name}")
 
 
+def _engine_arrays(table, s, which):
+    """what the components hand to the engine (cork.py _gas_arrays; cork/lw/component.py:243-287)"""
+    names, has_h2o, has_co2, fully, bg = cork.table_flags(table)
+    a = H.cork_arrays(dict(s, q=s["h2o"]), which)
+    a.pop("q_h2o"); a.pop("co2_vmr", None)
+    if fully:
+        return a
+    if bg:
+        a["q_h2o"] = s["h2o"]
+        if has_co2 and which == "lw":
+            a["co2_vmr"] = s["co2"]
+        return a
+    a["gas_q"] = np.stack([s[g] if g == "h2o" else s[g] * (cork.MOLAR_MASS.get(g, cork.MOLAR_MASS_DRY_AIR) / cork.MOLAR_MASS_DRY_AIR)
+                           for g in names])
+    return a
+
+
+@pytest.mark.parametrize("case,lwt,swt", [("esft2", None, None), ("esft3", None, None), ("diag_earth", "earth_low_res_lw", "earth_low_res_sw")])
+def test_kernel_code_diagnostics_match_the_reference(gold, tables, case, lwt, swt):
+    """The engine's per-thread code (host emulation, NaN-poisoned diagnostics buffers) at diagnostics_level 2 against the
+    reference components' extra diagnostics."""
+    s = _inputs(gold, case)
+    for which, tname in (("lw", lwt), ("sw", swt)):
+        table = cork.load_k_table(tname) if tname else tables(f"{case}_{which}")
+        esf = float(s["earth_sun_factor"].reshape(-1)[0])
+        out, fields = H.run_cork_emul(table, which, _engine_arrays(table, s, which), 1.66 if which == "lw" else esf, diagnostics_level=2)
+        pre = f"{case}/{which}2/"
+        fscale = float(np.abs(gold[pre + ("upwelling_longwave_flux_in_air" if which == "lw" else "downwelling_shortwave_flux_in_air")]).max())
+        assert fields and all(np.isfinite(v).all() for v in fields.values())
+        for name, got in fields.items():
+            ref = gold[pre + name]
+            got = np.moveaxis(got, 0, -1)
+            atol = RTOL * fscale if ("per_gpoint" in name or "direct_beam" in name) else 1e-13
+            np.testing.assert_allclose(got, ref, rtol=RTOL, atol=atol, err_msg=f"{case} {which} {name}")
+
+
 def _compare_component(gold, case, which, level, comp, s):
     tend, diag = comp.array_call(dict(s))
     pre = f"{case}/{which}{level}/"

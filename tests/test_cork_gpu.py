@@ -149,8 +149,9 @@ def test_components_through_state_dicts():
     np.testing.assert_allclose(diag["downwelling_shortwave_flux_in_air"].values.reshape(nlev + 1, ncol), GOLD["cloudy/sw/down_broad"], rtol=RTOL, atol=1e-9)
     with pytest.raises(ValueError):
         cork.CorkLongwaveRadiation(optics="line_by_line")   # cork/lw/component.py:60-61
-    with pytest.raises(NotImplementedError):
-        cork.CorkLongwaveRadiation(optics="correlated_k", table="earth_low_res_lw", diagnostics_level=1)
+    # diagnostics_level >= 1 adds the reference's extra diagnostics (cork/lw/component.py:189-202); values: tests/test_cork_esft_diag.py
+    lw1 = cork.CorkLongwaveRadiation(optics="correlated_k", table="earth_low_res_lw", diagnostics_level=1)
+    assert {"lw_layer_transmittance", "lw_up_per_gpoint", "lw_down_per_gpoint"} <= set(lw1.diagnostic_properties)
 
 
 def test_grey_limit_matches_gray_engine():
