@@ -160,6 +160,20 @@ inline double ld_policy(const double* p, unsigned long long) { return *p; }
 #endif
 
 // Fortran real->integer assignment / int(): truncation toward zero.
+// Slot of the exp / tau-transition tables, int(tblint * x / (bpade + x) + 0.5) (rrtmg_lw_rtrn.f90:357-360, rrtmg_sw_reftra.f90:
+// 208-211), WITHOUT the IEEE division (a ~35-instruction subroutine on the device, and the longest dependent chain of a cell):
+// fdiv's quotient is within 1 ulp of the correctly rounded one, so the truncated index can differ only when the argument of the
+// truncation lies within ~1e-12 of an integer -- those (one in ~1e9) take the IEEE division.  Same slot as the reference, always.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ int tbl_slot(double x, double bpade, double tblint) {
+  const double v = __dadd_rn(__dmul_rn(tblint, fdiv(x, bpade + x)), 0.5);
+  if (fabs(v - rint(v)) < 1.e-9) return (int)__dadd_rn(__dmul_rn(tblint, x / (bpade + x)), 0.5);
+  return (int)v;
+}
+#else
+inline int tbl_slot(double x, double bpade, double tblint) { return (int)((tblint * (x / (bpade + x))) + 0.5); }
+#endif
+
 CB_HD int f2i(double x) { return (int)x; }
 CB_HD int imin(int a, int b) { return a < b ? a : b; }
 CB_HD int imax(int a, int b) { return a > b ? a : b; }

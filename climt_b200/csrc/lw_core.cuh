@@ -1214,8 +1214,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
           const double odepth_rec = rec_6 * odepth;
           gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
           odtot = odepth + odcld;
-          const double tblind = odtot / (bpade + odtot);
-          const int ittot = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
+          const int ittot = tbl_slot(odtot, bpade, tblint);
           const Row<2> ett = ldrow<2>(et_tbl + 2 * ittot);
           const double tfactot = ett[1];
           bbdtot = plfrac * (blay + tfactot * dplankdn);
@@ -1224,16 +1223,14 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
           bbugas = plfrac * (blay + dplankup * odepth_rec);
           bbutot = plfrac * (blay + tfactot * dplankup);
         } else {
-          double tblind = odepth / (bpade + odepth);
-          const int itgas = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
+          const int itgas = tbl_slot(odepth, bpade, tblint);
           odepth = CB_LDG(tau_tbl + itgas);
           const Row<2> etg = ldrow<2>(et_tbl + 2 * itgas);
           atrans = 1. - etg[0];
           const double tfacgas = etg[1];
           gassrc = atrans * plfrac * (blay + tfacgas * dplankdn);
           odtot = odepth + odcld;
-          tblind = odtot / (bpade + odtot);
-          const int ittot = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
+          const int ittot = tbl_slot(odtot, bpade, tblint);
           const Row<2> ett = ldrow<2>(et_tbl + 2 * ittot);
           const double tfactot = ett[1];
           bbdtot = plfrac * (blay + tfactot * dplankdn);
@@ -1272,8 +1269,7 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
           bbd = plfrac * (blay + dplankdn * odepth);
           bbugas = plfrac * (blay + dplankup * odepth);
         } else {
-          const double tblind = odepth / (bpade + odepth);
-          const int itr = f2i(CB_MULADD_2R(tblint, tblind, 0.5));
+          const int itr = tbl_slot(odepth, bpade, tblint);
           const Row<2> et = ldrow<2>(et_tbl + 2 * itr);
           const double transc = et[0];
           atrans = 1. - transc;
@@ -1421,6 +1417,258 @@ CB_HD void lw_transfer_unit(const Tables& T, const In& in, const Work& W, int c0
     sink.put_up((size_t)lev, cloudy_col, s * wband, sc * wband, DRV, sd * wband, sdc * wband);
   }
   sink.end_sweep();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column-tile form of the transfer (lw_engine.cu: k_lw_tile; host emulation: tests/emul/lw_emul.cpp).
+// The recurrence over the levels is cheap and strictly serial; what costs time in lw_transfer_unit is everything around it, which
+// does NOT depend on the recurrence: the optical-depth -> transmittance / Planck source conversion of every (layer, column) cell.
+// The tile form separates the two:
+//   lw_tile_cell    one (layer, column) cell of one g-point: the layer's rows -- any thread of the block can evaluate any cell, so
+//                   the cells of a tile of TW adjacent columns are spread over all producer warps, their rows parked in SHARED memory;
+//   lw_tile_sweeps  the down sweep, surface and up sweep of one radiance stream of one column over those rows, adding the
+//                   band-weighted radiances of the g-point to per-level sums that also live in shared memory.
+// Nothing the two sweeps exchange reaches HBM; the sums over the g-points of a band group are written once per tile.
+// Same physics as lw_transfer_unit<U, MC, MR = false, DRV = false> with the per-level update brought to ONE dependent operation:
+//   clear layer   rad + (bb - rad) atrans                                  = rad (1 - atrans) + bb atrans       (rtrn.f90:408, 517)
+//   cloudy layer  rad - rad (atrans + efclfrac (1 - atrans)) + gassrc + cldfrac (bbtot atot - gassrc)            (rtrn.f90:386-393)
+//                                                                          = rad (1 - A) + S
+// i.e. rad <- fma(rad, T, S) with the layer's T and S formed per cell (a convex combination either way; the rounding differs from
+// the reference's association in the last bits, tests: <= 1e-12 of the unit form).
+// Rows of a cell: the clear-sky stream's T, S_down, S_up and -- cloudy form -- the total-sky stream's (equal to them in a clear layer).
+constexpr int TR_T = 0, TR_SD = 1, TR_SU = 2, TR_TT = 3, TR_SDT = 4, TR_SUT = 5;
+constexpr int kTileRowsClear = 3, kTileRowsCloudy = 6;
+
+// secdiff and cloud band of band ib for one column: what lw_transfer_unit derives in its prologue
+struct TileBandCol {
+  int ibc, ncb;
+  double secdiff;
+};
+CB_HD TileBandCol lw_tile_band_col(const Work& W, int c, int ib) {
+  TileBandCol b;
+  b.ncb = W.ncbands[c];
+  b.secdiff = secdiff_band(W.pwvcm[c], ib);
+  b.ibc = 0;
+  if (b.ncb == 5) b.ibc = ib <= 1 ? ib : (ib <= 4 ? 2 : (ib <= 7 ? 3 : 4));
+  else if (b.ncb == 16) b.ibc = ib;
+  return b;
+}
+// what a cell needs that does not depend on the band: is the layer cloudy, and for which g-points (McICA)
+struct TileCellCol {
+  bool cloudy;         // non-McICA: cloud fraction >= 1e-6 (rtrn.f90:302); McICA: ANY sub-column of the layer cloudy (rtrnmc.f90:298-309)
+  double cldfrac;      // non-McICA cloud fraction
+  unsigned mask[5];    // McICA: the layer's sub-column bits
+};
+template <bool MC>
+CB_HD TileCellCol lw_tile_cell_col(const In& in, const Work& W, int c0, int c, int l) {
+  TileCellCol k;
+  k.cloudy = false; k.cldfrac = 0.;
+  for (int i = 0; i < 5; ++i) k.mask[i] = 0u;
+  if (W.ncbands[c] > 0) {
+    if (MC) {
+      const size_t ms = (size_t)W.mstride;
+      const unsigned* mw = W.mask + ((size_t)l * 5) * ms + W.moff + c;
+      unsigned any = 0u;
+      for (int i = 0; i < 5; ++i) { k.mask[i] = mw[(size_t)i * ms]; any |= k.mask[i]; }
+      k.cloudy = any != 0u;
+      k.cldfrac = 1.0;
+    } else {
+      k.cldfrac = in.cldfr[(size_t)l * in.ncol + (size_t)(c0 + c)];
+      k.cloudy = k.cldfrac >= 1.e-6;
+    }
+  }
+  return k;
+}
+// what a cell needs that is the same for every g-point of its band: aerosol optical depth, the Planck terms of the layer, the
+// band's cloud optical depth and effective cloud fraction factor
+struct TileCellBand {
+  double taua, blay, dplankdn, dplankup, odcld, efclfrac;
+};
+template <bool CLOUDY>
+CB_HD TileCellBand lw_tile_cell_band(const Tables& T, const In& in, const Work& W, int c0, int c, int l, int ib, const TileBandCol& bc,
+                                     bool cloudy) {
+  const int nlay = in.nlay, ncol = in.ncol;
+  const size_t gc = (size_t)(c0 + c);
+  const double* __restrict__ tp = T.base + T.totplnk + (size_t)ib * 181;
+  const size_t o = (size_t)l * ncol + gc;
+  TileCellBand b;
+  b.taua = in.tauaer[((size_t)ib * nlay + l) * ncol + gc];
+  b.blay = planck_band(tp, in.tlay[o]);
+  b.dplankdn = planck_band(tp, in.tlev[o]) - b.blay;         // planklev(lev-1) - planklay(lev)
+  b.dplankup = planck_band(tp, in.tlev[o + ncol]) - b.blay;  // planklev(lev)   - planklay(lev)
+  b.odcld = 0.; b.efclfrac = 0.;
+  if (CLOUDY && cloudy) {
+    b.odcld = W.cld[((size_t)bc.ibc * nlay + l) * W.ncc + c];
+    b.efclfrac = W.cld[((size_t)(16 + bc.ibc) * nlay + l) * W.ncc + c];
+  }
+  return b;
+}
+// the two taumol rows of cell (l, c) for g-point gabs: optical depth and Planck fraction (streamed: read once)
+CB_HD void lw_tile_cell_load(const In& in, const Work& W, int c, int l, int gabs, double& tau, double& plfrac) {
+  const size_t wstride = (size_t)in.nlay * W.ncc;
+  const double* __restrict__ scr = W.scr + (((size_t)gabs * NSCR) * in.nlay + l) * W.ncc + c;
+  tau = ld_stream(scr + R_TAU * wstride);
+  plfrac = ld_stream(scr + R_FRAC * wstride);
+}
+
+// rows of one cell for g-point gabs -> out[r * rs], r = TR_*
+template <bool MC, bool CLOUDY>
+CB_HD void lw_tile_cell(const Tables& T, int gabs, const TileBandCol& bc, const TileCellCol& cc, const TileCellBand& cb_, double tau,
+                        double plfrac, double* __restrict__ out, size_t rs) {
+  const double* __restrict__ tb = T.base;
+  const double rec_6 = 0.166667, tblint = 10000.0, bpade = T.bpade;
+  const double* __restrict__ tau_tbl = tb + T.tau_tbl;
+  const double* __restrict__ et_tbl = tb + T.et_tbl;
+  const double taua = cb_.taua, blay = cb_.blay, dplankdn = cb_.dplankdn, dplankup = cb_.dplankup;
+  double odepth = bc.secdiff * (tau + taua);
+  if (odepth < 0.0) odepth = 0.0;
+  double atrans, bbd, bbugas;
+  if (CLOUDY && cc.cloudy) {
+    bool on = true;
+    if (MC) {  // this g-point's sub-column: cloud fraction 0 or 1
+      const int wi = gabs >> 5;
+      const unsigned w = wi == 0 ? cc.mask[0] : (wi == 1 ? cc.mask[1] : (wi == 2 ? cc.mask[2] : (wi == 3 ? cc.mask[3] : cc.mask[4])));
+      on = ((w >> (gabs & 31)) & 1u) != 0u;
+    }
+    const double odcld = on ? cb_.odcld : 0., efclfrac = on ? cb_.efclfrac : 0., cldfrac = on ? cc.cldfrac : 0.;
+    double odtot = odepth + odcld;
+    double gassrc, bbdtot, atot, bbutot;
+    if (odtot < 0.06) {
+      atrans = odepth - 0.5 * odepth * odepth;
+      const double odepth_rec = rec_6 * odepth;
+      gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
+      atot = odtot - 0.5 * odtot * odtot;
+      const double odtot_rec = rec_6 * odtot;
+      bbdtot = plfrac * (blay + dplankdn * odtot_rec);
+      bbd = plfrac * (blay + dplankdn * odepth_rec);
+      bbugas = plfrac * (blay + dplankup * odepth_rec);
+      bbutot = plfrac * (blay + dplankup * odtot_rec);
+    } else if (odepth <= 0.06) {
+      atrans = odepth - 0.5 * odepth * odepth;
+      const double odepth_rec = rec_6 * odepth;
+      gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
+      odtot = odepth + odcld;
+      const int ittot = tbl_slot(odtot, bpade, tblint);
+      const Row<2> ett = ldrow<2>(et_tbl + 2 * ittot);
+      const double tfactot = ett[1];
+      bbdtot = plfrac * (blay + tfactot * dplankdn);
+      bbd = plfrac * (blay + dplankdn * odepth_rec);
+      atot = 1. - ett[0];
+      bbugas = plfrac * (blay + dplankup * odepth_rec);
+      bbutot = plfrac * (blay + tfactot * dplankup);
+    } else {
+      const int itgas = tbl_slot(odepth, bpade, tblint);
+      odepth = CB_LDG(tau_tbl + itgas);
+      const Row<2> etg = ldrow<2>(et_tbl + 2 * itgas);
+      atrans = 1. - etg[0];
+      const double tfacgas = etg[1];
+      gassrc = atrans * plfrac * (blay + tfacgas * dplankdn);
+      odtot = odepth + odcld;
+      const int ittot = tbl_slot(odtot, bpade, tblint);
+      const Row<2> ett = ldrow<2>(et_tbl + 2 * ittot);
+      const double tfactot = ett[1];
+      bbdtot = plfrac * (blay + tfactot * dplankdn);
+      bbd = plfrac * (blay + tfacgas * dplankdn);
+      atot = 1. - ett[0];
+      bbugas = plfrac * (blay + tfacgas * dplankup);
+      bbutot = plfrac * (blay + tfactot * dplankup);
+    }
+    // rtrn.f90:386-393 / 503-508 (rtrnmc.f90:377-384 / 490-495), with the upward gas source bbugas * atrans
+    const double gassrc_up = bbugas * atrans;
+    out[TR_TT * rs] = 1. - (atrans + efclfrac * (1. - atrans));
+    out[TR_SDT * rs] = gassrc + cldfrac * (bbdtot * atot - gassrc);
+    out[TR_SUT * rs] = gassrc_up + cldfrac * (bbutot * atot - gassrc_up);
+    out[TR_T * rs] = 1. - atrans;
+    out[TR_SD * rs] = bbd * atrans;
+    out[TR_SU * rs] = gassrc_up;
+  } else {
+    if (odepth <= 0.06) {
+      atrans = odepth - 0.5 * odepth * odepth;
+      odepth = rec_6 * odepth;
+      bbd = plfrac * (blay + dplankdn * odepth);
+      bbugas = plfrac * (blay + dplankup * odepth);
+    } else {
+      const int itr = tbl_slot(odepth, bpade, tblint);
+      const Row<2> et = ldrow<2>(et_tbl + 2 * itr);
+      atrans = 1. - et[0];
+      const double tausfac = et[1];
+      bbd = plfrac * (blay + tausfac * dplankdn);
+      bbugas = plfrac * (blay + tausfac * dplankup);
+    }
+    const double t = 1. - atrans, sd = bbd * atrans, su = bbugas * atrans;
+    out[TR_T * rs] = t; out[TR_SD * rs] = sd; out[TR_SU * rs] = su;
+    if (CLOUDY) { out[TR_TT * rs] = t; out[TR_SDT * rs] = sd; out[TR_SUT * rs] = su; }
+  }
+}
+
+// The three sweeps of ONE radiance stream of one column over the parked rows of one g-point (rtrn.f90:320-526): P = the stream's
+// three rows of this column (T, S_down, S_up; row stride rs, layer stride ls); acc_dn / acc_up = the stream's per-level sums of
+// this column (level stride als).  The clear-sky stream of a column with clouds reads the clear rows from the top (lw_transfer_unit
+// copies the total-sky radiance above the highest cloud: the same update of the same inputs, the same bits).  The levels go in
+// chunks of four whose rows and sums are loaded before the chain -- one fma per level -- runs over them.
+// rad0 = plfrac(layer 1) * emissivity * B(T_sfc).
+CB_HD void lw_tile_sweeps(const double* __restrict__ P, size_t rs, size_t ls, int nlay, double rad0, double reflect, double wband,
+                          double* __restrict__ acc_dn, double* __restrict__ acc_up, size_t als) {
+  constexpr int NB = 4;
+  double rad = 0.;
+  int l = nlay - 1;
+  for (; l >= NB - 1; l -= NB) {
+    double t[NB], s[NB], a[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const double* __restrict__ r = P + (size_t)(l - k) * ls;
+      t[k] = r[0]; s[k] = r[rs];
+      a[k] = acc_dn[(size_t)(l - k) * als];
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      rad = rad * t[k] + s[k];
+      acc_dn[(size_t)(l - k) * als] = a[k] + rad * wband;
+    }
+  }
+  for (; l >= 0; --l) {
+    const double* __restrict__ r = P + (size_t)l * ls;
+    rad = rad * r[0] + r[rs];
+    acc_dn[(size_t)l * als] += rad * wband;
+  }
+  // surface (rtrn.f90:455-470)
+  rad = rad0 + reflect * rad;
+  acc_up[0] += rad * wband;
+  l = 0;
+  for (; l + NB <= nlay; l += NB) {
+    double t[NB], s[NB], a[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const double* __restrict__ r = P + (size_t)(l + k) * ls;
+      t[k] = r[0]; s[k] = r[2 * rs];
+      a[k] = acc_up[(size_t)(l + k + 1) * als];
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      rad = rad * t[k] + s[k];
+      acc_up[(size_t)(l + k + 1) * als] = a[k] + rad * wband;
+    }
+  }
+  for (; l < nlay; ++l) {
+    const double* __restrict__ r = P + (size_t)l * ls;
+    rad = rad * r[0] + r[2 * rs];
+    acc_up[(size_t)(l + 1) * als] += rad * wband;
+  }
+}
+
+// band groups of the tile form: every tile of columns is processed once per group, the group's g-points one after the other;
+// the groups' sums are reduced by lw_reduce_level like the unit groups of the other form.  4 groups of 38 + 38 + 32 + 32 g-points.
+constexpr int kTileGroups = 4;
+CB_HD void lw_tile_group_bands(int group, int& ib0, int& ib1) {  // 0-based bands [ib0, ib1)
+  switch (group) {
+    case 0: ib0 = 0; ib1 = 3; break;
+    case 1: ib0 = 3; ib1 = 6; break;
+    case 2: ib0 = 6; ib1 = 9; break;
+    default: ib0 = 9; ib1 = 16; break;
+  }
+}
+CB_HD int band_ngpt(int ib) {  // g-points of band ib (0-based): band_gstart differences
+  return (ib == 15 ? 140 : band_gstart(ib + 1)) - band_gstart(ib);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -236,6 +236,174 @@ __global__ void __launch_bounds__(32 * CB_LW_GROUP, CB_LW_SLAB_MIN_BLOCKS)
   }
 }
 
+
+// ---- column-tile form of the transfer (lw_core.cuh: lw_tile_cell / lw_tile_sweeps) ---------------------------------------------
+// One block = one tile of TW adjacent columns x one band group (lw_tile_group_bands); CB_LW_TILE_THREADS / 32 warps, specialised
+// (r02 B200: with 8 warps the 7 producer warps were latency-bound on their own dependent arithmetic -- 4.2 ms at 11 % issue
+// utilisation for 8192 x 60 -- the cell evaluation needs as many warps per scheduler as the unit form has):
+//   warps 1.. (producers)  evaluate the (layer, column) cells of one g-point -- warp-wide rows of TW columns, so the taumol rows
+//                          are read as coalesced 256-byte (128-byte) segments -- into one of two row buffers in shared memory;
+//   warp 0 (consumer)      runs the down sweep, the surface and the up sweep of its lane's column over a filled buffer and adds the
+//                          band-weighted radiances to the per-level sums, also in shared memory, while the producers fill the other
+//                          buffer with the next g-point.
+// Hand-over through named barriers (FULL / EMPTY per buffer: producers arrive, the consumer syncs, and the reverse).  At the end the
+// block writes the sums of its group: `part[group][row][level][column]` -- 4 groups instead of 18 and nothing else: the rows the two
+// sweeps exchange never leave the SM.  Shared memory: (2 NR nlay + NA (nlay + 1) + 2) TW doubles, NR / NA = 3 / 2 (cloud-free
+// call, TW = 32) or 6 / 4 (TW = 16): 123 KB at 60 layers, 148 KB at 72.
+#ifndef CB_LW_TILE_THREADS
+#define CB_LW_TILE_THREADS 512
+#endif
+constexpr int kTileThreads = CB_LW_TILE_THREADS;
+constexpr int kTileProducers = kTileThreads / 32 - 1;  // producer warps
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(kTileThreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(kTileThreads) : "memory"); }
+
+// KC: cells per producer thread, >= ceil(nlay / (kTileProducers * 32 / TW)) (chosen by the launcher)
+template <int TW, bool CLOUDY, bool MC, int KC, bool SELECT>
+__global__ void __launch_bounds__(kTileThreads, 1)
+    k_lw_tile(const __grid_constant__ Tables T, const __grid_constant__ In in, const __grid_constant__ Work W, int c0, int n) {
+  extern __shared__ double sm[];
+  constexpr int NR = CLOUDY ? kTileRowsCloudy : kTileRowsClear;
+  constexpr int NA = CLOUDY ? 4 : 2;
+  constexpr int FULL0 = 1, EMPTY0 = 3;  // barrier ids: FULL0 + b, EMPTY0 + b (0 is __syncthreads')
+  const int nlay = in.nlay;
+  const size_t prows = (size_t)nlay * TW;        // one row of a buffer
+  const size_t arows = (size_t)(nlay + 1) * TW;  // one row of the sums
+  double* const Pbuf = sm;                        // [2][NR][nlay][TW]
+  double* const acc = sm + 2 * NR * prows;        // [NA][nlay+1][TW]
+  double* const frac1 = acc + NA * arows;         // [2][TW]  Planck fraction of the lowest layer
+  const int tile = blockIdx.x, group = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (SELECT) {
+    // a call with clouds launches both forms; each 32-column supertile is taken by exactly one of them: the cloud-free form when
+    // none of its columns has a cloudy layer (k_prep's ncbands), else the cloudy form (two 16-column tiles)
+    const int c32 = (tile * TW / 32) * 32 + lane;
+    const bool anyc = __any_sync(0xffffffffu, c32 < n && W.ncbands[c32] > 0);
+    if (anyc != CLOUDY) return;
+  }
+  for (size_t i = threadIdx.x; i < NA * arows; i += kTileThreads) acc[i] = 0.0;
+  __syncthreads();
+  int ib0, ib1;
+  lw_tile_group_bands(group, ib0, ib1);
+  const int nit = band_gstart(ib1 - 1) + band_ngpt(ib1 - 1) - band_gstart(ib0);  // g-points of the group
+  int it = 0;
+  if (warp == 0) {
+    // ---- consumer: cloud-free form lane = column; cloudy form lanes 0-15 the total-sky stream of the 16 columns, lanes 16-31 their
+    // clear-sky stream (the same instruction stream: the update is selected, not branched on)
+    const int col = lane % TW, stream = lane / TW;
+    const int c = tile * TW + col;
+    const bool live = c < n;
+    const size_t gc = (size_t)c0 + (live ? c : 0);
+    double* const acc_up = acc + (size_t)(2 * stream) * arows + col;
+    double* const acc_dn = acc + (size_t)(2 * stream + 1) * arows + col;
+    for (int ib = ib0; ib < ib1; ++ib) {
+      const double* __restrict__ tp = T.base + T.totplnk + (size_t)ib * 181;
+      double semiss = 1.0, plankbnd = 0.0;
+      if (live) {
+        semiss = in.emis[(size_t)ib * in.ncol + gc];
+        plankbnd = semiss * planck_band(tp, in.tsfc[gc]);
+      }
+      const double wband = 0.5 * CB_LDG(T.base + T.delwave + ib);
+      const int ng = band_ngpt(ib);
+      for (int g = 0; g < ng; ++g, ++it) {
+        const int b = it & 1;
+        bar_sync(FULL0 + b);
+#ifndef CB_TILE_SKIP_CONSUMER  // (timing experiments only)
+        if (live)
+#else
+        if (live && it < 0)
+#endif
+          lw_tile_sweeps(Pbuf + ((size_t)b * NR + (CLOUDY && stream == 0 ? TR_TT : 0)) * prows + col, prows, TW, nlay,
+                         frac1[b * TW + col] * plankbnd, 1. - semiss, wband, acc_dn, acc_up, TW);
+        __threadfence_block();
+        if (it + 2 < nit) bar_arrive(EMPTY0 + b);  // (nobody waits for the last two)
+      }
+    }
+  } else {
+    // ---- producers: a warp covers 32 / TW layers at a time, lanes = columns.  A thread owns the same <= KC cells for every g-point:
+    // their per-band terms live in registers, and the two taumol rows of the NEXT g-point are loaded before the cells of the
+    // current one are evaluated (the rows stream from HBM once; nothing else hides their latency at 8 warps per SM).
+    constexpr int LPW = 32 / TW;  // layers per warp pass
+    const int col = lane % TW, lsub = lane / TW;
+    const int c = tile * TW + col;
+    const bool live = c < n;
+    const int pw = warp - 1, npw = kTileThreads / 32 - 1;
+    const int lstep = npw * LPW, lfirst = pw * LPW + lsub;
+    double tau_n[KC], frac_n[KC];
+    TileCellCol cck[KC];
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int l = lfirst + k * lstep;
+        if (l < nlay) {
+          lw_tile_cell_load(in, W, c, l, band_gstart(ib0), tau_n[k], frac_n[k]);
+          cck[k] = lw_tile_cell_col<MC>(in, W, c0, c, l);
+        }
+      }
+    }
+    for (int ib = ib0; ib < ib1; ++ib) {
+      TileBandCol bc{0, 0, 1.66};
+      TileCellBand cbk[KC];
+      if (live) {
+        bc = lw_tile_band_col(W, c, ib);
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const int l = lfirst + k * lstep;
+          if (l < nlay) cbk[k] = lw_tile_cell_band<CLOUDY>(T, in, W, c0, c, l, ib, bc, cck[k].cloudy);
+        }
+      }
+      const int ng = band_ngpt(ib), gs = band_gstart(ib);
+      for (int g = 0; g < ng; ++g, ++it) {
+        const int b = it & 1;
+        double tau_c[KC], frac_c[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) { tau_c[k] = tau_n[k]; frac_c[k] = frac_n[k]; }
+        if (live && it + 1 < nit) {
+#pragma unroll
+          for (int k = 0; k < KC; ++k) {
+            const int l = lfirst + k * lstep;
+            if (l < nlay) lw_tile_cell_load(in, W, c, l, gs + g + 1, tau_n[k], frac_n[k]);
+          }
+        }
+        if (it >= 2) bar_sync(EMPTY0 + b);
+        double* __restrict__ Pb = Pbuf + (size_t)b * NR * prows + col;
+#ifndef CB_TILE_SKIP_PRODUCER  // (timing experiments only)
+        if (live) {
+#else
+        if (live && it < 0) {
+#endif
+#pragma unroll
+          for (int k = 0; k < KC; ++k) {
+            const int l = lfirst + k * lstep;
+            if (l < nlay) {
+              lw_tile_cell<MC, CLOUDY>(T, gs + g, bc, cck[k], cbk[k], tau_c[k], frac_c[k], Pb + (size_t)l * TW, prows);
+              if (l == 0) frac1[b * TW + col] = frac_c[k];
+            }
+          }
+        }
+        __threadfence_block();
+        bar_arrive(FULL0 + b);
+      }
+    }
+  }
+  __syncthreads();
+  // the group's sums -> part[group][row][level][column]; the clear-sky rows only for columns with clouds (lw_reduce_level)
+  const size_t pstride = (size_t)(nlay + 1) * W.ncc;
+  for (size_t i = threadIdx.x; i < NA * arows; i += kTileThreads) {
+    const int col = (int)(i % TW);
+    const size_t rest = i / TW;
+    const int lev = (int)(rest % (nlay + 1)), q = (int)(rest / (nlay + 1));
+    const int c = tile * TW + col;
+    if (c >= n) continue;
+    if (q >= 2 && !(W.ncbands[c] > 0)) continue;
+    cb::st_stream(W.part + ((size_t)group * W.npart + q) * pstride + (size_t)lev * W.ncc + c, acc[i]);
+  }
+}
+template <int TW, bool CLOUDY>
+constexpr size_t lw_tile_smem(int nlay) {
+  return sizeof(double) * ((size_t)2 * (CLOUDY ? kTileRowsCloudy : kTileRowsClear) * nlay + (size_t)(CLOUDY ? 4 : 2) * (nlay + 1) + 2) * TW;
+}
+
 // McICA cloud mask with the per-column kissvec generator: one thread per column
 __global__ void __launch_bounds__(kBlock) k_mask_kiss(const __grid_constant__ In in, const __grid_constant__ Work W,
                                                       int icld, int seed, int c0, int n) {
@@ -245,11 +413,10 @@ __global__ void __launch_bounds__(kBlock) k_mask_kiss(const __grid_constant__ In
 }
 
 __global__ void __launch_bounds__(kBlock) k_reduce(const __grid_constant__ Tables T, const __grid_constant__ Work W,
-                                                   const __grid_constant__ UnitList UL, const Out out, int nlay,
-                                                   int ncol, int c0, int n) {
+                                                   int ngroups, const Out out, int nlay, int ncol, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int lev = blockIdx.y;
-  if (c < n) lw_reduce_level(T, W, (UL.n + CB_LW_GROUP - 1) / CB_LW_GROUP, nlay, c0, c, lev, ncol, out);
+  if (c < n) lw_reduce_level(T, W, ngroups, nlay, c0, c, lev, ncol, out);
 }
 
 __global__ void __launch_bounds__(kBlock) k_heat(const __grid_constant__ Tables T, const __grid_constant__ In in,
@@ -288,6 +455,8 @@ struct cb200_lw_engine {
   Work W{};
   double *drv_up = nullptr, *drv_upc = nullptr;  // idrv = 1 outputs of the next run call (host or device pointers, like its outputs)
   int max_chunk = 16384;
+  bool tile = true;          // column-tile form of the transfer kernel where it applies (CLIMT_B200_LW_TILE=0: the unit form)
+  size_t smem_optin = 0;     // opt-in shared memory per block of the device
   int slab_bps = 0;          // > 0: the slab form of the transfer kernel with this many 4-warp blocks per SM (CLIMT_B200_LW_SLAB)
   double* d_slabs = nullptr;
   size_t slabs_cap = 0;
@@ -365,6 +534,12 @@ extern "C" int cb200_lw_create(cb200_lw_engine** out, const char* table_blob, co
     if (const char* z = std::getenv("CLIMT_B200_SKIP_ZERO_INPUTS")) e->skip_zero_inputs = std::atoi(z) != 0;
     if (const char* sb = std::getenv("CLIMT_B200_LW_SLAB")) e->slab_bps = std::max(0, std::atoi(sb));
     cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (const char* tl = std::getenv("CLIMT_B200_LW_TILE")) e->tile = std::atoi(tl) != 0;
+    {
+      int optin = 0;
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+      e->smem_optin = (size_t)optin;
+    }
     cudaMallocHost(&e->h_err, sizeof(int));
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
@@ -451,7 +626,37 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
   if (e->timing) cudaEventRecord(e->evm, st);
   // non-McICA: icld = 1 -> rtrn (random overlap); icld = 2, 3 -> rtrnmr (maximum-random), rrtmg_lw_rad.nomcica.f90:527-541
   const dim3 gu((n + 31) / 32, (e->UL.n + CB_LW_GROUP - 1) / CB_LW_GROUP), bu(32, CB_LW_GROUP);
-  if (e->slab_bps > 0) {
+  int ngroups = (int)gu.y;
+  // the column-tile form (rows carried in shared memory) covers rtrn and rtrnmc without the surface-temperature derivative
+  const bool cloudy_call = e->fl.icld >= 1;
+  const size_t tile_smem = cloudy_call ? lw_tile_smem<16, true>(nlay) : lw_tile_smem<32, false>(nlay);
+  // cells per producer thread of the two forms (cloud-free: 32-column tiles, one layer per warp pass; cloudy: 16 columns, two layers)
+  const int kc32 = (nlay + kTileProducers - 1) / kTileProducers, kc16 = (nlay + 2 * kTileProducers - 1) / (2 * kTileProducers);
+  const size_t smem32 = lw_tile_smem<32, false>(nlay), smem16 = lw_tile_smem<16, true>(nlay);
+  if (e->tile && W.npart == 4 && (mc || e->fl.icld < 2) && smem32 <= e->smem_optin && smem16 <= e->smem_optin && kc32 <= 12) {
+#define CB_TILE(TW, CL, MCF, KC, SEL, SMEM)                                                                                        \
+    do {                                                                                                                             \
+      CUDA_OK(cudaFuncSetAttribute(k_lw_tile<TW, CL, MCF, KC, SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));      \
+      k_lw_tile<TW, CL, MCF, KC, SEL><<<dim3((n + TW - 1) / TW, kTileGroups), kTileThreads, SMEM, st>>>(e->T, in, W, c0, n);         \
+    } while (0)
+#define CB_TILE_KC(TW, CL, MCF, SEL, SMEM, KCV)                                                                     \
+    do {                                                                                                             \
+      if (KCV <= 3) CB_TILE(TW, CL, MCF, 3, SEL, SMEM); else if (KCV <= 5) CB_TILE(TW, CL, MCF, 5, SEL, SMEM);       \
+      else if (KCV <= 9) CB_TILE(TW, CL, MCF, 9, SEL, SMEM); else CB_TILE(TW, CL, MCF, 12, SEL, SMEM);               \
+    } while (0)
+    if (!cloudy_call) {
+      CB_TILE_KC(32, false, false, false, smem32, kc32);
+    } else {
+      // both forms; every block checks which of the two owns its 32-column supertile (k_lw_tile, SELECT)
+      CB_TILE_KC(32, false, false, true, smem32, kc32);
+      if (mc) CB_TILE_KC(16, true, true, true, smem16, kc16);
+      else CB_TILE_KC(16, true, false, true, smem16, kc16);
+      e->launches += 1;
+    }
+#undef CB_TILE_KC
+#undef CB_TILE
+    ngroups = kTileGroups;
+  } else if (e->slab_bps > 0) {
     const int nb = (int)std::min<size_t>((size_t)gu.x * gu.y, (size_t)e->n_sm * e->slab_bps);
     const size_t need = (size_t)nb * CB_LW_GROUP * nlay * CB_LW_UMAX * 4 * 32;
     if (need > e->slabs_cap) {
@@ -482,7 +687,7 @@ static int launch_chunk(cb200_lw_engine* e, const In& in, const Out& out, Work& 
     else k_units<false, false><<<gu, bu, 0, st>>>(e->T, in, W, e->UL, c0, n);
   }
   if (e->timing) cudaEventRecord(e->ev1, st);
-  k_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(e->T, W, e->UL, out, nlay, out_ncol, c0, n);
+  k_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(e->T, W, ngroups, out, nlay, out_ncol, c0, n);
   k_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
   e->launches += 6;
   if (e->timing) {

@@ -635,8 +635,7 @@ CB_HD void eval_band(const Tables& T, const double* __restrict__ ws, size_t wstr
 // exp(-x) through the reference's 10 001-entry table or its small-argument series (spcvrt.f90:463-470 etc.)
 CB_HD double exp_neg(const double* __restrict__ exp_tbl, double bpade, double ze1) {
   if (ze1 <= 0.06) return 1. - ze1 + 0.5 * ze1 * ze1;
-  const double tblind = ze1 / (bpade + ze1);
-  const int itind = f2i(CB_MULADD_2R(10000.0, tblind, 0.5));
+  const int itind = tbl_slot(ze1, bpade, 10000.0);  // int(10000 ze1 / (bpade + ze1) + 0.5), the reference's slot (cb_common.h)
   return CB_LDG(exp_tbl + itind);
 }
 
@@ -998,6 +997,150 @@ CB_HD void sw_transfer_unit(const Tables& T, const Solar& sol, const In& in, con
   }
   sink.finish();
 }
+
+// ---------------------------------------------------------------------------------------------
+// Column-tile form of the transfer (sw_engine.cu: k_sw_tile; host emulation: tests/emul/sw_emul.cpp) -- see lw_core.cuh for the
+// idea.  Here the cell is where the arithmetic is (delta scaling, reftra_sw: two exponentials, a square root, a dozen divisions)
+// and it does not depend on the adding recurrences at all:
+//   sw_tile_cell    one (layer, column) cell of one g-point: the five layer properties of the clear-sky stream (ref, refd, tra,
+//                   trad, dbt) and -- cloudy form -- of the total-sky stream; any thread of the block evaluates any cell, rows parked
+//                   in SHARED memory;
+//   sw_tile_sweeps  the upward adding sweep (rup, rupd per level, also in shared memory) and the downward sweep that turns them into
+//                   the g-point's fluxes, added to per-level sums in shared memory -- one stream of one column, the reference's own
+//                   formulas (vrtqdr.f90:107-169) in the reference's order.
+// The 14 rows per (g-point, layer, column) that sw_transfer_unit carries through HBM (7.2 GB per 8192 x 60 launch against 0.49 GB
+// of algorithmic bytes) never leave the SM.
+constexpr int SR_REF = 0, SR_REFD = 1, SR_TRA = 2, SR_TRAD = 3, SR_DBT = 4;  // clear stream; the total stream's rows follow (+5)
+constexpr int kSwTileRowsClear = 5, kSwTileRowsCloudy = 10;
+
+// the two taumol rows of cell (l, c) for g-point gabs (streamed: read once)
+CB_HD void sw_tile_cell_load(const In& in, const Work& W, int c, int l, int gabs, double& taug, double& taur) {
+  const size_t wstride = (size_t)in.nlay * W.ncc;
+  const double* __restrict__ scr = W.scr + (((size_t)gabs * NSCR) * in.nlay + l) * W.ncc + c;
+  taug = ld_stream(scr + R_TAUG * wstride);
+  taur = ld_stream(scr + R_TAUR * wstride);
+}
+
+// rows of cell (layer l, column c) for g-point gabs of band ib -> out[r * rs]: the band's aerosol and cloud properties of the layer
+// and the g-point's sub-column bit exactly as sw_transfer_unit reads them
+template <bool MC, bool CLOUDY>
+CB_HD void sw_tile_cell(const Tables& T, const In& in, const Flags& fl, const Work& W, int c0, int c, int l, int ib, int gabs,
+                        double prmu0, bool cloudy_col, double taug, double taur, double* __restrict__ out, size_t rs) {
+  const int nlay = in.nlay, ncol = in.ncol, ncc = W.ncc;
+  const size_t gc = (size_t)(c0 + c);
+  const double* __restrict__ exp_tbl = T.base + T.exp_tbl;
+  double ptaua = 0., pomga = 1., pasya = 0., pclfr = 0., ptauc = 0., pomgc = 1., pasyc = 0.;
+  if (fl.iaer == 10) {
+    const size_t oa = ((size_t)ib * nlay + l) * ncol + gc;
+    ptaua = in.tauaer[oa]; pomga = in.ssaaer[oa]; pasya = in.asmaer[oa];
+  } else if (fl.iaer == 6) {
+    ptaua = W.aer[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c];
+    pomga = W.aer[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c];
+    pasya = W.aer[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c];
+  }
+  const bool cl = CLOUDY && cloudy_col;
+  if (cl) {
+    bool on = true;
+    if (MC) {  // spcvmc: the sub-column is either overcast with its band's optics or clear (mcica_subcol_gen_sw.f90:523-548)
+      const unsigned w = W.mask[((size_t)l * 4 + (gabs >> 5)) * (size_t)W.mstride + W.moff + c];
+      on = ((w >> (gabs & 31)) & 1u) != 0u;
+    }
+    if (on) {
+      pclfr = MC ? 1.0 : in.cldfr[(size_t)l * ncol + gc];
+      ptauc = W.cld[((size_t)(0 * 14 + ib) * nlay + l) * ncc + c];
+      pomgc = W.cld[((size_t)(1 * 14 + ib) * nlay + l) * ncc + c];
+      pasyc = W.cld[((size_t)(2 * 14 + ib) * nlay + l) * ncc + c];
+    }
+  }
+  const SwLayer L = sw_layer_props(exp_tbl, T.bpade, prmu0, taug, taur, ptaua, pomga, pasya, cl, pclfr, ptauc, pomgc, pasyc);
+  out[SR_REF * rs] = L.refc; out[SR_REFD * rs] = L.refdc; out[SR_TRA * rs] = L.trac; out[SR_TRAD * rs] = L.tradc;
+  out[SR_DBT * rs] = L.dbtc;
+  if (CLOUDY) {
+    // a cloud-free column of a cloudy tile: its total-sky stream is its clear-sky one
+    out[(5 + SR_REF) * rs] = cl ? L.ref : L.refc; out[(5 + SR_REFD) * rs] = cl ? L.refd : L.refdc;
+    out[(5 + SR_TRA) * rs] = cl ? L.tra : L.trac; out[(5 + SR_TRAD) * rs] = cl ? L.trad : L.tradc;
+    out[(5 + SR_DBT) * rs] = cl ? L.dbt : L.dbtc;
+  }
+}
+
+// The two adding sweeps of ONE stream of one column over the parked rows of one g-point (spcvrt.f90:590-612, vrtqdr.f90:107-169):
+// P = the stream's five rows of this column (row stride rs, layer stride ls); R = two rows (rup, rupd at the interface ABOVE layer l,
+// row stride rrs, layer stride rls) written by the upward sweep and read by the downward one; acc_up / acc_dn = the stream's
+// per-level flux sums of this column (level stride als).  zinc = adjflux * solar source * mu0 of the g-point.
+//
+// The reference's recurrences divide inside the serial chain -- rupd' = refd + trad^2 rupd / (1 - rupd refd) and its three
+// siblings -- and a reciprocal plus its dependants is ~150 cycles of fp64 latency per level and sweep, which is what one warp per
+// tile can least afford (r02 B200: 2.8 ms for 8192 x 60 with the chain written that way).  The maps are linear-fractional, so the
+// sweeps carry numerators and a common denominator instead:
+//   upward    rupd = p / q, rup = r / q:   q' = q - p refd;    p' = refd q' + trad^2 p;    r' = ref q' + trad ((tra - dbt) p + dbt r)
+//   downward  rdnd = pd / qd, tdn = rd / qd, e = rd - tdbt qd (the diffuse part times qd):
+//             qd' = qd - refd pd;   pd' = refd qd' + trad^2 pd;   rd' = tdbt tra qd' + trad (e + tdbt ref pd);   tdbt' = dbt tdbt
+//             fu = (tdbt prup qd + e prupd) D,   fd = tdbt + (e + tdbt prup pd) D,   D = 1 / (qd - pd prupd)
+// -- the same rational functions of the same layer properties (substitute and cancel q / q'), two dependent fma per level in the
+// chain, the divisions (one per level and sweep) off it.  The denominators only shrink (by 1 - rupd refd <= 1 per level), so the
+// triple is renormalised every kSwRenorm levels.  Differences from the reference's operation order: last bits (tests: <= 1e-12 of
+// the unit form, <= 1e-10 of the oracle).
+constexpr int kSwRenorm = 8;
+CB_HD void sw_tile_sweeps(const double* __restrict__ P, size_t rs, size_t ls, int nlay, double albdir, double albdif, double zinc,
+                          double* __restrict__ R, size_t rrs, size_t rls, double* __restrict__ acc_up, double* __restrict__ acc_dn,
+                          size_t als) {
+  // ---- surface -> top: reflectances of everything below each interface
+  double p = albdif, q = 1., r = albdir;
+#pragma unroll 4
+  for (int l = 0; l < nlay; ++l) {
+    const double* __restrict__ c = P + (size_t)l * ls;
+    const double ref = c[SR_REF * rs], refd = c[SR_REFD * rs], tra = c[SR_TRA * rs], trad = c[SR_TRAD * rs], dbt = c[SR_DBT * rs];
+    const double t2p = trad * trad * p, dir = trad * ((tra - dbt) * p + dbt * r);
+    q = q - p * refd;
+    p = refd * q + t2p;
+    r = ref * q + dir;
+    const double inv = frcp(q);
+    const double rupd = p * inv, rup = r * inv;
+    R[(size_t)l * rls] = rup; R[rrs + (size_t)l * rls] = rupd;
+    if ((l & (kSwRenorm - 1)) == kSwRenorm - 1) { p = rupd; q = 1.; r = rup; }
+  }
+  // ---- top -> surface: downward adding and the fluxes at every interface
+  double pd = 0., qd = 1., rd = 1., tdbt = 1.;
+#pragma unroll 4
+  for (int l = nlay - 1; l >= -1; --l) {
+    double prup = albdir, prupd = albdif, ref = 0., refd = 0., tra = 0., trad = 0., dbt = 0.;
+    if (l >= 0) {
+      const double* __restrict__ c = P + (size_t)l * ls;
+      ref = c[SR_REF * rs]; refd = c[SR_REFD * rs]; tra = c[SR_TRA * rs]; trad = c[SR_TRAD * rs]; dbt = c[SR_DBT * rs];
+      prup = R[(size_t)l * rls]; prupd = R[rrs + (size_t)l * rls];
+    }
+    const double a_up = acc_up[(size_t)(l + 1) * als], a_dn = acc_dn[(size_t)(l + 1) * als];
+    const double e = rd - tdbt * qd;
+    const double D = frcp(qd - pd * prupd);
+    const double fu = (tdbt * prup * qd + e * prupd) * D;
+    const double fd = tdbt + (e + tdbt * prup * pd) * D;
+    acc_up[(size_t)(l + 1) * als] = a_up + zinc * fu;
+    acc_dn[(size_t)(l + 1) * als] = a_dn + zinc * fd;
+    if (l >= 0) {
+      const double t2p = trad * trad * pd, dif = trad * (e + tdbt * ref * pd), tt = tdbt * tra;
+      qd = qd - refd * pd;
+      pd = refd * qd + t2p;
+      rd = tt * qd + dif;
+      tdbt = dbt * tdbt;
+      if (((nlay - 1 - l) & (kSwRenorm - 1)) == kSwRenorm - 1) {
+        const double inv = frcp(qd);
+        pd = pd * inv; rd = rd * inv; qd = 1.;
+      }
+    }
+  }
+}
+
+// band groups of the tile form (see lw_core.cuh): 26 + 28 + 26 + 32 g-points
+constexpr int kTileGroups = 4;
+CB_HD void sw_tile_group_bands(int group, int& ib0, int& ib1) {  // 0-based bands [ib0, ib1)
+  switch (group) {
+    case 0: ib0 = 0; ib1 = 3; break;
+    case 1: ib0 = 3; ib1 = 6; break;
+    case 2: ib0 = 6; ib1 = 10; break;
+    default: ib0 = 10; ib1 = 14; break;
+  }
+}
+CB_HD int band_ngpt(int ib) { return (ib == 13 ? 112 : band_gstart(ib + 1)) - band_gstart(ib); }
 
 struct Unit {
   int band, g0, u;  // band = 16..29

@@ -193,6 +193,157 @@ __global__ void __launch_bounds__(32 * CB_SW_GROUP, CB_SW_SLAB_MIN_BLOCKS)
   }
 }
 
+
+// ---- column-tile form of the transfer (sw_core.cuh: sw_tile_cell / sw_tile_sweeps; the longwave twin is k_lw_tile) -----------------
+// One block = one tile of TW adjacent columns x one band group (sw_tile_group_bands); CB_SW_TILE_THREADS / 32 warps, specialised:
+//   warps 1.. (producers)  evaluate the (layer, column) cells of one g-point -- delta scaling and reftra_sw, all the arithmetic of the
+//                          path; warp-wide rows of TW columns, the taumol rows of the NEXT g-point loaded before the cells of the
+//                          current one -- into one of two row buffers in shared memory;
+//   warp 0 (consumer)      runs the upward and the downward adding sweep of its lane's (stream, column) over a filled buffer and adds
+//                          the g-point's fluxes to the per-level sums, also in shared memory, while the producers fill the other buffer.
+// Cloud-free form: lane = column (TW = 32), clear-sky stream only.  Cloudy form: lanes 0..TW-1 the clear-sky stream of the TW columns,
+// lanes TW..2TW-1 their total-sky stream.  A call with clouds launches both forms and every 32-column supertile is taken by exactly
+// one of them (SELECT).  Hand-over through named barriers as in k_lw_tile.  Shared memory: (2 NR nlay + 2 nlay NS + NA (nlay + 1)) TW
+// doubles with NR / NS / NA = 5 / 1 / 2 (cloud-free) or 10 / 2 / 4: 216 KB at 60 layers for TW = 32 / 16.
+#ifndef CB_SW_TILE_THREADS
+#define CB_SW_TILE_THREADS 512
+#endif
+constexpr int kTileThreads = CB_SW_TILE_THREADS;
+constexpr int kTileProducers = kTileThreads / 32 - 1;
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(kTileThreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(kTileThreads) : "memory"); }
+
+template <int TW, bool CLOUDY>
+constexpr size_t sw_tile_smem(int nlay) {
+  return sizeof(double) * ((size_t)2 * (CLOUDY ? kSwTileRowsCloudy : kSwTileRowsClear) * nlay * TW + (size_t)2 * nlay * (CLOUDY ? 2 : 1) * TW +
+                           (size_t)(CLOUDY ? 4 : 2) * (nlay + 1) * TW);
+}
+
+// KC: cells per producer thread, >= ceil(nlay / (kTileProducers * 32 / TW)) (chosen by the launcher)
+template <int TW, bool CLOUDY, bool MC, int KC, bool SELECT>
+__global__ void __launch_bounds__(kTileThreads, 1)
+    k_sw_tile(const __grid_constant__ Tables T, const __grid_constant__ Solar sol, const __grid_constant__ In in, const Flags fl,
+              const __grid_constant__ Work W, int c0, int n) {
+  extern __shared__ double sm[];
+  constexpr int NR = CLOUDY ? kSwTileRowsCloudy : kSwTileRowsClear;
+  constexpr int NS = CLOUDY ? 2 : 1;   // streams
+  constexpr int NA = 2 * NS;           // rows of sums: cloudy fu, fd, cu, cd; cloud-free cu, cd
+  constexpr int FULL0 = 1, EMPTY0 = 3;
+  const int nlay = in.nlay;
+  const size_t prows = (size_t)nlay * TW, arows = (size_t)(nlay + 1) * TW, rrows = (size_t)nlay * NS * TW;
+  double* const Pbuf = sm;                      // [2][NR][nlay][TW]
+  double* const Rbuf = sm + 2 * NR * prows;     // [2][nlay][NS * TW]   rup, rupd of every consumer lane
+  double* const acc = Rbuf + 2 * rrows;         // [NA][nlay+1][TW]
+  const int tile = blockIdx.x, group = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (SELECT) {
+    const int c32 = (tile * TW / 32) * 32 + lane;
+    const bool anyc = __any_sync(0xffffffffu, c32 < n && W.anycld[c32] != 0);
+    if (anyc != CLOUDY) return;
+  }
+  for (size_t i = threadIdx.x; i < NA * arows; i += kTileThreads) acc[i] = 0.0;
+  __syncthreads();
+  int ib0, ib1;
+  sw_tile_group_bands(group, ib0, ib1);
+  const int nit = band_gstart(ib1 - 1) + band_ngpt(ib1 - 1) - band_gstart(ib0);
+  int it = 0;
+  if (warp == 0) {
+    // ---- consumer
+    const int col = lane % TW, stream = lane / TW;  // stream 0: clear sky, 1: total sky
+    const int c = tile * TW + col;
+    const bool live = stream < NS && c < n;
+    const size_t gc = (size_t)c0 + (live ? c : 0);
+    double prmu0 = live ? in.coszen[gc] : 1.0;
+    if (prmu0 < 1.e-10) prmu0 = 1.e-10;
+    // rows of the sums: cloudy form [fu, fd, cu, cd], cloud-free form [cu, cd]
+    double* const acc_up = acc + (size_t)(CLOUDY ? 2 * (1 - stream) : 0) * arows + col;
+    double* const acc_dn = acc_up + arows;
+    double* const R = Rbuf + lane;
+    for (int ib = ib0; ib < ib1; ++ib) {
+      const bool nir = (ib <= 8) || ib == 13;  // rad.nomcica.f90:648-659
+      double albdir = 0., albdif = 0.;
+      if (live) { albdir = nir ? in.aldir[gc] : in.asdir[gc]; albdif = nir ? in.aldif[gc] : in.asdif[gc]; }
+      const int ng = band_ngpt(ib), gs = band_gstart(ib);
+      for (int g = 0; g < ng; ++g, ++it) {
+        const int b = it & 1;
+        const double zinc = live ? sol.adjflux[ib] * W.src[(size_t)(gs + g) * W.ncc + c] * prmu0 : 0.;
+        bar_sync(FULL0 + b);
+#ifndef CB_TILE_SKIP_CONSUMER  // (timing experiments only)
+        if (live)
+#else
+        if (live && it < 0)
+#endif
+          sw_tile_sweeps(Pbuf + ((size_t)b * NR + (size_t)stream * 5) * prows + col, prows, TW, nlay, albdir, albdif, zinc, R, rrows,
+                         (size_t)NS * TW, acc_up, acc_dn, TW);
+        __threadfence_block();
+        if (it + 2 < nit) bar_arrive(EMPTY0 + b);
+      }
+    }
+  } else {
+    // ---- producers
+    constexpr int LPW = 32 / TW;
+    const int col = lane % TW, lsub = lane / TW;
+    const int c = tile * TW + col;
+    const bool live = c < n;
+    const int pw = warp - 1;
+    const int lstep = kTileProducers * LPW, lfirst = pw * LPW + lsub;
+    double prmu0 = live ? in.coszen[(size_t)c0 + c] : 1.0;
+    if (prmu0 < 1.e-10) prmu0 = 1.e-10;
+    const bool cloudy_col = CLOUDY && live && W.anycld[c] != 0;
+    double tg_n[KC], tr_n[KC];
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int l = lfirst + k * lstep;
+        if (l < nlay) sw_tile_cell_load(in, W, c, l, band_gstart(ib0), tg_n[k], tr_n[k]);
+      }
+    }
+    for (int ib = ib0; ib < ib1; ++ib) {
+      const int ng = band_ngpt(ib), gs = band_gstart(ib);
+      for (int g = 0; g < ng; ++g, ++it) {
+        const int b = it & 1;
+        double tg_c[KC], tr_c[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) { tg_c[k] = tg_n[k]; tr_c[k] = tr_n[k]; }
+        if (live && it + 1 < nit) {
+#pragma unroll
+          for (int k = 0; k < KC; ++k) {
+            const int l = lfirst + k * lstep;
+            if (l < nlay) sw_tile_cell_load(in, W, c, l, gs + g + 1, tg_n[k], tr_n[k]);
+          }
+        }
+        if (it >= 2) bar_sync(EMPTY0 + b);
+        double* __restrict__ Pb = Pbuf + (size_t)b * NR * prows + col;
+#ifndef CB_TILE_SKIP_PRODUCER  // (timing experiments only)
+        if (live) {
+#else
+        if (live && it < 0) {
+#endif
+#pragma unroll 1
+          for (int k = 0; k < KC; ++k) {
+            const int l = lfirst + k * lstep;
+            if (l < nlay)
+              sw_tile_cell<MC, CLOUDY>(T, in, fl, W, c0, c, l, ib, gs + g, prmu0, cloudy_col, tg_c[k], tr_c[k], Pb + (size_t)l * TW, prows);
+          }
+        }
+        __threadfence_block();
+        bar_arrive(FULL0 + b);
+      }
+    }
+  }
+  __syncthreads();
+  // the group's sums -> part[group][fu, fd, cu, cd][level][column]; the cloud-free form writes the clear-sky rows only (sw_reduce_level)
+  const size_t pstride = (size_t)(nlay + 1) * W.ncc;
+  for (size_t i = threadIdx.x; i < NA * arows; i += kTileThreads) {
+    const int col = (int)(i % TW);
+    const size_t rest = i / TW;
+    const int lev = (int)(rest % (nlay + 1)), q = (int)(rest / (nlay + 1));
+    const int c = tile * TW + col;
+    if (c >= n) continue;
+    cb::st_stream(W.part + ((size_t)group * 4 + (CLOUDY ? q : q + 2)) * pstride + (size_t)lev * W.ncc + c, acc[i]);
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) k_sw_mask_kiss(const __grid_constant__ In in, const __grid_constant__ Work W,
                                                          int icld, int seed, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,11 +351,11 @@ __global__ void __launch_bounds__(kBlock) k_sw_mask_kiss(const __grid_constant__
   if (cb::mcica::mask_column_kiss(in.play, in.cldfr, in.ncol, in.nlay, 112, 4, icld, seed, W.mask, W.ncc, c0, c)) *W.err = 9;
 }
 
-__global__ void __launch_bounds__(kBlock) k_sw_reduce(const __grid_constant__ Work W, const __grid_constant__ UnitList UL,
-                                                      const Out out, int nlay, int ncol, int c0, int n) {
+__global__ void __launch_bounds__(kBlock) k_sw_reduce(const __grid_constant__ Work W, int ngroups, const Out out, int nlay, int ncol,
+                                                      int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int lev = blockIdx.y;
-  if (c < n) sw_reduce_level(W, (UL.n + CB_SW_GROUP - 1) / CB_SW_GROUP, nlay, c0, c, lev, ncol, out);
+  if (c < n) sw_reduce_level(W, ngroups, nlay, c0, c, lev, ncol, out);
 }
 
 __global__ void __launch_bounds__(kBlock) k_sw_heat(const __grid_constant__ Tables T, const __grid_constant__ In in,
@@ -240,6 +391,11 @@ struct cb200_sw_engine {
   int cap_ncc = 0, cap_nlay = 0;
   Work W{};
   int max_chunk = 8192;
+  bool tile = false;         // column-tile form of the transfer kernel (CLIMT_B200_SW_TILE=1).  Off by default: r02 B200, 8192 x 60
+                             // clear sky, it moves 0.89 GB instead of 7.2 GB but takes 2.79 ms against 1.83 ms -- the one consumer warp
+                             // of a tile issues ~60 fp64 instructions per level on one scheduler (profiles/r02_tile_kernels.md)
+  int tile_min_tw = 16;      // narrowest cloudy-form tile worth using (CLIMT_B200_SW_TILE_MIN_TW; 8 lets 72-layer cloudy calls through)
+  size_t smem_optin = 0;     // opt-in shared memory per block of the device
   int slab_bps = 0;          // > 0: the slab form of the transfer kernel with this many 4-warp blocks per SM (CLIMT_B200_SW_SLAB)
   double* d_slabs = nullptr;
   size_t slabs_cap = 0;
@@ -309,6 +465,13 @@ extern "C" int cb200_sw_create(cb200_sw_engine** out, const char* table_blob, co
     if (const char* z = std::getenv("CLIMT_B200_SKIP_ZERO_INPUTS")) e->skip_zero_inputs = std::atoi(z) != 0;
     if (const char* sb = std::getenv("CLIMT_B200_SW_SLAB")) e->slab_bps = CB_SW_UMAX == 1 ? std::max(0, std::atoi(sb)) : 0;
     cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (const char* tl = std::getenv("CLIMT_B200_SW_TILE")) e->tile = std::atoi(tl) != 0;
+    if (const char* tl = std::getenv("CLIMT_B200_SW_TILE_MIN_TW")) e->tile_min_tw = std::atoi(tl);
+    {
+      int optin = 0;
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+      e->smem_optin = (size_t)optin;
+    }
     cudaMallocHost(&e->h_err, sizeof(int));
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
@@ -390,7 +553,36 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
   k_sw_taumol<<<dim3(gx, e->UL_tau.n, CB_SW_LAYER_CHUNKS), kBlock, 0, st>>>(e->T, sol, in, W, e->UL_tau, c0, n);
   if (e->timing) cudaEventRecord(e->evm, st);
   const dim3 gt((n + 31) / 32, (e->UL.n + CB_SW_GROUP - 1) / CB_SW_GROUP), bt(32, CB_SW_GROUP);
-  if (e->slab_bps > 0) {
+  int ngroups = (int)gt.y;
+  // the column-tile form (layer properties and adding sweeps in shared memory): the widest tiles that fit, the cloudy form half as wide
+  const bool cloudy_call = e->fl.icld >= 1;
+  const int tw_clear = sw_tile_smem<32, false>(nlay) <= e->smem_optin ? 32 : (sw_tile_smem<16, false>(nlay) <= e->smem_optin ? 16 : 0);
+  const int tw_cloudy = tw_clear / 2;
+  if (e->tile && tw_clear >= (cloudy_call ? e->tile_min_tw * 2 : 16) && (nlay + kTileProducers - 1) / kTileProducers <= 8) {
+#define CB_TILE(TW, CL, MCF, KC, SEL)                                                                                                \
+    do {                                                                                                                               \
+      const size_t smem = sw_tile_smem<TW, CL>(nlay);                                                                                  \
+      CUDA_OK(cudaFuncSetAttribute(k_sw_tile<TW, CL, MCF, KC, SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+      k_sw_tile<TW, CL, MCF, KC, SEL><<<dim3((n + TW - 1) / TW, kTileGroups), kTileThreads, smem, st>>>(e->T, sol, in, e->fl, W, c0, n); \
+    } while (0)
+#define CB_TILE_KC(TW, CL, MCF, SEL)                                                                   \
+    do {                                                                                                \
+      const int kc = (nlay + kTileProducers * (32 / TW) - 1) / (kTileProducers * (32 / TW));            \
+      if (kc <= 3) CB_TILE(TW, CL, MCF, 3, SEL); else if (kc <= 5) CB_TILE(TW, CL, MCF, 5, SEL);        \
+      else CB_TILE(TW, CL, MCF, 8, SEL);                                                                \
+    } while (0)
+    if (!cloudy_call) {
+      if (tw_clear == 32) CB_TILE_KC(32, false, false, false); else CB_TILE_KC(16, false, false, false);
+    } else {
+      if (tw_clear == 32) CB_TILE_KC(32, false, false, true); else CB_TILE_KC(16, false, false, true);
+      if (tw_cloudy == 16) { if (mc) CB_TILE_KC(16, true, true, true); else CB_TILE_KC(16, true, false, true); }
+      else { if (mc) CB_TILE_KC(8, true, true, true); else CB_TILE_KC(8, true, false, true); }
+      e->launches += 1;
+    }
+#undef CB_TILE_KC
+#undef CB_TILE
+    ngroups = kTileGroups;
+  } else if (e->slab_bps > 0) {
     const int nblocks = (int)std::min<size_t>((size_t)gt.x * gt.y, (size_t)e->n_sm * e->slab_bps);
     const size_t need = (size_t)nblocks * CB_SW_GROUP * nlay * 14 * 32;
     if (need > e->slabs_cap) {
@@ -406,7 +598,7 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
   } else if (mc) k_sw_transfer<true><<<gt, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
   else k_sw_transfer<false><<<gt, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
   if (e->timing) cudaEventRecord(e->ev1, st);
-  k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, e->UL, out, nlay, out_ncol, c0, n);
+  k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, ngroups, out, nlay, out_ncol, c0, n);
   k_sw_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
   e->launches += 6;
   if (e->timing) {

@@ -1,6 +1,8 @@
 // TEST-ONLY host emulation of the CUDA LW engine: runs the very same per-thread code
 // (climt_b200/csrc/lw_core.cuh) serially on the CPU so the kernel logic can be checked against the
 // oracle in a container without a GPU.  Not part of the product; the product never falls back to this.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -28,6 +30,58 @@ static void run_transfer(const Tables& T, const In& in, const Work& W, int n, in
     if (mc) lw_transfer_unit<U, true, false, DRV>(T, in, W, 0, c, ib, g0, sink);
     else if (mr) lw_transfer_unit<U, false, true, DRV>(T, in, W, 0, c, ib, g0, sink);
     else lw_transfer_unit<U, false, false, DRV>(T, in, W, 0, c, ib, g0, sink);
+  }
+}
+
+// The column-tile form of the transfer (lw_core.cuh: lw_tile_cell / lw_tile_sweeps; CUDA kernel k_lw_tile): the cells of one
+// g-point are evaluated into NaN-poisoned row buffers, then the column's sweeps run over them -- same code, serial schedule.
+static int g_tile = 0;
+extern "C" void emul_lw_set_tile(int on) { g_tile = on; }
+
+template <bool MC, bool CLOUDY>
+static void run_tile(const Tables& T, const In& in, const Work& W, int n) {
+  const int nlay = in.nlay;
+  constexpr int NR = CLOUDY ? kTileRowsCloudy : kTileRowsClear;
+  const size_t pstride = (size_t)(nlay + 1) * W.ncc;
+  std::vector<double> P((size_t)NR * nlay), acc((size_t)4 * (nlay + 1));
+  for (int group = 0; group < kTileGroups; ++group) {
+    int ib0, ib1;
+    lw_tile_group_bands(group, ib0, ib1);
+    for (int c = 0; c < n; ++c) {
+      std::fill(acc.begin(), acc.end(), 0.0);
+      const bool cloudy_col = CLOUDY && W.ncbands[c] > 0;
+      for (int ib = ib0; ib < ib1; ++ib) {
+        const TileBandCol bc = lw_tile_band_col(W, c, ib);
+        const double* tp = T.base + T.totplnk + (size_t)ib * 181;
+        const double semiss = in.emis[(size_t)ib * in.ncol + c];
+        const double plankbnd = semiss * planck_band(tp, in.tsfc[c]);
+        const double wband = 0.5 * T.base[T.delwave + ib];
+        for (int g = 0; g < band_ngpt(ib); ++g) {
+          std::fill(P.begin(), P.end(), std::nan(""));
+          double frac1 = 0.;
+          for (int l = nlay - 1; l >= 0; --l) {
+            const TileCellCol cc = lw_tile_cell_col<MC>(in, W, 0, c, l);
+            const TileCellBand cb_ = lw_tile_cell_band<CLOUDY>(T, in, W, 0, c, l, ib, bc, cc.cloudy);
+            double tau, plfrac;
+            lw_tile_cell_load(in, W, c, l, band_gstart(ib) + g, tau, plfrac);
+            lw_tile_cell<MC, CLOUDY>(T, band_gstart(ib) + g, bc, cc, cb_, tau, plfrac, P.data() + l, (size_t)nlay);
+            if (l == 0) frac1 = plfrac;
+          }
+          const size_t as = (size_t)(nlay + 1);
+          // total-sky stream (the cloudy form's rows 3-5; cloud-free form: rows 0-2), then the clear-sky stream of a cloudy column
+          lw_tile_sweeps(P.data() + (CLOUDY ? (size_t)TR_TT * nlay : 0), (size_t)nlay, 1, nlay, frac1 * plankbnd, 1. - semiss, wband,
+                         acc.data() + as, acc.data(), 1);
+          if (cloudy_col)
+            lw_tile_sweeps(P.data(), (size_t)nlay, 1, nlay, frac1 * plankbnd, 1. - semiss, wband, acc.data() + 3 * as,
+                           acc.data() + 2 * as, 1);
+        }
+      }
+      for (int q = 0; q < 4; ++q) {
+        if (q >= 2 && !cloudy_col) continue;
+        for (int lev = 0; lev <= nlay; ++lev)
+          W.part[((size_t)group * W.npart + q) * pstride + (size_t)lev * W.ncc + c] = acc[(size_t)q * (nlay + 1) + lev];
+      }
+    }
   }
 }
 
@@ -88,7 +142,13 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
       }
 #undef CASE
     }
-    for (int k2 = 0; k2 < nunits; ++k2) {
+    const bool tile = g_tile && !drv && (mc || fl.icld < 2);
+    if (tile) {
+      if (mc) run_tile<true, true>(T, in, W, ncol);
+      else if (fl.icld >= 1) run_tile<false, true>(T, in, W, ncol);
+      else run_tile<false, false>(T, in, W, ncol);
+    }
+    for (int k2 = 0; k2 < nunits && !tile; ++k2) {
       const Unit un = units[k2];
       const bool mr = !mc && fl.icld >= 2;
       if (drv) {
@@ -100,7 +160,8 @@ extern "C" int emul_lw_run(const char* blob, const double* consts11, const int* 
       }
     }
     for (int c = 0; c < ncol; ++c)
-      for (int lev = 0; lev <= nlay; ++lev) lw_reduce_level(T, W, (nunits + CB_LW_GROUP - 1) / CB_LW_GROUP, nlay, 0, c, lev, ncol, out);
+      for (int lev = 0; lev <= nlay; ++lev)
+        lw_reduce_level(T, W, tile ? kTileGroups : (nunits + CB_LW_GROUP - 1) / CB_LW_GROUP, nlay, 0, c, lev, ncol, out);
     for (int c = 0; c < ncol; ++c)
       for (int l = 0; l < nlay; ++l) lw_heating(T, in, out, c, l);
     return err;

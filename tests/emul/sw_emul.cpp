@@ -1,4 +1,6 @@
 // TEST-ONLY host emulation of the CUDA SW engine (same per-thread code as the kernels, stepped serially).
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -26,6 +28,53 @@ static void run_transfer(const Tables& T, const Solar& sol, const In& in, const 
     SwPartDirect sink{W.part + (size_t)(unit / CB_SW_GROUP) * 4 * pstride + c, pstride, W.ncc};
     if (mc) sw_transfer_unit<U, true>(T, sol, in, fl, W, 0, c, ib, g0, sink);
     else sw_transfer_unit<U, false>(T, sol, in, fl, W, 0, c, ib, g0, sink);
+  }
+}
+
+// The column-tile form of the transfer (sw_core.cuh: sw_tile_cell / sw_tile_sweeps; CUDA kernel k_sw_tile): the cells of one g-point
+// are evaluated into NaN-poisoned row buffers, then the column's sweeps run over them -- same code, serial schedule.
+static int g_tile = 0;
+extern "C" void emul_sw_set_tile(int on) { g_tile = on; }
+
+template <bool MC, bool CLOUDY>
+static void run_tile(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int n) {
+  const int nlay = in.nlay;
+  constexpr int NR = CLOUDY ? kSwTileRowsCloudy : kSwTileRowsClear;
+  const size_t pstride = (size_t)(nlay + 1) * W.ncc, as = (size_t)(nlay + 1);
+  std::vector<double> P((size_t)NR * nlay), R((size_t)2 * nlay), acc((size_t)4 * (nlay + 1));
+  for (int group = 0; group < kTileGroups; ++group) {
+    int ib0, ib1;
+    sw_tile_group_bands(group, ib0, ib1);
+    for (int c = 0; c < n; ++c) {
+      std::fill(acc.begin(), acc.end(), 0.0);
+      const bool cloudy_col = W.anycld[c] != 0;
+      double prmu0 = in.coszen[c];
+      if (prmu0 < 1.e-10) prmu0 = 1.e-10;
+      for (int ib = ib0; ib < ib1; ++ib) {
+        const bool nir = (ib <= 8) || ib == 13;
+        const double albdir = nir ? in.aldir[c] : in.asdir[c], albdif = nir ? in.aldif[c] : in.asdif[c];
+        for (int g = 0; g < band_ngpt(ib); ++g) {
+          const int gabs = band_gstart(ib) + g;
+          std::fill(P.begin(), P.end(), std::nan(""));
+          std::fill(R.begin(), R.end(), std::nan(""));
+          for (int l = 0; l < nlay; ++l) {
+            double taug, taur;
+            sw_tile_cell_load(in, W, c, l, gabs, taug, taur);
+            sw_tile_cell<MC, CLOUDY>(T, in, fl, W, 0, c, l, ib, gabs, prmu0, cloudy_col, taug, taur, P.data() + l, (size_t)nlay);
+          }
+          const double zinc = sol.adjflux[ib] * W.src[(size_t)gabs * W.ncc + c] * prmu0;
+          // clear-sky stream -> rows 2, 3; total-sky stream (cloudy form) -> rows 0, 1
+          sw_tile_sweeps(P.data(), (size_t)nlay, 1, nlay, albdir, albdif, zinc, R.data(), (size_t)nlay, 1, acc.data() + 2 * as,
+                         acc.data() + 3 * as, 1);
+          if (CLOUDY)
+            sw_tile_sweeps(P.data() + (size_t)5 * nlay, (size_t)nlay, 1, nlay, albdir, albdif, zinc, R.data(), (size_t)nlay, 1,
+                           acc.data(), acc.data() + as, 1);
+        }
+      }
+      for (int q = CLOUDY ? 0 : 2; q < 4; ++q)
+        for (int lev = 0; lev <= nlay; ++lev)
+          W.part[((size_t)group * 4 + q) * pstride + (size_t)lev * W.ncc + c] = acc[(size_t)q * as + lev];
+    }
   }
 }
 
@@ -89,7 +138,13 @@ extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* 
       }
 #undef CASE
     }
-    for (int k2 = 0; k2 < nunits; ++k2) {
+    const bool tile = g_tile != 0;
+    if (tile) {
+      if (mc) run_tile<true, true>(T, sol, in, fl, W, ncol);
+      else if (fl.icld >= 1) run_tile<false, true>(T, sol, in, fl, W, ncol);
+      else run_tile<false, false>(T, sol, in, fl, W, ncol);
+    }
+    for (int k2 = 0; k2 < nunits && !tile; ++k2) {
       const Unit un = units[k2];
       if (un.u == 4) run_transfer<4>(T, sol, in, fl, W, ncol, un.band - 16, un.g0, k2, mc);
       else if (un.u == 1) run_transfer<1>(T, sol, in, fl, W, ncol, un.band - 16, un.g0, k2, mc);
@@ -97,7 +152,8 @@ extern "C" int emul_sw_run(const char* blob, const double* consts11, const int* 
     }
     if (g_scr_export) std::memcpy(g_scr_export, scr.data(), scr.size() * sizeof(double));
     for (int c = 0; c < ncol; ++c)
-      for (int lev = 0; lev <= nlay; ++lev) sw_reduce_level(W, (nunits + CB_SW_GROUP - 1) / CB_SW_GROUP, nlay, 0, c, lev, ncol, out);
+      for (int lev = 0; lev <= nlay; ++lev)
+        sw_reduce_level(W, tile ? kTileGroups : (nunits + CB_SW_GROUP - 1) / CB_SW_GROUP, nlay, 0, c, lev, ncol, out);
     for (int c = 0; c < ncol; ++c)
       for (int l = 0; l < nlay; ++l) sw_heating(T, in, out, c, l);
     return err;

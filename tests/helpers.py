@@ -115,10 +115,12 @@ def emul_lib(which="lw"):
     return ctypes.CDLL(so)
 
 
-def run_lw_emul(st, flags=(1, 0, 2, 1, 1), mcica=(0, 1, 0)):
-    """flags = (icld, idrv, inflag, iceflag, liqflag); mcica = (enabled, irng, permuteseed)"""
+def run_lw_emul(st, flags=(1, 0, 2, 1, 1), mcica=(0, 1, 0), tile=False):
+    """flags = (icld, idrv, inflag, iceflag, liqflag); mcica = (enabled, irng, permuteseed); tile: the column-tile form of the
+    transfer (lw_tile_cell / lw_tile_sweeps) instead of lw_transfer_unit"""
     flags = tuple(flags) + tuple(mcica)
     lib = emul_lib()
+    lib.emul_lw_set_tile(1 if tile else 0)
     k = C.rrtmg_constants()
     consts = np.array([k[n] for n in ("pi", "grav", "planck", "boltz", "clight", "avogad", "alosmt", "gascon",
                                       "sbcnst", "secdy", "cpdair")])
@@ -133,9 +135,11 @@ def run_lw_emul(st, flags=(1, 0, 2, 1, 1), mcica=(0, 1, 0)):
     return rc, out
 
 
-def run_sw_emul(st, iopt=(1, 0, 2, 1, 1, 0, 1), scal=None, mcica=(0, 1, 0)):
-    """iopt = (icld, iaer, inflag, iceflag, liqflag, isolvar, dyofyr); scal = [adjes, scon, solcycfrac, ind0, ind1, bnd[14]]"""
+def run_sw_emul(st, iopt=(1, 0, 2, 1, 1, 0, 1), scal=None, mcica=(0, 1, 0), tile=False):
+    """iopt = (icld, iaer, inflag, iceflag, liqflag, isolvar, dyofyr); scal = [adjes, scon, solcycfrac, ind0, ind1, bnd[14]];
+    tile: the column-tile form of the transfer (sw_tile_cell / sw_tile_sweeps) instead of sw_transfer_unit"""
     lib = emul_lib("sw")
+    lib.emul_sw_set_tile(1 if tile else 0)
     k = C.rrtmg_constants()
     consts = np.array([k[n] for n in ("pi", "grav", "planck", "boltz", "clight", "avogad", "alosmt", "gascon",
                                       "sbcnst", "secdy", "cpdair")])
