@@ -1130,6 +1130,120 @@ CB_HD void sw_tile_sweeps(const double* __restrict__ P, size_t rs, size_t ls, in
   }
 }
 
+// ---- scan form of the two sweeps (sw_engine.cu: k_sw_scan; host emulation: tests/emul/sw_emul.cpp) ----------------------------------
+// sw_tile_sweeps is serial over the levels, so only one warp of a tile can run it, and its ~60 fp64 instructions per level on one
+// scheduler are what bound k_sw_tile.  But the numerator / denominator maps above are LINEAR: a layer acts on the upward state
+// (p, q, r) and on the downward state (pd, qd, b, e) -- b = tdbt, e = rd - tdbt qd -- as a structured matrix, matrices compose
+// associatively, and the state at every interface is a prefix (from the surface) or suffix (from the top) product applied to a fixed
+// start vector.  A group of kScanLanes lanes shares one column: every lane owns KL consecutive interfaces and the layers above them,
+// multiplies its own layers' matrices, a log2(kScanLanes)-step shuffle scan gives each lane the product of everything below / above
+// its block, and the lane then walks its own KL layers with the direct recurrences.  Columns are independent, so every warp of the
+// block sweeps (32 / kScanLanes columns at a time): the sweeps are spread over all schedulers, nothing is parked between them (rup
+// and rupd of a lane's interfaces stay in its registers until its downward walk needs them), and the flux sums of a lane's
+// interfaces are register accumulators for the whole band group.
+//   upward    [p'; q'] = A [p; q],  r' = c . [p; q] + a33 r        A = [[trad^2 - refd^2, refd], [-refd, 1]],
+//                                                                   c = (trad (tra - dbt) - ref refd, ref),  a33 = trad dbt
+//   downward  [pd'; qd'] = A [pd; qd],  b' = dbt b,  e' = trad e + b g . [pd; qd]      g = (trad ref - (tra - dbt) refd, tra - dbt)
+// (expand sw_tile_sweeps' updates).  tools/adding_scan_study.py (r01) measured the reordering at <= 1.9e-15 of the serial sweep.
+constexpr int kScanLanes = 8;
+struct UpMap { double a11, a12, a21, a22, c1, c2, a33; };
+struct DnMap { double a11, a12, a21, a22, beta, t, g1, g2; };
+CB_HD UpMap up_identity() { return UpMap{1., 0., 0., 1., 0., 0., 1.}; }
+CB_HD DnMap dn_identity() { return DnMap{1., 0., 0., 1., 1., 1., 0., 0.}; }
+CB_HD UpMap up_layer(double ref, double refd, double tra, double trad, double dbt) {
+  return UpMap{trad * trad - refd * refd, refd, -refd, 1., trad * (tra - dbt) - ref * refd, ref, trad * dbt};
+}
+CB_HD DnMap dn_layer(double ref, double refd, double tra, double trad, double dbt) {
+  return DnMap{trad * trad - refd * refd, refd, -refd, 1., dbt, trad, trad * ref - (tra - dbt) * refd, tra - dbt};
+}
+// the map "m first, then n"
+CB_HD UpMap up_compose(const UpMap& n, const UpMap& m) {
+  UpMap o;
+  o.a11 = n.a11 * m.a11 + n.a12 * m.a21; o.a12 = n.a11 * m.a12 + n.a12 * m.a22;
+  o.a21 = n.a21 * m.a11 + n.a22 * m.a21; o.a22 = n.a21 * m.a12 + n.a22 * m.a22;
+  o.c1 = n.c1 * m.a11 + n.c2 * m.a21 + n.a33 * m.c1;
+  o.c2 = n.c1 * m.a12 + n.c2 * m.a22 + n.a33 * m.c2;
+  o.a33 = n.a33 * m.a33;
+  return o;
+}
+CB_HD DnMap dn_compose(const DnMap& n, const DnMap& m) {
+  DnMap o;
+  o.a11 = n.a11 * m.a11 + n.a12 * m.a21; o.a12 = n.a11 * m.a12 + n.a12 * m.a22;
+  o.a21 = n.a21 * m.a11 + n.a22 * m.a21; o.a22 = n.a21 * m.a12 + n.a22 * m.a22;
+  o.beta = n.beta * m.beta;
+  o.t = n.t * m.t;
+  o.g1 = n.t * m.g1 + m.beta * (n.g1 * m.a11 + n.g2 * m.a21);
+  o.g2 = n.t * m.g2 + m.beta * (n.g1 * m.a12 + n.g2 * m.a22);
+  return o;
+}
+// One lane's share of the two sweeps of one g-point.  i = lane of the column's group, KL = interfaces per lane (<= KLMAX); the lane
+// owns interfaces i KL + k and the layers with the same indices, k = 0 .. KL-1.  row(r, k) reads property r of the lane's k-th layer.
+// Part 1 (before the scans): the lane's own two products in one pass over its layers, lowest first -- the upward product takes each
+// new layer on the left (applied after the layers below), the downward one on the right (applied before them).
+template <int KLMAX, class RowFn>
+CB_HD void scan_local(const RowFn& row, int nlay, int i, int KL, UpMap& um, DnMap& dm) {
+  um = up_identity();
+  dm = dn_identity();
+#pragma unroll
+  for (int k = 0; k < KLMAX; ++k) {
+    if (k < KL && i * KL + k < nlay) {
+      const double ref = row(SR_REF, k), refd = row(SR_REFD, k), tra = row(SR_TRA, k), trad = row(SR_TRAD, k), dbt = row(SR_DBT, k);
+      um = up_compose(up_layer(ref, refd, tra, trad, dbt), um);
+      dm = dn_compose(dm, dn_layer(ref, refd, tra, trad, dbt));
+    }
+  }
+}
+// Part 2 (after the scans): below = product of all layers under the lane's block, above = of all layers over it.  The lane walks
+// its layers upward from the state at its lowest interface, keeping rup / rupd of its interfaces, then downward from the state at
+// the top of its block, and adds zinc x (fu, fd) of its interfaces to acc_up / acc_dn[KLMAX] (k-th interface of the lane).
+template <int KLMAX, class RowFn>
+CB_HD void scan_walk(const RowFn& row, int nlay, int i, int KL, const UpMap& below, const DnMap& above, double albdir, double albdif,
+                     double zinc, double* acc_up, double* acc_dn) {
+  double rup[KLMAX], rupd[KLMAX];
+  {
+    // state at the surface (albdif, 1, albdir) carried through everything below the block
+    double p = below.a11 * albdif + below.a12, q = below.a21 * albdif + below.a22;
+    double r = below.c1 * albdif + below.c2 + below.a33 * albdir;
+#pragma unroll
+    for (int k = 0; k < KLMAX; ++k) {
+      const int l = i * KL + k;  // interface l, then layer l above it
+      if (k < KL && l <= nlay) {
+        const double inv = frcp(q);
+        rup[k] = r * inv; rupd[k] = p * inv;
+        if (l < nlay) {
+          const double ref = row(SR_REF, k), refd = row(SR_REFD, k), tra = row(SR_TRA, k), trad = row(SR_TRAD, k), dbt = row(SR_DBT, k);
+          const double t2p = trad * trad * p, dir = trad * ((tra - dbt) * p + dbt * r);
+          q = q - p * refd;
+          p = refd * q + t2p;
+          r = ref * q + dir;
+        }
+      }
+    }
+  }
+  // state at the top of the atmosphere (pd, qd, b, e) = (0, 1, 1, 0) carried through everything above the block
+  double pd = above.a12, qd = above.a22, b = above.beta, e = above.g2;
+#pragma unroll
+  for (int k = KLMAX - 1; k >= 0; --k) {
+    const int l = i * KL + k;  // layer l (if any) first, then interface l below it
+    if (k < KL && l <= nlay) {
+      if (l < nlay) {
+        const double ref = row(SR_REF, k), refd = row(SR_REFD, k), tra = row(SR_TRA, k), trad = row(SR_TRAD, k), dbt = row(SR_DBT, k);
+        const double t2p = trad * trad * pd, g = trad * ref * pd;
+        const double qn = qd - refd * pd;
+        e = trad * e + b * ((tra - dbt) * qn + g);
+        pd = refd * qn + t2p;
+        qd = qn;
+        b = dbt * b;
+      }
+      const double D = frcp(qd - pd * rupd[k]);
+      const double fu = (b * rup[k] * qd + e * rupd[k]) * D;
+      const double fd = b + (e + b * rup[k] * pd) * D;
+      acc_up[k] = acc_up[k] + zinc * fu;
+      acc_dn[k] = acc_dn[k] + zinc * fd;
+    }
+  }
+}
+
 // band groups of the tile form (see lw_core.cuh): 26 + 28 + 26 + 32 g-points
 constexpr int kTileGroups = 4;
 CB_HD void sw_tile_group_bands(int group, int& ib0, int& ib1) {  // 0-based bands [ib0, ib1)

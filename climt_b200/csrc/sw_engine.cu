@@ -125,9 +125,12 @@ struct SwPartSmem {
 template <bool MC>
 __global__ void __launch_bounds__(32 * CB_SW_GROUP, CB_SW_RT_MIN_BLOCKS * 4 / CB_SW_GROUP)
     k_sw_transfer(const __grid_constant__ Tables T, const __grid_constant__ Solar sol, const __grid_constant__ In in, const Flags fl,
-                  const __grid_constant__ Work W, const __grid_constant__ UnitList UL, int c0, int n) {
+                  const __grid_constant__ Work W, const __grid_constant__ UnitList UL, int c0, int n, int skip_clear) {
   __shared__ double s_part[kPartK * 4 * 32 * CB_SW_GROUP];
   const int c = blockIdx.x * 32 + threadIdx.x;
+  // the cloud-free 32-column supertiles of a call with clouds belong to k_sw_scan (every warp of the block holds the same 32
+  // columns: the vote is block-uniform)
+  if (skip_clear && !__any_sync(0xffffffffu, c < n && W.anycld[c] != 0)) return;
   const int group = blockIdx.y;
   const int k = group * CB_SW_GROUP + threadIdx.y;
   SwPartSmem sink;
@@ -344,6 +347,136 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   }
 }
 
+// ---- scan form (sw_core.cuh: scan_up_local / scan_dn_local / scan_walk) ----------------------------------------------------------------
+// One block = a tile of 32 adjacent cloud-free columns x one band group, 8 warps, two blocks per SM; per g-point two phases:
+//   cells   every thread evaluates its (layer, column) cells (lanes = columns: the taumol rows are read as coalesced 256-byte rows,
+//           those of the next g-point loaded ahead) into ONE row buffer in shared memory;
+//   sweeps  every warp takes four columns, eight lanes per column: local matrix products over a lane's own layers, a three-step
+//           shuffle scan up and one down, then each lane walks its layers and adds the fluxes of its interfaces to REGISTER sums.
+// Nothing but the layer rows is parked, no sums in shared memory, no hand-over protocol: two __syncthreads per g-point, and while
+// one block of the SM sweeps the other evaluates cells.  Row buffer layout [row][l % KL][l / KL][36]: lanes of a column group read
+// different bank groups, a warp of the cells phase writes 32 consecutive doubles.  Shared memory 5 x KL x 8 x 36 doubles: 92 KB for
+// up to 63 layers.  Columns with clouds are left to k_sw_transfer (SELECT; sw_reduce picks the right group count per supertile).
+constexpr int kScanThreads = 256, kScanLS = 36;
+template <int KLMAX>
+constexpr size_t sw_scan_smem(int KL) { return sizeof(double) * (size_t)kSwTileRowsClear * KL * kScanLanes * kScanLS; }
+__device__ __forceinline__ UpMap shfl_up_map(const UpMap& m, int d) {
+  UpMap o;
+  o.a11 = __shfl_up_sync(0xffffffffu, m.a11, d, kScanLanes); o.a12 = __shfl_up_sync(0xffffffffu, m.a12, d, kScanLanes);
+  o.a21 = __shfl_up_sync(0xffffffffu, m.a21, d, kScanLanes); o.a22 = __shfl_up_sync(0xffffffffu, m.a22, d, kScanLanes);
+  o.c1 = __shfl_up_sync(0xffffffffu, m.c1, d, kScanLanes); o.c2 = __shfl_up_sync(0xffffffffu, m.c2, d, kScanLanes);
+  o.a33 = __shfl_up_sync(0xffffffffu, m.a33, d, kScanLanes);
+  return o;
+}
+__device__ __forceinline__ DnMap shfl_down_map(const DnMap& m, int d) {
+  DnMap o;
+  o.a11 = __shfl_down_sync(0xffffffffu, m.a11, d, kScanLanes); o.a12 = __shfl_down_sync(0xffffffffu, m.a12, d, kScanLanes);
+  o.a21 = __shfl_down_sync(0xffffffffu, m.a21, d, kScanLanes); o.a22 = __shfl_down_sync(0xffffffffu, m.a22, d, kScanLanes);
+  o.beta = __shfl_down_sync(0xffffffffu, m.beta, d, kScanLanes); o.t = __shfl_down_sync(0xffffffffu, m.t, d, kScanLanes);
+  o.g1 = __shfl_down_sync(0xffffffffu, m.g1, d, kScanLanes); o.g2 = __shfl_down_sync(0xffffffffu, m.g2, d, kScanLanes);
+  return o;
+}
+
+template <int KLMAX, bool SELECT>
+__global__ void __launch_bounds__(kScanThreads, 2)
+    k_sw_scan(const __grid_constant__ Tables T, const __grid_constant__ Solar sol, const __grid_constant__ In in, const Flags fl,
+              const __grid_constant__ Work W, int c0, int n) {
+  extern __shared__ double P[];
+  constexpr int TW = 32, NW = kScanThreads / 32;
+  const int nlay = in.nlay;
+  const int KL = (nlay + 1 + kScanLanes - 1) / kScanLanes;  // interfaces (and layers) per lane of a column group
+  const int tile = blockIdx.x, group = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (SELECT) {
+    const int c32 = tile * TW + lane;
+    if (__any_sync(0xffffffffu, c32 < n && W.anycld[c32] != 0)) return;  // a supertile with clouds: k_sw_transfer's
+  }
+  const size_t rstride = (size_t)KL * kScanLanes * kScanLS;
+  // cells phase: lane = column, warp w owns layers w, w + NW, ...
+  const int ccol = tile * TW + lane;
+  const bool clive = ccol < n;
+  double cmu0 = clive ? in.coszen[(size_t)c0 + ccol] : 1.0;
+  if (cmu0 < 1.e-10) cmu0 = 1.e-10;
+  // sweeps phase: lanes 8 gi .. 8 gi + 7 share column 4 warp + gi
+  const int gi = lane / kScanLanes, li = lane % kScanLanes;
+  const int scol_t = NW == 8 ? 4 * warp + gi : 0;  // column of the tile
+  const int scol = tile * TW + scol_t;
+  const bool slive = scol < n;
+  const size_t sgc = (size_t)c0 + (slive ? scol : 0);
+  double smu0 = slive ? in.coszen[sgc] : 1.0;
+  if (smu0 < 1.e-10) smu0 = 1.e-10;
+  double acc_up[KLMAX], acc_dn[KLMAX];
+#pragma unroll
+  for (int k = 0; k < KLMAX; ++k) { acc_up[k] = 0.; acc_dn[k] = 0.; }
+  // property r of this lane's k-th layer (layer li KL + k) of its column
+  const double* const Pl = P + (size_t)li * kScanLS + scol_t;
+  auto row = [&](int r, int k) { return Pl[(size_t)r * rstride + (size_t)k * (kScanLanes * kScanLS)]; };
+  int ib0, ib1;
+  sw_tile_group_bands(group, ib0, ib1);
+  const int nit = band_gstart(ib1 - 1) + band_ngpt(ib1 - 1) - band_gstart(ib0);
+  // the taumol rows of the next g-point are pulled into the L2 while the cells of the current one are evaluated (no registers held)
+  const size_t wstride = (size_t)nlay * W.ncc;
+  int it = 0;
+  for (int ib = ib0; ib < ib1; ++ib) {
+    const bool nir = (ib <= 8) || ib == 13;  // rad.nomcica.f90:648-659
+    double albdir = 0., albdif = 0.;
+    if (slive) { albdir = nir ? in.aldir[sgc] : in.asdir[sgc]; albdif = nir ? in.aldif[sgc] : in.asdif[sgc]; }
+    const int ng = band_ngpt(ib), gs = band_gstart(ib);
+    for (int g = 0; g < ng; ++g, ++it) {
+      const double zinc = slive ? sol.adjflux[ib] * W.src[(size_t)(gs + g) * W.ncc + scol] * smu0 : 0.;
+      if (clive) {
+        int kk = warp % KL, ii = warp / KL;  // slot of layer l = (l % KL, l / KL), advanced without dividing
+#pragma unroll 1
+        for (int l = warp; l < nlay; l += NW) {
+          const double* __restrict__ scr = W.scr + (((size_t)(gs + g) * NSCR) * nlay + l) * W.ncc + ccol;
+          if (it + 1 < nit) {
+            cb::prefetch_l2(scr + (size_t)NSCR * wstride + R_TAUG * wstride);
+            cb::prefetch_l2(scr + (size_t)NSCR * wstride + R_TAUR * wstride);
+          }
+          const double taug = cb::ld_stream(scr + R_TAUG * wstride), taur = cb::ld_stream(scr + R_TAUR * wstride);
+          sw_tile_cell<false, false>(T, in, fl, W, c0, ccol, l, ib, gs + g, cmu0, false, taug, taur,
+                                     P + ((size_t)kk * kScanLanes + ii) * kScanLS + lane, rstride);
+          kk += NW;
+          while (kk >= KL) { kk -= KL; ++ii; }
+        }
+      }
+      __syncthreads();
+      {
+        // every lane takes part in the shuffles (a ragged tile's dead column groups sweep whatever the buffer holds; nothing of
+        // theirs is written)
+        UpMap um;
+        DnMap dm;
+        scan_local<KLMAX>(row, nlay, li, KL, um, dm);
+#pragma unroll
+        for (int d = 1; d < kScanLanes; d <<= 1) {
+          const UpMap uo = shfl_up_map(um, d);
+          const DnMap dn_o = shfl_down_map(dm, d);
+          if (li >= d) um = up_compose(um, uo);
+          if (li + d < kScanLanes) dm = dn_compose(dm, dn_o);
+        }
+        UpMap below = shfl_up_map(um, 1);
+        DnMap above = shfl_down_map(dm, 1);
+        if (li == 0) below = up_identity();
+        if (li == kScanLanes - 1) above = dn_identity();
+        scan_walk<KLMAX>(row, nlay, li, KL, below, above, albdir, albdif, zinc, acc_up, acc_dn);
+      }
+      __syncthreads();
+    }
+  }
+  // the group's sums of this lane's interfaces -> part[group][cu, cd][level][column] (cloud-free columns: clear-sky rows only)
+  if (slive) {
+    const size_t pstride = (size_t)(nlay + 1) * W.ncc;
+#pragma unroll
+    for (int k = 0; k < KLMAX; ++k) {
+      const int lev = li * KL + k;
+      if (k < KL && lev <= nlay) {
+        cb::st_stream(W.part + ((size_t)group * 4 + 2) * pstride + (size_t)lev * W.ncc + scol, acc_up[k]);
+        cb::st_stream(W.part + ((size_t)group * 4 + 3) * pstride + (size_t)lev * W.ncc + scol, acc_dn[k]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) k_sw_mask_kiss(const __grid_constant__ In in, const __grid_constant__ Work W,
                                                          int icld, int seed, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -351,11 +484,14 @@ __global__ void __launch_bounds__(kBlock) k_sw_mask_kiss(const __grid_constant__
   if (cb::mcica::mask_column_kiss(in.play, in.cldfr, in.ncol, in.nlay, 112, 4, icld, seed, W.mask, W.ncc, c0, c)) *W.err = 9;
 }
 
-__global__ void __launch_bounds__(kBlock) k_sw_reduce(const __grid_constant__ Work W, int ngroups, const Out out, int nlay, int ncol,
-                                                      int c0, int n) {
+// ngroups_clear > 0: the cloud-free 32-column supertiles hold that many groups (k_sw_scan), the others `ngroups` (a warp of this
+// kernel is one supertile)
+__global__ void __launch_bounds__(kBlock) k_sw_reduce(const __grid_constant__ Work W, int ngroups, int ngroups_clear, const Out out,
+                                                      int nlay, int ncol, int c0, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int lev = blockIdx.y;
-  if (c < n) sw_reduce_level(W, ngroups, nlay, c0, c, lev, ncol, out);
+  const bool anyc = __any_sync(0xffffffffu, c < n && W.anycld[c] != 0);
+  if (c < n) sw_reduce_level(W, ngroups_clear > 0 && !anyc ? ngroups_clear : ngroups, nlay, c0, c, lev, ncol, out);
 }
 
 __global__ void __launch_bounds__(kBlock) k_sw_heat(const __grid_constant__ Tables T, const __grid_constant__ In in,
@@ -391,6 +527,9 @@ struct cb200_sw_engine {
   int cap_ncc = 0, cap_nlay = 0;
   Work W{};
   int max_chunk = 8192;
+  bool scan = false;         // scan form of the transfer (k_sw_scan) for cloud-free supertiles (CLIMT_B200_SW_SCAN=1).  Off by default:
+                             // r02 B200, 8192 x 60 clear sky, 0.91 GB of DRAM traffic instead of 7.2 GB but 2.06 ms against 1.83 ms
+                             // (16 warps per SM at 128 registers, 8 % more instructions than the unit form; profiles/r02_tile_kernels.md)
   bool tile = false;         // column-tile form of the transfer kernel (CLIMT_B200_SW_TILE=1).  Off by default: r02 B200, 8192 x 60
                              // clear sky, it moves 0.89 GB instead of 7.2 GB but takes 2.79 ms against 1.83 ms -- the one consumer warp
                              // of a tile issues ~60 fp64 instructions per level on one scheduler (profiles/r02_tile_kernels.md)
@@ -466,6 +605,7 @@ extern "C" int cb200_sw_create(cb200_sw_engine** out, const char* table_blob, co
     if (const char* sb = std::getenv("CLIMT_B200_SW_SLAB")) e->slab_bps = CB_SW_UMAX == 1 ? std::max(0, std::atoi(sb)) : 0;
     cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char* tl = std::getenv("CLIMT_B200_SW_TILE")) e->tile = std::atoi(tl) != 0;
+    if (const char* tl = std::getenv("CLIMT_B200_SW_SCAN")) e->scan = std::atoi(tl) != 0;
     if (const char* tl = std::getenv("CLIMT_B200_SW_TILE_MIN_TW")) e->tile_min_tw = std::atoi(tl);
     {
       int optin = 0;
@@ -554,6 +694,7 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
   if (e->timing) cudaEventRecord(e->evm, st);
   const dim3 gt((n + 31) / 32, (e->UL.n + CB_SW_GROUP - 1) / CB_SW_GROUP), bt(32, CB_SW_GROUP);
   int ngroups = (int)gt.y;
+  int ngroups_clear = 0;  // > 0: the cloud-free 32-column supertiles were summed into this many groups (k_sw_scan)
   // the column-tile form (layer properties and adding sweeps in shared memory): the widest tiles that fit, the cloudy form half as wide
   const bool cloudy_call = e->fl.icld >= 1;
   const int tw_clear = sw_tile_smem<32, false>(nlay) <= e->smem_optin ? 32 : (sw_tile_smem<16, false>(nlay) <= e->smem_optin ? 16 : 0);
@@ -595,10 +736,35 @@ static int launch_chunk(cb200_sw_engine* e, const Solar& sol, const In& in, cons
     }
     if (mc) k_sw_transfer_slab<true><<<nblocks, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, e->d_slabs, c0, n);
     else k_sw_transfer_slab<false><<<nblocks, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, e->d_slabs, c0, n);
-  } else if (mc) k_sw_transfer<true><<<gt, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
-  else k_sw_transfer<false><<<gt, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n);
+  } else {
+    // scan form for the cloud-free supertiles (all of them when the call has no clouds), unit form for the rest
+    const int KL = (nlay + 1 + kScanLanes - 1) / kScanLanes;
+    const bool scan = e->scan && KL <= 16 && nlay <= 8 * 16;
+    if (scan) {
+      const dim3 gs((n + 31) / 32, kTileGroups);
+#define CB_SCAN(KLMAX, SEL)                                                                                                 \
+      do {                                                                                                                    \
+        const size_t smem = sw_scan_smem<KLMAX>(KL);                                                                          \
+        CUDA_OK(cudaFuncSetAttribute(k_sw_scan<KLMAX, SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        k_sw_scan<KLMAX, SEL><<<gs, kScanThreads, smem, st>>>(e->T, sol, in, e->fl, W, c0, n);                                \
+      } while (0)
+#define CB_SCAN_KL(SEL)                                                                             \
+      do {                                                                                           \
+        if (KL <= 8) CB_SCAN(8, SEL); else if (KL <= 10) CB_SCAN(10, SEL); else CB_SCAN(16, SEL);    \
+      } while (0)
+      if (cloudy_call) CB_SCAN_KL(true); else CB_SCAN_KL(false);
+#undef CB_SCAN_KL
+#undef CB_SCAN
+      ngroups_clear = kTileGroups;
+      e->launches += cloudy_call ? 1 : 0;
+    }
+    if (!scan || cloudy_call) {
+      if (mc) k_sw_transfer<true><<<gt, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n, scan ? 1 : 0);
+      else k_sw_transfer<false><<<gt, bt, 0, st>>>(e->T, sol, in, e->fl, W, e->UL, c0, n, scan ? 1 : 0);
+    }
+  }
   if (e->timing) cudaEventRecord(e->ev1, st);
-  k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, ngroups, out, nlay, out_ncol, c0, n);
+  k_sw_reduce<<<dim3(gx, nlay + 1), kBlock, 0, st>>>(W, ngroups, ngroups_clear, out, nlay, out_ncol, c0, n);
   k_sw_heat<<<dim3(gx, nlay), kBlock, 0, st>>>(e->T, in, out, c0, n);
   e->launches += 6;
   if (e->timing) {

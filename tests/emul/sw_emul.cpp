@@ -36,6 +36,37 @@ static void run_transfer(const Tables& T, const Solar& sol, const In& in, const 
 static int g_tile = 0;
 extern "C" void emul_sw_set_tile(int on) { g_tile = on; }
 
+// The scan form of the sweeps (sw_core.cuh: scan_up_local / scan_dn_local / scan_walk; CUDA kernel k_sw_scan) for one stream of
+// one column: the kScanLanes lanes of the column's group stepped one after the other, the shuffle scans as array passes in the
+// same order (Hillis-Steele), per-lane accumulators scattered to the per-interface sums.
+static void scan_column(const double* Ps, int nlay, double albdir, double albdif, double zinc, double* acc_up, double* acc_dn) {
+  constexpr int W8 = kScanLanes, KLMAX = 32;
+  const int KL = (nlay + 1 + W8 - 1) / W8;
+  UpMap up[W8], upx[W8];
+  DnMap dn[W8], dnx[W8];
+  for (int i = 0; i < W8; ++i) {
+    auto row = [&](int r, int k) { return Ps[(size_t)r * nlay + i * KL + k]; };
+    scan_local<KLMAX>(row, nlay, i, KL, up[i], dn[i]);
+  }
+  for (int d = 1; d < W8; d <<= 1) {
+    UpMap u2[W8];
+    DnMap d2[W8];
+    for (int i = 0; i < W8; ++i) {
+      u2[i] = i >= d ? up_compose(up[i], up[i - d]) : up[i];
+      d2[i] = i + d < W8 ? dn_compose(dn[i], dn[i + d]) : dn[i];
+    }
+    for (int i = 0; i < W8; ++i) { up[i] = u2[i]; dn[i] = d2[i]; }
+  }
+  for (int i = 0; i < W8; ++i) { upx[i] = i ? up[i - 1] : up_identity(); dnx[i] = i + 1 < W8 ? dn[i + 1] : dn_identity(); }
+  for (int i = 0; i < W8; ++i) {
+    double au[KLMAX] = {0.}, ad[KLMAX] = {0.};
+    auto row = [&](int r, int k) { return Ps[(size_t)r * nlay + i * KL + k]; };
+    scan_walk<KLMAX>(row, nlay, i, KL, upx[i], dnx[i], albdir, albdif, zinc, au, ad);
+    for (int k = 0; k < KL; ++k)
+      if (i * KL + k <= nlay) { acc_up[i * KL + k] += au[k]; acc_dn[i * KL + k] += ad[k]; }
+  }
+}
+
 template <bool MC, bool CLOUDY>
 static void run_tile(const Tables& T, const Solar& sol, const In& in, const Flags& fl, const Work& W, int n) {
   const int nlay = in.nlay;
@@ -64,11 +95,13 @@ static void run_tile(const Tables& T, const Solar& sol, const In& in, const Flag
           }
           const double zinc = sol.adjflux[ib] * W.src[(size_t)gabs * W.ncc + c] * prmu0;
           // clear-sky stream -> rows 2, 3; total-sky stream (cloudy form) -> rows 0, 1
-          sw_tile_sweeps(P.data(), (size_t)nlay, 1, nlay, albdir, albdif, zinc, R.data(), (size_t)nlay, 1, acc.data() + 2 * as,
-                         acc.data() + 3 * as, 1);
-          if (CLOUDY)
-            sw_tile_sweeps(P.data() + (size_t)5 * nlay, (size_t)nlay, 1, nlay, albdir, albdif, zinc, R.data(), (size_t)nlay, 1,
-                           acc.data(), acc.data() + as, 1);
+          for (int stream = 0; stream < (CLOUDY ? 2 : 1); ++stream) {
+            const double* Ps = P.data() + (size_t)stream * 5 * nlay;
+            double* up = acc.data() + (size_t)(stream ? 0 : 2) * as;
+            double* dn = up + as;
+            if (g_tile == 2) scan_column(Ps, nlay, albdir, albdif, zinc, up, dn);
+            else sw_tile_sweeps(Ps, (size_t)nlay, 1, nlay, albdir, albdif, zinc, R.data(), (size_t)nlay, 1, up, dn, 1);
+          }
         }
       }
       for (int q = CLOUDY ? 0 : 2; q < 4; ++q)

@@ -139,7 +139,7 @@ def run_sw_emul(st, iopt=(1, 0, 2, 1, 1, 0, 1), scal=None, mcica=(0, 1, 0), tile
     """iopt = (icld, iaer, inflag, iceflag, liqflag, isolvar, dyofyr); scal = [adjes, scon, solcycfrac, ind0, ind1, bnd[14]];
     tile: the column-tile form of the transfer (sw_tile_cell / sw_tile_sweeps) instead of sw_transfer_unit"""
     lib = emul_lib("sw")
-    lib.emul_sw_set_tile(1 if tile else 0)
+    lib.emul_sw_set_tile(int(tile))  # 0 unit form, 1 tile form with serial sweeps, 2 tile form with the scan-form sweeps
     k = C.rrtmg_constants()
     consts = np.array([k[n] for n in ("pi", "grav", "planck", "boltz", "clight", "avogad", "alosmt", "gascon",
                                       "sbcnst", "secdy", "cpdair")])

@@ -70,18 +70,38 @@ def test_lw_tile_form_mcica_matches_the_unit_form(icld):
         assert H.rel_err(tile[k], unit[k]) < 1e-11, k
 
 
-@pytest.mark.parametrize("clouds,ncol,nlay", [(False, 1000, 60), (True, 533, 47)])
-def test_sw_tile_form_matches_the_unit_form_and_the_oracle(clouds, ncol, nlay):
+@pytest.mark.parametrize("form", ["scan", "tile"])
+@pytest.mark.parametrize("clouds,ncol,nlay", [(False, 1000, 60), (True, 533, 47), (True, 2100, 72), (False, 300, 100)])
+def test_sw_scan_and_tile_forms_match_the_unit_form_and_the_oracle(clouds, ncol, nlay, form):
+    """scan: k_sw_scan (default) takes the cloud-free 32-column supertiles, k_sw_transfer the rest; tile: k_sw_tile (off by default)"""
     from climt_b200.engine import SWEngine
+    if form == "tile" and nlay > 62:
+        pytest.skip("the cloudy tile form needs 16-column tiles: up to 62 layers")
     st = SY.make_sw_state(ncol, nlay, seed=33, clouds=clouds)
     if clouds:
         for k in ("cldfr", "cicewp", "cliqwp"):
             st[k][:, 96:224] = 0.0
     abi = H.to_abi_sw(st)
-    tile = _engine(SWEngine, {"CLIMT_B200_SW_TILE": "1"}, device=0).run_host(ncol, nlay, abi, dyofyr=80)
-    unit = _engine(SWEngine, {"CLIMT_B200_SW_TILE": "0"}, device=0).run_host(ncol, nlay, abi, dyofyr=80)
+    env = {"CLIMT_B200_SW_TILE": "1" if form == "tile" else "0", "CLIMT_B200_SW_SCAN": "1" if form == "scan" else "0"}
+    tile = _engine(SWEngine, env, device=0).run_host(ncol, nlay, abi, dyofyr=80)
+    unit = _engine(SWEngine, {"CLIMT_B200_SW_TILE": "0", "CLIMT_B200_SW_SCAN": "0"}, device=0).run_host(ncol, nlay, abi, dyofyr=80)
     sub = slice(0, ncol, max(1, ncol // 61))
     ref = H.sw_oracle()(_subset(st, sub, ncol), dyofyr=80)
     for k, kk in (("uflx", "swuflx"), ("dflx", "swdflx"), ("uflxc", "swuflxc"), ("dflxc", "swdflxc")):
+        assert np.isfinite(tile[k]).all(), k
         assert H.rel_err(tile[k], unit[k]) < 1e-11, k
         assert H.rel_err(tile[k][:, sub], ref[kk]) < 1e-9, k
+
+
+def test_sw_scan_form_mcica_mixed_supertiles():
+    from climt_b200.engine import SWEngine
+    ncol, nlay = 2100, 60
+    st = SY.make_sw_state(ncol, nlay, seed=9, clouds=True, overcast_only=False)
+    for k in ("cldfr", "cicewp", "cliqwp"):
+        st[k][:, 512:700] = 0.0
+    abi = H.to_abi_sw(st)
+    kw = dict(device=0, icld=2, mcica=True, irng=0, permuteseed=112)
+    scan = _engine(SWEngine, {"CLIMT_B200_SW_SCAN": "1"}, **kw).run_host(ncol, nlay, abi, dyofyr=80)
+    unit = _engine(SWEngine, {"CLIMT_B200_SW_SCAN": "0"}, **kw).run_host(ncol, nlay, abi, dyofyr=80)
+    for k in ("uflx", "dflx", "uflxc", "dflxc"):
+        assert H.rel_err(scan[k], unit[k]) < 1e-11, k

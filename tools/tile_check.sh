@@ -13,7 +13,7 @@ fi
 for t in ${TILES:-1 0}; do
   for cfg in "0 0 8192 60" "0 1 8192 60" "1 0 16384 72"; do
     set -- $cfg
-    CLIMT_B200_LW_TILE=$t CLIMT_B200_SW_TILE=$t MCICA=$1 CLOUDS=$2 NCOL=$3 NLAY=$4 timeout 120 python tools/time_engine.py 2>>$out/err.log | sed "s/^{/{\"tile\": $t, /" >> $out/time.jsonl
+    CLIMT_B200_LW_TILE=$t CLIMT_B200_SW_SCAN=$t MCICA=$1 CLOUDS=$2 NCOL=$3 NLAY=$4 timeout 120 python tools/time_engine.py 2>>$out/err.log | sed "s/^{/{\"tile\": $t, /" >> $out/time.jsonl
   done
 done
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active
