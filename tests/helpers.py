@@ -103,6 +103,27 @@ def rel_err(got, ref, floor=1e-3):
     return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), floor)))
 
 
+def _build_shared(so, src, deps, flags):
+    """Compile src -> so when it is older than a dependency.  Several pytest-xdist workers may want the same library at once:
+    the build is serialised by a file lock, written to a temporary name and moved into place, so nobody ever loads a half-written
+    file."""
+    import fcntl
+
+    def stale():
+        return not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps)
+    if stale():
+        with open(so + ".lock", "w") as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            try:
+                if stale():
+                    tmp = f"{so}.{os.getpid()}.tmp"
+                    subprocess.check_call(["g++"] + flags + ["-shared", "-o", tmp, src])
+                    os.replace(tmp, so)
+            finally:
+                fcntl.flock(lk, fcntl.LOCK_UN)
+    return ctypes.CDLL(so)
+
+
 # ---- host emulation of the kernel code (tests/emul/lw_emul.cpp) ---------------------------------
 def emul_lib(which="lw"):
     so = os.path.join(HERE, "emul", "libcb_emul.so" if which == "lw" else "libcb_emul_sw.so")
@@ -110,9 +131,7 @@ def emul_lib(which="lw"):
     deps = [src] + [os.path.join(HERE, "..", "climt_b200", "csrc", f)
                     for f in ("lw_core.cuh", "lw_tables.h", "cb_common.h", "sw_core.cuh", "sw_tables.h", "mcica_core.cuh",
                               "mcica_host.h")]
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
-    return ctypes.CDLL(so)
+    return _build_shared(so, src, deps, ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off"])
 
 
 def run_lw_emul(st, flags=(1, 0, 2, 1, 1), mcica=(0, 1, 0), tile=False):
@@ -172,9 +191,7 @@ def cork_emul_lib():
     src = os.path.join(HERE, "emul", "cork_emul.cpp")
     deps = [src] + [os.path.join(HERE, "..", "climt_b200", "csrc", f) for f in ("cork_core.cuh", "cork_tables.h", "cb_common.h")]
     deps.append(os.path.join(HERE, "..", "include", "climt_b200.h"))
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
-    return ctypes.CDLL(so)
+    return _build_shared(so, src, deps, ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off"])
 
 
 def cork_arrays(s, which):
@@ -328,9 +345,7 @@ def emanuel_emul_lib():
     src = os.path.join(HERE, "emul", "emanuel_emul.cpp")
     deps = [src, os.path.join(HERE, "..", "climt_b200", "csrc", "emanuel_core.cuh"), os.path.join(HERE, "..", "climt_b200", "csrc", "cb_common.h"),
             os.path.join(HERE, "..", "include", "climt_b200.h")]
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
-    return ctypes.CDLL(so)
+    return _build_shared(so, src, deps, ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off"])
 
 
 def run_emanuel_emul(params, arrays, dt, qs_mode, max_conv_lev=None, layout=1):
@@ -387,9 +402,7 @@ def host_pipe_emul_lib():
     so = os.path.join(HERE, "emul", "libcb_emul_hostpipe.so")
     src = os.path.join(HERE, "emul", "host_pipe_emul.cpp")
     deps = [src, os.path.join(HERE, "..", "climt_b200", "csrc", "engine_common.h")]
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-pthread", "-shared", "-o", so, src])
-    return ctypes.CDLL(so)
+    return _build_shared(so, src, deps, ["-O2", "-std=c++17", "-fPIC", "-pthread"])
 
 
 def simple_physics_emul_lib():
@@ -397,9 +410,7 @@ def simple_physics_emul_lib():
     so = os.path.join(HERE, "emul", "libcb_emul_simple_physics.so")
     src = os.path.join(HERE, "emul", "simple_physics_emul.cpp")
     deps = [src] + [os.path.join(HERE, "..", "climt_b200", "csrc", f) for f in ("simple_physics_core.cuh", "cb_common.h")]
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
-    return ctypes.CDLL(so)
+    return _build_shared(so, src, deps, ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off"])
 
 
 def run_simple_physics_emul(state, dtime, params, order=0):
