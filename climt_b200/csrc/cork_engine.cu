@@ -229,7 +229,7 @@ std::string read_ktable_file(const char* path, KTableFile& f) {
     return std::string("cork: ") + path + " is not a CB2KTB01 table container";
   int64_t n = 0;
   std::memcpy(&n, f.raw.data() + 8, 8);
-  if (n < 0 || 16 + (size_t)n * sizeof(FileEntry) > f.raw.size()) return std::string("cork: truncated header in ") + path;
+  if (n < 0 || (uint64_t)n > (f.raw.size() - 16) / sizeof(FileEntry)) return std::string("cork: truncated header in ") + path;
   f.entries.resize((size_t)n);
   std::memcpy(f.entries.data(), f.raw.data() + 16, (size_t)n * sizeof(FileEntry));
   for (auto& e : f.entries) {
@@ -246,10 +246,16 @@ std::string read_ktable_file(const char* path, KTableFile& f) {
 extern "C" int cb200_cork_create_from_file(cb200_cork_engine** out, const char* path, double g, double cpd, double sigma, int device) {
   *out = nullptr;
   KTableFile f;
-  const std::string bad = read_ktable_file(path, f);
+  std::string bad;
+  try {  // (nothing may unwind through the C ABI: a hostile size field ends here as an error string)
+    bad = read_ktable_file(path, f);
+  } catch (const std::exception& ex) {
+    bad = std::string("cork: cannot read ") + path + ": " + ex.what();
+  }
   if (!bad.empty()) { cb::set_global_error(bad); return -1; }
   if (f.i32("_overlap_additive", 1) == 0) {
-    cb::set_global_error("cork: ESFT-overlap k-tables are not supported by the CUDA engine (additive overlap only)");
+    cb::set_global_error("cork: this container holds an ESFT-overlap table; the engine evaluates those as additive tables on the "
+                         "combined g-points -- expand it first (climt_b200.cork.expand_esft_table, then cb200_cork_create)");
     return -1;
   }
   const FileEntry* k = f.find("k_coefficients");

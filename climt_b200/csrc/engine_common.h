@@ -1,5 +1,7 @@
 // climt_b200 -- bits shared by the engine translation units (host only).
 #pragma once
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <atomic>
@@ -108,6 +110,25 @@ class WorkerPool {
   std::atomic<int> next_{0};
   bool stop_ = false;
 };
+
+// Where the reference-named init symbols find their table blob (see lw_engine.cu / sw_engine.cu: default_blob)
+inline std::string find_table_blob(const char* env_name, const char* file, void* symbol_in_this_library) {
+  if (const char* p = std::getenv(env_name)) return p;
+  auto readable = [](const std::string& f) { FILE* fp = std::fopen(f.c_str(), "rb"); if (fp) std::fclose(fp); return fp != nullptr; };
+  if (const char* c = std::getenv("CLIMT_B200_CACHE")) {
+    const std::string f = std::string(c) + "/" + file;
+    if (readable(f)) return f;
+  }
+  std::string dir = ".";
+  Dl_info info;
+  if (dladdr(symbol_in_this_library, &info) && info.dli_fname) {
+    const std::string so = info.dli_fname;
+    const size_t k = so.find_last_of('/');
+    if (k != std::string::npos) dir = so.substr(0, k);
+  }
+  const std::string cached = dir + "/data/_cache/" + file, shipped = dir + "/data/" + file;
+  return readable(cached) ? cached : shipped;
+}
 
 // One array of a host-pointer call as the scan sees it: columns [c0, c0 + n) of a (rows, ncol) array of doubles.
 struct ZeroView {

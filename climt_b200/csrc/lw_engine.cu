@@ -993,17 +993,9 @@ namespace {
 double g_consts[11] = {0};
 cb200_lw_engine* g_engine = nullptr;
 
-std::string default_blob() {
-  if (const char* p = std::getenv("CLIMT_B200_LW_TABLES")) return p;
-  Dl_info info;
-  if (dladdr((void*)&cb200_lw_create, &info) && info.dli_fname) {
-    std::string so = info.dli_fname;
-    size_t k = so.find_last_of('/');
-    std::string dir = k == std::string::npos ? "." : so.substr(0, k);
-    return dir + "/data/_cache/rrtmg_lw_reduced.blob";
-  }
-  return "rrtmg_lw_reduced.blob";
-}
+// The reduced-table blob of the reference-named init symbol: $CLIMT_B200_LW_TABLES, else $CLIMT_B200_CACHE/<name>, else the copy
+// the Python side regenerates next to the library (data/_cache), else the one shipped with the package (data/).
+std::string default_blob() { return cb::find_table_blob("CLIMT_B200_LW_TABLES", "rrtmg_lw_reduced.blob", (void*)&cb200_lw_create); }
 }  // namespace
 
 extern "C" void rrtmg_set_constants(double* pi, double* grav, double* planck, double* boltz, double* clight,

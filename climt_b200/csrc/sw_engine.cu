@@ -1042,17 +1042,7 @@ extern "C" void cb200_sw_last_transfer_bytes(cb200_sw_engine* e, double* h2d, do
 namespace {
 double g_consts[11] = {0};
 cb200_sw_engine* g_engine = nullptr;
-std::string default_blob() {
-  if (const char* p = std::getenv("CLIMT_B200_SW_TABLES")) return p;
-  Dl_info info;
-  if (dladdr((void*)&cb200_sw_create, &info) && info.dli_fname) {
-    std::string so = info.dli_fname;
-    size_t k = so.find_last_of('/');
-    std::string dir = k == std::string::npos ? "." : so.substr(0, k);
-    return dir + "/data/_cache/rrtmg_sw_reduced.blob";
-  }
-  return "rrtmg_sw_reduced.blob";
-}
+std::string default_blob() { return cb::find_table_blob("CLIMT_B200_SW_TABLES", "rrtmg_sw_reduced.blob", (void*)&cb200_sw_create); }
 }  // namespace
 
 extern "C" void rrtmg_sw_set_constants(double* pi, double* grav, double* planck, double* boltz, double* clight,

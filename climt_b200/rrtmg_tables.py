@@ -191,24 +191,37 @@ def reduce_sw(raw=None):
     return out
 
 
+def _blob_path(name, src_name, reduce_fn, rebuild):
+    """The reduced tables as the engine's blob.  Derived data: regenerated when older than the raw tables or this file, into
+    $CLIMT_B200_CACHE if set, else `data/_cache` next to the package; when neither can be written (a read-only install) the copy
+    shipped under `data/` is used as it is (its digest is pinned by data/MANIFEST.json).  The library's reference-named init
+    symbols search the same places (csrc/engine_common.h: find_table_blob)."""
+    src = os.path.join(_t.DATA_DIR, src_name)
+    newest = max(os.path.getmtime(src), os.path.getmtime(os.path.abspath(__file__)))
+    shipped = os.path.join(_t.DATA_DIR, name)
+    for cache in ([os.environ["CLIMT_B200_CACHE"]] if os.environ.get("CLIMT_B200_CACHE") else []) + [os.path.join(_t.DATA_DIR, "_cache")]:
+        path = os.path.join(cache, name)
+        if not rebuild and os.path.exists(path) and os.path.getmtime(path) >= newest:
+            return path
+        try:
+            os.makedirs(cache, exist_ok=True)
+            tmp = f"{path}.{os.getpid()}.tmp"
+            _t.write_blob(reduce_fn(), tmp, order="C")
+            os.replace(tmp, path)
+            return path
+        except OSError:
+            continue
+    if os.path.exists(shipped):
+        return shipped
+    raise OSError(f"cannot write {name} (set CLIMT_B200_CACHE to a writable directory)")
+
+
 def sw_blob_path(rebuild=False):
-    path = os.path.join(_t.DATA_DIR, "_cache", "rrtmg_sw_reduced.blob")
-    src = os.path.join(_t.DATA_DIR, "rrtmg_sw_raw.npz")
-    if rebuild or not os.path.exists(path) or os.path.getmtime(path) < max(
-            os.path.getmtime(src), os.path.getmtime(os.path.abspath(__file__))):
-        os.makedirs(os.path.dirname(path), exist_ok=True)
-        _t.write_blob(reduce_sw(), path, order="C")
-    return path
+    return _blob_path("rrtmg_sw_reduced.blob", "rrtmg_sw_raw.npz", reduce_sw, rebuild)
 
 
 def lw_blob_path(rebuild=False):
-    path = os.path.join(_t.DATA_DIR, "_cache", "rrtmg_lw_reduced.blob")
-    src = os.path.join(_t.DATA_DIR, "rrtmg_lw_raw.npz")
-    if rebuild or not os.path.exists(path) or os.path.getmtime(path) < max(
-            os.path.getmtime(src), os.path.getmtime(os.path.abspath(__file__))):
-        os.makedirs(os.path.dirname(path), exist_ok=True)
-        _t.write_blob(reduce_lw(), path, order="C")
-    return path
+    return _blob_path("rrtmg_lw_reduced.blob", "rrtmg_lw_raw.npz", reduce_lw, rebuild)
 
 
 if __name__ == "__main__":

@@ -148,3 +148,16 @@ def test_create_from_file_rejects_bad_files(tmp_path):
     open(tmp_path / "trunc.cb2k", "wb").write(raw[: len(raw) // 2])
     assert L.cb200_cork_create_from_file(ctypes.byref(h), str(tmp_path / "trunc.cb2k").encode(), 9.8, 1004.0, 5.67e-8, 0) != 0
     assert b"bad entry" in L.cb200_global_error() or b"truncated" in L.cb200_global_error()
+
+
+def test_shipped_reduced_blobs_are_what_the_reduction_gives(tmp_path, monkeypatch):
+    """The reduced-table blobs shipped under climt_b200/data/ (for binders that never run the Python side: the reference-named
+    init symbols fall back to them) equal a fresh reduction written to a user cache directory (CLIMT_B200_CACHE)."""
+    import os
+    from climt_b200 import rrtmg_tables as RT, tables as TB
+    monkeypatch.setenv("CLIMT_B200_CACHE", str(tmp_path))
+    for which in ("lw", "sw"):
+        fresh = getattr(RT, which + "_blob_path")(rebuild=True)
+        assert os.path.dirname(fresh) == str(tmp_path)
+        shipped = os.path.join(TB.DATA_DIR, f"rrtmg_{which}_reduced.blob")
+        assert open(fresh, "rb").read() == open(shipped, "rb").read()
