@@ -16,7 +16,7 @@ timeout 600 python bench_extra.py --workload cork > $O/bench_cork.log 2>&1; tail
 timeout 600 python bench_extra.py --workload gmd > $O/bench_gmd.log 2>&1; tail -1 $O/bench_gmd.log
 timeout 200 python tools/pipe_trace.py > $O/pipe_trace.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_bench.log 2>&1
-for k in k_sw_transfer k_sw_taumol k_units k_lw_taumol; do
+for k in k_sw_transfer k_sw_taumol k_lw_tile k_lw_taumol; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o /tmp/$k -f python tools/time_engine.py > $O/ncu_$k.log 2>&1
   ncu -i /tmp/$k.ncu-rep --page details > $O/${k}_details.txt 2>&1
   ncu -i /tmp/$k.ncu-rep --page raw --csv > $O/${k}_raw.csv 2>&1
