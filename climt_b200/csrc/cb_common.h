@@ -131,6 +131,9 @@ inline double fdiv(double a, double b) { return a / b; }
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// The 128-byte line at p (128-byte aligned) holds scratch that has just been read for the last time: if it is still dirty in the
+// L2 it need not be written back to HBM.  (Its content is undefined afterwards -- the next launch writes it before reading it.)
+__device__ __forceinline__ void discard_l2(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 __device__ __forceinline__ unsigned long long policy_keep() {
   unsigned long long pol;
   asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -153,6 +156,7 @@ __device__ __forceinline__ double ld_policy(const double* p, unsigned long long 
 inline double ld_stream(const double* p) { return *p; }
 inline void st_stream(double* p, double v) { *p = v; }
 inline void prefetch_l2(const void*) {}
+inline void discard_l2(const void*) {}
 inline unsigned long long policy_keep() { return 0; }
 inline unsigned long long policy_drop() { return 0; }
 inline void st_policy(double* p, double v, unsigned long long) { *p = v; }
