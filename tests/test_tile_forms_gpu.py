@@ -37,8 +37,9 @@ def _engine(cls, env, **kw):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("clouds,ncol,nlay", [(False, 1000, 60), (True, 533, 47), (True, 4100, 72)])
+@pytest.mark.parametrize("clouds,ncol,nlay", [(False, 1000, 60), (True, 533, 47), (True, 4100, 72), (True, 300, 100), (False, 200, 150)])
 def test_lw_tile_and_unit_forms_agree_with_the_oracle(clouds, ncol, nlay):
+    """(100 layers: 9 cells per producer thread; 150 layers: the tile form's shared memory does not fit -> the unit form runs)"""
     from climt_b200.engine import LWEngine
     st = SY.make_lw_state(ncol, nlay, seed=31, clouds=clouds, aerosol=True)
     if clouds:  # a band of cloud-free columns: whole 32-column supertiles take the cloud-free form
