@@ -52,7 +52,7 @@ struct UnitList {
 };
 
 #ifndef CB_LW_TAU_MIN_BLOCKS
-#define CB_LW_TAU_MIN_BLOCKS 4
+#define CB_LW_TAU_MIN_BLOCKS 5  // r02 B200 sweep, 8192 x 60 | McICA 16384 x 72: 3 -> 0.824 | 2.053 ms, 4 -> 0.702 | 1.693, 5 -> 0.669 | 1.541, 6 -> 0.671 | 1.540, 8 -> 0.847 | 1.897
 #endif
 #ifndef CB_LW_LAYER_CHUNKS
 #define CB_LW_LAYER_CHUNKS 4  // taumol: layers are independent -> blockIdx.z cuts them into chunks for more threads in flight

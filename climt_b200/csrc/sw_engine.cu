@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kBlock) k_sw_prep(const __grid_constant__ Tabl
 }
 
 #ifndef CB_SW_TAU_MIN_BLOCKS
-#define CB_SW_TAU_MIN_BLOCKS 4
+#define CB_SW_TAU_MIN_BLOCKS 5  // r02 B200 sweep, 8192 x 60 | McICA 16384 x 72: 3 -> 0.401 | 0.971 ms, 4 -> 0.352 | 0.865, 5 -> 0.335 | 0.808, 6 -> 0.338 | 0.827, 8 -> 0.356 | 0.879
 #endif
 #ifndef CB_SW_LAYER_CHUNKS
 #define CB_SW_LAYER_CHUNKS 4  // taumol: layers are independent -> blockIdx.z cuts them into chunks for more threads in flight
