@@ -457,6 +457,10 @@ def main():
                          "lw_taumol_ms": km["lw_taumol"], "sw_taumol_ms": km["sw_taumol"],
                          "traffic_gbs": traffic / (dom_ms * 1e-3) / 1e9,
                          "traffic_over_algorithmic": traffic / (dom_bytes * NCOL),
+                         "lw_transfer": {"kernel": NCU["lw"]["kernel"], "kernel_ms": km["lw_transfer"],
+                                         "achieved": ALG_BYTES_LW * NCOL / (km["lw_transfer"] * 1e-3) / 1e9,
+                                         "traffic": NCU["lw"]["dram_bytes"],
+                                         "traffic_over_algorithmic": NCU["lw"]["dram_bytes"] / (ALG_BYTES_LW * NCOL)},
                          "ncu": NCU,
                          "note": "achieved = algorithmic bytes of the engine call (reference ABI, SURVEY.md 8d) x columns / time of "
                                  "the dominant kernel (CUDA events on its launch stream). `traffic` = DRAM bytes one launch of "
