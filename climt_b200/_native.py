@@ -81,7 +81,7 @@ EXPORTS = ["cb200_lw_zero_scan_state", "mcica_subcol_lw_wrapper", "rrtmg_lw_mcic
            "cb200_cork_create_picket", "cb200_marshal_device", "cb200_lw_last_taumol_kernel_ms", "cb200_sw_last_taumol_kernel_ms", "cb200_lw_run_host_async", "cb200_lw_wait", "cb200_lw_last_transfer_bytes", "cb200_sw_run_host_async", "cb200_sw_wait",
            "cb200_sw_last_transfer_bytes", "cb200_cork_create", "cb200_cork_destroy", "cb200_cork_last_error", "cb200_cork_last_launches", "cb200_cork_enable_timing",
            "cb200_cork_last_unit_kernel_ms", "cb200_cork_lw_run_device", "cb200_cork_sw_run_device", "cb200_cork_lw_run_host",
-           "cb200_cork_sw_run_host", "cb200_cork_set_diagnostics",
+           "cb200_cork_sw_run_host", "cb200_cork_set_diagnostics", "cb200_lw_set_host_marshal", "cb200_sw_set_host_marshal",
            "cb200_gray_lw_run_device", "cb200_gray_lw_run_host", "cb200_sw_create", "cb200_sw_destroy", "cb200_sw_set_options", "cb200_sw_set_mcica", "cb200_sw_set_solar", "cb200_sw_run_device",
            "cb200_sw_run_host", "cb200_sw_check", "cb200_sw_last_error", "cb200_sw_last_launches",
            "cb200_sw_enable_timing", "cb200_sw_last_unit_kernel_ms", "rrtmg_sw_set_constants", "rrtmg_sw_ini_wrapper",

@@ -186,6 +186,10 @@ inline void all_zero_parallel(const ZeroView* view, int nview, bool* zero) {
 // fluxes drain on the D2H stream.  Two input slots and two output slots; events order slot reuse.
 #ifdef __CUDACC__
 namespace cb {
+// marshal.cu: specific humidity -> volume mixing ratio (in place when h2ovmr == q) and ln-p interface temperatures of one chunk
+cudaError_t marshal_launch(int ncol, int nlay, const double* q, const double* t, const double* tsfc, const double* p, const double* p_int,
+                           double* h2ovmr, double* tlev, cudaStream_t st);
+
 struct HostPipe {
   cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
   cudaEvent_t in_done[2] = {nullptr, nullptr}, cmp_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};

@@ -466,6 +466,7 @@ struct cb200_lw_engine {
   size_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the last host-pointer call
   bool skip_zero_inputs = true;         // CLIMT_B200_SKIP_ZERO_INPUTS=0 turns the all-zero scan of the host call off
   cb::ScanGuard scan_guard;             // ... and so does a host on which the scan is slower than the copy it saves
+  int host_marshal = 0;       // host-pointer calls: bit 0 the h2ovmr argument is specific humidity, bit 1 tlev is computed (set_host_marshal)
   bool host_pending = false;
   std::future<int> enqueue;  // the chunk loop of a run_host_async call, running on its own host thread
   int* h_err = nullptr;
@@ -805,6 +806,7 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
   if (!clouds) for (int i = 16; i <= 21; ++i) used[i] = false;
   if (e->fl.inflag != 0) used[17] = false;
   const double* const* hp = reinterpret_cast<const double* const*>(hin);
+  const bool mar_q = (e->host_marshal & 1) != 0, mar_t = (e->host_marshal & 2) != 0;  // the components' marshal arithmetic on the device
   // Inputs the reference ABI always carries but that are all zero in most model states -- the four halocarbons (11..14), the
   // 16-band aerosol optical depth (22; LW `iaer = 10` is hard-wired, rrtmg_lw_rad.nomcica.f90:442) and the cloud fraction (16) --
   // are scanned on the host chunk by chunk (cb::all_zero_parallel) and, when zero, set in HBM by a memset instead of crossing PCIe.
@@ -883,7 +885,9 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
     size_t off = 0;
     for (int i = 0; i < 23; ++i) {
       if (!used[i]) { dp[i] = nullptr; continue; }
-      if (zero[i]) {
+      if (i == 3 && mar_t) {
+        // tlev: computed on the device from this chunk's tlay, tsfc, play, plev (below), nothing crosses PCIe
+      } else if (zero[i]) {
         CUDA_OK(cudaMemsetAsync(P.d_in[s] + off, 0, (size_t)irows[i] * inner[i] * n * sizeof(double), P.s_in));
       } else {
         if (pg_in[i]) CUDA_OK(P.gather_staged(P.d_in[s] + off, P.h_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
@@ -902,6 +906,9 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.in_done[s], 0));
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.out_done[s], 0));
     P.mark(P.s_cmp, k, 2);
+    if (mar_q || mar_t)  // the components' marshal arithmetic (util.py:47-142) on this chunk, before anything reads it
+      CUDA_OK(cb::marshal_launch(n, nlay, din.h2ovmr, din.tlay, din.tsfc, din.play, din.plev, mar_q ? const_cast<double*>(din.h2ovmr) : nullptr,
+                                 mar_t ? const_cast<double*>(din.tlev) : nullptr, P.s_cmp));
     const In in = make_in(n, nlay, &din);
     Out out{dop[0], dop[1], dop[2], dop[3], dop[4], dop[5]};
     out.duflx_dt = dop[6];
@@ -934,6 +941,15 @@ static int lw_host_enqueue(cb200_lw_engine* e, int ncol, int nlay, const cb200_l
 // The asynchronous form returns at once: the chunk loop (zero scans, copies, launches) runs on a host thread of its own, so that a
 // caller that starts the longwave and the shortwave call back to back has both pipelines feeding the GPU from the first chunk on
 // (r01 trace, 8192 x 60: issued from one thread the second engine started 1.2 ms late and finished 1.8 ms after the first).
+// The host-pointer calls can do the components' marshal arithmetic themselves, on the device, chunk by chunk: flags bit 0 -- the
+// h2ovmr argument holds SPECIFIC HUMIDITY (kg/kg) and is converted to a volume mixing ratio (climt/_core/util.py:47-86); bit 1 --
+// tlev is ignored (may be NULL) and computed from tlay, tsfc, play, plev by ln-p interpolation (util.py:89-142).  0 = the plain
+// reference ABI.  (The components spend more host time in those two numpy expressions than the whole call takes on the GPU.)
+extern "C" int cb200_lw_set_host_marshal(cb200_lw_engine* e, int flags) {
+  e->host_marshal = flags & 3;
+  return 0;
+}
+
 extern "C" int cb200_lw_run_host_async(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* hin,
                                        const cb200_lw_outputs* hout) {
   if (e->host_pending) { e->error = "a previous run_host_async call has not been waited for"; return -3; }

@@ -32,6 +32,16 @@ __global__ void __launch_bounds__(128) k_marshal(int ncol, int nlay, const doubl
 }
 }  // namespace
 
+// used by the host-pointer calls of the engines when the caller hands over specific humidity / no interface temperatures
+// (cb200_{lw,sw}_set_host_marshal): the same kernel on one chunk's device buffers
+namespace cb {
+cudaError_t marshal_launch(int ncol, int nlay, const double* q, const double* t, const double* tsfc, const double* p, const double* p_int,
+                           double* h2ovmr, double* tlev, cudaStream_t st) {
+  k_marshal<<<dim3((ncol + 127) / 128, nlay + 1), 128, 0, st>>>(ncol, nlay, q, t, tsfc, p, p_int, nullptr, h2ovmr, tlev, nullptr);
+  return cudaGetLastError();
+}
+}  // namespace cb
+
 extern "C" int cb200_marshal_device(int device, int ncol, int nlay, const double* q, const double* t, const double* tsfc,
                                     const double* p, const double* p_int, const double* zenith, double* h2ovmr, double* tlev,
                                     double* coszen, void* stream) {

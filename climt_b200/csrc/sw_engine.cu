@@ -542,6 +542,7 @@ struct cb200_sw_engine {
   cb::HostPipe pipe;
   size_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the last host-pointer call
   bool skip_zero_inputs = true;         // CLIMT_B200_SKIP_ZERO_INPUTS=0 turns the all-zero scan of the host call off
+  int host_marshal = 0;       // host-pointer calls: bit 0 the h2ovmr argument is specific humidity, bit 1 tlev is computed (set_host_marshal)
   bool host_pending = false;
   std::future<int> enqueue;  // the chunk loop of a run_host_async call, running on its own host thread
   int* h_err = nullptr;
@@ -897,6 +898,7 @@ static int sw_host_enqueue(cb200_sw_engine* e, int ncol, int nlay, double adjes,
   if (e->ensure_work(wchunk, nlay)) return -1;
   CUDA_OK(P.ensure(irow_tot * (size_t)chunk, orow_tot * (size_t)chunk));
   const double* const* hp = reinterpret_cast<const double* const*>(hin);
+  const bool mar_q = (e->host_marshal & 1) != 0, mar_t = (e->host_marshal & 2) != 0;  // the components' marshal arithmetic on the device
   double* const* hop = reinterpret_cast<double* const*>(hout);
   const Solar sol = compute_solar(e->solar, adjes, dyofyr, solcycfrac);
   Work W = e->W;
@@ -945,7 +947,9 @@ static int sw_host_enqueue(cb200_sw_engine* e, int ncol, int nlay, double adjes,
     size_t off = 0;
     for (int i = 0; i < 29; ++i) {
       if (!used[i]) { dp[i] = nullptr; continue; }
-      if (zero[i]) {
+      if (i == 3 && mar_t) {
+        // tlev: computed on the device from this chunk's tlay, tsfc, play, plev (below), nothing crosses PCIe
+      } else if (zero[i]) {
         CUDA_OK(cudaMemsetAsync(P.d_in[s] + off, 0, (size_t)irows[i] * inner[i] * n * sizeof(double), P.s_in));
       } else {
         if (pg_in[i]) CUDA_OK(P.gather_staged(P.d_in[s] + off, P.h_in[s] + off, hp[i], irows[i], ncol, c0, n, inner[i]));
@@ -964,6 +968,9 @@ static int sw_host_enqueue(cb200_sw_engine* e, int ncol, int nlay, double adjes,
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.in_done[s], 0));
     CUDA_OK(cudaStreamWaitEvent(P.s_cmp, P.out_done[s], 0));
     P.mark(P.s_cmp, k, 2);
+    if (mar_q || mar_t)  // the components' marshal arithmetic (util.py:47-142) on this chunk, before anything reads it
+      CUDA_OK(cb::marshal_launch(n, nlay, din.h2ovmr, din.tlay, din.tsfc, din.play, din.plev, mar_q ? const_cast<double*>(din.h2ovmr) : nullptr,
+                                 mar_t ? const_cast<double*>(din.tlev) : nullptr, P.s_cmp));
     const In in = make_in(n, nlay, &din);
     Out out{dout.uflx, dout.dflx, dout.hr, dout.uflxc, dout.dflxc, dout.hrc};
     if (mc && e->irng == 1) W.moff = c0;
@@ -991,6 +998,15 @@ static int sw_host_enqueue(cb200_sw_engine* e, int ncol, int nlay, double adjes,
 }
 
 // The asynchronous form returns at once: the chunk loop runs on a host thread of its own (see cb200_lw_run_host_async).
+// The host-pointer calls can do the components' marshal arithmetic themselves, on the device, chunk by chunk: flags bit 0 -- the
+// h2ovmr argument holds SPECIFIC HUMIDITY (kg/kg) and is converted to a volume mixing ratio (climt/_core/util.py:47-86); bit 1 --
+// tlev is ignored (may be NULL) and computed from tlay, tsfc, play, plev by ln-p interpolation (util.py:89-142).  0 = the plain
+// reference ABI.  (The components spend more host time in those two numpy expressions than the whole call takes on the GPU.)
+extern "C" int cb200_sw_set_host_marshal(cb200_sw_engine* e, int flags) {
+  e->host_marshal = flags & 3;
+  return 0;
+}
+
 extern "C" int cb200_sw_run_host_async(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
                                        const cb200_sw_inputs* hin, const cb200_sw_outputs* hout) {
   if (e->host_pending) { e->error = "a previous run_host_async call has not been waited for"; return -3; }

@@ -41,6 +41,14 @@ def marshal(q, t, tsfc, p, p_int, zenith=None, want_tlev=True):
     return h2o, tlev, cz
 
 
+def host_marshal_on_device():
+    """Host-array calls of the RRTMG components: let the engine do the q -> vmr conversion and the ln-p interface temperatures on
+    the device (cb200_*_set_host_marshal; default) or evaluate the reference's numpy expressions on the host
+    (CLIMT_B200_HOST_MARSHAL=numpy).  The two agree to the last bits of log()."""
+    import os
+    return os.environ.get("CLIMT_B200_HOST_MARSHAL", "device").lower() != "numpy"
+
+
 def finish(engine, asynchronous):
     """Synchronous mode (default): wait for the call and raise the input-validation errors the Fortran turns into `stop`;
     asynchronous mode: return at once, the caller synchronises and calls ``engine.check()`` when it wants to."""

@@ -43,6 +43,14 @@ class LWEngine:
         self.set_mcica(mcica, irng, permuteseed)
         self.set_options(icld, idrv, inflag, iceflag, liqflag)
 
+    def set_host_marshal(self, from_specific_humidity=False, compute_tlev=False):
+        """run_host only: the engine converts specific humidity (handed over as `h2ovmr`) and / or computes `tlev` (may then be
+        None) on the device, chunk by chunk -- the components' numpy marshal arithmetic (cb200_*_set_host_marshal)."""
+        self._host_marshal = (1 if from_specific_humidity else 0) | (2 if compute_tlev else 0)
+        fn = getattr(self._L, "cb200_lw_set_host_marshal" if isinstance(self, LWEngine) else "cb200_sw_set_host_marshal")
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        fn(self._h, self._host_marshal)
+
     def set_mcica(self, enabled, irng=1, permuteseed=0):
         """McICA on/off, RNG (0 kissvec on the device, 1 Mersenne twister on the host for bit parity), seed."""
         self._L.cb200_lw_set_mcica(self._h, 1 if enabled else 0, int(irng), int(permuteseed))
@@ -73,6 +81,8 @@ class LWEngine:
         keep = []
         pin = _native.LwInputs()
         for k in LW_IN:
+            if k == "tlev" and getattr(self, "_host_marshal", 0) & 2:
+                continue  # computed by the engine on the device (set_host_marshal); the pointer stays NULL
             a = np.ascontiguousarray(arrays[k], dtype=np.float64)
             if a.shape != ins[k]:
                 raise ValueError(f"{k}: expected shape {ins[k]}, got {a.shape}")
@@ -208,6 +218,14 @@ class SWEngine:
         bnd = np.ones(14) if bndsolvar is None else np.ascontiguousarray(np.asarray(bndsolvar, dtype=np.float64)[:14])
         self._L.cb200_sw_set_solar(self._h, int(isolvar), float(scon), ind.ctypes.data_as(_dp), bnd.ctypes.data_as(_dp))
 
+    def set_host_marshal(self, from_specific_humidity=False, compute_tlev=False):
+        """run_host only: the engine converts specific humidity (handed over as `h2ovmr`) and / or computes `tlev` (may then be
+        None) on the device, chunk by chunk -- the components' numpy marshal arithmetic (cb200_*_set_host_marshal)."""
+        self._host_marshal = (1 if from_specific_humidity else 0) | (2 if compute_tlev else 0)
+        fn = getattr(self._L, "cb200_lw_set_host_marshal" if isinstance(self, LWEngine) else "cb200_sw_set_host_marshal")
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        fn(self._h, self._host_marshal)
+
     def set_mcica(self, enabled, irng=1, permuteseed=0):
         self._L.cb200_sw_set_mcica(self._h, 1 if enabled else 0, int(irng), int(permuteseed))
 
@@ -230,6 +248,8 @@ class SWEngine:
         keep = []
         pin = _native.SwInputs()
         for k in SW_IN:
+            if k == "tlev" and getattr(self, "_host_marshal", 0) & 2:
+                continue  # computed by the engine on the device (set_host_marshal); the pointer stays NULL
             a = np.ascontiguousarray(arrays[k], dtype=np.float64)
             if a.shape != ins[k]:
                 raise ValueError(f"{k}: expected shape {ins[k]}, got {a.shape}")

@@ -100,13 +100,19 @@ class RRTMGLongwave(TendencyComponent):
         if device_state.is_device_state(state):
             return self._array_call_device(state)
         state = {k: np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v for k, v in state.items()}
-        Q = mass_to_volume_mixing_ratio(state["specific_humidity"], 18.02)
         n_layers, n_columns = state["air_temperature"].shape
-        if self._calc_Tint:
+        on_device = device_state.host_marshal_on_device()
+        # on_device: the engine converts q and interpolates the interface temperatures on the device, chunk by chunk (the two numpy
+        # expressions cost more host time than the whole call takes on the GPU); CLIMT_B200_HOST_MARSHAL=numpy: as the reference
+        Q = state["specific_humidity"] if on_device else mass_to_volume_mixing_ratio(state["specific_humidity"], 18.02)
+        if not self._calc_Tint:
+            T_interface = state["air_temperature_on_interface_levels"]
+        elif on_device:
+            T_interface = None
+        else:
             T_interface = get_interface_values(state["air_temperature"], state["surface_temperature"],
                                                state["air_pressure"], state["air_pressure_on_interface_levels"])
-        else:
-            T_interface = state["air_temperature_on_interface_levels"]
+        self._engine.set_host_marshal(on_device, on_device and self._calc_Tint)
         diagnostics = initialize_numpy_arrays_with_properties(self.diagnostic_properties, state, self.input_properties)
         tendencies = initialize_numpy_arrays_with_properties(self.tendency_properties, state, self.input_properties)
         arrays = {

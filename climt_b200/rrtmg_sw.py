@@ -117,10 +117,17 @@ class RRTMGShortwave(TendencyComponent):
         if device_state.is_device_state(state):
             return self._array_call_device(state)
         st = {k: np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v for k, v in state.items()}
-        Q = mass_to_volume_mixing_ratio(st["specific_humidity"], 18.02)
         assert st["air_pressure"].shape[0] + 1 == st["air_pressure_on_interface_levels"].shape[0]
-        Tint = get_interface_values(st["air_temperature"], st["surface_temperature"], st["air_pressure"],
-                                    st["air_pressure_on_interface_levels"])
+        if device_state.host_marshal_on_device():
+            # the engine converts q and interpolates the interface temperatures on the device, chunk by chunk (the two numpy
+            # expressions cost more host time than the whole call takes on the GPU); CLIMT_B200_HOST_MARSHAL=numpy: as the reference
+            Q, Tint = st["specific_humidity"], None
+            self._engine.set_host_marshal(True, True)
+        else:
+            Q = mass_to_volume_mixing_ratio(st["specific_humidity"], 18.02)
+            Tint = get_interface_values(st["air_temperature"], st["surface_temperature"], st["air_pressure"],
+                                        st["air_pressure_on_interface_levels"])
+            self._engine.set_host_marshal(False, False)
         diagnostics = initialize_numpy_arrays_with_properties(self.diagnostic_properties, st, self.input_properties)
         tendencies = initialize_numpy_arrays_with_properties(self.tendency_properties, st, self.input_properties)
         if self._ignore_day_of_year:

@@ -76,6 +76,11 @@ int cb200_lw_run_host(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inp
 /* The same call split in two: _async returns once every copy and kernel of the call is enqueued (host buffers must stay
  * valid and, to overlap, be page-locked); cb200_lw_wait blocks until the outputs are in the caller's buffers and reports
  * input-validation errors like cb200_lw_check.  Lets a caller overlap the LW and SW engines' pipelines. */
+/* Host-pointer calls only: let the engine do the components' marshal arithmetic on the device, chunk by chunk, instead of numpy on
+ * the host (replaces mass_to_volume_mixing_ratio and get_interface_values, climt/_core/util.py:47-142, as called by
+ * rrtmg/lw/component.py:373-393 and rrtmg/sw/component.py:560-600).  flags bit 0: the h2ovmr argument holds specific humidity
+ * (kg/kg); bit 1: tlev is ignored (may be NULL) and computed from tlay, tsfc, play, plev.  0 (default) = the plain reference ABI. */
+int cb200_lw_set_host_marshal(cb200_lw_engine* e, int flags);
 int cb200_lw_run_host_async(cb200_lw_engine* e, int ncol, int nlay, const cb200_lw_inputs* in, const cb200_lw_outputs* out);
 int cb200_lw_wait(cb200_lw_engine* e);
 /* bytes the last host-pointer call moved over PCIe (arrays the option flags make dead are not transferred) */
@@ -154,6 +159,7 @@ int cb200_sw_run_device(cb200_sw_engine* e, int ncol, int nlay, double adjes, in
                         const cb200_sw_inputs* in, const cb200_sw_outputs* out, void* stream);
 int cb200_sw_run_host(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
                       const cb200_sw_inputs* in, const cb200_sw_outputs* out);
+int cb200_sw_set_host_marshal(cb200_sw_engine* e, int flags); /* as cb200_lw_set_host_marshal */
 int cb200_sw_run_host_async(cb200_sw_engine* e, int ncol, int nlay, double adjes, int dyofyr, double solcycfrac,
                             const cb200_sw_inputs* in, const cb200_sw_outputs* out);
 int cb200_sw_wait(cb200_sw_engine* e);

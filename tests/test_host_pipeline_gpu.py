@@ -156,3 +156,24 @@ def test_all_zero_inputs_do_not_cross_pcie_and_results_are_unchanged(monkeypatch
         np.testing.assert_array_equal(host3[k], dev[k], err_msg=k)
     lw.close()
     sw.close()
+
+
+@pytest.mark.gpu
+def test_device_side_marshal_of_the_host_call_matches_the_numpy_marshal(monkeypatch):
+    """cb200_{lw,sw}_set_host_marshal: q -> vmr and the ln-p interface temperatures evaluated by the engine on the device, chunk by
+    chunk (the components' default), against the reference's numpy expressions on the host (CLIMT_B200_HOST_MARSHAL=numpy)."""
+    from climt_b200 import synthetic as SY
+    from climt_b200.rrtmg_lw import RRTMGLongwave
+    from climt_b200.rrtmg_sw import RRTMGShortwave
+    lw_state, sw_state = SY.component_states(3000, 40, seed=5, clouds=True)
+    out = {}
+    for mode in ("device", "numpy"):
+        monkeypatch.setenv("CLIMT_B200_HOST_MARSHAL", mode)
+        out[mode] = (RRTMGLongwave().array_call(dict(lw_state)), RRTMGShortwave().array_call(dict(sw_state)))
+    for which in (0, 1):
+        for part in (0, 1):
+            a, b = out["device"][which][part], out["numpy"][which][part]
+            assert set(a) == set(b)
+            for k in a:
+                scale = max(float(np.abs(b[k]).max()), 1e-30)
+                assert float(np.abs(a[k] - b[k]).max()) <= 1e-11 * scale, (which, k)
