@@ -15,7 +15,8 @@ from .engine import LWEngine
 from .rrtmg_common import (rrtmg_cloud_ice_props_dict, rrtmg_cloud_liquid_props_dict,
                            rrtmg_cloud_overlap_method_dict, rrtmg_cloud_props_dict, rrtmg_random_number_dict)
 from .state import get_interface_values, mass_to_volume_mixing_ratio
-from .sympl_shim import TendencyComponent, initialize_numpy_arrays_with_properties
+from .rrtmg_common import allocate_outputs
+from .sympl_shim import TendencyComponent
 
 
 def _p(dims, units):
@@ -113,8 +114,8 @@ class RRTMGLongwave(TendencyComponent):
             T_interface = get_interface_values(state["air_temperature"], state["surface_temperature"],
                                                state["air_pressure"], state["air_pressure_on_interface_levels"])
         self._engine.set_host_marshal(on_device, on_device and self._calc_Tint)
-        diagnostics = initialize_numpy_arrays_with_properties(self.diagnostic_properties, state, self.input_properties)
-        tendencies = initialize_numpy_arrays_with_properties(self.tendency_properties, state, self.input_properties)
+        diagnostics = allocate_outputs(self.diagnostic_properties, state, self.input_properties)
+        tendencies = allocate_outputs(self.tendency_properties, state, self.input_properties)
         arrays = {
             "play": state["air_pressure"], "plev": state["air_pressure_on_interface_levels"],
             "tlay": state["air_temperature"], "tlev": T_interface, "tsfc": state["surface_temperature"],

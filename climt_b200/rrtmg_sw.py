@@ -13,7 +13,8 @@ from .engine import SWEngine
 from .rrtmg_common import (rrtmg_aerosol_input_dict, rrtmg_cloud_ice_props_dict, rrtmg_cloud_liquid_props_dict,
                            rrtmg_cloud_overlap_method_dict, rrtmg_cloud_props_dict, rrtmg_random_number_dict)
 from .state import get_interface_values, mass_to_volume_mixing_ratio
-from .sympl_shim import TendencyComponent, initialize_numpy_arrays_with_properties
+from .rrtmg_common import allocate_outputs
+from .sympl_shim import TendencyComponent
 
 
 def _p(dims, units):
@@ -128,8 +129,8 @@ class RRTMGShortwave(TendencyComponent):
             Tint = get_interface_values(st["air_temperature"], st["surface_temperature"], st["air_pressure"],
                                         st["air_pressure_on_interface_levels"])
             self._engine.set_host_marshal(False, False)
-        diagnostics = initialize_numpy_arrays_with_properties(self.diagnostic_properties, st, self.input_properties)
-        tendencies = initialize_numpy_arrays_with_properties(self.tendency_properties, st, self.input_properties)
+        diagnostics = allocate_outputs(self.diagnostic_properties, st, self.input_properties)
+        tendencies = allocate_outputs(self.tendency_properties, st, self.input_properties)
         if self._ignore_day_of_year:
             day_of_year = 0
         else:
